@@ -1,0 +1,44 @@
+// C-ABI glue: error reporting, version, GEMM dispatch (see include/dlsg.h).
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace dlsg {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    cudaGetLastError();
+    return (int)e;
+  }
+  return 0;
+}
+
+int gemm_tc_dispatch(const dlsg_gemm_t* g, cudaStream_t st);
+int gemm_simt_dispatch(const dlsg_gemm_t* g, cudaStream_t st);
+
+}  // namespace dlsg
+
+extern "C" {
+
+int dlsg_version(void) { return 100; }
+int dlsg_sm_arch(void) { return 100; }
+const char* dlsg_last_error(void) { return dlsg::g_err; }
+
+int dlsg_gemm(const dlsg_gemm_t* p, void* stream) {
+  if (!p) { dlsg::set_error("dlsg_gemm: null params"); return -1; }
+  if (p->impl == DLSG_GEMM_TC) return dlsg::gemm_tc_dispatch(p, (cudaStream_t)stream);
+  return dlsg::gemm_simt_dispatch(p, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,372 @@
+// Per-decode-step fused kernels: the AttentionShare core (score / softmax / weighted sum), per-row
+// vocabulary kernels (argmax, log-softmax, masked cross-entropy fwd+bwd) and the beam-search kernels
+// (log-softmax + after-<end> mask + warp-level top-k, candidate merge, state gather, back-track).
+#include "common.cuh"
+
+namespace dlsg {
+
+constexpr int MAXP = 128;   // max nodes per attention (P=5/8 latent nodes, 26/52 frames in the baseline)
+constexpr int MAXK = 16;    // max beam / per-node beam
+
+// ------------------------------------------------------------------------------------------- node attention
+// grid (rows, nh); 128 threads.  logits_p = K_p . q / sqrt(H); alpha = softmax_p; ctx = sum_p alpha_p V_p
+__global__ void __launch_bounds__(128)
+node_attn_fwd_kernel(const dlsg_node_attn_fwd_t p) {
+  __shared__ float lg[MAXP];
+  const int r = blockIdx.x, hd = blockIdx.y;
+  const int node = r / p.rows_per_node;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* q = p.qp + ((int64_t)r * p.nh + hd) * p.H;
+  const float* K = p.Kp + (((int64_t)hd * p.nodes + node) * p.P) * p.H;
+  const float* V = p.Vp + (((int64_t)hd * p.nodes + node) * p.P) * p.H;
+  const float scale = 1.0f / sqrtf((float)p.H);
+  for (int j = w; j < p.P; j += nw) {
+    float s = 0.f;
+    for (int c = lane; c < p.H; c += 32) s = fmaf(K[(int64_t)j * p.H + c], q[c], s);
+    s = warp_sum(s);
+    if (lane == 0) lg[j] = s * scale;
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = 0; j < p.P; ++j) mx = fmaxf(mx, lg[j]);
+  float sum = 0.f;
+  for (int j = 0; j < p.P; ++j) sum += expf(lg[j] - mx);
+  const float inv = 1.f / sum;
+  __syncthreads();
+  for (int j = threadIdx.x; j < p.P; j += blockDim.x) {
+    const float a = expf(lg[j] - mx) * inv;
+    lg[j] = a;
+    if (p.alpha) p.alpha[(int64_t)r * p.ldalpha + hd * p.P + j] = a;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.H; c += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < p.P; ++j) acc = fmaf(lg[j], V[(int64_t)j * p.H + c], acc);
+    st_from_float(p.ctx, p.ctx_dtype, (int64_t)r * p.ldctx + hd * p.H + c, acc);
+  }
+}
+
+// backward of one step (training: one row per node set).  dKp / dVp accumulate across the 26 steps.
+__global__ void __launch_bounds__(128)
+node_attn_bwd_kernel(const dlsg_node_attn_bwd_t p) {
+  __shared__ float da[MAXP];
+  __shared__ float dl[MAXP];
+  const int r = blockIdx.x, hd = blockIdx.y;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* q = p.qp + ((int64_t)r * p.nh + hd) * p.H;
+  const int64_t nb = (((int64_t)hd * p.rows + r) * p.P) * p.H;   // layout (nh, rows, P, H)
+  const float* K = p.Kp + nb;
+  const float* V = p.Vp + nb;
+  const float* dctx = p.dctx + (int64_t)r * p.lddctx + hd * p.H;
+  const float* al = p.alpha + (int64_t)r * p.ldalpha + hd * p.P;
+  const float scale = 1.0f / sqrtf((float)p.H);
+  for (int j = w; j < p.P; j += nw) {
+    float s = 0.f;
+    for (int c = lane; c < p.H; c += 32) s = fmaf(V[(int64_t)j * p.H + c], dctx[c], s);
+    s = warp_sum(s);
+    if (lane == 0) da[j] = s + (p.dalpha_ext ? p.dalpha_ext[(int64_t)r * p.ldalpha + hd * p.P + j] : 0.f);
+  }
+  __syncthreads();
+  float dot = 0.f;
+  for (int j = 0; j < p.P; ++j) dot = fmaf(al[j], da[j], dot);
+  __syncthreads();
+  for (int j = threadIdx.x; j < p.P; j += blockDim.x) dl[j] = al[j] * (da[j] - dot) * scale;
+  __syncthreads();
+  const int64_t dq0 = ((int64_t)r * p.nh + hd) * p.H;
+  for (int c = threadIdx.x; c < p.H; c += blockDim.x) {
+    float acc = 0.f;
+    const float qc = q[c], dc = dctx[c];
+    for (int j = 0; j < p.P; ++j) {
+      acc = fmaf(dl[j], K[(int64_t)j * p.H + c], acc);
+      p.dKp[nb + (int64_t)j * p.H + c] += dl[j] * qc;
+      p.dVp[nb + (int64_t)j * p.H + c] += al[j] * dc;
+    }
+    st_from_float(p.dqp, p.dqp_dtype, dq0 + c, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- vocab rows
+struct ArgMax { float v; int i; };
+__device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {   // max value, lowest index on ties
+  if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+  return a;
+}
+__device__ __forceinline__ ArgMax warp_argmax(ArgMax a) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMax b; b.v = __shfl_xor_sync(0xffffffffu, a.v, o); b.i = __shfl_xor_sync(0xffffffffu, a.i, o);
+    a = better(a, b);
+  }
+  return a;
+}
+
+__global__ void __launch_bounds__(256)
+row_argmax_kernel(const float* __restrict__ logits, int64_t ld, int V, int64_t* __restrict__ ids, int64_t ld_ids) {
+  __shared__ float sv[8]; __shared__ int si[8];
+  const float* x = logits + (int64_t)blockIdx.x * ld;
+  ArgMax a; a.v = -INFINITY; a.i = 0x7fffffff;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) { ArgMax b; b.v = x[c]; b.i = c; a = better(a, b); }
+  a = warp_argmax(a);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { sv[w] = a.v; si[w] = a.i; }
+  __syncthreads();
+  if (w == 0) {
+    ArgMax b; b.v = lane < 8 ? sv[lane] : -INFINITY; b.i = lane < 8 ? si[lane] : 0x7fffffff;
+    b = warp_argmax(b);
+    if (lane == 0) ids[(int64_t)blockIdx.x * ld_ids] = b.i;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+log_softmax_kernel(const float* __restrict__ logits, int64_t ld, int V, float* __restrict__ out, int64_t ldo) {
+  __shared__ float red[32];
+  const float* x = logits + (int64_t)blockIdx.x * ld;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) mx = fmaxf(mx, x[c]);
+  mx = block_max(mx, red);
+  float s = 0.f;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) s += expf(x[c] - mx);
+  s = block_sum(s, red);
+  const float lse = mx + logf(s);
+  for (int c = threadIdx.x; c < V; c += blockDim.x) out[(int64_t)blockIdx.x * ldo + c] = x[c] - lse;
+}
+
+// masked CE: one CTA per (b,t) row.  loss_sum += -log p[target] for t < len[b];
+// dlogits = (softmax - onehot) * inv_count for counted rows, 0 for padded rows.
+__global__ void __launch_bounds__(256)
+ce_masked_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targets, const int32_t* __restrict__ lens,
+                 int L, int V, float* __restrict__ loss_sum, float* __restrict__ dlogits, float inv_count) {
+  __shared__ float red[32];
+  const int row = blockIdx.x, b = row / L, t = row % L;
+  const float* x = logits + (int64_t)row * V;
+  if (t >= lens[b]) {
+    if (dlogits) for (int c = threadIdx.x; c < V; c += blockDim.x) dlogits[(int64_t)row * V + c] = 0.f;
+    return;
+  }
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) mx = fmaxf(mx, x[c]);
+  mx = block_max(mx, red);
+  float s = 0.f;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) s += expf(x[c] - mx);
+  s = block_sum(s, red);
+  const float lse = mx + logf(s);
+  const int tgt = (int)targets[row];
+  if (threadIdx.x == 0) atomicAdd(loss_sum, (lse - x[tgt]) * inv_count);
+  if (dlogits) {
+    for (int c = threadIdx.x; c < V; c += blockDim.x) {
+      float g = expf(x[c] - lse);
+      if (c == tgt) g -= 1.f;
+      dlogits[(int64_t)row * V + c] = g * inv_count;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- beam search
+// Per row: lse over V, then top-k of (x - lse) by value desc / index asc.  Rows whose last token is <end>
+// emit {<end>: 0, then the k-1 lowest other indices at -inf} exactly as topk over the forced one-hot row
+// would on ties... (torch.topk's order among equal -inf entries is unspecified; only the first slot is used
+// downstream with a finite score).
+__device__ __forceinline__ bool kv_before(float v1, int i1, float v2, int i2) {
+  return v1 > v2 || (v1 == v2 && i1 < i2);
+}
+
+template <int KT>
+__device__ __forceinline__ void insert_topk(float (&tv)[KT], int (&ti)[KT], float v, int i) {
+  if (!kv_before(v, i, tv[KT - 1], ti[KT - 1])) return;
+  // fully unrolled insertion (static register indexing): walk up from the tail, shifting worse entries down
+#pragma unroll
+  for (int j = KT - 1; j >= 0; --j) {
+    if (kv_before(v, i, tv[j], ti[j])) {
+      if (j + 1 < KT) { tv[j + 1] = tv[j]; ti[j + 1] = ti[j]; }
+      tv[j] = v; ti[j] = i;
+    }
+  }
+}
+
+template <int KT>
+__global__ void __launch_bounds__(256)
+beam_topk_kernel(const float* __restrict__ logits, int64_t ld, int V, const int64_t* __restrict__ last, int end_index, int k,
+                 float* __restrict__ top_lp, int64_t* __restrict__ top_id, int normalize) {
+  __shared__ float red[32];
+  __shared__ float cv[8 * MAXK];
+  __shared__ int ci[8 * MAXK];
+  const int row = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (last && last[row] == end_index) {
+    // forced <end>: log-prob 0 at end_index, -inf elsewhere
+    if (threadIdx.x < k) {
+      int idx;
+      if (threadIdx.x == 0) idx = end_index;
+      else { idx = threadIdx.x - 1; if (idx >= end_index) idx += 1; }
+      top_lp[(int64_t)row * k + threadIdx.x] = threadIdx.x == 0 ? 0.f : -INFINITY;
+      top_id[(int64_t)row * k + threadIdx.x] = idx;
+    }
+    return;
+  }
+  const float* x = logits + (int64_t)row * ld;
+  float tv[KT]; int ti[KT];
+#pragma unroll
+  for (int j = 0; j < KT; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+    const float v = x[c];
+    mx = fmaxf(mx, v);
+    insert_topk<KT>(tv, ti, v, c);
+  }
+  float lse = 0.f;
+  if (normalize) {
+    mx = block_max(mx, red);
+    float s = 0.f;
+    for (int c = threadIdx.x; c < V; c += blockDim.x) s += expf(x[c] - mx);
+    s = block_sum(s, red);
+    lse = mx + logf(s);
+  }
+  // warp-level merge: k rounds of warp arg-max over the per-lane heads
+  int head = 0;
+  for (int j = 0; j < k; ++j) {
+    ArgMax a; a.v = -INFINITY; a.i = 0x7fffffff;
+    // select via static indexing to keep tv/ti in registers
+#pragma unroll
+    for (int u = 0; u < KT; ++u) if (u == head && u < k) { a.v = tv[u]; a.i = ti[u]; }
+    const ArgMax best = warp_argmax(a);
+    if (a.i == best.i && a.v == best.v && best.i != 0x7fffffff) ++head;
+    if (lane == 0) { cv[w * MAXK + j] = best.v; ci[w * MAXK + j] = best.i; }
+  }
+  __syncthreads();
+  if (w == 0) {
+    const int nwarps = blockDim.x >> 5;
+    int hp = 0;                       // lane l (< nwarps) walks warp l's sorted candidate list
+    for (int j = 0; j < k; ++j) {
+      ArgMax a; a.v = -INFINITY; a.i = 0x7fffffff;
+      if (lane < nwarps && hp < k) { a.v = cv[lane * MAXK + hp]; a.i = ci[lane * MAXK + hp]; }
+      const ArgMax best = warp_argmax(a);
+      if (lane < nwarps && hp < k && a.i == best.i && a.v == best.v && best.i != 0x7fffffff) ++hp;
+      if (lane == 0) {
+        top_lp[(int64_t)row * k + j] = best.v - lse;
+        top_id[(int64_t)row * k + j] = best.i;
+      }
+    }
+  }
+}
+
+// one warp per batch element: top `beam` of beam*k summed candidates (value desc, index asc)
+__global__ void __launch_bounds__(32)
+beam_merge_kernel(const float* __restrict__ top_lp, const int64_t* __restrict__ top_id, const float* __restrict__ last_lp,
+                  int beam, int k, float* __restrict__ new_lp, int64_t* __restrict__ new_cls, int64_t* __restrict__ backptr,
+                  int32_t* __restrict__ all_end, int end_index) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int n = beam * k;
+  // each lane holds up to 8 candidates (n <= 256)
+  float v[8]; int idx[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int c = lane + u * 32;
+    if (c < n) { v[u] = top_lp[(int64_t)b * n + c] + last_lp[(int64_t)b * beam + c / k]; idx[u] = c; }
+    else { v[u] = -INFINITY; idx[u] = 0x7fffffff; }
+  }
+  bool not_end = false;
+  for (int j = 0; j < beam; ++j) {
+    ArgMax a; a.v = -INFINITY; a.i = 0x7fffffff;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { ArgMax c; c.v = v[u]; c.i = idx[u]; if (idx[u] != 0x7fffffff) a = better(a, c); }
+    // -inf candidates must still be selectable (index order) once finite ones are exhausted
+    const ArgMax best = warp_argmax(a);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) if (idx[u] == best.i) { idx[u] = 0x7fffffff; v[u] = -INFINITY; }
+    if (lane == 0) {
+      const int64_t cls = top_id[(int64_t)b * n + best.i];
+      new_lp[(int64_t)b * beam + j] = best.v;
+      new_cls[(int64_t)b * beam + j] = cls;
+      backptr[(int64_t)b * beam + j] = best.i / k;
+      if (cls != end_index) not_end = true;
+    }
+  }
+  if (lane == 0 && not_end && all_end) atomicAnd(all_end, 0);
+}
+
+__global__ void beam_gather_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const int64_t* __restrict__ backptr,
+                                   int beam, int W) {
+  const int row = blockIdx.x;                 // b*beam + j ; W = row length in 32-bit words
+  const int b = row / beam;
+  const int64_t srow = (int64_t)b * beam + backptr[row];
+  for (int c = threadIdx.x; c < W; c += blockDim.x) dst[(int64_t)row * W + c] = src[srow * W + c];
+}
+
+__global__ void beam_backtrack_kernel(const int64_t* __restrict__ preds, const int64_t* __restrict__ backs, int S, int B, int beam,
+                                      int64_t* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B * beam) return;
+  const int b = e / beam;
+  int cur = e % beam;
+  for (int t = S - 1; t >= 0; --t) {
+    out[(int64_t)e * S + t] = preds[((int64_t)t * B + b) * beam + cur];
+    if (t > 0) cur = (int)backs[((int64_t)(t - 1) * B + b) * beam + cur];
+  }
+}
+
+}  // namespace dlsg
+
+using namespace dlsg;
+
+extern "C" {
+
+int dlsg_node_attn_fwd(const dlsg_node_attn_fwd_t* p, void* stream) {
+  DLSG_REQUIRE(p->P >= 1 && p->P <= MAXP, "node_attn: P=%d out of range (1..%d)", p->P, MAXP);
+  DLSG_REQUIRE(p->rows > 0 && p->nh > 0 && p->rows_per_node >= 1, "node_attn: bad shape");
+  node_attn_fwd_kernel<<<dim3(p->rows, p->nh), 128, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch("node_attn_fwd_kernel");
+}
+int dlsg_node_attn_bwd(const dlsg_node_attn_bwd_t* p, void* stream) {
+  DLSG_REQUIRE(p->P >= 1 && p->P <= MAXP, "node_attn_bwd: P=%d out of range (1..%d)", p->P, MAXP);
+  node_attn_bwd_kernel<<<dim3(p->rows, p->nh), 128, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch("node_attn_bwd_kernel");
+}
+int dlsg_row_argmax(const float* logits, int64_t ld, int32_t rows, int32_t V, int64_t* ids, int64_t ld_ids, void* stream) {
+  if (rows <= 0) return 0;
+  row_argmax_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(logits, ld, V, ids, ld_ids);
+  return check_launch("row_argmax_kernel");
+}
+int dlsg_log_softmax(const float* logits, int64_t ld, int32_t rows, int32_t V, float* out, int64_t ldo, void* stream) {
+  if (rows <= 0) return 0;
+  log_softmax_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(logits, ld, V, out, ldo);
+  return check_launch("log_softmax_kernel");
+}
+int dlsg_ce_masked(const float* logits, const int64_t* targets, const int32_t* lens, int32_t B, int32_t L, int32_t V,
+                   float* loss_sum, float* dlogits, float inv_count, void* stream) {
+  if (B * L <= 0) return 0;
+  ce_masked_kernel<<<B * L, 256, 0, (cudaStream_t)stream>>>(logits, targets, lens, L, V, loss_sum, dlogits, inv_count);
+  return check_launch("ce_masked_kernel");
+}
+int dlsg_beam_topk(const float* logits, int64_t ld, int32_t rows, int32_t V, const int64_t* last, int32_t end_index,
+                   int32_t k, float* top_lp, int64_t* top_id, int32_t normalize, void* stream) {
+  DLSG_REQUIRE(k >= 1 && k <= MAXK, "beam_topk: k=%d out of range (1..%d)", k, MAXK);
+  DLSG_REQUIRE(k <= V, "beam_topk: Target vocab size (%d) too small relative to per_node_beam_size (%d)", V, k);
+  if (rows <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (k <= 1) beam_topk_kernel<1><<<rows, 256, 0, st>>>(logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
+  else if (k <= 3) beam_topk_kernel<3><<<rows, 256, 0, st>>>(logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
+  else if (k <= 5) beam_topk_kernel<5><<<rows, 256, 0, st>>>(logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
+  else if (k <= 8) beam_topk_kernel<8><<<rows, 256, 0, st>>>(logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
+  else beam_topk_kernel<16><<<rows, 256, 0, st>>>(logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
+  return check_launch("beam_topk_kernel");
+}
+int dlsg_beam_merge(const float* top_lp, const int64_t* top_id, const float* last_lp, int32_t B, int32_t beam, int32_t k,
+                    float* new_lp, int64_t* new_cls, int64_t* backptr, int32_t* all_end, int32_t end_index, void* stream) {
+  DLSG_REQUIRE(beam * k <= 256 && beam >= 1 && k >= 1, "beam_merge: beam*k=%d > 256", beam * k);
+  if (B <= 0) return 0;
+  beam_merge_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(top_lp, top_id, last_lp, beam, k, new_lp, new_cls, backptr, all_end, end_index);
+  return check_launch("beam_merge_kernel");
+}
+int dlsg_beam_gather(const void* src, void* dst, const int64_t* backptr, int32_t B, int32_t beam, int32_t row_bytes, void* stream) {
+  if (B * beam <= 0) return 0;
+  DLSG_REQUIRE(row_bytes % 4 == 0, "beam_gather: row_bytes must be a multiple of 4");
+  beam_gather_kernel<<<B * beam, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)src, (uint32_t*)dst, backptr, beam, row_bytes / 4);
+  return check_launch("beam_gather_kernel");
+}
+int dlsg_beam_backtrack(const int64_t* preds, const int64_t* backs, int32_t S, int32_t B, int32_t beam, int64_t* out, void* stream) {
+  if (B * beam <= 0 || S <= 0) return 0;
+  beam_backtrack_kernel<<<(B * beam + 127) / 128, 128, 0, (cudaStream_t)stream>>>(preds, backs, S, B, beam, out);
+  return check_launch("beam_backtrack_kernel");
+}
+
+}  // extern "C"

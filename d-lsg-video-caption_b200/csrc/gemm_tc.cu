@@ -1,0 +1,356 @@
+// tcgen05 / TMA / TMEM GEMM for sm_100a:  C(P,Q) = A(P,K) . B(Q,K)^T, bf16 operands, fp32 accumulate.
+//
+// One CTA per 128 x BN output tile (BN in {32,64,128,256}), 6 warps:
+//   warp 0      : TMA producer  (cp.async.bulk.tensor.3d, 128B swizzle, mbarrier complete_tx)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, kind::f16)
+//   warps 2..5  : epilogue - tcgen05.ld 32x32b.x32 from their TMEM lane quarter (warp_id % 4),
+//                 bias / tanh / scale, smem-transposed coalesced stores (or direct transposed stores)
+// smem ring of STAGES x {A 128x64 bf16, B BNx64 bf16}; full/empty mbarriers; tcgen05.commit frees slots.
+// grid = (P tiles, Q tiles, batch*splitk).  Every spin-wait is bounded and traps instead of hanging.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace dlsg {
+
+constexpr int BM = 128;
+constexpr int BK = 64;           // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int TC_THREADS = 192;
+constexpr int EPI_PAD = 33;
+
+struct TcParams {
+  void* D; const float* bias;
+  int64_t ldd, stride_d, stride_split;
+  int P, Q;            // valid extents of the tile axes (rows of A / rows of B)
+  int bias_mode;       // 0 none, 1 per-p, 2 per-q
+  int store_t;         // 0: D[p*ldd+q]   1: D[q*ldd+p]
+  int d_dtype, do_tanh, accum;
+  float alpha;
+  int splitk, kb_total, kb_per_split;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if (++spins > (1u << 26)) __trap();   // deadlock guard: fail loudly, never hang the box
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 version=1)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address  [0,14)
+  d |= (uint64_t)1 << 16;                          // LBO (unused for swizzled K-major) [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                // SBO = 8 rows * 128 B           [32,46)
+  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+
+template <int BN> struct TcCfg {
+  static constexpr int STAGES = (BN >= 128) ? 4 : 6;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_BYTES = 4 * 32 * EPI_PAD * 4;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;  // +1024 alignment slack
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams prm) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* tiles = smem;
+  float* epi = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
+  // bars[0..S) full, bars[S..2S) empty, bars[2S] tmem_full ; then tmem base address slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p0 = blockIdx.x * BM, q0 = blockIdx.y * BN;
+  const int zb = blockIdx.z / prm.splitk, zs = blockIdx.z % prm.splitk;
+  const int kb_begin = zs * prm.kb_per_split;
+  const int kb_end = min(prm.kb_total, kb_begin + prm.kb_per_split);
+  const int nkb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(smem_u32(&bars[s]), 1);
+      mbar_init(smem_u32(&bars[Cfg::STAGES + s]), 1);
+    }
+    mbar_init(smem_u32(&bars[2 * Cfg::STAGES]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(smem_u32(&bars[Cfg::STAGES + s]), ph ^ 1);
+        const uint32_t full = smem_u32(&bars[s]);
+        mbar_expect_tx(full, Cfg::STAGE_BYTES);
+        const uint32_t a_dst = smem_u32(tiles + s * Cfg::STAGE_BYTES);
+        const int kc = (kb_begin + kb) * BK;
+        tma_load_3d(a_dst, &tmA, full, kc, p0, zb);
+        tma_load_3d(a_dst + Cfg::A_BYTES, &tmB, full, kc, q0, zb);
+        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one elected thread) =====
+    if (lane == 0) {
+      // instruction descriptor: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(smem_u32(&bars[s]), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_addr = smem_u32(tiles + s * Cfg::STAGE_BYTES);
+        const uint64_t adesc = make_sw128_desc(a_addr);
+        const uint64_t bdesc = make_sw128_desc(a_addr + Cfg::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // advance 16 bf16 = 32 bytes inside the 128B swizzle row: +2 in the (addr>>4) field
+          umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&bars[Cfg::STAGES + s]));     // frees the smem slot when the MMAs retire
+        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+      }
+      umma_commit(smem_u32(&bars[2 * Cfg::STAGES]));       // accumulator complete -> epilogue
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int g = warp & 3;                                // TMEM lane quarter this warp may access
+    float* st = epi + (warp - 2) * 32 * EPI_PAD;
+    mbar_wait(smem_u32(&bars[2 * Cfg::STAGES]), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int p_row = p0 + g * 32 + lane;                  // this thread's accumulator row
+    uint8_t* Dbase = reinterpret_cast<uint8_t*>(prm.D);
+    const int64_t doff = (int64_t)zb * prm.stride_d + (int64_t)zs * prm.stride_split;
+    const bool add_bias = (prm.bias_mode != 0) && (zs == 0);
+    float bias_p = 0.f;
+    if (add_bias && prm.bias_mode == 1 && p_row < prm.P) bias_p = prm.bias[p_row];
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (q0 + c0 >= prm.Q) break;                         // warp-uniform
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)c0, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * prm.alpha + bias_p;
+      if (prm.store_t) {
+        // element (p,q) -> D[q*ldd + p]: lanes are consecutive p -> coalesced
+        if (p_row < prm.P) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int q = q0 + c0 + j;
+            if (q < prm.Q) {
+              float x = f[j];
+              if (add_bias && prm.bias_mode == 2) x += prm.bias[q];
+              if (prm.do_tanh) x = tanhf(x);
+              const int64_t idx = doff + (int64_t)q * prm.ldd + p_row;
+              if (prm.d_dtype == DLSG_F32) {
+                float* d = reinterpret_cast<float*>(Dbase) + idx;
+                *d = prm.accum ? (*d + x) : x;
+              } else {
+                __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(Dbase) + idx;
+                *d = __float2bfloat16_rn(prm.accum ? (__bfloat162float(*d) + x) : x);
+              }
+            }
+          }
+        }
+      } else {
+        // element (p,q) -> D[p*ldd + q]: transpose through smem so lanes walk q
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st[lane * EPI_PAD + j] = f[j];
+        __syncwarp();
+        const int q = q0 + c0 + lane;
+        float bias_q = 0.f;
+        if (add_bias && prm.bias_mode == 2 && q < prm.Q) bias_q = prm.bias[q];
+        if (q < prm.Q) {
+#pragma unroll 4
+          for (int i = 0; i < 32; ++i) {
+            const int p = p0 + g * 32 + i;
+            if (p >= prm.P) break;
+            float x = st[i * EPI_PAD + lane] + bias_q;
+            if (prm.do_tanh) x = tanhf(x);
+            const int64_t idx = doff + (int64_t)p * prm.ldd + q;
+            if (prm.d_dtype == DLSG_F32) {
+              float* d = reinterpret_cast<float*>(Dbase) + idx;
+              *d = prm.accum ? (*d + x) : x;
+            } else {
+              __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(Dbase) + idx;
+              *d = __float2bfloat16_rn(prm.accum ? (__bfloat162float(*d) + x) : x);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t K, int64_t ld, int64_t batch,
+                    int64_t stride_batch, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  DLSG_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not found");
+  if (batch <= 1 || stride_batch == 0) stride_batch = rows * ld;
+  cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(batch < 1 ? 1 : batch)};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)stride_batch * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  DLSG_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "gemm_tc: operand base not 16-byte aligned");
+  DLSG_REQUIRE((gstr[0] % 16) == 0 && (gstr[1] % 16) == 0, "gemm_tc: ld/stride must be multiples of 8 elements (ld=%lld stride=%lld)",
+               (long long)ld, (long long)stride_batch);
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DLSG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld K=%lld ld=%lld", (int)r, (long long)rows,
+               (long long)K, (long long)ld);
+  return 0;
+}
+
+template <int BN>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& prm, dim3 grid, cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    DLSG_REQUIRE(e == cudaSuccess, "gemm_tc: cudaFuncSetAttribute(%d) failed: %s", Cfg::SMEM, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  gemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, st>>>(ta, tb, prm);
+  return check_launch("gemm_tc_kernel");
+}
+
+int gemm_tc_dispatch(const dlsg_gemm_t* g, cudaStream_t st) {
+  DLSG_REQUIRE(g->a_dtype == DLSG_BF16 && g->b_dtype == DLSG_BF16, "gemm_tc: operands must be bf16");
+  DLSG_REQUIRE(g->sak == 1 && g->sbk == 1, "gemm_tc: K must be the unit-stride axis of A and B");
+  DLSG_REQUIRE(g->M > 0 && g->N > 0 && g->K > 0, "gemm_tc: empty problem");
+  const int batch = g->batch < 1 ? 1 : g->batch;
+  // Put the wide operand on the 128-row UMMA-M side; skinny activations (M<=64) ride the N side ("swap-AB").
+  const bool swap = (g->M <= 64 && g->N > g->M);
+  const void* Ap = swap ? g->B : g->A;
+  const void* Bq = swap ? g->A : g->B;
+  const int P = swap ? g->N : g->M, Q = swap ? g->M : g->N;
+  const int64_t ldp = swap ? g->sbn : g->sam, ldq = swap ? g->sam : g->sbn;
+  const int64_t strp = swap ? g->stride_b : g->stride_a, strq = swap ? g->stride_a : g->stride_b;
+  TcParams prm;
+  prm.D = g->D; prm.bias = g->bias; prm.ldd = g->ldd; prm.stride_d = g->stride_d; prm.stride_split = g->stride_split;
+  prm.P = P; prm.Q = Q;
+  const bool user_t = (g->flags & DLSG_EPI_STORE_T) != 0;
+  prm.store_t = (swap != user_t) ? 1 : 0;
+  prm.bias_mode = 0;
+  if (g->bias && (g->flags & DLSG_EPI_BIAS_N)) prm.bias_mode = swap ? 1 : 2;
+  if (g->bias && (g->flags & DLSG_EPI_BIAS_M)) prm.bias_mode = swap ? 2 : 1;
+  prm.d_dtype = g->d_dtype; prm.do_tanh = (g->flags & DLSG_EPI_TANH) ? 1 : 0; prm.accum = (g->flags & DLSG_EPI_ACCUM) ? 1 : 0;
+  prm.alpha = g->alpha;
+  prm.kb_total = (g->K + BK - 1) / BK;
+  int splitk = g->splitk < 1 ? 1 : g->splitk;
+  if (splitk > prm.kb_total) splitk = prm.kb_total;
+  prm.kb_per_split = (prm.kb_total + splitk - 1) / splitk;
+  splitk = (prm.kb_total + prm.kb_per_split - 1) / prm.kb_per_split;   // no empty splits
+  DLSG_REQUIRE(splitk == (g->splitk < 1 ? 1 : g->splitk), "gemm_tc: splitk=%d does not divide %d k-blocks without empty splits (use %d)",
+               g->splitk, prm.kb_total, splitk);
+  prm.splitk = splitk;
+  DLSG_REQUIRE(!(splitk > 1 && (prm.do_tanh)), "gemm_tc: tanh epilogue is incompatible with split-K");
+
+  const int ptiles = (P + BM - 1) / BM;
+  auto tiles_for = [&](int bn) { return (int64_t)ptiles * ((Q + bn - 1) / bn) * batch * splitk; };
+  int bn;
+  if (Q <= 32) bn = 32;
+  else if (Q <= 64) bn = 64;
+  else if (Q > 128 && tiles_for(256) >= 2 * kNumSM) bn = 256;
+  else if (tiles_for(128) >= kNumSM || Q <= 128) bn = 128;
+  else bn = 64;
+  CUtensorMap ta, tb;
+  if (make_map(&ta, Ap, P, g->K, ldp, batch, strp, BM)) return -1;
+  if (make_map(&tb, Bq, Q, g->K, ldq, batch, strq, bn)) return -1;
+  dim3 grid(ptiles, (Q + bn - 1) / bn, batch * splitk);
+  DLSG_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm_tc: grid too large");
+  switch (bn) {
+    case 32: return launch_tc<32>(ta, tb, prm, grid, st);
+    case 64: return launch_tc<64>(ta, tb, prm, grid, st);
+    case 128: return launch_tc<128>(ta, tb, prm, grid, st);
+    default: return launch_tc<256>(ta, tb, prm, grid, st);
+  }
+}
+
+}  // namespace dlsg

@@ -1,0 +1,596 @@
+// HBM-bound row / pointwise kernels: dtype+layout conversion, the Tanh->LayerNorm family, the LSTM cell,
+// axis softmax, embedding gather/scatter and small elementwise helpers.  One warp owns one row (warp-shuffle
+// statistics, 128-bit / 64-bit vector accesses when the row is aligned), rows are staged once in shared memory.
+#include "common.cuh"
+
+namespace dlsg {
+
+// ------------------------------------------------------------------------------------------- convert2d
+// 32x32 tiles through smem: dst (cast) and optional dstT (transposed cast) in one pass over src.
+__global__ void __launch_bounds__(256)
+convert2d_kernel(const void* __restrict__ src_, int sdt, int64_t lds, void* __restrict__ dst_, int ddt, int64_t ldd,
+                 void* __restrict__ dstT_, int64_t ldt, int64_t rows, int64_t cols, int64_t bs_src, int64_t bs_dst, int64_t bs_dstT) {
+  __shared__ float tile[32][33];
+  const int es = sdt == DLSG_F32 ? 4 : 2, ed = ddt == DLSG_F32 ? 4 : 2;
+  const void* src = reinterpret_cast<const uint8_t*>(src_) + (int64_t)blockIdx.z * bs_src * es;
+  void* dst = dst_ ? reinterpret_cast<uint8_t*>(dst_) + (int64_t)blockIdx.z * bs_dst * ed : nullptr;
+  void* dstT = dstT_ ? reinterpret_cast<uint8_t*>(dstT_) + (int64_t)blockIdx.z * bs_dstT * ed : nullptr;
+  const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = r0 + ty + i * 8, c = c0 + tx;
+    float v = 0.f;
+    if (r < rows && c < cols) {
+      v = ld_as_float(src, sdt, r * lds + c);
+      if (dst) st_from_float(dst, ddt, r * ldd + c, v);
+    }
+    tile[ty + i * 8][tx] = v;
+  }
+  if (!dstT) return;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t c = c0 + ty + i * 8, r = r0 + tx;
+    if (r < rows && c < cols) st_from_float(dstT, ddt, c * ldt + r, tile[tx][ty + i * 8]);
+  }
+}
+
+// flat vectorised cast fp32 -> bf16 (contiguous case): 8 elements / thread, 2x128-bit loads, 1x128-bit store
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_flat(const float4* __restrict__ src, uint4* __restrict__ dst, int64_t n8) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(src + 2 * i), b = __ldg(src + 2 * i + 1);
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+    o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+    dst[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- row access
+struct RowIO {
+  // load 4 consecutive elements starting at element c (c % 4 == 0) of a row
+  __device__ static __forceinline__ float4 ld4(const void* base, int dt, int64_t off) {
+    if (dt == DLSG_F32) return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + off);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x), b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+    return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+  }
+  __device__ static __forceinline__ void st4(void* base, int dt, int64_t off, float4 v) {
+    if (dt == DLSG_F32) { *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off) = v; return; }
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + off) = u;
+  }
+};
+static inline bool vec_ok(const void* p, int dt, int64_t ld, int D) {
+  if (!p) return true;
+  const int es = dt == DLSG_F32 ? 4 : 2;
+  return (D % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) % (4 * es)) == 0);
+}
+
+// ------------------------------------------------------------------------------------------- norm fwd
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+norm_fwd_kernel(const dlsg_norm_fwd_t p) {
+  extern __shared__ float srow[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float* t = srow + (size_t)w * p.D;
+  const int D = p.D;
+  for (int64_t row = (int64_t)blockIdx.x * nw + w; row < p.rows; row += (int64_t)gridDim.x * nw) {
+    float sum = 0.f;
+    if (VEC) {
+      for (int c = lane * 4; c < D; c += 128) {
+        float4 v = RowIO::ld4(p.x, p.x_dtype, row * p.ldx + c);
+        if (p.res) { const float4 r = RowIO::ld4(p.res, p.res_dtype, row * p.ldres + c); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+        if (p.flags & DLSG_NORM_PRE_TANH) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
+        *reinterpret_cast<float4*>(t + c) = v;
+        sum += (v.x + v.y) + (v.z + v.w);
+      }
+    } else {
+      for (int c = lane; c < D; c += 32) {
+        float v = ld_as_float(p.x, p.x_dtype, row * p.ldx + c);
+        if (p.res) v += ld_as_float(p.res, p.res_dtype, row * p.ldres + c);
+        if (p.flags & DLSG_NORM_PRE_TANH) v = tanhf(v);
+        t[c] = v;
+        sum += v;
+      }
+    }
+    const float mean = warp_sum(sum) / (float)D;
+    float sq = 0.f;
+    __syncwarp();
+    for (int c = lane; c < D; c += 32) { const float d = t[c] - mean; sq = fmaf(d, d, sq); }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)D + 1e-5f);
+    if (p.stats && lane == 0) { p.stats[row * 2] = mean; p.stats[row * 2 + 1] = rstd; }
+    if (VEC) {
+      for (int c = lane * 4; c < D; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(t + c);
+        const float4 g = *reinterpret_cast<const float4*>(p.gamma + c), b = *reinterpret_cast<const float4*>(p.beta + c);
+        float4 y;
+        y.x = (v.x - mean) * rstd * g.x + b.x; y.y = (v.y - mean) * rstd * g.y + b.y;
+        y.z = (v.z - mean) * rstd * g.z + b.z; y.w = (v.w - mean) * rstd * g.w + b.w;
+        if (p.flags & DLSG_NORM_POST_TANH) { y.x = tanhf(y.x); y.y = tanhf(y.y); y.z = tanhf(y.z); y.w = tanhf(y.w); }
+        if (p.drop_p > 0.f) {
+          const uint64_t i0 = p.offset + (uint64_t)row * D + c;
+          y.x *= drop_scale(p.drop_p, p.seed, i0); y.y *= drop_scale(p.drop_p, p.seed, i0 + 1);
+          y.z *= drop_scale(p.drop_p, p.seed, i0 + 2); y.w *= drop_scale(p.drop_p, p.seed, i0 + 3);
+        }
+        if (p.y) RowIO::st4(p.y, p.y_dtype, row * p.ldy + c, y);
+        if (p.y2) RowIO::st4(p.y2, p.y2_dtype, row * p.ldy2 + c, y);
+      }
+    } else {
+      for (int c = lane; c < D; c += 32) {
+        float y = (t[c] - mean) * rstd * p.gamma[c] + p.beta[c];
+        if (p.flags & DLSG_NORM_POST_TANH) y = tanhf(y);
+        if (p.drop_p > 0.f) y *= drop_scale(p.drop_p, p.seed, p.offset + (uint64_t)row * D + c);
+        if (p.y) st_from_float(p.y, p.y_dtype, row * p.ldy + c, y);
+        if (p.y2) st_from_float(p.y2, p.y2_dtype, row * p.ldy2 + c, y);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+int norm_fwd_launch(const dlsg_norm_fwd_t* p, cudaStream_t st) {
+  DLSG_REQUIRE(p->rows >= 0 && p->D > 0 && p->D <= 8192, "norm_fwd: bad shape rows=%lld D=%d", (long long)p->rows, p->D);
+  if (p->rows == 0) return 0;
+  const int nw = p->D <= 2048 ? 8 : (p->D <= 4096 ? 4 : 2);
+  const size_t smem = (size_t)nw * p->D * sizeof(float);
+  const bool vec = vec_ok(p->x, p->x_dtype, p->ldx, p->D) && vec_ok(p->res, p->res_dtype, p->ldres, p->D) &&
+                   vec_ok(p->y, p->y_dtype, p->ldy, p->D) && vec_ok(p->y2, p->y2_dtype, p->ldy2, p->D) &&
+                   vec_ok(p->gamma, DLSG_F32, 4, p->D) && vec_ok(p->beta, DLSG_F32, 4, p->D);
+  int64_t blocks = (p->rows + nw - 1) / nw;
+  if (blocks > kNumSM * 16) blocks = kNumSM * 16;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(norm_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    cudaFuncSetAttribute(norm_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    attr = true;
+  }
+  if (vec) norm_fwd_kernel<true><<<(unsigned)blocks, nw * 32, smem, st>>>(*p);
+  else norm_fwd_kernel<false><<<(unsigned)blocks, nw * 32, smem, st>>>(*p);
+  return check_launch("norm_fwd_kernel");
+}
+
+// ------------------------------------------------------------------------------------------- norm bwd
+// Each warp owns rows; t=pre(x+res) and dxhat staged in smem; dgamma/dbeta reduced per CTA in smem, then
+// one global atomicAdd per column per CTA (grid is capped, rows are looped).
+template <bool VEC>
+__global__ void __launch_bounds__(128)
+norm_bwd_kernel(const dlsg_norm_bwd_t p) {
+  extern __shared__ float sm[];
+  const int D = p.D;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float* sdg = sm;                       // D
+  float* sdb = sm + D;                   // D
+  float* t = sm + 2 * (size_t)D + (size_t)w * 2 * D;
+  float* dxh = t + D;
+  const bool want_param = (p.dgamma != nullptr);
+  if (want_param) {
+    for (int c = threadIdx.x; c < D; c += blockDim.x) { sdg[c] = 0.f; sdb[c] = 0.f; }
+  }
+  __syncthreads();
+  for (int64_t row = (int64_t)blockIdx.x * nw + w; row < p.rows; row += (int64_t)gridDim.x * nw) {
+    const float mean = p.stats[row * 2], rstd = p.stats[row * 2 + 1];
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < D; c += 32) {
+      float x = ld_as_float(p.x, p.x_dtype, row * p.ldx + c);
+      if (p.res) x += ld_as_float(p.res, p.res_dtype, row * p.ldres + c);
+      const float tv = (p.flags & DLSG_NORM_PRE_TANH) ? tanhf(x) : x;
+      const float xh = (tv - mean) * rstd;
+      float dy = ld_as_float(p.dy, p.dy_dtype, row * p.lddy + c);
+      if (p.drop_p > 0.f) dy *= drop_scale(p.drop_p, p.seed, p.offset + (uint64_t)row * D + c);
+      const float g = p.gamma[c];
+      if (p.flags & DLSG_NORM_POST_TANH) { const float yt = tanhf(xh * g + p.beta[c]); dy *= (1.f - yt * yt); }
+      if (want_param) { atomicAdd(&sdg[c], dy * xh); atomicAdd(&sdb[c], dy); }
+      const float d = dy * g;
+      t[c] = tv; dxh[c] = d;
+      s1 += d; s2 = fmaf(d, xh, s2);
+    }
+    s1 = warp_sum(s1) / (float)D; s2 = warp_sum(s2) / (float)D;
+    __syncwarp();
+    if (p.dx) {
+      for (int c = lane; c < D; c += 32) {
+        const float tv = t[c], xh = (tv - mean) * rstd;
+        float dx = rstd * (dxh[c] - s1 - xh * s2);
+        if (p.flags & (DLSG_NORM_PRE_TANH | DLSG_NORM_IN_IS_TANH)) dx *= (1.f - tv * tv);
+        const int64_t idx = row * p.lddx + c;
+        if (p.dx_accum) dx += ld_as_float(p.dx, p.dx_dtype, idx);
+        st_from_float(p.dx, p.dx_dtype, idx, dx);
+      }
+    }
+    __syncwarp();
+  }
+  if (want_param) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      atomicAdd(&p.dgamma[c], sdg[c]);
+      atomicAdd(&p.dbeta[c], sdb[c]);
+    }
+  }
+}
+
+int norm_bwd_launch(const dlsg_norm_bwd_t* p, cudaStream_t st) {
+  DLSG_REQUIRE(p->rows >= 0 && p->D > 0 && p->D <= 4096, "norm_bwd: bad shape rows=%lld D=%d", (long long)p->rows, p->D);
+  if (p->rows == 0) return 0;
+  const int nw = 4;
+  const size_t smem = (size_t)(2 + 2 * nw) * p->D * sizeof(float);
+  int64_t blocks = (p->rows + nw - 1) / nw;
+  if (blocks > kNumSM * 4) blocks = kNumSM * 4;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(norm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 10 * 4096 * 4);
+    attr = true;
+  }
+  norm_bwd_kernel<false><<<(unsigned)blocks, nw * 32, smem, st>>>(*p);
+  return check_launch("norm_bwd_kernel");
+}
+
+// ------------------------------------------------------------------------------------------- LSTM cell
+__global__ void __launch_bounds__(256)
+lstm_cell_fwd_kernel(const dlsg_lstm_cell_fwd_t p) {
+  const int64_t n = (int64_t)p.B * p.H;
+  const int H = p.H;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(e / H), h = (int)(e % H);
+    float g[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t gi = (int64_t)b * 4 * H + (int64_t)k * H + h;
+      float v = 0.f;
+      for (int s = 0; s < p.nsplit; ++s) v += p.gates[gi + (int64_t)s * p.stride_split];
+      if (p.row_bias) v += p.row_bias[(int64_t)b * p.ld_row_bias + (int64_t)k * H + h];
+      if (p.bias) v += p.bias[k * H + h];
+      g[k] = v;
+    }
+    const float ig = sigmoidf_(g[0]), fg = sigmoidf_(g[1]), gg = tanhf(g[2]), og = sigmoidf_(g[3]);
+    const float c = fg * (p.c_prev ? p.c_prev[e] : 0.f) + ig * gg;
+    float hval = og * tanhf(c);
+    const int64_t g0 = (int64_t)b * 4 * H + h;
+    p.gates[g0] = ig; p.gates[g0 + H] = fg; p.gates[g0 + 2 * (int64_t)H] = gg; p.gates[g0 + 3 * (int64_t)H] = og;
+    p.c_out[e] = c;
+    if (p.drop_p > 0.f) hval *= drop_scale(p.drop_p, p.seed, p.offset + (uint64_t)e);
+    if (p.h_out) p.h_out[e] = hval;
+    if (p.h2) st_from_float(p.h2, p.h2_dtype, (int64_t)b * p.ldh2 + h, hval);
+    if (p.h3) st_from_float(p.h3, p.h3_dtype, (int64_t)b * p.ldh3 + h, hval);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+lstm_cell_bwd_kernel(const dlsg_lstm_cell_bwd_t p) {
+  const int64_t n = (int64_t)p.B * p.H;
+  const int H = p.H;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(e / H), h = (int)(e % H);
+    const int64_t g0 = (int64_t)b * 4 * H + h;
+    const float ig = p.acts[g0], fg = p.acts[g0 + H], gg = p.acts[g0 + 2 * (int64_t)H], og = p.acts[g0 + 3 * (int64_t)H];
+    float dh = p.dh[(int64_t)b * p.lddh + h];
+    if (p.dh2) dh += p.dh2[(int64_t)b * p.lddh2 + h];
+    if (p.drop_p > 0.f) dh *= drop_scale(p.drop_p, p.seed, p.offset + (uint64_t)e);
+    const float tc = tanhf(p.c_new[e]);
+    float dc = dh * og * (1.f - tc * tc);
+    if (p.dc_next) dc += p.dc_next[e];
+    const float cp = p.c_prev ? p.c_prev[e] : 0.f;
+    float d[4];
+    d[0] = dc * gg * ig * (1.f - ig);
+    d[1] = dc * cp * fg * (1.f - fg);
+    d[2] = dc * ig * (1.f - gg * gg);
+    d[3] = dh * tc * og * (1.f - og);
+    if (p.dc_prev) p.dc_prev[e] = dc * fg;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t col = (int64_t)k * H + h;
+      if (p.dgates) p.dgates[(int64_t)b * 4 * H + col] = d[k];
+      if (p.dgates2) st_from_float(p.dgates2, p.dgates2_dtype, (int64_t)b * p.ld_dgates2 + col, d[k]);
+      if (p.dgatesT) st_from_float(p.dgatesT, p.dgatesT_dtype, col * p.ld_dgatesT + b, d[k]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- axis softmax
+// one warp per (outer, inner) pair, lanes stride over the softmax axis
+__global__ void __launch_bounds__(256)
+softmax_fwd_kernel(const dlsg_softmax_t p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t pairs = p.outer * p.inner;
+  for (int64_t pr = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; pr < pairs; pr += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const int64_t base = (pr / p.inner) * p.so + (pr % p.inner) * p.si;
+    float mx = -INFINITY;
+    for (int64_t j = lane; j < p.n; j += 32) {
+      float v = p.x[base + j * p.sn] * p.scale;
+      if (p.mask_mode == 1 && !(p.mask[base + j * p.sn] > 0.f)) v = -9e15f;
+      mx = fmaxf(mx, v);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int64_t j = lane; j < p.n; j += 32) {
+      float v = p.x[base + j * p.sn] * p.scale;
+      if (p.mask_mode == 1 && !(p.mask[base + j * p.sn] > 0.f)) v = -9e15f;
+      sum += expf(v - mx);
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int64_t j = lane; j < p.n; j += 32) {
+      float v = p.x[base + j * p.sn] * p.scale;
+      if (p.mask_mode == 1 && !(p.mask[base + j * p.sn] > 0.f)) v = -9e15f;
+      float y = expf(v - mx) * inv;
+      if (p.mask_mode == 2 && !(p.mask[base + j * p.sn] > 0.f)) y = 0.f;
+      p.y[base + j * p.sn] = y;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+softmax_bwd_kernel(const dlsg_softmax_t p, const float* __restrict__ dy, float* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t pairs = p.outer * p.inner;
+  for (int64_t pr = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; pr < pairs; pr += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const int64_t base = (pr / p.inner) * p.so + (pr % p.inner) * p.si;
+    float mx = -INFINITY;
+    for (int64_t j = lane; j < p.n; j += 32) {
+      float v = p.x[base + j * p.sn] * p.scale;
+      if (p.mask_mode == 1 && !(p.mask[base + j * p.sn] > 0.f)) v = -9e15f;
+      mx = fmaxf(mx, v);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f, dot = 0.f;
+    for (int64_t j = lane; j < p.n; j += 32) {
+      const int64_t i = base + j * p.sn;
+      float v = p.x[i] * p.scale;
+      if (p.mask_mode == 1 && !(p.mask[i] > 0.f)) v = -9e15f;
+      const float e = expf(v - mx);
+      float g = dy[i];
+      if (p.mask_mode == 2 && !(p.mask[i] > 0.f)) g = 0.f;
+      sum += e; dot = fmaf(e, g, dot);
+    }
+    sum = warp_sum(sum); dot = warp_sum(dot);
+    const float inv = 1.f / sum;
+    dot *= inv;
+    for (int64_t j = lane; j < p.n; j += 32) {
+      const int64_t i = base + j * p.sn;
+      float v = p.x[i] * p.scale;
+      const bool masked_pre = (p.mask_mode == 1 && !(p.mask[i] > 0.f));
+      if (masked_pre) v = -9e15f;
+      const float s = expf(v - mx) * inv;
+      float g = dy[i];
+      if (p.mask_mode == 2 && !(p.mask[i] > 0.f)) g = 0.f;
+      dx[i] = masked_pre ? 0.f : p.scale * s * (g - dot);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- embedding etc.
+__global__ void __launch_bounds__(128)
+embedding_gather_kernel(const float* __restrict__ table, const int64_t* __restrict__ ids, int64_t ld_ids, int rows, int W,
+                        void* out, int odt, int64_t ldo, void* out2, int odt2, int64_t ldo2, float drop_p, uint64_t seed,
+                        uint64_t offset) {
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  const int64_t id = ids[(int64_t)r * ld_ids];
+  for (int c = threadIdx.x; c < W; c += blockDim.x) {
+    float v = table[id * W + c];
+    if (drop_p > 0.f) v *= drop_scale(drop_p, seed, offset + (uint64_t)r * W + c);
+    if (out) st_from_float(out, odt, (int64_t)r * ldo + c, v);
+    if (out2) st_from_float(out2, odt2, (int64_t)r * ldo2 + c, v);
+  }
+}
+__global__ void __launch_bounds__(128)
+embedding_scatter_kernel(float* __restrict__ dtable, const int64_t* __restrict__ ids, int64_t ld_ids, int rows, int W,
+                         const float* __restrict__ dout, int64_t lddo, float drop_p, uint64_t seed, uint64_t offset) {
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  const int64_t id = ids[(int64_t)r * ld_ids];
+  for (int c = threadIdx.x; c < W; c += blockDim.x) {
+    float v = dout[(int64_t)r * lddo + c];
+    if (drop_p > 0.f) v *= drop_scale(drop_p, seed, offset + (uint64_t)r * W + c);
+    atomicAdd(&dtable[id * W + c], v);
+  }
+}
+__global__ void mean_nodes_fwd_kernel(const float* __restrict__ x, int B, int P, int H, float* __restrict__ y, int64_t ldy) {
+  const int64_t n = (int64_t)B * H;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(e / H), h = (int)(e % H);
+    float s = 0.f;
+    for (int q = 0; q < P; ++q) s += x[((int64_t)b * P + q) * H + h];
+    y[(int64_t)b * ldy + h] = s / (float)P;
+  }
+}
+__global__ void mean_nodes_bwd_kernel(const float* __restrict__ dy, int64_t lddy, int B, int P, int H, float* __restrict__ dx) {
+  const int64_t n = (int64_t)B * P * H;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int h = (int)(e % H);
+    const int b = (int)(e / ((int64_t)P * H));
+    dx[e] += dy[(int64_t)b * lddy + h] / (float)P;
+  }
+}
+__global__ void axpby_kernel(const float* __restrict__ x, float a, float* __restrict__ y, float b, int64_t n) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+    y[e] = (b == 0.f) ? a * x[e] : fmaf(a, x[e], b * y[e]);
+}
+__global__ void add_rowbcast_kernel(const float* __restrict__ x, const float* __restrict__ pe, float* __restrict__ y, int64_t batch, int64_t inner,
+                                    float drop_p, uint64_t seed, uint64_t offset) {
+  const int64_t n = batch * inner;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    float v = x[e] + pe[e % inner];
+    if (drop_p > 0.f) v *= drop_scale(drop_p, seed, offset + (uint64_t)e);
+    y[e] = v;
+  }
+}
+// y = x * dropmask (inverted dropout); also its own backward (same mask)
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float drop_p, uint64_t seed, uint64_t offset) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+    y[e] = x[e] * drop_scale(drop_p, seed, offset + (uint64_t)e);
+}
+__global__ void relu_kernel(float* __restrict__ x, int64_t n) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) x[e] = fmaxf(x[e], 0.f);
+}
+__global__ void relu_bwd_kernel(const float* __restrict__ r, const float* __restrict__ dr, float* __restrict__ dx, int64_t n) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) dx[e] = r[e] > 0.f ? dr[e] : 0.f;
+}
+__global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, int64_t n) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) y[e] = a[e] * b[e];
+}
+
+
+// out[c] += sum_r x[r, c]  (bias gradients).  block = 32 columns x 8 row-lanes, rows chunked over grid.y
+__global__ void __launch_bounds__(256)
+colsum_kernel(const void* __restrict__ x, int dt, int64_t ld, int64_t rows, int64_t cols, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + tx;
+  const int64_t rchunk = (rows + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = (int64_t)blockIdx.y * rchunk, r1 = min(rows, r0 + rchunk);
+  float s = 0.f;
+  if (c < cols) for (int64_t r = r0 + ty; r < r1; r += 8) s += ld_as_float(x, dt, r * ld + c);
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    atomicAdd(&out[c], t);
+  }
+}
+
+static inline unsigned ew_blocks(int64_t n, int threads = 256) {
+  int64_t b = (n + threads - 1) / threads;
+  if (b > kNumSM * 8) b = kNumSM * 8;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace dlsg
+
+using namespace dlsg;
+
+extern "C" {
+
+int dlsg_convert2d_batched(const void* src, int sdt, int64_t lds, void* dst, int ddt, int64_t ldd, void* dstT, int64_t ldt,
+                           int64_t rows, int64_t cols, int64_t batch, int64_t bs_src, int64_t bs_dst, int64_t bs_dstT, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows <= 0 || cols <= 0 || batch <= 0) return 0;
+  if (batch == 1 && !dstT && sdt == DLSG_F32 && ddt == DLSG_BF16 && lds == cols && ldd == cols && ((rows * cols) % 8 == 0) &&
+      (reinterpret_cast<uintptr_t>(src) % 16 == 0) && (reinterpret_cast<uintptr_t>(dst) % 16 == 0)) {
+    const int64_t n8 = rows * cols / 8;
+    cast_f32_bf16_flat<<<ew_blocks(n8), 256, 0, st>>>((const float4*)src, (uint4*)dst, n8);
+    return check_launch("cast_f32_bf16_flat");
+  }
+  // rows ride grid.x (2^31 limit), columns grid.y
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)batch);
+  if (grid.y > 65535 || grid.z > 65535) {
+    // split the row range / batches into several launches
+    DLSG_REQUIRE(grid.z <= 65535, "convert2d: batch too large");
+    const int64_t step = 65535LL * 32;
+    for (int64_t r0 = 0; r0 < rows; r0 += step) {
+      const int64_t nr = rows - r0 < step ? rows - r0 : step;
+      const int es = sdt == DLSG_F32 ? 4 : 2, ed = ddt == DLSG_F32 ? 4 : 2;
+      dim3 g2((unsigned)((cols + 31) / 32), (unsigned)((nr + 31) / 32), (unsigned)batch);
+      convert2d_kernel<<<g2, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(src) + r0 * lds * es, sdt, lds,
+                                           dst ? reinterpret_cast<uint8_t*>(dst) + r0 * ldd * ed : nullptr, ddt, ldd,
+                                           dstT ? reinterpret_cast<uint8_t*>(dstT) + r0 * ed : nullptr, ldt, nr, cols, bs_src, bs_dst, bs_dstT);
+    }
+    return check_launch("convert2d_kernel");
+  }
+  convert2d_kernel<<<grid, 256, 0, st>>>(src, sdt, lds, dst, ddt, ldd, dstT, ldt, rows, cols, bs_src, bs_dst, bs_dstT);
+  return check_launch("convert2d_kernel");
+}
+int dlsg_convert2d(const void* src, int sdt, int64_t lds, void* dst, int ddt, int64_t ldd, void* dstT, int64_t ldt,
+                   int64_t rows, int64_t cols, void* stream) {
+  return dlsg_convert2d_batched(src, sdt, lds, dst, ddt, ldd, dstT, ldt, rows, cols, 1, 0, 0, 0, stream);
+}
+
+int dlsg_norm_fwd(const dlsg_norm_fwd_t* p, void* stream) { return norm_fwd_launch(p, (cudaStream_t)stream); }
+int dlsg_norm_bwd(const dlsg_norm_bwd_t* p, void* stream) { return norm_bwd_launch(p, (cudaStream_t)stream); }
+
+int dlsg_lstm_cell_fwd(const dlsg_lstm_cell_fwd_t* p, void* stream) {
+  DLSG_REQUIRE(p->B > 0 && p->H > 0 && p->nsplit >= 1, "lstm_cell_fwd: bad shape");
+  lstm_cell_fwd_kernel<<<ew_blocks((int64_t)p->B * p->H), 256, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch("lstm_cell_fwd_kernel");
+}
+int dlsg_lstm_cell_bwd(const dlsg_lstm_cell_bwd_t* p, void* stream) {
+  DLSG_REQUIRE(p->B > 0 && p->H > 0, "lstm_cell_bwd: bad shape");
+  lstm_cell_bwd_kernel<<<ew_blocks((int64_t)p->B * p->H), 256, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch("lstm_cell_bwd_kernel");
+}
+
+int dlsg_softmax_fwd(const dlsg_softmax_t* p, void* stream) {
+  const int64_t pairs = p->outer * p->inner;
+  if (pairs <= 0 || p->n <= 0) return 0;
+  DLSG_REQUIRE(p->mask_mode == 0 || p->mask != nullptr, "softmax: mask_mode set without mask");
+  softmax_fwd_kernel<<<ew_blocks(pairs * 32), 256, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch("softmax_fwd_kernel");
+}
+int dlsg_softmax_bwd(const dlsg_softmax_t* p, const float* dy, float* dx, void* stream) {
+  const int64_t pairs = p->outer * p->inner;
+  if (pairs <= 0 || p->n <= 0) return 0;
+  DLSG_REQUIRE(p->mask_mode == 0 || p->mask != nullptr, "softmax: mask_mode set without mask");
+  softmax_bwd_kernel<<<ew_blocks(pairs * 32), 256, 0, (cudaStream_t)stream>>>(*p, dy, dx);
+  return check_launch("softmax_bwd_kernel");
+}
+
+int dlsg_embedding_gather(const float* table, const int64_t* ids, int64_t ld_ids, int32_t rows, int32_t W, void* out,
+                          int odt, int64_t ldo, void* out2, int odt2, int64_t ldo2, float drop_p, uint64_t seed,
+                          uint64_t offset, void* stream) {
+  if (rows <= 0) return 0;
+  embedding_gather_kernel<<<rows, 128, 0, (cudaStream_t)stream>>>(table, ids, ld_ids, rows, W, out, odt, ldo, out2, odt2,
+                                                                 ldo2, drop_p, seed, offset);
+  return check_launch("embedding_gather_kernel");
+}
+int dlsg_embedding_scatter_add(float* dtable, const int64_t* ids, int64_t ld_ids, int32_t rows, int32_t W,
+                               const float* dout, int64_t lddo, float drop_p, uint64_t seed, uint64_t offset, void* stream) {
+  if (rows <= 0) return 0;
+  embedding_scatter_kernel<<<rows, 128, 0, (cudaStream_t)stream>>>(dtable, ids, ld_ids, rows, W, dout, lddo, drop_p, seed, offset);
+  return check_launch("embedding_scatter_kernel");
+}
+int dlsg_mean_nodes_fwd(const float* x, int32_t B, int32_t P, int32_t H, float* y, int64_t ldy, void* stream) {
+  mean_nodes_fwd_kernel<<<ew_blocks((int64_t)B * H), 256, 0, (cudaStream_t)stream>>>(x, B, P, H, y, ldy);
+  return check_launch("mean_nodes_fwd_kernel");
+}
+int dlsg_mean_nodes_bwd(const float* dy, int64_t lddy, int32_t B, int32_t P, int32_t H, float* dx, void* stream) {
+  mean_nodes_bwd_kernel<<<ew_blocks((int64_t)B * P * H), 256, 0, (cudaStream_t)stream>>>(dy, lddy, B, P, H, dx);
+  return check_launch("mean_nodes_bwd_kernel");
+}
+int dlsg_axpby(const float* x, float a, float* y, float b, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  axpby_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, a, y, b, n);
+  return check_launch("axpby_kernel");
+}
+int dlsg_add_rowbcast(const float* x, const float* pe, float* y, int64_t batch, int64_t inner, float drop_p, uint64_t seed,
+                      uint64_t offset, void* stream) {
+  if (batch * inner <= 0) return 0;
+  add_rowbcast_kernel<<<ew_blocks(batch * inner), 256, 0, (cudaStream_t)stream>>>(x, pe, y, batch, inner, drop_p, seed, offset);
+  return check_launch("add_rowbcast_kernel");
+}
+int dlsg_dropout(const float* x, float* y, int64_t n, float drop_p, uint64_t seed, uint64_t offset, void* stream) {
+  if (n <= 0) return 0;
+  dropout_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, y, n, drop_p, seed, offset);
+  return check_launch("dropout_kernel");
+}
+int dlsg_relu(float* x, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  relu_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, n);
+  return check_launch("relu_kernel");
+}
+int dlsg_relu_bwd(const float* r, const float* dr, float* dx, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  relu_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(r, dr, dx, n);
+  return check_launch("relu_bwd_kernel");
+}
+
+int dlsg_colsum(const void* x, int dtype, int64_t ld, int64_t rows, int64_t cols, float* out, void* stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  int64_t chunks = (rows + 255) / 256;
+  if (chunks > 64) chunks = 64;
+  colsum_kernel<<<dim3((unsigned)((cols + 31) / 32), (unsigned)chunks), 256, 0, (cudaStream_t)stream>>>(x, dtype, ld, rows, cols, out);
+  return check_launch("colsum_kernel");
+}
+int dlsg_mul(const float* a, const float* b, float* y, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  mul_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(a, b, y, n);
+  return check_launch("mul_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,464 @@
+"""Host orchestration of the D-LSG blocks over the libdlsg kernels: explicit forward AND backward
+for each block (no autograd inside), wrapped by `run_block` into one torch.autograd.Function per
+block so that the reference trainers' autograd / DDP / Adam drive them unchanged.
+
+Blocks (reference file:line they replace):
+  TunBlock            models/layer.py:172-201  EncoderVisualGraphTUN (+ sublayer.py:189-198 LatentPSL),
+                      E encoders share one region-projection GEMM (regions are read once).
+  EncoderVisualBlock  models/layer.py:46-61    Linear -> BiLSTM -> LN -> SelfAttention(PE) -> LN
+  DecoderBlock        models/layer.py:394-447,569-602  26-step two-LSTM decoder with node attention
+"""
+import itertools
+import math
+
+import torch
+
+from . import linalg as la
+from . import ops
+from .linalg import empty, zeros, op, op_empty, op_zeros, mm32
+
+_seed_counter = itertools.count(1)
+
+
+def next_seed():
+    """Per-call dropout seed derived from torch's seed (deterministic under torch.manual_seed)."""
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + next(_seed_counter) * 0xD1B54A32D192ED03) & 0x7FFFFFFFFFFFFFFF
+
+
+def site(p, seed, sid):
+    return (float(p), seed, sid << 32) if p > 0 else None
+
+
+WC = la.WeightCache()
+
+
+class _BlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, block, names, *tensors):
+        t = dict(zip(names, tensors))
+        outs, saved = block.forward(t)
+        ctx.block, ctx.saved, ctx.names = block, saved, names
+        for o in outs:
+            if o.dtype not in (torch.float32,):
+                ctx.mark_non_differentiable(o)
+        return tuple(outs)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *gouts):
+        grads = ctx.block.backward(ctx.saved, gouts)
+        ctx.saved = None
+        return (None, None) + tuple(grads.get(n) for n in ctx.names)
+
+
+def run_block(block, tensors):
+    """tensors: ordered dict name -> tensor (parameters and inputs). Returns tuple of outputs."""
+    names = tuple(tensors.keys())
+    block.need_grad = torch.is_grad_enabled() and any(v.requires_grad for v in tensors.values())
+    return _BlockFn.apply(block, names, *[tensors[n] for n in names])
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# =============================================================================================== TUN
+class TunBlock:
+    """encs: list of dicts {'prefix': str, 'use_embed': bool}.  Tensor names: 'regions', 'visual<e>',
+    '<prefix>obj_embed.weight' ... exactly the module's parameter names (prefix-qualified)."""
+
+    def __init__(self, encs, P, training, baseline=False):
+        self.encs, self.P, self.training, self.baseline = encs, P, training, baseline
+
+    def forward(self, t):
+        be = ops.backend()
+        regions = t['regions']
+        B, T, R, Dr = regions.shape
+        E = len(self.encs)
+        TR, M = T * R, B * T * R
+        sv = {'dims': (B, T, R, Dr), 'enc': []}
+        use_regions = R >= 5
+        need_grad = getattr(self, 'need_grad', True)
+        outs = []
+        if use_regions:
+            R2 = _c(regions).view(M, Dr)
+            if la.precision() == 'bf16':
+                Rb = op_empty((M,), Dr, R2)
+                RbT = op_empty((Dr,), M, R2) if need_grad else None
+                be.convert(R2, dst=Rb, dstT=RbT)
+            else:
+                Rb, RbT = R2, R2.t()
+            H = t[self.encs[0]['prefix'] + 'obj_embed.weight'].shape[0]
+            ws = [t[e['prefix'] + 'obj_embed.weight'] for e in self.encs]
+            bs = [t[e['prefix'] + 'obj_embed.bias'] for e in self.encs]
+
+            def build():
+                Wc = op_empty((E * H,), Dr, R2)
+                bc = empty((E * H,), R2)
+                for i, (w, b) in enumerate(zip(ws, bs)):
+                    be.convert(w.detach(), dst=Wc[i * H:(i + 1) * H])
+                    be.convert(b.detach().view(1, H), dst=bc[i * H:(i + 1) * H].view(1, H))
+                return Wc, bc
+            Wc, bc = WC.packed(('tunW',) + tuple(id(w) for w in ws), ws, la.pver(*ws, *bs), build)
+            Ot = empty((M, E * H), R2, la.opdtype())
+            be.gemm(Rb, Wc, Ot, bias=bc, tanh=True)
+            sv.update(RbT=RbT, Ot=Ot)
+        seed = next_seed()
+        for i, e in enumerate(self.encs):
+            pf = e['prefix']
+            v = _c(t['visual%d' % i])
+            H = t[pf + 'visual_norm.1.weight'].shape[0]
+            v2 = v.view(B * T, v.shape[-1])
+            s = {}
+            if e['use_embed']:
+                w = t[pf + 'visual_embed.weight']
+                Fv = la.mm(v2, WC.get(w), bias=t[pf + 'visual_embed.bias'])
+                s['v2'] = v2
+            else:
+                Fv = v2
+            F = empty((B * T, H), v2)
+            Fop = op_empty((B * T,), H, v2)
+            stF = empty((B * T, 2), v2)
+            be.norm_fwd(Fv, t[pf + 'visual_norm.1.weight'], t[pf + 'visual_norm.1.bias'], y=F, y2=Fop, stats=stF,
+                        pre_tanh=True)
+            s.update(Fv=Fv, F=F, stF=stF)
+            if use_regions:
+                O = empty((M, H), v2, la.opdtype())
+                stO = empty((M, 2), v2)
+                be.norm_fwd(Ot[:, i * H:(i + 1) * H], t[pf + 'obj_norm.1.weight'], t[pf + 'obj_norm.1.bias'], y=O, stats=stO)
+                O3 = O.view(B, TR, H)
+                St = empty((B, T, TR), v2)                      # raw scores, transposed: (frame, object)
+                be.gemm(Fop.view(B, T, H), O3, St)
+                Sm = empty((B, T, TR), v2)
+                scale = 1.0 / math.sqrt(Dr)
+                be.softmax_fwd(St, Sm, dim=2, scale=scale)       # softmax over the T*R objects (layer.py:188 dim=1)
+                OT = op(O3.transpose(1, 2))                      # (B,H,TR) K-major over objects
+                agg = empty((B, T, H), v2)
+                be.gemm(op(Sm), OT, agg)
+                X = empty((B * T, H), v2)
+                stX = empty((B * T, 2), v2)
+                be.norm_fwd(agg.view(B * T, H), t[pf + 'obj_visual_norm.1.weight'], t[pf + 'obj_visual_norm.1.bias'],
+                            y=X, res=F, stats=stX, pre_tanh=True)
+                s.update(O=O, stO=stO, St=St, Sm=Sm, OT=OT, agg=agg, X=X, stX=stX, scale=scale)
+            else:
+                X = F
+                s['X'] = X
+            if self.baseline:
+                outs.append(X.view(B, T, H))
+            else:
+                P = self.P
+                theta = t[pf + 'v2l_layer.theta']
+                G = mm32(X, theta.detach())                     # (B*T,P)
+                Gs = empty((B, T, P), v2)
+                be.softmax_fwd(G.view(B, T, P), Gs, dim=1)       # over the T frames (sublayer.py:192)
+                N = empty((B, P, H), v2)
+                be.gemm(Gs.transpose(1, 2), X.view(B, T, H).transpose(1, 2), N)
+                nodes = empty((B, P, H), v2)
+                stN = empty((B * P, 2), v2)
+                dn = site(0.3 if self.training else 0.0, seed, i)
+                be.norm_fwd(N.view(B * P, H), t[pf + 'v2l_layer.out_norm.1.weight'], t[pf + 'v2l_layer.out_norm.1.bias'],
+                            y=nodes.view(B * P, H), stats=stN, pre_tanh=True, drop=dn)
+                s.update(G=G, Gs=Gs, N=N, stN=stN, dn=dn)
+                outs.append(nodes)
+            sv['enc'].append(s)
+        sv['t'] = t
+        return outs, sv
+
+    def backward(self, sv, gouts):
+        be = ops.backend()
+        t = sv['t']
+        B, T, R, Dr = sv['dims']
+        TR, M = T * R, B * T * R
+        E = len(self.encs)
+        use_regions = R >= 5
+        grads = {}
+        dOpre = None
+        for i, e in enumerate(self.encs):
+            pf, s = e['prefix'], sv['enc'][i]
+            g = gouts[i]
+            X = s['X']
+            H = X.shape[-1]
+
+            def lnp(name):
+                w, b = t[pf + name + '.weight'], t[pf + name + '.bias']
+                dw, db = zeros(w.shape, w), zeros(b.shape, b)
+                grads[pf + name + '.weight'], grads[pf + name + '.bias'] = dw, db
+                return w, b, dw, db
+            if g is None:
+                continue
+            g = _c(g)
+            if self.baseline:
+                dX = g.view(B, T, H)
+            else:
+                P = self.P
+                w, b, dw, db = lnp('v2l_layer.out_norm.1')
+                dN = empty((B * P, H), X)
+                be.norm_bwd(g.view(B * P, H), s['N'].view(B * P, H), w, b, s['stN'], dx=dN, dgamma=dw, dbeta=db,
+                            pre_tanh=True, drop=s['dn'])
+                dN3 = dN.view(B, P, H)
+                dGs = empty((B, T, P), X)
+                be.gemm(X.view(B, T, H), dN3, dGs)
+                dX = empty((B, T, H), X)
+                be.gemm(s['Gs'], dN3.transpose(1, 2), dX)
+                dG = empty((B, T, P), X)
+                be.softmax_bwd(s['G'].view(B, T, P), dGs, dG, dim=1)
+                theta = t[pf + 'v2l_layer.theta'].detach()
+                be.gemm(dG.view(B * T, P), theta.t(), dX.view(B * T, H), accum=True)
+                dth = empty(theta.shape, X)
+                be.gemm(dG.view(B * T, P).t(), X.t(), dth)
+                grads[pf + 'v2l_layer.theta'] = dth
+            if use_regions:
+                w, b, dw, db = lnp('obj_visual_norm.1')
+                dA = empty((B * T, H), X)
+                be.norm_bwd(dX.view(B * T, H), s['agg'].view(B * T, H), w, b, s['stX'], dx=dA, res=s['F'], dgamma=dw,
+                            dbeta=db, pre_tanh=True)
+                dF = empty((B * T, H), X)
+                be.axpby(dA, 1.0, dF, 0.0)
+                O3 = s['O'].view(B, TR, H)
+                dAop = op(dA.view(B, T, H))
+                dSm = empty((B, T, TR), X)
+                be.gemm(dAop, O3, dSm)
+                dSt = empty((B, T, TR), X)
+                be.softmax_bwd(s['St'], dSm, dSt, dim=2, scale=s['scale'])
+                # dO = Sm^T dA + dSt^T F  as one GEMM with K = 2T
+                Ac = op_zeros((B, TR), 2 * T, X)
+                Bc = op_zeros((B, H), 2 * T, X)
+                be.convert(s['Sm'], dstT=Ac[:, :, :T])
+                be.convert(dSt, dstT=Ac[:, :, T:2 * T])
+                be.convert(dA.view(B, T, H), dstT=Bc[:, :, :T])
+                be.convert(s['F'].view(B, T, H), dstT=Bc[:, :, T:2 * T])
+                dO = empty((M, H), X, la.opdtype())
+                be.gemm(Ac, Bc, dO.view(B, TR, H))
+                be.gemm(op(dSt), s['OT'], dF.view(B, T, H), accum=True)
+                if dOpre is None:
+                    dOpre = empty((M, E * H), X, la.opdtype())
+                    if any(g_ is None for g_ in gouts):
+                        dOpre.zero_()
+                w, b, dw, db = lnp('obj_norm.1')
+                be.norm_bwd(dO, sv['Ot'][:, i * H:(i + 1) * H], w, b, s['stO'], dx=dOpre[:, i * H:(i + 1) * H], dgamma=dw,
+                            dbeta=db, in_is_tanh=True)
+            else:
+                dF = dX.view(B * T, H)
+            w, b, dw, db = lnp('visual_norm.1')
+            dFv = empty((B * T, H), X)
+            be.norm_bwd(dF, s['Fv'], w, b, s['stF'], dx=dFv, dgamma=dw, dbeta=db, pre_tanh=True)
+            if e['use_embed']:
+                wv = t[pf + 'visual_embed.weight']
+                grads[pf + 'visual_embed.weight'] = la.mm(dFv.t(), s['v2'].t())
+                dbv = zeros((H,), X)
+                be.colsum(dFv, dbv)
+                grads[pf + 'visual_embed.bias'] = dbv
+            else:
+                grads['visual%d' % i] = dFv.view(B, T, H)
+        if use_regions and dOpre is not None:
+            H = dOpre.shape[1] // E
+            dWc = empty((E * H, Dr), dOpre)
+            be.gemm(op(dOpre.t()), sv['RbT'], dWc)
+            dbc = zeros((E * H,), dOpre)
+            be.colsum(dOpre, dbc)
+            for i, e in enumerate(self.encs):
+                grads[e['prefix'] + 'obj_embed.weight'] = dWc[i * H:(i + 1) * H]
+                grads[e['prefix'] + 'obj_embed.bias'] = dbc[i * H:(i + 1) * H]
+        return grads
+
+
+# =============================================================================================== EncoderVisual
+class EncoderVisualBlock:
+    """layer.py:46-61.  Tensor names: 'frames' + the module's parameter names (prefix-qualified) + 'pe'."""
+
+    def __init__(self, prefix, baseline, p_drop, training):
+        self.pf, self.baseline, self.p, self.training = prefix, baseline, p_drop, training
+
+    @staticmethod
+    def _packs(t, pf):
+        wf, wr = t[pf + 'lstm.weight_ih_l0'], t[pf + 'lstm.weight_ih_l0_reverse']
+        bs = [t[pf + 'lstm.bias_ih_l0'], t[pf + 'lstm.bias_hh_l0'], t[pf + 'lstm.bias_ih_l0_reverse'],
+              t[pf + 'lstm.bias_hh_l0_reverse']]
+        be = ops.backend()
+        H4, H = wf.shape
+
+        def build():
+            Wih = op_empty((2 * H4,), H, wf)
+            be.convert(wf.detach(), dst=Wih[:H4])
+            be.convert(wr.detach(), dst=Wih[H4:])
+            bsum = empty((2 * H4,), wf)
+            be.axpby(bs[0].detach(), 1.0, bsum[:H4], 0.0)
+            be.axpby(bs[1].detach(), 1.0, bsum[:H4], 1.0)
+            be.axpby(bs[2].detach(), 1.0, bsum[H4:], 0.0)
+            be.axpby(bs[3].detach(), 1.0, bsum[H4:], 1.0)
+            return Wih, bsum
+        return WC.packed(('evW', id(wf)), None, la.pver(wf, wr, *bs), build)
+
+    def forward(self, t):
+        be = ops.backend()
+        pf = self.pf
+        frames = _c(t['frames'])
+        B, T, Din = frames.shape
+        H = t[pf + 'linear_embed.weight'].shape[0]
+        H4 = 4 * H
+        training = self.training
+        seed = next_seed()
+        f2 = op(frames.view(B * T, Din))
+        Xe = empty((B * T, H), frames, la.opdtype())
+        be.gemm(f2, WC.get(t[pf + 'linear_embed.weight']), Xe, bias=t[pf + 'linear_embed.bias'])
+        Wih, bsum = self._packs(t, pf)
+        Gin = empty((B, T, 2 * H4), frames)
+        be.gemm(Xe, Wih, Gin.view(B * T, 2 * H4), bias=bsum)
+        lstm_out = empty((B, T, 2 * H), frames)
+        gates = zeros((2, T, B, H4), frames)
+        cs = zeros((2, T + 1, B, H), frames)
+        hprev = op_zeros((2, T, B), H, frames)       # h fed INTO step t (operand dtype)
+        whh = [WC.get(t[pf + 'lstm.weight_hh_l0']), WC.get(t[pf + 'lstm.weight_hh_l0_reverse'])]
+        for d in range(2):
+            order = list(range(T)) if d == 0 else list(range(T - 1, -1, -1))
+            for k, tt in enumerate(order):
+                if k > 0:
+                    be.gemm(hprev[d, tt], whh[d], gates[d, tt])
+                nxt = order[k + 1] if k + 1 < T else None
+                be.lstm_cell_fwd(gates[d, tt], cs[d, k], cs[d, k + 1], row_bias=Gin[:, tt, d * H4:(d + 1) * H4],
+                                 h2=lstm_out[:, tt, d * H:(d + 1) * H], h3=(hprev[d, nxt] if nxt is not None else None))
+        Y = empty((B * T, 2 * H), frames)
+        stY = empty((B * T, 2), frames)
+        dY = site(self.p if training else 0.0, seed, 1)
+        be.norm_fwd(lstm_out.view(B * T, 2 * H), t[pf + 'layernorm_lstm.weight'], t[pf + 'layernorm_lstm.bias'], y=Y,
+                    stats=stY, drop=dY)
+        sv = dict(t=t, dims=(B, T, Din, H), f2=f2, Xe=Xe, gates=gates, cs=cs, hprev=hprev, lstm_out=lstm_out, stY=stY, dY=dY)
+        if self.baseline:
+            out = la.mm(Y, WC.get(t[pf + 'out_try.weight']), bias=t[pf + 'out_try.bias'])
+            sv.update(Y=Y)
+            return [out.view(B, T, H)], sv
+        D2 = 2 * H
+        dpe = site(0.2 if training else 0.0, seed, 2)
+        Ype = empty((B * T, D2), frames)
+        pe = _c(t['pe'].detach()[0, :T])
+        be.add_rowbcast(Y, pe, Ype, drop=dpe)
+        wk, wq, wv = t[pf + 'self_attention.K.weight'], t[pf + 'self_attention.Q.weight'], t[pf + 'self_attention.V.weight']
+
+        def build():
+            W = op_empty((3 * D2,), D2, wk)
+            for j, w in enumerate((wk, wq, wv)):
+                be.convert(w.detach(), dst=W[j * D2:(j + 1) * D2])
+            return W
+        Wkqv = WC.packed(('evKQV', id(wk)), None, la.pver(wk, wq, wv), build)
+        Ypo = op(Ype)
+        KQV = empty((B, T, 3 * D2), frames)
+        be.gemm(Ypo, Wkqv, KQV.view(B * T, 3 * D2))
+        Kt, Qt, Vt = KQV[:, :, :D2], KQV[:, :, D2:2 * D2], KQV[:, :, 2 * D2:]
+        lg = empty((B, T, T), frames)
+        be.gemm(Kt, Qt, lg)
+        Wt = empty((B, T, T), frames)
+        sc = 1.0 / math.sqrt(D2)
+        be.softmax_fwd(lg, Wt, dim=2, scale=sc)
+        att = empty((B, T, D2), frames)
+        be.gemm(Wt, Vt.transpose(1, 2), att)
+        att_op = op(att.view(B * T, D2))
+        Z = la.mm(att_op, WC.get(t[pf + 'self_attention.output_layer.0.weight']))
+        dz = site(self.p if training else 0.0, seed, 3)
+        if dz is not None:
+            be.dropout(Z, Z, dz)
+        out = empty((B, T, H), frames)
+        stZ = empty((B * T, 2), frames)
+        be.norm_fwd(Z, t[pf + 'layernorm_sa.weight'], t[pf + 'layernorm_sa.bias'], y=out.view(B * T, H), stats=stZ)
+        sv.update(dpe=dpe, Ypo=Ypo, KQV=KQV, lg=lg, Wt=Wt, sc=sc, att_op=att_op, Z=Z, dz=dz, stZ=stZ)
+        return [out], sv
+
+    def backward(self, sv, gouts):
+        be = ops.backend()
+        t, pf = sv['t'], self.pf
+        B, T, Din, H = sv['dims']
+        H4 = 4 * H
+        grads = {}
+        g = _c(gouts[0]).view(B * T, H)
+        ref = g
+
+        def lnp(name):
+            w, b = t[pf + name + '.weight'], t[pf + name + '.bias']
+            dw, db = zeros(w.shape, w), zeros(b.shape, b)
+            grads[pf + name + '.weight'], grads[pf + name + '.bias'] = dw, db
+            return w, b, dw, db
+        dYv = empty((B * T, 2 * H), ref)
+        if self.baseline:
+            wo = t[pf + 'out_try.weight']
+            gop = op(g)
+            be.gemm(gop, WC.get(wo, transpose=True), dYv)
+            grads[pf + 'out_try.weight'] = la.mm(g.t(), sv['Y'].t())
+            dbo = zeros((H,), ref)
+            be.colsum(g, dbo)
+            grads[pf + 'out_try.bias'] = dbo
+        else:
+            D2 = 2 * H
+            w, b, dw, db = lnp('layernorm_sa')
+            dZ = empty((B * T, H), ref)
+            be.norm_bwd(g, sv['Z'], w, b, sv['stZ'], dx=dZ, dgamma=dw, dbeta=db)
+            if sv['dz'] is not None:
+                be.dropout(dZ, dZ, sv['dz'])
+            wo = t[pf + 'self_attention.output_layer.0.weight']
+            dZop = op(dZ)
+            datt = empty((B, T, D2), ref)
+            be.gemm(dZop, WC.get(wo, transpose=True), datt.view(B * T, D2))
+            grads[pf + 'self_attention.output_layer.0.weight'] = la.mm(dZop.t(), sv['att_op'].t())
+            KQV = sv['KQV']
+            Kt, Qt, Vt = KQV[:, :, :D2], KQV[:, :, D2:2 * D2], KQV[:, :, 2 * D2:]
+            dKQV = empty((B, T, 3 * D2), ref)
+            dK, dQ, dV = dKQV[:, :, :D2], dKQV[:, :, D2:2 * D2], dKQV[:, :, 2 * D2:]
+            dW = empty((B, T, T), ref)
+            be.gemm(datt, Vt, dW)                                   # dW[i,j] = datt_i . V_j
+            be.gemm(sv['Wt'].transpose(1, 2), datt.transpose(1, 2), dV)   # dV_j = sum_i W[i,j] datt_i
+            dlg = empty((B, T, T), ref)
+            be.softmax_bwd(sv['lg'], dW, dlg, dim=2, scale=sv['sc'])
+            be.gemm(dlg, Qt.transpose(1, 2), dK)                    # dK_i = sum_j dlg[i,j] Q_j
+            be.gemm(dlg.transpose(1, 2), Kt.transpose(1, 2), dQ)    # dQ_j = sum_i dlg[i,j] K_i
+            dKQVop = op(dKQV.view(B * T, 3 * D2))
+            wk, wq, wv = t[pf + 'self_attention.K.weight'], t[pf + 'self_attention.Q.weight'], t[pf + 'self_attention.V.weight']
+            dYpe = empty((B * T, D2), ref)
+            for j, w_ in enumerate((wk, wq, wv)):
+                be.gemm(dKQVop[:, j * D2:(j + 1) * D2], WC.get(w_, transpose=True), dYpe, accum=(j > 0))
+            dWkqv = la.mm(dKQVop.t(), sv['Ypo'].t())                # (3*D2, D2)
+            for j, n in enumerate(('K', 'Q', 'V')):
+                grads[pf + 'self_attention.%s.weight' % n] = dWkqv[j * D2:(j + 1) * D2]
+            if sv['dpe'] is not None:
+                be.dropout(dYpe, dYpe, sv['dpe'])
+            dYv = dYpe
+        w, b, dw, db = lnp('layernorm_lstm')
+        dL = empty((B, T, 2 * H), ref)
+        be.norm_bwd(dYv, sv['lstm_out'].view(B * T, 2 * H), w, b, sv['stY'], dx=dL.view(B * T, 2 * H), dgamma=dw, dbeta=db,
+                    drop=sv['dY'])
+        # BiLSTM BPTT
+        dGin = empty((B, T, 2 * H4), ref, la.opdtype())
+        gates, cs, hprev = sv['gates'], sv['cs'], sv['hprev']
+        whhT = [WC.get(t[pf + 'lstm.weight_hh_l0'], transpose=True), WC.get(t[pf + 'lstm.weight_hh_l0_reverse'], transpose=True)]
+        names_hh = ['lstm.weight_hh_l0', 'lstm.weight_hh_l0_reverse']
+        for d in range(2):
+            order = list(range(T)) if d == 0 else list(range(T - 1, -1, -1))
+            dgT = op_empty((H4,), T * B, ref)
+            dhrec = zeros((B, H), ref)
+            dc = zeros((B, H), ref)
+            dc2 = empty((B, H), ref)
+            for k in range(T - 1, -1, -1):
+                tt = order[k]
+                dg2 = dGin[:, tt, d * H4:(d + 1) * H4]
+                be.lstm_cell_bwd(gates[d, tt], cs[d, k], cs[d, k + 1], dL[:, tt, d * H:(d + 1) * H], dc, dc2,
+                                 dgates2=dg2, dgatesT=dgT[:, tt * B:(tt + 1) * B], dh2=dhrec)
+                dc, dc2 = dc2, dc
+                if k > 0:
+                    be.gemm(op(dg2), whhT[d], dhrec)
+            hp = hprev[d]
+            grads[pf + names_hh[d]] = la.mm(dgT, hp.as_strided((T * B, H), (hp.stride(1), 1)).t())
+        Wih, _ = self._packs(t, pf)
+        dGin2 = dGin.view(B * T, 2 * H4)
+        dbg = zeros((2 * H4,), ref)
+        be.colsum(dGin2, dbg)
+        grads[pf + 'lstm.bias_ih_l0'] = dbg[:H4]
+        grads[pf + 'lstm.bias_hh_l0'] = dbg[:H4]
+        grads[pf + 'lstm.bias_ih_l0_reverse'] = dbg[H4:]
+        grads[pf + 'lstm.bias_hh_l0_reverse'] = dbg[H4:]
+        dWih = la.mm(dGin2.t(), sv['Xe'].t())
+        grads[pf + 'lstm.weight_ih_l0'] = dWih[:H4]
+        grads[pf + 'lstm.weight_ih_l0_reverse'] = dWih[H4:]
+        dXe = empty((B * T, H), ref, la.opdtype())
+        be.gemm(op(dGin2), op(Wih.t()), dXe)
+        grads[pf + 'linear_embed.weight'] = la.mm(dXe.t(), sv['f2'].t())
+        dbl = zeros((H,), ref)
+        be.colsum(dXe, dbl)
+        grads[pf + 'linear_embed.bias'] = dbl
+        return grads

@@ -1,0 +1,148 @@
+"""Precision policy + GEMM-operand plumbing shared by every block.
+
+precision 'bf16' (default): dense projections run on the tcgen05 kernel with bf16 operands and fp32
+accumulation; operands must be K-major (unit stride on the reduction axis), 16-byte aligned, row
+pitch a multiple of 8 elements.  `op()` materialises such a copy (dlsg_convert2d, cast and/or
+transpose) only when a tensor is not already usable.
+precision 'fp32': every product runs on the strided fp32 FFMA kernel on the original tensors
+(strict-parity mode: logits within 1e-4 of the fp32 reference, bit-exact token ids).
+Tiny fp32 x fp32 products (26x26 attention, P<=8 pooling) use the FFMA kernel in both modes.
+"""
+import os
+
+import torch
+
+from . import ops
+
+_PRECISION = os.environ.get('DLSG_PRECISION', 'bf16')
+
+
+def set_precision(p):
+    global _PRECISION
+    assert p in ('bf16', 'fp32')
+    _PRECISION = p
+
+
+def precision():
+    return _PRECISION
+
+
+def opdtype():
+    return torch.bfloat16 if _PRECISION == 'bf16' else torch.float32
+
+
+def ceil8(n):
+    return (n + 7) // 8 * 8
+
+
+def empty(shape, like, dtype=torch.float32):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+def zeros(shape, like, dtype=torch.float32):
+    return torch.zeros(shape, dtype=dtype, device=like.device)
+
+
+def op_empty(rows_shape, K, like):
+    """Operand buffer (..., K) in the operand dtype with an aligned row pitch; returns the [..., :K] view."""
+    buf = torch.empty(tuple(rows_shape) + (ceil8(K),), dtype=opdtype(), device=like.device)
+    return buf[..., :K]
+
+
+def op_zeros(rows_shape, K, like):
+    buf = torch.zeros(tuple(rows_shape) + (ceil8(K),), dtype=opdtype(), device=like.device)
+    return buf[..., :K]
+
+
+def _tc_ok(t):
+    if t.dtype != torch.bfloat16 or t.stride(-1) != 1:
+        return False
+    if t.data_ptr() % 16 != 0:
+        return False
+    for d in range(t.dim() - 1):
+        if t.shape[d] > 1 and t.stride(d) % 8 != 0:
+            return False
+    return True
+
+
+def op(t):
+    """Return `t` (2-D or batched 3-D, reduction axis last) as a GEMM operand for the current precision."""
+    if _PRECISION == 'fp32':
+        if t.dtype == torch.float32:
+            return t
+        out = torch.empty(t.shape, dtype=torch.float32, device=t.device)
+        _convert_into(t, out)
+        return out
+    if _tc_ok(t):
+        return t
+    out = op_empty(t.shape[:-1], t.shape[-1], t)
+    _convert_into(t, out)
+    return out
+
+
+def _convert_into(t, out):
+    be = ops.backend()
+    if t.stride(-1) == 1 or t.shape[-1] == 1:
+        be.convert(t, dst=out)
+    else:
+        assert t.stride(-2) == 1, 'operand needs a unit stride on one of its last two axes'
+        be.convert(t.transpose(-1, -2), dstT=out)
+
+
+def mm(a, b, out=None, out_dtype=torch.float32, **epi):
+    """out = epi(a @ b^T); a (..,M,K), b (..,N,K).  Operands are made precision-appropriate via op()."""
+    a2, b2 = op(a), op(b)
+    if out is None:
+        out = torch.empty(a.shape[:-1] + (b.shape[-2],), dtype=out_dtype, device=a.device)
+    ops.backend().gemm(a2, b2, out, **epi)
+    return out
+
+
+def mm32(a, b, out=None, **epi):
+    """Small fp32 product on the strided FFMA kernel regardless of precision mode."""
+    if out is None:
+        out = torch.empty(a.shape[:-1] + (b.shape[-2],), dtype=torch.float32, device=a.device)
+    ops.backend().gemm(a, b, out, **epi)
+    return out
+
+
+class WeightCache:
+    """bf16 K-major copies of parameters (and their transposes), refreshed when the parameter changes
+    (tensor._version bumps on every in-place optimizer update)."""
+
+    def __init__(self):
+        self._c = {}
+
+    def get(self, w, transpose=False, key=None):
+        if _PRECISION == 'fp32':
+            return w.detach().t() if transpose else w.detach()
+        k = (id(w) if key is None else key, transpose)
+        ver = (w._version, w.data_ptr(), tuple(w.shape))
+        hit = self._c.get(k)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        src = w.detach()
+        out = op_empty((src.shape[1],), src.shape[0], src) if transpose else op_empty((src.shape[0],), src.shape[1], src)
+        if transpose:
+            ops.backend().convert(src, dstT=out)
+        else:
+            ops.backend().convert(src, dst=out)
+        self._c[k] = (ver, out)
+        return out
+
+    def packed(self, key, parts, versions, builder):
+        """Cache an arbitrary packed operand (e.g. concatenated LSTM weights) keyed on part versions."""
+        ver = (_PRECISION,) + tuple(versions)
+        hit = self._c.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        val = builder()
+        self._c[key] = (ver, val)
+        return val
+
+    def clear(self):
+        self._c.clear()
+
+
+def pver(*params):
+    return tuple((p._version, p.data_ptr()) for p in params)

@@ -1,0 +1,406 @@
+"""Tensor-level wrappers over the libdlsg C-ABI (one Python call = one kernel launch).
+
+All arguments are torch CUDA tensors / strided views; outputs are written in place into
+caller-provided tensors (nothing is allocated here, so every call is CUDA-graph capturable).
+`backend` is the CUDA library; tests may install a CPU emulation of these primitives
+(tests/cpu_emul.py) to exercise the host orchestration without a GPU - the product never does.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+F32, BF16 = L.F32, L.BF16
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError('unsupported dtype %s' % t.dtype)
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _rows2d(t):
+    """(rows, cols, ld) of a 2-D (or flattenable leading dims) view with unit inner stride."""
+    assert t.stride(-1) == 1 or t.shape[-1] == 1, 'inner dim must be contiguous: %s %s' % (t.shape, t.stride())
+    if t.dim() == 1:
+        return 1, t.shape[0], t.shape[0]
+    if t.dim() == 2:
+        return t.shape[0], t.shape[1], t.stride(0)
+    # leading dims must collapse to a uniform row stride
+    ld = t.stride(-2)
+    rows = 1
+    exp = ld
+    for d in range(t.dim() - 2, -1, -1):
+        if t.shape[d] != 1:
+            assert t.stride(d) == exp, 'leading dims not collapsible: %s %s' % (t.shape, t.stride())
+        exp *= t.shape[d]
+        rows *= t.shape[d]
+    return rows, t.shape[-1], ld
+
+
+class CudaBackend:
+    name = 'cuda'
+
+    def __init__(self):
+        self.lib = L.load()
+        self.launches = 0
+
+    def _ck(self, t):
+        if not t.is_cuda:
+            raise L.DlsgError('dlsg ops need CUDA tensors (no CPU fallback)')
+
+    # ------------------------------------------------------------------ GEMM
+    def gemm(self, a, b, out, bias=None, bias_axis='n', tanh=False, alpha=1.0, accum=False, splitk=1,
+             impl=None):
+        """out[(batch,)M,N] = epi(alpha * a[(batch,)M,K] @ b[(batch,)N,K]^T + bias).
+
+        `out` may be a transposed view (unit stride on M) -> STORE_T.  For splitk>1 `out` has a
+        leading split dim: (splitk, M, N) and receives partial sums."""
+        self._ck(a)
+        g = L.GemmT()
+        if splitk > 1:
+            assert a.dim() == 2 and out.dim() == 3 and out.shape[0] == splitk
+            g.stride_split = out.stride(0)
+            o2 = out[0]
+        else:
+            o2 = out
+        if a.dim() == 3:
+            batch = a.shape[0]
+            assert b.dim() == 3 and o2.dim() == 3
+            g.stride_a, g.stride_b, g.stride_d = a.stride(0), b.stride(0), o2.stride(0)
+            a2, b2, o2 = a[0], b[0], o2[0]
+        else:
+            batch = 1
+            a2, b2 = a, b
+        M, K = a2.shape
+        N, K2 = b2.shape
+        assert K == K2 and tuple(o2.shape) == (M, N), (a.shape, b.shape, out.shape)
+        flags = 0
+        if o2.stride(1) == 1 or N == 1:
+            g.ldd = o2.stride(0)
+        else:
+            assert o2.stride(0) == 1, 'out must have a unit stride'
+            g.ldd = o2.stride(1)
+            flags |= L.EPI_STORE_T
+        if bias is not None:
+            flags |= L.EPI_BIAS_N if bias_axis == 'n' else L.EPI_BIAS_M
+        if tanh:
+            flags |= L.EPI_TANH
+        if accum:
+            flags |= L.EPI_ACCUM
+        g.A, g.B, g.D, g.bias = a2.data_ptr(), b2.data_ptr(), o2.data_ptr(), _ptr(bias)
+        g.M, g.N, g.K, g.batch = M, N, K, batch
+        g.sam, g.sak, g.sbn, g.sbk = a2.stride(0), a2.stride(1), b2.stride(0), b2.stride(1)
+        g.a_dtype, g.b_dtype, g.d_dtype = _dt(a2), _dt(b2), _dt(o2)
+        if impl is None:
+            impl = L.GEMM_TC if (g.a_dtype == BF16 and g.b_dtype == BF16 and g.sak == 1 and g.sbk == 1) else L.GEMM_SIMT
+        g.impl, g.flags, g.splitk, g.alpha = impl, flags, splitk, alpha
+        self.launches += 1
+        L.check(self.lib.dlsg_gemm(C.byref(g), _stream()), 'dlsg_gemm')
+
+    # ------------------------------------------------------------------ conversion
+    def convert(self, src, dst=None, dstT=None):
+        """dst[..., r, c] = src[..., r, c]; dstT[..., c, r] = src[..., r, c] (2-D or batched 3-D views)."""
+        self._ck(src)
+        ref = dst if dst is not None else dstT
+        if src.dim() == 3:
+            batch, rows, cols = src.shape
+            bs = (src.stride(0), dst.stride(0) if dst is not None else 0, dstT.stride(0) if dstT is not None else 0)
+            s2, d2, t2 = src[0], (dst[0] if dst is not None else None), (dstT[0] if dstT is not None else None)
+        else:
+            batch, bs = 1, (0, 0, 0)
+            rows, cols = src.shape
+            s2, d2, t2 = src, dst, dstT
+        assert s2.stride(1) == 1 or cols == 1
+        self.launches += 1
+        L.check(self.lib.dlsg_convert2d_batched(
+            s2.data_ptr(), _dt(s2), s2.stride(0), _ptr(d2), _dt(ref), d2.stride(0) if d2 is not None else 0,
+            _ptr(t2), t2.stride(0) if t2 is not None else 0, rows, cols, batch, bs[0], bs[1], bs[2], _stream()),
+            'dlsg_convert2d')
+
+    def colsum(self, x, out):
+        rows, cols, ld = _rows2d(x)
+        self.launches += 1
+        L.check(self.lib.dlsg_colsum(x.data_ptr(), _dt(x), ld, rows, cols, out.data_ptr(), _stream()), 'dlsg_colsum')
+
+    # ------------------------------------------------------------------ norm family
+    def norm_fwd(self, x, gamma, beta, y=None, y2=None, res=None, stats=None, pre_tanh=False, post_tanh=False,
+                 drop=None):
+        self._ck(x)
+        p = L.NormFwdT()
+        rows, D, p.ldx = _rows2d(x)
+        p.x, p.x_dtype, p.rows, p.D = x.data_ptr(), _dt(x), rows, D
+        if res is not None:
+            r_, d_, p.ldres = _rows2d(res)
+            assert (r_, d_) == (rows, D)
+            p.res, p.res_dtype = res.data_ptr(), _dt(res)
+        if y is not None:
+            r_, d_, p.ldy = _rows2d(y)
+            assert (r_, d_) == (rows, D), (y.shape, x.shape)
+            p.y, p.y_dtype = y.data_ptr(), _dt(y)
+        if y2 is not None:
+            r_, d_, p.ldy2 = _rows2d(y2)
+            assert (r_, d_) == (rows, D)
+            p.y2, p.y2_dtype = y2.data_ptr(), _dt(y2)
+        p.gamma, p.beta, p.stats = gamma.data_ptr(), beta.data_ptr(), _ptr(stats)
+        p.flags = (L.NORM_PRE_TANH if pre_tanh else 0) | (L.NORM_POST_TANH if post_tanh else 0)
+        if drop is not None and drop[0] > 0:
+            p.drop_p, p.seed, p.offset = drop
+        self.launches += 1
+        L.check(self.lib.dlsg_norm_fwd(C.byref(p), _stream()), 'dlsg_norm_fwd')
+
+    def norm_bwd(self, dy, x, gamma, beta, stats, dx=None, res=None, dgamma=None, dbeta=None, pre_tanh=False,
+                 post_tanh=False, in_is_tanh=False, drop=None, dx_accum=False):
+        self._ck(x)
+        p = L.NormBwdT()
+        rows, D, p.ldx = _rows2d(x)
+        p.x, p.x_dtype, p.rows, p.D = x.data_ptr(), _dt(x), rows, D
+        r_, d_, p.lddy = _rows2d(dy)
+        assert (r_, d_) == (rows, D), (dy.shape, x.shape)
+        p.dy, p.dy_dtype = dy.data_ptr(), _dt(dy)
+        if res is not None:
+            _, _, p.ldres = _rows2d(res)
+            p.res, p.res_dtype = res.data_ptr(), _dt(res)
+        if dx is not None:
+            r_, d_, p.lddx = _rows2d(dx)
+            assert (r_, d_) == (rows, D)
+            p.dx, p.dx_dtype = dx.data_ptr(), _dt(dx)
+        p.gamma, p.beta, p.stats = gamma.data_ptr(), beta.data_ptr(), stats.data_ptr()
+        p.dgamma, p.dbeta = _ptr(dgamma), _ptr(dbeta)
+        p.flags = ((L.NORM_PRE_TANH if pre_tanh else 0) | (L.NORM_POST_TANH if post_tanh else 0) |
+                   (L.NORM_IN_IS_TANH if in_is_tanh else 0))
+        p.dx_accum = 1 if dx_accum else 0
+        if drop is not None and drop[0] > 0:
+            p.drop_p, p.seed, p.offset = drop
+        self.launches += 1
+        L.check(self.lib.dlsg_norm_bwd(C.byref(p), _stream()), 'dlsg_norm_bwd')
+
+    # ------------------------------------------------------------------ LSTM cell
+    def lstm_cell_fwd(self, gates, c_prev, c_out, h_out=None, row_bias=None, bias=None, h2=None, h3=None, drop=None):
+        """gates: (B,4H) or (nsplit,B,4H) fp32 (overwritten with activated i,f,g,o in gates[0])."""
+        self._ck(gates)
+        p = L.CellFwdT()
+        if gates.dim() == 3:
+            p.nsplit, p.stride_split = gates.shape[0], gates.stride(0)
+            g0 = gates[0]
+        else:
+            p.nsplit, g0 = 1, gates
+        assert g0.is_contiguous()
+        B, H4 = g0.shape
+        p.gates, p.B, p.H = g0.data_ptr(), B, H4 // 4
+        if row_bias is not None:
+            p.row_bias, p.ld_row_bias = row_bias.data_ptr(), row_bias.stride(0)
+        p.bias, p.c_prev, p.c_out, p.h_out = _ptr(bias), _ptr(c_prev), c_out.data_ptr(), _ptr(h_out)
+        if h2 is not None:
+            p.h2, p.ldh2, p.h2_dtype = h2.data_ptr(), h2.stride(0), _dt(h2)
+        if h3 is not None:
+            p.h3, p.ldh3, p.h3_dtype = h3.data_ptr(), h3.stride(0), _dt(h3)
+        if drop is not None and drop[0] > 0:
+            p.drop_p, p.seed, p.offset = drop
+        self.launches += 1
+        L.check(self.lib.dlsg_lstm_cell_fwd(C.byref(p), _stream()), 'dlsg_lstm_cell_fwd')
+
+    def lstm_cell_bwd(self, acts, c_prev, c_new, dh, dc_next, dc_prev, dgates=None, dgates2=None, dgatesT=None,
+                      drop=None, dh2=None):
+        """dh / dh2: (B,H) fp32 views (unit inner stride); their sum is the gradient wrt the (dropped) h."""
+        self._ck(acts)
+        p = L.CellBwdT()
+        B, H4 = acts.shape
+        p.acts, p.c_prev, p.c_new, p.dh, p.dc_next = acts.data_ptr(), _ptr(c_prev), c_new.data_ptr(), dh.data_ptr(), _ptr(dc_next)
+        p.lddh = dh.stride(0)
+        if dh2 is not None:
+            p.dh2, p.lddh2 = dh2.data_ptr(), dh2.stride(0)
+        assert dh.stride(1) == 1 and c_new.is_contiguous() and acts.is_contiguous()
+        p.dgates, p.dc_prev, p.B, p.H = _ptr(dgates), _ptr(dc_prev), B, H4 // 4
+        if dgates2 is not None:
+            p.dgates2, p.ld_dgates2, p.dgates2_dtype = dgates2.data_ptr(), dgates2.stride(0), _dt(dgates2)
+        if dgatesT is not None:
+            p.dgatesT, p.ld_dgatesT, p.dgatesT_dtype = dgatesT.data_ptr(), dgatesT.stride(0), _dt(dgatesT)
+        if drop is not None and drop[0] > 0:
+            p.drop_p, p.seed, p.offset = drop
+        self.launches += 1
+        L.check(self.lib.dlsg_lstm_cell_bwd(C.byref(p), _stream()), 'dlsg_lstm_cell_bwd')
+
+    # ------------------------------------------------------------------ softmax
+    @staticmethod
+    def _softmax_desc(x, dim):
+        dim = dim % x.dim()
+        assert x.dim() == 3, 'softmax views are 3-D (outer, n, inner) after the caller reshapes'
+        order = [d for d in range(3) if d != dim]
+        o, i = order
+        return x.shape[o], x.shape[dim], x.shape[i], x.stride(o), x.stride(dim), x.stride(i)
+
+    def softmax_fwd(self, x, y, dim, scale=1.0, mask=None, mask_mode=0):
+        self._ck(x)
+        p = L.SoftmaxT()
+        assert x.stride() == y.stride() and (mask is None or mask.stride() == x.stride())
+        p.outer, p.n, p.inner, p.so, p.sn, p.si = self._softmax_desc(x, dim)
+        p.x, p.y, p.mask, p.scale, p.mask_mode = x.data_ptr(), y.data_ptr(), _ptr(mask), scale, mask_mode
+        self.launches += 1
+        L.check(self.lib.dlsg_softmax_fwd(C.byref(p), _stream()), 'dlsg_softmax_fwd')
+
+    def softmax_bwd(self, x, dy, dx, dim, scale=1.0, mask=None, mask_mode=0):
+        self._ck(x)
+        p = L.SoftmaxT()
+        assert x.stride() == dy.stride() == dx.stride() and (mask is None or mask.stride() == x.stride())
+        p.outer, p.n, p.inner, p.so, p.sn, p.si = self._softmax_desc(x, dim)
+        p.x, p.mask, p.scale, p.mask_mode = x.data_ptr(), _ptr(mask), scale, mask_mode
+        self.launches += 1
+        L.check(self.lib.dlsg_softmax_bwd(C.byref(p), dy.data_ptr(), dx.data_ptr(), _stream()), 'dlsg_softmax_bwd')
+
+    # ------------------------------------------------------------------ node attention
+    def node_attn_fwd(self, Kp, Vp, qp, alpha, ctx, rows_per_node=1):
+        """Kp,Vp (nh,nodes,P,H) fp32; qp (rows,nh*H) fp32; alpha (rows,nh*P) view; ctx (rows,nh*H) view."""
+        self._ck(Kp)
+        p = L.AttnFwdT()
+        nh, nodes, P, H = Kp.shape
+        assert Kp.is_contiguous() and Vp.is_contiguous() and qp.is_contiguous()
+        p.Kp, p.Vp, p.qp, p.alpha, p.ctx = Kp.data_ptr(), Vp.data_ptr(), qp.data_ptr(), _ptr(alpha), ctx.data_ptr()
+        p.rows, p.nh, p.P, p.H, p.rows_per_node, p.ctx_dtype = qp.shape[0], nh, P, H, rows_per_node, _dt(ctx)
+        p.ldctx, p.ldalpha, p.nodes = ctx.stride(0), (alpha.stride(0) if alpha is not None else 0), nodes
+        self.launches += 1
+        L.check(self.lib.dlsg_node_attn_fwd(C.byref(p), _stream()), 'dlsg_node_attn_fwd')
+
+    def node_attn_bwd(self, Kp, Vp, qp, alpha, dctx, dqp, dKp, dVp, dalpha_ext=None):
+        self._ck(Kp)
+        p = L.AttnBwdT()
+        nh, nodes, P, H = Kp.shape
+        assert nodes == qp.shape[0] and dqp.is_contiguous() and dKp.is_contiguous() and dVp.is_contiguous()
+        p.Kp, p.Vp, p.qp, p.alpha, p.dctx = Kp.data_ptr(), Vp.data_ptr(), qp.data_ptr(), alpha.data_ptr(), dctx.data_ptr()
+        p.dalpha_ext, p.dqp, p.dKp, p.dVp = _ptr(dalpha_ext), dqp.data_ptr(), dKp.data_ptr(), dVp.data_ptr()
+        p.rows, p.nh, p.P, p.H, p.lddctx, p.ldalpha, p.dqp_dtype = qp.shape[0], nh, P, H, dctx.stride(0), alpha.stride(0), _dt(dqp)
+        if dalpha_ext is not None:
+            assert dalpha_ext.stride(0) == alpha.stride(0)
+        self.launches += 1
+        L.check(self.lib.dlsg_node_attn_bwd(C.byref(p), _stream()), 'dlsg_node_attn_bwd')
+
+    # ------------------------------------------------------------------ embedding / small
+    def embedding_gather(self, table, ids, out=None, out2=None, drop=None):
+        """ids: 1-D int64 view (any stride). out/out2: (rows, W) views."""
+        self._ck(table)
+        dp, seed, off = drop if (drop is not None and drop[0] > 0) else (0.0, 0, 0)
+        ref = out if out is not None else out2
+        self.launches += 1
+        L.check(self.lib.dlsg_embedding_gather(
+            table.data_ptr(), ids.data_ptr(), ids.stride(0), ids.shape[0], table.shape[1],
+            _ptr(out), _dt(ref) if out is None else _dt(out), out.stride(0) if out is not None else 0,
+            _ptr(out2), _dt(out2) if out2 is not None else 0, out2.stride(0) if out2 is not None else 0,
+            dp, seed, off, _stream()), 'dlsg_embedding_gather')
+
+    def embedding_scatter_add(self, dtable, ids, dout, drop=None):
+        self._ck(dtable)
+        dp, seed, off = drop if (drop is not None and drop[0] > 0) else (0.0, 0, 0)
+        self.launches += 1
+        L.check(self.lib.dlsg_embedding_scatter_add(dtable.data_ptr(), ids.data_ptr(), ids.stride(0), ids.shape[0],
+                                                    dtable.shape[1], dout.data_ptr(), dout.stride(0), dp, seed, off,
+                                                    _stream()), 'dlsg_embedding_scatter_add')
+
+    def mean_nodes_fwd(self, x, y):
+        B, P, H = x.shape
+        assert x.is_contiguous()
+        self.launches += 1
+        L.check(self.lib.dlsg_mean_nodes_fwd(x.data_ptr(), B, P, H, y.data_ptr(), y.stride(0), _stream()), 'mean_nodes_fwd')
+
+    def mean_nodes_bwd(self, dy, dx):
+        B, P, H = dx.shape
+        assert dx.is_contiguous()
+        self.launches += 1
+        L.check(self.lib.dlsg_mean_nodes_bwd(dy.data_ptr(), dy.stride(0), B, P, H, dx.data_ptr(), _stream()), 'mean_nodes_bwd')
+
+    def axpby(self, x, a, y, b):
+        assert x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel()
+        self.launches += 1
+        L.check(self.lib.dlsg_axpby(x.data_ptr(), a, y.data_ptr(), b, x.numel(), _stream()), 'axpby')
+
+    def add_rowbcast(self, x, pe, y, drop=None):
+        assert x.is_contiguous() and pe.is_contiguous() and y.is_contiguous()
+        dp, seed, off = drop if (drop is not None and drop[0] > 0) else (0.0, 0, 0)
+        self.launches += 1
+        L.check(self.lib.dlsg_add_rowbcast(x.data_ptr(), pe.data_ptr(), y.data_ptr(), x.numel() // pe.numel(), pe.numel(),
+                                           dp, seed, off, _stream()), 'add_rowbcast')
+
+    def dropout(self, x, y, drop):
+        assert x.is_contiguous() and y.is_contiguous()
+        self.launches += 1
+        L.check(self.lib.dlsg_dropout(x.data_ptr(), y.data_ptr(), x.numel(), drop[0], drop[1], drop[2], _stream()), 'dropout')
+
+    def relu_(self, x):
+        assert x.is_contiguous()
+        self.launches += 1
+        L.check(self.lib.dlsg_relu(x.data_ptr(), x.numel(), _stream()), 'relu')
+
+    def relu_bwd(self, r, dr, dx):
+        self.launches += 1
+        L.check(self.lib.dlsg_relu_bwd(r.data_ptr(), dr.data_ptr(), dx.data_ptr(), r.numel(), _stream()), 'relu_bwd')
+
+    def mul(self, a, b, y):
+        self.launches += 1
+        L.check(self.lib.dlsg_mul(a.data_ptr(), b.data_ptr(), y.data_ptr(), a.numel(), _stream()), 'mul')
+
+    # ------------------------------------------------------------------ vocab / beam
+    def row_argmax(self, logits, ids):
+        rows, V = logits.shape
+        self.launches += 1
+        L.check(self.lib.dlsg_row_argmax(logits.data_ptr(), logits.stride(0), rows, V, ids.data_ptr(), ids.stride(0), _stream()), 'row_argmax')
+
+    def log_softmax(self, logits, out):
+        rows, V = logits.shape
+        self.launches += 1
+        L.check(self.lib.dlsg_log_softmax(logits.data_ptr(), logits.stride(0), rows, V, out.data_ptr(), out.stride(0), _stream()), 'log_softmax')
+
+    def ce_masked(self, logits, targets, lens, loss_sum, dlogits, inv_count):
+        B, Lw, V = logits.shape
+        assert logits.is_contiguous() and targets.is_contiguous() and lens.dtype == torch.int32
+        self.launches += 1
+        L.check(self.lib.dlsg_ce_masked(logits.data_ptr(), targets.data_ptr(), lens.data_ptr(), B, Lw, V,
+                                        loss_sum.data_ptr(), _ptr(dlogits), inv_count, _stream()), 'ce_masked')
+
+    def beam_topk(self, logits, last, end_index, k, top_lp, top_id, normalize=True):
+        rows, V = logits.shape
+        self.launches += 1
+        L.check(self.lib.dlsg_beam_topk(logits.data_ptr(), logits.stride(0), rows, V, _ptr(last), end_index, k,
+                                        top_lp.data_ptr(), top_id.data_ptr(), 1 if normalize else 0, _stream()), 'beam_topk')
+
+    def beam_merge(self, top_lp, top_id, last_lp, B, beam, k, new_lp, new_cls, backptr, all_end, end_index):
+        self.launches += 1
+        L.check(self.lib.dlsg_beam_merge(top_lp.data_ptr(), top_id.data_ptr(), last_lp.data_ptr(), B, beam, k,
+                                         new_lp.data_ptr(), new_cls.data_ptr(), backptr.data_ptr(), _ptr(all_end),
+                                         end_index, _stream()), 'beam_merge')
+
+    def beam_gather(self, src, dst, backptr, B, beam):
+        """src/dst: (B*beam, W) contiguous rows (padded operand buffers allowed: pass the full row)."""
+        assert src.stride(-1) == 1 and src.stride() == dst.stride() and src.dtype == dst.dtype
+        row_bytes = src.stride(0) * src.element_size()
+        self.launches += 1
+        L.check(self.lib.dlsg_beam_gather(src.data_ptr(), dst.data_ptr(), backptr.data_ptr(), B, beam, row_bytes, _stream()), 'beam_gather')
+
+    def beam_backtrack(self, preds, backs, S, B, beam, out):
+        self.launches += 1
+        L.check(self.lib.dlsg_beam_backtrack(preds.data_ptr(), _ptr(backs), S, B, beam, out.data_ptr(), _stream()), 'beam_backtrack')
+
+
+_backend = None
+
+
+def backend():
+    global _backend
+    if _backend is None:
+        _backend = CudaBackend()
+    return _backend
+
+
+def set_backend(b):
+    """Test hook only (tests/cpu_emul.py)."""
+    global _backend
+    _backend = b

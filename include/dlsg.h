@@ -1,0 +1,195 @@
+/* libdlsg - C-ABI of the B200 (sm_100a) kernels behind the D-LSG model API.
+ *
+ * The reference (baiyang4/D-LSG-Video-Caption) has no FFI: its boundary is the Python module API
+ * models/{model,layer,sublayer,allennlp_beamsearch}.py.  Our drop-in mirror of those modules
+ * (d-lsg-video-caption_b200/models/) binds these symbols with ctypes (dlsg/_lib.py); each entry
+ * cites the reference call site whose arithmetic it replaces (file:line in /root/reference).
+ *
+ * Conventions: every pointer is a caller-owned DEVICE pointer unless stated; sizes in elements;
+ * `stream` is a cudaStream_t; return 0 on success, nonzero on error (dlsg_last_error() explains).
+ * No allocation, no host sync, no global state besides the lazily resolved driver entry point for
+ * cuTensorMapEncodeTiled: every entry is CUDA-graph capturable and re-entrant per stream.
+ */
+#ifndef DLSG_H_
+#define DLSG_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { DLSG_F32 = 0, DLSG_BF16 = 1 };
+
+/* ---- library ------------------------------------------------------------------------------ */
+int dlsg_version(void);
+int dlsg_sm_arch(void);                /* 100 = built for sm_100a                               */
+const char* dlsg_last_error(void);
+
+/* ---- dense projections (nn.Linear / LSTM gate GEMMs / vocab projection / bmm) -------------
+ * D[b](M,N) = epi( A[b](M,K) . B[b](N,K)^T + bias ).  Replaces torch addmm/bmm at
+ * layer.py:51,179,184 (embeddings), layer.py:52,571,593 + model.py:152 (LSTM gates),
+ * sublayer.py:29-31,66-68,80 (attention projections), layer.py:600 (word_restore),
+ * model.py:148 (conv1d k=1), layer.py:187,191 / sublayer.py:69,76,191,196 (bmm).
+ *  impl DLSG_GEMM_TC  : TMA -> smem -> tcgen05.mma (TMEM accum), bf16 operands, fp32 accumulate.
+ *                        A,B row-major with unit K stride, lda/ldb multiples of 8 elements,
+ *                        16-byte aligned bases.  splitk>1 writes partial sums to D + s*stride_split.
+ *  impl DLSG_GEMM_SIMT: fp32 FFMA tiles, arbitrary element strides (sam,sak,sbn,sbk) and dtypes.
+ */
+enum { DLSG_GEMM_SIMT = 0, DLSG_GEMM_TC = 1 };
+enum {
+  DLSG_EPI_BIAS_N = 1,   /* bias[n] added                                                      */
+  DLSG_EPI_BIAS_M = 2,   /* bias[m] added                                                      */
+  DLSG_EPI_TANH = 4,     /* tanh after bias                                                    */
+  DLSG_EPI_ACCUM = 8,    /* D += result                                                        */
+  DLSG_EPI_STORE_T = 16  /* store D^T: element (m,n) goes to D[n*ldd + m]                      */
+};
+typedef struct {
+  const void* A; const void* B; void* D; const float* bias;
+  int32_t M, N, K, batch;
+  int64_t sam, sak, sbn, sbk, ldd;          /* element strides; TC requires sak == sbk == 1     */
+  int64_t stride_a, stride_b, stride_d;     /* batch strides (elements)                         */
+  int32_t a_dtype, b_dtype, d_dtype, impl, flags, _pad0;
+  int32_t splitk; int32_t _pad; int64_t stride_split;
+  float alpha;                              /* result scale applied before bias                 */
+} dlsg_gemm_t;
+int dlsg_gemm(const dlsg_gemm_t* p, void* stream);
+
+/* ---- layout / dtype conversion ------------------------------------------------------------
+ * dst[r,c] = src[r,c] (cast); optional dstT[c,r] = src[r,c].  Feeds bf16 GEMM operands.        */
+int dlsg_convert2d(const void* src, int src_dtype, int64_t ld_src, void* dst, int dst_dtype, int64_t ld_dst,
+                   void* dstT, int64_t ld_dstT, int64_t rows, int64_t cols, void* stream);
+int dlsg_convert2d_batched(const void* src, int src_dtype, int64_t ld_src, void* dst, int dst_dtype, int64_t ld_dst,
+                           void* dstT, int64_t ld_dstT, int64_t rows, int64_t cols, int64_t batch,
+                           int64_t bs_src, int64_t bs_dst, int64_t bs_dstT, void* stream);
+/* out[c] += sum_r x[r,c] : bias gradients (fp32 accumulate into out)                            */
+int dlsg_colsum(const void* x, int dtype, int64_t ld, int64_t rows, int64_t cols, float* out, void* stream);
+
+/* ---- Tanh->LayerNorm family ---------------------------------------------------------------
+ * y = post( LN( pre(x + res) ) ) * dropmask ; pre/post in {identity,tanh}.  Replaces
+ * layer.py:145-163,53,57,574,599, sublayer.py:21-26,183-187, model.py:128-131,153.
+ * stats (rows,2) = mean,rstd saved for backward.  y2 = optional second (bf16) copy of y.      */
+enum {
+  DLSG_NORM_PRE_TANH = 1, DLSG_NORM_POST_TANH = 2,
+  DLSG_NORM_IN_IS_TANH = 4   /* x already holds tanh(.) (fused in the GEMM epilogue); backward  */
+                             /* still applies (1-x^2)                                           */
+};
+typedef struct {
+  const void* x; const void* res; void* y; void* y2; const float* gamma; const float* beta; float* stats;
+  int64_t rows; int32_t D; int32_t flags;
+  int64_t ldx, ldres, ldy, ldy2;
+  int32_t x_dtype, res_dtype, y_dtype, y2_dtype;
+  float drop_p; uint32_t _pad; uint64_t seed, offset;     /* dropout: keep iff philox(seed,offset+idx) >= p */
+} dlsg_norm_fwd_t;
+int dlsg_norm_fwd(const dlsg_norm_fwd_t* p, void* stream);
+typedef struct {
+  const void* dy; const void* x; const void* res; const float* gamma; const float* beta; const float* stats;
+  void* dx; float* dgamma; float* dbeta;                   /* dgamma/dbeta are ACCUMULATED (+=)    */
+  int64_t rows; int32_t D; int32_t flags;
+  int64_t lddy, ldx, ldres, lddx;
+  int32_t dy_dtype, x_dtype, res_dtype, dx_dtype;
+  float drop_p; int32_t dx_accum; uint64_t seed, offset;
+} dlsg_norm_bwd_t;
+int dlsg_norm_bwd(const dlsg_norm_bwd_t* p, void* stream);
+
+/* ---- LSTM cell pointwise (nn.LSTMCell / nn.LSTM step, gate order i,f,g,o) ------------------
+ * layer.py:52,571,593, model.py:152.  gates: nsplit partial (B,4H) fp32 buffers (split-K GEMM
+ * output) + optional per-row bias (B,4H) + optional bias (4H).  Writes activated gates back to
+ * gates[0] (saved for backward), c_out, h_out (fp32) and up to two extra copies of h (any dtype,
+ * own leading dimension) straight into the next GEMM's operand buffers.                        */
+typedef struct {
+  float* gates; int32_t nsplit; int32_t _pad0; int64_t stride_split;
+  const float* row_bias; int64_t ld_row_bias; const float* bias;
+  const float* c_prev; float* c_out; float* h_out;
+  void* h2; int64_t ldh2; int32_t h2_dtype; int32_t _pad1;
+  void* h3; int64_t ldh3; int32_t h3_dtype; int32_t _pad2;
+  int32_t B, H;
+  float drop_p; int32_t _pad3; uint64_t seed, offset;     /* dropout on h (layer.py:594)           */
+} dlsg_lstm_cell_fwd_t;
+int dlsg_lstm_cell_fwd(const dlsg_lstm_cell_fwd_t* p, void* stream);
+typedef struct {
+  const float* acts; const float* c_prev; const float* c_new;
+  const float* dh; int64_t lddh; const float* dh2; int64_t lddh2;  /* dh_total = dh + dh2 (dh2 may be NULL) */
+  const float* dc_next;                                    /* dc_next may be NULL (=0)              */
+  float* dgates; void* dgates2; int64_t ld_dgates2; int32_t dgates2_dtype; int32_t _pad0;
+  void* dgatesT; int64_t ld_dgatesT; int32_t dgatesT_dtype; int32_t _pad1;  /* (4H, .) transposed copy */
+  float* dc_prev;
+  int32_t B, H;
+  float drop_p; int32_t _pad2; uint64_t seed, offset;
+} dlsg_lstm_cell_bwd_t;
+int dlsg_lstm_cell_bwd(const dlsg_lstm_cell_bwd_t* p, void* stream);
+
+/* ---- softmax over an arbitrary axis (layer.py:188 dim=1, sublayer.py:34,74,192, layer.py:706)
+ * x viewed as (outer, n, inner) with element strides; optional scale, optional mask (>0 keeps,
+ * else fill -9e15 BEFORE softmax: sublayer.py:70-72) or post-mask (zero AFTER softmax: layer.py:707). */
+typedef struct {
+  const float* x; float* y; const float* mask;
+  int64_t outer, n, inner; int64_t so, sn, si;   /* strides of x / y / mask (same layout)        */
+  float scale; int32_t mask_mode;                /* 0 none, 1 pre (-9e15), 2 post (zero)          */
+} dlsg_softmax_t;
+int dlsg_softmax_fwd(const dlsg_softmax_t* p, void* stream);
+/* dx = scale * y_unmasked*(dy' - sum(dy'*y_unmasked)), dy' = dy*postmask; y = forward output   */
+int dlsg_softmax_bwd(const dlsg_softmax_t* p, const float* dy, float* dx, void* stream);
+
+/* ---- AttentionShare core, one decode step (sublayer.py:32-39) ------------------------------
+ * logits[r,p] = Kp[node(r),p,:].qp[r,:]/sqrt(H); alpha = softmax_p; ctx[r,:] = sum_p alpha*Vp.
+ * node(r) = r / rows_per_node (beam rows share their clip's nodes).  heads: qp (rows, nh*H),
+ * Kp/Vp (nodes, nh, P, H) fp32, alpha (rows, nh*P), ctx (rows, nh*H).                          */
+typedef struct {
+  const float* Kp; const float* Vp; const float* qp; float* alpha; void* ctx;
+  int32_t rows, nh, P, H, rows_per_node, ctx_dtype; int64_t ldctx, ldalpha;
+  int32_t nodes; int32_t _pad;
+} dlsg_node_attn_fwd_t;
+int dlsg_node_attn_fwd(const dlsg_node_attn_fwd_t* p, void* stream);
+typedef struct {
+  const float* Kp; const float* Vp; const float* qp; const float* alpha; const float* dctx; const float* dalpha_ext;
+  void* dqp; float* dKp; float* dVp;                      /* dKp,dVp ACCUMULATED over steps        */
+  int32_t rows, nh, P, H; int64_t lddctx, ldalpha;
+  int32_t dqp_dtype; int32_t _pad;
+} dlsg_node_attn_bwd_t;
+int dlsg_node_attn_bwd(const dlsg_node_attn_bwd_t* p, void* stream);
+
+/* ---- embedding (layer.py:421,438,535) and small reductions ---------------------------------- */
+int dlsg_embedding_gather(const float* table, const int64_t* ids, int64_t ld_ids, int32_t rows, int32_t W,
+                          void* out, int out_dtype, int64_t ldo, void* out2, int out2_dtype, int64_t ldo2,
+                          float drop_p, uint64_t seed, uint64_t offset, void* stream);
+int dlsg_embedding_scatter_add(float* dtable, const int64_t* ids, int64_t ld_ids, int32_t rows, int32_t W,
+                               const float* dout, int64_t lddo, float drop_p, uint64_t seed, uint64_t offset,
+                               void* stream);
+/* y[b,:] = mean_p x[b,p,:] (layer.py:407-409); bwd: dx[b,p,:] += dy[b,:]/P                     */
+int dlsg_mean_nodes_fwd(const float* x, int32_t B, int32_t P, int32_t H, float* y, int64_t ldy, void* stream);
+int dlsg_mean_nodes_bwd(const float* dy, int64_t lddy, int32_t B, int32_t P, int32_t H, float* dx, void* stream);
+/* generic elementwise: y = a*x + b*y (n elements) ; y = x + pe (broadcast over batch)           */
+int dlsg_axpby(const float* x, float a, float* y, float b, int64_t n, void* stream);
+int dlsg_add_rowbcast(const float* x, const float* pe, float* y, int64_t batch, int64_t inner, float drop_p, uint64_t seed,
+                      uint64_t offset, void* stream);
+/* inverted dropout y = x*mask/(1-p), mask from philox(seed, offset+i); backward = same call on dy (nn.Dropout sites:
+ * layer.py:53,422,439,574,594, sublayer.py:25,60,104,186)                                        */
+int dlsg_dropout(const float* x, float* y, int64_t n, float drop_p, uint64_t seed, uint64_t offset, void* stream);
+/* ResBlock pieces (sublayer.py:117-119): r = relu(x) in place; dx = (x>0)*dr                    */
+int dlsg_relu(float* x, int64_t n, void* stream);
+int dlsg_relu_bwd(const float* r, const float* dr, float* dx, int64_t n, void* stream);
+int dlsg_mul(const float* a, const float* b, float* y, int64_t n, void* stream);
+
+/* ---- vocabulary rows: log-softmax / argmax / CE (layer.py:437,540; run_gun.py:189-197) ------ */
+int dlsg_row_argmax(const float* logits, int64_t ld, int32_t rows, int32_t V, int64_t* ids, int64_t ld_ids, void* stream);
+int dlsg_log_softmax(const float* logits, int64_t ld, int32_t rows, int32_t V, float* out, int64_t ldo, void* stream);
+/* masked CE over (B,L,V): rows with t < len[b] count.  loss_sum/count are ACCUMULATED (zero first).
+ * dlogits (may be NULL) = (softmax - onehot)*gscale/count_total for counted rows, 0 otherwise.   */
+int dlsg_ce_masked(const float* logits, const int64_t* targets, const int32_t* lens, int32_t B, int32_t L, int32_t V,
+                   float* loss_sum, float* dlogits, float inv_count, void* stream);
+
+/* ---- beam search (allennlp_beamsearch.py:127,186-260,272-292) ------------------------------- */
+/* per row: log-softmax, force <end> if last==end (:186-190), top-k (value desc, lowest index on ties) */
+int dlsg_beam_topk(const float* logits, int64_t ld, int32_t rows, int32_t V, const int64_t* last, int32_t end_index,
+                   int32_t k, float* top_lp, int64_t* top_id, int32_t normalize /* 0: input already log-probs */, void* stream);
+/* (B, beam*k) candidates + parent log-probs -> top beam: new log-probs, classes, back-pointers   */
+int dlsg_beam_merge(const float* top_lp, const int64_t* top_id, const float* last_lp, int32_t B, int32_t beam, int32_t k,
+                    float* new_lp, int64_t* new_cls, int64_t* backptr, int32_t* all_end, int32_t end_index, void* stream);
+/* dst[b,j,:] = src[b, backptr[b,j], :] for contiguous state rows of row_bytes bytes (any dtype)    */
+int dlsg_beam_gather(const void* src, void* dst, const int64_t* backptr, int32_t B, int32_t beam, int32_t row_bytes, void* stream);
+/* back-track: preds (S,B,beam), backs (S-1,B,beam) -> out (B,beam,S)                             */
+int dlsg_beam_backtrack(const int64_t* preds, const int64_t* backs, int32_t S, int32_t B, int32_t beam, int64_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

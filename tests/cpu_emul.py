@@ -1,0 +1,314 @@
+"""CPU emulation of the dlsg.ops primitives - TEST INFRASTRUCTURE ONLY.
+
+Lets `-m "not gpu"` tests drive the real host orchestration (dlsg/functional.py, models/) on CPU
+tensors so that layout / stride / backward-pass logic is checked without a GPU.  Each method
+restates the semantics of one C-ABI entry (include/dlsg.h) with plain torch CPU ops and writes
+into the caller's output views exactly like the kernels do.  bf16 operands are rounded like the
+device path (fp32 accumulate).  Never imported by the product.
+"""
+import math
+
+import torch
+
+
+def _f(t):
+    return t.float()
+
+
+class CpuEmulBackend:
+    name = 'cpu-emul'
+
+    def __init__(self):
+        self.launches = 0
+
+    def gemm(self, a, b, out, bias=None, bias_axis='n', tanh=False, alpha=1.0, accum=False, splitk=1, impl=None):
+        self.launches += 1
+        r = torch.matmul(_f(a), _f(b).transpose(-1, -2)) * alpha
+        if splitk > 1:
+            K = a.shape[-1]
+            nkb = (K + 63) // 64
+            per = (nkb + splitk - 1) // splitk
+            for s in range(splitk):
+                k0, k1 = s * per * 64, min(K, (s + 1) * per * 64)
+                part = torch.matmul(_f(a[:, k0:k1]), _f(b[:, k0:k1]).t()) * alpha
+                if s == 0 and bias is not None:
+                    part = part + (bias if bias_axis == 'n' else bias.unsqueeze(-1))
+                out[s].copy_(part + (_f(out[s]) if accum else 0))
+            return
+        if bias is not None:
+            r = r + (bias if bias_axis == 'n' else bias.unsqueeze(-1))
+        if tanh:
+            r = torch.tanh(r)
+        if accum:
+            r = r + _f(out)
+        out.copy_(r)
+
+    def convert(self, src, dst=None, dstT=None):
+        self.launches += 1
+        if dst is not None:
+            dst.copy_(src)
+        if dstT is not None:
+            dstT.copy_(src.transpose(-1, -2))
+
+    def colsum(self, x, out):
+        self.launches += 1
+        out.add_(_f(x).reshape(-1, x.shape[-1]).sum(0))
+
+    @staticmethod
+    def _ln(t, gamma, beta):
+        mean = t.mean(-1, keepdim=True)
+        var = ((t - mean) ** 2).mean(-1, keepdim=True)
+        rstd = torch.rsqrt(var + 1e-5)
+        return (t - mean) * rstd * gamma + beta, mean, rstd
+
+    def norm_fwd(self, x, gamma, beta, y=None, y2=None, res=None, stats=None, pre_tanh=False, post_tanh=False, drop=None):
+        self.launches += 1
+        assert drop is None or drop[0] == 0, 'dropout is not emulated on CPU'
+        t = _f(x)
+        if res is not None:
+            t = t + _f(res)
+        if pre_tanh:
+            t = torch.tanh(t)
+        o, mean, rstd = self._ln(t, gamma, beta)
+        if post_tanh:
+            o = torch.tanh(o)
+        if stats is not None:
+            stats.view(-1, 2).copy_(torch.cat([mean.reshape(-1, 1), rstd.reshape(-1, 1)], 1))
+        if y is not None:
+            y.copy_(o)
+        if y2 is not None:
+            y2.copy_(o)
+
+    def norm_bwd(self, dy, x, gamma, beta, stats, dx=None, res=None, dgamma=None, dbeta=None, pre_tanh=False,
+                 post_tanh=False, in_is_tanh=False, drop=None, dx_accum=False):
+        self.launches += 1
+        assert drop is None or drop[0] == 0
+        t = _f(x)
+        if res is not None:
+            t = t + _f(res)
+        if pre_tanh:
+            t = torch.tanh(t)
+        D = t.shape[-1]
+        st = stats.view(*t.shape[:-1], 2)
+        mean, rstd = st[..., 0:1], st[..., 1:2]
+        xh = (t - mean) * rstd
+        g = _f(dy)
+        if post_tanh:
+            yt = torch.tanh(xh * gamma + beta)
+            g = g * (1 - yt * yt)
+        if dgamma is not None:
+            dgamma.add_((g * xh).reshape(-1, D).sum(0))
+            dbeta.add_(g.reshape(-1, D).sum(0))
+        d = g * gamma
+        s1 = d.mean(-1, keepdim=True)
+        s2 = (d * xh).mean(-1, keepdim=True)
+        r = rstd * (d - s1 - xh * s2)
+        if pre_tanh or in_is_tanh:
+            r = r * (1 - t * t)
+        if dx is not None:
+            if dx_accum:
+                r = r + _f(dx)
+            dx.copy_(r)
+
+    def lstm_cell_fwd(self, gates, c_prev, c_out, h_out=None, row_bias=None, bias=None, h2=None, h3=None, drop=None):
+        self.launches += 1
+        assert drop is None or drop[0] == 0
+        g = gates.sum(0) if gates.dim() == 3 else gates.clone()
+        g0 = gates[0] if gates.dim() == 3 else gates
+        if row_bias is not None:
+            g = g + row_bias
+        if bias is not None:
+            g = g + bias
+        H = g.shape[1] // 4
+        i, f, gg, o = torch.sigmoid(g[:, :H]), torch.sigmoid(g[:, H:2 * H]), torch.tanh(g[:, 2 * H:3 * H]), torch.sigmoid(g[:, 3 * H:])
+        c = f * (c_prev if c_prev is not None else 0) + i * gg
+        h = o * torch.tanh(c)
+        g0.copy_(torch.cat([i, f, gg, o], 1))
+        c_out.copy_(c)
+        for dst in (h_out, h2, h3):
+            if dst is not None:
+                dst.copy_(h)
+
+    def lstm_cell_bwd(self, acts, c_prev, c_new, dh, dc_next, dc_prev, dgates=None, dgates2=None, dgatesT=None, drop=None,
+                      dh2=None):
+        self.launches += 1
+        assert drop is None or drop[0] == 0
+        if dh2 is not None:
+            dh = dh + dh2
+        H = acts.shape[1] // 4
+        i, f, g, o = acts[:, :H], acts[:, H:2 * H], acts[:, 2 * H:3 * H], acts[:, 3 * H:]
+        tc = torch.tanh(c_new)
+        dc = dh * o * (1 - tc * tc)
+        if dc_next is not None:
+            dc = dc + dc_next
+        cp = c_prev if c_prev is not None else torch.zeros_like(c_new)
+        d = torch.cat([dc * g * i * (1 - i), dc * cp * f * (1 - f), dc * i * (1 - g * g), dh * tc * o * (1 - o)], 1)
+        if dc_prev is not None:
+            dc_prev.copy_(dc * f)
+        if dgates is not None:
+            dgates.copy_(d)
+        if dgates2 is not None:
+            dgates2.copy_(d)
+        if dgatesT is not None:
+            dgatesT[:, :d.shape[0]].copy_(d.t())
+
+    @staticmethod
+    def _sm(x, dim, scale, mask, mask_mode):
+        v = x * scale
+        if mask_mode == 1:
+            v = torch.where(mask > 0, v, torch.full_like(v, -9e15))
+        return torch.softmax(v, dim)
+
+    def softmax_fwd(self, x, y, dim, scale=1.0, mask=None, mask_mode=0):
+        self.launches += 1
+        s = self._sm(x, dim, scale, mask, mask_mode)
+        if mask_mode == 2:
+            s = torch.where(mask > 0, s, torch.zeros_like(s))
+        y.copy_(s)
+
+    def softmax_bwd(self, x, dy, dx, dim, scale=1.0, mask=None, mask_mode=0):
+        self.launches += 1
+        s = self._sm(x, dim, scale, mask, mask_mode)
+        g = dy
+        if mask_mode == 2:
+            g = torch.where(mask > 0, g, torch.zeros_like(g))
+        r = scale * s * (g - (g * s).sum(dim, keepdim=True))
+        if mask_mode == 1:
+            r = torch.where(mask > 0, r, torch.zeros_like(r))
+        dx.copy_(r)
+
+    def node_attn_fwd(self, Kp, Vp, qp, alpha, ctx, rows_per_node=1):
+        self.launches += 1
+        nh, nodes, P, H = Kp.shape
+        rows = qp.shape[0]
+        idx = torch.arange(rows) // rows_per_node
+        q = qp.view(rows, nh, H)
+        for h in range(nh):
+            K, V = Kp[h][idx], Vp[h][idx]                        # (rows,P,H)
+            lg = torch.einsum('rph,rh->rp', K, q[:, h]) / math.sqrt(H)
+            a = torch.softmax(lg, 1)
+            if alpha is not None:
+                alpha[:, h * P:(h + 1) * P].copy_(a)
+            ctx[:, h * H:(h + 1) * H].copy_(torch.einsum('rp,rph->rh', a, V))
+
+    def node_attn_bwd(self, Kp, Vp, qp, alpha, dctx, dqp, dKp, dVp, dalpha_ext=None):
+        self.launches += 1
+        nh, nodes, P, H = Kp.shape
+        rows = qp.shape[0]
+        q = qp.view(rows, nh, H)
+        sc = 1.0 / math.sqrt(H)
+        for h in range(nh):
+            a = alpha[:, h * P:(h + 1) * P]
+            dc = dctx[:, h * H:(h + 1) * H]
+            da = torch.einsum('rph,rh->rp', Vp[h], dc)
+            if dalpha_ext is not None:
+                da = da + dalpha_ext[:, h * P:(h + 1) * P]
+            dl = a * (da - (a * da).sum(1, keepdim=True)) * sc
+            dqp.view(rows, nh, H)[:, h].copy_(torch.einsum('rp,rph->rh', dl, Kp[h]))
+            dKp[h].add_(torch.einsum('rp,rh->rph', dl, q[:, h]))
+            dVp[h].add_(torch.einsum('rp,rh->rph', a, dc))
+
+    def embedding_gather(self, table, ids, out=None, out2=None, drop=None):
+        self.launches += 1
+        assert drop is None or drop[0] == 0
+        v = table[ids]
+        for dst in (out, out2):
+            if dst is not None:
+                dst.copy_(v)
+
+    def embedding_scatter_add(self, dtable, ids, dout, drop=None):
+        self.launches += 1
+        dtable.index_add_(0, ids, _f(dout))
+
+    def mean_nodes_fwd(self, x, y):
+        self.launches += 1
+        y.copy_(x.mean(1))
+
+    def mean_nodes_bwd(self, dy, dx):
+        self.launches += 1
+        dx.add_(dy.unsqueeze(1) / dx.shape[1])
+
+    def axpby(self, x, a, y, b):
+        self.launches += 1
+        y.copy_(a * x.reshape(y.shape) + (b * y if b != 0 else 0))
+
+    def dropout(self, x, y, drop):
+        raise AssertionError('dropout is not emulated on CPU')
+
+    def add_rowbcast(self, x, pe, y, drop=None):
+        assert drop is None or drop[0] == 0
+        self.launches += 1
+        y.copy_(x + pe.reshape(-1).repeat(x.numel() // pe.numel()).view(x.shape))
+
+    def relu_(self, x):
+        self.launches += 1
+        x.clamp_(min=0)
+
+    def relu_bwd(self, r, dr, dx):
+        self.launches += 1
+        dx.copy_(torch.where(r > 0, dr, torch.zeros_like(dr)))
+
+    def mul(self, a, b, y):
+        self.launches += 1
+        y.copy_(a * b)
+
+    def row_argmax(self, logits, ids):
+        self.launches += 1
+        ids.copy_(logits.max(1)[1])
+
+    def log_softmax(self, logits, out):
+        self.launches += 1
+        out.copy_(torch.log_softmax(logits, 1))
+
+    def ce_masked(self, logits, targets, lens, loss_sum, dlogits, inv_count):
+        self.launches += 1
+        B, Lw, V = logits.shape
+        lp = torch.log_softmax(logits, -1)
+        m = (torch.arange(Lw).unsqueeze(0) < lens.unsqueeze(1)).float()
+        nll = -lp.gather(2, targets.unsqueeze(2)).squeeze(2)
+        loss_sum.add_((nll * m).sum() * inv_count)
+        if dlogits is not None:
+            g = torch.exp(lp)
+            g.scatter_add_(2, targets.unsqueeze(2), -torch.ones(B, Lw, 1))
+            dlogits.copy_(g * m.unsqueeze(2) * inv_count)
+
+    def beam_topk(self, logits, last, end_index, k, top_lp, top_id, normalize=True):
+        self.launches += 1
+        lp = torch.log_softmax(logits, 1) if normalize else logits
+        if last is not None:
+            forced = torch.full_like(lp, float('-inf'))
+            forced[:, end_index] = 0
+            lp = torch.where((last == end_index).unsqueeze(1), forced, lp)
+        v, i = self._topk_stable(lp, k)
+        top_lp.copy_(v)
+        top_id.copy_(i)
+
+    @staticmethod
+    def _topk_stable(x, k):
+        # value desc, lowest index first on ties (the device kernels' tie rule)
+        idx = torch.argsort(x, dim=1, descending=True, stable=True)[:, :k]
+        return x.gather(1, idx), idx
+
+    def beam_merge(self, top_lp, top_id, last_lp, B, beam, k, new_lp, new_cls, backptr, all_end, end_index):
+        self.launches += 1
+        s = (top_lp.view(B, beam, k) + last_lp.view(B, beam, 1)).reshape(B, beam * k)
+        v, i = self._topk_stable(s, beam)
+        cls = top_id.view(B, beam * k).gather(1, i)
+        new_lp.copy_(v)
+        new_cls.copy_(cls)
+        backptr.copy_(i // k)
+        if all_end is not None and bool((cls != end_index).any()):
+            all_end.zero_()
+
+    def beam_gather(self, src, dst, backptr, B, beam):
+        self.launches += 1
+        idx = (torch.arange(B).unsqueeze(1) * beam + backptr.view(B, beam)).reshape(-1)
+        dst.copy_(src[idx])
+
+    def beam_backtrack(self, preds, backs, S, B, beam, out):
+        self.launches += 1
+        cur = torch.arange(beam).unsqueeze(0).expand(B, beam).clone()
+        for t in range(S - 1, -1, -1):
+            out[:, :, t] = preds[t].gather(1, cur)
+            if t > 0:
+                cur = backs[t - 1].gather(1, cur)
