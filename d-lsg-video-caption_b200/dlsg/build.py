@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
             if r.returncode != 0:
                 raise RuntimeError('nvcc failed for %s' % s)
     if jobs or force or not os.path.exists(LIB):
-        r = subprocess.run([NVCC, '-shared', '-o', LIB] + objs + ['-lcudart'], capture_output=True, text=True)
+        r = subprocess.run([NVCC, '-shared', '-o', LIB] + objs + ['-cudart', 'static'], capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError('link failed')

@@ -1,0 +1,30 @@
+"""Fused masked cross-entropy: the caller-side packing loop + nn.CrossEntropyLoss of
+run_gun.py:189-197 (B Python slices + torch.cat of ~70 MB + log-softmax) as ONE kernel that reads the
+(B,L,V) logits once and writes d(loss)/d(logits) in the same pass (no packing copy)."""
+import torch
+
+from . import ops
+
+
+class _PackedCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, targets, lens_t, inv_count):
+        logits = logits if logits.is_contiguous() else logits.contiguous()
+        loss = torch.zeros(1, dtype=torch.float32, device=logits.device)
+        dlogits = torch.empty_like(logits)
+        ops.backend().ce_masked(logits, targets.contiguous(), lens_t, loss, dlogits, inv_count)
+        ctx.save_for_backward(dlogits)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * g, None, None, None
+
+
+def packed_cross_entropy(outputs, targets, cap_lens):
+    """outputs (B,L,V) raw logits, targets (B,L) int64, cap_lens: python ints.  Mean NLL over sum(cap_lens) tokens."""
+    lens_t = torch.as_tensor(list(cap_lens), dtype=torch.int32).to(outputs.device, non_blocking=True)
+    L = outputs.shape[1]
+    n = sum(min(int(c), L) for c in cap_lens)
+    return _PackedCE.apply(outputs, targets[:, :L], lens_t, 1.0 / max(n, 1))

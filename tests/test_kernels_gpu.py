@@ -1,0 +1,295 @@
+"""Per-kernel parity on the GPU: every libdlsg entry (through the C-ABI / ctypes) against a plain
+torch fp32 restatement of the same op (tests/cpu_emul.py) on the same seeded inputs.
+
+Tolerances: fp32 kernels 1e-5 relative to the output scale; bf16-operand GEMMs are compared against the
+fp32 product of the SAME bf16-rounded operands (accumulation-order noise only, 2e-3 of the output scale);
+integer outputs (ids, back-pointers, token tables) bit-exact.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from dlsg import ops
+from cpu_emul import CpuEmulBackend
+
+DEV = 'cuda'
+
+
+@pytest.fixture(scope='module')
+def be():
+    if not torch.cuda.is_available():
+        pytest.skip('no GPU')
+    return ops.CudaBackend()
+
+
+EM = CpuEmulBackend()
+
+
+def R(*shape, dtype=torch.float32, scale=1.0, seed=[0]):
+    seed[0] += 1
+    g = torch.Generator().manual_seed(seed[0])
+    return (torch.randn(*shape, generator=g) * scale).to(dtype)
+
+
+def both(fn_name, be, cpu_args, cpu_kwargs, outs, tol=1e-5, int_outs=()):
+    """Run emulator on CPU tensors and the kernel on CUDA clones; compare the named output tensors."""
+    def to_dev(x):
+        if not torch.is_tensor(x):
+            return x
+        # clone the whole storage so that views keep their offsets / strides / padding on the device
+        base = torch.empty(0, dtype=x.dtype).set_(x.untyped_storage()).to(DEV)
+        return torch.as_strided(base, x.shape, x.stride(), x.storage_offset())
+    g_args = [to_dev(a) for a in cpu_args]
+    g_kwargs = {k: to_dev(v) for k, v in cpu_kwargs.items()}
+    getattr(EM, fn_name)(*cpu_args, **cpu_kwargs)
+    getattr(be, fn_name)(*g_args, **g_kwargs)
+    torch.cuda.synchronize()
+    allv = dict(zip(range(len(cpu_args)), zip(cpu_args, g_args)))
+    allv.update({k: (cpu_kwargs[k], g_kwargs[k]) for k in cpu_kwargs})
+    for o in outs:
+        c, g = allv[o]
+        c, g = c.float(), g.float().cpu()
+        scale = max(1.0, float(c.abs().max()))
+        err = float((c - g).abs().max())
+        assert err <= tol * scale, (fn_name, o, err, scale)
+    for o in int_outs:
+        c, g = allv[o]
+        assert torch.equal(c, g.cpu()), (fn_name, o)
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+# ----------------------------------------------------------------------------------------------- GEMM (tcgen05)
+TC_SHAPES = [(300, 200, 256), (128, 128, 64), (129, 257, 72), (64, 4096, 2880), (26, 1024, 936), (1664, 1055, 1536),
+             (5, 24, 8), (2000, 2048, 2048)]
+
+
+@pytest.mark.parametrize('M,N,K', TC_SHAPES)
+def test_gemm_tc_plain(be, M, N, K):
+    a, b = bf(R(M, K)), bf(R(N, K))
+    out = torch.zeros(M, N)
+    both('gemm', be, [a, b, out], {}, [2], tol=2e-3)
+
+
+@pytest.mark.parametrize('M,N,K', [(200, 300, 128), (64, 512, 200), (936, 26, 1024)])
+def test_gemm_tc_epilogues(be, M, N, K):
+    a, b = bf(R(M, K, scale=0.2)), bf(R(N, K, scale=0.2))
+    bias_n, bias_m = R(N), R(M)
+    both('gemm', be, [a, b, torch.zeros(M, N)], dict(bias=bias_n, bias_axis='n', tanh=True), [2], tol=2e-3)
+    both('gemm', be, [a, b, torch.zeros(M, N)], dict(bias=bias_m, bias_axis='m', alpha=0.5), [2], tol=2e-3)
+    both('gemm', be, [a, b, R(M, N)], dict(accum=True), [2], tol=2e-3)
+    both('gemm', be, [a, b, torch.zeros(M, N, dtype=torch.bfloat16)], dict(bias=bias_n), [2], tol=1e-2)
+    both('gemm', be, [a, b, torch.zeros(N, M).t()], dict(bias=bias_n), [2], tol=2e-3)      # STORE_T
+    both('gemm', be, [a, b, torch.zeros(M, N + 5)[:, :N]], dict(), [2], tol=2e-3)            # ldd > N
+
+
+def test_gemm_tc_batched_and_strided_views(be):
+    B_, M, N, K = 6, 150, 40, 136
+    a, b = bf(R(B_, M, K)), bf(R(B_, N, K))
+    both('gemm', be, [a, b, torch.zeros(B_, M, N)], {}, [2], tol=2e-3)
+    both('gemm', be, [a, b, torch.zeros(B_, N, M).transpose(1, 2)], dict(alpha=0.25), [2], tol=2e-3)
+    # operand views with a column offset / padded pitch (the decoder's Xl[:, oq:oq+Hq] pattern)
+    big_a, big_b = bf(R(70, 512)), bf(R(96, 640))
+    both('gemm', be, [big_a[:, 128:384], big_b[:, 64:320], torch.zeros(70, 96)], {}, [2], tol=2e-3)
+    # heads as batch with interleaved rows (ctx (R, nh, H) -> (nh, R, H))
+    x = bf(R(33, 2, 64))
+    w = bf(R(2, 48, 64))
+    both('gemm', be, [x.transpose(0, 1), w, torch.zeros(33, 2, 48).transpose(0, 1)], {}, [2], tol=2e-3)
+
+
+@pytest.mark.parametrize('splitk', [2, 3, 5])
+def test_gemm_tc_splitk(be, splitk):
+    M, N, K = 64, 1024, 64 * 15
+    a, b = bf(R(M, K)), bf(R(N, K))
+    both('gemm', be, [a, b, torch.zeros(splitk, M, N)], dict(splitk=splitk, bias=R(N)), [2], tol=2e-3)
+
+
+# ----------------------------------------------------------------------------------------------- GEMM (FFMA)
+def test_gemm_simt_strided(be):
+    a, b = R(70, 90), R(50, 90)
+    both('gemm', be, [a, b, torch.zeros(70, 50)], dict(bias=R(50), tanh=True), [2])
+    at, bt = R(90, 70).t(), R(90, 50).t()
+    both('gemm', be, [at, bt, torch.zeros(70, 50)], dict(alpha=0.3), [2])
+    both('gemm', be, [R(4, 26, 5).transpose(1, 2), R(4, 26, 64).transpose(1, 2), torch.zeros(4, 5, 64)], {}, [2])
+    both('gemm', be, [R(33, 17), bf(R(9, 17)), torch.zeros(33, 9)], dict(accum=False), [2])
+    both('gemm', be, [R(3, 10), R(1, 10), torch.zeros(3, 1)], {}, [2])
+
+
+# ----------------------------------------------------------------------------------------------- conversions
+def test_convert_and_colsum(be):
+    x = R(77, 130)
+    both('convert', be, [x], dict(dst=torch.zeros(77, 136, dtype=torch.bfloat16)[:, :130], dstT=torch.zeros(130, 80, dtype=torch.bfloat16)[:, :77]),
+         ['dst', 'dstT'], tol=1e-2)
+    both('convert', be, [R(64, 256)], dict(dst=torch.zeros(64, 256, dtype=torch.bfloat16)), ['dst'], tol=1e-2)
+    xb = R(5, 26, 40)
+    both('convert', be, [xb], dict(dstT=torch.zeros(5, 40, 32)[:, :, :26]), ['dstT'])
+    both('convert', be, [bf(R(40, 24))], dict(dst=torch.zeros(40, 24)), ['dst'])
+    both('colsum', be, [R(1000, 70), torch.zeros(70)], {}, [1], tol=1e-5)
+    both('colsum', be, [bf(R(300, 64)), R(64)], {}, [1], tol=1e-3)
+
+
+# ----------------------------------------------------------------------------------------------- norm family
+@pytest.mark.parametrize('D', [64, 52, 1024, 1536, 2048])
+@pytest.mark.parametrize('pre,post', [(True, False), (False, False), (False, True)])
+def test_norm_fwd_bwd(be, D, pre, post):
+    rows = 37
+    x, res = R(rows, D), R(rows, D)
+    gamma, beta = 1 + 0.1 * R(D), 0.1 * R(D)
+    stats = torch.zeros(rows, 2)
+    both('norm_fwd', be, [x, gamma, beta], dict(y=torch.zeros(rows, D), y2=torch.zeros(rows, D + 8, dtype=torch.bfloat16)[:, :D],
+                                                 res=res, stats=stats, pre_tanh=pre, post_tanh=post), ['y', 'stats'], tol=2e-5)
+    EM.norm_fwd(x, gamma, beta, res=res, stats=stats, pre_tanh=pre, post_tanh=post)
+    dy = R(rows, D)
+    both('norm_bwd', be, [dy, x, gamma, beta, stats], dict(dx=R(rows, D), res=res, dgamma=R(D), dbeta=R(D), pre_tanh=pre,
+                                                           post_tanh=post, dx_accum=True), ['dx', 'dgamma', 'dbeta'], tol=3e-5)
+    # fused-tanh input (GEMM epilogue produced tanh): backward still applies (1-x^2)
+    t = torch.tanh(x)
+    EM.norm_fwd(t, gamma, beta, stats=stats)
+    both('norm_bwd', be, [dy, bf(t), gamma, beta, stats], dict(dx=torch.zeros(rows, D, dtype=torch.bfloat16), dgamma=torch.zeros(D),
+                                                               dbeta=torch.zeros(D), in_is_tanh=True), ['dx'], tol=2e-2)
+
+
+def test_norm_strided_slices(be):
+    D, rows = 96, 12
+    big = R(rows, 4 * D)
+    gamma, beta = 1 + 0.1 * R(D), 0.1 * R(D)
+    both('norm_fwd', be, [big[:, D:2 * D], gamma, beta], dict(y=torch.zeros(rows, 3, D)[:, 1], stats=torch.zeros(rows, 2), post_tanh=True),
+         ['y', 'stats'], tol=2e-5)
+
+
+# ----------------------------------------------------------------------------------------------- LSTM cell
+@pytest.mark.parametrize('H', [64, 1024, 1536])
+def test_lstm_cell(be, H):
+    B_ = 9
+    gates = R(3, B_, 4 * H)
+    c_prev = R(B_, H)
+    kw = dict(h_out=torch.zeros(B_, H), row_bias=R(B_, 2, 4 * H)[:, 1], bias=R(4 * H), h2=torch.zeros(B_, H + 40, dtype=torch.bfloat16)[:, 8:8 + H],
+              h3=torch.zeros(B_, 2 * H)[:, H:])
+    both('lstm_cell_fwd', be, [gates, c_prev, torch.zeros(B_, H)], kw, [0, 2, 'h_out', 'h3'], tol=1e-5)
+    acts = gates[0].clone()
+    EM.lstm_cell_fwd(gates.clone(), c_prev, torch.zeros(B_, H))
+    g2 = gates.clone()
+    c_new = torch.zeros(B_, H)
+    EM.lstm_cell_fwd(g2, c_prev, c_new)
+    acts = g2[0].contiguous()
+    kw = dict(dgates=torch.zeros(B_, 4 * H), dgates2=torch.zeros(B_, 4 * H + 16, dtype=torch.bfloat16)[:, :4 * H],
+              dgatesT=torch.zeros(4 * H, 5 * B_)[:, 2 * B_:3 * B_], dh2=R(B_, 3 * H)[:, H:2 * H])
+    both('lstm_cell_bwd', be, [acts, c_prev, c_new, R(B_, 2 * H)[:, :H], R(B_, H), torch.zeros(B_, H)], kw, [5, 'dgates', 'dgatesT'], tol=1e-5)
+
+
+# ----------------------------------------------------------------------------------------------- softmax
+@pytest.mark.parametrize('shape,dim', [((4, 936, 26), 1), ((4, 26, 936), 2), ((3, 26, 5), 1), ((6, 26, 26), 2), ((7, 5, 1), 1)])
+@pytest.mark.parametrize('mask_mode', [0, 1, 2])
+def test_softmax(be, shape, dim, mask_mode):
+    x = R(*shape, scale=3.0)
+    mask = (R(*shape) > -0.5).float()
+    mask[0] = 0          # a fully masked slice -> uniform rows (sublayer.py:70-72)
+    kw = dict(scale=0.37, mask=mask if mask_mode else None, mask_mode=mask_mode)
+    both('softmax_fwd', be, [x, torch.zeros(*shape), dim], kw, [1], tol=1e-6)
+    both('softmax_bwd', be, [x, R(*shape), torch.zeros(*shape), dim], kw, [2], tol=1e-5)
+
+
+# ----------------------------------------------------------------------------------------------- node attention
+@pytest.mark.parametrize('nh,P,H,rpn', [(2, 5, 1024, 1), (2, 8, 64, 1), (1, 26, 64, 1), (2, 5, 64, 5)])
+def test_node_attn(be, nh, P, H, rpn):
+    nodes, rows = 6, 6 * rpn
+    Kp, Vp, qp = R(nh, nodes, P, H), R(nh, nodes, P, H), R(rows, nh * H)
+    alpha = torch.zeros(rows, nh * P)
+    both('node_attn_fwd', be, [Kp, Vp, qp, alpha, torch.zeros(rows, nh * H + 8)[:, :nh * H], rpn], {}, [3, 4], tol=2e-5)
+    if rpn == 1:
+        EM.node_attn_fwd(Kp, Vp, qp, alpha, torch.zeros(rows, nh * H), 1)
+        both('node_attn_bwd', be, [Kp, Vp, qp, alpha, R(rows, nh * H), torch.zeros(rows, nh * H), R(nh, nodes, P, H), R(nh, nodes, P, H)],
+             dict(dalpha_ext=R(rows, nh * P)), [5, 6, 7], tol=3e-5)
+
+
+# ----------------------------------------------------------------------------------------------- embedding & co
+def test_embedding_mean_elementwise(be):
+    V_, W = 50, 20
+    table = R(V_, W)
+    ids = torch.randint(0, V_, (4, 9))
+    both('embedding_gather', be, [table, ids[:, 3]], dict(out=torch.zeros(4, 64)[:, 8:28], out2=torch.zeros(4, 24, dtype=torch.bfloat16)[:, :W]),
+         ['out'], tol=1e-6)
+    both('embedding_scatter_add', be, [torch.zeros(V_, W), ids.reshape(-1), R(36, 40)[:, 10:30]], {}, [0], tol=1e-5)
+    x = R(5, 8, 64)
+    both('mean_nodes_fwd', be, [x, torch.zeros(5, 128)[:, 64:]], {}, [1], tol=1e-6)
+    both('mean_nodes_bwd', be, [R(5, 128)[:, :64], R(5, 8, 64)], {}, [1], tol=1e-6)
+    both('axpby', be, [R(1000), 0.5, R(1000), 2.0], {}, [2], tol=1e-6)
+    both('add_rowbcast', be, [R(6, 26, 32), R(26, 32), torch.zeros(6, 26, 32)], {}, [2], tol=1e-6)
+    both('relu_', be, [R(999)], {}, [0], tol=0)
+    both('mul', be, [R(100), R(100), torch.zeros(100)], {}, [2], tol=1e-6)
+
+
+def test_dropout_statistics_and_mask_reuse(be):
+    n, p = 1 << 20, 0.3
+    x = torch.ones(n, device=DEV)
+    y = torch.empty_like(x)
+    be.dropout(x, y, (p, 1234, 0))
+    keep = float((y > 0).float().mean())
+    assert abs(keep - (1 - p)) < 5e-3
+    assert torch.allclose(y[y > 0], torch.full_like(y[y > 0], 1 / (1 - p)))
+    y2 = torch.empty_like(x)
+    be.dropout(x, y2, (p, 1234, 0))
+    assert torch.equal(y, y2)                                   # same (seed, offset) -> same mask (backward reuses it)
+    be.dropout(x, y2, (p, 1235, 0))
+    assert not torch.equal(y, y2)
+    # norm_fwd / norm_bwd regenerate identical masks: d(sum y)/dx is zero exactly where y was dropped
+    D = 256
+    xx = torch.randn(64, D, device=DEV)
+    g, b = torch.ones(D, device=DEV), torch.zeros(D, device=DEV)
+    yy, st = torch.empty_like(xx), torch.empty(64, 2, device=DEV)
+    be.norm_fwd(xx, g, b, y=yy, stats=st, drop=(p, 77, 5 << 32))
+    dg, db = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+    be.norm_bwd(torch.ones_like(xx), xx, g, b, st, dx=torch.empty_like(xx), dgamma=dg, dbeta=db, drop=(p, 77, 5 << 32))
+    assert torch.allclose(db, (yy != 0).float().sum(0) / (1 - p), atol=1e-3)
+
+
+# ----------------------------------------------------------------------------------------------- vocab / beam
+@pytest.mark.parametrize('V_', [37, 10547])
+def test_vocab_rows(be, V_):
+    rows = 20
+    lg = R(rows, V_, scale=2.0)
+    lg[3, 5] = lg[3, 9] = lg[3].max() + 1            # tie -> lowest index
+    both('row_argmax', be, [lg, torch.zeros(rows, 3, dtype=torch.int64)[:, 1]], {}, [], int_outs=[1])
+    both('log_softmax', be, [lg, torch.zeros(rows, V_)], {}, [1], tol=2e-6)
+    B_, L = 4, 5
+    lg3 = R(B_, L, V_, scale=2.0)
+    tg = torch.randint(0, V_, (B_, L))
+    lens = torch.tensor([5, 3, 1, 4], dtype=torch.int32)
+    both('ce_masked', be, [lg3, tg, lens, torch.zeros(1), torch.zeros(B_, L, V_), 1.0 / 13], {}, [3, 4], tol=2e-6)
+
+
+@pytest.mark.parametrize('V_,k', [(37, 5), (10547, 5), (10547, 3), (41, 1), (500, 8)])
+def test_beam_kernels(be, V_, k):
+    B_, beam = 6, k
+    rows = B_ * beam
+    lg = R(rows, V_, scale=2.0)
+    last = torch.randint(0, 6, (rows,))
+    end = 2
+    tl, ti = torch.zeros(rows, k), torch.zeros(rows, k, dtype=torch.int64)
+    getattr(EM, 'beam_topk')(lg, last, end, k, tl, ti)
+    gtl, gti = torch.zeros(rows, k, device=DEV), torch.zeros(rows, k, dtype=torch.int64, device=DEV)
+    be.beam_topk(lg.to(DEV), last.to(DEV), end, k, gtl, gti)
+    live = last != end
+    assert torch.equal(ti[live], gti.cpu()[live])
+    assert (tl[live] - gtl.cpu()[live]).abs().max() < 1e-5
+    assert torch.equal(gti.cpu()[~live][:, 0], torch.full((int((~live).sum()),), end))
+    assert torch.all(gtl.cpu()[~live][:, 0] == 0) and (k == 1 or torch.all(torch.isinf(gtl.cpu()[~live][:, 1:])))
+    # merge on the device's own top-k (the -inf tail of forced rows may pick different dummy ids than torch.topk)
+    tl, ti = gtl.cpu(), gti.cpu()
+    last_lp = R(B_, beam)
+    outs = [torch.zeros(B_, beam), torch.zeros(B_, beam, dtype=torch.int64), torch.zeros(B_, beam, dtype=torch.int64)]
+    both('beam_merge', be, [tl, ti, last_lp, B_, beam, k, outs[0], outs[1], outs[2], None, end], {}, [6], int_outs=[7, 8])
+    src = R(rows, 72)
+    bp = torch.randint(0, beam, (B_, beam))
+    both('beam_gather', be, [src, torch.zeros(rows, 72), bp, B_, beam], {}, [1], tol=0)
+    both('beam_gather', be, [bf(R(rows, 80))[:, :72], torch.zeros(rows, 80, dtype=torch.bfloat16)[:, :72], bp, B_, beam], {}, [1], tol=0)
+    S = 7
+    preds = torch.randint(0, V_, (S, B_, beam))
+    backs = torch.randint(0, beam, (S - 1, B_, beam))
+    both('beam_backtrack', be, [preds, backs, S, B_, beam, torch.zeros(B_, beam, S, dtype=torch.int64)], {}, [], int_outs=[5])
+    both('beam_backtrack', be, [preds, backs, 4, B_, beam, torch.zeros(B_, beam, 4, dtype=torch.int64)], {}, [], int_outs=[5])
