@@ -40,6 +40,7 @@ def parse():
     ap.add_argument('--no-decode', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--graph', type=int, default=int(os.environ.get('DLSG_GRAPH', '1')))
+    ap.add_argument('--profile-step', action='store_true', help='run W warm-up steps, then ONE eager step inside cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)')
     return ap.parse_args()
 
 
@@ -160,10 +161,11 @@ def main():
         net = M.CapGnnModel(args, synth.Vocab(V_MSR)).to(dev)
     net.train()
     model = net
-    if world > 1:
+    use_graph = bool(a.graph) and not a.profile_step
+    if world > 1 and not use_graph:
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], find_unused_parameters=True,
                                                           gradient_as_bucket_view=True)
-    opt = torch.optim.Adam(net.parameters(), lr=1.6e-4, betas=(0.5, 0.9), fused=True)
+    opt = torch.optim.Adam(net.parameters(), lr=1.6e-4, betas=(0.5, 0.9), fused=True, capturable=use_graph)
     frames, regions, caps, lens = synth.make_inputs(B, args, V_MSR, seed=12 + rank)
     h_fr, h_rg, h_cp = frames.pin_memory(), regions.pin_memory(), caps.pin_memory()
     d_fr, d_rg, d_cp = h_fr.to(dev), h_rg.to(dev), h_cp.to(dev)
@@ -197,23 +199,52 @@ def main():
             ms = float(t.item())
         return ms / n
 
-    # ---- device-resident timing
-    for _ in range(a.warmup):
+    if a.profile_step:
+        for _ in range(a.warmup):
+            step(d_fr, d_rg, d_cp)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
         step(d_fr, d_rg, d_cp)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+    # ---- device-resident timing
+    eager_ms = None
+    if use_graph:
+        from dlsg.graphs import GraphedTrainStep
+        if world == 1:
+            for _ in range(2):
+                step(d_fr, d_rg, d_cp)
+            eager_ms = timed(lambda: step(d_fr, d_rg, d_cp), 3)
+        l0 = be.launches
+        gs = GraphedTrainStep(net, opt, d_fr, d_rg, d_cp, lens, 26, 1.0,
+                              process_group=(dist.group.WORLD if dist is not None else None), warmup=(0 if world == 1 else 3))
+        launches = be.launches - l0
+        run_dev = lambda: gs()
+
+        def e2e_step():
+            gs.load(h_fr, h_rg, h_cp)
+            return gs().item()
+    else:
+        launches = None
+        run_dev = lambda: step(d_fr, d_rg, d_cp)
+
+        def e2e_step():
+            fr = h_fr.to(dev, non_blocking=True)
+            rg = h_rg.to(dev, non_blocking=True)
+            cp = h_cp.to(dev, non_blocking=True)
+            return step(fr, rg, cp).item()
+    for _ in range(a.warmup):
+        run_dev()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = be.launches
-    ms = timed(lambda: step(d_fr, d_rg, d_cp), a.steps)
-    launches = (be.launches - l0) // a.steps
+    ms = timed(run_dev, a.steps)
+    if launches is None:
+        launches = (be.launches - l0) // a.steps
     clocks = sampler.stop() if rank == 0 else None
-
     # ---- end-to-end: host pinned inputs -> H2D -> step -> loss.item()
-    def e2e_step():
-        fr = h_fr.to(dev, non_blocking=True)
-        rg = h_rg.to(dev, non_blocking=True)
-        cp = h_cp.to(dev, non_blocking=True)
-        return step(fr, rg, cp).item()
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, a.steps)
@@ -285,7 +316,8 @@ def main():
                            'l2': 'inputs (490 MB regions/step) exceed the 126 MB L2; no explicit flush'},
                 'e2e': {'value': world * B / (ms_e2e * 1e-3), 'unit': 'clips/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                         'ms_per_step': ms_e2e},
-                'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu}
+                'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
+                'cuda_graph': use_graph, 'eager_ms_per_step': eager_ms}
         line.update(extra)
         print(json.dumps(line))
     if dist is not None:

@@ -135,8 +135,10 @@ log_softmax_kernel(const float* __restrict__ logits, int64_t ld, int V, float* _
 // dlogits = (softmax - onehot) * inv_count for counted rows, 0 for padded rows.
 __global__ void __launch_bounds__(256)
 ce_masked_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targets, const int32_t* __restrict__ lens,
-                 int L, int V, float* __restrict__ loss_sum, float* __restrict__ dlogits, float inv_count) {
+                 int L, int V, float* __restrict__ loss_sum, float* __restrict__ dlogits, float inv_count_host,
+                 const float* __restrict__ inv_count_dev) {
   __shared__ float red[32];
+  const float inv_count = inv_count_dev ? *inv_count_dev : inv_count_host;
   const int row = blockIdx.x, b = row / L, t = row % L;
   const float* x = logits + (int64_t)row * V;
   if (t >= lens[b]) {
@@ -332,9 +334,9 @@ int dlsg_log_softmax(const float* logits, int64_t ld, int32_t rows, int32_t V, f
   return check_launch("log_softmax_kernel");
 }
 int dlsg_ce_masked(const float* logits, const int64_t* targets, const int32_t* lens, int32_t B, int32_t L, int32_t V,
-                   float* loss_sum, float* dlogits, float inv_count, void* stream) {
+                   float* loss_sum, float* dlogits, float inv_count, const float* inv_count_dev, void* stream) {
   if (B * L <= 0) return 0;
-  ce_masked_kernel<<<B * L, 256, 0, (cudaStream_t)stream>>>(logits, targets, lens, L, V, loss_sum, dlogits, inv_count);
+  ce_masked_kernel<<<B * L, 256, 0, (cudaStream_t)stream>>>(logits, targets, lens, L, V, loss_sum, dlogits, inv_count, inv_count_dev);
   return check_launch("ce_masked_kernel");
 }
 int dlsg_beam_topk(const float* logits, int64_t ld, int32_t rows, int32_t V, const int64_t* last, int32_t end_index,

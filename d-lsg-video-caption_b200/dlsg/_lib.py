@@ -103,7 +103,7 @@ SIGNATURES = {
     'dlsg_mul': (i32, [vp, vp, vp, i64, vp]),
     'dlsg_row_argmax': (i32, [vp, i64, i32, i32, vp, i64, vp]),
     'dlsg_log_softmax': (i32, [vp, i64, i32, i32, vp, i64, vp]),
-    'dlsg_ce_masked': (i32, [vp, vp, vp, i32, i32, i32, vp, vp, f32, vp]),
+    'dlsg_ce_masked': (i32, [vp, vp, vp, i32, i32, i32, vp, vp, f32, vp, vp]),
     'dlsg_beam_topk': (i32, [vp, i64, i32, i32, vp, i32, i32, vp, vp, i32, vp]),
     'dlsg_beam_merge': (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp]),
     'dlsg_beam_gather': (i32, [vp, vp, vp, i32, i32, i32, vp]),

@@ -112,6 +112,7 @@ class WeightCache:
 
     def __init__(self):
         self._c = {}
+        self.force = False      # True while a CUDA graph is being captured: refresh kernels must be recorded every time
 
     def get(self, w, transpose=False, key=None):
         if _PRECISION == 'fp32':
@@ -119,7 +120,7 @@ class WeightCache:
         k = (id(w) if key is None else key, transpose)
         ver = (w._version, w.data_ptr(), tuple(w.shape))
         hit = self._c.get(k)
-        if hit is not None and hit[0] == ver:
+        if hit is not None and hit[0] == ver and not self.force:
             return hit[1]
         src = w.detach()
         out = op_empty((src.shape[1],), src.shape[0], src) if transpose else op_empty((src.shape[0],), src.shape[1], src)
@@ -134,7 +135,7 @@ class WeightCache:
         """Cache an arbitrary packed operand (e.g. concatenated LSTM weights) keyed on part versions."""
         ver = (_PRECISION,) + tuple(versions)
         hit = self._c.get(key)
-        if hit is not None and hit[0] == ver:
+        if hit is not None and hit[0] == ver and not self.force:
             return hit[1]
         val = builder()
         self._c[key] = (ver, val)

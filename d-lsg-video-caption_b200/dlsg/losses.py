@@ -8,22 +8,25 @@ from . import ops
 
 class _PackedCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, targets, lens_t, inv_count):
+    def forward(ctx, logits, targets, lens_t, inv_count, inv_dev=None):
         logits = logits if logits.is_contiguous() else logits.contiguous()
         loss = torch.zeros(1, dtype=torch.float32, device=logits.device)
         dlogits = torch.empty_like(logits)
-        ops.backend().ce_masked(logits, targets.contiguous(), lens_t, loss, dlogits, inv_count)
+        ops.backend().ce_masked(logits, targets.contiguous(), lens_t, loss, dlogits, inv_count, inv_dev)
         ctx.save_for_backward(dlogits)
         return loss[0]
 
     @staticmethod
     def backward(ctx, g):
         (dlogits,) = ctx.saved_tensors
-        return dlogits * g, None, None, None
+        return dlogits * g, None, None, None, None
 
 
-def packed_cross_entropy(outputs, targets, cap_lens):
-    """outputs (B,L,V) raw logits, targets (B,L) int64, cap_lens: python ints.  Mean NLL over sum(cap_lens) tokens."""
+def packed_cross_entropy(outputs, targets, cap_lens, inv_count_dev=None):
+    """outputs (B,L,V) raw logits, targets (B,L) int64, cap_lens: python ints (or a device int32 tensor together with
+    inv_count_dev = 1/sum(lens) as a 1-element device tensor: graph-capturable form).  Mean NLL over the tokens."""
+    if torch.is_tensor(cap_lens):
+        return _PackedCE.apply(outputs, targets[:, :outputs.shape[1]], cap_lens, 0.0, inv_count_dev)
     lens_t = torch.as_tensor(list(cap_lens), dtype=torch.int32).to(outputs.device, non_blocking=True)
     L = outputs.shape[1]
     n = sum(min(int(c), L) for c in cap_lens)

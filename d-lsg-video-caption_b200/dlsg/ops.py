@@ -359,12 +359,12 @@ class CudaBackend:
         self.launches += 1
         L.check(self.lib.dlsg_log_softmax(logits.data_ptr(), logits.stride(0), rows, V, out.data_ptr(), out.stride(0), _stream()), 'log_softmax')
 
-    def ce_masked(self, logits, targets, lens, loss_sum, dlogits, inv_count):
+    def ce_masked(self, logits, targets, lens, loss_sum, dlogits, inv_count, inv_count_dev=None):
         B, Lw, V = logits.shape
         assert logits.is_contiguous() and targets.is_contiguous() and lens.dtype == torch.int32
         self.launches += 1
         L.check(self.lib.dlsg_ce_masked(logits.data_ptr(), targets.data_ptr(), lens.data_ptr(), B, Lw, V,
-                                        loss_sum.data_ptr(), _ptr(dlogits), inv_count, _stream()), 'ce_masked')
+                                        loss_sum.data_ptr(), _ptr(dlogits), inv_count, _ptr(inv_count_dev), _stream()), 'ce_masked')
 
     def beam_topk(self, logits, last, end_index, k, top_lp, top_id, normalize=True):
         rows, V = logits.shape

@@ -175,7 +175,8 @@ int dlsg_log_softmax(const float* logits, int64_t ld, int32_t rows, int32_t V, f
 /* masked CE over (B,L,V): rows with t < len[b] count.  loss_sum/count are ACCUMULATED (zero first).
  * dlogits (may be NULL) = (softmax - onehot)*gscale/count_total for counted rows, 0 otherwise.   */
 int dlsg_ce_masked(const float* logits, const int64_t* targets, const int32_t* lens, int32_t B, int32_t L, int32_t V,
-                   float* loss_sum, float* dlogits, float inv_count, void* stream);
+                   float* loss_sum, float* dlogits, float inv_count, const float* inv_count_dev /* overrides if non-NULL */,
+                   void* stream);
 
 /* ---- beam search (allennlp_beamsearch.py:127,186-260,272-292) ------------------------------- */
 /* per row: log-softmax, force <end> if last==end (:186-190), top-k (value desc, lowest index on ties) */

@@ -260,8 +260,10 @@ class CpuEmulBackend:
         self.launches += 1
         out.copy_(torch.log_softmax(logits, 1))
 
-    def ce_masked(self, logits, targets, lens, loss_sum, dlogits, inv_count):
+    def ce_masked(self, logits, targets, lens, loss_sum, dlogits, inv_count, inv_count_dev=None):
         self.launches += 1
+        if inv_count_dev is not None:
+            inv_count = float(inv_count_dev)
         B, Lw, V = logits.shape
         lp = torch.log_softmax(logits, -1)
         m = (torch.arange(Lw).unsqueeze(0) < lens.unsqueeze(1)).float()
