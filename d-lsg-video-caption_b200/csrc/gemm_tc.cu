@@ -1,12 +1,14 @@
 // tcgen05 / TMA / TMEM GEMM for sm_100a:  C(P,Q) = A(P,K) . B(Q,K)^T, bf16 operands, fp32 accumulate.
 //
-// One CTA per 128 x BN output tile (BN in {32,64,128,256}), 6 warps:
+// Persistent CTAs (one per SM) walk 128 x BN output tiles (BN in {32,64,128,256}); TMEM holds two accumulator
+// stages so the epilogue of one tile overlaps the main loop of the next.  6 warps:
 //   warp 0      : TMA producer  (cp.async.bulk.tensor.3d, 128B swizzle, mbarrier complete_tx)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, kind::f16)
 //   warps 2..5  : epilogue - tcgen05.ld 32x32b.x32 from their TMEM lane quarter (warp_id % 4),
 //                 bias / tanh / scale, smem-transposed coalesced stores (or direct transposed stores)
 // smem ring of STAGES x {A 128x64 bf16, B BNx64 bf16}; full/empty mbarriers; tcgen05.commit frees slots.
-// grid = (P tiles, Q tiles, batch*splitk).  Every spin-wait is bounded and traps instead of hanging.
+// tile index -> (batch*splitk, P tile, Q tile) with the Q tile fastest.  Every spin-wait is bounded and traps
+// instead of hanging.
 #include <cuda.h>
 #include "common.cuh"
 
@@ -27,6 +29,7 @@ struct TcParams {
   int d_dtype, do_tanh, accum;
   float alpha;
   int splitk, kb_total, kb_per_split;
+  int ntm, ntn, tiles_total;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -87,15 +90,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 }
 
 template <int BN> struct TcCfg {
-  static constexpr int STAGES = (BN >= 128) ? 4 : 6;
+  static constexpr int STAGES = (BN >= 256) ? 4 : 6;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_BYTES = 4 * 32 * EPI_PAD * 4;
   static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;  // +1024 alignment slack
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int ACC_COLS = BN < 32 ? 32 : BN;                          // one accumulator stage
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;                              // double-buffered (<= 512)
 };
 
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Persistent: grid = min(#tiles, #SMs); CTA walks tiles t = blockIdx.x + i*gridDim.x (n-tile fastest so that the CTAs
+// running concurrently share A row-panels and the whole weight matrix in L2).  Two TMEM accumulator stages let the
+// epilogue of tile i overlap the TMA/MMA main loop of tile i+1.
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams prm) {
@@ -105,22 +118,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* tiles = smem;
   float* epi = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
-  // bars[0..S) full, bars[S..2S) empty, bars[2S] tmem_full ; then tmem base address slot
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 1);
+  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty ; then the TMEM base-address slot
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::STAGES;
+  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
+  uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p0 = blockIdx.x * BM, q0 = blockIdx.y * BN;
-  const int zb = blockIdx.z / prm.splitk, zs = blockIdx.z % prm.splitk;
-  const int kb_begin = zs * prm.kb_per_split;
-  const int kb_end = min(prm.kb_total, kb_begin + prm.kb_per_split);
-  const int nkb = kb_end - kb_begin;
+  const int ntn = prm.ntn, ntm = prm.ntm;
+  const int tiles_total = prm.tiles_total;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(smem_u32(&bars[s]), 1);
-      mbar_init(smem_u32(&bars[Cfg::STAGES + s]), 1);
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    mbar_init(smem_u32(&bars[2 * Cfg::STAGES]), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tfull_bar[s]), 1);
+      mbar_init(smem_u32(&tempty_bar[s]), 4);          // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -139,15 +156,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
       int s = 0; uint32_t ph = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(smem_u32(&bars[Cfg::STAGES + s]), ph ^ 1);
-        const uint32_t full = smem_u32(&bars[s]);
-        mbar_expect_tx(full, Cfg::STAGE_BYTES);
-        const uint32_t a_dst = smem_u32(tiles + s * Cfg::STAGE_BYTES);
-        const int kc = (kb_begin + kb) * BK;
-        tma_load_3d(a_dst, &tmA, full, kc, p0, zb);
-        tma_load_3d(a_dst + Cfg::A_BYTES, &tmB, full, kc, q0, zb);
-        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+      for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+        const int tn = tile % ntn, tm = (tile / ntn) % ntm, z = tile / (ntn * ntm);
+        const int zb = z / prm.splitk, zs = z % prm.splitk;
+        const int kb_begin = zs * prm.kb_per_split;
+        const int nkb = min(prm.kb_total, kb_begin + prm.kb_per_split) - kb_begin;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+          const uint32_t full = smem_u32(&full_bar[s]);
+          mbar_expect_tx(full, Cfg::STAGE_BYTES);
+          const uint32_t a_dst = smem_u32(tiles + s * Cfg::STAGE_BYTES);
+          const int kc = (kb_begin + kb) * BK;
+          tma_load_3d(a_dst, &tmA, full, kc, tm * BM, zb);
+          tma_load_3d(a_dst + Cfg::A_BYTES, &tmB, full, kc, tn * BN, zb);
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -156,91 +179,141 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // instruction descriptor: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int s = 0; uint32_t ph = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(smem_u32(&bars[s]), ph);
+      int acc = 0; uint32_t acc_ph = 0;
+      for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+        const int z = tile / (ntn * ntm);
+        const int zs = z % prm.splitk;
+        const int kb_begin = zs * prm.kb_per_split;
+        const int nkb = min(prm.kb_total, kb_begin + prm.kb_per_split) - kb_begin;
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_ph ^ 1);           // epilogue has drained this accumulator stage
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_addr = smem_u32(tiles + s * Cfg::STAGE_BYTES);
-        const uint64_t adesc = make_sw128_desc(a_addr);
-        const uint64_t bdesc = make_sw128_desc(a_addr + Cfg::A_BYTES);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(smem_u32(&full_bar[s]), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_addr = smem_u32(tiles + s * Cfg::STAGE_BYTES);
+          const uint64_t adesc = make_sw128_desc(a_addr);
+          const uint64_t bdesc = make_sw128_desc(a_addr + Cfg::A_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance 16 bf16 = 32 bytes inside the 128B swizzle row: +2 in the (addr>>4) field
-          umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 bytes inside the 128B swizzle row: +2 in the (addr>>4) field
+            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[s]));                      // frees the smem slot when the MMAs retire
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(smem_u32(&bars[Cfg::STAGES + s]));     // frees the smem slot when the MMAs retire
-        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        umma_commit(smem_u32(&tfull_bar[acc]));                      // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
       }
-      umma_commit(smem_u32(&bars[2 * Cfg::STAGES]));       // accumulator complete -> epilogue
     }
   } else {
     // ===== epilogue warps =====
     const int g = warp & 3;                                // TMEM lane quarter this warp may access
     float* st = epi + (warp - 2) * 32 * EPI_PAD;
-    mbar_wait(smem_u32(&bars[2 * Cfg::STAGES]), 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int p_row = p0 + g * 32 + lane;                  // this thread's accumulator row
     uint8_t* Dbase = reinterpret_cast<uint8_t*>(prm.D);
-    const int64_t doff = (int64_t)zb * prm.stride_d + (int64_t)zs * prm.stride_split;
-    const bool add_bias = (prm.bias_mode != 0) && (zs == 0);
-    float bias_p = 0.f;
-    if (add_bias && prm.bias_mode == 1 && p_row < prm.P) bias_p = prm.bias[p_row];
+    const bool bf16_out = prm.d_dtype != DLSG_F32;
+    // packed bf16x2 stores need 4-byte aligned pairs
+    const bool pair_ok = bf16_out && !prm.store_t && !prm.accum && (prm.ldd % 2 == 0) && ((prm.stride_d | prm.stride_split) % 2 == 0) &&
+                         ((reinterpret_cast<uintptr_t>(prm.D) & 3) == 0);
+    int acc = 0; uint32_t acc_ph = 0;
+    for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+      const int tn = tile % ntn, tm = (tile / ntn) % ntm, z = tile / (ntn * ntm);
+      const int zb = z / prm.splitk, zs = z % prm.splitk;
+      const int p0 = tm * BM, q0 = tn * BN;
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS) + ((uint32_t)(g * 32) << 16);
+      const int p_row = p0 + g * 32 + lane;                  // this thread's accumulator row
+      const int64_t doff = (int64_t)zb * prm.stride_d + (int64_t)zs * prm.stride_split;
+      const bool add_bias = (prm.bias_mode != 0) && (zs == 0);
+      float bias_p = 0.f;
+      if (add_bias && prm.bias_mode == 1 && p_row < prm.P) bias_p = prm.bias[p_row];
+      int nchunks = 0;
+      for (int c0 = 0; c0 < BN; c0 += 32) if (q0 + c0 < prm.Q) ++nchunks;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (q0 + c0 >= prm.Q) break;                         // warp-uniform
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)c0, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      float f[32];
+      for (int ci = 0; ci < nchunks; ++ci) {
+        const int c0 = ci * 32;
+        uint32_t v[32];
+        tmem_ld32(tmem_d + (uint32_t)c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (ci == nchunks - 1) {
+          // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty_bar[acc])) : "memory");
+        }
+        float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * prm.alpha + bias_p;
-      if (prm.store_t) {
-        // element (p,q) -> D[q*ldd + p]: lanes are consecutive p -> coalesced
-        if (p_row < prm.P) {
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * prm.alpha + bias_p;
+        if (prm.store_t) {
+          // element (p,q) -> D[q*ldd + p]: lanes are consecutive p -> coalesced
+          if (p_row < prm.P) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int q = q0 + c0 + j;
-            if (q < prm.Q) {
-              float x = f[j];
-              if (add_bias && prm.bias_mode == 2) x += prm.bias[q];
-              if (prm.do_tanh) x = tanhf(x);
-              const int64_t idx = doff + (int64_t)q * prm.ldd + p_row;
-              if (prm.d_dtype == DLSG_F32) {
-                float* d = reinterpret_cast<float*>(Dbase) + idx;
-                *d = prm.accum ? (*d + x) : x;
-              } else {
-                __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(Dbase) + idx;
-                *d = __float2bfloat16_rn(prm.accum ? (__bfloat162float(*d) + x) : x);
+            for (int j = 0; j < 32; ++j) {
+              const int q = q0 + c0 + j;
+              if (q < prm.Q) {
+                float x = f[j];
+                if (add_bias && prm.bias_mode == 2) x += prm.bias[q];
+                if (prm.do_tanh) x = bf16_out ? tanh_fast(x) : tanhf(x);
+                const int64_t idx = doff + (int64_t)q * prm.ldd + p_row;
+                if (!bf16_out) {
+                  float* d = reinterpret_cast<float*>(Dbase) + idx;
+                  *d = prm.accum ? (*d + x) : x;
+                } else {
+                  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(Dbase) + idx;
+                  *d = __float2bfloat16_rn(prm.accum ? (__bfloat162float(*d) + x) : x);
+                }
               }
             }
           }
-        }
-      } else {
-        // element (p,q) -> D[p*ldd + q]: transpose through smem so lanes walk q
+        } else {
+          // element (p,q) -> D[p*ldd + q]: transpose through smem so lanes walk q
 #pragma unroll
-        for (int j = 0; j < 32; ++j) st[lane * EPI_PAD + j] = f[j];
-        __syncwarp();
-        const int q = q0 + c0 + lane;
-        float bias_q = 0.f;
-        if (add_bias && prm.bias_mode == 2 && q < prm.Q) bias_q = prm.bias[q];
-        if (q < prm.Q) {
+          for (int j = 0; j < 32; ++j) st[lane * EPI_PAD + j] = f[j];
+          __syncwarp();
+          if (pair_ok && (q0 + c0 + 32 <= prm.Q)) {
+            // bf16 output: lane -> (row 2*it + lane/16, column pair 2*(lane%16)): 64 B contiguous per half-warp
+            const int cp = 2 * (lane & 15), rsel = lane >> 4;
+            const int q = q0 + c0 + cp;
+            float b0 = 0.f, b1 = 0.f;
+            if (add_bias && prm.bias_mode == 2) { b0 = prm.bias[q]; b1 = prm.bias[q + 1]; }
 #pragma unroll 4
-          for (int i = 0; i < 32; ++i) {
-            const int p = p0 + g * 32 + i;
-            if (p >= prm.P) break;
-            float x = st[i * EPI_PAD + lane] + bias_q;
-            if (prm.do_tanh) x = tanhf(x);
-            const int64_t idx = doff + (int64_t)p * prm.ldd + q;
-            if (prm.d_dtype == DLSG_F32) {
-              float* d = reinterpret_cast<float*>(Dbase) + idx;
-              *d = prm.accum ? (*d + x) : x;
-            } else {
-              __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(Dbase) + idx;
-              *d = __float2bfloat16_rn(prm.accum ? (__bfloat162float(*d) + x) : x);
+            for (int it = 0; it < 16; ++it) {
+              const int i = 2 * it + rsel;
+              const int p = p0 + g * 32 + i;
+              if (p < prm.P) {
+                float x0 = st[i * EPI_PAD + cp] + b0, x1 = st[i * EPI_PAD + cp + 1] + b1;
+                if (prm.do_tanh) { x0 = tanh_fast(x0); x1 = tanh_fast(x1); }
+                __nv_bfloat162 pk = __floats2bfloat162_rn(x0, x1);
+                *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(Dbase) + doff + (int64_t)p * prm.ldd + q) = pk;
+              }
+            }
+          } else {
+            const int q = q0 + c0 + lane;
+            float bias_q = 0.f;
+            if (add_bias && prm.bias_mode == 2 && q < prm.Q) bias_q = prm.bias[q];
+            if (q < prm.Q) {
+#pragma unroll 4
+              for (int i = 0; i < 32; ++i) {
+                const int p = p0 + g * 32 + i;
+                if (p >= prm.P) break;
+                float x = st[i * EPI_PAD + lane] + bias_q;
+                if (prm.do_tanh) x = bf16_out ? tanh_fast(x) : tanhf(x);
+                const int64_t idx = doff + (int64_t)p * prm.ldd + q;
+                if (!bf16_out) {
+                  float* d = reinterpret_cast<float*>(Dbase) + idx;
+                  *d = prm.accum ? (*d + x) : x;
+                } else {
+                  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(Dbase) + idx;
+                  *d = __float2bfloat16_rn(prm.accum ? (__bfloat162float(*d) + x) : x);
+                }
+              }
             }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -287,6 +360,29 @@ static int make_map(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t K, i
   return 0;
 }
 
+// sum split-K partials (S, batch, M, N) fp32 from the workspace and apply the epilogue into the user's D
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int S, int batch, int M, int N, void* __restrict__ D, int d_dtype, int64_t ldd,
+                     int64_t stride_d, const float* __restrict__ bias, int flags, float alpha) {
+  const int64_t per = (int64_t)M * N, total = per * batch;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(e / per);
+    const int64_t r = e % per;
+    const int m = (int)(r / N), n = (int)(r % N);
+    float x = 0.f;
+    for (int s = 0; s < S; ++s) x += ws[(int64_t)s * total + e];
+    x *= alpha;
+    if (bias) {
+      if (flags & DLSG_EPI_BIAS_N) x += bias[n];
+      if (flags & DLSG_EPI_BIAS_M) x += bias[m];
+    }
+    if (flags & DLSG_EPI_TANH) x = tanhf(x);
+    const int64_t idx = (int64_t)b * stride_d + ((flags & DLSG_EPI_STORE_T) ? ((int64_t)n * ldd + m) : ((int64_t)m * ldd + n));
+    if (flags & DLSG_EPI_ACCUM) x += ld_as_float(D, d_dtype, idx);
+    st_from_float(D, d_dtype, idx, x);
+  }
+}
+
 template <int BN>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& prm, dim3 grid, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
@@ -300,7 +396,44 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcParam
   return check_launch("gemm_tc_kernel");
 }
 
+static int gemm_tc_direct(const dlsg_gemm_t* g, cudaStream_t st);
+
 int gemm_tc_dispatch(const dlsg_gemm_t* g, cudaStream_t st) {
+  // Automatic split-K for skinny problems: too few 128-row tiles to fill 148 SMs and a long K loop
+  // (the per-step recurrent GEMMs: M = batch = 64, weights streamed once).
+  if (g->splitk <= 1 && g->workspace && g->M > 0 && g->N > 0) {
+    const int batch = g->batch < 1 ? 1 : g->batch;
+    const bool swap = (g->M <= 64 && g->N > g->M);
+    const int P = swap ? g->N : g->M, Q = swap ? g->M : g->N;
+    const int bn = Q <= 32 ? 32 : (Q <= 64 ? 64 : 128);
+    const int64_t tiles = (int64_t)((P + BM - 1) / BM) * ((Q + bn - 1) / bn) * batch;
+    const int kb = (g->K + BK - 1) / BK;
+    if (tiles * 2 <= kNumSM && kb >= 8) {
+      int S = (int)((kNumSM + tiles - 1) / tiles);
+      if (S > kb / 4) S = kb / 4;
+      if (S > 16) S = 16;
+      const int per = (kb + S - 1) / S;
+      S = (kb + per - 1) / per;
+      const int64_t need = (int64_t)S * batch * g->M * g->N * 4;
+      if (S >= 2 && need <= g->workspace_bytes) {
+        dlsg_gemm_t part = *g;
+        part.D = g->workspace; part.d_dtype = DLSG_F32; part.bias = nullptr; part.flags = 0; part.alpha = 1.f;
+        part.ldd = g->N; part.stride_d = (int64_t)g->M * g->N; part.splitk = S;
+        part.stride_split = (int64_t)batch * g->M * g->N; part.workspace = nullptr;
+        if (int rc = gemm_tc_direct(&part, st)) return rc;
+        const int64_t total = (int64_t)batch * g->M * g->N;
+        int64_t blocks = (total + 255) / 256;
+        if (blocks > kNumSM * 8) blocks = kNumSM * 8;
+        splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>((const float*)g->workspace, S, batch, g->M, g->N, g->D, g->d_dtype,
+                                                               g->ldd, g->stride_d, g->bias, g->flags, g->alpha);
+        return check_launch("splitk_reduce_kernel");
+      }
+    }
+  }
+  return gemm_tc_direct(g, st);
+}
+
+static int gemm_tc_direct(const dlsg_gemm_t* g, cudaStream_t st) {
   DLSG_REQUIRE(g->a_dtype == DLSG_BF16 && g->b_dtype == DLSG_BF16, "gemm_tc: operands must be bf16");
   DLSG_REQUIRE(g->sak == 1 && g->sbk == 1, "gemm_tc: K must be the unit-stride axis of A and B");
   DLSG_REQUIRE(g->M > 0 && g->N > 0 && g->K > 0, "gemm_tc: empty problem");
@@ -343,8 +476,12 @@ int gemm_tc_dispatch(const dlsg_gemm_t* g, cudaStream_t st) {
   CUtensorMap ta, tb;
   if (make_map(&ta, Ap, P, g->K, ldp, batch, strp, BM)) return -1;
   if (make_map(&tb, Bq, Q, g->K, ldq, batch, strq, bn)) return -1;
-  dim3 grid(ptiles, (Q + bn - 1) / bn, batch * splitk);
-  DLSG_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm_tc: grid too large");
+  prm.ntm = ptiles;
+  prm.ntn = (Q + bn - 1) / bn;
+  const int64_t tiles_total = (int64_t)prm.ntm * prm.ntn * batch * splitk;
+  DLSG_REQUIRE(tiles_total < (1ll << 31), "gemm_tc: too many tiles");
+  prm.tiles_total = (int)tiles_total;
+  dim3 grid((unsigned)(tiles_total < kNumSM ? tiles_total : kNumSM));
   switch (bn) {
     case 32: return launch_tc<32>(ta, tb, prm, grid, st);
     case 64: return launch_tc<64>(ta, tb, prm, grid, st);

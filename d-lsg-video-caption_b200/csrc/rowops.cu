@@ -213,9 +213,143 @@ norm_bwd_kernel(const dlsg_norm_bwd_t p) {
   }
 }
 
+// Fast path (D % 4 == 0, D <= 128*NV, aligned rows): one warp per row, each lane owns the float4 chunks
+// {128*j + 4*lane}, j < NV.  dgamma/dbeta are accumulated in REGISTERS across all rows a warp processes, reduced
+// across the CTA's warps through smem once, then one global atomicAdd per column per CTA.  Rows are read twice
+// (statistics pass, dx pass); the second read is served by L1/L2.
+template <int NV>
+__device__ __forceinline__ void nb_elem(const dlsg_norm_bwd_t& p, float x, float dy, float g, float b, float mean, float rstd,
+                                        float& tv, float& xh, float& dl) {
+  tv = (p.flags & DLSG_NORM_PRE_TANH) ? tanhf(x) : x;
+  xh = (tv - mean) * rstd;
+  dl = dy;
+  if (p.flags & DLSG_NORM_POST_TANH) { const float yt = tanhf(xh * g + b); dl *= (1.f - yt * yt); }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(128)
+norm_bwd_vec_kernel(const dlsg_norm_bwd_t p) {
+  extern __shared__ float sm[];          // [nw][2][D]
+  const int D = p.D;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float ag[NV][4], ab[NV][4];
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { ag[j][k] = 0.f; ab[j][k] = 0.f; }
+  const bool want_param = (p.dgamma != nullptr);
+  const float invD = 1.f / (float)D;
+  for (int64_t row = (int64_t)blockIdx.x * nw + w; row < p.rows; row += (int64_t)gridDim.x * nw) {
+    const float mean = p.stats[row * 2], rstd = p.stats[row * 2 + 1];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = 128 * j + 4 * lane;
+      if (c < D) {
+        float4 x = RowIO::ld4(p.x, p.x_dtype, row * p.ldx + c);
+        if (p.res) { const float4 r = RowIO::ld4(p.res, p.res_dtype, row * p.ldres + c); x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w; }
+        float4 dy = RowIO::ld4(p.dy, p.dy_dtype, row * p.lddy + c);
+        if (p.drop_p > 0.f) {
+          const uint64_t i0 = p.offset + (uint64_t)row * D + c;
+          dy.x *= drop_scale(p.drop_p, p.seed, i0); dy.y *= drop_scale(p.drop_p, p.seed, i0 + 1);
+          dy.z *= drop_scale(p.drop_p, p.seed, i0 + 2); dy.w *= drop_scale(p.drop_p, p.seed, i0 + 3);
+        }
+        const float4 g = *reinterpret_cast<const float4*>(p.gamma + c), b = *reinterpret_cast<const float4*>(p.beta + c);
+        const float xs[4] = {x.x, x.y, x.z, x.w}, ds[4] = {dy.x, dy.y, dy.z, dy.w}, gs[4] = {g.x, g.y, g.z, g.w}, bs[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float tv, xh, dl;
+          nb_elem<NV>(p, xs[k], ds[k], gs[k], bs[k], mean, rstd, tv, xh, dl);
+          ag[j][k] = fmaf(dl, xh, ag[j][k]); ab[j][k] += dl;
+          const float d = dl * gs[k];
+          s1 += d; s2 = fmaf(d, xh, s2);
+        }
+      }
+    }
+    s1 = warp_sum(s1) * invD; s2 = warp_sum(s2) * invD;
+    if (p.dx) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c = 128 * j + 4 * lane;
+        if (c < D) {
+          float4 x = RowIO::ld4(p.x, p.x_dtype, row * p.ldx + c);
+          if (p.res) { const float4 r = RowIO::ld4(p.res, p.res_dtype, row * p.ldres + c); x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w; }
+          float4 dy = RowIO::ld4(p.dy, p.dy_dtype, row * p.lddy + c);
+          if (p.drop_p > 0.f) {
+            const uint64_t i0 = p.offset + (uint64_t)row * D + c;
+            dy.x *= drop_scale(p.drop_p, p.seed, i0); dy.y *= drop_scale(p.drop_p, p.seed, i0 + 1);
+            dy.z *= drop_scale(p.drop_p, p.seed, i0 + 2); dy.w *= drop_scale(p.drop_p, p.seed, i0 + 3);
+          }
+          const float4 g = *reinterpret_cast<const float4*>(p.gamma + c), b = *reinterpret_cast<const float4*>(p.beta + c);
+          const float xs[4] = {x.x, x.y, x.z, x.w}, ds[4] = {dy.x, dy.y, dy.z, dy.w}, gs[4] = {g.x, g.y, g.z, g.w}, bs[4] = {b.x, b.y, b.z, b.w};
+          float o[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float tv, xh, dl;
+            nb_elem<NV>(p, xs[k], ds[k], gs[k], bs[k], mean, rstd, tv, xh, dl);
+            float dx = rstd * (dl * gs[k] - s1 - xh * s2);
+            if (p.flags & (DLSG_NORM_PRE_TANH | DLSG_NORM_IN_IS_TANH)) dx *= (1.f - tv * tv);
+            o[k] = dx;
+          }
+          const int64_t idx = row * p.lddx + c;
+          float4 ov = make_float4(o[0], o[1], o[2], o[3]);
+          if (p.dx_accum) { const float4 old = RowIO::ld4(p.dx, p.dx_dtype, idx); ov.x += old.x; ov.y += old.y; ov.z += old.z; ov.w += old.w; }
+          RowIO::st4(p.dx, p.dx_dtype, idx, ov);
+        }
+      }
+    }
+  }
+  if (want_param) {
+    float* mg = sm + (size_t)w * 2 * D;
+    float* mb = mg + D;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = 128 * j + 4 * lane;
+      if (c < D) {
+        *reinterpret_cast<float4*>(mg + c) = make_float4(ag[j][0], ag[j][1], ag[j][2], ag[j][3]);
+        *reinterpret_cast<float4*>(mb + c) = make_float4(ab[j][0], ab[j][1], ab[j][2], ab[j][3]);
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      float tg = 0.f, tb = 0.f;
+      for (int ww = 0; ww < nw; ++ww) { tg += sm[(size_t)ww * 2 * D + c]; tb += sm[(size_t)ww * 2 * D + D + c]; }
+      atomicAdd(&p.dgamma[c], tg);
+      atomicAdd(&p.dbeta[c], tb);
+    }
+  }
+}
+
+template <int NV>
+static int norm_bwd_vec_launch(const dlsg_norm_bwd_t* p, cudaStream_t st) {
+  const int nw = 4;
+  const size_t smem = (size_t)nw * 2 * p->D * sizeof(float);
+  int64_t blocks = (p->rows + nw - 1) / nw;
+  if (blocks > kNumSM * 3) blocks = kNumSM * 3;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(norm_bwd_vec_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, nw * 2 * 128 * NV * 4);
+    attr = true;
+  }
+  norm_bwd_vec_kernel<NV><<<(unsigned)blocks, nw * 32, smem, st>>>(*p);
+  return check_launch("norm_bwd_vec_kernel");
+}
+
 int norm_bwd_launch(const dlsg_norm_bwd_t* p, cudaStream_t st) {
   DLSG_REQUIRE(p->rows >= 0 && p->D > 0 && p->D <= 4096, "norm_bwd: bad shape rows=%lld D=%d", (long long)p->rows, p->D);
   if (p->rows == 0) return 0;
+  const bool vec = p->D <= 2048 && vec_ok(p->x, p->x_dtype, p->ldx, p->D) && vec_ok(p->res, p->res_dtype, p->ldres, p->D) &&
+                   vec_ok(p->dy, p->dy_dtype, p->lddy, p->D) && vec_ok(p->dx, p->dx_dtype, p->lddx, p->D) &&
+                   vec_ok(p->gamma, DLSG_F32, 4, p->D) && vec_ok(p->beta, DLSG_F32, 4, p->D);
+  if (vec) {
+    const int nv = (p->D + 127) / 128;
+    if (nv <= 1) return norm_bwd_vec_launch<1>(p, st);
+    if (nv <= 2) return norm_bwd_vec_launch<2>(p, st);
+    if (nv <= 4) return norm_bwd_vec_launch<4>(p, st);
+    if (nv <= 8) return norm_bwd_vec_launch<8>(p, st);
+    if (nv <= 12) return norm_bwd_vec_launch<12>(p, st);
+    return norm_bwd_vec_launch<16>(p, st);
+  }
   const int nw = 4;
   const size_t smem = (size_t)(2 + 2 * nw) * p->D * sizeof(float);
   int64_t blocks = (p->rows + nw - 1) / nw;

@@ -19,7 +19,8 @@ class GemmT(C.Structure):
                 ('sam', i64), ('sak', i64), ('sbn', i64), ('sbk', i64), ('ldd', i64),
                 ('stride_a', i64), ('stride_b', i64), ('stride_d', i64),
                 ('a_dtype', i32), ('b_dtype', i32), ('d_dtype', i32), ('impl', i32), ('flags', i32), ('_pad0', i32),
-                ('splitk', i32), ('_pad', i32), ('stride_split', i64), ('alpha', f32)]
+                ('splitk', i32), ('_pad', i32), ('stride_split', i64), ('alpha', f32), ('_pad1', i32),
+                ('workspace', vp), ('workspace_bytes', i64)]
 
 
 class NormFwdT(C.Structure):

@@ -52,9 +52,20 @@ def _rows2d(t):
 class CudaBackend:
     name = 'cuda'
 
+    WORKSPACE_BYTES = 64 << 20
+
     def __init__(self):
         self.lib = L.load()
         self.launches = 0
+        self._ws = {}
+
+    def _workspace(self, dev):
+        """Per-device scratch for automatic split-K (allocated once, before any graph capture uses it)."""
+        ws = self._ws.get(dev)
+        if ws is None:
+            ws = torch.empty(self.WORKSPACE_BYTES, dtype=torch.uint8, device=dev)
+            self._ws[dev] = ws
+        return ws
 
     def _ck(self, t):
         if not t.is_cuda:
@@ -106,6 +117,9 @@ class CudaBackend:
         if impl is None:
             impl = L.GEMM_TC if (g.a_dtype == BF16 and g.b_dtype == BF16 and g.sak == 1 and g.sbk == 1) else L.GEMM_SIMT
         g.impl, g.flags, g.splitk, g.alpha = impl, flags, splitk, alpha
+        if impl == L.GEMM_TC and splitk <= 1:
+            ws = self._workspace(a.device)
+            g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
         self.launches += 1
         L.check(self.lib.dlsg_gemm(C.byref(g), _stream()), 'dlsg_gemm')
 

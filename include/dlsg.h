@@ -50,6 +50,9 @@ typedef struct {
   int32_t a_dtype, b_dtype, d_dtype, impl, flags, _pad0;
   int32_t splitk; int32_t _pad; int64_t stride_split;
   float alpha;                              /* result scale applied before bias                 */
+  int32_t _pad1;
+  void* workspace; int64_t workspace_bytes; /* optional scratch: lets DLSG_GEMM_TC split K automatically for skinny   */
+                                            /* problems (partials -> workspace, then a reduce+epilogue kernel)        */
 } dlsg_gemm_t;
 int dlsg_gemm(const dlsg_gemm_t* p, void* stream);
 
