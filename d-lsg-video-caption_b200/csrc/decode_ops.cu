@@ -85,6 +85,142 @@ node_attn_bwd_kernel(const dlsg_node_attn_bwd_t p) {
   }
 }
 
+
+// ---- fast paths: P <= 8 nodes, H <= 1024, H % 4 == 0.  256 threads, thread t owns columns [4t, 4t+4); all K / V / q
+// (and dctx) loads of the step are issued back to back (one memory latency), P dot products reduced by shuffles.
+constexpr int APM = 8;
+
+__device__ __forceinline__ float dot4(const float4 a, const float4 b) { return (a.x * b.x + a.y * b.y) + (a.z * b.z + a.w * b.w); }
+
+__global__ void __launch_bounds__(256)
+node_attn_fwd_fast(const dlsg_node_attn_fwd_t p) {
+  __shared__ float red[8][APM];
+  __shared__ float al[APM];
+  const int r = blockIdx.x, hd = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int node = r / p.rows_per_node;
+  const int c = tid * 4;
+  const bool act = c < p.H;
+  const float* q = p.qp + ((int64_t)r * p.nh + hd) * p.H;
+  const float* K = p.Kp + (((int64_t)hd * p.nodes + node) * p.P) * p.H;
+  const float* V = p.Vp + (((int64_t)hd * p.nodes + node) * p.P) * p.H;
+  float4 k4[APM], v4[APM], q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (act) q4 = *reinterpret_cast<const float4*>(q + c);
+#pragma unroll
+  for (int j = 0; j < APM; ++j) {
+    k4[j] = make_float4(0.f, 0.f, 0.f, 0.f); v4[j] = k4[j];
+    if (act && j < p.P) {
+      k4[j] = *reinterpret_cast<const float4*>(K + (int64_t)j * p.H + c);
+      v4[j] = *reinterpret_cast<const float4*>(V + (int64_t)j * p.H + c);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < APM; ++j) {
+    const float s = warp_sum(dot4(k4[j], q4));
+    if (lane == 0) red[w][j] = s;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const float scale = 1.0f / sqrtf((float)p.H);
+    float lg[APM], mx = -INFINITY;
+    for (int j = 0; j < p.P; ++j) {
+      float s = 0.f;
+      for (int ww = 0; ww < 8; ++ww) s += red[ww][j];
+      lg[j] = s * scale; mx = fmaxf(mx, lg[j]);
+    }
+    float sum = 0.f;
+    for (int j = 0; j < p.P; ++j) { lg[j] = expf(lg[j] - mx); sum += lg[j]; }
+    const float inv = 1.f / sum;
+    for (int j = 0; j < p.P; ++j) {
+      const float a = lg[j] * inv;
+      al[j] = a;
+      if (p.alpha) p.alpha[(int64_t)r * p.ldalpha + hd * p.P + j] = a;
+    }
+  }
+  __syncthreads();
+  if (act) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < APM; ++j) {
+      if (j < p.P) { const float a = al[j]; acc.x = fmaf(a, v4[j].x, acc.x); acc.y = fmaf(a, v4[j].y, acc.y); acc.z = fmaf(a, v4[j].z, acc.z); acc.w = fmaf(a, v4[j].w, acc.w); }
+    }
+    const int64_t o = (int64_t)r * p.ldctx + hd * p.H + c;
+    if (p.ctx_dtype == DLSG_F32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.ctx) + o) = acc;
+    else {
+      __nv_bfloat162 a = __floats2bfloat162_rn(acc.x, acc.y), b = __floats2bfloat162_rn(acc.z, acc.w);
+      uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.ctx) + o) = u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+node_attn_bwd_fast(const dlsg_node_attn_bwd_t p) {
+  __shared__ float red[8][APM];
+  __shared__ float dl[APM];
+  const int r = blockIdx.x, hd = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int c = tid * 4;
+  const bool act = c < p.H;
+  const float* q = p.qp + ((int64_t)r * p.nh + hd) * p.H;
+  const int64_t nb = (((int64_t)hd * p.rows + r) * p.P) * p.H;
+  const float* al = p.alpha + (int64_t)r * p.ldalpha + hd * p.P;
+  float4 k4[APM], v4[APM], q4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = q4;
+  if (act) {
+    q4 = *reinterpret_cast<const float4*>(q + c);
+    d4 = *reinterpret_cast<const float4*>(p.dctx + (int64_t)r * p.lddctx + hd * p.H + c);
+  }
+#pragma unroll
+  for (int j = 0; j < APM; ++j) {
+    k4[j] = make_float4(0.f, 0.f, 0.f, 0.f); v4[j] = k4[j];
+    if (act && j < p.P) {
+      k4[j] = *reinterpret_cast<const float4*>(p.Kp + nb + (int64_t)j * p.H + c);
+      v4[j] = *reinterpret_cast<const float4*>(p.Vp + nb + (int64_t)j * p.H + c);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < APM; ++j) {
+    const float s = warp_sum(dot4(v4[j], d4));
+    if (lane == 0) red[w][j] = s;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const float scale = 1.0f / sqrtf((float)p.H);
+    float da[APM], dot = 0.f;
+    for (int j = 0; j < p.P; ++j) {
+      float s = 0.f;
+      for (int ww = 0; ww < 8; ++ww) s += red[ww][j];
+      if (p.dalpha_ext) s += p.dalpha_ext[(int64_t)r * p.ldalpha + hd * p.P + j];
+      da[j] = s; dot = fmaf(al[j], s, dot);
+    }
+    for (int j = 0; j < p.P; ++j) dl[j] = al[j] * (da[j] - dot) * scale;
+  }
+  __syncthreads();
+  if (act) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < APM; ++j) {
+      if (j < p.P) {
+        const float g = dl[j], a = al[j];
+        acc.x = fmaf(g, k4[j].x, acc.x); acc.y = fmaf(g, k4[j].y, acc.y); acc.z = fmaf(g, k4[j].z, acc.z); acc.w = fmaf(g, k4[j].w, acc.w);
+        float4* dk = reinterpret_cast<float4*>(p.dKp + nb + (int64_t)j * p.H + c);
+        float4* dv = reinterpret_cast<float4*>(p.dVp + nb + (int64_t)j * p.H + c);
+        float4 ok = *dk, ov = *dv;
+        ok.x = fmaf(g, q4.x, ok.x); ok.y = fmaf(g, q4.y, ok.y); ok.z = fmaf(g, q4.z, ok.z); ok.w = fmaf(g, q4.w, ok.w);
+        ov.x = fmaf(a, d4.x, ov.x); ov.y = fmaf(a, d4.y, ov.y); ov.z = fmaf(a, d4.z, ov.z); ov.w = fmaf(a, d4.w, ov.w);
+        *dk = ok; *dv = ov;
+      }
+    }
+    const int64_t o = ((int64_t)r * p.nh + hd) * p.H + c;
+    if (p.dqp_dtype == DLSG_F32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dqp) + o) = acc;
+    else {
+      __nv_bfloat162 a = __floats2bfloat162_rn(acc.x, acc.y), b = __floats2bfloat162_rn(acc.z, acc.w);
+      uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.dqp) + o) = u;
+    }
+  }
+}
+
+static inline bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
+
 // ------------------------------------------------------------------------------------------- vocab rows
 struct ArgMax { float v; int i; };
 __device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {   // max value, lowest index on ties
@@ -315,11 +451,23 @@ extern "C" {
 int dlsg_node_attn_fwd(const dlsg_node_attn_fwd_t* p, void* stream) {
   DLSG_REQUIRE(p->P >= 1 && p->P <= MAXP, "node_attn: P=%d out of range (1..%d)", p->P, MAXP);
   DLSG_REQUIRE(p->rows > 0 && p->nh > 0 && p->rows_per_node >= 1, "node_attn: bad shape");
+  const int es = p->ctx_dtype == DLSG_F32 ? 4 : 2;
+  if (p->P <= APM && p->H <= 1024 && p->H % 4 == 0 && al16(p->Kp) && al16(p->Vp) && al16(p->qp) &&
+      (reinterpret_cast<uintptr_t>(p->ctx) % (4 * es)) == 0 && p->ldctx % 4 == 0) {
+    node_attn_fwd_fast<<<dim3(p->rows, p->nh), 256, 0, (cudaStream_t)stream>>>(*p);
+    return check_launch("node_attn_fwd_fast");
+  }
   node_attn_fwd_kernel<<<dim3(p->rows, p->nh), 128, 0, (cudaStream_t)stream>>>(*p);
   return check_launch("node_attn_fwd_kernel");
 }
 int dlsg_node_attn_bwd(const dlsg_node_attn_bwd_t* p, void* stream) {
   DLSG_REQUIRE(p->P >= 1 && p->P <= MAXP, "node_attn_bwd: P=%d out of range (1..%d)", p->P, MAXP);
+  const int es = p->dqp_dtype == DLSG_F32 ? 4 : 2;
+  if (p->P <= APM && p->H <= 1024 && p->H % 4 == 0 && al16(p->Kp) && al16(p->Vp) && al16(p->qp) && al16(p->dKp) && al16(p->dVp) &&
+      al16(p->dctx) && p->lddctx % 4 == 0 && (reinterpret_cast<uintptr_t>(p->dqp) % (4 * es)) == 0) {
+    node_attn_bwd_fast<<<dim3(p->rows, p->nh), 256, 0, (cudaStream_t)stream>>>(*p);
+    return check_launch("node_attn_bwd_fast");
+  }
   node_attn_bwd_kernel<<<dim3(p->rows, p->nh), 128, 0, (cudaStream_t)stream>>>(*p);
   return check_launch("node_attn_bwd_kernel");
 }

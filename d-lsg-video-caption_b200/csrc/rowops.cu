@@ -134,9 +134,94 @@ norm_fwd_kernel(const dlsg_norm_fwd_t p) {
   }
 }
 
+// Register-resident fast path: one warp per row, lane owns float4 chunks {128*j + 4*lane}, j < NV (D <= 128*NV).
+// All loads of a row are issued back to back (one memory latency), statistics by warp shuffles, no shared memory.
+template <int NV>
+__global__ void __launch_bounds__(128)
+norm_fwd_vec_kernel(const dlsg_norm_fwd_t p) {
+  const int D = p.D;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float invD = 1.f / (float)D;
+  for (int64_t row = (int64_t)blockIdx.x * nw + w; row < p.rows; row += (int64_t)gridDim.x * nw) {
+    float4 t[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = 128 * j + 4 * lane;
+      t[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < D) t[j] = RowIO::ld4(p.x, p.x_dtype, row * p.ldx + c);
+    }
+    if (p.res) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c = 128 * j + 4 * lane;
+        if (c < D) { const float4 r = RowIO::ld4(p.res, p.res_dtype, row * p.ldres + c); t[j].x += r.x; t[j].y += r.y; t[j].z += r.z; t[j].w += r.w; }
+      }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = 128 * j + 4 * lane;
+      if (c < D) {
+        if (p.flags & DLSG_NORM_PRE_TANH) { t[j].x = tanhf(t[j].x); t[j].y = tanhf(t[j].y); t[j].z = tanhf(t[j].z); t[j].w = tanhf(t[j].w); }
+        sum += (t[j].x + t[j].y) + (t[j].z + t[j].w);
+      }
+    }
+    const float mean = warp_sum(sum) * invD;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = 128 * j + 4 * lane;
+      if (c < D) {
+        const float a = t[j].x - mean, b = t[j].y - mean, cc = t[j].z - mean, d = t[j].w - mean;
+        sq += (a * a + b * b) + (cc * cc + d * d);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * invD + 1e-5f);
+    if (p.stats && lane == 0) { p.stats[row * 2] = mean; p.stats[row * 2 + 1] = rstd; }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = 128 * j + 4 * lane;
+      if (c < D) {
+        const float4 g = *reinterpret_cast<const float4*>(p.gamma + c), b = *reinterpret_cast<const float4*>(p.beta + c);
+        float4 y;
+        y.x = (t[j].x - mean) * rstd * g.x + b.x; y.y = (t[j].y - mean) * rstd * g.y + b.y;
+        y.z = (t[j].z - mean) * rstd * g.z + b.z; y.w = (t[j].w - mean) * rstd * g.w + b.w;
+        if (p.flags & DLSG_NORM_POST_TANH) { y.x = tanhf(y.x); y.y = tanhf(y.y); y.z = tanhf(y.z); y.w = tanhf(y.w); }
+        if (p.drop_p > 0.f) {
+          const uint64_t i0 = p.offset + (uint64_t)row * D + c;
+          y.x *= drop_scale(p.drop_p, p.seed, i0); y.y *= drop_scale(p.drop_p, p.seed, i0 + 1);
+          y.z *= drop_scale(p.drop_p, p.seed, i0 + 2); y.w *= drop_scale(p.drop_p, p.seed, i0 + 3);
+        }
+        if (p.y) RowIO::st4(p.y, p.y_dtype, row * p.ldy + c, y);
+        if (p.y2) RowIO::st4(p.y2, p.y2_dtype, row * p.ldy2 + c, y);
+      }
+    }
+  }
+}
+
+template <int NV>
+static int norm_fwd_vec_launch(const dlsg_norm_fwd_t* p, cudaStream_t st) {
+  const int nw = 4;
+  int64_t blocks = (p->rows + nw - 1) / nw;
+  if (blocks > kNumSM * 8) blocks = kNumSM * 8;
+  norm_fwd_vec_kernel<NV><<<(unsigned)blocks, nw * 32, 0, st>>>(*p);
+  return check_launch("norm_fwd_vec_kernel");
+}
+
 int norm_fwd_launch(const dlsg_norm_fwd_t* p, cudaStream_t st) {
   DLSG_REQUIRE(p->rows >= 0 && p->D > 0 && p->D <= 8192, "norm_fwd: bad shape rows=%lld D=%d", (long long)p->rows, p->D);
   if (p->rows == 0) return 0;
+  if (p->D <= 2048 && vec_ok(p->x, p->x_dtype, p->ldx, p->D) && vec_ok(p->res, p->res_dtype, p->ldres, p->D) &&
+      vec_ok(p->y, p->y_dtype, p->ldy, p->D) && vec_ok(p->y2, p->y2_dtype, p->ldy2, p->D) &&
+      vec_ok(p->gamma, DLSG_F32, 4, p->D) && vec_ok(p->beta, DLSG_F32, 4, p->D)) {
+    const int nv = (p->D + 127) / 128;
+    if (nv <= 1) return norm_fwd_vec_launch<1>(p, st);
+    if (nv <= 2) return norm_fwd_vec_launch<2>(p, st);
+    if (nv <= 4) return norm_fwd_vec_launch<4>(p, st);
+    if (nv <= 8) return norm_fwd_vec_launch<8>(p, st);
+    if (nv <= 12) return norm_fwd_vec_launch<12>(p, st);
+    return norm_fwd_vec_launch<16>(p, st);
+  }
   const int nw = p->D <= 2048 ? 8 : (p->D <= 4096 ? 4 : 2);
   const size_t smem = (size_t)nw * p->D * sizeof(float);
   const bool vec = vec_ok(p->x, p->x_dtype, p->ldx, p->D) && vec_ok(p->res, p->res_dtype, p->ldres, p->D) &&

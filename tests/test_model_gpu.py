@@ -219,7 +219,9 @@ def test_batch64_rows_are_independent_and_train_mode_runs():
     with torch.no_grad():
         o64 = net(fr, rg, cp, 26, 1.0)[0]
         o4 = net(fr[:4].contiguous(), rg[:4].contiguous(), cp[:4].contiguous(), 26, 1.0)[0]
-    assert rel(o64[:4], o4) < 2e-3
+    # not bit-equal: tile / split-K choices depend on the batch size, so fp32 summation order and hence the bf16
+    # roundings of intermediate activations differ (bf16 eps = 3.9e-3)
+    assert rel(o64[:4], o4) < 1e-2
     net.train()
     out = net(fr, rg, cp, 26, 1.0)[0]
     loss = O.packed_ce_loss(out, cp, lens)
