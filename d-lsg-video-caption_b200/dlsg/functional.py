@@ -148,11 +148,15 @@ class TunBlock:
             else:
                 P = self.P
                 theta = t[pf + 'v2l_layer.theta']
-                G = mm32(X, theta.detach())                     # (B*T,P)
                 Gs = empty((B, T, P), v2)
-                be.softmax_fwd(G.view(B, T, P), Gs, dim=1)       # over the T frames (sublayer.py:192)
                 N = empty((B, P, H), v2)
-                be.gemm(Gs.transpose(1, 2), X.view(B, T, H).transpose(1, 2), N)
+                if be.latent_psl_supported(T, P, H):
+                    G = None
+                    be.latent_psl_fwd(X.view(B, T, H), theta.detach(), Gs, N)   # fused: scores, softmax over T, pooling
+                else:
+                    G = mm32(X, theta.detach())                     # (B*T,P)
+                    be.softmax_fwd(G.view(B, T, P), Gs, dim=1)       # over the T frames (sublayer.py:192)
+                    be.gemm(Gs.transpose(1, 2), X.view(B, T, H).transpose(1, 2), N)
                 nodes = empty((B, P, H), v2)
                 stN = empty((B * P, 2), v2)
                 dn = site(0.3 if self.training else 0.0, seed, i)
@@ -196,16 +200,20 @@ class TunBlock:
                 be.norm_bwd(g.view(B * P, H), s['N'].view(B * P, H), w, b, s['stN'], dx=dN, dgamma=dw, dbeta=db,
                             pre_tanh=True, drop=s['dn'])
                 dN3 = dN.view(B, P, H)
-                dGs = empty((B, T, P), X)
-                be.gemm(X.view(B, T, H), dN3, dGs)
                 dX = empty((B, T, H), X)
-                be.gemm(s['Gs'], dN3.transpose(1, 2), dX)
-                dG = empty((B, T, P), X)
-                be.softmax_bwd(s['G'].view(B, T, P), dGs, dG, dim=1)
                 theta = t[pf + 'v2l_layer.theta'].detach()
-                be.gemm(dG.view(B * T, P), theta.t(), dX.view(B * T, H), accum=True)
-                dth = empty(theta.shape, X)
-                be.gemm(dG.view(B * T, P).t(), X.t(), dth)
+                if s['G'] is None:
+                    dth = zeros(theta.shape, X)
+                    be.latent_psl_bwd(X.view(B, T, H), theta, s['Gs'], dN3, dX, dth)
+                else:
+                    dGs = empty((B, T, P), X)
+                    be.gemm(X.view(B, T, H), dN3, dGs)
+                    be.gemm(s['Gs'], dN3.transpose(1, 2), dX)
+                    dG = empty((B, T, P), X)
+                    be.softmax_bwd(s['G'].view(B, T, P), dGs, dG, dim=1)
+                    be.gemm(dG.view(B * T, P), theta.t(), dX.view(B * T, H), accum=True)
+                    dth = empty(theta.shape, X)
+                    be.gemm(dG.view(B * T, P).t(), X.t(), dth)
                 grads[pf + 'v2l_layer.theta'] = dth
             if use_regions:
                 w, b, dw, db = lnp('obj_visual_norm.1')

@@ -299,6 +299,27 @@ class CudaBackend:
         self.launches += 1
         L.check(self.lib.dlsg_node_attn_bwd(C.byref(p), _stream()), 'dlsg_node_attn_bwd')
 
+    # ------------------------------------------------------------------ LatentPSL
+    @staticmethod
+    def latent_psl_supported(T, P, H):
+        return P <= 8 and T <= 32 and H % 4 == 0
+
+    def latent_psl_fwd(self, X, theta, Gs, N):
+        B, T, H = X.shape
+        P = theta.shape[0]
+        assert X.is_contiguous() and theta.is_contiguous() and Gs.is_contiguous() and N.is_contiguous()
+        self.launches += 1
+        L.check(self.lib.dlsg_latent_psl_fwd(X.data_ptr(), theta.data_ptr(), Gs.data_ptr(), N.data_ptr(), B, T, P, H, _stream()),
+                'latent_psl_fwd')
+
+    def latent_psl_bwd(self, X, theta, Gs, dN, dX, dtheta):
+        B, T, H = X.shape
+        P = theta.shape[0]
+        assert X.is_contiguous() and dN.is_contiguous() and dX.is_contiguous() and dtheta.is_contiguous()
+        self.launches += 1
+        L.check(self.lib.dlsg_latent_psl_bwd(X.data_ptr(), theta.data_ptr(), Gs.data_ptr(), dN.data_ptr(), dX.data_ptr(),
+                                             dtheta.data_ptr(), B, T, P, H, _stream()), 'latent_psl_bwd')
+
     # ------------------------------------------------------------------ embedding / small
     def embedding_gather(self, table, ids, out=None, out2=None, drop=None):
         """ids: 1-D int64 view (any stride). out/out2: (rows, W) views."""

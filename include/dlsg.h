@@ -150,6 +150,12 @@ typedef struct {
 } dlsg_node_attn_bwd_t;
 int dlsg_node_attn_bwd(const dlsg_node_attn_bwd_t* p, void* stream);
 
+/* ---- LatentPSL pooling (sublayer.py:191-196), one fused kernel per direction, one CTA per clip (P<=8, T<=32, H%4==0)
+ * fwd: Gs (B,T,P) = softmax over T of X theta^T ; N (B,P,H) = Gs^T X.   bwd: dX (B,T,H) written, dtheta (P,H) ACCUMULATED. */
+int dlsg_latent_psl_fwd(const float* X, const float* theta, float* Gs, float* N, int32_t B, int32_t T, int32_t P, int32_t H, void* stream);
+int dlsg_latent_psl_bwd(const float* X, const float* theta, const float* Gs, const float* dN, float* dX, float* dtheta,
+                        int32_t B, int32_t T, int32_t P, int32_t H, void* stream);
+
 /* ---- embedding (layer.py:421,438,535) and small reductions ---------------------------------- */
 int dlsg_embedding_gather(const float* table, const int64_t* ids, int64_t ld_ids, int32_t rows, int32_t W,
                           void* out, int out_dtype, int64_t ldo, void* out2, int out2_dtype, int64_t ldo2,

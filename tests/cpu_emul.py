@@ -208,6 +208,23 @@ class CpuEmulBackend:
             dKp[h].add_(torch.einsum('rp,rh->rph', dl, q[:, h]))
             dVp[h].add_(torch.einsum('rp,rh->rph', a, dc))
 
+    @staticmethod
+    def latent_psl_supported(T, P, H):
+        return P <= 8 and T <= 32 and H % 4 == 0
+
+    def latent_psl_fwd(self, X, theta, Gs, N):
+        self.launches += 1
+        g = torch.softmax(X @ theta.t(), dim=1)
+        Gs.copy_(g)
+        N.copy_(g.transpose(1, 2) @ X)
+
+    def latent_psl_bwd(self, X, theta, Gs, dN, dX, dtheta):
+        self.launches += 1
+        dGs = X @ dN.transpose(1, 2)
+        dG = Gs * (dGs - (Gs * dGs).sum(1, keepdim=True))
+        dX.copy_(Gs @ dN + dG @ theta)
+        dtheta.add_((dG.transpose(1, 2) @ X).sum(0))
+
     def embedding_gather(self, table, ids, out=None, out2=None, drop=None):
         self.launches += 1
         assert drop is None or drop[0] == 0

@@ -1,0 +1,71 @@
+"""DiscV2 (models/model.py:145-168) + WGAN-GP double backward (run_gun.py:351-375) through the drop-in mirror,
+kernels emulated on CPU (tests/cpu_emul.py), against the golden vectors produced by the unmodified reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from dlsg import synth, ops
+from dlsg import linalg as la
+from dlsg import functional as DF
+from cpu_emul import CpuEmulBackend
+
+
+@pytest.fixture(autouse=True)
+def emul_backend():
+    old = ops._backend
+    ops.set_backend(CpuEmulBackend())
+    DF.WC.clear()
+    la.set_precision('fp32')
+    yield
+    ops.set_backend(old)
+    DF.WC.clear()
+    la.set_precision('bf16')
+
+
+def disc_case(golden_dir, tag, P, K, dev='cpu'):
+    import models.model as M
+    args = synth.small_args(visual_hidden_size=1024, num_proposals=P, num_topk=K)
+    V, B, L = 37, 3, args.max_words
+    g = np.load(os.path.join(golden_dir, tag + '.npz'))
+    net = M.DiscV2(args, V)
+    synth.fill_state_dict(net, prefix='D.')
+    net = net.to(dev).eval()
+    rs = np.random.RandomState(5)
+    _, _, caps, lens = synth.make_inputs(B, args, V, seed=14)
+    att_mask = synth.att_mask_from_captions(caps).to(dev)
+    obj = torch.from_numpy(rs.standard_normal((B, P, 1024)).astype(np.float32)).to(dev)
+    mot = torch.from_numpy(rs.standard_normal((B, P, 1024)).astype(np.float32)).to(dev)
+    alpha = torch.softmax(torch.from_numpy(rs.standard_normal((B, L, 2 * P)).astype(np.float32)), -1).to(dev)
+    fake = torch.from_numpy(rs.standard_normal((B, L, V)).astype(np.float32)).to(dev)
+    real = torch.zeros(B, L, V).scatter_(2, caps.unsqueeze(2), 1).to(dev)
+    eps = torch.from_numpy(rs.uniform(size=(B, 1, 1)).astype(np.float32)).to(dev)
+    net.zero_grad()
+    r_logit = net(real.clone(), obj, mot, att_mask, alpha)
+    f_in = fake.clone().requires_grad_(True)
+    f_logit = net(f_in, obj, mot, att_mask, alpha)
+    mixed = (real * eps + fake * (1 - eps)).requires_grad_(True)
+    m_logit = net(mixed, obj, mot, att_mask, alpha)
+    gr = torch.autograd.grad(m_logit, mixed, torch.ones_like(m_logit), create_graph=True, retain_graph=True)[0]
+    gn = gr.contiguous().view(B, -1).norm(2, dim=1)
+    gp = ((gn - 1) * (gn - 1)).mean()
+    loss_d = f_logit.mean() - r_logit.mean() + 10 * gp
+    loss_d.backward()
+    return g, net, r_logit, f_logit, m_logit, gn, gp, loss_d, f_in
+
+
+@pytest.mark.parametrize('tag,P,K', [('disc_small_msr', 5, 5), ('disc_small_msvd', 8, 3)])
+def test_disc_forward_and_gradient_penalty(golden_dir, tag, P, K):
+    g, net, r, f, m, gn, gp, loss_d, f_in = disc_case(golden_dir, tag, P, K)
+    assert np.abs(r.detach().numpy() - g['r_logit']).max() < 2e-5
+    assert np.abs(f.detach().numpy() - g['f_logit']).max() < 2e-5
+    assert np.abs(m.detach().numpy() - g['m_logit']).max() < 2e-5
+    assert np.abs(gn.detach().numpy() - g['gnorm_mixed']).max() < 1e-4
+    assert abs(gp.item() - g['gp'][0]) < 1e-4
+    assert abs(loss_d.item() - g['loss_d'][0]) < 1e-4
+    assert np.abs(f_in.grad.numpy() - g['dfake']).max() < 1e-5
+    for k, p in net.named_parameters():
+        ref = float(g['gnorm.' + k][0])
+        gn_k = float(p.grad.double().norm())
+        assert abs(gn_k - ref) <= 5e-4 * max(ref, 1e-3), (k, gn_k, ref)

@@ -207,6 +207,15 @@ def test_node_attn(be, nh, P, H, rpn):
              dict(dalpha_ext=R(rows, nh * P)), [5, 6, 7], tol=3e-5)
 
 
+@pytest.mark.parametrize('B_,T,P,H', [(6, 26, 5, 1024), (3, 26, 8, 64), (4, 26, 1, 512), (2, 6, 5, 64)])
+def test_latent_psl(be, B_, T, P, H):
+    X, theta = R(B_, T, H), R(P, H, scale=0.05)
+    Gs, N = torch.zeros(B_, T, P), torch.zeros(B_, P, H)
+    both('latent_psl_fwd', be, [X, theta, Gs, N], {}, [2, 3], tol=2e-5)
+    EM.latent_psl_fwd(X, theta, Gs, N)
+    both('latent_psl_bwd', be, [X, theta, Gs, R(B_, P, H), torch.zeros(B_, T, H), R(P, H)], {}, [4, 5], tol=3e-5)
+
+
 # ----------------------------------------------------------------------------------------------- embedding & co
 def test_embedding_mean_elementwise(be):
     V_, W = 50, 20

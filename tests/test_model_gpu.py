@@ -247,3 +247,24 @@ def test_fused_masked_ce_matches_packed_ce():
     ref.backward()
     assert abs(loss.item() - ref.item()) < 1e-5
     assert (logits.grad - l2.grad).abs().max() < 1e-7
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+@pytest.mark.parametrize('tag,P,K', [('disc_small_msr', 5, 5), ('disc_small_msvd', 8, 3)])
+def test_disc_v2_and_wgan_gp_golden(golden_dir, tag, P, K, prec):
+    """DiscV2 forward (3 input kinds), first-order grads and the WGAN-GP double backward against the reference's
+    golden vectors.  fp32: 1e-4; bf16: the critic scores are O(0.1), tolerance 2e-2 absolute, penalty 5e-2."""
+    from test_disc_cpu import disc_case
+    la.set_precision(prec)
+    g, net, r, f, m, gn, gp, loss_d, f_in = disc_case(golden_dir, tag, P, K, dev=DEV)
+    tol = 1e-4 if prec == 'fp32' else 2e-2
+    assert np.abs(r.detach().cpu().numpy() - g['r_logit']).max() < tol
+    assert np.abs(f.detach().cpu().numpy() - g['f_logit']).max() < tol
+    assert np.abs(m.detach().cpu().numpy() - g['m_logit']).max() < tol
+    assert np.abs(gn.detach().cpu().numpy() - g['gnorm_mixed']).max() < (1e-3 if prec == 'fp32' else 5e-2)
+    assert abs(loss_d.item() - g['loss_d'][0]) < (1e-3 if prec == 'fp32' else 0.3)
+    if prec == 'fp32':
+        assert np.abs(f_in.grad.cpu().numpy() - g['dfake']).max() < 1e-5
+        for k, p in net.named_parameters():
+            ref = float(g['gnorm.' + k][0])
+            assert abs(float(p.grad.double().norm()) - ref) <= 2e-3 * max(ref, 1e-3), k
