@@ -68,8 +68,9 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 // Philox4x32-10 counter RNG -> one uniform in [0,1) per (seed, index).  Used for dropout so that
 // forward and backward regenerate the same mask without storing it.
 __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
-__device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t idx) {
-  uint32_t c0 = (uint32_t)idx, c1 = (uint32_t)(idx >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
+// Philox4x32-10: counter = element index / 4, the four 32-bit outputs serve four consecutive elements.
+__device__ __forceinline__ uint4 philox4(uint64_t seed, uint64_t ctr) {
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
@@ -78,12 +79,21 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t idx) {
     c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
-  return (float)(c0 >> 8) * (1.0f / 16777216.0f);
+  return make_uint4(c0, c1, c2, c3);
 }
-// multiplier of inverted dropout: 0 or 1/(1-p)
+__device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }
+// multiplier of inverted dropout for element idx: 0 or 1/(1-p)
 __device__ __forceinline__ float drop_scale(float p, uint64_t seed, uint64_t idx) {
   if (p <= 0.f) return 1.f;
-  return philox_uniform(seed, idx) >= p ? 1.f / (1.f - p) : 0.f;
+  const uint4 r = philox4(seed, idx >> 2);
+  const uint32_t k = (uint32_t)idx & 3u;
+  const uint32_t v = k == 0 ? r.x : (k == 1 ? r.y : (k == 2 ? r.z : r.w));
+  return u01(v) >= p ? 1.f / (1.f - p) : 0.f;
+}
+// the four multipliers of elements idx..idx+3 (idx % 4 == 0): one Philox evaluation
+__device__ __forceinline__ float4 drop_mask4(float p, float keep, uint64_t seed, uint64_t idx) {
+  const uint4 r = philox4(seed, idx >> 2);
+  return make_float4(u01(r.x) >= p ? keep : 0.f, u01(r.y) >= p ? keep : 0.f, u01(r.z) >= p ? keep : 0.f, u01(r.w) >= p ? keep : 0.f);
 }
 
 }  // namespace dlsg

@@ -188,9 +188,8 @@ norm_fwd_vec_kernel(const dlsg_norm_fwd_t p) {
         y.z = (t[j].z - mean) * rstd * g.z + b.z; y.w = (t[j].w - mean) * rstd * g.w + b.w;
         if (p.flags & DLSG_NORM_POST_TANH) { y.x = tanhf(y.x); y.y = tanhf(y.y); y.z = tanhf(y.z); y.w = tanhf(y.w); }
         if (p.drop_p > 0.f) {
-          const uint64_t i0 = p.offset + (uint64_t)row * D + c;
-          y.x *= drop_scale(p.drop_p, p.seed, i0); y.y *= drop_scale(p.drop_p, p.seed, i0 + 1);
-          y.z *= drop_scale(p.drop_p, p.seed, i0 + 2); y.w *= drop_scale(p.drop_p, p.seed, i0 + 3);
+          const float4 m = drop_mask4(p.drop_p, 1.f / (1.f - p.drop_p), p.seed, p.offset + (uint64_t)row * D + c);
+          y.x *= m.x; y.y *= m.y; y.z *= m.z; y.w *= m.w;
         }
         if (p.y) RowIO::st4(p.y, p.y_dtype, row * p.ldy + c, y);
         if (p.y2) RowIO::st4(p.y2, p.y2_dtype, row * p.ldy2 + c, y);
@@ -299,56 +298,83 @@ norm_bwd_kernel(const dlsg_norm_bwd_t p) {
 }
 
 // Fast path (D % 4 == 0, D <= 128*NV, aligned rows): one warp per row, each lane owns the float4 chunks
-// {128*j + 4*lane}, j < NV.  dgamma/dbeta are accumulated in REGISTERS across all rows a warp processes, reduced
-// across the CTA's warps through smem once, then one global atomicAdd per column per CTA.  Rows are read twice
-// (statistics pass, dx pass); the second read is served by L1/L2.
-template <int NV>
-__device__ __forceinline__ void nb_elem(const dlsg_norm_bwd_t& p, float x, float dy, float g, float b, float mean, float rstd,
-                                        float& tv, float& xh, float& dl) {
-  tv = (p.flags & DLSG_NORM_PRE_TANH) ? tanhf(x) : x;
-  xh = (tv - mean) * rstd;
-  dl = dy;
-  if (p.flags & DLSG_NORM_POST_TANH) { const float yt = tanhf(xh * g + b); dl *= (1.f - yt * yt); }
-}
-
+// {128*j + 4*lane}, j < NV.  The row (t = pre(x+res) and d = dl*gamma) stays in registers between the statistics
+// and the dx computation (single pass over global memory); dgamma/dbeta are accumulated in a warp-private shared-
+// memory slab (plain read-modify-write, no atomics), reduced across the CTA's warps once at the end, then one
+// global atomicAdd per column per CTA.
 template <int NV>
 __global__ void __launch_bounds__(128)
 norm_bwd_vec_kernel(const dlsg_norm_bwd_t p) {
   extern __shared__ float sm[];          // [nw][2][D]
   const int D = p.D;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  float ag[NV][4], ab[NV][4];
-#pragma unroll
-  for (int j = 0; j < NV; ++j)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { ag[j][k] = 0.f; ab[j][k] = 0.f; }
   const bool want_param = (p.dgamma != nullptr);
+  float* mg = sm + (size_t)w * 2 * D;
+  float* mb = mg + D;
+  if (want_param) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = 128 * j + 4 * lane;
+      if (c < D) {
+        *reinterpret_cast<float4*>(mg + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(mb + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
   const float invD = 1.f / (float)D;
+  const bool pre = p.flags & DLSG_NORM_PRE_TANH, post = p.flags & DLSG_NORM_POST_TANH;
+  const bool dtanh = p.flags & (DLSG_NORM_PRE_TANH | DLSG_NORM_IN_IS_TANH);
+  const bool drop = p.drop_p > 0.f;
+  const float keep = drop ? 1.f / (1.f - p.drop_p) : 1.f;
   for (int64_t row = (int64_t)blockIdx.x * nw + w; row < p.rows; row += (int64_t)gridDim.x * nw) {
     const float mean = p.stats[row * 2], rstd = p.stats[row * 2 + 1];
+    float4 tv[NV], dv[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = 128 * j + 4 * lane;
+      tv[j] = make_float4(0.f, 0.f, 0.f, 0.f); dv[j] = tv[j];
+      if (c < D) {
+        tv[j] = RowIO::ld4(p.x, p.x_dtype, row * p.ldx + c);
+        dv[j] = RowIO::ld4(p.dy, p.dy_dtype, row * p.lddy + c);
+      }
+    }
+    if (p.res) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c = 128 * j + 4 * lane;
+        if (c < D) { const float4 r = RowIO::ld4(p.res, p.res_dtype, row * p.ldres + c); tv[j].x += r.x; tv[j].y += r.y; tv[j].z += r.z; tv[j].w += r.w; }
+      }
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int c = 128 * j + 4 * lane;
       if (c < D) {
-        float4 x = RowIO::ld4(p.x, p.x_dtype, row * p.ldx + c);
-        if (p.res) { const float4 r = RowIO::ld4(p.res, p.res_dtype, row * p.ldres + c); x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w; }
-        float4 dy = RowIO::ld4(p.dy, p.dy_dtype, row * p.lddy + c);
-        if (p.drop_p > 0.f) {
-          const uint64_t i0 = p.offset + (uint64_t)row * D + c;
-          dy.x *= drop_scale(p.drop_p, p.seed, i0); dy.y *= drop_scale(p.drop_p, p.seed, i0 + 1);
-          dy.z *= drop_scale(p.drop_p, p.seed, i0 + 2); dy.w *= drop_scale(p.drop_p, p.seed, i0 + 3);
+        if (pre) { tv[j].x = tanhf(tv[j].x); tv[j].y = tanhf(tv[j].y); tv[j].z = tanhf(tv[j].z); tv[j].w = tanhf(tv[j].w); }
+        if (drop) {
+          const float4 m = drop_mask4(p.drop_p, keep, p.seed, p.offset + (uint64_t)row * D + c);
+          dv[j].x *= m.x; dv[j].y *= m.y; dv[j].z *= m.z; dv[j].w *= m.w;
         }
-        const float4 g = *reinterpret_cast<const float4*>(p.gamma + c), b = *reinterpret_cast<const float4*>(p.beta + c);
-        const float xs[4] = {x.x, x.y, x.z, x.w}, ds[4] = {dy.x, dy.y, dy.z, dy.w}, gs[4] = {g.x, g.y, g.z, g.w}, bs[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float tv, xh, dl;
-          nb_elem<NV>(p, xs[k], ds[k], gs[k], bs[k], mean, rstd, tv, xh, dl);
-          ag[j][k] = fmaf(dl, xh, ag[j][k]); ab[j][k] += dl;
-          const float d = dl * gs[k];
-          s1 += d; s2 = fmaf(d, xh, s2);
+        const float4 g = *reinterpret_cast<const float4*>(p.gamma + c);
+        float4 xh;
+        xh.x = (tv[j].x - mean) * rstd; xh.y = (tv[j].y - mean) * rstd; xh.z = (tv[j].z - mean) * rstd; xh.w = (tv[j].w - mean) * rstd;
+        if (post) {
+          const float4 b = *reinterpret_cast<const float4*>(p.beta + c);
+          float yt;
+          yt = tanhf(xh.x * g.x + b.x); dv[j].x *= (1.f - yt * yt);
+          yt = tanhf(xh.y * g.y + b.y); dv[j].y *= (1.f - yt * yt);
+          yt = tanhf(xh.z * g.z + b.z); dv[j].z *= (1.f - yt * yt);
+          yt = tanhf(xh.w * g.w + b.w); dv[j].w *= (1.f - yt * yt);
         }
+        if (want_param) {
+          float4 a = *reinterpret_cast<float4*>(mg + c), bsum = *reinterpret_cast<float4*>(mb + c);
+          a.x = fmaf(dv[j].x, xh.x, a.x); a.y = fmaf(dv[j].y, xh.y, a.y); a.z = fmaf(dv[j].z, xh.z, a.z); a.w = fmaf(dv[j].w, xh.w, a.w);
+          bsum.x += dv[j].x; bsum.y += dv[j].y; bsum.z += dv[j].z; bsum.w += dv[j].w;
+          *reinterpret_cast<float4*>(mg + c) = a; *reinterpret_cast<float4*>(mb + c) = bsum;
+        }
+        dv[j].x *= g.x; dv[j].y *= g.y; dv[j].z *= g.z; dv[j].w *= g.w;
+        s1 += (dv[j].x + dv[j].y) + (dv[j].z + dv[j].w);
+        s2 += (dv[j].x * xh.x + dv[j].y * xh.y) + (dv[j].z * xh.z + dv[j].w * xh.w);
       }
     }
     s1 = warp_sum(s1) * invD; s2 = warp_sum(s2) * invD;
@@ -357,44 +383,23 @@ norm_bwd_vec_kernel(const dlsg_norm_bwd_t p) {
       for (int j = 0; j < NV; ++j) {
         const int c = 128 * j + 4 * lane;
         if (c < D) {
-          float4 x = RowIO::ld4(p.x, p.x_dtype, row * p.ldx + c);
-          if (p.res) { const float4 r = RowIO::ld4(p.res, p.res_dtype, row * p.ldres + c); x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w; }
-          float4 dy = RowIO::ld4(p.dy, p.dy_dtype, row * p.lddy + c);
-          if (p.drop_p > 0.f) {
-            const uint64_t i0 = p.offset + (uint64_t)row * D + c;
-            dy.x *= drop_scale(p.drop_p, p.seed, i0); dy.y *= drop_scale(p.drop_p, p.seed, i0 + 1);
-            dy.z *= drop_scale(p.drop_p, p.seed, i0 + 2); dy.w *= drop_scale(p.drop_p, p.seed, i0 + 3);
-          }
-          const float4 g = *reinterpret_cast<const float4*>(p.gamma + c), b = *reinterpret_cast<const float4*>(p.beta + c);
-          const float xs[4] = {x.x, x.y, x.z, x.w}, ds[4] = {dy.x, dy.y, dy.z, dy.w}, gs[4] = {g.x, g.y, g.z, g.w}, bs[4] = {b.x, b.y, b.z, b.w};
-          float o[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float tv, xh, dl;
-            nb_elem<NV>(p, xs[k], ds[k], gs[k], bs[k], mean, rstd, tv, xh, dl);
-            float dx = rstd * (dl * gs[k] - s1 - xh * s2);
-            if (p.flags & (DLSG_NORM_PRE_TANH | DLSG_NORM_IN_IS_TANH)) dx *= (1.f - tv * tv);
-            o[k] = dx;
+          float4 o;
+          o.x = rstd * (dv[j].x - s1 - (tv[j].x - mean) * rstd * s2);
+          o.y = rstd * (dv[j].y - s1 - (tv[j].y - mean) * rstd * s2);
+          o.z = rstd * (dv[j].z - s1 - (tv[j].z - mean) * rstd * s2);
+          o.w = rstd * (dv[j].w - s1 - (tv[j].w - mean) * rstd * s2);
+          if (dtanh) {
+            o.x *= (1.f - tv[j].x * tv[j].x); o.y *= (1.f - tv[j].y * tv[j].y);
+            o.z *= (1.f - tv[j].z * tv[j].z); o.w *= (1.f - tv[j].w * tv[j].w);
           }
           const int64_t idx = row * p.lddx + c;
-          float4 ov = make_float4(o[0], o[1], o[2], o[3]);
-          if (p.dx_accum) { const float4 old = RowIO::ld4(p.dx, p.dx_dtype, idx); ov.x += old.x; ov.y += old.y; ov.z += old.z; ov.w += old.w; }
-          RowIO::st4(p.dx, p.dx_dtype, idx, ov);
+          if (p.dx_accum) { const float4 old = RowIO::ld4(p.dx, p.dx_dtype, idx); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+          RowIO::st4(p.dx, p.dx_dtype, idx, o);
         }
       }
     }
   }
   if (want_param) {
-    float* mg = sm + (size_t)w * 2 * D;
-    float* mb = mg + D;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int c = 128 * j + 4 * lane;
-      if (c < D) {
-        *reinterpret_cast<float4*>(mg + c) = make_float4(ag[j][0], ag[j][1], ag[j][2], ag[j][3]);
-        *reinterpret_cast<float4*>(mb + c) = make_float4(ab[j][0], ab[j][1], ab[j][2], ab[j][3]);
-      }
-    }
     __syncthreads();
     for (int c = threadIdx.x; c < D; c += blockDim.x) {
       float tg = 0.f, tb = 0.f;
@@ -410,7 +415,7 @@ static int norm_bwd_vec_launch(const dlsg_norm_bwd_t* p, cudaStream_t st) {
   const int nw = 4;
   const size_t smem = (size_t)nw * 2 * p->D * sizeof(float);
   int64_t blocks = (p->rows + nw - 1) / nw;
-  if (blocks > kNumSM * 3) blocks = kNumSM * 3;
+  if (blocks > kNumSM * 4) blocks = kNumSM * 4;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(norm_bwd_vec_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, nw * 2 * 128 * NV * 4);

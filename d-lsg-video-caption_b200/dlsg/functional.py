@@ -48,7 +48,51 @@ class _BlockFn(torch.autograd.Function):
     def backward(ctx, *gouts):
         grads = ctx.block.backward(ctx.saved, gouts)
         ctx.saved = None
+        if GRAD_SYNC is not None:
+            grads = GRAD_SYNC.reduce(grads)
         return (None, None) + tuple(grads.get(n) for n in ctx.names)
+
+
+BLOCK_INPUTS = ('regions', 'visual0', 'visual1', 'frames', 'pe', 'n1', 'n2', 'captions')
+GRAD_SYNC = None
+
+
+class GradSync:
+    """Data-parallel gradient averaging, one flat fp32 bucket per block, launched on a side stream the moment the
+    block's backward has produced its parameter gradients: the decoder bucket (~76 M params) is reduced over
+    NCCL/NVLink while the encoder backward is still computing; only the last (smallest) bucket is exposed.
+    Same arithmetic as DistributedDataParallel's bucketed all-reduce (run_gun.py:63-72): SUM over ranks / world."""
+
+    def __init__(self, process_group=None):
+        import torch.distributed as dist
+        self.dist, self.pg = dist, process_group
+        self.side = torch.cuda.Stream()
+
+    def reduce(self, grads):
+        items = [(k, v) for k, v in grads.items() if v is not None and k not in BLOCK_INPUTS]
+        if not items:
+            return grads
+        uniq = {}
+        for k, v in items:
+            uniq.setdefault(id(v), v)
+        tensors = list(uniq.values())
+        flat = torch.cat([x.reshape(-1) for x in tensors])
+        cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)
+        flat.record_stream(self.side)
+        with torch.cuda.stream(self.side):
+            self.dist.all_reduce(flat, op=self.dist.ReduceOp.AVG, group=self.pg)
+        out, off, views = dict(grads), 0, {}
+        for x in tensors:
+            n = x.numel()
+            views[id(x)] = flat[off:off + n].view(x.shape)
+            off += n
+        for k, v in items:
+            out[k] = views[id(v)]
+        return out
+
+    def wait(self):
+        torch.cuda.current_stream().wait_stream(self.side)
 
 
 def run_block(block, tensors):

@@ -28,6 +28,7 @@ class GraphedTrainStep:
             import torch.distributed as dist
             self.dist = dist
             self.world = dist.get_world_size(process_group)
+            self.sync = DF.GradSync(process_group)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -49,19 +50,17 @@ class GraphedTrainStep:
         self.opt.zero_grad(set_to_none=True)
         out = self.model(self.frames, self.regions, self.captions, self.max_words, self.tf)[0]
         loss = losses.packed_cross_entropy(out, self.captions, self.lens, self.inv)
-        loss.backward()
         if self.world > 1:
-            self._allreduce()
+            # per-block flat buckets, all-reduced on a side stream as soon as each block's backward is done
+            DF.GRAD_SYNC = self.sync
+        try:
+            loss.backward()
+        finally:
+            DF.GRAD_SYNC = None
+        if self.world > 1:
+            self.sync.wait()
         self.opt.step()
         return loss.detach()
-
-    def _allreduce(self):
-        """Data-parallel gradient averaging (what DDP does in run_gun.py:63-72): one flat fp32 bucket over NCCL."""
-        grads = [p.grad for p in self.params if p.grad is not None]
-        flat = torch._utils._flatten_dense_tensors(grads)
-        self.dist.all_reduce(flat, op=self.dist.ReduceOp.AVG, group=self.pg)
-        for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-            g.copy_(f)
 
     def load(self, frames, regions, captions, cap_lens=None):
         """Copy a new batch (host pinned or device tensors) into the static buffers."""

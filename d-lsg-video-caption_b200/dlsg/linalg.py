@@ -75,6 +75,8 @@ def op(t):
         return out
     if _tc_ok(t):
         return t
+    if t.stride(-1) != 1 and t.shape[-1] != 1 and t.stride(-2) != 1:
+        t = t.contiguous()          # e.g. one tap of a conv1d weight (C_out, C_in, k)[:, :, j]
     out = op_empty(t.shape[:-1], t.shape[-1], t)
     _convert_into(t, out)
     return out

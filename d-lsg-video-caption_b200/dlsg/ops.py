@@ -255,10 +255,14 @@ class CudaBackend:
         o, i = order
         return x.shape[o], x.shape[dim], x.shape[i], x.stride(o), x.stride(dim), x.stride(i)
 
+    @staticmethod
+    def _same_layout(a, b):
+        return a.shape == b.shape and all(sa == sb or n == 1 for sa, sb, n in zip(a.stride(), b.stride(), a.shape))
+
     def softmax_fwd(self, x, y, dim, scale=1.0, mask=None, mask_mode=0):
         self._ck(x)
         p = L.SoftmaxT()
-        assert x.stride() == y.stride() and (mask is None or mask.stride() == x.stride())
+        assert self._same_layout(x, y) and (mask is None or self._same_layout(x, mask))
         p.outer, p.n, p.inner, p.so, p.sn, p.si = self._softmax_desc(x, dim)
         p.x, p.y, p.mask, p.scale, p.mask_mode = x.data_ptr(), y.data_ptr(), _ptr(mask), scale, mask_mode
         self.launches += 1
@@ -267,7 +271,7 @@ class CudaBackend:
     def softmax_bwd(self, x, dy, dx, dim, scale=1.0, mask=None, mask_mode=0):
         self._ck(x)
         p = L.SoftmaxT()
-        assert x.stride() == dy.stride() == dx.stride() and (mask is None or mask.stride() == x.stride())
+        assert self._same_layout(x, dy) and self._same_layout(x, dx) and (mask is None or self._same_layout(x, mask))
         p.outer, p.n, p.inner, p.so, p.sn, p.si = self._softmax_desc(x, dim)
         p.x, p.mask, p.scale, p.mask_mode = x.data_ptr(), _ptr(mask), scale, mask_mode
         self.launches += 1
