@@ -219,6 +219,136 @@ node_attn_bwd_fast(const dlsg_node_attn_bwd_t p) {
   }
 }
 
+// ---- hoisted AttentionShare (P <= 8, Hk,Hv <= 1024): the query / output projections are folded into the node
+// tensors once per sequence (KW = K Wq, VW = V Wo^T), so a decode step needs NO per-step attention GEMM:
+//   logits_p = KW_p . q * scale ; alpha = softmax_p ; co = sum_p alpha_p VW_p   (pre-LayerNorm context, sublayer.py:29-41)
+__global__ void __launch_bounds__(256)
+attn2_fwd_kernel(const dlsg_attn2_fwd_t p) {
+  __shared__ float red[8][APM];
+  __shared__ float al[APM];
+  const int r = blockIdx.x, hd = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int node = r / p.rows_per_node;
+  const int c = tid * 4;
+  const bool ak = c < p.Hk, av = c < p.Hv;
+  const float* KW = p.KW + (((int64_t)hd * p.nodes + node) * p.P) * p.Hk;
+  const float* VW = p.VW + (((int64_t)hd * p.nodes + node) * p.P) * p.Hv;
+  float4 k4[APM], v4[APM], q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ak) q4 = *reinterpret_cast<const float4*>(p.q + (int64_t)r * p.ldq + c);
+#pragma unroll
+  for (int j = 0; j < APM; ++j) {
+    k4[j] = make_float4(0.f, 0.f, 0.f, 0.f); v4[j] = k4[j];
+    if (j < p.P) {
+      if (ak) k4[j] = *reinterpret_cast<const float4*>(KW + (int64_t)j * p.Hk + c);
+      if (av) v4[j] = *reinterpret_cast<const float4*>(VW + (int64_t)j * p.Hv + c);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < APM; ++j) {
+    const float s = warp_sum(dot4(k4[j], q4));
+    if (lane == 0) red[w][j] = s;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float lg[APM], mx = -INFINITY;
+    for (int j = 0; j < p.P; ++j) {
+      float s = 0.f;
+      for (int ww = 0; ww < 8; ++ww) s += red[ww][j];
+      lg[j] = s * p.scale; mx = fmaxf(mx, lg[j]);
+    }
+    float sum = 0.f;
+    for (int j = 0; j < p.P; ++j) { lg[j] = expf(lg[j] - mx); sum += lg[j]; }
+    const float inv = 1.f / sum;
+    for (int j = 0; j < p.P; ++j) {
+      const float a = lg[j] * inv;
+      al[j] = a;
+      if (p.alpha) p.alpha[(int64_t)r * p.ldalpha + hd * p.P + j] = a;
+    }
+  }
+  __syncthreads();
+  if (av) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < APM; ++j) {
+      if (j < p.P) { const float a = al[j]; acc.x = fmaf(a, v4[j].x, acc.x); acc.y = fmaf(a, v4[j].y, acc.y); acc.z = fmaf(a, v4[j].z, acc.z); acc.w = fmaf(a, v4[j].w, acc.w); }
+    }
+    *reinterpret_cast<float4*>(p.co + (int64_t)r * p.ldco + hd * p.Hv + c) = acc;
+  }
+}
+
+// grid (rows), block 256*nh: thread group hd = tid/256 handles head hd; the heads' dq contributions are summed
+// through smem in a fixed order (deterministic) and ADDED to dq by group 0.
+__global__ void __launch_bounds__(512)
+attn2_bwd_kernel(const dlsg_attn2_bwd_t p) {
+  __shared__ float red[2][8][APM];
+  __shared__ float dl[2][APM];
+  __shared__ float dqs[1][1024];
+  const int r = blockIdx.x, hd = threadIdx.x >> 8, tid = threadIdx.x & 255, lane = tid & 31, w = tid >> 5;
+  const int c = tid * 4;
+  const bool ak = c < p.Hk, av = c < p.Hv;
+  const int64_t nk = (((int64_t)hd * p.rows + r) * p.P) * p.Hk, nv = (((int64_t)hd * p.rows + r) * p.P) * p.Hv;
+  const float* al = p.alpha + (int64_t)r * p.ldalpha + hd * p.P;
+  float4 k4[APM], v4[APM], q4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = q4;
+  if (ak) q4 = *reinterpret_cast<const float4*>(p.q + (int64_t)r * p.ldq + c);
+  if (av) d4 = *reinterpret_cast<const float4*>(p.dco + (int64_t)r * p.lddco + hd * p.Hv + c);
+#pragma unroll
+  for (int j = 0; j < APM; ++j) {
+    k4[j] = make_float4(0.f, 0.f, 0.f, 0.f); v4[j] = k4[j];
+    if (j < p.P) {
+      if (ak) k4[j] = *reinterpret_cast<const float4*>(p.KW + nk + (int64_t)j * p.Hk + c);
+      if (av) v4[j] = *reinterpret_cast<const float4*>(p.VW + nv + (int64_t)j * p.Hv + c);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < APM; ++j) {
+    const float s = warp_sum(dot4(v4[j], d4));
+    if (lane == 0) red[hd][w][j] = s;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float da[APM], dot = 0.f;
+    for (int j = 0; j < p.P; ++j) {
+      float s = 0.f;
+      for (int ww = 0; ww < 8; ++ww) s += red[hd][ww][j];
+      if (p.dalpha_ext) s += p.dalpha_ext[(int64_t)r * p.ldalpha + hd * p.P + j];
+      da[j] = s; dot = fmaf(al[j], s, dot);
+    }
+    for (int j = 0; j < p.P; ++j) dl[hd][j] = al[j] * (da[j] - dot) * p.scale;
+  }
+  __syncthreads();
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < APM; ++j) {
+    if (j < p.P) {
+      const float g = dl[hd][j], a = al[j];
+      if (ak) {
+        acc.x = fmaf(g, k4[j].x, acc.x); acc.y = fmaf(g, k4[j].y, acc.y); acc.z = fmaf(g, k4[j].z, acc.z); acc.w = fmaf(g, k4[j].w, acc.w);
+        float4* dk = reinterpret_cast<float4*>(p.dKW + nk + (int64_t)j * p.Hk + c);
+        float4 ok = *dk;
+        ok.x = fmaf(g, q4.x, ok.x); ok.y = fmaf(g, q4.y, ok.y); ok.z = fmaf(g, q4.z, ok.z); ok.w = fmaf(g, q4.w, ok.w);
+        *dk = ok;
+      }
+      if (av) {
+        float4* dv = reinterpret_cast<float4*>(p.dVW + nv + (int64_t)j * p.Hv + c);
+        float4 ov = *dv;
+        ov.x = fmaf(a, d4.x, ov.x); ov.y = fmaf(a, d4.y, ov.y); ov.z = fmaf(a, d4.z, ov.z); ov.w = fmaf(a, d4.w, ov.w);
+        *dv = ov;
+      }
+    }
+  }
+  if (hd > 0 && ak) *reinterpret_cast<float4*>(&dqs[hd - 1][c]) = acc;
+  __syncthreads();
+  if (hd == 0 && ak) {
+    for (int h2 = 1; h2 < p.nh; ++h2) {
+      const float4 o = *reinterpret_cast<const float4*>(&dqs[h2 - 1][c]);
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    float4* dq = reinterpret_cast<float4*>(p.dq + (int64_t)r * p.lddq + c);
+    float4 old = *dq;
+    old.x += acc.x; old.y += acc.y; old.z += acc.z; old.w += acc.w;
+    *dq = old;
+  }
+}
+
 static inline bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
 // ------------------------------------------------------------------------------------------- vocab rows
@@ -470,6 +600,25 @@ int dlsg_node_attn_bwd(const dlsg_node_attn_bwd_t* p, void* stream) {
   }
   node_attn_bwd_kernel<<<dim3(p->rows, p->nh), 128, 0, (cudaStream_t)stream>>>(*p);
   return check_launch("node_attn_bwd_kernel");
+}
+
+int dlsg_attn2_supported(int32_t nh, int32_t P, int32_t Hk, int32_t Hv) {
+  return (nh >= 1 && nh <= 2 && P >= 1 && P <= APM && Hk <= 1024 && Hv <= 1024 && Hk % 4 == 0 && Hv % 4 == 0) ? 1 : 0;
+}
+int dlsg_attn2_fwd(const dlsg_attn2_fwd_t* p, void* stream) {
+  DLSG_REQUIRE(dlsg_attn2_supported(p->nh, p->P, p->Hk, p->Hv), "attn2_fwd: unsupported shape nh=%d P=%d Hk=%d Hv=%d", p->nh, p->P, p->Hk, p->Hv);
+  DLSG_REQUIRE(al16(p->KW) && al16(p->VW) && al16(p->q) && al16(p->co) && p->ldq % 4 == 0 && p->ldco % 4 == 0, "attn2_fwd: unaligned operands");
+  if (p->rows <= 0) return 0;
+  attn2_fwd_kernel<<<dim3(p->rows, p->nh), 256, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch("attn2_fwd_kernel");
+}
+int dlsg_attn2_bwd(const dlsg_attn2_bwd_t* p, void* stream) {
+  DLSG_REQUIRE(dlsg_attn2_supported(p->nh, p->P, p->Hk, p->Hv), "attn2_bwd: unsupported shape nh=%d P=%d Hk=%d Hv=%d", p->nh, p->P, p->Hk, p->Hv);
+  DLSG_REQUIRE(al16(p->KW) && al16(p->VW) && al16(p->q) && al16(p->dco) && al16(p->dq) && al16(p->dKW) && al16(p->dVW) &&
+               p->ldq % 4 == 0 && p->lddco % 4 == 0 && p->lddq % 4 == 0, "attn2_bwd: unaligned operands");
+  if (p->rows <= 0) return 0;
+  attn2_bwd_kernel<<<p->rows, 256 * p->nh, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch("attn2_bwd_kernel");
 }
 int dlsg_row_argmax(const float* logits, int64_t ld, int32_t rows, int32_t V, int64_t* ids, int64_t ld_ids, void* stream) {
   if (rows <= 0) return 0;

@@ -76,7 +76,24 @@ class AttnBwdT(C.Structure):
                 ('dqp_dtype', i32), ('_pad', i32)]
 
 
+class Attn2FwdT(C.Structure):
+    _fields_ = [('KW', vp), ('VW', vp), ('q', vp), ('alpha', vp), ('co', vp),
+                ('ldq', i64), ('ldalpha', i64), ('ldco', i64),
+                ('rows', i32), ('nh', i32), ('P', i32), ('Hk', i32), ('Hv', i32), ('rows_per_node', i32), ('nodes', i32),
+                ('scale', f32)]
+
+
+class Attn2BwdT(C.Structure):
+    _fields_ = [('KW', vp), ('VW', vp), ('q', vp), ('alpha', vp), ('dco', vp), ('dalpha_ext', vp),
+                ('dq', vp), ('dKW', vp), ('dVW', vp),
+                ('ldq', i64), ('ldalpha', i64), ('lddco', i64), ('lddq', i64),
+                ('rows', i32), ('nh', i32), ('P', i32), ('Hk', i32), ('Hv', i32), ('scale', f32)]
+
+
 SIGNATURES = {
+    'dlsg_attn2_supported': (i32, [i32, i32, i32, i32]),
+    'dlsg_attn2_fwd': (i32, [C.POINTER(Attn2FwdT), vp]),
+    'dlsg_attn2_bwd': (i32, [C.POINTER(Attn2BwdT), vp]),
     'dlsg_version': (i32, []),
     'dlsg_sm_arch': (i32, []),
     'dlsg_last_error': (C.c_char_p, []),

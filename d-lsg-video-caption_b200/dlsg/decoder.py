@@ -129,6 +129,17 @@ class DecoderCore:
             be.mean_nodes_fwd(nodes[i], glob[:, i * H:(i + 1) * H])
         Gq = empty((Bn, 4 * self.Hq), nodes)
         be.gemm(op(glob), self.pk['Wg'], Gq, bias=self.pk['bq'])
+        self.hoist = be.attn2_supported(nh, P, self.Hq, H)
+        self.KpVp = (Kp, Vp)
+        if self.hoist:
+            # fold the query projection into K and the output projection into V once per sequence:
+            #   K_p.(Wq q) = (K_p Wq).q        Wo (sum_p a_p V_p) = sum_p a_p (Wo V_p)
+            KW = empty((nh, Bn, P, self.Hq), nodes)
+            VW = empty((nh, Bn, P, H), nodes)
+            for i, h in enumerate(self.heads):
+                be.gemm(op(Kp[i].view(Bn * P, H)), WC.get(t[pf + h + '.Q.weight'], transpose=True), KW[i].view(Bn * P, self.Hq))
+                be.gemm(op(Vp[i].view(Bn * P, H)), WC.get(t[pf + h + '.output_layer.0.weight']), VW[i].view(Bn * P, H))
+            return KW, VW, glob, Gq, n_op
         return Kp, Vp, glob, Gq, n_op
 
     # ------------------------------------------------------------------ one decode step
@@ -145,11 +156,16 @@ class DecoderCore:
         be.gemm(b.Xq[i], pk['Wq'], b.gq[i])
         be.lstm_cell_fwd(b.gq[i], b.cq[i], b.cq[j], h_out=b.qh[i], row_bias=(Gq if gq_rows is None else gq_rows),
                          h2=b.Xq[j][:, oQ:oQ + Hq])
-        be.norm_fwd(b.qh[i], t[pf + 'query_lstm_layernorm.weight'], t[pf + 'query_lstm_layernorm.bias'],
-                    y=b.Xl[i][:, oq:oq + Hq], stats=b.statq[i], drop=dq)
-        be.gemm(b.Xl[i][:, oq:oq + Hq], pk['Wqp'], b.qp[i])
-        be.node_attn_fwd(Kp, Vp, b.qp[i], b.alpha[i], b.ctxr[i], rows_per_node)
-        be.gemm(b.ctxr[i].view(R, nh, H).transpose(0, 1), pk['Wo'], b.co[i].view(R, nh, H).transpose(0, 1))
+        if self.hoist:
+            be.norm_fwd(b.qh[i], t[pf + 'query_lstm_layernorm.weight'], t[pf + 'query_lstm_layernorm.bias'],
+                        y=b.q32[i], y2=b.Xl[i][:, oq:oq + Hq], stats=b.statq[i], drop=dq)
+            be.attn2_fwd(Kp, Vp, b.q32[i], b.alpha[i], b.co[i], 1.0 / math.sqrt(H), rows_per_node)   # Kp,Vp hold KW,VW
+        else:
+            be.norm_fwd(b.qh[i], t[pf + 'query_lstm_layernorm.weight'], t[pf + 'query_lstm_layernorm.bias'],
+                        y=b.Xl[i][:, oq:oq + Hq], stats=b.statq[i], drop=dq)
+            be.gemm(b.Xl[i][:, oq:oq + Hq], pk['Wqp'], b.qp[i])
+            be.node_attn_fwd(Kp, Vp, b.qp[i], b.alpha[i], b.ctxr[i], rows_per_node)
+            be.gemm(b.ctxr[i].view(R, nh, H).transpose(0, 1), pk['Wo'], b.co[i].view(R, nh, H).transpose(0, 1))
         for k, h in enumerate(self.heads):
             be.norm_fwd(b.co[i][:, k * H:(k + 1) * H], t[pf + h + '.output_layer.2.weight'], t[pf + h + '.output_layer.2.bias'],
                         y=b.Xl[i][:, k * H:(k + 1) * H], stats=b.statc[i, k], pre_tanh=True,
@@ -173,10 +189,13 @@ class DecoderCore:
         b.statq = empty((S, R, 2), like)
         b.statl = empty((S, R, 2), like)
         b.statc = empty((S, nh, R, 2), like)
-        b.qp = empty((S, R, nh * H), like)
         b.alpha = empty((S, R, nh * P), like)
-        b.ctxr = op_empty((S, R), nh * H, like)
         b.co = empty((S, R, nh * H), like)
+        if getattr(self, 'hoist', False):
+            b.q32 = empty((S, R, Hq), like)
+        else:
+            b.qp = empty((S, R, nh * H), like)
+            b.ctxr = op_empty((S, R), nh * H, like)
         return b
 
 
@@ -303,10 +322,15 @@ class DecoderTrainBlock:
         dglT = op_empty((4 * Hd,), TB, ref)
         dgq32 = empty((B, 4 * Hq), ref)
         dgq_sum = zeros((B, 4 * Hq), ref)
-        dqp_all = op_empty((TB,), nh * H, ref)
-        dco_all = op_empty((T, B), nh * H, ref)
-        dctxr = empty((B, nh * H), ref)
-        dKp, dVp = zeros(Kp.shape, ref), zeros(Vp.shape, ref)
+        hoist = core.hoist
+        if hoist:
+            dco32 = empty((B, nh * H), ref)
+        else:
+            dqp_all = op_empty((TB,), nh * H, ref)
+            dco_all = op_empty((T, B), nh * H, ref)
+            dctxr = empty((B, nh * H), ref)
+        dKp, dVp = zeros(Kp.shape, ref), zeros(Vp.shape, ref)        # (dKW, dVW when hoisted)
+        att_scale = 1.0 / math.sqrt(H)
         dcq, dcq2 = zeros((B, Hq), ref), empty((B, Hq), ref)
         dcl, dcl2 = zeros((B, Hd), ref), empty((B, Hd), ref)
         for i in range(T - 1, -1, -1):
@@ -322,12 +346,17 @@ class DecoderTrainBlock:
             be.gemm(dgl_all[rows], pk['WlT'], dXl[i])
             for k, h in enumerate(heads):
                 be.norm_bwd(dXl[i][:, k * H:(k + 1) * H], b.co[i][:, k * H:(k + 1) * H], lnc[k][0], lnc[k][1], b.statc[i, k],
-                            dx=dco_all[i][:, k * H:(k + 1) * H], dgamma=lnc[k][2], dbeta=lnc[k][3], pre_tanh=True,
-                            drop=(None if dc is None else (dc[0], dc[1], dc[2] + (k << 28))))
-            be.gemm(dco_all[i].view(B, nh, H).transpose(0, 1), pk['WoT'], dctxr.view(B, nh, H).transpose(0, 1))
-            be.node_attn_bwd(Kp, Vp, b.qp[i], b.alpha[i], dctxr, dqp_all[rows], dKp, dVp,
+                            dx=(dco32 if hoist else dco_all[i])[:, k * H:(k + 1) * H], dgamma=lnc[k][2], dbeta=lnc[k][3],
+                            pre_tanh=True, drop=(None if dc is None else (dc[0], dc[1], dc[2] + (k << 28))))
+            if hoist:
+                # one kernel: d(alpha), softmax backward, dq += sum_h sum_p dl KW, dKW / dVW accumulated over time
+                be.attn2_bwd(Kp, Vp, b.q32[i], b.alpha[i], dco32, dXl[i][:, oq:oq + Hq], dKp, dVp, att_scale,
                              dalpha_ext=(da_ext[i] if da_ext is not None else None))
-            be.gemm(dqp_all[rows], pk['WqpT'], dXl[i][:, oq:oq + Hq], accum=True)
+            else:
+                be.gemm(dco_all[i].view(B, nh, H).transpose(0, 1), pk['WoT'], dctxr.view(B, nh, H).transpose(0, 1))
+                be.node_attn_bwd(Kp, Vp, b.qp[i], b.alpha[i], dctxr, dqp_all[rows], dKp, dVp,
+                                 dalpha_ext=(da_ext[i] if da_ext is not None else None))
+                be.gemm(dqp_all[rows], pk['WqpT'], dXl[i][:, oq:oq + Hq], accum=True)
             # query LN -> grad wrt query_h(i): accumulate onto recurrent grad from step i+1 (dXq[j][:, oQ:])
             be.norm_bwd(dXl[i][:, oq:oq + Hq], b.qh[i], lnq[0], lnq[1], b.statq[i], dx=dXq[j][:, oQ:oQ + Hq], dgamma=lnq[2],
                         dbeta=lnq[3], drop=dq, dx_accum=True)
@@ -363,13 +392,27 @@ class DecoderTrainBlock:
         be.colsum(dgl_all, dbl)
         grads[pf + 'lang_lstm.bias_ih'] = dbl
         grads[pf + 'lang_lstm.bias_hh'] = dbl
-        dWqp = la.mm(dqp_all.t(), Xl2[:, oq:oq + Hq].t())         # (nh*H, Hq)
-        dco2, ctx2 = flat2(dco_all), flat2(b.ctxr)
         dnodes = empty((nh, B, P, H), ref)
         n_op = sv['n_op']
+        if hoist:
+            # unfold the hoisted projections: KW = K Wq, VW = V Wo^T  (K, V = node projections saved by precompute)
+            K0, V0 = core.KpVp
+            dKW, dVW = dKp, dVp
+            dKp, dVp = empty(K0.shape, ref), empty(V0.shape, ref)
+            for k, h in enumerate(heads):
+                dKWo, dVWo = op(dKW[k].view(B * P, Hq)), op(dVW[k].view(B * P, H))
+                Ko, Vo = op(K0[k].view(B * P, H)), op(V0[k].view(B * P, H))
+                grads[pf + h + '.Q.weight'] = la.mm(Ko.t(), dKWo.t())                                  # (H, Hq)
+                grads[pf + h + '.output_layer.0.weight'] = la.mm(dVWo.t(), Vo.t())                    # (H, H)
+                be.gemm(dKWo, WC.get(t[pf + h + '.Q.weight']), dKp[k].view(B * P, H))
+                be.gemm(dVWo, WC.get(t[pf + h + '.output_layer.0.weight'], transpose=True), dVp[k].view(B * P, H))
+        else:
+            dWqp = la.mm(dqp_all.t(), Xl2[:, oq:oq + Hq].t())         # (nh*H, Hq)
+            dco2, ctx2 = flat2(dco_all), flat2(b.ctxr)
         for k, h in enumerate(heads):
-            grads[pf + h + '.Q.weight'] = dWqp[k * H:(k + 1) * H]
-            grads[pf + h + '.output_layer.0.weight'] = la.mm(dco2[:, k * H:(k + 1) * H].t(), ctx2[:, k * H:(k + 1) * H].t())
+            if not hoist:
+                grads[pf + h + '.Q.weight'] = dWqp[k * H:(k + 1) * H]
+                grads[pf + h + '.output_layer.0.weight'] = la.mm(dco2[:, k * H:(k + 1) * H].t(), ctx2[:, k * H:(k + 1) * H].t())
             dK2, dV2 = dKp[k].view(B * P, H), dVp[k].view(B * P, H)
             dKo, dVo = op(dK2), op(dV2)
             grads[pf + h + '.K.weight'] = la.mm(dKo.t(), n_op[k].t())

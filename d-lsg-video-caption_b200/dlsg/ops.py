@@ -303,6 +303,37 @@ class CudaBackend:
         self.launches += 1
         L.check(self.lib.dlsg_node_attn_bwd(C.byref(p), _stream()), 'dlsg_node_attn_bwd')
 
+    # ------------------------------------------------------------------ hoisted attention
+    @staticmethod
+    def attn2_supported(nh, P, Hk, Hv):
+        return 1 <= nh <= 2 and 1 <= P <= 8 and Hk <= 1024 and Hv <= 1024 and Hk % 4 == 0 and Hv % 4 == 0
+
+    def attn2_fwd(self, KW, VW, q, alpha, co, scale, rows_per_node=1):
+        """KW (nh,nodes,P,Hk), VW (nh,nodes,P,Hv) fp32 contiguous; q (rows,Hk) view; alpha (rows,nh*P); co (rows,nh*Hv) view."""
+        self._ck(KW)
+        p = L.Attn2FwdT()
+        nh, nodes, P, Hk = KW.shape
+        assert KW.is_contiguous() and VW.is_contiguous() and q.stride(1) == 1 and co.stride(1) == 1
+        p.KW, p.VW, p.q, p.alpha, p.co = KW.data_ptr(), VW.data_ptr(), q.data_ptr(), _ptr(alpha), co.data_ptr()
+        p.ldq, p.ldalpha, p.ldco = q.stride(0), (alpha.stride(0) if alpha is not None else 0), co.stride(0)
+        p.rows, p.nh, p.P, p.Hk, p.Hv, p.rows_per_node, p.nodes, p.scale = q.shape[0], nh, P, Hk, VW.shape[3], rows_per_node, nodes, scale
+        self.launches += 1
+        L.check(self.lib.dlsg_attn2_fwd(C.byref(p), _stream()), 'dlsg_attn2_fwd')
+
+    def attn2_bwd(self, KW, VW, q, alpha, dco, dq, dKW, dVW, scale, dalpha_ext=None):
+        self._ck(KW)
+        p = L.Attn2BwdT()
+        nh, nodes, P, Hk = KW.shape
+        assert nodes == q.shape[0] and dKW.is_contiguous() and dVW.is_contiguous() and dq.stride(1) == 1
+        p.KW, p.VW, p.q, p.alpha, p.dco, p.dalpha_ext = KW.data_ptr(), VW.data_ptr(), q.data_ptr(), alpha.data_ptr(), dco.data_ptr(), _ptr(dalpha_ext)
+        p.dq, p.dKW, p.dVW = dq.data_ptr(), dKW.data_ptr(), dVW.data_ptr()
+        p.ldq, p.ldalpha, p.lddco, p.lddq = q.stride(0), alpha.stride(0), dco.stride(0), dq.stride(0)
+        p.rows, p.nh, p.P, p.Hk, p.Hv, p.scale = q.shape[0], nh, P, Hk, VW.shape[3], scale
+        if dalpha_ext is not None:
+            assert dalpha_ext.stride(0) == alpha.stride(0)
+        self.launches += 1
+        L.check(self.lib.dlsg_attn2_bwd(C.byref(p), _stream()), 'dlsg_attn2_bwd')
+
     # ------------------------------------------------------------------ LatentPSL
     @staticmethod
     def latent_psl_supported(T, P, H):

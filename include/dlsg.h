@@ -150,6 +150,25 @@ typedef struct {
 } dlsg_node_attn_bwd_t;
 int dlsg_node_attn_bwd(const dlsg_node_attn_bwd_t* p, void* stream);
 
+/* ---- hoisted AttentionShare: query / output projections folded into the node tensors once per sequence
+ * (KW = K Wq (nh,nodes,P,Hk), VW = V Wo^T (nh,nodes,P,Hv)); a step is ONE kernel: logits_p = KW_p.q*scale, softmax over
+ * nodes, co = sum_p alpha_p VW_p (pre-LayerNorm context, sublayer.py:29-41).  Requires P<=8, Hk,Hv<=1024 (multiples of 4).
+ * bwd: dq (rows,Hk) += , dKW / dVW ACCUMULATED over the steps; heads are summed in a fixed order (deterministic).       */
+typedef struct {
+  const float* KW; const float* VW; const float* q; float* alpha; float* co;
+  int64_t ldq, ldalpha, ldco;
+  int32_t rows, nh, P, Hk, Hv, rows_per_node, nodes; float scale;
+} dlsg_attn2_fwd_t;
+typedef struct {
+  const float* KW; const float* VW; const float* q; const float* alpha; const float* dco; const float* dalpha_ext;
+  float* dq; float* dKW; float* dVW;
+  int64_t ldq, ldalpha, lddco, lddq;
+  int32_t rows, nh, P, Hk, Hv; float scale;
+} dlsg_attn2_bwd_t;
+int dlsg_attn2_supported(int32_t nh, int32_t P, int32_t Hk, int32_t Hv);
+int dlsg_attn2_fwd(const dlsg_attn2_fwd_t* p, void* stream);
+int dlsg_attn2_bwd(const dlsg_attn2_bwd_t* p, void* stream);
+
 /* ---- LatentPSL pooling (sublayer.py:191-196), one fused kernel per direction, one CTA per clip (P<=8, T<=32, H%4==0)
  * fwd: Gs (B,T,P) = softmax over T of X theta^T ; N (B,P,H) = Gs^T X.   bwd: dX (B,T,H) written, dtheta (P,H) ACCUMULATED. */
 int dlsg_latent_psl_fwd(const float* X, const float* theta, float* Gs, float* N, int32_t B, int32_t T, int32_t P, int32_t H, void* stream);

@@ -209,6 +209,37 @@ class CpuEmulBackend:
             dVp[h].add_(torch.einsum('rp,rh->rph', a, dc))
 
     @staticmethod
+    def attn2_supported(nh, P, Hk, Hv):
+        return 1 <= nh <= 2 and 1 <= P <= 8 and Hk <= 1024 and Hv <= 1024 and Hk % 4 == 0 and Hv % 4 == 0
+
+    def attn2_fwd(self, KW, VW, q, alpha, co, scale, rows_per_node=1):
+        self.launches += 1
+        nh, nodes, P, Hk = KW.shape
+        Hv = VW.shape[3]
+        idx = torch.arange(q.shape[0]) // rows_per_node
+        for h in range(nh):
+            lg = torch.einsum('rpk,rk->rp', KW[h][idx], q) * scale
+            a = torch.softmax(lg, 1)
+            if alpha is not None:
+                alpha[:, h * P:(h + 1) * P].copy_(a)
+            co[:, h * Hv:(h + 1) * Hv].copy_(torch.einsum('rp,rpv->rv', a, VW[h][idx]))
+
+    def attn2_bwd(self, KW, VW, q, alpha, dco, dq, dKW, dVW, scale, dalpha_ext=None):
+        self.launches += 1
+        nh, nodes, P, Hk = KW.shape
+        Hv = VW.shape[3]
+        for h in range(nh):
+            a = alpha[:, h * P:(h + 1) * P]
+            dc = dco[:, h * Hv:(h + 1) * Hv]
+            da = torch.einsum('rpv,rv->rp', VW[h], dc)
+            if dalpha_ext is not None:
+                da = da + dalpha_ext[:, h * P:(h + 1) * P]
+            dl = a * (da - (a * da).sum(1, keepdim=True)) * scale
+            dq.add_(torch.einsum('rp,rpk->rk', dl, KW[h]))
+            dKW[h].add_(torch.einsum('rp,rk->rpk', dl, q))
+            dVW[h].add_(torch.einsum('rp,rv->rpv', a, dc))
+
+    @staticmethod
     def latent_psl_supported(T, P, H):
         return P <= 8 and T <= 32 and H % 4 == 0
 

@@ -169,3 +169,28 @@ def test_state_dict_keys_match_reference_dump(golden_dir):
     ours = {k for k, _ in net.named_parameters()}
     assert ours == ref_params
     assert 'encoder.motion_pre_encoder.self_attention.pe.pe' in net.state_dict()
+
+
+def test_baseline1_many_frames_uses_per_step_projection_path():
+    """P = 10 attention nodes (> 8): the non-hoisted AttentionShare path (per-step q/out projections) vs the oracle."""
+    la.set_precision('fp32')
+    args, V, B = synth.small_args(decode_hidden_size=52, max_frames=10), 37, 2
+    net = _build('CapBaseline1', args, V)
+    net.eval()
+    sd = _sd(net)
+    for v in sd.values():
+        v.requires_grad_(True)
+    frames, regions, caps, lens = synth.make_inputs(B, args, V, seed=21)
+    out = net(frames, regions, caps, args.max_words, 1.0)[0]
+    ro = O.cap_baseline1_forward(sd, frames, caps, args.max_words, 1.0)
+    assert (out - ro).abs().max() < 3e-5
+    O.packed_ce_loss(out, caps, lens).backward()
+    O.packed_ce_loss(ro, caps, lens).backward()
+    for k, p in net.named_parameters():
+        if p.grad is None:
+            continue
+        ref = sd[k].grad
+        assert float((p.grad - ref).abs().max()) < 1e-7 or float((p.grad - ref).norm() / (ref.norm() + 1e-8)) < 1e-4, k
+    with torch.no_grad():
+        net.update_beam_size(3)
+        assert torch.equal(net(frames, regions, None)[0], O.cap_baseline1_forward(sd, frames, None, args.max_words, beam_size=3))

@@ -207,6 +207,18 @@ def test_node_attn(be, nh, P, H, rpn):
              dict(dalpha_ext=R(rows, nh * P)), [5, 6, 7], tol=3e-5)
 
 
+@pytest.mark.parametrize('nh,P,Hk,Hv,rpn', [(2, 5, 1024, 1024, 1), (2, 8, 64, 64, 1), (1, 6, 64, 96, 1), (2, 5, 1024, 1024, 5)])
+def test_attn2_hoisted(be, nh, P, Hk, Hv, rpn):
+    nodes, rows = 6, 6 * rpn
+    KW, VW, q = R(nh, nodes, P, Hk, scale=0.3), R(nh, nodes, P, Hv), R(rows, Hk + 8)[:, :Hk]
+    alpha = torch.zeros(rows, nh * P)
+    both('attn2_fwd', be, [KW, VW, q, alpha, torch.zeros(rows, nh * Hv + 4)[:, :nh * Hv], 0.11, rpn], {}, [3, 4], tol=2e-5)
+    if rpn == 1:
+        EM.attn2_fwd(KW, VW, q, alpha, torch.zeros(rows, nh * Hv), 0.11, 1)
+        both('attn2_bwd', be, [KW, VW, q, alpha, R(rows, nh * Hv), R(rows, Hk + 12)[:, 4:4 + Hk], R(nh, nodes, P, Hk), R(nh, nodes, P, Hv), 0.11],
+             dict(dalpha_ext=R(rows, nh * P)), [5, 6, 7], tol=3e-5)
+
+
 @pytest.mark.parametrize('B_,T,P,H', [(6, 26, 5, 1024), (3, 26, 8, 64), (4, 26, 1, 512), (2, 6, 5, 64)])
 def test_latent_psl(be, B_, T, P, H):
     X, theta = R(B_, T, H), R(P, H, scale=0.05)
