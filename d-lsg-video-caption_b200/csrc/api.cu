@@ -1,6 +1,7 @@
 // C-ABI glue: error reporting, version, GEMM dispatch (see include/dlsg.h).
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace dlsg {
@@ -22,6 +23,12 @@ int check_launch(const char* what) {
     return (int)e;
   }
   return 0;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DLSG_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
 }
 
 int gemm_tc_dispatch(const dlsg_gemm_t* g, cudaStream_t st);

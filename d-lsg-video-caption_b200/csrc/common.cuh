@@ -21,6 +21,29 @@ int check_launch(const char* what);
 
 constexpr int kNumSM = 148;
 
+// ---- launch helper: every kernel is launched with programmatic stream serialization (PDL) so that, inside a stream or
+// a captured CUDA graph, the next kernel's CTAs are scheduled and run their prologue while the previous kernel drains.
+// Kernels call pdl_prologue() before touching global memory (griddepcontrol.wait = all prerequisite grids complete and
+// their writes visible).  DLSG_PDL=0 disables the attribute.
+bool pdl_enabled();
+template <typename K, typename... Args>
+inline void launch(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+#define DLSG_LAUNCH(kernel, grid, block, smem, st, ...) ::dlsg::launch(kernel, dim3(grid), dim3(block), smem, st, __VA_ARGS__)
+
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

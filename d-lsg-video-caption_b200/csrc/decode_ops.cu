@@ -12,6 +12,7 @@ constexpr int MAXK = 16;    // max beam / per-node beam
 // grid (rows, nh); 128 threads.  logits_p = K_p . q / sqrt(H); alpha = softmax_p; ctx = sum_p alpha_p V_p
 __global__ void __launch_bounds__(128)
 node_attn_fwd_kernel(const dlsg_node_attn_fwd_t p) {
+  pdl_prologue();
   __shared__ float lg[MAXP];
   const int r = blockIdx.x, hd = blockIdx.y;
   const int node = r / p.rows_per_node;
@@ -49,6 +50,7 @@ node_attn_fwd_kernel(const dlsg_node_attn_fwd_t p) {
 // backward of one step (training: one row per node set).  dKp / dVp accumulate across the 26 steps.
 __global__ void __launch_bounds__(128)
 node_attn_bwd_kernel(const dlsg_node_attn_bwd_t p) {
+  pdl_prologue();
   __shared__ float da[MAXP];
   __shared__ float dl[MAXP];
   const int r = blockIdx.x, hd = blockIdx.y;
@@ -94,6 +96,7 @@ __device__ __forceinline__ float dot4(const float4 a, const float4 b) { return (
 
 __global__ void __launch_bounds__(256)
 node_attn_fwd_fast(const dlsg_node_attn_fwd_t p) {
+  pdl_prologue();
   __shared__ float red[8][APM];
   __shared__ float al[APM];
   const int r = blockIdx.x, hd = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -155,6 +158,7 @@ node_attn_fwd_fast(const dlsg_node_attn_fwd_t p) {
 
 __global__ void __launch_bounds__(256)
 node_attn_bwd_fast(const dlsg_node_attn_bwd_t p) {
+  pdl_prologue();
   __shared__ float red[8][APM];
   __shared__ float dl[APM];
   const int r = blockIdx.x, hd = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -224,6 +228,7 @@ node_attn_bwd_fast(const dlsg_node_attn_bwd_t p) {
 //   logits_p = KW_p . q * scale ; alpha = softmax_p ; co = sum_p alpha_p VW_p   (pre-LayerNorm context, sublayer.py:29-41)
 __global__ void __launch_bounds__(256)
 attn2_fwd_kernel(const dlsg_attn2_fwd_t p) {
+  pdl_prologue();
   __shared__ float red[8][APM];
   __shared__ float al[APM];
   const int r = blockIdx.x, hd = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -279,6 +284,7 @@ attn2_fwd_kernel(const dlsg_attn2_fwd_t p) {
 // through smem in a fixed order (deterministic) and ADDED to dq by group 0.
 __global__ void __launch_bounds__(512)
 attn2_bwd_kernel(const dlsg_attn2_bwd_t p) {
+  pdl_prologue();
   __shared__ float red[2][8][APM];
   __shared__ float dl[2][APM];
   __shared__ float dqs[1][1024];
@@ -368,6 +374,7 @@ __device__ __forceinline__ ArgMax warp_argmax(ArgMax a) {
 
 __global__ void __launch_bounds__(256)
 row_argmax_kernel(const float* __restrict__ logits, int64_t ld, int V, int64_t* __restrict__ ids, int64_t ld_ids) {
+  pdl_prologue();
   __shared__ float sv[8]; __shared__ int si[8];
   const float* x = logits + (int64_t)blockIdx.x * ld;
   ArgMax a; a.v = -INFINITY; a.i = 0x7fffffff;
@@ -385,6 +392,7 @@ row_argmax_kernel(const float* __restrict__ logits, int64_t ld, int V, int64_t* 
 
 __global__ void __launch_bounds__(256)
 log_softmax_kernel(const float* __restrict__ logits, int64_t ld, int V, float* __restrict__ out, int64_t ldo) {
+  pdl_prologue();
   __shared__ float red[32];
   const float* x = logits + (int64_t)blockIdx.x * ld;
   float mx = -INFINITY;
@@ -403,6 +411,7 @@ __global__ void __launch_bounds__(256)
 ce_masked_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targets, const int32_t* __restrict__ lens,
                  int L, int V, float* __restrict__ loss_sum, float* __restrict__ dlogits, float inv_count_host,
                  const float* __restrict__ inv_count_dev) {
+  pdl_prologue();
   __shared__ float red[32];
   const float inv_count = inv_count_dev ? *inv_count_dev : inv_count_host;
   const int row = blockIdx.x, b = row / L, t = row % L;
@@ -455,6 +464,7 @@ template <int KT>
 __global__ void __launch_bounds__(256)
 beam_topk_kernel(const float* __restrict__ logits, int64_t ld, int V, const int64_t* __restrict__ last, int end_index, int k,
                  float* __restrict__ top_lp, int64_t* __restrict__ top_id, int normalize) {
+  pdl_prologue();
   __shared__ float red[32];
   __shared__ float cv[8 * MAXK];
   __shared__ int ci[8 * MAXK];
@@ -522,6 +532,7 @@ __global__ void __launch_bounds__(32)
 beam_merge_kernel(const float* __restrict__ top_lp, const int64_t* __restrict__ top_id, const float* __restrict__ last_lp,
                   int beam, int k, float* __restrict__ new_lp, int64_t* __restrict__ new_cls, int64_t* __restrict__ backptr,
                   int32_t* __restrict__ all_end, int end_index) {
+  pdl_prologue();
   const int b = blockIdx.x, lane = threadIdx.x;
   const int n = beam * k;
   // each lane holds up to 8 candidates (n <= 256)
@@ -554,6 +565,7 @@ beam_merge_kernel(const float* __restrict__ top_lp, const int64_t* __restrict__ 
 
 __global__ void beam_gather_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const int64_t* __restrict__ backptr,
                                    int beam, int W) {
+  pdl_prologue();
   const int row = blockIdx.x;                 // b*beam + j ; W = row length in 32-bit words
   const int b = row / beam;
   const int64_t srow = (int64_t)b * beam + backptr[row];
@@ -562,6 +574,7 @@ __global__ void beam_gather_kernel(const uint32_t* __restrict__ src, uint32_t* _
 
 __global__ void beam_backtrack_kernel(const int64_t* __restrict__ preds, const int64_t* __restrict__ backs, int S, int B, int beam,
                                       int64_t* __restrict__ out) {
+  pdl_prologue();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= B * beam) return;
   const int b = e / beam;
@@ -584,10 +597,10 @@ int dlsg_node_attn_fwd(const dlsg_node_attn_fwd_t* p, void* stream) {
   const int es = p->ctx_dtype == DLSG_F32 ? 4 : 2;
   if (p->P <= APM && p->H <= 1024 && p->H % 4 == 0 && al16(p->Kp) && al16(p->Vp) && al16(p->qp) &&
       (reinterpret_cast<uintptr_t>(p->ctx) % (4 * es)) == 0 && p->ldctx % 4 == 0) {
-    node_attn_fwd_fast<<<dim3(p->rows, p->nh), 256, 0, (cudaStream_t)stream>>>(*p);
+    DLSG_LAUNCH(node_attn_fwd_fast, dim3(p->rows, p->nh), 256, 0, (cudaStream_t)stream, *p);
     return check_launch("node_attn_fwd_fast");
   }
-  node_attn_fwd_kernel<<<dim3(p->rows, p->nh), 128, 0, (cudaStream_t)stream>>>(*p);
+  DLSG_LAUNCH(node_attn_fwd_kernel, dim3(p->rows, p->nh), 128, 0, (cudaStream_t)stream, *p);
   return check_launch("node_attn_fwd_kernel");
 }
 int dlsg_node_attn_bwd(const dlsg_node_attn_bwd_t* p, void* stream) {
@@ -595,10 +608,10 @@ int dlsg_node_attn_bwd(const dlsg_node_attn_bwd_t* p, void* stream) {
   const int es = p->dqp_dtype == DLSG_F32 ? 4 : 2;
   if (p->P <= APM && p->H <= 1024 && p->H % 4 == 0 && al16(p->Kp) && al16(p->Vp) && al16(p->qp) && al16(p->dKp) && al16(p->dVp) &&
       al16(p->dctx) && p->lddctx % 4 == 0 && (reinterpret_cast<uintptr_t>(p->dqp) % (4 * es)) == 0) {
-    node_attn_bwd_fast<<<dim3(p->rows, p->nh), 256, 0, (cudaStream_t)stream>>>(*p);
+    DLSG_LAUNCH(node_attn_bwd_fast, dim3(p->rows, p->nh), 256, 0, (cudaStream_t)stream, *p);
     return check_launch("node_attn_bwd_fast");
   }
-  node_attn_bwd_kernel<<<dim3(p->rows, p->nh), 128, 0, (cudaStream_t)stream>>>(*p);
+  DLSG_LAUNCH(node_attn_bwd_kernel, dim3(p->rows, p->nh), 128, 0, (cudaStream_t)stream, *p);
   return check_launch("node_attn_bwd_kernel");
 }
 
@@ -609,7 +622,7 @@ int dlsg_attn2_fwd(const dlsg_attn2_fwd_t* p, void* stream) {
   DLSG_REQUIRE(dlsg_attn2_supported(p->nh, p->P, p->Hk, p->Hv), "attn2_fwd: unsupported shape nh=%d P=%d Hk=%d Hv=%d", p->nh, p->P, p->Hk, p->Hv);
   DLSG_REQUIRE(al16(p->KW) && al16(p->VW) && al16(p->q) && al16(p->co) && p->ldq % 4 == 0 && p->ldco % 4 == 0, "attn2_fwd: unaligned operands");
   if (p->rows <= 0) return 0;
-  attn2_fwd_kernel<<<dim3(p->rows, p->nh), 256, 0, (cudaStream_t)stream>>>(*p);
+  DLSG_LAUNCH(attn2_fwd_kernel, dim3(p->rows, p->nh), 256, 0, (cudaStream_t)stream, *p);
   return check_launch("attn2_fwd_kernel");
 }
 int dlsg_attn2_bwd(const dlsg_attn2_bwd_t* p, void* stream) {
@@ -617,23 +630,23 @@ int dlsg_attn2_bwd(const dlsg_attn2_bwd_t* p, void* stream) {
   DLSG_REQUIRE(al16(p->KW) && al16(p->VW) && al16(p->q) && al16(p->dco) && al16(p->dq) && al16(p->dKW) && al16(p->dVW) &&
                p->ldq % 4 == 0 && p->lddco % 4 == 0 && p->lddq % 4 == 0, "attn2_bwd: unaligned operands");
   if (p->rows <= 0) return 0;
-  attn2_bwd_kernel<<<p->rows, 256 * p->nh, 0, (cudaStream_t)stream>>>(*p);
+  DLSG_LAUNCH(attn2_bwd_kernel, p->rows, 256 * p->nh, 0, (cudaStream_t)stream, *p);
   return check_launch("attn2_bwd_kernel");
 }
 int dlsg_row_argmax(const float* logits, int64_t ld, int32_t rows, int32_t V, int64_t* ids, int64_t ld_ids, void* stream) {
   if (rows <= 0) return 0;
-  row_argmax_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(logits, ld, V, ids, ld_ids);
+  DLSG_LAUNCH(row_argmax_kernel, rows, 256, 0, (cudaStream_t)stream, logits, ld, V, ids, ld_ids);
   return check_launch("row_argmax_kernel");
 }
 int dlsg_log_softmax(const float* logits, int64_t ld, int32_t rows, int32_t V, float* out, int64_t ldo, void* stream) {
   if (rows <= 0) return 0;
-  log_softmax_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(logits, ld, V, out, ldo);
+  DLSG_LAUNCH(log_softmax_kernel, rows, 256, 0, (cudaStream_t)stream, logits, ld, V, out, ldo);
   return check_launch("log_softmax_kernel");
 }
 int dlsg_ce_masked(const float* logits, const int64_t* targets, const int32_t* lens, int32_t B, int32_t L, int32_t V,
                    float* loss_sum, float* dlogits, float inv_count, const float* inv_count_dev, void* stream) {
   if (B * L <= 0) return 0;
-  ce_masked_kernel<<<B * L, 256, 0, (cudaStream_t)stream>>>(logits, targets, lens, L, V, loss_sum, dlogits, inv_count, inv_count_dev);
+  DLSG_LAUNCH(ce_masked_kernel, B * L, 256, 0, (cudaStream_t)stream, logits, targets, lens, L, V, loss_sum, dlogits, inv_count, inv_count_dev);
   return check_launch("ce_masked_kernel");
 }
 int dlsg_beam_topk(const float* logits, int64_t ld, int32_t rows, int32_t V, const int64_t* last, int32_t end_index,
@@ -642,29 +655,29 @@ int dlsg_beam_topk(const float* logits, int64_t ld, int32_t rows, int32_t V, con
   DLSG_REQUIRE(k <= V, "beam_topk: Target vocab size (%d) too small relative to per_node_beam_size (%d)", V, k);
   if (rows <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (k <= 1) beam_topk_kernel<1><<<rows, 256, 0, st>>>(logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
-  else if (k <= 3) beam_topk_kernel<3><<<rows, 256, 0, st>>>(logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
-  else if (k <= 5) beam_topk_kernel<5><<<rows, 256, 0, st>>>(logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
-  else if (k <= 8) beam_topk_kernel<8><<<rows, 256, 0, st>>>(logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
-  else beam_topk_kernel<16><<<rows, 256, 0, st>>>(logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
+  if (k <= 1) DLSG_LAUNCH(beam_topk_kernel<1>, rows, 256, 0, st, logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
+  else if (k <= 3) DLSG_LAUNCH(beam_topk_kernel<3>, rows, 256, 0, st, logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
+  else if (k <= 5) DLSG_LAUNCH(beam_topk_kernel<5>, rows, 256, 0, st, logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
+  else if (k <= 8) DLSG_LAUNCH(beam_topk_kernel<8>, rows, 256, 0, st, logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
+  else DLSG_LAUNCH(beam_topk_kernel<16>, rows, 256, 0, st, logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
   return check_launch("beam_topk_kernel");
 }
 int dlsg_beam_merge(const float* top_lp, const int64_t* top_id, const float* last_lp, int32_t B, int32_t beam, int32_t k,
                     float* new_lp, int64_t* new_cls, int64_t* backptr, int32_t* all_end, int32_t end_index, void* stream) {
   DLSG_REQUIRE(beam * k <= 256 && beam >= 1 && k >= 1, "beam_merge: beam*k=%d > 256", beam * k);
   if (B <= 0) return 0;
-  beam_merge_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(top_lp, top_id, last_lp, beam, k, new_lp, new_cls, backptr, all_end, end_index);
+  DLSG_LAUNCH(beam_merge_kernel, B, 32, 0, (cudaStream_t)stream, top_lp, top_id, last_lp, beam, k, new_lp, new_cls, backptr, all_end, end_index);
   return check_launch("beam_merge_kernel");
 }
 int dlsg_beam_gather(const void* src, void* dst, const int64_t* backptr, int32_t B, int32_t beam, int32_t row_bytes, void* stream) {
   if (B * beam <= 0) return 0;
   DLSG_REQUIRE(row_bytes % 4 == 0, "beam_gather: row_bytes must be a multiple of 4");
-  beam_gather_kernel<<<B * beam, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)src, (uint32_t*)dst, backptr, beam, row_bytes / 4);
+  DLSG_LAUNCH(beam_gather_kernel, B * beam, 256, 0, (cudaStream_t)stream, (const uint32_t*)src, (uint32_t*)dst, backptr, beam, row_bytes / 4);
   return check_launch("beam_gather_kernel");
 }
 int dlsg_beam_backtrack(const int64_t* preds, const int64_t* backs, int32_t S, int32_t B, int32_t beam, int64_t* out, void* stream) {
   if (B * beam <= 0 || S <= 0) return 0;
-  beam_backtrack_kernel<<<(B * beam + 127) / 128, 128, 0, (cudaStream_t)stream>>>(preds, backs, S, B, beam, out);
+  DLSG_LAUNCH(beam_backtrack_kernel, (B * beam + 127) / 128, 128, 0, (cudaStream_t)stream, preds, backs, S, B, beam, out);
   return check_launch("beam_backtrack_kernel");
 }
 

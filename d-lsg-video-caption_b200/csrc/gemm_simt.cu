@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const TA* __restrict__ A, const TB* __restrict__ B, void* __restrict__ D, const float* __restrict__ bias,
                  int M, int N, int K, int64_t sam, int64_t sak, int64_t sbn, int64_t sbk, int64_t ldd,
                  int64_t stride_a, int64_t stride_b, int64_t stride_d, int d_dtype, int flags, float alpha) {
+  pdl_prologue();
   __shared__ float As[SK][SB + 4];
   __shared__ float Bs[SK][SB + 4];
   const int tid = threadIdx.x;
@@ -91,7 +92,7 @@ int gemm_simt_dispatch(const dlsg_gemm_t* g, cudaStream_t st) {
   dim3 grid((g->N + SB - 1) / SB, (g->M + SB - 1) / SB, batch);
   DLSG_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm_simt: grid too large");
 #define DLSG_SIMT_LAUNCH(TA, TB)                                                                                     \
-  gemm_simt_kernel<TA, TB><<<grid, 256, 0, st>>>((const TA*)g->A, (const TB*)g->B, g->D, g->bias, g->M, g->N, g->K,   \
+  DLSG_LAUNCH((gemm_simt_kernel<TA, TB>), grid, 256, 0, st, (const TA*)g->A, (const TB*)g->B, g->D, g->bias, g->M, g->N, g->K,   \
                                                  g->sam, g->sak, g->sbn, g->sbk, g->ldd, g->stride_a, g->stride_b,     \
                                                  g->stride_d, g->d_dtype, g->flags, g->alpha)
   if (g->a_dtype == DLSG_F32 && g->b_dtype == DLSG_F32) DLSG_SIMT_LAUNCH(float, float);

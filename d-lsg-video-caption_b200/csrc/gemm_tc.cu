@@ -149,6 +149,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_prologue();      // barrier init / TMEM allocation above overlap the previous kernel's tail; operands are read below
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -364,6 +365,7 @@ static int make_map(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t K, i
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ ws, int S, int batch, int M, int N, void* __restrict__ D, int d_dtype, int64_t ldd,
                      int64_t stride_d, const float* __restrict__ bias, int flags, float alpha) {
+  pdl_prologue();
   const int64_t per = (int64_t)M * N, total = per * batch;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int b = (int)(e / per);
@@ -392,7 +394,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcParam
     DLSG_REQUIRE(e == cudaSuccess, "gemm_tc: cudaFuncSetAttribute(%d) failed: %s", Cfg::SMEM, cudaGetErrorString(e));
     attr_set = true;
   }
-  gemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, st>>>(ta, tb, prm);
+  DLSG_LAUNCH(gemm_tc_kernel<BN>, grid, TC_THREADS, Cfg::SMEM, st, ta, tb, prm);
   return check_launch("gemm_tc_kernel");
 }
 
@@ -424,7 +426,7 @@ int gemm_tc_dispatch(const dlsg_gemm_t* g, cudaStream_t st) {
         const int64_t total = (int64_t)batch * g->M * g->N;
         int64_t blocks = (total + 255) / 256;
         if (blocks > kNumSM * 8) blocks = kNumSM * 8;
-        splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>((const float*)g->workspace, S, batch, g->M, g->N, g->D, g->d_dtype,
+        DLSG_LAUNCH(splitk_reduce_kernel, (unsigned)blocks, 256, 0, st, (const float*)g->workspace, S, batch, g->M, g->N, g->D, g->d_dtype,
                                                                g->ldd, g->stride_d, g->bias, g->flags, g->alpha);
         return check_launch("splitk_reduce_kernel");
       }

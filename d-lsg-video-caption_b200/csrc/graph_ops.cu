@@ -37,6 +37,7 @@ __device__ __forceinline__ void lp_row_dots(const float* __restrict__ X, const f
 __global__ void __launch_bounds__(256)
 latent_psl_fwd_kernel(const float* __restrict__ X, const float* __restrict__ theta, float* __restrict__ Gs, float* __restrict__ N,
                       int T, int P, int H) {
+  pdl_prologue();
   extern __shared__ float sm[];                // theta (P x H)
   __shared__ float g[LP_MAXT][LP_MAXP];
   const int b = blockIdx.x;
@@ -76,6 +77,7 @@ latent_psl_fwd_kernel(const float* __restrict__ X, const float* __restrict__ the
 __global__ void __launch_bounds__(256)
 latent_psl_bwd_kernel(const float* __restrict__ X, const float* __restrict__ theta, const float* __restrict__ Gs,
                       const float* __restrict__ dN, float* __restrict__ dX, float* __restrict__ dtheta, int T, int P, int H) {
+  pdl_prologue();
   extern __shared__ float sm[];                // dN (P x H) then theta (P x H)
   __shared__ float gs[LP_MAXT][LP_MAXP];
   __shared__ float dg[LP_MAXT][LP_MAXP];
@@ -139,7 +141,7 @@ int dlsg_latent_psl_fwd(const float* X, const float* theta, float* Gs, float* N,
   DLSG_REQUIRE(smem <= 200 * 1024, "latent_psl_fwd: P*H too large");
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(latent_psl_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-  latent_psl_fwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(X, theta, Gs, N, T, P, H);
+  DLSG_LAUNCH(latent_psl_fwd_kernel, B, 256, smem, (cudaStream_t)stream, X, theta, Gs, N, T, P, H);
   return check_launch("latent_psl_fwd_kernel");
 }
 
@@ -151,7 +153,7 @@ int dlsg_latent_psl_bwd(const float* X, const float* theta, const float* Gs, con
   DLSG_REQUIRE(smem <= 200 * 1024, "latent_psl_bwd: P*H too large");
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(latent_psl_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-  latent_psl_bwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(X, theta, Gs, dN, dX, dtheta, T, P, H);
+  DLSG_LAUNCH(latent_psl_bwd_kernel, B, 256, smem, (cudaStream_t)stream, X, theta, Gs, dN, dX, dtheta, T, P, H);
   return check_launch("latent_psl_bwd_kernel");
 }
 

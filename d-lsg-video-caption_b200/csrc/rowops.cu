@@ -10,6 +10,7 @@ namespace dlsg {
 __global__ void __launch_bounds__(256)
 convert2d_kernel(const void* __restrict__ src_, int sdt, int64_t lds, void* __restrict__ dst_, int ddt, int64_t ldd,
                  void* __restrict__ dstT_, int64_t ldt, int64_t rows, int64_t cols, int64_t bs_src, int64_t bs_dst, int64_t bs_dstT) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const int es = sdt == DLSG_F32 ? 4 : 2, ed = ddt == DLSG_F32 ? 4 : 2;
   const void* src = reinterpret_cast<const uint8_t*>(src_) + (int64_t)blockIdx.z * bs_src * es;
@@ -39,6 +40,7 @@ convert2d_kernel(const void* __restrict__ src_, int sdt, int64_t lds, void* __re
 // flat vectorised cast fp32 -> bf16 (contiguous case): 8 elements / thread, 2x128-bit loads, 1x128-bit store
 __global__ void __launch_bounds__(256)
 cast_f32_bf16_flat(const float4* __restrict__ src, uint4* __restrict__ dst, int64_t n8) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 a = __ldg(src + 2 * i), b = __ldg(src + 2 * i + 1);
     __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
@@ -76,6 +78,7 @@ static inline bool vec_ok(const void* p, int dt, int64_t ld, int D) {
 template <bool VEC>
 __global__ void __launch_bounds__(256)
 norm_fwd_kernel(const dlsg_norm_fwd_t p) {
+  pdl_prologue();
   extern __shared__ float srow[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float* t = srow + (size_t)w * p.D;
@@ -139,6 +142,7 @@ norm_fwd_kernel(const dlsg_norm_fwd_t p) {
 template <int NV>
 __global__ void __launch_bounds__(128)
 norm_fwd_vec_kernel(const dlsg_norm_fwd_t p) {
+  pdl_prologue();
   const int D = p.D;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const float invD = 1.f / (float)D;
@@ -203,7 +207,7 @@ static int norm_fwd_vec_launch(const dlsg_norm_fwd_t* p, cudaStream_t st) {
   const int nw = 4;
   int64_t blocks = (p->rows + nw - 1) / nw;
   if (blocks > kNumSM * 8) blocks = kNumSM * 8;
-  norm_fwd_vec_kernel<NV><<<(unsigned)blocks, nw * 32, 0, st>>>(*p);
+  DLSG_LAUNCH(norm_fwd_vec_kernel<NV>, (unsigned)blocks, nw * 32, 0, st, *p);
   return check_launch("norm_fwd_vec_kernel");
 }
 
@@ -234,8 +238,8 @@ int norm_fwd_launch(const dlsg_norm_fwd_t* p, cudaStream_t st) {
     cudaFuncSetAttribute(norm_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     attr = true;
   }
-  if (vec) norm_fwd_kernel<true><<<(unsigned)blocks, nw * 32, smem, st>>>(*p);
-  else norm_fwd_kernel<false><<<(unsigned)blocks, nw * 32, smem, st>>>(*p);
+  if (vec) DLSG_LAUNCH(norm_fwd_kernel<true>, (unsigned)blocks, nw * 32, smem, st, *p);
+  else DLSG_LAUNCH(norm_fwd_kernel<false>, (unsigned)blocks, nw * 32, smem, st, *p);
   return check_launch("norm_fwd_kernel");
 }
 
@@ -245,6 +249,7 @@ int norm_fwd_launch(const dlsg_norm_fwd_t* p, cudaStream_t st) {
 template <bool VEC>
 __global__ void __launch_bounds__(128)
 norm_bwd_kernel(const dlsg_norm_bwd_t p) {
+  pdl_prologue();
   extern __shared__ float sm[];
   const int D = p.D;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -305,6 +310,7 @@ norm_bwd_kernel(const dlsg_norm_bwd_t p) {
 template <int NV>
 __global__ void __launch_bounds__(128)
 norm_bwd_vec_kernel(const dlsg_norm_bwd_t p) {
+  pdl_prologue();
   extern __shared__ float sm[];          // [nw][2][D]
   const int D = p.D;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -421,7 +427,7 @@ static int norm_bwd_vec_launch(const dlsg_norm_bwd_t* p, cudaStream_t st) {
     cudaFuncSetAttribute(norm_bwd_vec_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, nw * 2 * 128 * NV * 4);
     attr = true;
   }
-  norm_bwd_vec_kernel<NV><<<(unsigned)blocks, nw * 32, smem, st>>>(*p);
+  DLSG_LAUNCH(norm_bwd_vec_kernel<NV>, (unsigned)blocks, nw * 32, smem, st, *p);
   return check_launch("norm_bwd_vec_kernel");
 }
 
@@ -449,13 +455,14 @@ int norm_bwd_launch(const dlsg_norm_bwd_t* p, cudaStream_t st) {
     cudaFuncSetAttribute(norm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 10 * 4096 * 4);
     attr = true;
   }
-  norm_bwd_kernel<false><<<(unsigned)blocks, nw * 32, smem, st>>>(*p);
+  DLSG_LAUNCH(norm_bwd_kernel<false>, (unsigned)blocks, nw * 32, smem, st, *p);
   return check_launch("norm_bwd_kernel");
 }
 
 // ------------------------------------------------------------------------------------------- LSTM cell
 __global__ void __launch_bounds__(256)
 lstm_cell_fwd_kernel(const dlsg_lstm_cell_fwd_t p) {
+  pdl_prologue();
   const int64_t n = (int64_t)p.B * p.H;
   const int H = p.H;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
@@ -485,6 +492,7 @@ lstm_cell_fwd_kernel(const dlsg_lstm_cell_fwd_t p) {
 
 __global__ void __launch_bounds__(256)
 lstm_cell_bwd_kernel(const dlsg_lstm_cell_bwd_t p) {
+  pdl_prologue();
   const int64_t n = (int64_t)p.B * p.H;
   const int H = p.H;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
@@ -518,6 +526,7 @@ lstm_cell_bwd_kernel(const dlsg_lstm_cell_bwd_t p) {
 // one warp per (outer, inner) pair, lanes stride over the softmax axis
 __global__ void __launch_bounds__(256)
 softmax_fwd_kernel(const dlsg_softmax_t p) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t pairs = p.outer * p.inner;
   for (int64_t pr = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; pr < pairs; pr += ((int64_t)gridDim.x * blockDim.x) >> 5) {
@@ -549,6 +558,7 @@ softmax_fwd_kernel(const dlsg_softmax_t p) {
 
 __global__ void __launch_bounds__(256)
 softmax_bwd_kernel(const dlsg_softmax_t p, const float* __restrict__ dy, float* __restrict__ dx) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t pairs = p.outer * p.inner;
   for (int64_t pr = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; pr < pairs; pr += ((int64_t)gridDim.x * blockDim.x) >> 5) {
@@ -591,6 +601,7 @@ __global__ void __launch_bounds__(128)
 embedding_gather_kernel(const float* __restrict__ table, const int64_t* __restrict__ ids, int64_t ld_ids, int rows, int W,
                         void* out, int odt, int64_t ldo, void* out2, int odt2, int64_t ldo2, float drop_p, uint64_t seed,
                         uint64_t offset) {
+  pdl_prologue();
   const int r = blockIdx.x;
   if (r >= rows) return;
   const int64_t id = ids[(int64_t)r * ld_ids];
@@ -604,6 +615,7 @@ embedding_gather_kernel(const float* __restrict__ table, const int64_t* __restri
 __global__ void __launch_bounds__(128)
 embedding_scatter_kernel(float* __restrict__ dtable, const int64_t* __restrict__ ids, int64_t ld_ids, int rows, int W,
                          const float* __restrict__ dout, int64_t lddo, float drop_p, uint64_t seed, uint64_t offset) {
+  pdl_prologue();
   const int r = blockIdx.x;
   if (r >= rows) return;
   const int64_t id = ids[(int64_t)r * ld_ids];
@@ -614,6 +626,7 @@ embedding_scatter_kernel(float* __restrict__ dtable, const int64_t* __restrict__
   }
 }
 __global__ void mean_nodes_fwd_kernel(const float* __restrict__ x, int B, int P, int H, float* __restrict__ y, int64_t ldy) {
+  pdl_prologue();
   const int64_t n = (int64_t)B * H;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
     const int b = (int)(e / H), h = (int)(e % H);
@@ -623,6 +636,7 @@ __global__ void mean_nodes_fwd_kernel(const float* __restrict__ x, int B, int P,
   }
 }
 __global__ void mean_nodes_bwd_kernel(const float* __restrict__ dy, int64_t lddy, int B, int P, int H, float* __restrict__ dx) {
+  pdl_prologue();
   const int64_t n = (int64_t)B * P * H;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
     const int h = (int)(e % H);
@@ -631,11 +645,13 @@ __global__ void mean_nodes_bwd_kernel(const float* __restrict__ dy, int64_t lddy
   }
 }
 __global__ void axpby_kernel(const float* __restrict__ x, float a, float* __restrict__ y, float b, int64_t n) {
+  pdl_prologue();
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
     y[e] = (b == 0.f) ? a * x[e] : fmaf(a, x[e], b * y[e]);
 }
 __global__ void add_rowbcast_kernel(const float* __restrict__ x, const float* __restrict__ pe, float* __restrict__ y, int64_t batch, int64_t inner,
                                     float drop_p, uint64_t seed, uint64_t offset) {
+  pdl_prologue();
   const int64_t n = batch * inner;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
     float v = x[e] + pe[e % inner];
@@ -645,16 +661,20 @@ __global__ void add_rowbcast_kernel(const float* __restrict__ x, const float* __
 }
 // y = x * dropmask (inverted dropout); also its own backward (same mask)
 __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float drop_p, uint64_t seed, uint64_t offset) {
+  pdl_prologue();
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
     y[e] = x[e] * drop_scale(drop_p, seed, offset + (uint64_t)e);
 }
 __global__ void relu_kernel(float* __restrict__ x, int64_t n) {
+  pdl_prologue();
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) x[e] = fmaxf(x[e], 0.f);
 }
 __global__ void relu_bwd_kernel(const float* __restrict__ r, const float* __restrict__ dr, float* __restrict__ dx, int64_t n) {
+  pdl_prologue();
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) dx[e] = r[e] > 0.f ? dr[e] : 0.f;
 }
 __global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, int64_t n) {
+  pdl_prologue();
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) y[e] = a[e] * b[e];
 }
 
@@ -662,6 +682,7 @@ __global__ void mul_kernel(const float* __restrict__ a, const float* __restrict_
 // out[c] += sum_r x[r, c]  (bias gradients).  block = 32 columns x 8 row-lanes, rows chunked over grid.y
 __global__ void __launch_bounds__(256)
 colsum_kernel(const void* __restrict__ x, int dt, int64_t ld, int64_t rows, int64_t cols, float* __restrict__ out) {
+  pdl_prologue();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t c = (int64_t)blockIdx.x * 32 + tx;
@@ -699,7 +720,7 @@ int dlsg_convert2d_batched(const void* src, int sdt, int64_t lds, void* dst, int
   if (batch == 1 && !dstT && sdt == DLSG_F32 && ddt == DLSG_BF16 && lds == cols && ldd == cols && ((rows * cols) % 8 == 0) &&
       (reinterpret_cast<uintptr_t>(src) % 16 == 0) && (reinterpret_cast<uintptr_t>(dst) % 16 == 0)) {
     const int64_t n8 = rows * cols / 8;
-    cast_f32_bf16_flat<<<ew_blocks(n8), 256, 0, st>>>((const float4*)src, (uint4*)dst, n8);
+    DLSG_LAUNCH(cast_f32_bf16_flat, ew_blocks(n8), 256, 0, st, (const float4*)src, (uint4*)dst, n8);
     return check_launch("cast_f32_bf16_flat");
   }
   // rows ride grid.x (2^31 limit), columns grid.y
@@ -712,13 +733,13 @@ int dlsg_convert2d_batched(const void* src, int sdt, int64_t lds, void* dst, int
       const int64_t nr = rows - r0 < step ? rows - r0 : step;
       const int es = sdt == DLSG_F32 ? 4 : 2, ed = ddt == DLSG_F32 ? 4 : 2;
       dim3 g2((unsigned)((cols + 31) / 32), (unsigned)((nr + 31) / 32), (unsigned)batch);
-      convert2d_kernel<<<g2, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(src) + r0 * lds * es, sdt, lds,
+      DLSG_LAUNCH(convert2d_kernel, g2, 256, 0, st, reinterpret_cast<const uint8_t*>(src) + r0 * lds * es, sdt, lds,
                                            dst ? reinterpret_cast<uint8_t*>(dst) + r0 * ldd * ed : nullptr, ddt, ldd,
                                            dstT ? reinterpret_cast<uint8_t*>(dstT) + r0 * ed : nullptr, ldt, nr, cols, bs_src, bs_dst, bs_dstT);
     }
     return check_launch("convert2d_kernel");
   }
-  convert2d_kernel<<<grid, 256, 0, st>>>(src, sdt, lds, dst, ddt, ldd, dstT, ldt, rows, cols, bs_src, bs_dst, bs_dstT);
+  DLSG_LAUNCH(convert2d_kernel, grid, 256, 0, st, src, sdt, lds, dst, ddt, ldd, dstT, ldt, rows, cols, bs_src, bs_dst, bs_dstT);
   return check_launch("convert2d_kernel");
 }
 int dlsg_convert2d(const void* src, int sdt, int64_t lds, void* dst, int ddt, int64_t ldd, void* dstT, int64_t ldt,
@@ -731,12 +752,12 @@ int dlsg_norm_bwd(const dlsg_norm_bwd_t* p, void* stream) { return norm_bwd_laun
 
 int dlsg_lstm_cell_fwd(const dlsg_lstm_cell_fwd_t* p, void* stream) {
   DLSG_REQUIRE(p->B > 0 && p->H > 0 && p->nsplit >= 1, "lstm_cell_fwd: bad shape");
-  lstm_cell_fwd_kernel<<<ew_blocks((int64_t)p->B * p->H), 256, 0, (cudaStream_t)stream>>>(*p);
+  DLSG_LAUNCH(lstm_cell_fwd_kernel, ew_blocks((int64_t)p->B * p->H), 256, 0, (cudaStream_t)stream, *p);
   return check_launch("lstm_cell_fwd_kernel");
 }
 int dlsg_lstm_cell_bwd(const dlsg_lstm_cell_bwd_t* p, void* stream) {
   DLSG_REQUIRE(p->B > 0 && p->H > 0, "lstm_cell_bwd: bad shape");
-  lstm_cell_bwd_kernel<<<ew_blocks((int64_t)p->B * p->H), 256, 0, (cudaStream_t)stream>>>(*p);
+  DLSG_LAUNCH(lstm_cell_bwd_kernel, ew_blocks((int64_t)p->B * p->H), 256, 0, (cudaStream_t)stream, *p);
   return check_launch("lstm_cell_bwd_kernel");
 }
 
@@ -744,14 +765,14 @@ int dlsg_softmax_fwd(const dlsg_softmax_t* p, void* stream) {
   const int64_t pairs = p->outer * p->inner;
   if (pairs <= 0 || p->n <= 0) return 0;
   DLSG_REQUIRE(p->mask_mode == 0 || p->mask != nullptr, "softmax: mask_mode set without mask");
-  softmax_fwd_kernel<<<ew_blocks(pairs * 32), 256, 0, (cudaStream_t)stream>>>(*p);
+  DLSG_LAUNCH(softmax_fwd_kernel, ew_blocks(pairs * 32), 256, 0, (cudaStream_t)stream, *p);
   return check_launch("softmax_fwd_kernel");
 }
 int dlsg_softmax_bwd(const dlsg_softmax_t* p, const float* dy, float* dx, void* stream) {
   const int64_t pairs = p->outer * p->inner;
   if (pairs <= 0 || p->n <= 0) return 0;
   DLSG_REQUIRE(p->mask_mode == 0 || p->mask != nullptr, "softmax: mask_mode set without mask");
-  softmax_bwd_kernel<<<ew_blocks(pairs * 32), 256, 0, (cudaStream_t)stream>>>(*p, dy, dx);
+  DLSG_LAUNCH(softmax_bwd_kernel, ew_blocks(pairs * 32), 256, 0, (cudaStream_t)stream, *p, dy, dx);
   return check_launch("softmax_bwd_kernel");
 }
 
@@ -759,48 +780,48 @@ int dlsg_embedding_gather(const float* table, const int64_t* ids, int64_t ld_ids
                           int odt, int64_t ldo, void* out2, int odt2, int64_t ldo2, float drop_p, uint64_t seed,
                           uint64_t offset, void* stream) {
   if (rows <= 0) return 0;
-  embedding_gather_kernel<<<rows, 128, 0, (cudaStream_t)stream>>>(table, ids, ld_ids, rows, W, out, odt, ldo, out2, odt2,
+  DLSG_LAUNCH(embedding_gather_kernel, rows, 128, 0, (cudaStream_t)stream, table, ids, ld_ids, rows, W, out, odt, ldo, out2, odt2,
                                                                  ldo2, drop_p, seed, offset);
   return check_launch("embedding_gather_kernel");
 }
 int dlsg_embedding_scatter_add(float* dtable, const int64_t* ids, int64_t ld_ids, int32_t rows, int32_t W,
                                const float* dout, int64_t lddo, float drop_p, uint64_t seed, uint64_t offset, void* stream) {
   if (rows <= 0) return 0;
-  embedding_scatter_kernel<<<rows, 128, 0, (cudaStream_t)stream>>>(dtable, ids, ld_ids, rows, W, dout, lddo, drop_p, seed, offset);
+  DLSG_LAUNCH(embedding_scatter_kernel, rows, 128, 0, (cudaStream_t)stream, dtable, ids, ld_ids, rows, W, dout, lddo, drop_p, seed, offset);
   return check_launch("embedding_scatter_kernel");
 }
 int dlsg_mean_nodes_fwd(const float* x, int32_t B, int32_t P, int32_t H, float* y, int64_t ldy, void* stream) {
-  mean_nodes_fwd_kernel<<<ew_blocks((int64_t)B * H), 256, 0, (cudaStream_t)stream>>>(x, B, P, H, y, ldy);
+  DLSG_LAUNCH(mean_nodes_fwd_kernel, ew_blocks((int64_t)B * H), 256, 0, (cudaStream_t)stream, x, B, P, H, y, ldy);
   return check_launch("mean_nodes_fwd_kernel");
 }
 int dlsg_mean_nodes_bwd(const float* dy, int64_t lddy, int32_t B, int32_t P, int32_t H, float* dx, void* stream) {
-  mean_nodes_bwd_kernel<<<ew_blocks((int64_t)B * P * H), 256, 0, (cudaStream_t)stream>>>(dy, lddy, B, P, H, dx);
+  DLSG_LAUNCH(mean_nodes_bwd_kernel, ew_blocks((int64_t)B * P * H), 256, 0, (cudaStream_t)stream, dy, lddy, B, P, H, dx);
   return check_launch("mean_nodes_bwd_kernel");
 }
 int dlsg_axpby(const float* x, float a, float* y, float b, int64_t n, void* stream) {
   if (n <= 0) return 0;
-  axpby_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, a, y, b, n);
+  DLSG_LAUNCH(axpby_kernel, ew_blocks(n), 256, 0, (cudaStream_t)stream, x, a, y, b, n);
   return check_launch("axpby_kernel");
 }
 int dlsg_add_rowbcast(const float* x, const float* pe, float* y, int64_t batch, int64_t inner, float drop_p, uint64_t seed,
                       uint64_t offset, void* stream) {
   if (batch * inner <= 0) return 0;
-  add_rowbcast_kernel<<<ew_blocks(batch * inner), 256, 0, (cudaStream_t)stream>>>(x, pe, y, batch, inner, drop_p, seed, offset);
+  DLSG_LAUNCH(add_rowbcast_kernel, ew_blocks(batch * inner), 256, 0, (cudaStream_t)stream, x, pe, y, batch, inner, drop_p, seed, offset);
   return check_launch("add_rowbcast_kernel");
 }
 int dlsg_dropout(const float* x, float* y, int64_t n, float drop_p, uint64_t seed, uint64_t offset, void* stream) {
   if (n <= 0) return 0;
-  dropout_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, y, n, drop_p, seed, offset);
+  DLSG_LAUNCH(dropout_kernel, ew_blocks(n), 256, 0, (cudaStream_t)stream, x, y, n, drop_p, seed, offset);
   return check_launch("dropout_kernel");
 }
 int dlsg_relu(float* x, int64_t n, void* stream) {
   if (n <= 0) return 0;
-  relu_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, n);
+  DLSG_LAUNCH(relu_kernel, ew_blocks(n), 256, 0, (cudaStream_t)stream, x, n);
   return check_launch("relu_kernel");
 }
 int dlsg_relu_bwd(const float* r, const float* dr, float* dx, int64_t n, void* stream) {
   if (n <= 0) return 0;
-  relu_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(r, dr, dx, n);
+  DLSG_LAUNCH(relu_bwd_kernel, ew_blocks(n), 256, 0, (cudaStream_t)stream, r, dr, dx, n);
   return check_launch("relu_bwd_kernel");
 }
 
@@ -808,12 +829,12 @@ int dlsg_colsum(const void* x, int dtype, int64_t ld, int64_t rows, int64_t cols
   if (rows <= 0 || cols <= 0) return 0;
   int64_t chunks = (rows + 255) / 256;
   if (chunks > 64) chunks = 64;
-  colsum_kernel<<<dim3((unsigned)((cols + 31) / 32), (unsigned)chunks), 256, 0, (cudaStream_t)stream>>>(x, dtype, ld, rows, cols, out);
+  DLSG_LAUNCH(colsum_kernel, dim3((unsigned)((cols + 31) / 32), (unsigned)chunks), 256, 0, (cudaStream_t)stream, x, dtype, ld, rows, cols, out);
   return check_launch("colsum_kernel");
 }
 int dlsg_mul(const float* a, const float* b, float* y, int64_t n, void* stream) {
   if (n <= 0) return 0;
-  mul_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(a, b, y, n);
+  DLSG_LAUNCH(mul_kernel, ew_blocks(n), 256, 0, (cudaStream_t)stream, a, b, y, n);
   return check_launch("mul_kernel");
 }
 

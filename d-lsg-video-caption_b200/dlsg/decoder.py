@@ -21,6 +21,20 @@ from .linalg import empty, zeros, op, op_empty, op_zeros, ceil8
 START = 1
 
 
+def splitk_for(rows, n_out, K):
+    """Split-K factor for a skinny recurrent GEMM (rows <= 64 ride the UMMA N side, weights fill 128-row tiles): enough
+    CTAs to cover the 148 SMs, >= 4 k-blocks (of 64) per split, no empty split.  1 when the batch is not skinny."""
+    if rows > 64 or la.precision() != 'bf16':
+        return 1
+    tiles = (n_out + 127) // 128
+    kb = (K + 63) // 64
+    if tiles * 2 > 148 or kb < 8:
+        return 1
+    s = min((148 + tiles - 1) // tiles, kb // 4, 16)
+    per = (kb + s - 1) // s
+    return max(1, (kb + per - 1) // per)
+
+
 def flat2(x):
     """Collapse the leading dims of a (possibly column-padded) operand buffer view into rows."""
     rows = 1
@@ -153,8 +167,9 @@ class DecoderCore:
         oq, ol, oQ = self.oq, self.ol, self.oQ
         dq, dc, dl, _ = drops
         R = b.Xq.shape[1]
-        be.gemm(b.Xq[i], pk['Wq'], b.gq[i])
-        be.lstm_cell_fwd(b.gq[i], b.cq[i], b.cq[j], h_out=b.qh[i], row_bias=(Gq if gq_rows is None else gq_rows),
+        # split-K partial sums go straight into the cell kernel (no reduce launch)
+        be.gemm(b.Xq[i], pk['Wq'], b.gq[:, i] if b.Sq > 1 else b.gq[0, i], splitk=b.Sq)
+        be.lstm_cell_fwd(b.gq[:, i], b.cq[i], b.cq[j], h_out=b.qh[i], row_bias=(Gq if gq_rows is None else gq_rows),
                          h2=b.Xq[j][:, oQ:oQ + Hq])
         if self.hoist:
             be.norm_fwd(b.qh[i], t[pf + 'query_lstm_layernorm.weight'], t[pf + 'query_lstm_layernorm.bias'],
@@ -170,8 +185,8 @@ class DecoderCore:
             be.norm_fwd(b.co[i][:, k * H:(k + 1) * H], t[pf + h + '.output_layer.2.weight'], t[pf + h + '.output_layer.2.bias'],
                         y=b.Xl[i][:, k * H:(k + 1) * H], stats=b.statc[i, k], pre_tanh=True,
                         drop=(None if dc is None else (dc[0], dc[1], dc[2] + (k << 28))))
-        be.gemm(b.Xl[i], pk['Wl'], b.gl[i])
-        be.lstm_cell_fwd(b.gl[i], b.cl[i], b.cl[j], h_out=b.lh[j], bias=pk['bl'], h2=b.Xq[j][:, :Hd],
+        be.gemm(b.Xl[i], pk['Wl'], b.gl[:, i] if b.Sl > 1 else b.gl[0, i], splitk=b.Sl)
+        be.lstm_cell_fwd(b.gl[:, i], b.cl[i], b.cl[j], h_out=b.lh[j], bias=pk['bl'], h2=b.Xq[j][:, :Hd],
                          h3=b.Xl[j][:, ol:ol + Hd], drop=dl)
 
     def alloc(self, S, R, P, like):
@@ -180,8 +195,9 @@ class DecoderCore:
         b = type('Buf', (), {})()
         b.Xq = op_zeros((S + 1, R), self.Kq, like)
         b.Xl = op_zeros((S + 1, R), self.Kl, like)
-        b.gq = empty((S, R, 4 * Hq), like)
-        b.gl = empty((S, R, 4 * Hd), like)
+        b.Sq, b.Sl = splitk_for(R, 4 * Hq, self.Kq), splitk_for(R, 4 * Hd, self.Kl)
+        b.gq = empty((b.Sq, S, R, 4 * Hq), like)       # [0] ends up holding the activated gates (saved for BPTT)
+        b.gl = empty((b.Sl, S, R, 4 * Hd), like)
         b.cq = zeros((S + 1, R, Hq), like)
         b.cl = zeros((S + 1, R, Hd), like)
         b.qh = empty((S, R, Hq), like)
@@ -340,7 +356,7 @@ class DecoderTrainBlock:
             # lang LN+tanh -> grad wrt dropped lang_h(i): accumulate onto the recurrent grad from step i+1 (dXq[j][:, :Hd])
             be.norm_bwd(dDall[:, i], b.lh[j], lnl[0], lnl[1], b.statl[i], dx=dXq[j][:, :Hd], dgamma=lnl[2], dbeta=lnl[3],
                         post_tanh=True, dx_accum=True)
-            be.lstm_cell_bwd(b.gl[i], b.cl[i], b.cl[j], dXq[j][:, :Hd], dcl, dcl2, dgates2=dgl_all[rows],
+            be.lstm_cell_bwd(b.gl[0, i], b.cl[i], b.cl[j], dXq[j][:, :Hd], dcl, dcl2, dgates2=dgl_all[rows],
                              dgatesT=dglT[:, rows], drop=dl, dh2=dXl[j][:, ol:ol + Hd])
             dcl, dcl2 = dcl2, dcl
             be.gemm(dgl_all[rows], pk['WlT'], dXl[i])
@@ -360,7 +376,7 @@ class DecoderTrainBlock:
             # query LN -> grad wrt query_h(i): accumulate onto recurrent grad from step i+1 (dXq[j][:, oQ:])
             be.norm_bwd(dXl[i][:, oq:oq + Hq], b.qh[i], lnq[0], lnq[1], b.statq[i], dx=dXq[j][:, oQ:oQ + Hq], dgamma=lnq[2],
                         dbeta=lnq[3], drop=dq, dx_accum=True)
-            be.lstm_cell_bwd(b.gq[i], b.cq[i], b.cq[j], dXq[j][:, oQ:oQ + Hq], dcq, dcq2, dgates=dgq32, dgates2=dgq_all[rows],
+            be.lstm_cell_bwd(b.gq[0, i], b.cq[i], b.cq[j], dXq[j][:, oQ:oQ + Hq], dcq, dcq2, dgates=dgq32, dgates2=dgq_all[rows],
                              dgatesT=dgqT[:, rows])
             dcq, dcq2 = dcq2, dcq
             be.axpby(dgq32, 1.0, dgq_sum, 1.0)
