@@ -58,6 +58,19 @@ class CellBwdT(C.Structure):
                 ('drop_p', f32), ('_pad2', i32), ('seed', u64), ('offset', u64)]
 
 
+class CellNormFwdT(C.Structure):
+    _fields_ = [('cell', CellFwdT), ('gamma', vp), ('beta', vp), ('stats', vp),
+                ('y', vp), ('ldy', i64), ('y2', vp), ('ldy2', i64),
+                ('y_dtype', i32), ('y2_dtype', i32), ('post_tanh', i32), ('_pad', i32),
+                ('ydrop_p', f32), ('_pad2', i32), ('yseed', u64), ('yoffset', u64)]
+
+
+class NormCellBwdT(C.Structure):
+    _fields_ = [('cell', CellBwdT), ('dy', vp), ('lddy', i64), ('x', vp), ('ldx', i64),
+                ('gamma', vp), ('beta', vp), ('stats', vp), ('dgamma', vp), ('dbeta', vp), ('dgates_sum', vp),
+                ('post_tanh', i32), ('_pad', i32), ('ydrop_p', f32), ('_pad2', i32), ('yseed', u64), ('yoffset', u64)]
+
+
 class SoftmaxT(C.Structure):
     _fields_ = [('x', vp), ('y', vp), ('mask', vp), ('outer', i64), ('n', i64), ('inner', i64),
                 ('so', i64), ('sn', i64), ('si', i64), ('scale', f32), ('mask_mode', i32)]
@@ -105,6 +118,8 @@ SIGNATURES = {
     'dlsg_norm_bwd': (i32, [C.POINTER(NormBwdT), vp]),
     'dlsg_lstm_cell_fwd': (i32, [C.POINTER(CellFwdT), vp]),
     'dlsg_lstm_cell_bwd': (i32, [C.POINTER(CellBwdT), vp]),
+    'dlsg_lstm_cell_norm_fwd': (i32, [C.POINTER(CellNormFwdT), vp]),
+    'dlsg_norm_lstm_cell_bwd': (i32, [C.POINTER(NormCellBwdT), vp]),
     'dlsg_softmax_fwd': (i32, [C.POINTER(SoftmaxT), vp]),
     'dlsg_softmax_bwd': (i32, [C.POINTER(SoftmaxT), vp, vp, vp]),
     'dlsg_node_attn_fwd': (i32, [C.POINTER(AttnFwdT), vp]),

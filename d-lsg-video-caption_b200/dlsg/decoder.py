@@ -157,10 +157,12 @@ class DecoderCore:
         return Kp, Vp, glob, Gq, n_op
 
     # ------------------------------------------------------------------ one decode step
-    def step(self, b, i, j, Kp, Vp, Gq, rows_per_node=1, drops=(None, None, None, None), gq_rows=None):
+    def step(self, b, i, j, Kp, Vp, Gq, rows_per_node=1, drops=(None, None, None, None), gq_rows=None, lang_y=None,
+             lang_stats=None):
         """Run step reading operand rows b.Xq[i], state slot i and writing slot j (= next step's inputs).
 
-        b: namespace of buffers (see alloc()).  Gq rows are indexed by node set (rows_per_node)."""
+        b: namespace of buffers (see alloc()).  Gq rows are indexed by node set (rows_per_node).
+        lang_y: (R, Hd) view receiving tanh(LN(lang_h)) (the vocabulary projection's operand row, layer.py:599)."""
         be = ops.backend()
         pk, t, pf = self.pk, self.t, self.pf
         nh, H, Hq, Hd = self.nh, self.H, self.Hq, self.Hd
@@ -169,15 +171,15 @@ class DecoderCore:
         R = b.Xq.shape[1]
         # split-K partial sums go straight into the cell kernel (no reduce launch)
         be.gemm(b.Xq[i], pk['Wq'], b.gq[:, i] if b.Sq > 1 else b.gq[0, i], splitk=b.Sq)
-        be.lstm_cell_fwd(b.gq[:, i], b.cq[i], b.cq[j], h_out=b.qh[i], row_bias=(Gq if gq_rows is None else gq_rows),
-                         h2=b.Xq[j][:, oQ:oQ + Hq])
+        # fused: split-K partials + hoisted global-feature bias -> cell -> q = dropout(LN(query_h))
+        qy, qy2 = (b.q32[i], b.Xl[i][:, oq:oq + Hq]) if self.hoist else (b.Xl[i][:, oq:oq + Hq], None)
+        be.lstm_cell_norm_fwd(b.gq[:, i], b.cq[i], b.cq[j], t[pf + 'query_lstm_layernorm.weight'],
+                              t[pf + 'query_lstm_layernorm.bias'], qy, h_out=b.qh[i],
+                              row_bias=(Gq if gq_rows is None else gq_rows), h2=b.Xq[j][:, oQ:oQ + Hq], y2=qy2,
+                              stats=b.statq[i], ydrop=dq)
         if self.hoist:
-            be.norm_fwd(b.qh[i], t[pf + 'query_lstm_layernorm.weight'], t[pf + 'query_lstm_layernorm.bias'],
-                        y=b.q32[i], y2=b.Xl[i][:, oq:oq + Hq], stats=b.statq[i], drop=dq)
             be.attn2_fwd(Kp, Vp, b.q32[i], b.alpha[i], b.co[i], 1.0 / math.sqrt(H), rows_per_node)   # Kp,Vp hold KW,VW
         else:
-            be.norm_fwd(b.qh[i], t[pf + 'query_lstm_layernorm.weight'], t[pf + 'query_lstm_layernorm.bias'],
-                        y=b.Xl[i][:, oq:oq + Hq], stats=b.statq[i], drop=dq)
             be.gemm(b.Xl[i][:, oq:oq + Hq], pk['Wqp'], b.qp[i])
             be.node_attn_fwd(Kp, Vp, b.qp[i], b.alpha[i], b.ctxr[i], rows_per_node)
             be.gemm(b.ctxr[i].view(R, nh, H).transpose(0, 1), pk['Wo'], b.co[i].view(R, nh, H).transpose(0, 1))
@@ -186,8 +188,11 @@ class DecoderCore:
                         y=b.Xl[i][:, k * H:(k + 1) * H], stats=b.statc[i, k], pre_tanh=True,
                         drop=(None if dc is None else (dc[0], dc[1], dc[2] + (k << 28))))
         be.gemm(b.Xl[i], pk['Wl'], b.gl[:, i] if b.Sl > 1 else b.gl[0, i], splitk=b.Sl)
-        be.lstm_cell_fwd(b.gl[:, i], b.cl[i], b.cl[j], h_out=b.lh[j], bias=pk['bl'], h2=b.Xq[j][:, :Hd],
-                         h3=b.Xl[j][:, ol:ol + Hd], drop=dl)
+        # fused: cell -> lang_h = dropout(h) (recurrent state, layer.py:594) -> tanh(LN(lang_h))
+        be.lstm_cell_norm_fwd(b.gl[:, i], b.cl[i], b.cl[j], t[pf + 'lang_lstm_layernorm.weight'],
+                              t[pf + 'lang_lstm_layernorm.bias'], lang_y, h_out=b.lh[j], bias=pk['bl'], h2=b.Xq[j][:, :Hd],
+                              h3=b.Xl[j][:, ol:ol + Hd], drop=dl, stats=(lang_stats if lang_stats is not None else b.statl[i]),
+                              post_tanh=True)
 
     def alloc(self, S, R, P, like):
         """Buffers for S step slots (+1) of R rows."""
@@ -262,9 +267,7 @@ class DecoderTrainBlock:
         for i in range(T):
             drops = (site(p, seed, 4 * i), site(0.1 if self.training else 0.0, seed, 4 * i + 1), site(p, seed, 4 * i + 2), None)
             drops_t.append(drops)
-            core.step(b, i, i + 1, Kp, Vp, Gq, 1, drops)
-            be.norm_fwd(b.lh[i + 1], t[pf + 'lang_lstm_layernorm.weight'], t[pf + 'lang_lstm_layernorm.bias'],
-                        y=Dall[:, i], stats=b.statl[i], post_tanh=True)
+            core.step(b, i, i + 1, Kp, Vp, Gq, 1, drops, lang_y=Dall[:, i])
             if not all_tf:
                 if self.tf[i]:
                     wid[i + 1].copy_(caps[:, i])
@@ -354,10 +357,10 @@ class DecoderTrainBlock:
             dq, dc, dl, _ = sv['drops'][i]
             rows = slice(i * B, (i + 1) * B)
             # lang LN+tanh -> grad wrt dropped lang_h(i): accumulate onto the recurrent grad from step i+1 (dXq[j][:, :Hd])
-            be.norm_bwd(dDall[:, i], b.lh[j], lnl[0], lnl[1], b.statl[i], dx=dXq[j][:, :Hd], dgamma=lnl[2], dbeta=lnl[3],
-                        post_tanh=True, dx_accum=True)
-            be.lstm_cell_bwd(b.gl[0, i], b.cl[i], b.cl[j], dXq[j][:, :Hd], dcl, dcl2, dgates2=dgl_all[rows],
-                             dgatesT=dglT[:, rows], drop=dl, dh2=dXl[j][:, ol:ol + Hd])
+            # fused: grad wrt dropped lang_h(i) = LN/tanh path (dDall) + recurrent paths from step i+1 (Xq and Xl rows)
+            be.norm_lstm_cell_bwd(b.gl[0, i], b.cl[i], b.cl[j], dcl, dcl2, dDall[:, i], b.lh[j], lnl[0], lnl[1], b.statl[i],
+                                  lnl[2], lnl[3], dh=dXq[j][:, :Hd], dh2=dXl[j][:, ol:ol + Hd], dgates2=dgl_all[rows],
+                                  dgatesT=dglT[:, rows], drop=dl, post_tanh=True)
             dcl, dcl2 = dcl2, dcl
             be.gemm(dgl_all[rows], pk['WlT'], dXl[i])
             for k, h in enumerate(heads):
@@ -374,12 +377,11 @@ class DecoderTrainBlock:
                                  dalpha_ext=(da_ext[i] if da_ext is not None else None))
                 be.gemm(dqp_all[rows], pk['WqpT'], dXl[i][:, oq:oq + Hq], accum=True)
             # query LN -> grad wrt query_h(i): accumulate onto recurrent grad from step i+1 (dXq[j][:, oQ:])
-            be.norm_bwd(dXl[i][:, oq:oq + Hq], b.qh[i], lnq[0], lnq[1], b.statq[i], dx=dXq[j][:, oQ:oQ + Hq], dgamma=lnq[2],
-                        dbeta=lnq[3], drop=dq, dx_accum=True)
-            be.lstm_cell_bwd(b.gq[0, i], b.cq[i], b.cq[j], dXq[j][:, oQ:oQ + Hq], dcq, dcq2, dgates=dgq32, dgates2=dgq_all[rows],
-                             dgatesT=dgqT[:, rows])
+            # fused: grad wrt query_h(i) = LN path (dq) + recurrent path from step i+1; gate grads also summed over time
+            be.norm_lstm_cell_bwd(b.gq[0, i], b.cq[i], b.cq[j], dcq, dcq2, dXl[i][:, oq:oq + Hq], b.qh[i], lnq[0], lnq[1],
+                                  b.statq[i], lnq[2], lnq[3], dh=dXq[j][:, oQ:oQ + Hq], dgates2=dgq_all[rows],
+                                  dgatesT=dgqT[:, rows], dgates_sum=dgq_sum, ydrop=dq)
             dcq, dcq2 = dcq2, dcq
-            be.axpby(dgq32, 1.0, dgq_sum, 1.0)
             be.gemm(dgq_all[rows], pk['WqT'], dXq[i])
         # ---- parameter gradients batched over time
         Xq2, Xl2 = flat2(b.Xq[:T]), flat2(b.Xl[:T])
@@ -461,8 +463,7 @@ def _decode_setup(t, pf, multi_modal, n1, n2, R_per_clip):
 def _step_logits(core, b, i, j, Kp, Vp, Gq, rpn, dbuf, logits):
     be = ops.backend()
     t, pf = core.t, core.pf
-    core.step(b, i, j, Kp, Vp, Gq, rpn)
-    be.norm_fwd(b.lh[j], t[pf + 'lang_lstm_layernorm.weight'], t[pf + 'lang_lstm_layernorm.bias'], y=dbuf, post_tanh=True)
+    core.step(b, i, j, Kp, Vp, Gq, rpn, lang_y=dbuf)
     be.gemm(dbuf, WC.get(t[pf + 'word_restore.weight']), logits, bias=t[pf + 'word_restore.bias'].detach())
 
 
@@ -580,8 +581,7 @@ def decode_api(t, multi_modal, word, qh, qc, lh, lc, global_feat, n1, n2=None, r
     dbuf = op_zeros((R,), Hd, nodes)
     logits = empty((R, core.V), nodes)
     gq_rows = Gq if Gq.shape[0] == R else Gq.repeat_interleave(R // Gq.shape[0], 0)
-    core.step(b, 0, 1, Kp, Vp, gq_rows, R // Kp.shape[1])
-    be.norm_fwd(b.lh[1], t['lang_lstm_layernorm.weight'], t['lang_lstm_layernorm.bias'], y=dbuf, post_tanh=True)
+    core.step(b, 0, 1, Kp, Vp, gq_rows, R // Kp.shape[1], lang_y=dbuf)
     be.gemm(dbuf, WC.get(t['word_restore.weight']), logits, bias=t['word_restore.bias'].detach())
     return logits, b.qh[0], b.cq[1], b.lh[1], b.cl[1], b.alpha[0].unsqueeze(-1)
 

@@ -205,6 +205,28 @@ class CudaBackend:
         """gates: (B,4H) or (nsplit,B,4H) fp32 (overwritten with activated i,f,g,o in gates[0])."""
         self._ck(gates)
         p = L.CellFwdT()
+        self._fill_cell_fwd(p, gates, c_prev, c_out, h_out, row_bias, bias, h2, h3, drop)
+        self.launches += 1
+        L.check(self.lib.dlsg_lstm_cell_fwd(C.byref(p), _stream()), 'dlsg_lstm_cell_fwd')
+
+    def lstm_cell_norm_fwd(self, gates, c_prev, c_out, gamma, beta, y, h_out=None, row_bias=None, bias=None, h2=None, h3=None,
+                           drop=None, y2=None, stats=None, post_tanh=False, ydrop=None):
+        """Fused cell + LayerNorm: y = [tanh](LN(h)) (+dropout); h itself goes to h_out/h2/h3 as in lstm_cell_fwd."""
+        self._ck(gates)
+        q = L.CellNormFwdT()
+        self._fill_cell_fwd(q.cell, gates, c_prev, c_out, h_out, row_bias, bias, h2, h3, drop)
+        q.gamma, q.beta, q.stats = gamma.data_ptr(), beta.data_ptr(), _ptr(stats)
+        q.y, q.ldy, q.y_dtype = y.data_ptr(), y.stride(0), _dt(y)
+        if y2 is not None:
+            q.y2, q.ldy2, q.y2_dtype = y2.data_ptr(), y2.stride(0), _dt(y2)
+        q.post_tanh = 1 if post_tanh else 0
+        if ydrop is not None and ydrop[0] > 0:
+            q.ydrop_p, q.yseed, q.yoffset = ydrop
+        self.launches += 1
+        L.check(self.lib.dlsg_lstm_cell_norm_fwd(C.byref(q), _stream()), 'dlsg_lstm_cell_norm_fwd')
+
+    @staticmethod
+    def _fill_cell_fwd(p, gates, c_prev, c_out, h_out, row_bias, bias, h2, h3, drop):
         if gates.dim() == 3:
             p.nsplit, p.stride_split = gates.shape[0], gates.stride(0)
             g0 = gates[0]
@@ -222,20 +244,42 @@ class CudaBackend:
             p.h3, p.ldh3, p.h3_dtype = h3.data_ptr(), h3.stride(0), _dt(h3)
         if drop is not None and drop[0] > 0:
             p.drop_p, p.seed, p.offset = drop
-        self.launches += 1
-        L.check(self.lib.dlsg_lstm_cell_fwd(C.byref(p), _stream()), 'dlsg_lstm_cell_fwd')
 
     def lstm_cell_bwd(self, acts, c_prev, c_new, dh, dc_next, dc_prev, dgates=None, dgates2=None, dgatesT=None,
                       drop=None, dh2=None):
         """dh / dh2: (B,H) fp32 views (unit inner stride); their sum is the gradient wrt the (dropped) h."""
         self._ck(acts)
         p = L.CellBwdT()
+        self._fill_cell_bwd(p, acts, c_prev, c_new, dh, dc_next, dc_prev, dgates, dgates2, dgatesT, drop, dh2)
+        self.launches += 1
+        L.check(self.lib.dlsg_lstm_cell_bwd(C.byref(p), _stream()), 'dlsg_lstm_cell_bwd')
+
+    def norm_lstm_cell_bwd(self, acts, c_prev, c_new, dc_next, dc_prev, dy, x, gamma, beta, stats, dgamma, dbeta, dh=None, dh2=None,
+                           dgates=None, dgates2=None, dgatesT=None, dgates_sum=None, drop=None, post_tanh=False, ydrop=None):
+        """Fused LayerNorm backward (dy wrt y=[tanh](LN(x)), x = the cell's dropped h) + LSTM cell backward."""
+        self._ck(acts)
+        q = L.NormCellBwdT()
+        self._fill_cell_bwd(q.cell, acts, c_prev, c_new, dh, dc_next, dc_prev, dgates, dgates2, dgatesT, drop, dh2)
+        assert dy.stride(1) == 1 and x.stride(1) == 1
+        q.dy, q.lddy, q.x, q.ldx = dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0)
+        q.gamma, q.beta, q.stats, q.dgamma, q.dbeta = gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr()
+        q.dgates_sum = _ptr(dgates_sum)
+        q.post_tanh = 1 if post_tanh else 0
+        if ydrop is not None and ydrop[0] > 0:
+            q.ydrop_p, q.yseed, q.yoffset = ydrop
+        self.launches += 1
+        L.check(self.lib.dlsg_norm_lstm_cell_bwd(C.byref(q), _stream()), 'dlsg_norm_lstm_cell_bwd')
+
+    @staticmethod
+    def _fill_cell_bwd(p, acts, c_prev, c_new, dh, dc_next, dc_prev, dgates, dgates2, dgatesT, drop, dh2):
         B, H4 = acts.shape
-        p.acts, p.c_prev, p.c_new, p.dh, p.dc_next = acts.data_ptr(), _ptr(c_prev), c_new.data_ptr(), dh.data_ptr(), _ptr(dc_next)
-        p.lddh = dh.stride(0)
+        p.acts, p.c_prev, p.c_new, p.dc_next = acts.data_ptr(), _ptr(c_prev), c_new.data_ptr(), _ptr(dc_next)
+        if dh is not None:
+            p.dh, p.lddh = dh.data_ptr(), dh.stride(0)
+            assert dh.stride(1) == 1
         if dh2 is not None:
             p.dh2, p.lddh2 = dh2.data_ptr(), dh2.stride(0)
-        assert dh.stride(1) == 1 and c_new.is_contiguous() and acts.is_contiguous()
+        assert c_new.is_contiguous() and acts.is_contiguous()
         p.dgates, p.dc_prev, p.B, p.H = _ptr(dgates), _ptr(dc_prev), B, H4 // 4
         if dgates2 is not None:
             p.dgates2, p.ld_dgates2, p.dgates2_dtype = dgates2.data_ptr(), dgates2.stride(0), _dt(dgates2)
@@ -243,8 +287,6 @@ class CudaBackend:
             p.dgatesT, p.ld_dgatesT, p.dgatesT_dtype = dgatesT.data_ptr(), dgatesT.stride(0), _dt(dgatesT)
         if drop is not None and drop[0] > 0:
             p.drop_p, p.seed, p.offset = drop
-        self.launches += 1
-        L.check(self.lib.dlsg_lstm_cell_bwd(C.byref(p), _stream()), 'dlsg_lstm_cell_bwd')
 
     # ------------------------------------------------------------------ softmax
     @staticmethod

@@ -120,6 +120,28 @@ typedef struct {
 } dlsg_lstm_cell_bwd_t;
 int dlsg_lstm_cell_bwd(const dlsg_lstm_cell_bwd_t* p, void* stream);
 
+/* ---- per-step fusions (one CTA per batch row, H <= 2048): cell + LayerNorm forward, LayerNorm + cell backward.
+ * fwd: split-K partials/bias -> gates -> c,h (dropout on h) -> y = [tanh](LN(h)) (dropout on y); replaces
+ *      reduce + lstm_cell_fwd + norm_fwd (layer.py:571-574, 593-599).
+ * bwd: dh = LNbwd(dy; x=h) + cell.dh + cell.dh2, then the cell backward; dgates_sum (optional) += dgates. */
+typedef struct {
+  dlsg_lstm_cell_fwd_t cell;
+  const float* gamma; const float* beta; float* stats;
+  void* y; int64_t ldy; void* y2; int64_t ldy2;
+  int32_t y_dtype, y2_dtype, post_tanh, _pad;
+  float ydrop_p; int32_t _pad2; uint64_t yseed, yoffset;
+} dlsg_lstm_cell_norm_fwd_t;
+int dlsg_lstm_cell_norm_fwd(const dlsg_lstm_cell_norm_fwd_t* p, void* stream);
+typedef struct {
+  dlsg_lstm_cell_bwd_t cell;            /* cell.dh / cell.dh2: recurrent gradients wrt the dropped h (may be NULL) */
+  const float* dy; int64_t lddy; const float* x; int64_t ldx;
+  const float* gamma; const float* beta; const float* stats; float* dgamma; float* dbeta;
+  float* dgates_sum;
+  int32_t post_tanh, _pad;
+  float ydrop_p; int32_t _pad2; uint64_t yseed, yoffset;
+} dlsg_norm_lstm_cell_bwd_t;
+int dlsg_norm_lstm_cell_bwd(const dlsg_norm_lstm_cell_bwd_t* p, void* stream);
+
 /* ---- softmax over an arbitrary axis (layer.py:188 dim=1, sublayer.py:34,74,192, layer.py:706)
  * x viewed as (outer, n, inner) with element strides; optional scale, optional mask (>0 keeps,
  * else fill -9e15 BEFORE softmax: sublayer.py:70-72) or post-mask (zero AFTER softmax: layer.py:707). */

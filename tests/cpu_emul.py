@@ -152,6 +152,31 @@ class CpuEmulBackend:
         if dgatesT is not None:
             dgatesT[:, :d.shape[0]].copy_(d.t())
 
+    def lstm_cell_norm_fwd(self, gates, c_prev, c_out, gamma, beta, y, h_out=None, row_bias=None, bias=None, h2=None, h3=None,
+                           drop=None, y2=None, stats=None, post_tanh=False, ydrop=None):
+        B, H = c_out.shape
+        h = torch.empty(B, H)
+        self.lstm_cell_fwd(gates, c_prev, c_out, h_out=h, row_bias=row_bias, bias=bias, h2=h2, h3=h3, drop=drop)
+        if h_out is not None:
+            h_out.copy_(h)
+        self.norm_fwd(h, gamma, beta, y=y, y2=y2, stats=stats, post_tanh=post_tanh, drop=ydrop)
+        self.launches -= 1
+
+    def norm_lstm_cell_bwd(self, acts, c_prev, c_new, dc_next, dc_prev, dy, x, gamma, beta, stats, dgamma, dbeta, dh=None, dh2=None,
+                           dgates=None, dgates2=None, dgatesT=None, dgates_sum=None, drop=None, post_tanh=False, ydrop=None):
+        B, H = c_new.shape
+        dx = torch.zeros(B, H)
+        self.norm_bwd(dy, x, gamma, beta, stats, dx=dx, dgamma=dgamma, dbeta=dbeta, post_tanh=post_tanh, drop=ydrop)
+        if dh is not None:
+            dx = dx + dh
+        d = torch.empty(B, 4 * H)
+        self.lstm_cell_bwd(acts, c_prev, c_new, dx, dc_next, dc_prev, dgates=d, dgates2=dgates2, dgatesT=dgatesT, drop=drop, dh2=dh2)
+        if dgates is not None:
+            dgates.copy_(d)
+        if dgates_sum is not None:
+            dgates_sum.add_(d)
+        self.launches -= 1
+
     @staticmethod
     def _sm(x, dim, scale, mask, mask_mode):
         v = x * scale

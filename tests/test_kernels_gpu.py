@@ -182,6 +182,27 @@ def test_lstm_cell(be, H):
     both('lstm_cell_bwd', be, [acts, c_prev, c_new, R(B_, 2 * H)[:, :H], R(B_, H), torch.zeros(B_, H)], kw, [5, 'dgates', 'dgatesT'], tol=1e-5)
 
 
+@pytest.mark.parametrize('H,post', [(64, False), (1024, False), (1536, True)])
+def test_fused_cell_norm(be, H, post):
+    B_ = 7
+    gates = R(3, B_, 4 * H)
+    c_prev = R(B_, H)
+    gamma, beta = 1 + 0.1 * R(H), 0.1 * R(H)
+    kw = dict(h_out=torch.zeros(B_, H), row_bias=R(B_, 4 * H), bias=R(4 * H), h2=torch.zeros(B_, H + 40, dtype=torch.bfloat16)[:, 8:8 + H],
+              y2=torch.zeros(B_, 2 * H, dtype=torch.bfloat16)[:, H:], stats=torch.zeros(B_, 2), post_tanh=post)
+    both('lstm_cell_norm_fwd', be, [gates, c_prev, torch.zeros(B_, H), gamma, beta, torch.zeros(B_, 3 * H)[:, H:2 * H]], kw,
+         [0, 2, 5, 'h_out', 'stats'], tol=2e-5)
+    g2, c_new, hh, st = gates.clone(), torch.zeros(B_, H), torch.zeros(B_, H), torch.zeros(B_, 2)
+    EM.lstm_cell_norm_fwd(g2, c_prev, c_new, gamma, beta, torch.zeros(B_, H), h_out=hh, row_bias=kw['row_bias'], bias=kw['bias'], stats=st,
+                          post_tanh=post)
+    acts = g2[0].contiguous()
+    kw = dict(dh=R(B_, 2 * H)[:, :H], dh2=R(B_, 3 * H)[:, H:2 * H], dgates=torch.zeros(B_, 4 * H),
+              dgates2=torch.zeros(B_, 4 * H + 16, dtype=torch.bfloat16)[:, :4 * H], dgatesT=torch.zeros(4 * H, 5 * B_)[:, 2 * B_:3 * B_],
+              dgates_sum=R(B_, 4 * H), post_tanh=post)
+    both('norm_lstm_cell_bwd', be, [acts, c_prev, c_new, R(B_, H), torch.zeros(B_, H), R(B_, 2 * H)[:, H:], hh, gamma, beta, st, R(H), R(H)],
+         kw, [4, 10, 11, 'dgates', 'dgatesT', 'dgates_sum'], tol=3e-5)
+
+
 # ----------------------------------------------------------------------------------------------- softmax
 @pytest.mark.parametrize('shape,dim', [((4, 936, 26), 1), ((4, 26, 936), 2), ((3, 26, 5), 1), ((6, 26, 26), 2), ((7, 5, 1), 1)])
 @pytest.mark.parametrize('mask_mode', [0, 1, 2])
