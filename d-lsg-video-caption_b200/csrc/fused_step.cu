@@ -1,14 +1,40 @@
-// Per-step fusions of the decoder's LSTM stages (one CTA per batch row, 256 threads):
+// Per-step fusions of the decoder's LSTM stages (one CTA per batch row, 256 threads, 4 consecutive hidden units per
+// thread so every access is a 128-bit load and all loads of a thread are issued back to back):
 //   lstm_cell_norm_fwd : split-K partial sums + hoisted row bias -> gates -> c,h (dropout) -> LayerNorm(h) [-> tanh]
 //                        [-> dropout]; writes h into the next step's operand rows and LN(h) into its consumer's row
 //                        (layer.py:571-574 query LSTM + LN, layer.py:593-599 lang LSTM + LN + tanh)
-//   norm_lstm_cell_bwd : LayerNorm backward + LSTM cell backward (+ running sum of the gate gradients)
+//   norm_lstm_cell_bwd : LayerNorm backward + LSTM cell backward (+ running sum of the gate gradients); the per-row
+//                        dgamma / dbeta contributions are written out (reduced over time by one colsum after BPTT)
 // They replace 3 launches each (reduce / cell / norm, resp. norm_bwd / cell_bwd / axpby) in the 26-step loop.
 #include "common.cuh"
 
 namespace dlsg {
 
-constexpr int FS_MAXE = 8;        // elements per thread: H <= 2048
+constexpr int FS_NG = 2;          // float4 groups per thread: H <= 2048
+constexpr int FS_MAXS = 8;        // split-K partials summed in registers
+
+__device__ __forceinline__ float4 ld4f(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4any(void* base, int dt, int64_t off, float4 v, bool vec) {
+  if (dt == DLSG_F32) {
+    if (vec) { *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off) = v; return; }
+    float* d = reinterpret_cast<float*>(base) + off;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    return;
+  }
+  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(base) + off;
+  if (vec) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(d) = u;
+    return;
+  }
+  d[0] = __float2bfloat16_rn(v.x); d[1] = __float2bfloat16_rn(v.y); d[2] = __float2bfloat16_rn(v.z); d[3] = __float2bfloat16_rn(v.w);
+}
+__device__ __forceinline__ bool vecok(const void* p, int dt, int64_t ld) {
+  const int es = dt == DLSG_F32 ? 4 : 2;
+  return (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) % (4 * es)) == 0);
+}
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 __global__ void __launch_bounds__(256)
 lstm_cell_norm_fwd_kernel(const dlsg_lstm_cell_norm_fwd_t q) {
@@ -16,58 +42,83 @@ lstm_cell_norm_fwd_kernel(const dlsg_lstm_cell_norm_fwd_t q) {
   __shared__ float red[32];
   const dlsg_lstm_cell_fwd_t& p = q.cell;
   const int b = blockIdx.x, H = p.H, tid = threadIdx.x;
-  float hv[FS_MAXE];
+  const bool v2 = p.h2 && vecok(p.h2, p.h2_dtype, p.ldh2), v3 = p.h3 && vecok(p.h3, p.h3_dtype, p.ldh3);
+  const bool vy = q.y && vecok(q.y, q.y_dtype, q.ldy), vy2 = q.y2 && vecok(q.y2, q.y2_dtype, q.ldy2);
+  float4 hv[FS_NG];
   float sum = 0.f;
-  const float hkeep = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
 #pragma unroll
-  for (int e = 0; e < FS_MAXE; ++e) {
-    const int h = tid + e * 256;
-    hv[e] = 0.f;
+  for (int e = 0; e < FS_NG; ++e) {
+    const int h = (tid + e * 256) * 4;
+    hv[e] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (h < H) {
-      float g[4];
+      float4 g[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int64_t gi = (int64_t)b * 4 * H + (int64_t)k * H + h;
-        float v = 0.f;
-        for (int s = 0; s < p.nsplit; ++s) v += p.gates[gi + (int64_t)s * p.stride_split];
-        if (p.row_bias) v += p.row_bias[(int64_t)b * p.ld_row_bias + (int64_t)k * H + h];
-        if (p.bias) v += p.bias[k * H + h];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int s = 0; s < FS_MAXS; ++s)
+          if (s < p.nsplit) v = f4add(v, ld4f(p.gates + gi + (int64_t)s * p.stride_split));
+        for (int s = FS_MAXS; s < p.nsplit; ++s) v = f4add(v, ld4f(p.gates + gi + (int64_t)s * p.stride_split));
+        if (p.row_bias) v = f4add(v, ld4f(p.row_bias + (int64_t)b * p.ld_row_bias + (int64_t)k * H + h));
+        if (p.bias) v = f4add(v, ld4f(p.bias + k * H + h));
         g[k] = v;
       }
-      const float ig = sigmoidf_(g[0]), fg = sigmoidf_(g[1]), gg = tanhf(g[2]), og = sigmoidf_(g[3]);
       const int64_t ei = (int64_t)b * H + h;
-      const float c = fg * (p.c_prev ? p.c_prev[ei] : 0.f) + ig * gg;
-      float hval = og * tanhf(c);
+      float4 cp = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.c_prev) cp = ld4f(p.c_prev + ei);
+      const float gi_[4] = {g[0].x, g[0].y, g[0].z, g[0].w}, gf_[4] = {g[1].x, g[1].y, g[1].z, g[1].w};
+      const float gg_[4] = {g[2].x, g[2].y, g[2].z, g[2].w}, go_[4] = {g[3].x, g[3].y, g[3].z, g[3].w};
+      const float cp_[4] = {cp.x, cp.y, cp.z, cp.w};
+      float ai[4], af[4], ag[4], ao[4], cc[4], hh[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        ai[u] = sigmoidf_(gi_[u]); af[u] = sigmoidf_(gf_[u]); ag[u] = tanhf(gg_[u]); ao[u] = sigmoidf_(go_[u]);
+        cc[u] = af[u] * cp_[u] + ai[u] * ag[u];
+        hh[u] = ao[u] * tanhf(cc[u]);
+        if (p.drop_p > 0.f) hh[u] *= drop_scale(p.drop_p, p.seed, p.offset + (uint64_t)ei + u);
+      }
       const int64_t g0 = (int64_t)b * 4 * H + h;
-      p.gates[g0] = ig; p.gates[g0 + H] = fg; p.gates[g0 + 2 * (int64_t)H] = gg; p.gates[g0 + 3 * (int64_t)H] = og;
-      p.c_out[ei] = c;
-      if (p.drop_p > 0.f) hval *= drop_scale(p.drop_p, p.seed, p.offset + (uint64_t)ei);
-      if (p.h_out) p.h_out[ei] = hval;
-      if (p.h2) st_from_float(p.h2, p.h2_dtype, (int64_t)b * p.ldh2 + h, hval);
-      if (p.h3) st_from_float(p.h3, p.h3_dtype, (int64_t)b * p.ldh3 + h, hval);
-      hv[e] = hval;
-      sum += hval;
+      *reinterpret_cast<float4*>(p.gates + g0) = make_float4(ai[0], ai[1], ai[2], ai[3]);
+      *reinterpret_cast<float4*>(p.gates + g0 + H) = make_float4(af[0], af[1], af[2], af[3]);
+      *reinterpret_cast<float4*>(p.gates + g0 + 2 * (int64_t)H) = make_float4(ag[0], ag[1], ag[2], ag[3]);
+      *reinterpret_cast<float4*>(p.gates + g0 + 3 * (int64_t)H) = make_float4(ao[0], ao[1], ao[2], ao[3]);
+      *reinterpret_cast<float4*>(p.c_out + ei) = make_float4(cc[0], cc[1], cc[2], cc[3]);
+      const float4 h4 = make_float4(hh[0], hh[1], hh[2], hh[3]);
+      if (p.h_out) *reinterpret_cast<float4*>(p.h_out + ei) = h4;
+      if (p.h2) st4any(p.h2, p.h2_dtype, (int64_t)b * p.ldh2 + h, h4, v2);
+      if (p.h3) st4any(p.h3, p.h3_dtype, (int64_t)b * p.ldh3 + h, h4, v3);
+      hv[e] = h4;
+      sum += (h4.x + h4.y) + (h4.z + h4.w);
     }
   }
-  (void)hkeep;
   const float mean = block_sum(sum, red) / (float)H;
   float sq = 0.f;
 #pragma unroll
-  for (int e = 0; e < FS_MAXE; ++e) {
-    const int h = tid + e * 256;
-    if (h < H) { const float d = hv[e] - mean; sq = fmaf(d, d, sq); }
+  for (int e = 0; e < FS_NG; ++e) {
+    const int h = (tid + e * 256) * 4;
+    if (h < H) {
+      const float a = hv[e].x - mean, b2 = hv[e].y - mean, c = hv[e].z - mean, d = hv[e].w - mean;
+      sq += (a * a + b2 * b2) + (c * c + d * d);
+    }
   }
   const float rstd = rsqrtf(block_sum(sq, red) / (float)H + 1e-5f);
   if (q.stats && tid == 0) { q.stats[b * 2] = mean; q.stats[b * 2 + 1] = rstd; }
 #pragma unroll
-  for (int e = 0; e < FS_MAXE; ++e) {
-    const int h = tid + e * 256;
+  for (int e = 0; e < FS_NG; ++e) {
+    const int h = (tid + e * 256) * 4;
     if (h < H) {
-      float y = (hv[e] - mean) * rstd * q.gamma[h] + q.beta[h];
-      if (q.post_tanh) y = tanhf(y);
-      if (q.ydrop_p > 0.f) y *= drop_scale(q.ydrop_p, q.yseed, q.yoffset + (uint64_t)b * H + h);
-      if (q.y) st_from_float(q.y, q.y_dtype, (int64_t)b * q.ldy + h, y);
-      if (q.y2) st_from_float(q.y2, q.y2_dtype, (int64_t)b * q.ldy2 + h, y);
+      const float4 ga = ld4f(q.gamma + h), be = ld4f(q.beta + h);
+      float y[4] = {(hv[e].x - mean) * rstd * ga.x + be.x, (hv[e].y - mean) * rstd * ga.y + be.y,
+                    (hv[e].z - mean) * rstd * ga.z + be.z, (hv[e].w - mean) * rstd * ga.w + be.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (q.post_tanh) y[u] = tanhf(y[u]);
+        if (q.ydrop_p > 0.f) y[u] *= drop_scale(q.ydrop_p, q.yseed, q.yoffset + (uint64_t)b * H + h + u);
+      }
+      const float4 y4 = make_float4(y[0], y[1], y[2], y[3]);
+      if (q.y) st4any(q.y, q.y_dtype, (int64_t)b * q.ldy + h, y4, vy);
+      if (q.y2) st4any(q.y2, q.y2_dtype, (int64_t)b * q.ldy2 + h, y4, vy2);
     }
   }
 }
@@ -79,57 +130,90 @@ norm_lstm_cell_bwd_kernel(const dlsg_norm_lstm_cell_bwd_t q) {
   const dlsg_lstm_cell_bwd_t& p = q.cell;
   const int b = blockIdx.x, H = p.H, tid = threadIdx.x;
   const float mean = q.stats[b * 2], rstd = q.stats[b * 2 + 1];
-  float xh[FS_MAXE], dv[FS_MAXE];
+  const bool vd2 = p.dgates2 && vecok(p.dgates2, p.dgates2_dtype, p.ld_dgates2);
+  float4 xh[FS_NG], dv[FS_NG];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int e = 0; e < FS_MAXE; ++e) {
-    const int h = tid + e * 256;
-    xh[e] = 0.f; dv[e] = 0.f;
+  for (int e = 0; e < FS_NG; ++e) {
+    const int h = (tid + e * 256) * 4;
+    xh[e] = make_float4(0.f, 0.f, 0.f, 0.f); dv[e] = xh[e];
     if (h < H) {
-      const float x = q.x[(int64_t)b * q.ldx + h];
-      float dy = q.dy[(int64_t)b * q.lddy + h];
-      if (q.ydrop_p > 0.f) dy *= drop_scale(q.ydrop_p, q.yseed, q.yoffset + (uint64_t)b * H + h);
-      const float g = q.gamma[h];
-      const float xn = (x - mean) * rstd;
-      if (q.post_tanh) { const float yt = tanhf(xn * g + q.beta[h]); dy *= (1.f - yt * yt); }
-      atomicAdd(&q.dgamma[h], dy * xn);
-      atomicAdd(&q.dbeta[h], dy);
-      const float d = dy * g;
+      const float4 x = ld4f(q.x + (int64_t)b * q.ldx + h);
+      float4 dy = ld4f(q.dy + (int64_t)b * q.lddy + h);
+      const float4 g = ld4f(q.gamma + h);
+      if (q.ydrop_p > 0.f) {
+        const uint64_t i0 = q.yoffset + (uint64_t)b * H + h;
+        dy.x *= drop_scale(q.ydrop_p, q.yseed, i0); dy.y *= drop_scale(q.ydrop_p, q.yseed, i0 + 1);
+        dy.z *= drop_scale(q.ydrop_p, q.yseed, i0 + 2); dy.w *= drop_scale(q.ydrop_p, q.yseed, i0 + 3);
+      }
+      float4 xn = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
+      if (q.post_tanh) {
+        const float4 be = ld4f(q.beta + h);
+        float yt;
+        yt = tanhf(xn.x * g.x + be.x); dy.x *= (1.f - yt * yt);
+        yt = tanhf(xn.y * g.y + be.y); dy.y *= (1.f - yt * yt);
+        yt = tanhf(xn.z * g.z + be.z); dy.z *= (1.f - yt * yt);
+        yt = tanhf(xn.w * g.w + be.w); dy.w *= (1.f - yt * yt);
+      }
+      // per-row LayerNorm parameter-gradient contributions (summed over rows / time by the caller)
+      *reinterpret_cast<float4*>(q.dgamma + (int64_t)b * q.ld_dparam + h) = make_float4(dy.x * xn.x, dy.y * xn.y, dy.z * xn.z, dy.w * xn.w);
+      *reinterpret_cast<float4*>(q.dbeta + (int64_t)b * q.ld_dparam + h) = dy;
+      const float4 d = make_float4(dy.x * g.x, dy.y * g.y, dy.z * g.z, dy.w * g.w);
       xh[e] = xn; dv[e] = d;
-      s1 += d; s2 = fmaf(d, xn, s2);
+      s1 += (d.x + d.y) + (d.z + d.w);
+      s2 += (d.x * xn.x + d.y * xn.y) + (d.z * xn.z + d.w * xn.w);
     }
   }
   s1 = block_sum(s1, red) / (float)H;
   s2 = block_sum(s2, red) / (float)H;
 #pragma unroll
-  for (int e = 0; e < FS_MAXE; ++e) {
-    const int h = tid + e * 256;
+  for (int e = 0; e < FS_NG; ++e) {
+    const int h = (tid + e * 256) * 4;
     if (h < H) {
-      // gradient wrt the (dropped) h: LayerNorm path + recurrent paths
-      float dh = rstd * (dv[e] - s1 - xh[e] * s2);
-      if (p.dh) dh += p.dh[(int64_t)b * p.lddh + h];
-      if (p.dh2) dh += p.dh2[(int64_t)b * p.lddh2 + h];
       const int64_t ei = (int64_t)b * H + h;
-      if (p.drop_p > 0.f) dh *= drop_scale(p.drop_p, p.seed, p.offset + (uint64_t)ei);
       const int64_t g0 = (int64_t)b * 4 * H + h;
-      const float ig = p.acts[g0], fg = p.acts[g0 + H], gg = p.acts[g0 + 2 * (int64_t)H], og = p.acts[g0 + 3 * (int64_t)H];
-      const float tc = tanhf(p.c_new[ei]);
-      float dc = dh * og * (1.f - tc * tc);
-      if (p.dc_next) dc += p.dc_next[ei];
-      const float cp = p.c_prev ? p.c_prev[ei] : 0.f;
-      float d[4];
-      d[0] = dc * gg * ig * (1.f - ig);
-      d[1] = dc * cp * fg * (1.f - fg);
-      d[2] = dc * ig * (1.f - gg * gg);
-      d[3] = dh * tc * og * (1.f - og);
-      if (p.dc_prev) p.dc_prev[ei] = dc * fg;
+      // all loads first
+      const float4 ai = ld4f(p.acts + g0), af = ld4f(p.acts + g0 + H), ag = ld4f(p.acts + g0 + 2 * (int64_t)H), ao = ld4f(p.acts + g0 + 3 * (int64_t)H);
+      const float4 cn = ld4f(p.c_new + ei);
+      float4 cp = make_float4(0.f, 0.f, 0.f, 0.f), dcn = cp, r1 = cp, r2 = cp, gs[4];
+      if (p.c_prev) cp = ld4f(p.c_prev + ei);
+      if (p.dc_next) dcn = ld4f(p.dc_next + ei);
+      if (p.dh) r1 = ld4f(p.dh + (int64_t)b * p.lddh + h);
+      if (p.dh2) r2 = ld4f(p.dh2 + (int64_t)b * p.lddh2 + h);
+      if (q.dgates_sum) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gs[k] = ld4f(q.dgates_sum + (int64_t)b * 4 * H + (int64_t)k * H + h);
+      }
+      const float dxl[4] = {rstd * (dv[e].x - s1 - xh[e].x * s2), rstd * (dv[e].y - s1 - xh[e].y * s2),
+                            rstd * (dv[e].z - s1 - xh[e].z * s2), rstd * (dv[e].w - s1 - xh[e].w * s2)};
+      const float r1_[4] = {r1.x, r1.y, r1.z, r1.w}, r2_[4] = {r2.x, r2.y, r2.z, r2.w};
+      const float i_[4] = {ai.x, ai.y, ai.z, ai.w}, f_[4] = {af.x, af.y, af.z, af.w}, g_[4] = {ag.x, ag.y, ag.z, ag.w}, o_[4] = {ao.x, ao.y, ao.z, ao.w};
+      const float cn_[4] = {cn.x, cn.y, cn.z, cn.w}, cp_[4] = {cp.x, cp.y, cp.z, cp.w}, dcn_[4] = {dcn.x, dcn.y, dcn.z, dcn.w};
+      float d[4][4], dcp[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float dh = dxl[u] + r1_[u] + r2_[u];            // gradient wrt the (dropped) h: LayerNorm path + recurrent paths
+        if (p.drop_p > 0.f) dh *= drop_scale(p.drop_p, p.seed, p.offset + (uint64_t)ei + u);
+        const float tc = tanhf(cn_[u]);
+        const float dc = dh * o_[u] * (1.f - tc * tc) + dcn_[u];
+        d[0][u] = dc * g_[u] * i_[u] * (1.f - i_[u]);
+        d[1][u] = dc * cp_[u] * f_[u] * (1.f - f_[u]);
+        d[2][u] = dc * i_[u] * (1.f - g_[u] * g_[u]);
+        d[3][u] = dh * tc * o_[u] * (1.f - o_[u]);
+        dcp[u] = dc * f_[u];
+      }
+      if (p.dc_prev) *reinterpret_cast<float4*>(p.dc_prev + ei) = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int64_t col = (int64_t)k * H + h;
-        if (p.dgates) p.dgates[(int64_t)b * 4 * H + col] = d[k];
-        if (q.dgates_sum) q.dgates_sum[(int64_t)b * 4 * H + col] += d[k];
-        if (p.dgates2) st_from_float(p.dgates2, p.dgates2_dtype, (int64_t)b * p.ld_dgates2 + col, d[k]);
-        if (p.dgatesT) st_from_float(p.dgatesT, p.dgatesT_dtype, col * p.ld_dgatesT + b, d[k]);
+        const float4 d4 = make_float4(d[k][0], d[k][1], d[k][2], d[k][3]);
+        if (p.dgates) *reinterpret_cast<float4*>(p.dgates + (int64_t)b * 4 * H + col) = d4;
+        if (q.dgates_sum) *reinterpret_cast<float4*>(q.dgates_sum + (int64_t)b * 4 * H + col) = f4add(gs[k], d4);
+        if (p.dgates2) st4any(p.dgates2, p.dgates2_dtype, (int64_t)b * p.ld_dgates2 + col, d4, vd2);
+        if (p.dgatesT) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) st_from_float(p.dgatesT, p.dgatesT_dtype, (col + u) * p.ld_dgatesT + b, d[k][u]);
+        }
       }
     }
   }
@@ -139,18 +223,32 @@ norm_lstm_cell_bwd_kernel(const dlsg_norm_lstm_cell_bwd_t q) {
 
 using namespace dlsg;
 
+static inline bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 extern "C" {
 
+int dlsg_fused_step_supported(int32_t H) { return (H % 4 == 0 && H <= 1024 * FS_NG) ? 1 : 0; }
+
 int dlsg_lstm_cell_norm_fwd(const dlsg_lstm_cell_norm_fwd_t* q, void* stream) {
-  DLSG_REQUIRE(q->cell.B > 0 && q->cell.H > 0 && q->cell.H <= 256 * FS_MAXE && q->cell.nsplit >= 1, "lstm_cell_norm_fwd: bad shape (H <= %d)", 256 * FS_MAXE);
-  DLSG_LAUNCH(lstm_cell_norm_fwd_kernel, q->cell.B, 256, 0, (cudaStream_t)stream, *q);
+  const dlsg_lstm_cell_fwd_t& p = q->cell;
+  DLSG_REQUIRE(p.B > 0 && p.H > 0 && dlsg_fused_step_supported(p.H) && p.nsplit >= 1, "lstm_cell_norm_fwd: H=%d unsupported (H %% 4 == 0, H <= %d)", p.H, 1024 * FS_NG);
+  DLSG_REQUIRE(a16(p.gates) && p.stride_split % 4 == 0 && (!p.row_bias || (a16(p.row_bias) && p.ld_row_bias % 4 == 0)) && (!p.bias || a16(p.bias)) &&
+               (!p.c_prev || a16(p.c_prev)) && a16(p.c_out) && (!p.h_out || a16(p.h_out)) && a16(q->gamma) && a16(q->beta),
+               "lstm_cell_norm_fwd: fp32 operands must be 16-byte aligned");
+  DLSG_LAUNCH(lstm_cell_norm_fwd_kernel, p.B, 256, 0, (cudaStream_t)stream, *q);
   return check_launch("lstm_cell_norm_fwd_kernel");
 }
 
 int dlsg_norm_lstm_cell_bwd(const dlsg_norm_lstm_cell_bwd_t* q, void* stream) {
-  DLSG_REQUIRE(q->cell.B > 0 && q->cell.H > 0 && q->cell.H <= 256 * FS_MAXE, "norm_lstm_cell_bwd: bad shape (H <= %d)", 256 * FS_MAXE);
-  DLSG_REQUIRE(q->dgamma && q->dbeta && q->stats, "norm_lstm_cell_bwd: dgamma/dbeta/stats required");
-  DLSG_LAUNCH(norm_lstm_cell_bwd_kernel, q->cell.B, 256, 0, (cudaStream_t)stream, *q);
+  const dlsg_lstm_cell_bwd_t& p = q->cell;
+  DLSG_REQUIRE(p.B > 0 && p.H > 0 && dlsg_fused_step_supported(p.H), "norm_lstm_cell_bwd: H=%d unsupported", p.H);
+  DLSG_REQUIRE(q->dgamma && q->dbeta && q->stats && q->ld_dparam % 4 == 0 && a16(q->dgamma) && a16(q->dbeta), "norm_lstm_cell_bwd: dgamma/dbeta rows (B,H) and stats required");
+  DLSG_REQUIRE(a16(q->x) && q->ldx % 4 == 0 && a16(q->dy) && q->lddy % 4 == 0 && a16(q->gamma) && a16(q->beta) && a16(p.acts) && a16(p.c_new) &&
+               (!p.c_prev || a16(p.c_prev)) && (!p.dc_next || a16(p.dc_next)) && (!p.dc_prev || a16(p.dc_prev)) &&
+               (!p.dh || (a16(p.dh) && p.lddh % 4 == 0)) && (!p.dh2 || (a16(p.dh2) && p.lddh2 % 4 == 0)) &&
+               (!p.dgates || a16(p.dgates)) && (!q->dgates_sum || a16(q->dgates_sum)),
+               "norm_lstm_cell_bwd: fp32 operands must be 16-byte aligned with row pitches multiple of 4");
+  DLSG_LAUNCH(norm_lstm_cell_bwd_kernel, p.B, 256, 0, (cudaStream_t)stream, *q);
   return check_launch("norm_lstm_cell_bwd_kernel");
 }
 

@@ -372,7 +372,10 @@ splitk_reduce_kernel(const float* __restrict__ ws, int S, int batch, int M, int 
     const int64_t r = e % per;
     const int m = (int)(r / N), n = (int)(r % N);
     float x = 0.f;
-    for (int s = 0; s < S; ++s) x += ws[(int64_t)s * total + e];
+#pragma unroll
+    for (int s = 0; s < 16; ++s)             // unrolled + predicated: all partial loads are in flight together
+      if (s < S) x += ws[(int64_t)s * total + e];
+    for (int s = 16; s < S; ++s) x += ws[(int64_t)s * total + e];
     x *= alpha;
     if (bias) {
       if (flags & DLSG_EPI_BIAS_N) x += bias[n];

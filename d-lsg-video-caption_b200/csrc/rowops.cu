@@ -472,7 +472,10 @@ lstm_cell_fwd_kernel(const dlsg_lstm_cell_fwd_t p) {
     for (int k = 0; k < 4; ++k) {
       const int64_t gi = (int64_t)b * 4 * H + (int64_t)k * H + h;
       float v = 0.f;
-      for (int s = 0; s < p.nsplit; ++s) v += p.gates[gi + (int64_t)s * p.stride_split];
+#pragma unroll
+      for (int s = 0; s < 8; ++s)            // unrolled + predicated: all partial loads are in flight together
+        if (s < p.nsplit) v += p.gates[gi + (int64_t)s * p.stride_split];
+      for (int s = 8; s < p.nsplit; ++s) v += p.gates[gi + (int64_t)s * p.stride_split];
       if (p.row_bias) v += p.row_bias[(int64_t)b * p.ld_row_bias + (int64_t)k * H + h];
       if (p.bias) v += p.bias[k * H + h];
       g[k] = v;

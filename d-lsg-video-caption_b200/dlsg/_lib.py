@@ -67,7 +67,7 @@ class CellNormFwdT(C.Structure):
 
 class NormCellBwdT(C.Structure):
     _fields_ = [('cell', CellBwdT), ('dy', vp), ('lddy', i64), ('x', vp), ('ldx', i64),
-                ('gamma', vp), ('beta', vp), ('stats', vp), ('dgamma', vp), ('dbeta', vp), ('dgates_sum', vp),
+                ('gamma', vp), ('beta', vp), ('stats', vp), ('dgamma', vp), ('dbeta', vp), ('ld_dparam', i64), ('dgates_sum', vp),
                 ('post_tanh', i32), ('_pad', i32), ('ydrop_p', f32), ('_pad2', i32), ('yseed', u64), ('yoffset', u64)]
 
 
@@ -120,6 +120,7 @@ SIGNATURES = {
     'dlsg_lstm_cell_bwd': (i32, [C.POINTER(CellBwdT), vp]),
     'dlsg_lstm_cell_norm_fwd': (i32, [C.POINTER(CellNormFwdT), vp]),
     'dlsg_norm_lstm_cell_bwd': (i32, [C.POINTER(NormCellBwdT), vp]),
+    'dlsg_fused_step_supported': (i32, [i32]),
     'dlsg_softmax_fwd': (i32, [C.POINTER(SoftmaxT), vp]),
     'dlsg_softmax_bwd': (i32, [C.POINTER(SoftmaxT), vp, vp, vp]),
     'dlsg_node_attn_fwd': (i32, [C.POINTER(AttnFwdT), vp]),

@@ -63,6 +63,8 @@ class DecoderCore:
         self.oq = nh * H
         self.ol = self.oq + ceil8(Hq)
         self.Kl = self.ol + Hd
+        be = ops.backend()
+        self.fused = be.fused_step_supported(Hq) and be.fused_step_supported(Hd)   # cell+LayerNorm fused kernels
         self._pack()
 
     def _pack(self):
@@ -173,10 +175,14 @@ class DecoderCore:
         be.gemm(b.Xq[i], pk['Wq'], b.gq[:, i] if b.Sq > 1 else b.gq[0, i], splitk=b.Sq)
         # fused: split-K partials + hoisted global-feature bias -> cell -> q = dropout(LN(query_h))
         qy, qy2 = (b.q32[i], b.Xl[i][:, oq:oq + Hq]) if self.hoist else (b.Xl[i][:, oq:oq + Hq], None)
-        be.lstm_cell_norm_fwd(b.gq[:, i], b.cq[i], b.cq[j], t[pf + 'query_lstm_layernorm.weight'],
-                              t[pf + 'query_lstm_layernorm.bias'], qy, h_out=b.qh[i],
-                              row_bias=(Gq if gq_rows is None else gq_rows), h2=b.Xq[j][:, oQ:oQ + Hq], y2=qy2,
-                              stats=b.statq[i], ydrop=dq)
+        lnq_w, lnq_b = t[pf + 'query_lstm_layernorm.weight'], t[pf + 'query_lstm_layernorm.bias']
+        rb = Gq if gq_rows is None else gq_rows
+        if self.fused:
+            be.lstm_cell_norm_fwd(b.gq[:, i], b.cq[i], b.cq[j], lnq_w, lnq_b, qy, h_out=b.qh[i], row_bias=rb,
+                                  h2=b.Xq[j][:, oQ:oQ + Hq], y2=qy2, stats=b.statq[i], ydrop=dq)
+        else:
+            be.lstm_cell_fwd(b.gq[:, i], b.cq[i], b.cq[j], h_out=b.qh[i], row_bias=rb, h2=b.Xq[j][:, oQ:oQ + Hq])
+            be.norm_fwd(b.qh[i], lnq_w, lnq_b, y=qy, y2=qy2, stats=b.statq[i], drop=dq)
         if self.hoist:
             be.attn2_fwd(Kp, Vp, b.q32[i], b.alpha[i], b.co[i], 1.0 / math.sqrt(H), rows_per_node)   # Kp,Vp hold KW,VW
         else:
@@ -189,10 +195,15 @@ class DecoderCore:
                         drop=(None if dc is None else (dc[0], dc[1], dc[2] + (k << 28))))
         be.gemm(b.Xl[i], pk['Wl'], b.gl[:, i] if b.Sl > 1 else b.gl[0, i], splitk=b.Sl)
         # fused: cell -> lang_h = dropout(h) (recurrent state, layer.py:594) -> tanh(LN(lang_h))
-        be.lstm_cell_norm_fwd(b.gl[:, i], b.cl[i], b.cl[j], t[pf + 'lang_lstm_layernorm.weight'],
-                              t[pf + 'lang_lstm_layernorm.bias'], lang_y, h_out=b.lh[j], bias=pk['bl'], h2=b.Xq[j][:, :Hd],
-                              h3=b.Xl[j][:, ol:ol + Hd], drop=dl, stats=(lang_stats if lang_stats is not None else b.statl[i]),
-                              post_tanh=True)
+        lnl_w, lnl_b = t[pf + 'lang_lstm_layernorm.weight'], t[pf + 'lang_lstm_layernorm.bias']
+        stl = lang_stats if lang_stats is not None else b.statl[i]
+        if self.fused:
+            be.lstm_cell_norm_fwd(b.gl[:, i], b.cl[i], b.cl[j], lnl_w, lnl_b, lang_y, h_out=b.lh[j], bias=pk['bl'],
+                                  h2=b.Xq[j][:, :Hd], h3=b.Xl[j][:, ol:ol + Hd], drop=dl, stats=stl, post_tanh=True)
+        else:
+            be.lstm_cell_fwd(b.gl[:, i], b.cl[i], b.cl[j], h_out=b.lh[j], bias=pk['bl'], h2=b.Xq[j][:, :Hd],
+                             h3=b.Xl[j][:, ol:ol + Hd], drop=dl)
+            be.norm_fwd(b.lh[j], lnl_w, lnl_b, y=lang_y, stats=stl, post_tanh=True)
 
     def alloc(self, S, R, P, like):
         """Buffers for S step slots (+1) of R rows."""
@@ -352,15 +363,26 @@ class DecoderTrainBlock:
         att_scale = 1.0 / math.sqrt(H)
         dcq, dcq2 = zeros((B, Hq), ref), empty((B, Hq), ref)
         dcl, dcl2 = zeros((B, Hd), ref), empty((B, Hd), ref)
+        fused = core.fused
+        if fused:
+            # per-row LayerNorm parameter-gradient contributions of every step; reduced by one colsum each after BPTT
+            lq_g, lq_b = empty((T, B, Hq), ref), empty((T, B, Hq), ref)
+            ll_g, ll_b = empty((T, B, Hd), ref), empty((T, B, Hd), ref)
         for i in range(T - 1, -1, -1):
             j = i + 1
             dq, dc, dl, _ = sv['drops'][i]
             rows = slice(i * B, (i + 1) * B)
             # lang LN+tanh -> grad wrt dropped lang_h(i): accumulate onto the recurrent grad from step i+1 (dXq[j][:, :Hd])
             # fused: grad wrt dropped lang_h(i) = LN/tanh path (dDall) + recurrent paths from step i+1 (Xq and Xl rows)
-            be.norm_lstm_cell_bwd(b.gl[0, i], b.cl[i], b.cl[j], dcl, dcl2, dDall[:, i], b.lh[j], lnl[0], lnl[1], b.statl[i],
-                                  lnl[2], lnl[3], dh=dXq[j][:, :Hd], dh2=dXl[j][:, ol:ol + Hd], dgates2=dgl_all[rows],
-                                  dgatesT=dglT[:, rows], drop=dl, post_tanh=True)
+            if fused:
+                be.norm_lstm_cell_bwd(b.gl[0, i], b.cl[i], b.cl[j], dcl, dcl2, dDall[:, i], b.lh[j], lnl[0], lnl[1], b.statl[i],
+                                      ll_g[i], ll_b[i], dh=dXq[j][:, :Hd], dh2=dXl[j][:, ol:ol + Hd], dgates2=dgl_all[rows],
+                                      dgatesT=dglT[:, rows], drop=dl, post_tanh=True)
+            else:
+                be.norm_bwd(dDall[:, i], b.lh[j], lnl[0], lnl[1], b.statl[i], dx=dXq[j][:, :Hd], dgamma=lnl[2], dbeta=lnl[3],
+                            post_tanh=True, dx_accum=True)
+                be.lstm_cell_bwd(b.gl[0, i], b.cl[i], b.cl[j], dXq[j][:, :Hd], dcl, dcl2, dgates2=dgl_all[rows],
+                                 dgatesT=dglT[:, rows], drop=dl, dh2=dXl[j][:, ol:ol + Hd])
             dcl, dcl2 = dcl2, dcl
             be.gemm(dgl_all[rows], pk['WlT'], dXl[i])
             for k, h in enumerate(heads):
@@ -378,12 +400,24 @@ class DecoderTrainBlock:
                 be.gemm(dqp_all[rows], pk['WqpT'], dXl[i][:, oq:oq + Hq], accum=True)
             # query LN -> grad wrt query_h(i): accumulate onto recurrent grad from step i+1 (dXq[j][:, oQ:])
             # fused: grad wrt query_h(i) = LN path (dq) + recurrent path from step i+1; gate grads also summed over time
-            be.norm_lstm_cell_bwd(b.gq[0, i], b.cq[i], b.cq[j], dcq, dcq2, dXl[i][:, oq:oq + Hq], b.qh[i], lnq[0], lnq[1],
-                                  b.statq[i], lnq[2], lnq[3], dh=dXq[j][:, oQ:oQ + Hq], dgates2=dgq_all[rows],
-                                  dgatesT=dgqT[:, rows], dgates_sum=dgq_sum, ydrop=dq)
+            if fused:
+                be.norm_lstm_cell_bwd(b.gq[0, i], b.cq[i], b.cq[j], dcq, dcq2, dXl[i][:, oq:oq + Hq], b.qh[i], lnq[0], lnq[1],
+                                      b.statq[i], lq_g[i], lq_b[i], dh=dXq[j][:, oQ:oQ + Hq], dgates2=dgq_all[rows],
+                                      dgatesT=dgqT[:, rows], dgates_sum=dgq_sum, ydrop=dq)
+            else:
+                be.norm_bwd(dXl[i][:, oq:oq + Hq], b.qh[i], lnq[0], lnq[1], b.statq[i], dx=dXq[j][:, oQ:oQ + Hq], dgamma=lnq[2],
+                            dbeta=lnq[3], drop=dq, dx_accum=True)
+                be.lstm_cell_bwd(b.gq[0, i], b.cq[i], b.cq[j], dXq[j][:, oQ:oQ + Hq], dcq, dcq2, dgates=dgq32,
+                                 dgates2=dgq_all[rows], dgatesT=dgqT[:, rows])
+                be.axpby(dgq32, 1.0, dgq_sum, 1.0)
             dcq, dcq2 = dcq2, dcq
             be.gemm(dgq_all[rows], pk['WqT'], dXq[i])
         # ---- parameter gradients batched over time
+        if fused:
+            be.colsum(lq_g.view(TB, Hq), lnq[2])
+            be.colsum(lq_b.view(TB, Hq), lnq[3])
+            be.colsum(ll_g.view(TB, Hd), lnl[2])
+            be.colsum(ll_b.view(TB, Hd), lnl[3])
         Xq2, Xl2 = flat2(b.Xq[:T]), flat2(b.Xl[:T])
         dWq = la.mm(dgqT, Xq2.t())                                # (4Hq, Kq)
         dWl = la.mm(dglT, Xl2.t())                                # (4Hd, Kl)

@@ -106,6 +106,28 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+_SIDE = {}
+
+
+def two_streams(like, f0, f1):
+    """Run two independent launch sequences concurrently: f0 on the current stream, f1 on a side stream (fork/join by
+    events, so it is CUDA-graph capturable).  Used for the two directions of the BiLSTM, whose 26-step chains are
+    latency-bound and each use a fraction of the SMs."""
+    if not like.is_cuda:
+        f0()
+        f1()
+        return
+    cur = torch.cuda.current_stream()
+    side = _SIDE.get(like.device)
+    if side is None:
+        side = _SIDE[like.device] = torch.cuda.Stream(device=like.device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        f1()
+    f0()
+    cur.wait_stream(side)
+
+
 # =============================================================================================== TUN
 class TunBlock:
     """encs: list of dicts {'prefix': str, 'use_embed': bool}.  Tensor names: 'regions', 'visual<e>',
@@ -361,7 +383,8 @@ class EncoderVisualBlock:
         cs = zeros((2, T + 1, B, H), frames)
         hprev = op_zeros((2, T, B), H, frames)       # h fed INTO step t (operand dtype)
         whh = [WC.get(t[pf + 'lstm.weight_hh_l0']), WC.get(t[pf + 'lstm.weight_hh_l0_reverse'])]
-        for d in range(2):
+
+        def run_dir(d):
             order = list(range(T)) if d == 0 else list(range(T - 1, -1, -1))
             for k, tt in enumerate(order):
                 if k > 0:
@@ -369,6 +392,7 @@ class EncoderVisualBlock:
                 nxt = order[k + 1] if k + 1 < T else None
                 be.lstm_cell_fwd(gates[d, tt], cs[d, k], cs[d, k + 1], row_bias=Gin[:, tt, d * H4:(d + 1) * H4],
                                  h2=lstm_out[:, tt, d * H:(d + 1) * H], h3=(hprev[d, nxt] if nxt is not None else None))
+        two_streams(frames, lambda: run_dir(0), lambda: run_dir(1))     # the two directions are independent chains
         Y = empty((B * T, 2 * H), frames)
         stY = empty((B * T, 2), frames)
         dY = site(self.p if training else 0.0, seed, 1)
@@ -480,12 +504,14 @@ class EncoderVisualBlock:
         gates, cs, hprev = sv['gates'], sv['cs'], sv['hprev']
         whhT = [WC.get(t[pf + 'lstm.weight_hh_l0'], transpose=True), WC.get(t[pf + 'lstm.weight_hh_l0_reverse'], transpose=True)]
         names_hh = ['lstm.weight_hh_l0', 'lstm.weight_hh_l0_reverse']
-        for d in range(2):
+        # everything that crosses the stream fork/join is allocated here, on the main stream
+        dgTs = [op_empty((H4,), T * B, ref) for _ in range(2)]
+        bufs = [(zeros((B, H), ref), zeros((B, H), ref), empty((B, H), ref)) for _ in range(2)]
+
+        def run_dir_bwd(d):
             order = list(range(T)) if d == 0 else list(range(T - 1, -1, -1))
-            dgT = op_empty((H4,), T * B, ref)
-            dhrec = zeros((B, H), ref)
-            dc = zeros((B, H), ref)
-            dc2 = empty((B, H), ref)
+            dgT = dgTs[d]
+            dhrec, dc, dc2 = bufs[d]
             for k in range(T - 1, -1, -1):
                 tt = order[k]
                 dg2 = dGin[:, tt, d * H4:(d + 1) * H4]
@@ -494,8 +520,10 @@ class EncoderVisualBlock:
                 dc, dc2 = dc2, dc
                 if k > 0:
                     be.gemm(op(dg2), whhT[d], dhrec)
+        two_streams(ref, lambda: run_dir_bwd(0), lambda: run_dir_bwd(1))
+        for d in range(2):
             hp = hprev[d]
-            grads[pf + names_hh[d]] = la.mm(dgT, hp.as_strided((T * B, H), (hp.stride(1), 1)).t())
+            grads[pf + names_hh[d]] = la.mm(dgTs[d], hp.as_strided((T * B, H), (hp.stride(1), 1)).t())
         Wih, _ = self._packs(t, pf)
         dGin2 = dGin.view(B * T, 2 * H4)
         dbg = zeros((2 * H4,), ref)

@@ -61,10 +61,11 @@ class CudaBackend:
 
     def _workspace(self, dev):
         """Per-device scratch for automatic split-K (allocated once, before any graph capture uses it)."""
-        ws = self._ws.get(dev)
+        key = (dev, torch.cuda.current_stream(dev).cuda_stream)      # concurrent streams must not share scratch
+        ws = self._ws.get(key)
         if ws is None:
             ws = torch.empty(self.WORKSPACE_BYTES, dtype=torch.uint8, device=dev)
-            self._ws[dev] = ws
+            self._ws[key] = ws
         return ws
 
     def _ck(self, t):
@@ -209,6 +210,10 @@ class CudaBackend:
         self.launches += 1
         L.check(self.lib.dlsg_lstm_cell_fwd(C.byref(p), _stream()), 'dlsg_lstm_cell_fwd')
 
+    @staticmethod
+    def fused_step_supported(H):
+        return H % 4 == 0 and H <= 2048
+
     def lstm_cell_norm_fwd(self, gates, c_prev, c_out, gamma, beta, y, h_out=None, row_bias=None, bias=None, h2=None, h3=None,
                            drop=None, y2=None, stats=None, post_tanh=False, ydrop=None):
         """Fused cell + LayerNorm: y = [tanh](LN(h)) (+dropout); h itself goes to h_out/h2/h3 as in lstm_cell_fwd."""
@@ -263,6 +268,8 @@ class CudaBackend:
         assert dy.stride(1) == 1 and x.stride(1) == 1
         q.dy, q.lddy, q.x, q.ldx = dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0)
         q.gamma, q.beta, q.stats, q.dgamma, q.dbeta = gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr()
+        assert dgamma.shape == x.shape and dgamma.stride(0) == dbeta.stride(0), 'dgamma/dbeta are per-row (B,H) outputs'
+        q.ld_dparam = dgamma.stride(0)
         q.dgates_sum = _ptr(dgates_sum)
         q.post_tanh = 1 if post_tanh else 0
         if ydrop is not None and ydrop[0] > 0:

@@ -135,12 +135,15 @@ int dlsg_lstm_cell_norm_fwd(const dlsg_lstm_cell_norm_fwd_t* p, void* stream);
 typedef struct {
   dlsg_lstm_cell_bwd_t cell;            /* cell.dh / cell.dh2: recurrent gradients wrt the dropped h (may be NULL) */
   const float* dy; int64_t lddy; const float* x; int64_t ldx;
-  const float* gamma; const float* beta; const float* stats; float* dgamma; float* dbeta;
+  const float* gamma; const float* beta; const float* stats;
+  float* dgamma; float* dbeta; int64_t ld_dparam;   /* per-ROW contributions (B,H), written (not accumulated): the caller */
+                                                    /* sums them over rows / time steps with one dlsg_colsum after BPTT   */
   float* dgates_sum;
   int32_t post_tanh, _pad;
   float ydrop_p; int32_t _pad2; uint64_t yseed, yoffset;
 } dlsg_norm_lstm_cell_bwd_t;
 int dlsg_norm_lstm_cell_bwd(const dlsg_norm_lstm_cell_bwd_t* p, void* stream);
+int dlsg_fused_step_supported(int32_t H);          /* H % 4 == 0 && H <= 2048 */
 
 /* ---- softmax over an arbitrary axis (layer.py:188 dim=1, sublayer.py:34,74,192, layer.py:706)
  * x viewed as (outer, n, inner) with element strides; optional scale, optional mask (>0 keeps,

@@ -152,6 +152,10 @@ class CpuEmulBackend:
         if dgatesT is not None:
             dgatesT[:, :d.shape[0]].copy_(d.t())
 
+    @staticmethod
+    def fused_step_supported(H):
+        return H % 4 == 0 and H <= 2048
+
     def lstm_cell_norm_fwd(self, gates, c_prev, c_out, gamma, beta, y, h_out=None, row_bias=None, bias=None, h2=None, h3=None,
                            drop=None, y2=None, stats=None, post_tanh=False, ydrop=None):
         B, H = c_out.shape
@@ -166,7 +170,16 @@ class CpuEmulBackend:
                            dgates=None, dgates2=None, dgatesT=None, dgates_sum=None, drop=None, post_tanh=False, ydrop=None):
         B, H = c_new.shape
         dx = torch.zeros(B, H)
-        self.norm_bwd(dy, x, gamma, beta, stats, dx=dx, dgamma=dgamma, dbeta=dbeta, post_tanh=post_tanh, drop=ydrop)
+        self.norm_bwd(dy, x, gamma, beta, stats, dx=dx, post_tanh=post_tanh, drop=ydrop)
+        # per-row LayerNorm parameter-gradient contributions
+        st = stats.view(B, 2)
+        xn = (x - st[:, 0:1]) * st[:, 1:2]
+        g = dy
+        if post_tanh:
+            yt = torch.tanh(xn * gamma + beta)
+            g = g * (1 - yt * yt)
+        dgamma.copy_(g * xn)
+        dbeta.copy_(g)
         if dh is not None:
             dx = dx + dh
         d = torch.empty(B, 4 * H)
