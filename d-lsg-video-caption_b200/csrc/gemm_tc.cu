@@ -414,7 +414,7 @@ int gemm_tc_dispatch(const dlsg_gemm_t* g, cudaStream_t st) {
     const int64_t tiles = (int64_t)((P + BM - 1) / BM) * ((Q + bn - 1) / bn) * batch;
     const int kb = (g->K + BK - 1) / BK;
     if (tiles * 2 <= kNumSM && kb >= 8) {
-      int S = (int)((kNumSM + tiles - 1) / tiles);
+      int S = (int)(kNumSM / tiles);      // floor: all tiles*S CTAs run in ONE wave of the persistent grid
       if (S > kb / 4) S = kb / 4;
       if (S > 16) S = 16;
       const int per = (kb + S - 1) / S;

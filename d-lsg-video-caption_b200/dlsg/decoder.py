@@ -30,7 +30,7 @@ def splitk_for(rows, n_out, K):
     kb = (K + 63) // 64
     if tiles * 2 > 148 or kb < 8:
         return 1
-    s = min((148 + tiles - 1) // tiles, kb // 4, 16)
+    s = min(148 // tiles, kb // 4, 16)          # floor: tiles*s CTAs fit in one wave of the 148-CTA persistent grid
     per = (kb + s - 1) // s
     return max(1, (kb + per - 1) // per)
 
