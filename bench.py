@@ -323,9 +323,17 @@ def main():
                     f2, r2, _, _ = synth.make_inputs(Bd, args, V_MSR, seed=7)
                     f2, r2 = f2.to(dev), r2.to(dev)
                     net.update_beam_size(beam)
-                    for _ in range(2):
+                    for _ in range(3):
                         net(f2, r2, None)
-                    dms = timed(lambda: net(f2, r2, None), 3)
+                    dms = timed(lambda: net(f2, r2, None), 5)
+                    extra[name + '_eager'] = Bd / (dms * 1e-3)
+                    if use_graph:
+                        from dlsg.graphs import GraphedDecode
+                        gd = GraphedDecode(net, f2, r2, beam)
+                        for _ in range(2):
+                            gd()
+                        dms = timed(lambda: gd(), 5)
+                        del gd
                     extra[name] = Bd / (dms * 1e-3)
             net.train()
     # ---- CPU baseline beside it (rank 0, N=1 only)

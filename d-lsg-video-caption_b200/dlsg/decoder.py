@@ -525,6 +525,13 @@ def decode_beam(t, pf, multi_modal, n1, n2, T, beam, end_index, per_node=None):
 
     Returns (best (B,S), all_predictions (B,beam,S), log_probs (B,beam)); S = steps taken (early stop when
     every beam of every clip has emitted <end>, exactly like allennlp_beamsearch.py:168)."""
+    preds, backs, final_lp, first_lp = decode_beam_core(t, pf, multi_modal, n1, n2, T, beam, end_index, per_node)
+    return decode_beam_finish(preds, backs, final_lp, first_lp, end_index)
+
+
+def decode_beam_core(t, pf, multi_modal, n1, n2, T, beam, end_index, per_node=None):
+    """The T beam steps without any host synchronisation (CUDA-graph capturable).  Returns the raw search trace:
+    preds (T,B,beam), back-pointers (T-1,B,beam), log-probs after the last step and after step 0."""
     be = ops.backend()
     k = per_node or beam
     core, nodes, Kp, Vp, Gq, b = _decode_setup(t, pf, multi_modal, n1, n2, beam)
@@ -561,6 +568,14 @@ def decode_beam(t, pf, multi_modal, n1, n2, T, beam, end_index, per_node=None):
         for buf in (b.Xq, b.Xl, b.cq, b.cl):
             be.beam_gather(_fullrows(buf[j]), _fullrows(buf[g]), backs[s - 1], B, beam)
         i, j, g = g, i, j
+    return preds, backs, lps[cur], lps[0]
+
+
+def decode_beam_finish(preds, backs, last_lp, first_lp, end_index):
+    """Early-stop length (one D2H read per search), back-track, best beam (layer.py:455-460)."""
+    be = ops.backend()
+    T, B, beam = preds.shape
+    dev = preds.device
     # early-stop semantics: the reference breaks before step s when all of preds[s-1] are <end>
     ended = (preds == end_index).view(T, -1).all(1).tolist()        # one D2H read per search
     S = T
@@ -571,11 +586,11 @@ def decode_beam(t, pf, multi_modal, n1, n2, T, beam, end_index, per_node=None):
     out = torch.empty((B, beam, S), dtype=torch.int64, device=dev)
     if S == 1:
         out.copy_(preds[0].unsqueeze(-1))
-        final_lp = lps[0]
+        final_lp = first_lp
     else:
         be.beam_backtrack(preds, backs, S, B, beam, out)
-        # lps[cur] holds step T-1; after an early stop every later step only appended <end> with log-prob 0
-        final_lp = lps[cur]
+        # last_lp holds step T-1; after an early stop every later step only appended <end> with log-prob 0
+        final_lp = last_lp
     best = torch.empty((B,), dtype=torch.int64, device=dev)
     be.row_argmax(final_lp, best)
     return out[torch.arange(B, device=dev), best], out, final_lp

@@ -74,3 +74,48 @@ class GraphedTrainStep:
     def __call__(self):
         self.graph.replay()
         return self.loss
+
+
+class GraphedDecode:
+    """CUDA-graph capture of CapGnnModel inference (evaluate.py:68: net(frames, regions, None)) for a fixed batch shape:
+    encoder + all decode steps (greedy: 26 steps; beam: 26 batched beam steps) replay as ONE graph, so the ~450-570
+    kernel launches per batch no longer pay the host launch path.  The beam search's only host interaction (early-stop
+    length, one D2H read) happens after the replay.  bf16 weight copies are taken from the cache at capture time:
+    re-capture after the weights change."""
+
+    def __init__(self, net, frames, regions, beam_size, warmup=2):
+        from . import decoder as DD
+        self.DD, self.net, self.beam = DD, net, beam_size
+        self.frames, self.regions = frames.clone(), regions.clone()
+        dec = net.decoder
+        self.T = dec.max_words
+        self.end = dec.vocab('<end>')
+        net.update_beam_size(beam_size)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s), torch.no_grad():
+            for _ in range(warmup):
+                self._core()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.trace = self._core()
+        torch.cuda.synchronize()
+
+    def _core(self):
+        net, DD = self.net, self.DD
+        obj, mot = net.encoder(self.frames, self.regions)
+        t = {k: v.detach() for k, v in net.decoder._used().items()}
+        if self.beam == 1:
+            return DD.decode_greedy(t, '', True, obj, mot, self.T)
+        return DD.decode_beam_core(t, '', True, obj, mot, self.T, self.beam, self.end, net.decoder.beam_search.per_node_beam_size)
+
+    def __call__(self, frames=None, regions=None):
+        if frames is not None:
+            self.frames.copy_(frames, non_blocking=True)
+            self.regions.copy_(regions, non_blocking=True)
+        self.graph.replay()
+        if self.beam == 1:
+            return self.trace
+        return self.DD.decode_beam_finish(*self.trace, self.end)[0]
