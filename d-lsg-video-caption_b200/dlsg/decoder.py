@@ -484,6 +484,7 @@ class DecoderTrainBlock:
 
 # =============================================================================================== inference
 def _decode_setup(t, pf, multi_modal, n1, n2, R_per_clip):
+    WC.eval_scope()
     core = DecoderCore(t, pf, multi_modal, 0.0)
     nodes = _stack_nodes(n1, n2, multi_modal)
     nh, B, P, H = nodes.shape
@@ -608,6 +609,7 @@ def decode_api(t, multi_modal, word, qh, qc, lh, lc, global_feat, n1, n2=None, r
 
     Returns (word_logits, query_h, query_c, lang_h, lang_c, alpha (R, nh*P, 1))."""
     be = ops.backend()
+    WC.eval_scope()
     core = DecoderCore(t, '', multi_modal, 0.0)
     nodes = _stack_nodes(n1, n2, multi_modal)
     nh, Bn, P, H = nodes.shape

@@ -36,6 +36,8 @@ class _BlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, block, names, *tensors):
         t = dict(zip(names, tensors))
+        # weight-copy cache scope: a training forward always re-converts its weights (see linalg.WeightCache)
+        ctx.wc_scope = WC.begin_train_block() if getattr(block, 'need_grad', False) else WC.eval_scope()
         outs, saved = block.forward(t)
         ctx.block, ctx.saved, ctx.names = block, saved, names
         for o in outs:
@@ -46,6 +48,7 @@ class _BlockFn(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, *gouts):
+        WC.set_scope(ctx.wc_scope)
         grads = ctx.block.backward(ctx.saved, gouts)
         ctx.saved = None
         if GRAD_SYNC is not None:

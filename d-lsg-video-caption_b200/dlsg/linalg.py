@@ -109,18 +109,39 @@ def mm32(a, b, out=None, **epi):
 
 
 class WeightCache:
-    """bf16 K-major copies of parameters (and their transposes), refreshed when the parameter changes
-    (tensor._version bumps on every in-place optimizer update)."""
+    """bf16 K-major copies of parameters (and their transposes / packed forms).
+
+    Validity is NOT keyed on tensor._version alone: fused optimizers (torch.optim.Adam(fused=True)) update parameters
+    without bumping it.  Entries carry the *scope* they were built in:
+      ('train', g) - built during training-block forward number g; reused only by that block's own backward;
+      ('eval', g)  - built under no_grad after g training forwards; reused by later no_grad calls (all decode steps)
+                     until the next training forward.
+    So every training forward re-converts the weights it uses (they changed since the last optimizer step), inference
+    converts once."""
 
     def __init__(self):
         self._c = {}
         self.force = False      # True while a CUDA graph is being captured: refresh kernels must be recorded every time
+        self.gen = 0
+        self.scope = ('eval', 0)
+
+    def begin_train_block(self):
+        self.gen += 1
+        self.scope = ('train', self.gen)
+        return self.scope
+
+    def eval_scope(self):
+        self.scope = ('eval', self.gen)
+        return self.scope
+
+    def set_scope(self, scope):
+        self.scope = scope
 
     def get(self, w, transpose=False, key=None):
         if _PRECISION == 'fp32':
             return w.detach().t() if transpose else w.detach()
         k = (id(w) if key is None else key, transpose)
-        ver = (w._version, w.data_ptr(), tuple(w.shape))
+        ver = (w._version, w.data_ptr(), tuple(w.shape), self.scope)
         hit = self._c.get(k)
         if hit is not None and hit[0] == ver and not self.force:
             return hit[1]
@@ -135,7 +156,7 @@ class WeightCache:
 
     def packed(self, key, parts, versions, builder):
         """Cache an arbitrary packed operand (e.g. concatenated LSTM weights) keyed on part versions."""
-        ver = (_PRECISION,) + tuple(versions)
+        ver = (_PRECISION, self.scope) + tuple(versions)
         hit = self._c.get(key)
         if hit is not None and hit[0] == ver and not self.force:
             return hit[1]

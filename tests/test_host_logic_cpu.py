@@ -194,3 +194,33 @@ def test_baseline1_many_frames_uses_per_step_projection_path():
     with torch.no_grad():
         net.update_beam_size(3)
         assert torch.equal(net(frames, regions, None)[0], O.cap_baseline1_forward(sd, frames, None, args.max_words, beam_size=3))
+
+
+def test_weight_copy_cache_sees_fused_optimizer_updates():
+    """torch.optim.Adam(fused=True) updates parameters WITHOUT bumping tensor._version: the bf16 weight-copy cache must
+    not rely on it (every training forward re-converts; inference converts once per eval phase)."""
+    la.set_precision('bf16')
+    tag, args, V, B = CASES[0]
+    frames, regions, caps, lens = synth.make_inputs(B, args, V, seed=12)
+    losses_ = {}
+    for kind in ('fused', 'foreach'):
+        DF.WC.clear()
+        net = _build('CapGnnModel', args, V)
+        net.eval()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-2, fused=True) if kind == 'fused' else \
+            torch.optim.Adam(net.parameters(), lr=1e-2, foreach=True)
+        ls = []
+        for _ in range(3):
+            opt.zero_grad()
+            out = net(frames, regions, caps, args.max_words, 1.0)[0]
+            loss = O.packed_ce_loss(out, caps, lens)
+            loss.backward()
+            opt.step()
+            ls.append(loss.item())
+        with torch.no_grad():
+            net.update_beam_size(1)
+            ids = net(frames, regions, None)[0]
+        losses_[kind] = (ls, ids)
+    assert losses_['fused'][0][2] < losses_['fused'][0][0] - 0.05          # it actually trains
+    assert max(abs(a - b) for a, b in zip(losses_['fused'][0], losses_['foreach'][0])) < 1e-4
+    assert torch.equal(losses_['fused'][1], losses_['foreach'][1])          # eval after training sees the final weights
