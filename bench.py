@@ -219,7 +219,7 @@ def main():
         l0 = be.launches
         gs = GraphedTrainStep(net, opt, d_fr, d_rg, d_cp, lens, 26, 1.0,
                               process_group=(dist.group.WORLD if dist is not None else None), warmup=(0 if world == 1 else 3))
-        launches = be.launches - l0
+        launches = gs.launches
         run_dev = lambda: gs()
 
         def e2e_step():

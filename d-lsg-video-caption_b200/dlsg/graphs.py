@@ -39,11 +39,14 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         self.opt.zero_grad(set_to_none=True)
         DF.WC.force = True
+        from . import ops
+        l0 = ops.backend().launches
         try:
             with torch.cuda.graph(self.graph):
                 self.loss = self._body()
         finally:
             DF.WC.force = False
+        self.launches = ops.backend().launches - l0          # libdlsg kernels recorded in one replay
         torch.cuda.synchronize()
 
     def _body(self):

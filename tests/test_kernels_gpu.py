@@ -109,6 +109,32 @@ def test_gemm_tc_splitk(be, splitk):
     both('gemm', be, [a, b, torch.zeros(splitk, M, N)], dict(splitk=splitk, bias=R(N)), [2], tol=2e-3)
 
 
+@pytest.mark.parametrize('M,N,K', [(64, 4096, 2880), (64, 2880, 4096), (17, 1000, 1544), (256, 384, 1664), (3, 130, 520)])
+def test_gemm_tc_auto_splitk_fixup(be, M, N, K):
+    """Skinny problems split K inside ONE launch (last CTA of a tile sums the parked partials in split order):
+    every epilogue form, repeated launches (the tile counters must return to zero) and run-to-run determinism."""
+    a, b = bf(R(M, K, scale=0.2)), bf(R(N, K, scale=0.2))
+    bias_n, bias_m = R(N), R(M)
+    for _ in range(2):
+        both('gemm', be, [a, b, torch.zeros(M, N)], dict(bias=bias_n, tanh=True), [2], tol=2e-3)
+        both('gemm', be, [a, b, torch.zeros(M, N)], dict(bias=bias_m, bias_axis='m', alpha=0.5), [2], tol=2e-3)
+        both('gemm', be, [a, b, R(M, N)], dict(accum=True), [2], tol=2e-3)
+        both('gemm', be, [a, b, torch.zeros(M, N, dtype=torch.bfloat16)], dict(bias=bias_n), [2], tol=1e-2)
+        both('gemm', be, [a, b, torch.zeros(N, M).t()], dict(bias=bias_n), [2], tol=2e-3)
+    ad, bd = a.to(DEV), b.to(DEV)
+    outs = []
+    for _ in range(4):
+        o = torch.empty(M, N, device=DEV)
+        be.gemm(ad, bd, o)
+        outs.append(o)
+    torch.cuda.synchronize()
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+    if (M, N, K) == (3, 130, 520):
+        B_ = 5                                             # batched skinny problem: per-batch tile counters
+        a3, b3 = bf(R(B_, M, K)), bf(R(B_, N, K))
+        both('gemm', be, [a3, b3, torch.zeros(B_, M, N)], {}, [2], tol=2e-3)
+
+
 # ----------------------------------------------------------------------------------------------- GEMM (FFMA)
 def test_gemm_simt_strided(be):
     a, b = R(70, 90), R(50, 90)
