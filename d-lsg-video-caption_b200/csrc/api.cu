@@ -33,6 +33,7 @@ bool pdl_enabled() {
 
 int gemm_tc_dispatch(const dlsg_gemm_t* g, cudaStream_t st);
 int gemm_simt_dispatch(const dlsg_gemm_t* g, cudaStream_t st);
+void gemm_tc_set_trace(void* p);
 
 }  // namespace dlsg
 
@@ -41,6 +42,7 @@ extern "C" {
 int dlsg_version(void) { return 100; }
 int dlsg_sm_arch(void) { return 100; }
 const char* dlsg_last_error(void) { return dlsg::g_err; }
+void dlsg_debug_gemm_trace(void* dev_buf) { dlsg::gemm_tc_set_trace(dev_buf); }
 
 int dlsg_gemm(const dlsg_gemm_t* p, void* stream) {
   if (!p) { dlsg::set_error("dlsg_gemm: null params"); return -1; }

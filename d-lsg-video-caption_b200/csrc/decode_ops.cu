@@ -410,7 +410,7 @@ log_softmax_kernel(const float* __restrict__ logits, int64_t ld, int V, float* _
 __global__ void __launch_bounds__(256)
 ce_masked_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targets, const int32_t* __restrict__ lens,
                  int L, int V, float* __restrict__ loss_sum, float* __restrict__ dlogits, float inv_count_host,
-                 const float* __restrict__ inv_count_dev) {
+                 const float* __restrict__ inv_count_dev, float* __restrict__ row_loss) {
   pdl_prologue();
   __shared__ float red[32];
   const float inv_count = inv_count_dev ? *inv_count_dev : inv_count_host;
@@ -418,6 +418,7 @@ ce_masked_kernel(const float* __restrict__ logits, const int64_t* __restrict__ t
   const float* x = logits + (int64_t)row * V;
   if (t >= lens[b]) {
     if (dlogits) for (int c = threadIdx.x; c < V; c += blockDim.x) dlogits[(int64_t)row * V + c] = 0.f;
+    if (row_loss && threadIdx.x == 0) row_loss[row] = 0.f;
     return;
   }
   float mx = -INFINITY;
@@ -428,7 +429,11 @@ ce_masked_kernel(const float* __restrict__ logits, const int64_t* __restrict__ t
   s = block_sum(s, red);
   const float lse = mx + logf(s);
   const int tgt = (int)targets[row];
-  if (threadIdx.x == 0) atomicAdd(loss_sum, (lse - x[tgt]) * inv_count);
+  if (threadIdx.x == 0) {
+    const float l = (lse - x[tgt]) * inv_count;
+    if (row_loss) row_loss[row] = l;               // summed in row order by ce_sum_rows_kernel: deterministic
+    else atomicAdd(loss_sum, l);
+  }
   if (dlogits) {
     for (int c = threadIdx.x; c < V; c += blockDim.x) {
       float g = expf(x[c] - lse);
@@ -436,6 +441,17 @@ ce_masked_kernel(const float* __restrict__ logits, const int64_t* __restrict__ t
       dlogits[(int64_t)row * V + c] = g * inv_count;
     }
   }
+}
+
+// loss_sum += sum(row_loss[0..n)) with a fixed summation tree (one block): run-to-run deterministic
+__global__ void __launch_bounds__(1024)
+ce_sum_rows_kernel(const float* __restrict__ row_loss, int n, float* __restrict__ loss_sum) {
+  pdl_prologue();
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += row_loss[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) *loss_sum += s;
 }
 
 // ------------------------------------------------------------------------------------------- beam search
@@ -644,10 +660,14 @@ int dlsg_log_softmax(const float* logits, int64_t ld, int32_t rows, int32_t V, f
   return check_launch("log_softmax_kernel");
 }
 int dlsg_ce_masked(const float* logits, const int64_t* targets, const int32_t* lens, int32_t B, int32_t L, int32_t V,
-                   float* loss_sum, float* dlogits, float inv_count, const float* inv_count_dev, void* stream) {
+                   float* loss_sum, float* dlogits, float inv_count, const float* inv_count_dev, float* row_loss, void* stream) {
   if (B * L <= 0) return 0;
-  DLSG_LAUNCH(ce_masked_kernel, B * L, 256, 0, (cudaStream_t)stream, logits, targets, lens, L, V, loss_sum, dlogits, inv_count, inv_count_dev);
-  return check_launch("ce_masked_kernel");
+  DLSG_LAUNCH(ce_masked_kernel, B * L, 256, 0, (cudaStream_t)stream, logits, targets, lens, L, V, loss_sum, dlogits, inv_count, inv_count_dev,
+              row_loss);
+  if (int rc = check_launch("ce_masked_kernel")) return rc;
+  if (!row_loss) return 0;
+  DLSG_LAUNCH(ce_sum_rows_kernel, 1, 1024, 0, (cudaStream_t)stream, (const float*)row_loss, B * L, loss_sum);
+  return check_launch("ce_sum_rows_kernel");
 }
 int dlsg_beam_topk(const float* logits, int64_t ld, int32_t rows, int32_t V, const int64_t* last, int32_t end_index,
                    int32_t k, float* top_lp, int64_t* top_id, int32_t normalize, void* stream) {

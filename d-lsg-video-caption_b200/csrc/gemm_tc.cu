@@ -30,7 +30,19 @@ struct TcParams {
   float alpha;
   int splitk, kb_total, kb_per_split;
   int ntm, ntn, tiles_total;
+  unsigned long long* trace;   // debug: per-CTA phase timestamps (dlsg_debug_gemm_trace), nullptr in production
 };
+
+// phase timestamps: slot i of CTA b -> trace[b*16 + 2i] = %globaltimer (ns), trace[b*16 + 2i + 1] = clock64
+__device__ __forceinline__ void tc_trace(const TcParams& prm, int i) {
+  if (prm.trace) {
+    unsigned long long g, c;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(c));
+    prm.trace[blockIdx.x * 16 + 2 * i] = g;
+    prm.trace[blockIdx.x * 16 + 2 * i + 1] = c;
+  }
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -130,6 +142,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tiles_total = prm.tiles_total;
 
   if (threadIdx.x == 0) {
+    tc_trace(prm, 0);                                   // CTA entry
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");     // descriptor fetch overlaps the set-up below
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
@@ -149,13 +164,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) tc_trace(prm, 1);               // barriers + TMEM ready
   pdl_prologue();      // barrier init / TMEM allocation above overlap the previous kernel's tail; operands are read below
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
       int s = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
         const int tn = tile % ntn, tm = (tile / ntn) % ntm, z = tile / (ntn * ntm);
@@ -170,9 +184,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int kc = (kb_begin + kb) * BK;
           tma_load_3d(a_dst, &tmA, full, kc, tm * BM, zb);
           tma_load_3d(a_dst + Cfg::A_BYTES, &tmB, full, kc, tn * BN, zb);
+          if (tile == (int)blockIdx.x && kb == 0) tc_trace(prm, 2);     // first TMA issued
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
       }
+      tc_trace(prm, 3);                                 // all loads issued
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one elected thread) =====
@@ -191,6 +207,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(smem_u32(&full_bar[s]), ph);
+          if (tile == (int)blockIdx.x && kb == 0) tc_trace(prm, 4);     // first operands landed
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_addr = smem_u32(tiles + s * Cfg::STAGE_BYTES);
           const uint64_t adesc = make_sw128_desc(a_addr);
@@ -206,6 +223,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         umma_commit(smem_u32(&tfull_bar[acc]));                      // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
       }
+      tc_trace(prm, 5);                                 // all MMAs issued
     }
   } else {
     // ===== epilogue warps =====
@@ -216,12 +234,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // packed bf16x2 stores need 4-byte aligned pairs
     const bool pair_ok = bf16_out && !prm.store_t && !prm.accum && (prm.ldd % 2 == 0) && ((prm.stride_d | prm.stride_split) % 2 == 0) &&
                          ((reinterpret_cast<uintptr_t>(prm.D) & 3) == 0);
+    const bool plain_f32 = !bf16_out && !prm.accum && !prm.do_tanh;     // fp32 store, nothing else: the per-step GEMMs
     int acc = 0; uint32_t acc_ph = 0;
     for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
       const int tn = tile % ntn, tm = (tile / ntn) % ntm, z = tile / (ntn * ntm);
       const int zb = z / prm.splitk, zs = z % prm.splitk;
       const int p0 = tm * BM, q0 = tn * BN;
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_ph);
+      if (threadIdx.x == 64 && tile + (int)gridDim.x >= tiles_total) tc_trace(prm, 6);   // last accumulator complete
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS) + ((uint32_t)(g * 32) << 16);
       const int p_row = p0 + g * 32 + lane;                  // this thread's accumulator row
@@ -246,24 +266,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * prm.alpha + bias_p;
+        const int qb = q0 + c0;
+        const int qn = min(32, prm.Q - qb);                  // valid columns of this chunk (>= 1)
+        const int pb = p0 + g * 32;
+        const int pn = min(32, prm.P - pb);                  // valid rows of this warp's slab (may be <= 0)
+        // Mode decisions are warp-uniform and hoisted: each store loop below is branch-free (predicated stores only).
         if (prm.store_t) {
           // element (p,q) -> D[q*ldd + p]: lanes are consecutive p -> coalesced
-          if (p_row < prm.P) {
+          if (plain_f32) {
+            if (add_bias && prm.bias_mode == 2) {
+              float bq[32];                                 // all loads in flight before the first add
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int q = q0 + c0 + j;
-              if (q < prm.Q) {
-                float x = f[j];
-                if (add_bias && prm.bias_mode == 2) x += prm.bias[q];
-                if (prm.do_tanh) x = bf16_out ? tanh_fast(x) : tanhf(x);
-                const int64_t idx = doff + (int64_t)q * prm.ldd + p_row;
-                if (!bf16_out) {
-                  float* d = reinterpret_cast<float*>(Dbase) + idx;
-                  *d = prm.accum ? (*d + x) : x;
-                } else {
-                  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(Dbase) + idx;
-                  *d = __float2bfloat16_rn(prm.accum ? (__bfloat162float(*d) + x) : x);
-                }
+              for (int j = 0; j < 32; ++j) bq[j] = (j < qn) ? __ldg(prm.bias + qb + j) : 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] += bq[j];
+            }
+            if (lane < pn) {
+              float* d = reinterpret_cast<float*>(Dbase) + doff + (int64_t)qb * prm.ldd + p_row;
+              if (qn == 32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { *d = f[j]; d += prm.ldd; }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { if (j < qn) *d = f[j]; d += prm.ldd; }
+              }
+            }
+          } else if (lane < pn) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {            // static register indexing (a rolled loop would spill f[] to local memory)
+              if (j >= qn) break;
+              float x = f[j];
+              if (add_bias && prm.bias_mode == 2) x += prm.bias[qb + j];
+              if (prm.do_tanh) x = bf16_out ? tanh_fast(x) : tanhf(x);
+              const int64_t idx = doff + (int64_t)(qb + j) * prm.ldd + p_row;
+              if (!bf16_out) {
+                float* d = reinterpret_cast<float*>(Dbase) + idx;
+                *d = prm.accum ? (*d + x) : x;
+              } else {
+                __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(Dbase) + idx;
+                *d = __float2bfloat16_rn(prm.accum ? (__bfloat162float(*d) + x) : x);
               }
             }
           }
@@ -272,35 +313,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) st[lane * EPI_PAD + j] = f[j];
           __syncwarp();
-          if (pair_ok && (q0 + c0 + 32 <= prm.Q)) {
+          if (pair_ok && qn == 32) {
             // bf16 output: lane -> (row 2*it + lane/16, column pair 2*(lane%16)): 64 B contiguous per half-warp
             const int cp = 2 * (lane & 15), rsel = lane >> 4;
-            const int q = q0 + c0 + cp;
             float b0 = 0.f, b1 = 0.f;
-            if (add_bias && prm.bias_mode == 2) { b0 = prm.bias[q]; b1 = prm.bias[q + 1]; }
-#pragma unroll 4
-            for (int it = 0; it < 16; ++it) {
-              const int i = 2 * it + rsel;
-              const int p = p0 + g * 32 + i;
-              if (p < prm.P) {
-                float x0 = st[i * EPI_PAD + cp] + b0, x1 = st[i * EPI_PAD + cp + 1] + b1;
-                if (prm.do_tanh) { x0 = tanh_fast(x0); x1 = tanh_fast(x1); }
-                __nv_bfloat162 pk = __floats2bfloat162_rn(x0, x1);
-                *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(Dbase) + doff + (int64_t)p * prm.ldd + q) = pk;
+            if (add_bias && prm.bias_mode == 2) { b0 = prm.bias[qb + cp]; b1 = prm.bias[qb + cp + 1]; }
+            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(Dbase) + doff + (int64_t)(pb + rsel) * prm.ldd + qb + cp;
+            const float* sp = st + rsel * EPI_PAD + cp;
+            const int64_t ld2 = 2 * prm.ldd;
+            const int pv = pn >= 32 ? 32 : pn;              // full slab: no predicates at all
+            if (prm.do_tanh) {
+#pragma unroll
+              for (int it = 0; it < 16; ++it) {
+                if (pv == 32 || 2 * it + rsel < pv)
+                  *reinterpret_cast<__nv_bfloat162*>(d) =
+                      __floats2bfloat162_rn(tanh_fast(sp[2 * it * EPI_PAD] + b0), tanh_fast(sp[2 * it * EPI_PAD + 1] + b1));
+                d += ld2;
+              }
+            } else {
+#pragma unroll
+              for (int it = 0; it < 16; ++it) {
+                if (pv == 32 || 2 * it + rsel < pv)
+                  *reinterpret_cast<__nv_bfloat162*>(d) = __floats2bfloat162_rn(sp[2 * it * EPI_PAD] + b0, sp[2 * it * EPI_PAD + 1] + b1);
+                d += ld2;
               }
             }
-          } else {
-            const int q = q0 + c0 + lane;
+          } else if (lane < qn) {
+            const int q = qb + lane;
             float bias_q = 0.f;
-            if (add_bias && prm.bias_mode == 2 && q < prm.Q) bias_q = prm.bias[q];
-            if (q < prm.Q) {
-#pragma unroll 4
-              for (int i = 0; i < 32; ++i) {
-                const int p = p0 + g * 32 + i;
-                if (p >= prm.P) break;
+            if (add_bias && prm.bias_mode == 2) bias_q = prm.bias[q];
+            if (plain_f32) {
+              float* d = reinterpret_cast<float*>(Dbase) + doff + (int64_t)pb * prm.ldd + q;
+              if (pn >= 32) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { *d = st[i * EPI_PAD + lane] + bias_q; d += prm.ldd; }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { if (i < pn) *d = st[i * EPI_PAD + lane] + bias_q; d += prm.ldd; }
+              }
+            } else {
+#pragma unroll 1
+              for (int i = 0; i < pn; ++i) {
                 float x = st[i * EPI_PAD + lane] + bias_q;
                 if (prm.do_tanh) x = bf16_out ? tanh_fast(x) : tanhf(x);
-                const int64_t idx = doff + (int64_t)p * prm.ldd + q;
+                const int64_t idx = doff + (int64_t)(pb + i) * prm.ldd + q;
                 if (!bf16_out) {
                   float* d = reinterpret_cast<float*>(Dbase) + idx;
                   *d = prm.accum ? (*d + x) : x;
@@ -319,6 +375,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (threadIdx.x == 0) tc_trace(prm, 7);               // epilogue stores issued, CTA about to exit
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
@@ -402,6 +459,8 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcParam
 }
 
 static int gemm_tc_direct(const dlsg_gemm_t* g, cudaStream_t st);
+static unsigned long long* g_tc_trace = nullptr;
+void gemm_tc_set_trace(void* p) { g_tc_trace = static_cast<unsigned long long*>(p); }
 
 int gemm_tc_dispatch(const dlsg_gemm_t* g, cudaStream_t st) {
   // Automatic split-K for skinny problems: too few 128-row tiles to fill 148 SMs and a long K loop
@@ -451,6 +510,7 @@ static int gemm_tc_direct(const dlsg_gemm_t* g, cudaStream_t st) {
   const int64_t ldp = swap ? g->sbn : g->sam, ldq = swap ? g->sam : g->sbn;
   const int64_t strp = swap ? g->stride_b : g->stride_a, strq = swap ? g->stride_a : g->stride_b;
   TcParams prm;
+  prm.trace = g_tc_trace;
   prm.D = g->D; prm.bias = g->bias; prm.ldd = g->ldd; prm.stride_d = g->stride_d; prm.stride_split = g->stride_split;
   prm.P = P; prm.Q = Q;
   const bool user_t = (g->flags & DLSG_EPI_STORE_T) != 0;

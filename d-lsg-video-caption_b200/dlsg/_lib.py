@@ -110,6 +110,7 @@ SIGNATURES = {
     'dlsg_version': (i32, []),
     'dlsg_sm_arch': (i32, []),
     'dlsg_last_error': (C.c_char_p, []),
+    'dlsg_debug_gemm_trace': (None, [vp]),
     'dlsg_gemm': (i32, [C.POINTER(GemmT), vp]),
     'dlsg_convert2d': (i32, [vp, i32, i64, vp, i32, i64, vp, i64, i64, i64, vp]),
     'dlsg_convert2d_batched': (i32, [vp, i32, i64, vp, i32, i64, vp, i64, i64, i64, i64, i64, i64, i64, vp]),
@@ -139,7 +140,7 @@ SIGNATURES = {
     'dlsg_mul': (i32, [vp, vp, vp, i64, vp]),
     'dlsg_row_argmax': (i32, [vp, i64, i32, i32, vp, i64, vp]),
     'dlsg_log_softmax': (i32, [vp, i64, i32, i32, vp, i64, vp]),
-    'dlsg_ce_masked': (i32, [vp, vp, vp, i32, i32, i32, vp, vp, f32, vp, vp]),
+    'dlsg_ce_masked': (i32, [vp, vp, vp, i32, i32, i32, vp, vp, f32, vp, vp, vp]),
     'dlsg_beam_topk': (i32, [vp, i64, i32, i32, vp, i32, i32, vp, vp, i32, vp]),
     'dlsg_beam_merge': (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp]),
     'dlsg_beam_gather': (i32, [vp, vp, vp, i32, i32, i32, vp]),

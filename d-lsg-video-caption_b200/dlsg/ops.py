@@ -482,8 +482,10 @@ class CudaBackend:
         B, Lw, V = logits.shape
         assert logits.is_contiguous() and targets.is_contiguous() and lens.dtype == torch.int32
         self.launches += 1
+        row_loss = torch.empty(B * Lw, dtype=torch.float32, device=logits.device)     # deterministic loss summation
         L.check(self.lib.dlsg_ce_masked(logits.data_ptr(), targets.data_ptr(), lens.data_ptr(), B, Lw, V,
-                                        loss_sum.data_ptr(), _ptr(dlogits), inv_count, _ptr(inv_count_dev), _stream()), 'ce_masked')
+                                        loss_sum.data_ptr(), _ptr(dlogits), inv_count, _ptr(inv_count_dev),
+                                        row_loss.data_ptr(), _stream()), 'ce_masked')
 
     def beam_topk(self, logits, last, end_index, k, top_lp, top_id, normalize=True):
         rows, V = logits.shape

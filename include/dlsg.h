@@ -23,6 +23,9 @@ enum { DLSG_F32 = 0, DLSG_BF16 = 1 };
 int dlsg_version(void);
 int dlsg_sm_arch(void);                /* 100 = built for sm_100a                               */
 const char* dlsg_last_error(void);
+/* Debug only: when dev_buf != NULL every following DLSG_GEMM_TC launch writes per-CTA phase timestamps
+ * (148 CTAs x 8 phases x {globaltimer ns, clock64}) into it; NULL switches tracing off (default).     */
+void dlsg_debug_gemm_trace(void* dev_buf);
 
 /* ---- dense projections (nn.Linear / LSTM gate GEMMs / vocab projection / bmm) -------------
  * D[b](M,N) = epi( A[b](M,K) . B[b](N,K)^T + bias ).  Replaces torch addmm/bmm at
@@ -229,6 +232,8 @@ int dlsg_log_softmax(const float* logits, int64_t ld, int32_t rows, int32_t V, f
  * dlogits (may be NULL) = (softmax - onehot)*gscale/count_total for counted rows, 0 otherwise.   */
 int dlsg_ce_masked(const float* logits, const int64_t* targets, const int32_t* lens, int32_t B, int32_t L, int32_t V,
                    float* loss_sum, float* dlogits, float inv_count, const float* inv_count_dev /* overrides if non-NULL */,
+                   float* row_loss /* optional B*L scratch: per-row losses, summed in a fixed order (deterministic
+                                      loss_sum); NULL = atomicAdd accumulation */,
                    void* stream);
 
 /* ---- beam search (allennlp_beamsearch.py:127,186-260,272-292) ------------------------------- */

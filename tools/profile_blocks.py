@@ -126,11 +126,13 @@ with torch.no_grad():
 
 # loss (fused masked CE) forward + backward
 logits = out.detach().clone().requires_grad_(True)
+lens_d = torch.as_tensor(list(lens), dtype=torch.int32, device=dev)
+inv = torch.tensor([1.0 / max(1, int(sum(lens)))], dtype=torch.float32, device=dev)
 
 
 def ce():
     logits.grad = None
-    loss = losses.packed_cross_entropy(logits, cp, lens)
+    loss = losses.packed_cross_entropy(logits, cp, lens_d, inv)
     loss.backward()
     return loss
 
