@@ -270,13 +270,48 @@ attn2_fwd_kernel(const dlsg_attn2_fwd_t p) {
     }
   }
   __syncthreads();
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (av) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < APM; ++j) {
       if (j < p.P) { const float a = al[j]; acc.x = fmaf(a, v4[j].x, acc.x); acc.y = fmaf(a, v4[j].y, acc.y); acc.z = fmaf(a, v4[j].z, acc.z); acc.w = fmaf(a, v4[j].w, acc.w); }
     }
     *reinterpret_cast<float4*>(p.co + (int64_t)r * p.ldco + hd * p.Hv + c) = acc;
+  }
+  if (p.y == nullptr) return;                       // uniform
+  // fused context output layer: tanh -> LayerNorm (two-pass statistics over the head's Hv values) -> dropout
+  __shared__ float red2[32];
+  float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (av) t4 = make_float4(tanhf(acc.x), tanhf(acc.y), tanhf(acc.z), tanhf(acc.w));
+  const float* gam = hd ? p.gamma[1] : p.gamma[0];
+  const float* bet = hd ? p.beta[1] : p.beta[0];
+  float4 g4 = t4, b4 = t4;
+  if (av) { g4 = *reinterpret_cast<const float4*>(gam + c); b4 = *reinterpret_cast<const float4*>(bet + c); }   // in flight during the reductions
+  const float invH = 1.f / (float)p.Hv;
+  const float mean = block_sum(av ? (t4.x + t4.y) + (t4.z + t4.w) : 0.f, red2) * invH;
+  float sq = 0.f;
+  if (av) { const float a = t4.x - mean, b = t4.y - mean, cc = t4.z - mean, d = t4.w - mean; sq = (a * a + b * b) + (cc * cc + d * d); }
+  const float rstd = rsqrtf(block_sum(sq, red2) * invH + 1e-5f);
+  if (p.stats && tid == 0) {
+    float* st = p.stats + (int64_t)hd * p.stats_head_stride + 2 * (int64_t)r;
+    st[0] = mean; st[1] = rstd;
+  }
+  if (av) {
+    float4 y;
+    y.x = (t4.x - mean) * rstd * g4.x + b4.x; y.y = (t4.y - mean) * rstd * g4.y + b4.y;
+    y.z = (t4.z - mean) * rstd * g4.z + b4.z; y.w = (t4.w - mean) * rstd * g4.w + b4.w;
+    if (p.drop_p > 0.f) {
+      const float4 m = drop_mask4(p.drop_p, 1.f / (1.f - p.drop_p), p.seed,
+                                  p.offset + (uint64_t)hd * p.offset_head_stride + (uint64_t)r * p.Hv + c);
+      y.x *= m.x; y.y *= m.y; y.z *= m.z; y.w *= m.w;
+    }
+    const int64_t o = (int64_t)r * p.ldy + hd * p.Hv + c;
+    if (p.y_dtype == DLSG_F32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + o) = y;
+    else {
+      __nv_bfloat162 a = __floats2bfloat162_rn(y.x, y.y), b = __floats2bfloat162_rn(y.z, y.w);
+      uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.y) + o) = u;
+    }
   }
 }
 
@@ -295,7 +330,7 @@ attn2_bwd_kernel(const dlsg_attn2_bwd_t p) {
   const float* al = p.alpha + (int64_t)r * p.ldalpha + hd * p.P;
   float4 k4[APM], v4[APM], q4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = q4;
   if (ak) q4 = *reinterpret_cast<const float4*>(p.q + (int64_t)r * p.ldq + c);
-  if (av) d4 = *reinterpret_cast<const float4*>(p.dco + (int64_t)r * p.lddco + hd * p.Hv + c);
+  if (av && !p.dy) d4 = *reinterpret_cast<const float4*>(p.dco + (int64_t)r * p.lddco + hd * p.Hv + c);
 #pragma unroll
   for (int j = 0; j < APM; ++j) {
     k4[j] = make_float4(0.f, 0.f, 0.f, 0.f); v4[j] = k4[j];
@@ -303,6 +338,45 @@ attn2_bwd_kernel(const dlsg_attn2_bwd_t p) {
       if (ak) k4[j] = *reinterpret_cast<const float4*>(p.KW + nk + (int64_t)j * p.Hk + c);
       if (av) v4[j] = *reinterpret_cast<const float4*>(p.VW + nv + (int64_t)j * p.Hv + c);
     }
+  }
+  if (p.dy) {                                       // uniform
+    // fused head: backward of dropout(LN(tanh(co))) for this (row, head): d4 = gradient wrt co
+    __shared__ float gr[2][2][8];
+    const float* st = p.stats + (int64_t)hd * p.stats_head_stride + 2 * (int64_t)r;
+    const float mean = st[0], rstd = st[1];
+    float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f), xh = t4, d = t4;
+    float s1 = 0.f, s2 = 0.f;
+    if (av) {
+      const int64_t o = (int64_t)hd * p.Hv + c;
+      const float4 x4 = *reinterpret_cast<const float4*>(p.co + (int64_t)r * p.ldco + o);
+      float4 dy4 = *reinterpret_cast<const float4*>(p.dy + (int64_t)r * p.lddy + o);
+      const float4 g4 = *reinterpret_cast<const float4*>((hd ? p.gamma[1] : p.gamma[0]) + c);
+      if (p.drop_p > 0.f) {
+        const float4 m = drop_mask4(p.drop_p, 1.f / (1.f - p.drop_p), p.seed,
+                                    p.offset + (uint64_t)hd * p.offset_head_stride + (uint64_t)r * p.Hv + c);
+        dy4.x *= m.x; dy4.y *= m.y; dy4.z *= m.z; dy4.w *= m.w;
+      }
+      t4 = make_float4(tanhf(x4.x), tanhf(x4.y), tanhf(x4.z), tanhf(x4.w));
+      xh = make_float4((t4.x - mean) * rstd, (t4.y - mean) * rstd, (t4.z - mean) * rstd, (t4.w - mean) * rstd);
+      *reinterpret_cast<float4*>(p.dgamma_rows + (int64_t)r * p.ld_dparam + o) = make_float4(dy4.x * xh.x, dy4.y * xh.y, dy4.z * xh.z, dy4.w * xh.w);
+      *reinterpret_cast<float4*>(p.dbeta_rows + (int64_t)r * p.ld_dparam + o) = dy4;
+      d = make_float4(dy4.x * g4.x, dy4.y * g4.y, dy4.z * g4.z, dy4.w * g4.w);
+      s1 = (d.x + d.y) + (d.z + d.w);
+      s2 = (d.x * xh.x + d.y * xh.y) + (d.z * xh.z + d.w * xh.w);
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) { gr[0][hd][w] = s1; gr[1][hd][w] = s2; }
+    __syncthreads();
+    s1 = 0.f; s2 = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) { s1 += gr[0][hd][ww]; s2 += gr[1][hd][ww]; }
+    const float invH = 1.f / (float)p.Hv;
+    s1 *= invH; s2 *= invH;
+    d4.x = rstd * (d.x - s1 - xh.x * s2) * (1.f - t4.x * t4.x);
+    d4.y = rstd * (d.y - s1 - xh.y * s2) * (1.f - t4.y * t4.y);
+    d4.z = rstd * (d.z - s1 - xh.z * s2) * (1.f - t4.z * t4.z);
+    d4.w = rstd * (d.w - s1 - xh.w * s2) * (1.f - t4.w * t4.w);
+    if (!av) d4 = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 #pragma unroll
   for (int j = 0; j < APM; ++j) {
@@ -637,14 +711,27 @@ int dlsg_attn2_supported(int32_t nh, int32_t P, int32_t Hk, int32_t Hv) {
 int dlsg_attn2_fwd(const dlsg_attn2_fwd_t* p, void* stream) {
   DLSG_REQUIRE(dlsg_attn2_supported(p->nh, p->P, p->Hk, p->Hv), "attn2_fwd: unsupported shape nh=%d P=%d Hk=%d Hv=%d", p->nh, p->P, p->Hk, p->Hv);
   DLSG_REQUIRE(al16(p->KW) && al16(p->VW) && al16(p->q) && al16(p->co) && p->ldq % 4 == 0 && p->ldco % 4 == 0, "attn2_fwd: unaligned operands");
+  if (p->y) {
+    const int es = p->y_dtype == DLSG_F32 ? 4 : 2;
+    DLSG_REQUIRE((reinterpret_cast<uintptr_t>(p->y) % (4 * es)) == 0 && p->ldy % 4 == 0 && al16(p->gamma[0]) && al16(p->beta[0]) &&
+                 (p->nh < 2 || (al16(p->gamma[1]) && al16(p->beta[1]))) && (p->offset % 4 == 0) && (p->offset_head_stride % 4 == 0),
+                 "attn2_fwd: unaligned fused-LayerNorm operands");
+  }
   if (p->rows <= 0) return 0;
   DLSG_LAUNCH(attn2_fwd_kernel, dim3(p->rows, p->nh), 256, 0, (cudaStream_t)stream, *p);
   return check_launch("attn2_fwd_kernel");
 }
 int dlsg_attn2_bwd(const dlsg_attn2_bwd_t* p, void* stream) {
   DLSG_REQUIRE(dlsg_attn2_supported(p->nh, p->P, p->Hk, p->Hv), "attn2_bwd: unsupported shape nh=%d P=%d Hk=%d Hv=%d", p->nh, p->P, p->Hk, p->Hv);
-  DLSG_REQUIRE(al16(p->KW) && al16(p->VW) && al16(p->q) && al16(p->dco) && al16(p->dq) && al16(p->dKW) && al16(p->dVW) &&
-               p->ldq % 4 == 0 && p->lddco % 4 == 0 && p->lddq % 4 == 0, "attn2_bwd: unaligned operands");
+  DLSG_REQUIRE(al16(p->KW) && al16(p->VW) && al16(p->q) && al16(p->dq) && al16(p->dKW) && al16(p->dVW) &&
+               p->ldq % 4 == 0 && p->lddq % 4 == 0, "attn2_bwd: unaligned operands");
+  if (p->dy) {
+    DLSG_REQUIRE(al16(p->dy) && al16(p->co) && al16(p->gamma[0]) && (p->nh < 2 || al16(p->gamma[1])) && al16(p->dgamma_rows) && al16(p->dbeta_rows) &&
+                 p->lddy % 4 == 0 && p->ldco % 4 == 0 && p->ld_dparam % 4 == 0 && p->stats && (p->offset % 4 == 0) &&
+                 (p->offset_head_stride % 4 == 0), "attn2_bwd: unaligned fused-LayerNorm operands");
+  } else {
+    DLSG_REQUIRE(al16(p->dco) && p->lddco % 4 == 0, "attn2_bwd: unaligned dco");
+  }
   if (p->rows <= 0) return 0;
   DLSG_LAUNCH(attn2_bwd_kernel, p->rows, 256 * p->nh, 0, (cudaStream_t)stream, *p);
   return check_launch("attn2_bwd_kernel");

@@ -1,4 +1,4 @@
-// Per-step fusions of the decoder's LSTM stages (one CTA per batch row, 256 threads, 4 consecutive hidden units per
+// Per-step fusions of the decoder's LSTM stages (one CTA per batch row, H/4 threads (<= 512), 4 consecutive hidden units per
 // thread so every access is a 128-bit load and all loads of a thread are issued back to back):
 //   lstm_cell_norm_fwd : split-K partial sums + hoisted row bias -> gates -> c,h (dropout) -> LayerNorm(h) [-> tanh]
 //                        [-> dropout]; writes h into the next step's operand rows and LN(h) into its consumer's row
@@ -10,7 +10,8 @@
 
 namespace dlsg {
 
-constexpr int FS_NG = 2;          // float4 groups per thread: H <= 2048
+constexpr int FS_NG = 1;          // float4 groups per thread (threads = H/4 <= 512 cover H <= 2048)
+constexpr int FS_MAXH = 2048;
 constexpr int FS_MAXS = 8;        // split-K partials summed in registers
 
 __device__ __forceinline__ float4 ld4f(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -36,7 +37,7 @@ __device__ __forceinline__ bool vecok(const void* p, int dt, int64_t ld) {
 }
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 lstm_cell_norm_fwd_kernel(const dlsg_lstm_cell_norm_fwd_t q) {
   pdl_prologue();
   __shared__ float red[32];
@@ -48,7 +49,7 @@ lstm_cell_norm_fwd_kernel(const dlsg_lstm_cell_norm_fwd_t q) {
   float sum = 0.f;
 #pragma unroll
   for (int e = 0; e < FS_NG; ++e) {
-    const int h = (tid + e * 256) * 4;
+    const int h = (tid + e * (int)blockDim.x) * 4;
     hv[e] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (h < H) {
       float4 g[4];
@@ -76,7 +77,10 @@ lstm_cell_norm_fwd_kernel(const dlsg_lstm_cell_norm_fwd_t q) {
         ai[u] = sigmoidf_(gi_[u]); af[u] = sigmoidf_(gf_[u]); ag[u] = tanhf(gg_[u]); ao[u] = sigmoidf_(go_[u]);
         cc[u] = af[u] * cp_[u] + ai[u] * ag[u];
         hh[u] = ao[u] * tanhf(cc[u]);
-        if (p.drop_p > 0.f) hh[u] *= drop_scale(p.drop_p, p.seed, p.offset + (uint64_t)ei + u);
+      }
+      if (p.drop_p > 0.f) {       // offsets are multiples of 4 (checked on the host): one Philox evaluation per float4
+        const float4 m = drop_mask4(p.drop_p, 1.f / (1.f - p.drop_p), p.seed, p.offset + (uint64_t)ei);
+        hh[0] *= m.x; hh[1] *= m.y; hh[2] *= m.z; hh[3] *= m.w;
       }
       const int64_t g0 = (int64_t)b * 4 * H + h;
       *reinterpret_cast<float4*>(p.gates + g0) = make_float4(ai[0], ai[1], ai[2], ai[3]);
@@ -92,11 +96,18 @@ lstm_cell_norm_fwd_kernel(const dlsg_lstm_cell_norm_fwd_t q) {
       sum += (h4.x + h4.y) + (h4.z + h4.w);
     }
   }
+  float4 ga[FS_NG], bt[FS_NG];                      // LayerNorm parameters: loads in flight during the two reductions
+#pragma unroll
+  for (int e = 0; e < FS_NG; ++e) {
+    const int h = (tid + e * (int)blockDim.x) * 4;
+    ga[e] = make_float4(0.f, 0.f, 0.f, 0.f); bt[e] = ga[e];
+    if (h < H) { ga[e] = ld4f(q.gamma + h); bt[e] = ld4f(q.beta + h); }
+  }
   const float mean = block_sum(sum, red) / (float)H;
   float sq = 0.f;
 #pragma unroll
   for (int e = 0; e < FS_NG; ++e) {
-    const int h = (tid + e * 256) * 4;
+    const int h = (tid + e * (int)blockDim.x) * 4;
     if (h < H) {
       const float a = hv[e].x - mean, b2 = hv[e].y - mean, c = hv[e].z - mean, d = hv[e].w - mean;
       sq += (a * a + b2 * b2) + (c * c + d * d);
@@ -106,15 +117,17 @@ lstm_cell_norm_fwd_kernel(const dlsg_lstm_cell_norm_fwd_t q) {
   if (q.stats && tid == 0) { q.stats[b * 2] = mean; q.stats[b * 2 + 1] = rstd; }
 #pragma unroll
   for (int e = 0; e < FS_NG; ++e) {
-    const int h = (tid + e * 256) * 4;
+    const int h = (tid + e * (int)blockDim.x) * 4;
     if (h < H) {
-      const float4 ga = ld4f(q.gamma + h), be = ld4f(q.beta + h);
-      float y[4] = {(hv[e].x - mean) * rstd * ga.x + be.x, (hv[e].y - mean) * rstd * ga.y + be.y,
-                    (hv[e].z - mean) * rstd * ga.z + be.z, (hv[e].w - mean) * rstd * ga.w + be.w};
+      float y[4] = {(hv[e].x - mean) * rstd * ga[e].x + bt[e].x, (hv[e].y - mean) * rstd * ga[e].y + bt[e].y,
+                    (hv[e].z - mean) * rstd * ga[e].z + bt[e].z, (hv[e].w - mean) * rstd * ga[e].w + bt[e].w};
+      if (q.post_tanh) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (q.post_tanh) y[u] = tanhf(y[u]);
-        if (q.ydrop_p > 0.f) y[u] *= drop_scale(q.ydrop_p, q.yseed, q.yoffset + (uint64_t)b * H + h + u);
+        for (int u = 0; u < 4; ++u) y[u] = tanhf(y[u]);
+      }
+      if (q.ydrop_p > 0.f) {
+        const float4 m = drop_mask4(q.ydrop_p, 1.f / (1.f - q.ydrop_p), q.yseed, q.yoffset + (uint64_t)b * H + h);
+        y[0] *= m.x; y[1] *= m.y; y[2] *= m.z; y[3] *= m.w;
       }
       const float4 y4 = make_float4(y[0], y[1], y[2], y[3]);
       if (q.y) st4any(q.y, q.y_dtype, (int64_t)b * q.ldy + h, y4, vy);
@@ -123,7 +136,7 @@ lstm_cell_norm_fwd_kernel(const dlsg_lstm_cell_norm_fwd_t q) {
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 norm_lstm_cell_bwd_kernel(const dlsg_norm_lstm_cell_bwd_t q) {
   pdl_prologue();
   __shared__ float red[32];
@@ -135,16 +148,15 @@ norm_lstm_cell_bwd_kernel(const dlsg_norm_lstm_cell_bwd_t q) {
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int e = 0; e < FS_NG; ++e) {
-    const int h = (tid + e * 256) * 4;
+    const int h = (tid + e * (int)blockDim.x) * 4;
     xh[e] = make_float4(0.f, 0.f, 0.f, 0.f); dv[e] = xh[e];
     if (h < H) {
       const float4 x = ld4f(q.x + (int64_t)b * q.ldx + h);
       float4 dy = ld4f(q.dy + (int64_t)b * q.lddy + h);
       const float4 g = ld4f(q.gamma + h);
       if (q.ydrop_p > 0.f) {
-        const uint64_t i0 = q.yoffset + (uint64_t)b * H + h;
-        dy.x *= drop_scale(q.ydrop_p, q.yseed, i0); dy.y *= drop_scale(q.ydrop_p, q.yseed, i0 + 1);
-        dy.z *= drop_scale(q.ydrop_p, q.yseed, i0 + 2); dy.w *= drop_scale(q.ydrop_p, q.yseed, i0 + 3);
+        const float4 m = drop_mask4(q.ydrop_p, 1.f / (1.f - q.ydrop_p), q.yseed, q.yoffset + (uint64_t)b * H + h);
+        dy.x *= m.x; dy.y *= m.y; dy.z *= m.z; dy.w *= m.w;
       }
       float4 xn = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
       if (q.post_tanh) {
@@ -168,7 +180,7 @@ norm_lstm_cell_bwd_kernel(const dlsg_norm_lstm_cell_bwd_t q) {
   s2 = block_sum(s2, red) / (float)H;
 #pragma unroll
   for (int e = 0; e < FS_NG; ++e) {
-    const int h = (tid + e * 256) * 4;
+    const int h = (tid + e * (int)blockDim.x) * 4;
     if (h < H) {
       const int64_t ei = (int64_t)b * H + h;
       const int64_t g0 = (int64_t)b * 4 * H + h;
@@ -179,7 +191,12 @@ norm_lstm_cell_bwd_kernel(const dlsg_norm_lstm_cell_bwd_t q) {
       if (p.c_prev) cp = ld4f(p.c_prev + ei);
       if (p.dc_next) dcn = ld4f(p.dc_next + ei);
       if (p.dh) r1 = ld4f(p.dh + (int64_t)b * p.lddh + h);
-      if (p.dh2) r2 = ld4f(p.dh2 + (int64_t)b * p.lddh2 + h);
+      if (p.dh2) {
+        r2 = ld4f(p.dh2 + (int64_t)b * p.lddh2 + h);
+#pragma unroll
+        for (int s = 1; s < 16; ++s)
+          if (s < p.dh2_nsplit) r2 = f4add(r2, ld4f(p.dh2 + (int64_t)b * p.lddh2 + h + (int64_t)s * p.dh2_stride_split));
+      }
       if (q.dgates_sum) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) gs[k] = ld4f(q.dgates_sum + (int64_t)b * 4 * H + (int64_t)k * H + h);
@@ -190,10 +207,12 @@ norm_lstm_cell_bwd_kernel(const dlsg_norm_lstm_cell_bwd_t q) {
       const float i_[4] = {ai.x, ai.y, ai.z, ai.w}, f_[4] = {af.x, af.y, af.z, af.w}, g_[4] = {ag.x, ag.y, ag.z, ag.w}, o_[4] = {ao.x, ao.y, ao.z, ao.w};
       const float cn_[4] = {cn.x, cn.y, cn.z, cn.w}, cp_[4] = {cp.x, cp.y, cp.z, cp.w}, dcn_[4] = {dcn.x, dcn.y, dcn.z, dcn.w};
       float d[4][4], dcp[4];
+      float4 hm = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (p.drop_p > 0.f) hm = drop_mask4(p.drop_p, 1.f / (1.f - p.drop_p), p.seed, p.offset + (uint64_t)ei);
+      const float hm_[4] = {hm.x, hm.y, hm.z, hm.w};
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        float dh = dxl[u] + r1_[u] + r2_[u];            // gradient wrt the (dropped) h: LayerNorm path + recurrent paths
-        if (p.drop_p > 0.f) dh *= drop_scale(p.drop_p, p.seed, p.offset + (uint64_t)ei + u);
+        const float dh = (dxl[u] + r1_[u] + r2_[u]) * hm_[u];   // gradient wrt the (dropped) h: LayerNorm path + recurrent paths
         const float tc = tanhf(cn_[u]);
         const float dc = dh * o_[u] * (1.f - tc * tc) + dcn_[u];
         d[0][u] = dc * g_[u] * i_[u] * (1.f - i_[u]);
@@ -224,18 +243,21 @@ norm_lstm_cell_bwd_kernel(const dlsg_norm_lstm_cell_bwd_t q) {
 using namespace dlsg;
 
 static inline bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+// one float4 group per thread up to H = 2048 (512 threads); whole warps
+static inline int fs_threads(int H) { int t = ((H / 4 + 31) / 32) * 32; return t < 64 ? 64 : (t > 512 ? 512 : t); }
 
 extern "C" {
 
-int dlsg_fused_step_supported(int32_t H) { return (H % 4 == 0 && H <= 1024 * FS_NG) ? 1 : 0; }
+int dlsg_fused_step_supported(int32_t H) { return (H % 4 == 0 && H <= FS_MAXH) ? 1 : 0; }
 
 int dlsg_lstm_cell_norm_fwd(const dlsg_lstm_cell_norm_fwd_t* q, void* stream) {
   const dlsg_lstm_cell_fwd_t& p = q->cell;
-  DLSG_REQUIRE(p.B > 0 && p.H > 0 && dlsg_fused_step_supported(p.H) && p.nsplit >= 1, "lstm_cell_norm_fwd: H=%d unsupported (H %% 4 == 0, H <= %d)", p.H, 1024 * FS_NG);
+  DLSG_REQUIRE(p.B > 0 && p.H > 0 && dlsg_fused_step_supported(p.H) && p.nsplit >= 1, "lstm_cell_norm_fwd: H=%d unsupported (H %% 4 == 0, H <= %d)", p.H, FS_MAXH);
   DLSG_REQUIRE(a16(p.gates) && p.stride_split % 4 == 0 && (!p.row_bias || (a16(p.row_bias) && p.ld_row_bias % 4 == 0)) && (!p.bias || a16(p.bias)) &&
                (!p.c_prev || a16(p.c_prev)) && a16(p.c_out) && (!p.h_out || a16(p.h_out)) && a16(q->gamma) && a16(q->beta),
                "lstm_cell_norm_fwd: fp32 operands must be 16-byte aligned");
-  DLSG_LAUNCH(lstm_cell_norm_fwd_kernel, p.B, 256, 0, (cudaStream_t)stream, *q);
+  DLSG_REQUIRE(p.offset % 4 == 0 && q->yoffset % 4 == 0, "lstm_cell_norm_fwd: dropout offsets must be multiples of 4");
+  DLSG_LAUNCH(lstm_cell_norm_fwd_kernel, p.B, fs_threads(p.H), 0, (cudaStream_t)stream, *q);
   return check_launch("lstm_cell_norm_fwd_kernel");
 }
 
@@ -248,7 +270,8 @@ int dlsg_norm_lstm_cell_bwd(const dlsg_norm_lstm_cell_bwd_t* q, void* stream) {
                (!p.dh || (a16(p.dh) && p.lddh % 4 == 0)) && (!p.dh2 || (a16(p.dh2) && p.lddh2 % 4 == 0)) &&
                (!p.dgates || a16(p.dgates)) && (!q->dgates_sum || a16(q->dgates_sum)),
                "norm_lstm_cell_bwd: fp32 operands must be 16-byte aligned with row pitches multiple of 4");
-  DLSG_LAUNCH(norm_lstm_cell_bwd_kernel, p.B, 256, 0, (cudaStream_t)stream, *q);
+  DLSG_REQUIRE(p.offset % 4 == 0 && q->yoffset % 4 == 0, "norm_lstm_cell_bwd: dropout offsets must be multiples of 4");
+  DLSG_LAUNCH(norm_lstm_cell_bwd_kernel, p.B, fs_threads(p.H), 0, (cudaStream_t)stream, *q);
   return check_launch("norm_lstm_cell_bwd_kernel");
 }
 

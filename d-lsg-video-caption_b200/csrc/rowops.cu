@@ -503,7 +503,14 @@ lstm_cell_bwd_kernel(const dlsg_lstm_cell_bwd_t p) {
     const int64_t g0 = (int64_t)b * 4 * H + h;
     const float ig = p.acts[g0], fg = p.acts[g0 + H], gg = p.acts[g0 + 2 * (int64_t)H], og = p.acts[g0 + 3 * (int64_t)H];
     float dh = p.dh[(int64_t)b * p.lddh + h];
-    if (p.dh2) dh += p.dh2[(int64_t)b * p.lddh2 + h];
+    if (p.dh2) {
+      const float* d2 = p.dh2 + (int64_t)b * p.lddh2 + h;
+      float v = d2[0];
+#pragma unroll
+      for (int s = 1; s < 16; ++s)              // unrolled + predicated: all partial loads in flight together
+        if (s < p.dh2_nsplit) v += d2[(int64_t)s * p.dh2_stride_split];
+      dh += v;
+    }
     if (p.drop_p > 0.f) dh *= drop_scale(p.drop_p, p.seed, p.offset + (uint64_t)e);
     const float tc = tanhf(p.c_new[e]);
     float dc = dh * og * (1.f - tc * tc);

@@ -55,7 +55,8 @@ class CellBwdT(C.Structure):
                 ('dgates', vp), ('dgates2', vp), ('ld_dgates2', i64), ('dgates2_dtype', i32), ('_pad0', i32),
                 ('dgatesT', vp), ('ld_dgatesT', i64), ('dgatesT_dtype', i32), ('_pad1', i32),
                 ('dc_prev', vp), ('B', i32), ('H', i32),
-                ('drop_p', f32), ('_pad2', i32), ('seed', u64), ('offset', u64)]
+                ('drop_p', f32), ('_pad2', i32), ('seed', u64), ('offset', u64),
+                ('dh2_nsplit', i32), ('_pad3', i32), ('dh2_stride_split', i64)]
 
 
 class CellNormFwdT(C.Structure):
@@ -93,14 +94,21 @@ class Attn2FwdT(C.Structure):
     _fields_ = [('KW', vp), ('VW', vp), ('q', vp), ('alpha', vp), ('co', vp),
                 ('ldq', i64), ('ldalpha', i64), ('ldco', i64),
                 ('rows', i32), ('nh', i32), ('P', i32), ('Hk', i32), ('Hv', i32), ('rows_per_node', i32), ('nodes', i32),
-                ('scale', f32)]
+                ('scale', f32),
+                ('y', vp), ('ldy', i64), ('y_dtype', i32), ('_pad0', i32),
+                ('gamma', vp * 2), ('beta', vp * 2), ('stats', vp), ('stats_head_stride', i64),
+                ('drop_p', f32), ('_pad1', i32), ('seed', u64), ('offset', u64), ('offset_head_stride', u64)]
 
 
 class Attn2BwdT(C.Structure):
     _fields_ = [('KW', vp), ('VW', vp), ('q', vp), ('alpha', vp), ('dco', vp), ('dalpha_ext', vp),
                 ('dq', vp), ('dKW', vp), ('dVW', vp),
                 ('ldq', i64), ('ldalpha', i64), ('lddco', i64), ('lddq', i64),
-                ('rows', i32), ('nh', i32), ('P', i32), ('Hk', i32), ('Hv', i32), ('scale', f32)]
+                ('rows', i32), ('nh', i32), ('P', i32), ('Hk', i32), ('Hv', i32), ('scale', f32),
+                ('dy', vp), ('lddy', i64), ('co', vp), ('ldco', i64),
+                ('gamma', vp * 2), ('stats', vp), ('stats_head_stride', i64),
+                ('dgamma_rows', vp), ('dbeta_rows', vp), ('ld_dparam', i64),
+                ('drop_p', f32), ('_pad1', i32), ('seed', u64), ('offset', u64), ('offset_head_stride', u64)]
 
 
 SIGNATURES = {

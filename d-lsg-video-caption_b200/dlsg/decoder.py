@@ -21,18 +21,7 @@ from .linalg import empty, zeros, op, op_empty, op_zeros, ceil8
 START = 1
 
 
-def splitk_for(rows, n_out, K):
-    """Split-K factor for a skinny recurrent GEMM (rows <= 64 ride the UMMA N side, weights fill 128-row tiles): enough
-    CTAs to cover the 148 SMs, >= 4 k-blocks (of 64) per split, no empty split.  1 when the batch is not skinny."""
-    if rows > 64 or la.precision() != 'bf16':
-        return 1
-    tiles = (n_out + 127) // 128
-    kb = (K + 63) // 64
-    if tiles * 2 > 148 or kb < 8:
-        return 1
-    s = min(148 // tiles, kb // 4, 16)          # floor: tiles*s CTAs fit in one wave of the 148-CTA persistent grid
-    per = (kb + s - 1) // s
-    return max(1, (kb + per - 1) // per)
+splitk_for = la.splitk_for
 
 
 def flat2(x):
@@ -184,15 +173,20 @@ class DecoderCore:
             be.lstm_cell_fwd(b.gq[:, i], b.cq[i], b.cq[j], h_out=b.qh[i], row_bias=rb, h2=b.Xq[j][:, oQ:oQ + Hq])
             be.norm_fwd(b.qh[i], lnq_w, lnq_b, y=qy, y2=qy2, stats=b.statq[i], drop=dq)
         if self.hoist:
-            be.attn2_fwd(Kp, Vp, b.q32[i], b.alpha[i], b.co[i], 1.0 / math.sqrt(H), rows_per_node)   # Kp,Vp hold KW,VW
+            # one kernel: attention over the hoisted KW / VW (Kp, Vp hold them) + the context output layer
+            # tanh -> LayerNorm -> dropout of both heads, written straight into the lang-LSTM operand row
+            be.attn2_fwd(Kp, Vp, b.q32[i], b.alpha[i], b.co[i], 1.0 / math.sqrt(H), rows_per_node,
+                         ln=dict(gamma=[t[pf + h + '.output_layer.2.weight'] for h in self.heads],
+                                 beta=[t[pf + h + '.output_layer.2.bias'] for h in self.heads],
+                                 y=b.Xl[i][:, :nh * H], stats=b.statc[i], drop=dc, drop_head_stride=1 << 28))
         else:
             be.gemm(b.Xl[i][:, oq:oq + Hq], pk['Wqp'], b.qp[i])
             be.node_attn_fwd(Kp, Vp, b.qp[i], b.alpha[i], b.ctxr[i], rows_per_node)
             be.gemm(b.ctxr[i].view(R, nh, H).transpose(0, 1), pk['Wo'], b.co[i].view(R, nh, H).transpose(0, 1))
-        for k, h in enumerate(self.heads):
-            be.norm_fwd(b.co[i][:, k * H:(k + 1) * H], t[pf + h + '.output_layer.2.weight'], t[pf + h + '.output_layer.2.bias'],
-                        y=b.Xl[i][:, k * H:(k + 1) * H], stats=b.statc[i, k], pre_tanh=True,
-                        drop=(None if dc is None else (dc[0], dc[1], dc[2] + (k << 28))))
+            for k, h in enumerate(self.heads):
+                be.norm_fwd(b.co[i][:, k * H:(k + 1) * H], t[pf + h + '.output_layer.2.weight'], t[pf + h + '.output_layer.2.bias'],
+                            y=b.Xl[i][:, k * H:(k + 1) * H], stats=b.statc[i, k], pre_tanh=True,
+                            drop=(None if dc is None else (dc[0], dc[1], dc[2] + (k << 28))))
         be.gemm(b.Xl[i], pk['Wl'], b.gl[:, i] if b.Sl > 1 else b.gl[0, i], splitk=b.Sl)
         # fused: cell -> lang_h = dropout(h) (recurrent state, layer.py:594) -> tanh(LN(lang_h))
         lnl_w, lnl_b = t[pf + 'lang_lstm_layernorm.weight'], t[pf + 'lang_lstm_layernorm.bias']
@@ -354,7 +348,7 @@ class DecoderTrainBlock:
         dgq_sum = zeros((B, 4 * Hq), ref)
         hoist = core.hoist
         if hoist:
-            dco32 = empty((B, nh * H), ref)
+            lc_g, lc_b = empty((T, B, nh * H), ref), empty((T, B, nh * H), ref)     # per-row ctx-LayerNorm gradient terms
         else:
             dqp_all = op_empty((TB,), nh * H, ref)
             dco_all = op_empty((T, B), nh * H, ref)
@@ -377,23 +371,26 @@ class DecoderTrainBlock:
             if fused:
                 be.norm_lstm_cell_bwd(b.gl[0, i], b.cl[i], b.cl[j], dcl, dcl2, dDall[:, i], b.lh[j], lnl[0], lnl[1], b.statl[i],
                                       ll_g[i], ll_b[i], dh=dXq[j][:, :Hd], dh2=dXl[j][:, ol:ol + Hd], dgates2=dgl_all[rows],
-                                      dgatesT=dglT[:, rows], drop=dl, post_tanh=True)
+                                      drop=dl, post_tanh=True)
             else:
                 be.norm_bwd(dDall[:, i], b.lh[j], lnl[0], lnl[1], b.statl[i], dx=dXq[j][:, :Hd], dgamma=lnl[2], dbeta=lnl[3],
                             post_tanh=True, dx_accum=True)
                 be.lstm_cell_bwd(b.gl[0, i], b.cl[i], b.cl[j], dXq[j][:, :Hd], dcl, dcl2, dgates2=dgl_all[rows],
-                                 dgatesT=dglT[:, rows], drop=dl, dh2=dXl[j][:, ol:ol + Hd])
+                                 drop=dl, dh2=dXl[j][:, ol:ol + Hd])
             dcl, dcl2 = dcl2, dcl
             be.gemm(dgl_all[rows], pk['WlT'], dXl[i])
-            for k, h in enumerate(heads):
-                be.norm_bwd(dXl[i][:, k * H:(k + 1) * H], b.co[i][:, k * H:(k + 1) * H], lnc[k][0], lnc[k][1], b.statc[i, k],
-                            dx=(dco32 if hoist else dco_all[i])[:, k * H:(k + 1) * H], dgamma=lnc[k][2], dbeta=lnc[k][3],
-                            pre_tanh=True, drop=(None if dc is None else (dc[0], dc[1], dc[2] + (k << 28))))
             if hoist:
-                # one kernel: d(alpha), softmax backward, dq += sum_h sum_p dl KW, dKW / dVW accumulated over time
-                be.attn2_bwd(Kp, Vp, b.q32[i], b.alpha[i], dco32, dXl[i][:, oq:oq + Hq], dKp, dVp, att_scale,
-                             dalpha_ext=(da_ext[i] if da_ext is not None else None))
+                # one kernel: output-layer backward (dropout, LayerNorm, tanh) of both heads -> d(alpha), softmax backward,
+                # dq += sum_h sum_p dl KW, dKW / dVW accumulated over time; LN parameter gradients as per-row contributions
+                be.attn2_bwd(Kp, Vp, b.q32[i], b.alpha[i], None, dXl[i][:, oq:oq + Hq], dKp, dVp, att_scale,
+                             dalpha_ext=(da_ext[i] if da_ext is not None else None),
+                             ln=dict(dy=dXl[i][:, :nh * H], co=b.co[i], gamma=[lnc[k][0] for k in range(nh)], stats=b.statc[i],
+                                     dgamma_rows=lc_g[i], dbeta_rows=lc_b[i], drop=dc, drop_head_stride=1 << 28))
             else:
+                for k, h in enumerate(heads):
+                    be.norm_bwd(dXl[i][:, k * H:(k + 1) * H], b.co[i][:, k * H:(k + 1) * H], lnc[k][0], lnc[k][1], b.statc[i, k],
+                                dx=dco_all[i][:, k * H:(k + 1) * H], dgamma=lnc[k][2], dbeta=lnc[k][3],
+                                pre_tanh=True, drop=(None if dc is None else (dc[0], dc[1], dc[2] + (k << 28))))
                 be.gemm(dco_all[i].view(B, nh, H).transpose(0, 1), pk['WoT'], dctxr.view(B, nh, H).transpose(0, 1))
                 be.node_attn_bwd(Kp, Vp, b.qp[i], b.alpha[i], dctxr, dqp_all[rows], dKp, dVp,
                                  dalpha_ext=(da_ext[i] if da_ext is not None else None))
@@ -403,12 +400,12 @@ class DecoderTrainBlock:
             if fused:
                 be.norm_lstm_cell_bwd(b.gq[0, i], b.cq[i], b.cq[j], dcq, dcq2, dXl[i][:, oq:oq + Hq], b.qh[i], lnq[0], lnq[1],
                                       b.statq[i], lq_g[i], lq_b[i], dh=dXq[j][:, oQ:oQ + Hq], dgates2=dgq_all[rows],
-                                      dgatesT=dgqT[:, rows], dgates_sum=dgq_sum, ydrop=dq)
+                                      dgates_sum=dgq_sum, ydrop=dq)
             else:
                 be.norm_bwd(dXl[i][:, oq:oq + Hq], b.qh[i], lnq[0], lnq[1], b.statq[i], dx=dXq[j][:, oQ:oQ + Hq], dgamma=lnq[2],
                             dbeta=lnq[3], drop=dq, dx_accum=True)
                 be.lstm_cell_bwd(b.gq[0, i], b.cq[i], b.cq[j], dXq[j][:, oQ:oQ + Hq], dcq, dcq2, dgates=dgq32,
-                                 dgates2=dgq_all[rows], dgatesT=dgqT[:, rows])
+                                 dgates2=dgq_all[rows])
                 be.axpby(dgq32, 1.0, dgq_sum, 1.0)
             dcq, dcq2 = dcq2, dcq
             be.gemm(dgq_all[rows], pk['WqT'], dXq[i])
@@ -418,7 +415,15 @@ class DecoderTrainBlock:
             be.colsum(lq_b.view(TB, Hq), lnq[3])
             be.colsum(ll_g.view(TB, Hd), lnl[2])
             be.colsum(ll_b.view(TB, Hd), lnl[3])
+        if hoist:
+            for k in range(nh):
+                be.colsum(lc_g.view(TB, nh * H)[:, k * H:(k + 1) * H], lnc[k][2])
+                be.colsum(lc_b.view(TB, nh * H)[:, k * H:(k + 1) * H], lnc[k][3])
         Xq2, Xl2 = flat2(b.Xq[:T]), flat2(b.Xl[:T])
+        # transposed gate-gradient operands of the time-batched weight-gradient GEMMs: ONE coalesced transpose each
+        # after the loop (per-step transposed stores would be 2-byte scattered writes)
+        be.convert(dgq_all, dstT=dgqT)
+        be.convert(dgl_all, dstT=dglT)
         dWq = la.mm(dgqT, Xq2.t())                                # (4Hq, Kq)
         dWl = la.mm(dglT, Xl2.t())                                # (4Hd, Kl)
         dgs_op = op(dgq_sum)

@@ -382,7 +382,10 @@ class EncoderVisualBlock:
         Gin = empty((B, T, 2 * H4), frames)
         be.gemm(Xe, Wih, Gin.view(B * T, 2 * H4), bias=bsum)
         lstm_out = empty((B, T, 2 * H), frames)
-        gates = zeros((2, T, B, H4), frames)
+        # the two directions run concurrently: each recurrent GEMM is split over K to fill HALF of the SMs and the cell
+        # kernel sums the partials itself (no reduce launch)
+        Sg = la.splitk_for(B, H4, H, sms=74)
+        gates = zeros((Sg, 2, T, B, H4), frames)     # [0] ends up holding the activated gates (saved for BPTT)
         cs = zeros((2, T + 1, B, H), frames)
         hprev = op_zeros((2, T, B), H, frames)       # h fed INTO step t (operand dtype)
         whh = [WC.get(t[pf + 'lstm.weight_hh_l0']), WC.get(t[pf + 'lstm.weight_hh_l0_reverse'])]
@@ -391,9 +394,9 @@ class EncoderVisualBlock:
             order = list(range(T)) if d == 0 else list(range(T - 1, -1, -1))
             for k, tt in enumerate(order):
                 if k > 0:
-                    be.gemm(hprev[d, tt], whh[d], gates[d, tt])
+                    be.gemm(hprev[d, tt], whh[d], gates[:, d, tt] if Sg > 1 else gates[0, d, tt], splitk=Sg)
                 nxt = order[k + 1] if k + 1 < T else None
-                be.lstm_cell_fwd(gates[d, tt], cs[d, k], cs[d, k + 1], row_bias=Gin[:, tt, d * H4:(d + 1) * H4],
+                be.lstm_cell_fwd(gates[:, d, tt], cs[d, k], cs[d, k + 1], row_bias=Gin[:, tt, d * H4:(d + 1) * H4],
                                  h2=lstm_out[:, tt, d * H:(d + 1) * H], h3=(hprev[d, nxt] if nxt is not None else None))
         two_streams(frames, lambda: run_dir(0), lambda: run_dir(1))     # the two directions are independent chains
         Y = empty((B * T, 2 * H), frames)
@@ -401,7 +404,7 @@ class EncoderVisualBlock:
         dY = site(self.p if training else 0.0, seed, 1)
         be.norm_fwd(lstm_out.view(B * T, 2 * H), t[pf + 'layernorm_lstm.weight'], t[pf + 'layernorm_lstm.bias'], y=Y,
                     stats=stY, drop=dY)
-        sv = dict(t=t, dims=(B, T, Din, H), f2=f2, Xe=Xe, gates=gates, cs=cs, hprev=hprev, lstm_out=lstm_out, stY=stY, dY=dY)
+        sv = dict(t=t, dims=(B, T, Din, H), f2=f2, Xe=Xe, gates=gates[0], cs=cs, hprev=hprev, lstm_out=lstm_out, stY=stY, dY=dY)
         if self.baseline:
             out = la.mm(Y, WC.get(t[pf + 'out_try.weight']), bias=t[pf + 'out_try.bias'])
             sv.update(Y=Y)
@@ -509,22 +512,25 @@ class EncoderVisualBlock:
         names_hh = ['lstm.weight_hh_l0', 'lstm.weight_hh_l0_reverse']
         # everything that crosses the stream fork/join is allocated here, on the main stream
         dgTs = [op_empty((H4,), T * B, ref) for _ in range(2)]
-        bufs = [(zeros((B, H), ref), zeros((B, H), ref), empty((B, H), ref)) for _ in range(2)]
+        Sd = la.splitk_for(B, H, H4, sms=74)             # recurrent data-gradient GEMM: partials summed by the cell kernel
+        bufs = [(zeros((Sd, B, H), ref), zeros((B, H), ref), empty((B, H), ref)) for _ in range(2)]
 
         def run_dir_bwd(d):
             order = list(range(T)) if d == 0 else list(range(T - 1, -1, -1))
-            dgT = dgTs[d]
             dhrec, dc, dc2 = bufs[d]
             for k in range(T - 1, -1, -1):
                 tt = order[k]
                 dg2 = dGin[:, tt, d * H4:(d + 1) * H4]
                 be.lstm_cell_bwd(gates[d, tt], cs[d, k], cs[d, k + 1], dL[:, tt, d * H:(d + 1) * H], dc, dc2,
-                                 dgates2=dg2, dgatesT=dgT[:, tt * B:(tt + 1) * B], dh2=dhrec)
+                                 dgates2=dg2, dh2=dhrec)
                 dc, dc2 = dc2, dc
                 if k > 0:
-                    be.gemm(op(dg2), whhT[d], dhrec)
+                    be.gemm(op(dg2), whhT[d], dhrec if Sd > 1 else dhrec[0], splitk=Sd)
         two_streams(ref, lambda: run_dir_bwd(0), lambda: run_dir_bwd(1))
         for d in range(2):
+            # transposed gate gradients (H4, T*B) for the time-batched weight-gradient GEMM: one batched transpose
+            src = dGin.transpose(0, 1)[:, :, d * H4:(d + 1) * H4]                  # (T, B, H4)
+            be.convert(src, dstT=dgTs[d].as_strided((T, H4, B), (B, dgTs[d].stride(0), 1)))
             hp = hprev[d]
             grads[pf + names_hh[d]] = la.mm(dgTs[d], hp.as_strided((T * B, H), (hp.stride(1), 1)).t())
         Wih, _ = self._packs(t, pf)

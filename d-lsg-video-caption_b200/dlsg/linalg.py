@@ -170,3 +170,18 @@ class WeightCache:
 
 def pver(*params):
     return tuple((p._version, p.data_ptr()) for p in params)
+
+
+def splitk_for(rows, n_out, K, sms=148):
+    """Split-K factor for a skinny recurrent GEMM (rows <= 64 ride the UMMA N side, weights fill 128-row tiles): enough
+    CTAs to cover `sms` SMs (148 = the whole GPU; 74 when two such chains run concurrently on two streams), >= 4
+    k-blocks (of 64) per split, no empty split.  1 when the batch is not skinny."""
+    if rows > 64 or precision() != 'bf16':
+        return 1
+    tiles = (n_out + 127) // 128
+    kb = (K + 63) // 64
+    if tiles * 2 > sms or kb < 8:
+        return 1
+    s = min(sms // tiles, kb // 4, 16)          # floor: tiles*s CTAs fit in one wave of the persistent grid
+    per = (kb + s - 1) // s
+    return max(1, (kb + per - 1) // per)

@@ -285,6 +285,10 @@ class CudaBackend:
             p.dh, p.lddh = dh.data_ptr(), dh.stride(0)
             assert dh.stride(1) == 1
         if dh2 is not None:
+            if dh2.dim() == 3:                              # (S, B, H) split-K partial sums of the recurrent gradient
+                p.dh2_nsplit, p.dh2_stride_split = dh2.shape[0], dh2.stride(0)
+                dh2 = dh2[0]
+            assert dh2.stride(1) == 1
             p.dh2, p.lddh2 = dh2.data_ptr(), dh2.stride(0)
         assert c_new.is_contiguous() and acts.is_contiguous()
         p.dgates, p.dc_prev, p.B, p.H = _ptr(dgates), _ptr(dc_prev), B, H4 // 4
@@ -357,8 +361,11 @@ class CudaBackend:
     def attn2_supported(nh, P, Hk, Hv):
         return 1 <= nh <= 2 and 1 <= P <= 8 and Hk <= 1024 and Hv <= 1024 and Hk % 4 == 0 and Hv % 4 == 0
 
-    def attn2_fwd(self, KW, VW, q, alpha, co, scale, rows_per_node=1):
-        """KW (nh,nodes,P,Hk), VW (nh,nodes,P,Hv) fp32 contiguous; q (rows,Hk) view; alpha (rows,nh*P); co (rows,nh*Hv) view."""
+    def attn2_fwd(self, KW, VW, q, alpha, co, scale, rows_per_node=1, ln=None):
+        """KW (nh,nodes,P,Hk), VW (nh,nodes,P,Hv) fp32 contiguous; q (rows,Hk) view; alpha (rows,nh*P); co (rows,nh*Hv) view.
+
+        ln = dict(gamma=[..nh], beta=[..nh], y=(rows,nh*Hv) view, stats=(nh,rows,2), drop=(p,seed,offset)|None,
+        drop_head_stride=int) fuses the context output layer tanh -> LayerNorm -> dropout into the same kernel."""
         self._ck(KW)
         p = L.Attn2FwdT()
         nh, nodes, P, Hk = KW.shape
@@ -366,20 +373,46 @@ class CudaBackend:
         p.KW, p.VW, p.q, p.alpha, p.co = KW.data_ptr(), VW.data_ptr(), q.data_ptr(), _ptr(alpha), co.data_ptr()
         p.ldq, p.ldalpha, p.ldco = q.stride(0), (alpha.stride(0) if alpha is not None else 0), co.stride(0)
         p.rows, p.nh, p.P, p.Hk, p.Hv, p.rows_per_node, p.nodes, p.scale = q.shape[0], nh, P, Hk, VW.shape[3], rows_per_node, nodes, scale
+        if ln is not None:
+            y, st = ln['y'], ln['stats']
+            assert y.stride(1) == 1 and st.is_contiguous() and tuple(st.shape) == (nh, q.shape[0], 2)
+            p.y, p.ldy, p.y_dtype = y.data_ptr(), y.stride(0), _dt(y)
+            for k in range(nh):
+                p.gamma[k], p.beta[k] = ln['gamma'][k].data_ptr(), ln['beta'][k].data_ptr()
+            p.stats, p.stats_head_stride = st.data_ptr(), st.stride(0)
+            if ln.get('drop') is not None:
+                p.drop_p, p.seed, p.offset = ln['drop']
+                p.offset_head_stride = ln['drop_head_stride']
         self.launches += 1
         L.check(self.lib.dlsg_attn2_fwd(C.byref(p), _stream()), 'dlsg_attn2_fwd')
 
-    def attn2_bwd(self, KW, VW, q, alpha, dco, dq, dKW, dVW, scale, dalpha_ext=None):
+    def attn2_bwd(self, KW, VW, q, alpha, dco, dq, dKW, dVW, scale, dalpha_ext=None, ln=None):
+        """ln = dict(dy=(rows,nh*Hv) fp32 view, co=(rows,nh*Hv), gamma=[..nh], stats=(nh,rows,2), dgamma_rows, dbeta_rows
+        (rows,nh*Hv) views, drop, drop_head_stride): the backward of the fused output layer produces dco in-kernel."""
         self._ck(KW)
         p = L.Attn2BwdT()
         nh, nodes, P, Hk = KW.shape
         assert nodes == q.shape[0] and dKW.is_contiguous() and dVW.is_contiguous() and dq.stride(1) == 1
-        p.KW, p.VW, p.q, p.alpha, p.dco, p.dalpha_ext = KW.data_ptr(), VW.data_ptr(), q.data_ptr(), alpha.data_ptr(), dco.data_ptr(), _ptr(dalpha_ext)
+        p.KW, p.VW, p.q, p.alpha, p.dco, p.dalpha_ext = KW.data_ptr(), VW.data_ptr(), q.data_ptr(), alpha.data_ptr(), _ptr(dco), _ptr(dalpha_ext)
         p.dq, p.dKW, p.dVW = dq.data_ptr(), dKW.data_ptr(), dVW.data_ptr()
-        p.ldq, p.ldalpha, p.lddco, p.lddq = q.stride(0), alpha.stride(0), dco.stride(0), dq.stride(0)
+        p.ldq, p.ldalpha, p.lddco, p.lddq = q.stride(0), alpha.stride(0), (dco.stride(0) if dco is not None else 0), dq.stride(0)
         p.rows, p.nh, p.P, p.Hk, p.Hv, p.scale = q.shape[0], nh, P, Hk, VW.shape[3], scale
         if dalpha_ext is not None:
             assert dalpha_ext.stride(0) == alpha.stride(0)
+        if ln is not None:
+            dy, co, st, dgr, dbr = ln['dy'], ln['co'], ln['stats'], ln['dgamma_rows'], ln['dbeta_rows']
+            assert dy.dtype == torch.float32 and dy.stride(1) == 1 and co.stride(1) == 1 and st.is_contiguous()
+            assert dgr.stride(1) == 1 and dbr.stride(1) == 1 and dgr.stride(0) == dbr.stride(0)
+            p.dy, p.lddy, p.co, p.ldco = dy.data_ptr(), dy.stride(0), co.data_ptr(), co.stride(0)
+            for k in range(nh):
+                p.gamma[k] = ln['gamma'][k].data_ptr()
+            p.stats, p.stats_head_stride = st.data_ptr(), st.stride(0)
+            p.dgamma_rows, p.dbeta_rows, p.ld_dparam = dgr.data_ptr(), dbr.data_ptr(), dgr.stride(0)
+            if ln.get('drop') is not None:
+                p.drop_p, p.seed, p.offset = ln['drop']
+                p.offset_head_stride = ln['drop_head_stride']
+        else:
+            assert dco is not None
         self.launches += 1
         L.check(self.lib.dlsg_attn2_bwd(C.byref(p), _stream()), 'dlsg_attn2_bwd')
 

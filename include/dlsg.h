@@ -120,6 +120,7 @@ typedef struct {
   float* dc_prev;
   int32_t B, H;
   float drop_p; int32_t _pad2; uint64_t seed, offset;
+  int32_t dh2_nsplit; int32_t _pad3; int64_t dh2_stride_split;   /* dh2 = sum of dh2_nsplit (<=1: one) split-K partial buffers */
 } dlsg_lstm_cell_bwd_t;
 int dlsg_lstm_cell_bwd(const dlsg_lstm_cell_bwd_t* p, void* stream);
 
@@ -186,12 +187,25 @@ typedef struct {
   const float* KW; const float* VW; const float* q; float* alpha; float* co;
   int64_t ldq, ldalpha, ldco;
   int32_t rows, nh, P, Hk, Hv, rows_per_node, nodes; float scale;
+  /* optional fused tail = the context output layer (sublayer.py:41 Tanh -> LayerNorm -> Dropout), active when y != NULL:
+   * y[r, hd*Hv + c] = dropout(LN_hd(tanh(co[r, hd*Hv + c]))), stats[hd*stats_head_stride + 2r] = {mean, rstd};
+   * dropout keeps element iff philox(seed, offset + hd*offset_head_stride + r*Hv + c) >= drop_p.                    */
+  void* y; int64_t ldy; int32_t y_dtype; int32_t _pad0;
+  const float* gamma[2]; const float* beta[2]; float* stats; int64_t stats_head_stride;
+  float drop_p; int32_t _pad1; uint64_t seed, offset, offset_head_stride;
 } dlsg_attn2_fwd_t;
 typedef struct {
   const float* KW; const float* VW; const float* q; const float* alpha; const float* dco; const float* dalpha_ext;
   float* dq; float* dKW; float* dVW;
   int64_t ldq, ldalpha, lddco, lddq;
   int32_t rows, nh, P, Hk, Hv; float scale;
+  /* optional fused head = backward of the context output layer, active when dy != NULL (dco is then ignored):
+   * dco = d/dco [ dropout(LN_hd(tanh(co))) ] . dy ; the LayerNorm parameter gradients are written as per-ROW
+   * contributions dgamma_rows / dbeta_rows (rows, nh*Hv) [ld_dparam] for one dlsg_colsum after BPTT (no atomics). */
+  const float* dy; int64_t lddy; const float* co; int64_t ldco;
+  const float* gamma[2]; const float* stats; int64_t stats_head_stride;
+  float* dgamma_rows; float* dbeta_rows; int64_t ld_dparam;
+  float drop_p; int32_t _pad1; uint64_t seed, offset, offset_head_stride;
 } dlsg_attn2_bwd_t;
 int dlsg_attn2_supported(int32_t nh, int32_t P, int32_t Hk, int32_t Hv);
 int dlsg_attn2_fwd(const dlsg_attn2_fwd_t* p, void* stream);

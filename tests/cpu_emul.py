@@ -134,7 +134,7 @@ class CpuEmulBackend:
         self.launches += 1
         assert drop is None or drop[0] == 0
         if dh2 is not None:
-            dh = dh + dh2
+            dh = dh + (dh2.sum(0) if dh2.dim() == 3 else dh2)
         H = acts.shape[1] // 4
         i, f, g, o = acts[:, :H], acts[:, H:2 * H], acts[:, 2 * H:3 * H], acts[:, 3 * H:]
         tc = torch.tanh(c_new)
@@ -250,7 +250,7 @@ class CpuEmulBackend:
     def attn2_supported(nh, P, Hk, Hv):
         return 1 <= nh <= 2 and 1 <= P <= 8 and Hk <= 1024 and Hv <= 1024 and Hk % 4 == 0 and Hv % 4 == 0
 
-    def attn2_fwd(self, KW, VW, q, alpha, co, scale, rows_per_node=1):
+    def attn2_fwd(self, KW, VW, q, alpha, co, scale, rows_per_node=1, ln=None):
         self.launches += 1
         nh, nodes, P, Hk = KW.shape
         Hv = VW.shape[3]
@@ -261,11 +261,35 @@ class CpuEmulBackend:
             if alpha is not None:
                 alpha[:, h * P:(h + 1) * P].copy_(a)
             co[:, h * Hv:(h + 1) * Hv].copy_(torch.einsum('rp,rpv->rv', a, VW[h][idx]))
+        if ln is not None:
+            for h in range(nh):
+                d = ln.get('drop')
+                d = None if d is None else (d[0], d[1], d[2] + h * ln['drop_head_stride'])
+                self.norm_fwd(co[:, h * Hv:(h + 1) * Hv], ln['gamma'][h], ln['beta'][h], y=ln['y'][:, h * Hv:(h + 1) * Hv],
+                              stats=ln['stats'][h], pre_tanh=True, drop=d)
+                self.launches -= 1
 
-    def attn2_bwd(self, KW, VW, q, alpha, dco, dq, dKW, dVW, scale, dalpha_ext=None):
+    def attn2_bwd(self, KW, VW, q, alpha, dco, dq, dKW, dVW, scale, dalpha_ext=None, ln=None):
         self.launches += 1
         nh, nodes, P, Hk = KW.shape
         Hv = VW.shape[3]
+        if ln is not None:
+            dco = torch.empty_like(ln['co'])
+            for h in range(nh):
+                sl = slice(h * Hv, (h + 1) * Hv)
+                d = ln.get('drop')
+                d = None if d is None else (d[0], d[1], d[2] + h * ln['drop_head_stride'])
+                dg, db = torch.zeros(Hv), torch.zeros(Hv)
+                # per-row parameter-gradient contributions: run the row-wise reference one row at a time
+                x, dy, st = ln['co'][:, sl], ln['dy'][:, sl], ln['stats'][h]
+                t = torch.tanh(x)
+                xh = (t - st[:, :1]) * st[:, 1:2]
+                assert d is None or d[0] == 0, 'dropout is not emulated on CPU'
+                dyd = dy
+                ln['dgamma_rows'][:, sl].copy_(dyd * xh)
+                ln['dbeta_rows'][:, sl].copy_(dyd)
+                self.norm_bwd(dy, x, ln['gamma'][h], None, st, dx=dco[:, sl], dgamma=dg, dbeta=db, pre_tanh=True, drop=d)
+                self.launches -= 1
         for h in range(nh):
             a = alpha[:, h * P:(h + 1) * P]
             dc = dco[:, h * Hv:(h + 1) * Hv]

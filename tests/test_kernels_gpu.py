@@ -267,6 +267,59 @@ def test_attn2_hoisted(be, nh, P, Hk, Hv, rpn):
              dict(dalpha_ext=R(rows, nh * P)), [5, 6, 7], tol=3e-5)
 
 
+@pytest.mark.parametrize('nh,P,Hk,Hv,ydt', [(2, 5, 1024, 1024, torch.bfloat16), (2, 8, 64, 64, torch.float32), (1, 6, 64, 96, torch.float32)])
+def test_attn2_fused_output_layer(be, nh, P, Hk, Hv, ydt):
+    """attn2 with the context output layer (tanh -> LayerNorm -> dropout) fused in: forward and backward against the
+    emulator without dropout, and against the unfused GPU kernels (attn2 + norm per head, same Philox sites) with it."""
+    rows = 7
+    KW, VW, q = R(nh, rows, P, Hk, scale=0.3), R(nh, rows, P, Hv), R(rows, Hk)
+    gam, bet = [1 + 0.1 * R(Hv) for _ in range(nh)], [0.1 * R(Hv) for _ in range(nh)]
+    dy, dq0, dK0, dV0, da = R(rows, nh * Hv + 8)[:, :nh * Hv], R(rows, Hk), R(nh, rows, P, Hk), R(nh, rows, P, Hv), R(rows, nh * P)
+    D = lambda x: x.to(DEV)
+    for drop in (None, (0.3, 77, 4 << 32)):
+        # ---- reference: emulator (no dropout) or the unfused GPU kernels (dropout)
+        rb, dev_ref = (EM, (lambda x: x.clone())) if drop is None else (be, D)
+        r = dict(alpha=dev_ref(torch.zeros(rows, nh * P)), co=dev_ref(torch.zeros(rows, nh * Hv)), y=dev_ref(torch.zeros(rows, nh * Hv)),
+                 st=dev_ref(torch.zeros(nh, rows, 2)), dco=dev_ref(torch.zeros(rows, nh * Hv)), dq=dev_ref(dq0), dK=dev_ref(dK0), dV=dev_ref(dV0),
+                 dg=[dev_ref(torch.zeros(Hv)) for _ in range(nh)], db=[dev_ref(torch.zeros(Hv)) for _ in range(nh)])
+        a_ = [dev_ref(x) for x in (KW, VW, q, dy, da)]
+        g_, b_ = [dev_ref(x) for x in gam], [dev_ref(x) for x in bet]
+        rb.attn2_fwd(a_[0], a_[1], a_[2], r['alpha'], r['co'], 0.11, 1)
+        for k in range(nh):
+            sl = slice(k * Hv, (k + 1) * Hv)
+            dk = None if drop is None else (drop[0], drop[1], drop[2] + (k << 28))
+            rb.norm_fwd(r['co'][:, sl], g_[k], b_[k], y=r['y'][:, sl], stats=r['st'][k], pre_tanh=True, drop=dk)
+            rb.norm_bwd(a_[3][:, sl], r['co'][:, sl], g_[k], b_[k], r['st'][k], dx=r['dco'][:, sl], dgamma=r['dg'][k], dbeta=r['db'][k],
+                        pre_tanh=True, drop=dk)
+        rb.attn2_bwd(a_[0], a_[1], a_[2], r['alpha'], r['dco'], r['dq'], r['dK'], r['dV'], 0.11, dalpha_ext=a_[4])
+        # ---- fused kernels
+        f = dict(alpha=D(torch.zeros(rows, nh * P)), co=D(torch.zeros(rows, nh * Hv)), y=D(torch.zeros(rows, nh * Hv + 8, dtype=ydt))[:, :nh * Hv],
+                 st=D(torch.zeros(nh, rows, 2)), dq=D(dq0), dK=D(dK0), dV=D(dV0),
+                 dgr=D(torch.zeros(rows, nh * Hv)), dbr=D(torch.zeros(rows, nh * Hv)))
+        d_ = [D(x) for x in (KW, VW, q, dy, da)]
+        dg_, db_ = [D(x) for x in gam], [D(x) for x in bet]
+        be.attn2_fwd(d_[0], d_[1], d_[2], f['alpha'], f['co'], 0.11, 1,
+                     ln=dict(gamma=dg_, beta=db_, y=f['y'], stats=f['st'], drop=drop, drop_head_stride=1 << 28))
+        be.attn2_bwd(d_[0], d_[1], d_[2], f['alpha'], None, f['dq'], f['dK'], f['dV'], 0.11, dalpha_ext=d_[4],
+                     ln=dict(dy=d_[3], co=f['co'], gamma=dg_, stats=f['st'], dgamma_rows=f['dgr'], dbeta_rows=f['dbr'], drop=drop,
+                             drop_head_stride=1 << 28))
+        torch.cuda.synchronize()
+        cmp = lambda name, a, b, tol: _close(name, a, b, tol)
+        ytol = 2e-2 if ydt == torch.bfloat16 else 3e-5
+        cmp('alpha', r['alpha'], f['alpha'], 2e-5); cmp('co', r['co'], f['co'], 2e-5); cmp('y', r['y'], f['y'], ytol)
+        cmp('stats', r['st'], f['st'], 1e-4); cmp('dq', r['dq'], f['dq'], 1e-4); cmp('dKW', r['dK'], f['dK'], 1e-4)
+        cmp('dVW', r['dV'], f['dV'], 1e-4)
+        for k in range(nh):
+            sl = slice(k * Hv, (k + 1) * Hv)
+            cmp('dgamma', r['dg'][k], f['dgr'][:, sl].sum(0), 1e-4); cmp('dbeta', r['db'][k], f['dbr'][:, sl].sum(0), 1e-4)
+
+
+def _close(name, a, b, tol):
+    a, b = a.float().cpu(), b.float().cpu()
+    err, scale = float((a - b).abs().max()), max(1.0, float(a.abs().max()))
+    assert err <= tol * scale, (name, err, scale)
+
+
 @pytest.mark.parametrize('B_,T,P,H', [(6, 26, 5, 1024), (3, 26, 8, 64), (4, 26, 1, 512), (2, 6, 5, 64)])
 def test_latent_psl(be, B_, T, P, H):
     X, theta = R(B_, T, H), R(P, H, scale=0.05)

@@ -101,9 +101,42 @@ def time_graph(name, fn, reps=5):
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
-    print(json.dumps({'segment': name, 'ms': round(best, 3), 'dlsg_calls': n}), flush=True)
+    if name is not None:
+        print(json.dumps({'segment': name, 'ms': round(best, 3), 'dlsg_calls': n}), flush=True)
     del keep
     return best
+
+
+ABLATE = ('gemm', 'convert', 'norm_fwd', 'norm_bwd', 'lstm_cell_fwd', 'lstm_cell_bwd', 'lstm_cell_norm_fwd', 'norm_lstm_cell_bwd',
+          'attn2_fwd', 'attn2_bwd', 'colsum', 'embedding_gather', 'embedding_scatter_add', 'latent_psl_fwd', 'latent_psl_bwd',
+          'softmax_fwd', 'softmax_bwd', 'dropout', 'axpby', 'add_rowbcast', 'mean_nodes_fwd', 'mean_nodes_bwd', 'cast')
+ablate = '--ablate' in sys.argv
+
+
+class CountCalls:
+    def __init__(self, fn):
+        self.fn, self.n = fn, 0
+
+    def __call__(self, *a, **k):
+        self.n += 1
+
+
+def ablation(name, fn, base_ms):
+    """Marginal cost of each backend method inside this segment: replace it by a no-op (results are garbage, the launch
+    sequence has no data-dependent control flow) and re-time the segment."""
+    for m in ABLATE:
+        if not hasattr(be, m):
+            continue
+        cc = CountCalls(getattr(be, m))
+        setattr(be, m, cc)
+        try:
+            ms = time_graph(None, fn, reps=3)
+        finally:
+            delattr(be, m)
+        if cc.n:
+            # capture ran fn twice (warm-up + capture)
+            print(json.dumps({'segment': name, 'without': m, 'calls': cc.n // 2, 'ms': round(ms, 3), 'delta_us': round((base_ms - ms) * 1e3, 1),
+                              'us_per_call': round((base_ms - ms) * 1e3 / max(1, cc.n // 2), 2)}), flush=True)
 
 
 total = 0.0
@@ -122,7 +155,10 @@ with torch.no_grad():
                     for k in [k for k in core.pk if k.endswith('T')]:
                         del core.pk[k]
                 return blk.backward(sv, gouts)
-        total += time_graph(name, fn)
+        base = time_graph(name, fn)
+        total += base
+        if ablate:
+            ablation(name, fn, base)
 
 # loss (fused masked CE) forward + backward
 logits = out.detach().clone().requires_grad_(True)
