@@ -19,6 +19,7 @@ constexpr int BK = 64;           // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
 constexpr int TC_THREADS = 192;
 constexpr int EPI_PAD = 33;
+constexpr int MN_BLOCK_BYTES = 64 * BK * 2;   // one 64(MN) x 64(K) bf16 box of an MN-major operand
 
 struct TcParams {
   void* D; const float* bias;
@@ -30,6 +31,7 @@ struct TcParams {
   float alpha;
   int splitk, kb_total, kb_per_split;
   int ntm, ntn, tiles_total;
+  int a_mn, b_mn;      // operand is MN-major in global memory (unit stride along P resp. Q, not along K)
   unsigned long long* trace;   // debug: per-CTA phase timestamps (dlsg_debug_gemm_trace), nullptr in production
 };
 
@@ -78,6 +80,18 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   d |= (uint64_t)(1024 >> 4) << 32;                // SBO = 8 rows * 128 B           [32,46)
   d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+// MN-major, SWIZZLE_128B: the tile is stored as 64-element (128 B) MN blocks, each block = K rows of 128 B
+// (8-row swizzle atoms of 1024 B).  Canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units
+// (cute make_umma_desc<Major::MN>): LBO = byte distance between MN blocks, SBO = between 8-row K groups.
+__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t saddr, uint32_t mn_block_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(mn_block_bytes >> 4) << 16;      // LBO
+  d |= (uint64_t)(1024 >> 4) << 32;                // SBO = 8 K-rows * 128 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
   return d;
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -182,8 +196,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_expect_tx(full, Cfg::STAGE_BYTES);
           const uint32_t a_dst = smem_u32(tiles + s * Cfg::STAGE_BYTES);
           const int kc = (kb_begin + kb) * BK;
-          tma_load_3d(a_dst, &tmA, full, kc, tm * BM, zb);
-          tma_load_3d(a_dst + Cfg::A_BYTES, &tmB, full, kc, tn * BN, zb);
+          if (!prm.a_mn) {
+            tma_load_3d(a_dst, &tmA, full, kc, tm * BM, zb);
+          } else {                                     // two 64(P) x 64(K) boxes
+            tma_load_3d(a_dst, &tmA, full, tm * BM, kc, zb);
+            tma_load_3d(a_dst + MN_BLOCK_BYTES, &tmA, full, tm * BM + 64, kc, zb);
+          }
+          if (!prm.b_mn) {
+            tma_load_3d(a_dst + Cfg::A_BYTES, &tmB, full, kc, tn * BN, zb);
+          } else {
+#pragma unroll
+            for (int jb = 0; jb < BN / 64; ++jb)
+              tma_load_3d(a_dst + Cfg::A_BYTES + jb * MN_BLOCK_BYTES, &tmB, full, tn * BN + 64 * jb, kc, zb);
+          }
           if (tile == (int)blockIdx.x && kb == 0) tc_trace(prm, 2);     // first TMA issued
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
@@ -194,7 +219,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===== MMA issuer (one elected thread) =====
     if (lane == 0) {
       // instruction descriptor: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      //                         a_major @15, b_major @16 (1 = MN-major)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24) |
+                             (prm.a_mn ? (1u << 15) : 0u) | (prm.b_mn ? (1u << 16) : 0u);
+      // descriptor advance per UMMA_K=16 step: K-major +32 B inside the swizzle row, MN-major +16 K-rows (2048 B)
+      const uint32_t a_step = prm.a_mn ? (16 * 128) >> 4 : 2, b_step = prm.b_mn ? (16 * 128) >> 4 : 2;
       int s = 0; uint32_t ph = 0;
       int acc = 0; uint32_t acc_ph = 0;
       for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
@@ -210,13 +239,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (tile == (int)blockIdx.x && kb == 0) tc_trace(prm, 4);     // first operands landed
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_addr = smem_u32(tiles + s * Cfg::STAGE_BYTES);
-          const uint64_t adesc = make_sw128_desc(a_addr);
-          const uint64_t bdesc = make_sw128_desc(a_addr + Cfg::A_BYTES);
+          const uint64_t adesc = prm.a_mn ? make_sw128_mn_desc(a_addr, MN_BLOCK_BYTES) : make_sw128_desc(a_addr);
+          const uint64_t bdesc = prm.b_mn ? make_sw128_mn_desc(a_addr + Cfg::A_BYTES, MN_BLOCK_BYTES) : make_sw128_desc(a_addr + Cfg::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 bytes inside the 128B swizzle row: +2 in the (addr>>4) field
-            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16(tmem_d, adesc + (uint64_t)(a_step * k), bdesc + (uint64_t)(b_step * k), idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(smem_u32(&empty_bar[s]));                      // frees the smem slot when the MMAs retire
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
@@ -398,14 +425,16 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// K-major operand (mn = false): dims {K, rows, batch}, ld = row pitch, box {64 K, box_rows}.
+// MN-major operand (mn = true):  dims {rows, K, batch}, ld = pitch between consecutive k, box {64 rows, 64 K}.
 static int make_map(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t K, int64_t ld, int64_t batch,
-                    int64_t stride_batch, int box_rows) {
+                    int64_t stride_batch, int box_rows, bool mn) {
   EncodeTiledFn enc = get_encode();
   DLSG_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not found");
-  if (batch <= 1 || stride_batch == 0) stride_batch = rows * ld;
-  cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(batch < 1 ? 1 : batch)};
+  if (batch <= 1 || stride_batch == 0) stride_batch = (mn ? K : rows) * ld;
+  cuuint64_t gdim[3] = {(cuuint64_t)(mn ? rows : K), (cuuint64_t)(mn ? K : rows), (cuuint64_t)(batch < 1 ? 1 : batch)};
   cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)stride_batch * 2};
-  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(mn ? BK : box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   DLSG_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "gemm_tc: operand base not 16-byte aligned");
   DLSG_REQUIRE((gstr[0] % 16) == 0 && (gstr[1] % 16) == 0, "gemm_tc: ld/stride must be multiples of 8 elements (ld=%lld stride=%lld)",
@@ -499,7 +528,10 @@ int gemm_tc_dispatch(const dlsg_gemm_t* g, cudaStream_t st) {
 
 static int gemm_tc_direct(const dlsg_gemm_t* g, cudaStream_t st) {
   DLSG_REQUIRE(g->a_dtype == DLSG_BF16 && g->b_dtype == DLSG_BF16, "gemm_tc: operands must be bf16");
-  DLSG_REQUIRE(g->sak == 1 && g->sbk == 1, "gemm_tc: K must be the unit-stride axis of A and B");
+  // each operand is K-major (unit stride along K) or MN-major (unit stride along its row axis: a transposed view)
+  const bool a_mn_user = !(g->sak == 1 || g->K == 1), b_mn_user = !(g->sbk == 1 || g->K == 1);
+  DLSG_REQUIRE((!a_mn_user || g->sam == 1 || g->M == 1) && (!b_mn_user || g->sbn == 1 || g->N == 1),
+               "gemm_tc: each operand needs a unit stride along K or along its row axis");
   DLSG_REQUIRE(g->M > 0 && g->N > 0 && g->K > 0, "gemm_tc: empty problem");
   const int batch = g->batch < 1 ? 1 : g->batch;
   // Put the wide operand on the 128-row UMMA-M side; skinny activations (M<=64) ride the N side ("swap-AB").
@@ -507,7 +539,9 @@ static int gemm_tc_direct(const dlsg_gemm_t* g, cudaStream_t st) {
   const void* Ap = swap ? g->B : g->A;
   const void* Bq = swap ? g->A : g->B;
   const int P = swap ? g->N : g->M, Q = swap ? g->M : g->N;
-  const int64_t ldp = swap ? g->sbn : g->sam, ldq = swap ? g->sam : g->sbn;
+  const bool p_mn = swap ? b_mn_user : a_mn_user, q_mn = swap ? a_mn_user : b_mn_user;
+  const int64_t ldp = p_mn ? (swap ? g->sbk : g->sak) : (swap ? g->sbn : g->sam);
+  const int64_t ldq = q_mn ? (swap ? g->sak : g->sbk) : (swap ? g->sam : g->sbn);
   const int64_t strp = swap ? g->stride_b : g->stride_a, strq = swap ? g->stride_a : g->stride_b;
   TcParams prm;
   prm.trace = g_tc_trace;
@@ -533,14 +567,15 @@ static int gemm_tc_direct(const dlsg_gemm_t* g, cudaStream_t st) {
   const int ptiles = (P + BM - 1) / BM;
   auto tiles_for = [&](int bn) { return (int64_t)ptiles * ((Q + bn - 1) / bn) * batch * splitk; };
   int bn;
-  if (Q <= 32) bn = 32;
+  if (Q <= 32 && !q_mn) bn = 32;             // (an MN-major Q operand is loaded in 64-element blocks)
   else if (Q <= 64) bn = 64;
   else if (Q > 128 && tiles_for(256) >= 2 * kNumSM) bn = 256;
   else if (tiles_for(128) >= kNumSM || Q <= 128) bn = 128;
   else bn = 64;
   CUtensorMap ta, tb;
-  if (make_map(&ta, Ap, P, g->K, ldp, batch, strp, BM)) return -1;
-  if (make_map(&tb, Bq, Q, g->K, ldq, batch, strq, bn)) return -1;
+  if (make_map(&ta, Ap, P, g->K, ldp, batch, strp, BM, p_mn)) return -1;
+  if (make_map(&tb, Bq, Q, g->K, ldq, batch, strq, bn, q_mn)) return -1;
+  prm.a_mn = p_mn ? 1 : 0; prm.b_mn = q_mn ? 1 : 0;
   prm.ntm = ptiles;
   prm.ntn = (Q + bn - 1) / bn;
   const int64_t tiles_total = (int64_t)prm.ntm * prm.ntn * batch * splitk;

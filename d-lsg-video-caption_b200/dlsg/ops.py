@@ -116,7 +116,10 @@ class CudaBackend:
         g.sam, g.sak, g.sbn, g.sbk = a2.stride(0), a2.stride(1), b2.stride(0), b2.stride(1)
         g.a_dtype, g.b_dtype, g.d_dtype = _dt(a2), _dt(b2), _dt(o2)
         if impl is None:
-            impl = L.GEMM_TC if (g.a_dtype == BF16 and g.b_dtype == BF16 and g.sak == 1 and g.sbk == 1) else L.GEMM_SIMT
+            # tcgen05 path: bf16 operands, each K-major (unit K stride) or MN-major (a transposed view: unit row stride)
+            tc_a = g.sak == 1 or K == 1 or g.sam == 1 or M == 1
+            tc_b = g.sbk == 1 or K == 1 or g.sbn == 1 or N == 1
+            impl = L.GEMM_TC if (g.a_dtype == BF16 and g.b_dtype == BF16 and tc_a and tc_b) else L.GEMM_SIMT
         g.impl, g.flags, g.splitk, g.alpha = impl, flags, splitk, alpha
         if impl == L.GEMM_TC and splitk <= 1:
             ws = self._workspace(a.device)

@@ -33,7 +33,9 @@ void dlsg_debug_gemm_trace(void* dev_buf);
  * sublayer.py:29-31,66-68,80 (attention projections), layer.py:600 (word_restore),
  * model.py:148 (conv1d k=1), layer.py:187,191 / sublayer.py:69,76,191,196 (bmm).
  *  impl DLSG_GEMM_TC  : TMA -> smem -> tcgen05.mma (TMEM accum), bf16 operands, fp32 accumulate.
- *                        A,B row-major with unit K stride, lda/ldb multiples of 8 elements,
+ *                        Each operand is K-major (sak == 1 / sbk == 1) or MN-major (a transposed view: sam == 1 /
+ *                        sbn == 1, read in place through 64x64 TMA boxes and the UMMA MN-major descriptor - no
+ *                        transposed copy is ever needed); the non-unit pitch is a multiple of 8 elements,
  *                        16-byte aligned bases.  splitk>1 writes partial sums to D + s*stride_split.
  *  impl DLSG_GEMM_SIMT: fp32 FFMA tiles, arbitrary element strides (sam,sak,sbn,sbk) and dtypes.
  */

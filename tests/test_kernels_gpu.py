@@ -102,6 +102,27 @@ def test_gemm_tc_batched_and_strided_views(be):
     both('gemm', be, [x.transpose(0, 1), w, torch.zeros(33, 2, 48).transpose(0, 1)], {}, [2], tol=2e-3)
 
 
+@pytest.mark.parametrize('M,N,K', [(304, 200, 256), (128, 128, 64), (136, 264, 72), (64, 4096, 2880), (24, 1024, 936), (1664, 1056, 1536),
+                                   (8, 24, 8), (2048, 2048, 1664), (64, 40, 520)])
+@pytest.mark.parametrize('ta,tb', [(True, False), (False, True), (True, True)])
+def test_gemm_tc_mn_major_operands(be, M, N, K, ta, tb):
+    """Transposed (MN-major) operand views are read in place: a = A^T view of a (K,M) buffer, b likewise."""
+    a = bf(R(K, M)).t() if ta else bf(R(M, K))
+    b = bf(R(K, N)).t() if tb else bf(R(N, K))
+    both('gemm', be, [a, b, torch.zeros(M, N)], {}, [2], tol=2e-3)
+    both('gemm', be, [a, b, torch.zeros(N, M).t()], dict(bias=R(N), alpha=0.5), [2], tol=2e-3)
+
+
+def test_gemm_tc_mn_major_batched_and_padded(be):
+    B_, M, N, K = 3, 150, 72, 136
+    a = bf(R(B_, K, M + 2))[:, :, :M].transpose(1, 2)       # MN-major with a padded pitch
+    b = bf(R(B_, K, N)).transpose(1, 2)
+    both('gemm', be, [a, b, torch.zeros(B_, M, N)], {}, [2], tol=2e-3)
+    # wgrad shape: both operands MN-major, long K (split-K path for the small output)
+    dy, x = bf(R(1664, 256)), bf(R(1664, 320))
+    both('gemm', be, [dy.t(), x.t(), torch.zeros(256, 320)], {}, [2], tol=4e-3)
+
+
 @pytest.mark.parametrize('splitk', [2, 3, 5])
 def test_gemm_tc_splitk(be, splitk):
     M, N, K = 64, 1024, 64 * 15
@@ -111,8 +132,8 @@ def test_gemm_tc_splitk(be, splitk):
 
 @pytest.mark.parametrize('M,N,K', [(64, 4096, 2880), (64, 2880, 4096), (17, 1000, 1544), (256, 384, 1664), (3, 130, 520)])
 def test_gemm_tc_auto_splitk_fixup(be, M, N, K):
-    """Skinny problems split K inside ONE launch (last CTA of a tile sums the parked partials in split order):
-    every epilogue form, repeated launches (the tile counters must return to zero) and run-to-run determinism."""
+    """Skinny problems split K automatically (partials in the workspace + a reduce/epilogue kernel, fixed summation
+    order): every epilogue form, repeated launches and run-to-run determinism."""
     a, b = bf(R(M, K, scale=0.2)), bf(R(N, K, scale=0.2))
     bias_n, bias_m = R(N), R(M)
     for _ in range(2):
