@@ -24,12 +24,7 @@ START = 1
 splitk_for = la.splitk_for
 
 
-def flat2(x):
-    """Collapse the leading dims of a (possibly column-padded) operand buffer view into rows."""
-    rows = 1
-    for s in x.shape[:-1]:
-        rows *= s
-    return x.as_strided((rows, x.shape[-1]), (x.stride(-2), 1))
+flat2 = la.flat2
 
 
 class DecoderCore:
@@ -98,22 +93,10 @@ class DecoderCore:
         self.heads = heads
 
     def packT(self):
-        """Transposed packs for the data-gradient GEMMs (training backward only)."""
-        be = ops.backend()
+        """Transposed packs for the data-gradient GEMMs (training backward only): views - the GEMM reads them in place."""
         pk = self.pk
-        if 'WqT' in pk:
-            return pk
-        if la.precision() == 'fp32':
+        if 'WqT' not in pk:
             pk.update(WqT=pk['Wq'].t(), WlT=pk['Wl'].t(), WgT=pk['Wg'].t(), WqpT=pk['Wqp'].t(), WoT=pk['Wo'].transpose(1, 2))
-            return pk
-        for n in ('Wq', 'Wl', 'Wg', 'Wqp'):
-            src = pk[n]
-            dst = op_empty((src.shape[1],), src.shape[0], src)
-            be.convert(src, dstT=dst)
-            pk[n + 'T'] = dst
-        WoT = op_empty(tuple(pk['Wo'].shape[:2]), pk['Wo'].shape[2], pk['Wo'])
-        be.convert(pk['Wo'], dstT=WoT)
-        pk['WoT'] = WoT
         return pk
 
     # ------------------------------------------------------------------ sequence-invariant precompute
@@ -322,12 +305,8 @@ class DecoderTrainBlock:
         dDall = zeros((B, T, Hd), ref)
         if dlogits is not None:
             dl2 = _c(dlogits).view(B * T, V)
-            if la.precision() == 'bf16':
-                dlo = op_empty((B * T,), V, ref)
-                dloT = op_empty((V,), B * T, ref)
-                be.convert(dl2, dst=dlo, dstT=dloT)
-            else:
-                dlo, dloT = dl2, dl2.t()
+            dlo = op(dl2)
+            dloT = dlo.t()
             wout = t[pf + 'word_restore.weight']
             be.gemm(dlo, WC.get(wout, transpose=True), dDall.view(B * T, Hd))
             grads[pf + 'word_restore.weight'] = la.mm(dloT, D2.t())
@@ -342,8 +321,6 @@ class DecoderTrainBlock:
         dXl = zeros((T + 1, B, Kl), ref)
         dgq_all = op_empty((TB,), 4 * Hq, ref)
         dgl_all = op_empty((TB,), 4 * Hd, ref)
-        dgqT = op_empty((4 * Hq,), TB, ref)
-        dglT = op_empty((4 * Hd,), TB, ref)
         dgq32 = empty((B, 4 * Hq), ref)
         dgq_sum = zeros((B, 4 * Hq), ref)
         hoist = core.hoist
@@ -420,10 +397,8 @@ class DecoderTrainBlock:
                 be.colsum(lc_g.view(TB, nh * H)[:, k * H:(k + 1) * H], lnc[k][2])
                 be.colsum(lc_b.view(TB, nh * H)[:, k * H:(k + 1) * H], lnc[k][3])
         Xq2, Xl2 = flat2(b.Xq[:T]), flat2(b.Xl[:T])
-        # transposed gate-gradient operands of the time-batched weight-gradient GEMMs: ONE coalesced transpose each
-        # after the loop (per-step transposed stores would be 2-byte scattered writes)
-        be.convert(dgq_all, dstT=dgqT)
-        be.convert(dgl_all, dstT=dglT)
+        # time-batched weight-gradient GEMMs read the gate gradients transposed IN PLACE (MN-major operands)
+        dgqT, dglT = dgq_all.t(), dgl_all.t()
         dWq = la.mm(dgqT, Xq2.t())                                # (4Hq, Kq)
         dWl = la.mm(dglT, Xl2.t())                                # (4Hd, Kl)
         dgs_op = op(dgq_sum)

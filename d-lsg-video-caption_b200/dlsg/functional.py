@@ -15,7 +15,7 @@ import torch
 
 from . import linalg as la
 from . import ops
-from .linalg import empty, zeros, op, op_empty, op_zeros, mm32
+from .linalg import empty, zeros, op, op_empty, op_zeros, mm32, flat2
 
 _seed_counter = itertools.count(1)
 
@@ -151,12 +151,8 @@ class TunBlock:
         outs = []
         if use_regions:
             R2 = _c(regions).view(M, Dr)
-            if la.precision() == 'bf16':
-                Rb = op_empty((M,), Dr, R2)
-                RbT = op_empty((Dr,), M, R2) if need_grad else None
-                be.convert(R2, dst=Rb, dstT=RbT)
-            else:
-                Rb, RbT = R2, R2.t()
+            Rb = op(R2)                 # one cast; the weight-gradient GEMM reads it transposed in place
+            RbT = Rb.t()
             H = t[self.encs[0]['prefix'] + 'obj_embed.weight'].shape[0]
             ws = [t[e['prefix'] + 'obj_embed.weight'] for e in self.encs]
             bs = [t[e['prefix'] + 'obj_embed.bias'] for e in self.encs]
@@ -387,17 +383,17 @@ class EncoderVisualBlock:
         Sg = la.splitk_for(B, H4, H, sms=74)
         gates = zeros((Sg, 2, T, B, H4), frames)     # [0] ends up holding the activated gates (saved for BPTT)
         cs = zeros((2, T + 1, B, H), frames)
-        hprev = op_zeros((2, T, B), H, frames)       # h fed INTO step t (operand dtype)
+        hprev = op_zeros((2, B, T), H, frames)       # h fed INTO step t (operand dtype), clip-major like Gin / dGin
         whh = [WC.get(t[pf + 'lstm.weight_hh_l0']), WC.get(t[pf + 'lstm.weight_hh_l0_reverse'])]
 
         def run_dir(d):
             order = list(range(T)) if d == 0 else list(range(T - 1, -1, -1))
             for k, tt in enumerate(order):
                 if k > 0:
-                    be.gemm(hprev[d, tt], whh[d], gates[:, d, tt] if Sg > 1 else gates[0, d, tt], splitk=Sg)
+                    be.gemm(hprev[d, :, tt], whh[d], gates[:, d, tt] if Sg > 1 else gates[0, d, tt], splitk=Sg)
                 nxt = order[k + 1] if k + 1 < T else None
                 be.lstm_cell_fwd(gates[:, d, tt], cs[d, k], cs[d, k + 1], row_bias=Gin[:, tt, d * H4:(d + 1) * H4],
-                                 h2=lstm_out[:, tt, d * H:(d + 1) * H], h3=(hprev[d, nxt] if nxt is not None else None))
+                                 h2=lstm_out[:, tt, d * H:(d + 1) * H], h3=(hprev[d, :, nxt] if nxt is not None else None))
         two_streams(frames, lambda: run_dir(0), lambda: run_dir(1))     # the two directions are independent chains
         Y = empty((B * T, 2 * H), frames)
         stY = empty((B * T, 2), frames)
@@ -423,7 +419,7 @@ class EncoderVisualBlock:
             return W
         Wkqv = WC.packed(('evKQV', id(wk)), None, la.pver(wk, wq, wv), build)
         Ypo = op(Ype)
-        KQV = empty((B, T, 3 * D2), frames)
+        KQV = empty((B, T, 3 * D2), frames, la.opdtype())          # K | Q | V projections as GEMM operands
         be.gemm(Ypo, Wkqv, KQV.view(B * T, 3 * D2))
         Kt, Qt, Vt = KQV[:, :, :D2], KQV[:, :, D2:2 * D2], KQV[:, :, 2 * D2:]
         lg = empty((B, T, T), frames)
@@ -431,9 +427,9 @@ class EncoderVisualBlock:
         Wt = empty((B, T, T), frames)
         sc = 1.0 / math.sqrt(D2)
         be.softmax_fwd(lg, Wt, dim=2, scale=sc)
-        att = empty((B, T, D2), frames)
-        be.gemm(Wt, Vt.transpose(1, 2), att)
-        att_op = op(att.view(B * T, D2))
+        att_op = op_empty((B, T), D2, frames)
+        be.gemm(op(Wt), Vt.transpose(1, 2), att_op)                  # V read transposed in place
+        att_op = flat2(att_op)
         Z = la.mm(att_op, WC.get(t[pf + 'self_attention.output_layer.0.weight']))
         dz = site(self.p if training else 0.0, seed, 3)
         if dz is not None:
@@ -476,21 +472,23 @@ class EncoderVisualBlock:
                 be.dropout(dZ, dZ, sv['dz'])
             wo = t[pf + 'self_attention.output_layer.0.weight']
             dZop = op(dZ)
-            datt = empty((B, T, D2), ref)
+            datt = empty((B, T, D2), ref, la.opdtype())
             be.gemm(dZop, WC.get(wo, transpose=True), datt.view(B * T, D2))
             grads[pf + 'self_attention.output_layer.0.weight'] = la.mm(dZop.t(), sv['att_op'].t())
             KQV = sv['KQV']
             Kt, Qt, Vt = KQV[:, :, :D2], KQV[:, :, D2:2 * D2], KQV[:, :, 2 * D2:]
-            dKQV = empty((B, T, 3 * D2), ref)
+            dKQV = empty((B, T, 3 * D2), ref, la.opdtype())
             dK, dQ, dV = dKQV[:, :, :D2], dKQV[:, :, D2:2 * D2], dKQV[:, :, 2 * D2:]
             dW = empty((B, T, T), ref)
-            be.gemm(datt, Vt, dW)                                   # dW[i,j] = datt_i . V_j
-            be.gemm(sv['Wt'].transpose(1, 2), datt.transpose(1, 2), dV)   # dV_j = sum_i W[i,j] datt_i
+            datt_op, Wt_op = datt, op(sv['Wt'])
+            be.gemm(datt_op, Vt, dW)                                          # dW[i,j] = datt_i . V_j
+            be.gemm(Wt_op.transpose(1, 2), datt_op.transpose(1, 2), dV)       # dV_j = sum_i W[i,j] datt_i
             dlg = empty((B, T, T), ref)
             be.softmax_bwd(sv['lg'], dW, dlg, dim=2, scale=sv['sc'])
-            be.gemm(dlg, Qt.transpose(1, 2), dK)                    # dK_i = sum_j dlg[i,j] Q_j
-            be.gemm(dlg.transpose(1, 2), Kt.transpose(1, 2), dQ)    # dQ_j = sum_i dlg[i,j] K_i
-            dKQVop = op(dKQV.view(B * T, 3 * D2))
+            dlg_op = op(dlg)
+            be.gemm(dlg_op, Qt.transpose(1, 2), dK)                           # dK_i = sum_j dlg[i,j] Q_j
+            be.gemm(dlg_op.transpose(1, 2), Kt.transpose(1, 2), dQ)           # dQ_j = sum_i dlg[i,j] K_i
+            dKQVop = dKQV.view(B * T, 3 * D2)
             wk, wq, wv = t[pf + 'self_attention.K.weight'], t[pf + 'self_attention.Q.weight'], t[pf + 'self_attention.V.weight']
             dYpe = empty((B * T, D2), ref)
             for j, w_ in enumerate((wk, wq, wv)):
@@ -511,7 +509,6 @@ class EncoderVisualBlock:
         whhT = [WC.get(t[pf + 'lstm.weight_hh_l0'], transpose=True), WC.get(t[pf + 'lstm.weight_hh_l0_reverse'], transpose=True)]
         names_hh = ['lstm.weight_hh_l0', 'lstm.weight_hh_l0_reverse']
         # everything that crosses the stream fork/join is allocated here, on the main stream
-        dgTs = [op_empty((H4,), T * B, ref) for _ in range(2)]
         Sd = la.splitk_for(B, H, H4, sms=74)             # recurrent data-gradient GEMM: partials summed by the cell kernel
         bufs = [(zeros((Sd, B, H), ref), zeros((B, H), ref), empty((B, H), ref)) for _ in range(2)]
 
@@ -527,14 +524,13 @@ class EncoderVisualBlock:
                 if k > 0:
                     be.gemm(op(dg2), whhT[d], dhrec if Sd > 1 else dhrec[0], splitk=Sd)
         two_streams(ref, lambda: run_dir_bwd(0), lambda: run_dir_bwd(1))
-        for d in range(2):
-            # transposed gate gradients (H4, T*B) for the time-batched weight-gradient GEMM: one batched transpose
-            src = dGin.transpose(0, 1)[:, :, d * H4:(d + 1) * H4]                  # (T, B, H4)
-            be.convert(src, dstT=dgTs[d].as_strided((T, H4, B), (B, dgTs[d].stride(0), 1)))
-            hp = hprev[d]
-            grads[pf + names_hh[d]] = la.mm(dgTs[d], hp.as_strided((T * B, H), (hp.stride(1), 1)).t())
-        Wih, _ = self._packs(t, pf)
         dGin2 = dGin.view(B * T, 2 * H4)
+        for d in range(2):
+            # time-batched recurrent weight gradient: dW_hh = dgates^T . h_prev, both operands read transposed in place
+            hp = hprev[d]
+            hp2 = hp.as_strided((B * T, H), (hp.stride(1), 1))
+            grads[pf + names_hh[d]] = la.mm(dGin2[:, d * H4:(d + 1) * H4].t(), hp2.t())
+        Wih, _ = self._packs(t, pf)
         dbg = zeros((2 * H4,), ref)
         be.colsum(dGin2, dbg)
         grads[pf + 'lstm.bias_ih_l0'] = dbg[:H4]

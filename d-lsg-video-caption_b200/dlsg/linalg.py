@@ -1,9 +1,9 @@
 """Precision policy + GEMM-operand plumbing shared by every block.
 
 precision 'bf16' (default): dense projections run on the tcgen05 kernel with bf16 operands and fp32
-accumulation; operands must be K-major (unit stride on the reduction axis), 16-byte aligned, row
-pitch a multiple of 8 elements.  `op()` materialises such a copy (dlsg_convert2d, cast and/or
-transpose) only when a tensor is not already usable.
+accumulation; operands are K-major (unit stride on the reduction axis) or MN-major (transposed views), 16-byte
+aligned, pitch a multiple of 8 elements.  `op()` materialises a cast copy (dlsg_convert2d) only when a tensor is
+not already usable; transposed copies are never needed.
 precision 'fp32': every product runs on the strided fp32 FFMA kernel on the original tensors
 (strict-parity mode: logits within 1e-4 of the fp32 reference, bit-exact token ids).
 Tiny fp32 x fp32 products (26x26 attention, P<=8 pooling) use the FFMA kernel in both modes.
@@ -54,19 +54,35 @@ def op_zeros(rows_shape, K, like):
     return buf[..., :K]
 
 
+def flat2(x):
+    """Collapse the leading dims of a (possibly column-padded) operand buffer view into rows."""
+    rows = 1
+    for s_ in x.shape[:-1]:
+        rows *= s_
+    return x.as_strided((rows, x.shape[-1]), (x.stride(-2), 1), x.storage_offset())
+
+
 def _tc_ok(t):
-    if t.dtype != torch.bfloat16 or t.stride(-1) != 1:
+    """bf16, 16-byte aligned, and either K-major (unit stride on the last axis) or MN-major (a transposed view: unit
+    stride on the second-last axis) with every other pitch a multiple of 8 elements - the tcgen05 GEMM reads both
+    in place (MN-major through 64x64 TMA boxes and the UMMA MN-major descriptor)."""
+    if t.dtype != torch.bfloat16 or t.data_ptr() % 16 != 0:
         return False
-    if t.data_ptr() % 16 != 0:
+    if t.stride(-1) == 1 or t.shape[-1] == 1:
+        unit = t.dim() - 1
+    elif t.dim() >= 2 and (t.stride(-2) == 1 or t.shape[-2] == 1):
+        unit = t.dim() - 2
+    else:
         return False
-    for d in range(t.dim() - 1):
-        if t.shape[d] > 1 and t.stride(d) % 8 != 0:
+    for d in range(t.dim()):
+        if d != unit and t.shape[d] > 1 and t.stride(d) % 8 != 0:
             return False
     return True
 
 
 def op(t):
-    """Return `t` (2-D or batched 3-D, reduction axis last) as a GEMM operand for the current precision."""
+    """Return `t` (2-D or batched 3-D, reduction axis last) as a GEMM operand for the current precision.  A transposed
+    view stays a transposed view (of a cast copy when it is not bf16 yet): no transposed copy is ever made."""
     if _PRECISION == 'fp32':
         if t.dtype == torch.float32:
             return t
@@ -75,7 +91,12 @@ def op(t):
         return out
     if _tc_ok(t):
         return t
-    if t.stride(-1) != 1 and t.shape[-1] != 1 and t.stride(-2) != 1:
+    if t.stride(-1) != 1 and t.shape[-1] != 1:
+        if t.dim() >= 2 and t.stride(-2) == 1:
+            tt = t.transpose(-1, -2)                       # the row-major tensor underneath: cast it, hand back the view
+            out = op_empty(tt.shape[:-1], tt.shape[-1], t)
+            ops.backend().convert(tt, dst=out)
+            return out.transpose(-1, -2)
         t = t.contiguous()          # e.g. one tap of a conv1d weight (C_out, C_in, k)[:, :, j]
     out = op_empty(t.shape[:-1], t.shape[-1], t)
     _convert_into(t, out)
@@ -109,7 +130,7 @@ def mm32(a, b, out=None, **epi):
 
 
 class WeightCache:
-    """bf16 K-major copies of parameters (and their transposes / packed forms).
+    """bf16 copies of parameters (one per weight; the transposed operand is a view of it) and packed forms.
 
     Validity is NOT keyed on tensor._version alone: fused optimizers (torch.optim.Adam(fused=True)) update parameters
     without bumping it.  Entries carry the *scope* they were built in:
@@ -140,17 +161,16 @@ class WeightCache:
     def get(self, w, transpose=False, key=None):
         if _PRECISION == 'fp32':
             return w.detach().t() if transpose else w.detach()
-        k = (id(w) if key is None else key, transpose)
+        if transpose:
+            return self.get(w, key=key).t()         # MN-major view of the same bf16 copy (read in place by the GEMM)
+        k = (id(w) if key is None else key, False)
         ver = (w._version, w.data_ptr(), tuple(w.shape), self.scope)
         hit = self._c.get(k)
         if hit is not None and hit[0] == ver and not self.force:
             return hit[1]
         src = w.detach()
-        out = op_empty((src.shape[1],), src.shape[0], src) if transpose else op_empty((src.shape[0],), src.shape[1], src)
-        if transpose:
-            ops.backend().convert(src, dstT=out)
-        else:
-            ops.backend().convert(src, dst=out)
+        out = op_empty((src.shape[0],), src.shape[1], src)
+        ops.backend().convert(src, dst=out)
         self._c[k] = (ver, out)
         return out
 
