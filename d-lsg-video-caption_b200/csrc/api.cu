@@ -27,7 +27,7 @@ int check_launch(const char* what) {
 
 bool pdl_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("DLSG_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("DLSG_PDL"); v = (e && e[0] == '0') ? 0 : 1; }   // on by default; DLSG_PDL=0 disables
   return v == 1;
 }
 

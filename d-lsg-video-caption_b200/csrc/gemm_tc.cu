@@ -566,12 +566,21 @@ static int gemm_tc_direct(const dlsg_gemm_t* g, cudaStream_t st) {
 
   const int ptiles = (P + BM - 1) / BM;
   auto tiles_for = [&](int bn) { return (int64_t)ptiles * ((Q + bn - 1) / bn) * batch * splitk; };
+  // Tile width: fewest (waves of the persistent grid) x (time of one k-block of a 128 x bn tile).  A k-block costs the
+  // larger of its operand fill ((128 + bn) rows x 128 B at ~106 B/ns per SM, measured) and its MMAs (11.1 TFLOP/s per SM).
+  auto cost = [&](int bn) {
+    const int64_t waves = (tiles_for(bn) + kNumSM - 1) / kNumSM;
+    const double fill = (128.0 + bn) * 128.0 / 106.0, mma = 128.0 * bn * 128.0 / 11100.0;
+    return (double)waves * (fill > mma ? fill : mma);
+  };
   int bn;
   if (Q <= 32 && !q_mn) bn = 32;             // (an MN-major Q operand is loaded in 64-element blocks)
   else if (Q <= 64) bn = 64;
-  else if (Q > 128 && tiles_for(256) >= 2 * kNumSM) bn = 256;
-  else if (tiles_for(128) >= kNumSM || Q <= 128) bn = 128;
-  else bn = 64;
+  else {
+    bn = 128;
+    if (Q > 128 && cost(256) <= cost(bn)) bn = 256;
+    if (cost(64) < cost(bn)) bn = 64;        // small problems: more, narrower tiles cover more SMs
+  }
   CUtensorMap ta, tb;
   if (make_map(&ta, Ap, P, g->K, ldp, batch, strp, BM, p_mn)) return -1;
   if (make_map(&tb, Bq, Q, g->K, ldq, batch, strq, bn, q_mn)) return -1;

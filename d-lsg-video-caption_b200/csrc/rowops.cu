@@ -211,9 +211,15 @@ static int norm_fwd_vec_launch(const dlsg_norm_fwd_t* p, cudaStream_t st) {
   return check_launch("norm_fwd_vec_kernel");
 }
 
+bool norm_fwd_bf16_ok(const dlsg_norm_fwd_t* p);
+int norm_fwd_bf16_launch(const dlsg_norm_fwd_t* p, cudaStream_t st);
+bool norm_bwd_bf16_ok(const dlsg_norm_bwd_t* p);
+int norm_bwd_bf16_launch(const dlsg_norm_bwd_t* p, cudaStream_t st);
+
 int norm_fwd_launch(const dlsg_norm_fwd_t* p, cudaStream_t st) {
   DLSG_REQUIRE(p->rows >= 0 && p->D > 0 && p->D <= 8192, "norm_fwd: bad shape rows=%lld D=%d", (long long)p->rows, p->D);
   if (p->rows == 0) return 0;
+  if (norm_fwd_bf16_ok(p)) return norm_fwd_bf16_launch(p, st);      // big bf16 activations: streaming kernel (norm_bf16.cu)
   if (p->D <= 2048 && vec_ok(p->x, p->x_dtype, p->ldx, p->D) && vec_ok(p->res, p->res_dtype, p->ldres, p->D) &&
       vec_ok(p->y, p->y_dtype, p->ldy, p->D) && vec_ok(p->y2, p->y2_dtype, p->ldy2, p->D) &&
       vec_ok(p->gamma, DLSG_F32, 4, p->D) && vec_ok(p->beta, DLSG_F32, 4, p->D)) {
@@ -434,6 +440,7 @@ static int norm_bwd_vec_launch(const dlsg_norm_bwd_t* p, cudaStream_t st) {
 int norm_bwd_launch(const dlsg_norm_bwd_t* p, cudaStream_t st) {
   DLSG_REQUIRE(p->rows >= 0 && p->D > 0 && p->D <= 4096, "norm_bwd: bad shape rows=%lld D=%d", (long long)p->rows, p->D);
   if (p->rows == 0) return 0;
+  if (norm_bwd_bf16_ok(p)) return norm_bwd_bf16_launch(p, st);
   const bool vec = p->D <= 2048 && vec_ok(p->x, p->x_dtype, p->ldx, p->D) && vec_ok(p->res, p->res_dtype, p->ldres, p->D) &&
                    vec_ok(p->dy, p->dy_dtype, p->lddy, p->D) && vec_ok(p->dx, p->dx_dtype, p->lddx, p->D) &&
                    vec_ok(p->gamma, DLSG_F32, 4, p->D) && vec_ok(p->beta, DLSG_F32, 4, p->D);

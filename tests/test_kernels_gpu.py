@@ -201,6 +201,24 @@ def test_norm_fwd_bwd(be, D, pre, post):
                                                                dbeta=torch.zeros(D), in_is_tanh=True), ['dx'], tol=2e-2)
 
 
+@pytest.mark.parametrize('rows,D,Dpad', [(2500, 1024, 2048), (2049, 512, 512), (4100, 136, 144)])
+def test_norm_bf16_streaming(be, rows, D, Dpad):
+    """The big-activation form (bf16 in / out, rows >= 2048): streaming kernels of norm_bf16.cu, column slices of a wider
+    buffer (the two encoders' halves of the region projection), backward through the GEMM's fused tanh."""
+    t = bf(torch.tanh(R(rows, Dpad)))[:, Dpad - D:]
+    gamma, beta = 1 + 0.1 * R(D), 0.1 * R(D)
+    stats = torch.zeros(rows, 2)
+    both('norm_fwd', be, [t, gamma, beta], dict(y=torch.zeros(rows, D, dtype=torch.bfloat16), stats=stats), ['y', 'stats'], tol=1e-2)
+    EM.norm_fwd(t, gamma, beta, stats=stats)
+    dy = bf(R(rows, D))
+    for tanh_in in (True, False):
+        both('norm_bwd', be, [dy, t, gamma, beta, stats],
+             dict(dx=torch.zeros(rows, Dpad, dtype=torch.bfloat16)[:, :D], dgamma=R(D), dbeta=R(D), in_is_tanh=tanh_in), ['dx'], tol=2e-2)
+        both('norm_bwd', be, [dy, t, gamma, beta, stats],
+             dict(dx=torch.zeros(rows, D, dtype=torch.bfloat16), dgamma=torch.zeros(D), dbeta=torch.zeros(D), in_is_tanh=tanh_in),
+             ['dgamma', 'dbeta'], tol=2e-3)
+
+
 def test_norm_strided_slices(be):
     D, rows = 96, 12
     big = R(rows, 4 * D)

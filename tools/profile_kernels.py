@@ -32,10 +32,9 @@ if which in ('all', 'gemm'):
     o = torch.empty(M, N, device=dev, dtype=bf)
     for _ in range(2):
         be.gemm(a, w, o, bias=bias, tanh=True)              # region projection (both encoders), bf16 out, bias+tanh
-    dO = R(N, M, dtype=bf)
-    aT = R(K, M, dtype=bf)
+    dO = R(M, N, dtype=bf)
     dW = torch.empty(N, K, device=dev)
-    be.gemm(dO, aT, dW)                                      # its weight gradient (K = 59904)
+    be.gemm(dO.t(), a.t(), dW)                               # its weight gradient (K = 59904), both operands read transposed in place
     x = R(B, 2880, dtype=bf)
     wq = R(4096, 2880, dtype=bf)
     g = torch.empty(B, 4096, device=dev)
@@ -53,6 +52,6 @@ if which in ('all', 'rows'):
     for _ in range(2):
         be.norm_bwd(dy, x, g_, b_, st, dx=dx, dgamma=dg, dbeta=db, in_is_tanh=True)
     r = R(M, 2048)
-    d1, d2 = torch.empty(M, 2048, device=dev, dtype=bf), torch.empty(2048, M, device=dev, dtype=bf)
-    be.convert(r, dst=d1, dstT=d2)                           # regions fp32 -> bf16 (+ transposed copy)
+    d1 = torch.empty(M, 2048, device=dev, dtype=bf)
+    be.convert(r, dst=d1)                                    # regions fp32 -> bf16
 torch.cuda.synchronize()
