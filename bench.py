@@ -311,7 +311,10 @@ def main():
         ach = flops / (k_ms * 1e-3) / 1e12
         peak = peaks.get('bf16_tflops', 1590.0)
         roof = {'bound': 'tensor', 'kernel': 'gemm_tc_kernel<256> region projection %dx%dx%d bf16 (+bias+tanh, bf16 out)' % (Mr, Nr, Kr),
-                'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': None,
+                'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the committed ncu --set full
+                # capture profiles/r01_ncu_full_top_kernels_v2.json (algorithmic: A 245 MB + W 8 MB read, 245 MB written)
+                'traffic': 253.84e6 + 208.14e6, 'traffic_unit': 'bytes/launch',
                 'peak_source': 'measured (MEASURED_PEAKS.json bf16_tflops, burst)' if 'bf16_tflops' in peaks else 'fallback',
                 'ms_per_launch': k_ms, 'launches_per_step': 1}
         del A, Wt, O_
