@@ -262,6 +262,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool pair_ok = bf16_out && !prm.store_t && !prm.accum && (prm.ldd % 2 == 0) && ((prm.stride_d | prm.stride_split) % 2 == 0) &&
                          ((reinterpret_cast<uintptr_t>(prm.D) & 3) == 0);
     const bool plain_f32 = !bf16_out && !prm.accum && !prm.do_tanh;     // fp32 store, nothing else: the per-step GEMMs
+    const bool accum_f32 = !bf16_out && prm.accum && !prm.do_tanh;      // D += ...: all 32 loads in flight before the first store
     int acc = 0; uint32_t acc_ph = 0;
     for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
       const int tn = tile % ntn, tm = (tile / ntn) % ntm, z = tile / (ntn * ntm);
@@ -317,6 +318,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { if (j < qn) *d = f[j]; d += prm.ldd; }
               }
+            }
+          } else if (accum_f32) {
+            if (add_bias && prm.bias_mode == 2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] += (j < qn) ? __ldg(prm.bias + qb + j) : 0.f;
+            }
+            if (lane < pn) {
+              float* d = reinterpret_cast<float*>(Dbase) + doff + (int64_t)qb * prm.ldd + p_row;
+              float o[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] = (j < qn) ? d[(int64_t)j * prm.ldd] : 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < qn) d[(int64_t)j * prm.ldd] = o[j] + f[j];
             }
           } else if (lane < pn) {
 #pragma unroll
@@ -378,6 +392,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < 32; ++i) { if (i < pn) *d = st[i * EPI_PAD + lane] + bias_q; d += prm.ldd; }
               }
+            } else if (accum_f32) {
+              float* d = reinterpret_cast<float*>(Dbase) + doff + (int64_t)pb * prm.ldd + q;
+              float o[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = (i < pn) ? d[(int64_t)i * prm.ldd] : 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (i < pn) d[(int64_t)i * prm.ldd] = o[i] + st[i * EPI_PAD + lane] + bias_q;
             } else {
 #pragma unroll 1
               for (int i = 0; i < pn; ++i) {

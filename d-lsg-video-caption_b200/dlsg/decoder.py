@@ -16,7 +16,7 @@ import torch
 from . import linalg as la
 from . import ops
 from .functional import WC, next_seed, site, _c
-from .linalg import empty, zeros, op, op_empty, op_zeros, ceil8
+from .linalg import empty, zeros, small_zeros, op, op_empty, op_zeros, ceil8
 
 START = 1
 
@@ -293,7 +293,7 @@ class DecoderTrainBlock:
 
         def lnp(name):
             w, bb = t[pf + name + '.weight'], t[pf + name + '.bias']
-            dw_, db_ = zeros(w.shape, w), zeros(bb.shape, bb)
+            dw_, db_ = small_zeros(w.shape, w), small_zeros(bb.shape, bb)
             grads[pf + name + '.weight'], grads[pf + name + '.bias'] = dw_, db_
             return w, bb, dw_, db_
         lnq = lnp('query_lstm_layernorm')
@@ -310,7 +310,7 @@ class DecoderTrainBlock:
             wout = t[pf + 'word_restore.weight']
             be.gemm(dlo, WC.get(wout, transpose=True), dDall.view(B * T, Hd))
             grads[pf + 'word_restore.weight'] = la.mm(dloT, D2.t())
-            dbo = zeros((V,), ref)
+            dbo = small_zeros((V,), ref)
             be.colsum(dl2, dbo)
             grads[pf + 'word_restore.bias'] = dbo
         da_ext = None
@@ -332,7 +332,7 @@ class DecoderTrainBlock:
             dctxr = empty((B, nh * H), ref)
         dKp, dVp = zeros(Kp.shape, ref), zeros(Vp.shape, ref)        # (dKW, dVW when hoisted)
         att_scale = 1.0 / math.sqrt(H)
-        dcq, dcq2 = zeros((B, Hq), ref), empty((B, Hq), ref)
+        dcq, dcq2 = small_zeros((B, Hq), ref), empty((B, Hq), ref)
         dcl, dcl2 = zeros((B, Hd), ref), empty((B, Hd), ref)
         fused = core.fused
         if fused:
@@ -411,7 +411,7 @@ class DecoderTrainBlock:
         be.convert(dWq[:, oW:oW + W], dst=dwih[:, Hd + GH:])
         grads[pf + 'query_lstm.weight_ih'] = dwih
         grads[pf + 'query_lstm.weight_hh'] = dWq[:, oQ:oQ + Hq]
-        dbq = zeros((4 * Hq,), ref)
+        dbq = small_zeros((4 * Hq,), ref)
         be.colsum(dgq_all, dbq)
         grads[pf + 'query_lstm.bias_ih'] = dbq
         grads[pf + 'query_lstm.bias_hh'] = dbq
@@ -420,7 +420,7 @@ class DecoderTrainBlock:
         be.convert(dWl[:, oq:oq + Hq], dst=dlih[:, nh * H:])
         grads[pf + 'lang_lstm.weight_ih'] = dlih
         grads[pf + 'lang_lstm.weight_hh'] = dWl[:, ol:ol + Hd]
-        dbl = zeros((4 * Hd,), ref)
+        dbl = small_zeros((4 * Hd,), ref)
         be.colsum(dgl_all, dbl)
         grads[pf + 'lang_lstm.bias_ih'] = dbl
         grads[pf + 'lang_lstm.bias_hh'] = dbl

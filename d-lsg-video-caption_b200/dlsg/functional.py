@@ -15,7 +15,7 @@ import torch
 
 from . import linalg as la
 from . import ops
-from .linalg import empty, zeros, op, op_empty, op_zeros, mm32, flat2
+from .linalg import empty, zeros, small_zeros, op, op_empty, op_zeros, mm32, flat2
 
 _seed_counter = itertools.count(1)
 
@@ -49,7 +49,11 @@ class _BlockFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, *gouts):
         WC.set_scope(ctx.wc_scope)
-        grads = ctx.block.backward(ctx.saved, gouts)
+        la.begin_pool(gouts[0].device if gouts[0] is not None else next(g for g in gouts if g is not None).device)
+        try:
+            grads = ctx.block.backward(ctx.saved, gouts)
+        finally:
+            la.end_pool()
         ctx.saved = None
         if GRAD_SYNC is not None:
             grads = GRAD_SYNC.reduce(grads)
@@ -250,7 +254,7 @@ class TunBlock:
 
             def lnp(name):
                 w, b = t[pf + name + '.weight'], t[pf + name + '.bias']
-                dw, db = zeros(w.shape, w), zeros(b.shape, b)
+                dw, db = small_zeros(w.shape, w), small_zeros(b.shape, b)
                 grads[pf + name + '.weight'], grads[pf + name + '.bias'] = dw, db
                 return w, b, dw, db
             if g is None:
@@ -268,7 +272,7 @@ class TunBlock:
                 dX = empty((B, T, H), X)
                 theta = t[pf + 'v2l_layer.theta'].detach()
                 if s['G'] is None:
-                    dth = zeros(theta.shape, X)
+                    dth = small_zeros(theta.shape, X)
                     be.latent_psl_bwd(X.view(B, T, H), theta, s['Gs'], dN3, dX, dth)
                 else:
                     dGs = empty((B, T, P), X)
@@ -318,7 +322,7 @@ class TunBlock:
             if e['use_embed']:
                 wv = t[pf + 'visual_embed.weight']
                 grads[pf + 'visual_embed.weight'] = la.mm(dFv.t(), s['v2'].t())
-                dbv = zeros((H,), X)
+                dbv = small_zeros((H,), X)
                 be.colsum(dFv, dbv)
                 grads[pf + 'visual_embed.bias'] = dbv
             else:
@@ -327,7 +331,7 @@ class TunBlock:
             H = dOpre.shape[1] // E
             dWc = empty((E * H, Dr), dOpre)
             be.gemm(op(dOpre.t()), sv['RbT'], dWc)
-            dbc = zeros((E * H,), dOpre)
+            dbc = small_zeros((E * H,), dOpre)
             be.colsum(dOpre, dbc)
             for i, e in enumerate(self.encs):
                 grads[e['prefix'] + 'obj_embed.weight'] = dWc[i * H:(i + 1) * H]
@@ -437,7 +441,7 @@ class EncoderVisualBlock:
         out = empty((B, T, H), frames)
         stZ = empty((B * T, 2), frames)
         be.norm_fwd(Z, t[pf + 'layernorm_sa.weight'], t[pf + 'layernorm_sa.bias'], y=out.view(B * T, H), stats=stZ)
-        sv.update(dpe=dpe, Ypo=Ypo, KQV=KQV, lg=lg, Wt=Wt, sc=sc, att_op=att_op, Z=Z, dz=dz, stZ=stZ)
+        sv.update(dpe=dpe, Ypo=Ypo, Wkqv=Wkqv, KQV=KQV, lg=lg, Wt=Wt, sc=sc, att_op=att_op, Z=Z, dz=dz, stZ=stZ)
         return [out], sv
 
     def backward(self, sv, gouts):
@@ -451,7 +455,7 @@ class EncoderVisualBlock:
 
         def lnp(name):
             w, b = t[pf + name + '.weight'], t[pf + name + '.bias']
-            dw, db = zeros(w.shape, w), zeros(b.shape, b)
+            dw, db = small_zeros(w.shape, w), small_zeros(b.shape, b)
             grads[pf + name + '.weight'], grads[pf + name + '.bias'] = dw, db
             return w, b, dw, db
         dYv = empty((B * T, 2 * H), ref)
@@ -460,7 +464,7 @@ class EncoderVisualBlock:
             gop = op(g)
             be.gemm(gop, WC.get(wo, transpose=True), dYv)
             grads[pf + 'out_try.weight'] = la.mm(g.t(), sv['Y'].t())
-            dbo = zeros((H,), ref)
+            dbo = small_zeros((H,), ref)
             be.colsum(g, dbo)
             grads[pf + 'out_try.bias'] = dbo
         else:
@@ -491,8 +495,8 @@ class EncoderVisualBlock:
             dKQVop = dKQV.view(B * T, 3 * D2)
             wk, wq, wv = t[pf + 'self_attention.K.weight'], t[pf + 'self_attention.Q.weight'], t[pf + 'self_attention.V.weight']
             dYpe = empty((B * T, D2), ref)
-            for j, w_ in enumerate((wk, wq, wv)):
-                be.gemm(dKQVop[:, j * D2:(j + 1) * D2], WC.get(w_, transpose=True), dYpe, accum=(j > 0))
+            # one GEMM with K = 3*D2 over the packed [K;Q;V] weight read transposed in place (no accumulate passes)
+            be.gemm(dKQVop, sv['Wkqv'].t(), dYpe)
             dWkqv = la.mm(dKQVop.t(), sv['Ypo'].t())                # (3*D2, D2)
             for j, n in enumerate(('K', 'Q', 'V')):
                 grads[pf + 'self_attention.%s.weight' % n] = dWkqv[j * D2:(j + 1) * D2]
@@ -531,7 +535,7 @@ class EncoderVisualBlock:
             hp2 = hp.as_strided((B * T, H), (hp.stride(1), 1))
             grads[pf + names_hh[d]] = la.mm(dGin2[:, d * H4:(d + 1) * H4].t(), hp2.t())
         Wih, _ = self._packs(t, pf)
-        dbg = zeros((2 * H4,), ref)
+        dbg = small_zeros((2 * H4,), ref)
         be.colsum(dGin2, dbg)
         grads[pf + 'lstm.bias_ih_l0'] = dbg[:H4]
         grads[pf + 'lstm.bias_hh_l0'] = dbg[:H4]
@@ -543,7 +547,7 @@ class EncoderVisualBlock:
         dXe = empty((B * T, H), ref, la.opdtype())
         be.gemm(op(dGin2), op(Wih.t()), dXe)
         grads[pf + 'linear_embed.weight'] = la.mm(dXe.t(), sv['f2'].t())
-        dbl = zeros((H,), ref)
+        dbl = small_zeros((H,), ref)
         be.colsum(dXe, dbl)
         grads[pf + 'linear_embed.bias'] = dbl
         return grads

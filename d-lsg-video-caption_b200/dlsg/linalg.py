@@ -43,6 +43,49 @@ def zeros(shape, like, dtype=torch.float32):
     return torch.zeros(shape, dtype=dtype, device=like.device)
 
 
+_POOL = None
+
+
+class ZeroPool:
+    """One zero-filled fp32 slab per block backward, handed out in 16-byte aligned slices: the ~50 small parameter-
+    gradient accumulators of a step (LayerNorm gamma/beta, biases, theta) cost ONE fill launch per block instead of
+    one each."""
+
+    def __init__(self, device, numel=1 << 16):
+        self.buf = torch.zeros(numel, dtype=torch.float32, device=device)
+        self.off = 0
+
+    def take(self, shape):
+        n = 1
+        for s_ in shape:
+            n *= s_
+        if self.off + n > self.buf.numel():
+            return None
+        v = self.buf[self.off:self.off + n].view(shape)
+        self.off += (n + 3) // 4 * 4
+        return v
+
+
+def begin_pool(device):
+    global _POOL
+    _POOL = ZeroPool(device)
+
+
+def end_pool():
+    global _POOL
+    _POOL = None
+
+
+def small_zeros(shape, like):
+    """fp32 zeros for a small gradient accumulator: a slice of the active ZeroPool when a block backward is running."""
+    shape = tuple(shape)
+    if _POOL is not None and _POOL.buf.device == like.device:
+        v = _POOL.take(shape)
+        if v is not None:
+            return v
+    return torch.zeros(shape, dtype=torch.float32, device=like.device)
+
+
 def op_empty(rows_shape, K, like):
     """Operand buffer (..., K) in the operand dtype with an aligned row pitch; returns the [..., :K] view."""
     buf = torch.empty(tuple(rows_shape) + (ceil8(K),), dtype=opdtype(), device=like.device)

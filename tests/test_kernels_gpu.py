@@ -83,6 +83,8 @@ def test_gemm_tc_epilogues(be, M, N, K):
     both('gemm', be, [a, b, torch.zeros(M, N)], dict(bias=bias_n, bias_axis='n', tanh=True), [2], tol=2e-3)
     both('gemm', be, [a, b, torch.zeros(M, N)], dict(bias=bias_m, bias_axis='m', alpha=0.5), [2], tol=2e-3)
     both('gemm', be, [a, b, R(M, N)], dict(accum=True), [2], tol=2e-3)
+    both('gemm', be, [a, b, R(M, N)], dict(accum=True, bias=bias_n), [2], tol=2e-3)
+    both('gemm', be, [a, b, R(N, M).t()], dict(accum=True, bias=bias_m, bias_axis='m'), [2], tol=2e-3)   # accumulate + STORE_T
     both('gemm', be, [a, b, torch.zeros(M, N, dtype=torch.bfloat16)], dict(bias=bias_n), [2], tol=1e-2)
     both('gemm', be, [a, b, torch.zeros(N, M).t()], dict(bias=bias_n), [2], tol=2e-3)      # STORE_T
     both('gemm', be, [a, b, torch.zeros(M, N + 5)[:, :N]], dict(), [2], tol=2e-3)            # ldd > N
