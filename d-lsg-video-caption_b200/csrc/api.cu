@@ -47,6 +47,11 @@ void dlsg_debug_gemm_trace(void* dev_buf) { dlsg::gemm_tc_set_trace(dev_buf); }
 int dlsg_gemm(const dlsg_gemm_t* p, void* stream) {
   if (!p) { dlsg::set_error("dlsg_gemm: null params"); return -1; }
   if (p->impl == DLSG_GEMM_TC) return dlsg::gemm_tc_dispatch(p, (cudaStream_t)stream);
+  if (p->flags & DLSG_EPI_ATOMIC) {
+    dlsg_gemm_t q = *p;
+    q.flags = (q.flags & ~DLSG_EPI_ATOMIC) | DLSG_EPI_ACCUM;
+    return dlsg::gemm_simt_dispatch(&q, (cudaStream_t)stream);
+  }
   return dlsg::gemm_simt_dispatch(p, (cudaStream_t)stream);
 }
 

@@ -28,6 +28,7 @@ struct TcParams {
   int bias_mode;       // 0 none, 1 per-p, 2 per-q
   int store_t;         // 0: D[p*ldd+q]   1: D[q*ldd+p]
   int d_dtype, do_tanh, accum;
+  int atomic;          // D += result with red.global.add.f32 (split-K CTAs all land in the same D)
   float alpha;
   int splitk, kb_total, kb_per_split;
   int ntm, ntn, tiles_total;
@@ -261,7 +262,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // packed bf16x2 stores need 4-byte aligned pairs
     const bool pair_ok = bf16_out && !prm.store_t && !prm.accum && (prm.ldd % 2 == 0) && ((prm.stride_d | prm.stride_split) % 2 == 0) &&
                          ((reinterpret_cast<uintptr_t>(prm.D) & 3) == 0);
-    const bool plain_f32 = !bf16_out && !prm.accum && !prm.do_tanh;     // fp32 store, nothing else: the per-step GEMMs
+    const bool plain_f32 = !bf16_out && !prm.accum && !prm.do_tanh && !prm.atomic;   // fp32 store, nothing else: the per-step GEMMs
+    const bool atomic_f32 = prm.atomic != 0;                            // (host guarantees fp32 D, no tanh)
     const bool accum_f32 = !bf16_out && prm.accum && !prm.do_tanh;      // D += ...: all 32 loads in flight before the first store
     int acc = 0; uint32_t acc_ph = 0;
     for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
@@ -318,6 +320,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { if (j < qn) *d = f[j]; d += prm.ldd; }
               }
+            }
+          } else if (atomic_f32) {
+            if (add_bias && prm.bias_mode == 2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] += (j < qn) ? __ldg(prm.bias + qb + j) : 0.f;
+            }
+            if (lane < pn) {
+              float* d = reinterpret_cast<float*>(Dbase) + doff + (int64_t)qb * prm.ldd + p_row;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { if (j < qn) atomicAdd(d, f[j]); d += prm.ldd; }
             }
           } else if (accum_f32) {
             if (add_bias && prm.bias_mode == 2) {
@@ -392,6 +404,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < 32; ++i) { if (i < pn) *d = st[i * EPI_PAD + lane] + bias_q; d += prm.ldd; }
               }
+            } else if (atomic_f32) {
+              float* d = reinterpret_cast<float*>(Dbase) + doff + (int64_t)pb * prm.ldd + q;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) { if (i < pn) atomicAdd(d, st[i * EPI_PAD + lane] + bias_q); d += prm.ldd; }
             } else if (accum_f32) {
               float* d = reinterpret_cast<float*>(Dbase) + doff + (int64_t)pb * prm.ldd + q;
               float o[32];
@@ -513,6 +529,30 @@ static unsigned long long* g_tc_trace = nullptr;
 void gemm_tc_set_trace(void* p) { g_tc_trace = static_cast<unsigned long long*>(p); }
 
 int gemm_tc_dispatch(const dlsg_gemm_t* g, cudaStream_t st) {
+  if (g->flags & DLSG_EPI_ATOMIC) {
+    // D += A.B^T with atomic adds: split K over the idle SMs, every split's epilogue lands in D itself
+    DLSG_REQUIRE(g->d_dtype == DLSG_F32 && !(g->flags & (DLSG_EPI_TANH | DLSG_EPI_ACCUM)) && g->splitk <= 1,
+                 "gemm_tc: DLSG_EPI_ATOMIC needs an fp32 D, no tanh / accumulate flag and no explicit splitk");
+    dlsg_gemm_t part = *g;
+    part.workspace = nullptr;
+    const int batch = g->batch < 1 ? 1 : g->batch;
+    const bool swap = (g->M <= 64 && g->N > g->M);
+    const int P = swap ? g->N : g->M, Q = swap ? g->M : g->N;
+    const int bn = Q <= 32 ? 32 : (Q <= 64 ? 64 : 128);
+    const int64_t tiles = (int64_t)((P + BM - 1) / BM) * ((Q + bn - 1) / bn) * batch;
+    const int kb = (g->K + BK - 1) / BK;
+    int S = 1;
+    if (tiles * 2 <= kNumSM && kb >= 8) {
+      S = (int)(kNumSM / tiles);
+      if (S > kb / 4) S = kb / 4;
+      if (S > 16) S = 16;
+      const int per = (kb + S - 1) / S;
+      S = (kb + per - 1) / per;
+    }
+    part.splitk = S < 1 ? 1 : S;
+    part.stride_split = 0;
+    return gemm_tc_direct(&part, st);
+  }
   // Automatic split-K for skinny problems: too few 128-row tiles to fill 148 SMs and a long K loop
   // (the per-step recurrent GEMMs: M = batch = 64, weights streamed once).
   if (g->splitk <= 1 && g->workspace && g->M > 0 && g->N > 0) {
@@ -522,9 +562,10 @@ int gemm_tc_dispatch(const dlsg_gemm_t* g, cudaStream_t st) {
     const int bn = Q <= 32 ? 32 : (Q <= 64 ? 64 : 128);
     const int64_t tiles = (int64_t)((P + BM - 1) / BM) * ((Q + bn - 1) / bn) * batch;
     const int kb = (g->K + BK - 1) / BK;
-    if (tiles * 2 <= kNumSM && kb >= 8) {
+    // the reduce launch costs ~2-3 us in a dependent chain: only worth it when every split still streams >= 8 k-blocks
+    if (tiles * 2 <= kNumSM && kb >= 16) {
       int S = (int)(kNumSM / tiles);      // floor: all tiles*S CTAs run in ONE wave of the persistent grid
-      if (S > kb / 4) S = kb / 4;
+      if (S > kb / 8) S = kb / 8;
       if (S > 16) S = 16;
       const int per = (kb + S - 1) / S;
       S = (kb + per - 1) / per;
@@ -574,6 +615,7 @@ static int gemm_tc_direct(const dlsg_gemm_t* g, cudaStream_t st) {
   if (g->bias && (g->flags & DLSG_EPI_BIAS_N)) prm.bias_mode = swap ? 1 : 2;
   if (g->bias && (g->flags & DLSG_EPI_BIAS_M)) prm.bias_mode = swap ? 2 : 1;
   prm.d_dtype = g->d_dtype; prm.do_tanh = (g->flags & DLSG_EPI_TANH) ? 1 : 0; prm.accum = (g->flags & DLSG_EPI_ACCUM) ? 1 : 0;
+  prm.atomic = (g->flags & DLSG_EPI_ATOMIC) ? 1 : 0;
   prm.alpha = g->alpha;
   prm.kb_total = (g->K + BK - 1) / BK;
   int splitk = g->splitk < 1 ? 1 : g->splitk;

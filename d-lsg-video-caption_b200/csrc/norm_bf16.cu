@@ -110,11 +110,12 @@ norm_bwd_bf16_kernel(const dlsg_norm_bwd_t p) {
   const float invD = 1.f / (float)D;
   const int64_t stride = (int64_t)gridDim.x * nw;
   int64_t row = (int64_t)blockIdx.x * nw + w;
-  float ag[NC][8], ab[NC][8];
+  float ag[NC][8], ab[NC][8], ax[NC][8];          // per-lane column partial sums: dgamma, dbeta, sum(dx)
 #pragma unroll
   for (int j = 0; j < NC; ++j)
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { ag[j][u] = 0.f; ab[j][u] = 0.f; }
+    for (int u = 0; u < 8; ++u) { ag[j][u] = 0.f; ab[j][u] = 0.f; ax[j][u] = 0.f; }
+  const bool want_dxsum = p.dxsum != nullptr;
   uint4 cx[NC], cd[NC], nx[NC], nd[NC];
   float2 st = make_float2(0.f, 0.f), stn = st;
 #pragma unroll
@@ -176,6 +177,7 @@ norm_bwd_bf16_kernel(const dlsg_norm_bwd_t p) {
         for (int u = 0; u < 8; ++u) {
           o[u] = rstd * (d[j][u] - s1 - xh[j][u] * s2);
           if (dtanh) { const float t = fmaf(xh[j][u], istd, mean); o[u] *= (1.f - t * t); }   // t = x (the tanh output)
+          if (want_dxsum) ax[j][u] += o[u];
         }
         *reinterpret_cast<uint4*>(DX + row * p.lddx + c) = pack8(o);
       }
@@ -184,8 +186,26 @@ norm_bwd_bf16_kernel(const dlsg_norm_bwd_t p) {
     for (int j = 0; j < NC; ++j) { cx[j] = nx[j]; cd[j] = nd[j]; }
     st = stn;
   }
+  if (want_dxsum) {                              // uniform; reduce sum(dx) across the CTA's warps, one atomic per column
+    __syncthreads();                             // gamma in smem no longer needed
+    float* mx = sm + (size_t)w * D;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const int c = 256 * j + 8 * lane;
+      if (c < D) {
+        *reinterpret_cast<float4*>(mx + c) = make_float4(ax[j][0], ax[j][1], ax[j][2], ax[j][3]);
+        *reinterpret_cast<float4*>(mx + c + 4) = make_float4(ax[j][4], ax[j][5], ax[j][6], ax[j][7]);
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      float tx = 0.f;
+      for (int ww = 0; ww < nw; ++ww) tx += sm[(size_t)ww * D + c];
+      atomicAdd(&p.dxsum[c], tx);
+    }
+  }
   if (p.dgamma == nullptr) return;               // uniform
-  __syncthreads();                               // gamma in smem no longer needed
+  __syncthreads();                               // gamma / dxsum staging in smem no longer needed
   float* mg = sm + (size_t)w * 2 * D;
 #pragma unroll
   for (int j = 0; j < NC; ++j) {

@@ -441,6 +441,7 @@ int norm_bwd_launch(const dlsg_norm_bwd_t* p, cudaStream_t st) {
   DLSG_REQUIRE(p->rows >= 0 && p->D > 0 && p->D <= 4096, "norm_bwd: bad shape rows=%lld D=%d", (long long)p->rows, p->D);
   if (p->rows == 0) return 0;
   if (norm_bwd_bf16_ok(p)) return norm_bwd_bf16_launch(p, st);
+  DLSG_REQUIRE(p->dxsum == nullptr, "norm_bwd: dxsum is only produced by the streaming bf16 form (dlsg_norm_bwd_streaming)");
   const bool vec = p->D <= 2048 && vec_ok(p->x, p->x_dtype, p->ldx, p->D) && vec_ok(p->res, p->res_dtype, p->ldres, p->D) &&
                    vec_ok(p->dy, p->dy_dtype, p->lddy, p->D) && vec_ok(p->dx, p->dx_dtype, p->lddx, p->D) &&
                    vec_ok(p->gamma, DLSG_F32, 4, p->D) && vec_ok(p->beta, DLSG_F32, 4, p->D);
@@ -535,6 +536,44 @@ lstm_cell_bwd_kernel(const dlsg_lstm_cell_bwd_t p) {
       if (p.dgates) p.dgates[(int64_t)b * 4 * H + col] = d[k];
       if (p.dgates2) st_from_float(p.dgates2, p.dgates2_dtype, (int64_t)b * p.ld_dgates2 + col, d[k]);
       if (p.dgatesT) st_from_float(p.dgatesT, p.dgatesT_dtype, col * p.ld_dgatesT + b, d[k]);
+    }
+  }
+}
+
+// Backward OF the cell backward (WGAN-GP double backward through the discriminator LSTM, run_gun.py:362-375).
+// The cell backward maps (dh, dc; a=pre-activations, c0) -> (dpre[4], dc0) with D = dh*o*(1-tc^2) + dc:
+//   dpre_i = D*g*i(1-i)  dpre_f = D*c0*f(1-f)  dpre_g = D*i*(1-g^2)  dpre_o = dh*tc*o(1-o)  dc0 = D*f .
+// Given cotangents u[4] (for dpre) and w (for dc0) this kernel returns the cotangents of dh, dc, a[4] and c0
+// (c = f*c0 + i*g is treated as a function of a and c0).
+__global__ void __launch_bounds__(256)
+lstm_cell_bwd2_kernel(const dlsg_lstm_cell_bwd2_t p) {
+  pdl_prologue();
+  const int64_t n = (int64_t)p.B * p.H;
+  const int H = p.H;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(e / H), h = (int)(e % H);
+    const int64_t g0 = (int64_t)b * 4 * H + h;
+    const float ig = p.acts[g0], fg = p.acts[g0 + H], gg = p.acts[g0 + 2 * (int64_t)H], og = p.acts[g0 + 3 * (int64_t)H];
+    const float dh = p.dh[e];
+    const float dcn = p.dc_next ? p.dc_next[e] : 0.f;
+    const float c0 = p.c_prev ? p.c_prev[e] : 0.f;
+    const float tc = tanhf(p.c_new[e]);
+    const float omt = 1.f - tc * tc;
+    float ui = 0.f, uf = 0.f, ug = 0.f, uo = 0.f;
+    if (p.u) { ui = p.u[g0]; uf = p.u[g0 + H]; ug = p.u[g0 + 2 * (int64_t)H]; uo = p.u[g0 + 3 * (int64_t)H]; }
+    const float w = p.w ? p.w[e] : 0.f;
+    const float si = ig * (1.f - ig), sf = fg * (1.f - fg), sg = 1.f - gg * gg, so = og * (1.f - og);
+    const float D = dh * og * omt + dcn;
+    const float S = ui * gg * si + uf * c0 * sf + ug * ig * sg + w * fg;       // d(L2)/dD
+    const float Q = S * dh * og * (-2.f * tc * omt) + uo * dh * so * omt;       // d(L2)/dc through tc
+    if (p.g_dh) p.g_dh[e] = S * og * omt + uo * tc * so;
+    if (p.g_dc) p.g_dc[e] = S;
+    if (p.g_cprev) p.g_cprev[e] = D * uf * sf + Q * fg;
+    if (p.g_pre) {
+      p.g_pre[g0] = D * (ui * gg * si * (1.f - 2.f * ig) + ug * sg * si) + Q * gg * si;
+      p.g_pre[g0 + H] = D * (uf * c0 * sf * (1.f - 2.f * fg) + w * sf) + Q * c0 * sf;
+      p.g_pre[g0 + 2 * (int64_t)H] = D * (ui * si * sg + ug * ig * (-2.f * gg) * sg) + Q * ig * sg;
+      p.g_pre[g0 + 3 * (int64_t)H] = S * dh * omt * so + uo * dh * tc * so * (1.f - 2.f * og);
     }
   }
 }
@@ -766,6 +805,7 @@ int dlsg_convert2d(const void* src, int sdt, int64_t lds, void* dst, int ddt, in
 
 int dlsg_norm_fwd(const dlsg_norm_fwd_t* p, void* stream) { return norm_fwd_launch(p, (cudaStream_t)stream); }
 int dlsg_norm_bwd(const dlsg_norm_bwd_t* p, void* stream) { return norm_bwd_launch(p, (cudaStream_t)stream); }
+int dlsg_norm_bwd_streaming(const dlsg_norm_bwd_t* p) { return norm_bwd_bf16_ok(p) ? 1 : 0; }
 
 int dlsg_lstm_cell_fwd(const dlsg_lstm_cell_fwd_t* p, void* stream) {
   DLSG_REQUIRE(p->B > 0 && p->H > 0 && p->nsplit >= 1, "lstm_cell_fwd: bad shape");
@@ -776,6 +816,12 @@ int dlsg_lstm_cell_bwd(const dlsg_lstm_cell_bwd_t* p, void* stream) {
   DLSG_REQUIRE(p->B > 0 && p->H > 0, "lstm_cell_bwd: bad shape");
   DLSG_LAUNCH(lstm_cell_bwd_kernel, ew_blocks((int64_t)p->B * p->H), 256, 0, (cudaStream_t)stream, *p);
   return check_launch("lstm_cell_bwd_kernel");
+}
+
+int dlsg_lstm_cell_bwd2(const dlsg_lstm_cell_bwd2_t* p, void* stream) {
+  DLSG_REQUIRE(p->B > 0 && p->H > 0 && p->acts && p->c_new && p->dh, "lstm_cell_bwd2: bad arguments");
+  DLSG_LAUNCH(lstm_cell_bwd2_kernel, ew_blocks((int64_t)p->B * p->H), 256, 0, (cudaStream_t)stream, *p);
+  return check_launch("lstm_cell_bwd2_kernel");
 }
 
 int dlsg_softmax_fwd(const dlsg_softmax_t* p, void* stream) {

@@ -7,7 +7,7 @@ LIB_PATH = os.path.join(HERE, 'libdlsg.so')
 
 F32, BF16 = 0, 1
 GEMM_SIMT, GEMM_TC = 0, 1
-EPI_BIAS_N, EPI_BIAS_M, EPI_TANH, EPI_ACCUM, EPI_STORE_T = 1, 2, 4, 8, 16
+EPI_BIAS_N, EPI_BIAS_M, EPI_TANH, EPI_ACCUM, EPI_STORE_T, EPI_ATOMIC = 1, 2, 4, 8, 16, 32
 NORM_PRE_TANH, NORM_POST_TANH, NORM_IN_IS_TANH = 1, 2, 4
 
 i32, i64, u32, u64, f32, vp = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_float, C.c_void_p
@@ -37,7 +37,7 @@ class NormBwdT(C.Structure):
                 ('rows', i64), ('D', i32), ('flags', i32),
                 ('lddy', i64), ('ldx', i64), ('ldres', i64), ('lddx', i64),
                 ('dy_dtype', i32), ('x_dtype', i32), ('res_dtype', i32), ('dx_dtype', i32),
-                ('drop_p', f32), ('dx_accum', i32), ('seed', u64), ('offset', u64)]
+                ('drop_p', f32), ('dx_accum', i32), ('seed', u64), ('offset', u64), ('dxsum', vp)]
 
 
 class CellFwdT(C.Structure):
@@ -57,6 +57,11 @@ class CellBwdT(C.Structure):
                 ('dc_prev', vp), ('B', i32), ('H', i32),
                 ('drop_p', f32), ('_pad2', i32), ('seed', u64), ('offset', u64),
                 ('dh2_nsplit', i32), ('_pad3', i32), ('dh2_stride_split', i64)]
+
+
+class CellBwd2T(C.Structure):
+    _fields_ = [('acts', vp), ('c_prev', vp), ('c_new', vp), ('dh', vp), ('dc_next', vp), ('u', vp), ('w', vp),
+                ('g_dh', vp), ('g_dc', vp), ('g_pre', vp), ('g_cprev', vp), ('B', i32), ('H', i32)]
 
 
 class CellNormFwdT(C.Structure):
@@ -125,8 +130,10 @@ SIGNATURES = {
     'dlsg_colsum': (i32, [vp, i32, i64, i64, i64, vp, vp]),
     'dlsg_norm_fwd': (i32, [C.POINTER(NormFwdT), vp]),
     'dlsg_norm_bwd': (i32, [C.POINTER(NormBwdT), vp]),
+    'dlsg_norm_bwd_streaming': (i32, [C.POINTER(NormBwdT)]),
     'dlsg_lstm_cell_fwd': (i32, [C.POINTER(CellFwdT), vp]),
     'dlsg_lstm_cell_bwd': (i32, [C.POINTER(CellBwdT), vp]),
+    'dlsg_lstm_cell_bwd2': (i32, [C.POINTER(CellBwd2T), vp]),
     'dlsg_lstm_cell_norm_fwd': (i32, [C.POINTER(CellNormFwdT), vp]),
     'dlsg_norm_lstm_cell_bwd': (i32, [C.POINTER(NormCellBwdT), vp]),
     'dlsg_fused_step_supported': (i32, [i32]),

@@ -355,7 +355,7 @@ class DecoderTrainBlock:
                 be.lstm_cell_bwd(b.gl[0, i], b.cl[i], b.cl[j], dXq[j][:, :Hd], dcl, dcl2, dgates2=dgl_all[rows],
                                  drop=dl, dh2=dXl[j][:, ol:ol + Hd])
             dcl, dcl2 = dcl2, dcl
-            be.gemm(dgl_all[rows], pk['WlT'], dXl[i])
+            be.gemm(dgl_all[rows], pk['WlT'], dXl[i], atomic=True)      # dXl / dXq start as zeros: split-K lands by atomic adds
             if hoist:
                 # one kernel: output-layer backward (dropout, LayerNorm, tanh) of both heads -> d(alpha), softmax backward,
                 # dq += sum_h sum_p dl KW, dKW / dVW accumulated over time; LN parameter gradients as per-row contributions
@@ -385,7 +385,7 @@ class DecoderTrainBlock:
                                  dgates2=dgq_all[rows])
                 be.axpby(dgq32, 1.0, dgq_sum, 1.0)
             dcq, dcq2 = dcq2, dcq
-            be.gemm(dgq_all[rows], pk['WqT'], dXq[i])
+            be.gemm(dgq_all[rows], pk['WqT'], dXq[i], atomic=True)
         # ---- parameter gradients batched over time
         if fused:
             be.colsum(lq_g.view(TB, Hq), lnq[2])

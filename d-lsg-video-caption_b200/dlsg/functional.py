@@ -245,7 +245,7 @@ class TunBlock:
         E = len(self.encs)
         use_regions = R >= 5
         grads = {}
-        dOpre = None
+        dOpre = dbc = None
         for i, e in enumerate(self.encs):
             pf, s = e['prefix'], sv['enc'][i]
             g = gouts[i]
@@ -312,8 +312,11 @@ class TunBlock:
                     if any(g_ is None for g_ in gouts):
                         dOpre.zero_()
                 w, b, dw, db = lnp('obj_norm.1')
+                if dbc is None:
+                    dbc = small_zeros((E * H,), dOpre)
+                # the region-projection bias gradient (column sums of dOpre) is accumulated by the same kernel
                 be.norm_bwd(dO, sv['Ot'][:, i * H:(i + 1) * H], w, b, s['stO'], dx=dOpre[:, i * H:(i + 1) * H], dgamma=dw,
-                            dbeta=db, in_is_tanh=True)
+                            dbeta=db, in_is_tanh=True, dxsum=dbc[i * H:(i + 1) * H])
             else:
                 dF = dX.view(B * T, H)
             w, b, dw, db = lnp('visual_norm.1')
@@ -331,8 +334,6 @@ class TunBlock:
             H = dOpre.shape[1] // E
             dWc = empty((E * H, Dr), dOpre)
             be.gemm(op(dOpre.t()), sv['RbT'], dWc)
-            dbc = small_zeros((E * H,), dOpre)
-            be.colsum(dOpre, dbc)
             for i, e in enumerate(self.encs):
                 grads[e['prefix'] + 'obj_embed.weight'] = dWc[i * H:(i + 1) * H]
                 grads[e['prefix'] + 'obj_embed.bias'] = dbc[i * H:(i + 1) * H]

@@ -1,0 +1,146 @@
+"""One full iteration of the live GAN trainer (run_gun.py:147-234 + train_disc :339-398) on the drop-in modules,
+optionally captured as ONE CUDA graph.
+
+  G forward #1 (fake sample)                                         run_gun.py:167
+  num_D x [ D(real one-hot), D(fake logits), D(mixed), WGAN-GP double backward, Adam(D) ]     :339-383
+  G forward #2 -> packed CE -> D(raw logits) -> total.backward() -> Adam(G)                  :183-234
+
+The reference's own loop (run_gun.py, unchanged) runs on the same modules eagerly; this entry exists because an
+iteration is ~10^4 small kernels and eager Python launches them at ~20 us each.  As with GraphedTrainStep the
+teacher-forcing coin flips (layer.py:432) and the dropout seeds are frozen at capture time; the WGAN-GP epsilon
+(torch.rand, run_gun.py:355) is re-drawn on every replay (graph-safe CUDA RNG).
+"""
+import torch
+
+from . import functional as DF
+from . import linalg as la
+from . import losses
+
+
+class GanIteration:
+    def __init__(self, G, D, opt_g, opt_d, frames, regions, captions, cap_lens, max_words=26, tf_ratio=0.6, num_d=5,
+                 gan_lambda=0.01, process_group=None, graph=True, warmup=2):
+        dev = frames.device
+        self.G, self.D, self.opt_g, self.opt_d = G, D, opt_g, opt_d
+        self.frames, self.regions, self.captions = frames.clone(), regions.clone(), captions.clone()
+        self.lens = torch.as_tensor(list(cap_lens), dtype=torch.int32, device=dev)
+        self.inv = torch.tensor([1.0 / max(1, int(sum(cap_lens)))], dtype=torch.float32, device=dev)
+        self.lam = torch.tensor(float(gan_lambda), dtype=torch.float32, device=dev)
+        self.max_words, self.tf, self.num_d = max_words, tf_ratio, num_d
+        self.V = D.conv1d.weight.shape[1]
+        self.pg, self.world, self.sync = process_group, 1, None
+        if process_group is not None:
+            import torch.distributed as dist
+            self.dist = dist
+            self.world = dist.get_world_size(process_group)
+            self.sync = DF.GradSync(process_group)
+        self.d_params = [p for p in D.parameters() if p.requires_grad]
+        self.graph = None
+        self.out = None
+        if graph:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(warmup):
+                    self._body()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.opt_g.zero_grad(set_to_none=True)
+            self.opt_d.zero_grad(set_to_none=True)
+            self.graph = torch.cuda.CUDAGraph()
+            from . import ops
+            l0 = ops.backend().launches
+            DF.WC.force = True
+            try:
+                with torch.cuda.graph(self.graph):
+                    self.out = self._body()
+            finally:
+                DF.WC.force = False
+            self.launches = ops.backend().launches - l0
+            torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ run_gun.py:339-383
+    def _disc_steps(self, real, fake, obj, mot, att_mask, alpha):
+        D, B = self.D, real.shape[0]
+        loss_d = wass = torch.zeros((), device=real.device)
+        for _ in range(self.num_d):
+            self.opt_d.zero_grad(set_to_none=True)
+            r_logit = D(real, obj, mot, att_mask, alpha)
+            f_logit = D(fake, obj, mot, att_mask, alpha)
+            eps = torch.rand(B, 1, 1, device=real.device, requires_grad=True)
+            mixed = real * eps + fake * (1 - eps)
+            m_logit = D(mixed, obj, mot, att_mask, alpha)
+            g = torch.autograd.grad(inputs=mixed, outputs=m_logit, grad_outputs=torch.ones_like(m_logit),
+                                    create_graph=True, retain_graph=True)[0]
+            gn = g.contiguous().view(B, -1).norm(2, dim=1)
+            gp = ((gn - 1) * (gn - 1)).mean()
+            r_loss, f_loss = r_logit.mean(), f_logit.mean()
+            loss_d = f_loss - r_loss + 10 * gp
+            loss_d.backward()
+            if self.world > 1:
+                flat = torch.cat([p.grad.reshape(-1) for p in self.d_params if p.grad is not None])
+                self.dist.all_reduce(flat, op=self.dist.ReduceOp.AVG, group=self.pg)
+                off = 0
+                for p in self.d_params:
+                    if p.grad is not None:
+                        n = p.grad.numel()
+                        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                        off += n
+            self.opt_d.step()
+            la.new_param_epoch()                      # critic weights changed: refresh their bf16 copies on next use
+            wass = (r_loss - f_loss).detach()
+        return loss_d.detach(), wass
+
+    def _body(self):
+        la.set_manual_param_epochs(True)              # one weight conversion per optimizer step, not per D forward
+        la.new_param_epoch()
+        try:
+            return self._iteration()
+        finally:
+            la.set_manual_param_epochs(False)
+            la.new_param_epoch()
+
+    def _iteration(self):
+        G, D = self.G, self.D
+        caps = self.captions
+        B, L = caps.shape[0], self.max_words
+        seq = (caps[:, :L] > 0).to(torch.float32)
+        att_mask = seq.unsqueeze(2) * seq.unsqueeze(1)                                   # run_gun.py:164-166
+        with torch.no_grad():                                                            # :167 (detached right after, :170-174)
+            f_cap, obj, mot, alpha = G(self.frames, self.regions, caps, L, self.tf)
+        real = torch.zeros(B, L, self.V, device=caps.device).scatter_(2, caps[:, :L].unsqueeze(2), 1)      # :449-453
+        loss_d, wass = self._disc_steps(real, f_cap, obj, mot, att_mask, alpha)
+        self.opt_g.zero_grad(set_to_none=True)
+        out, obj, mot, alpha = G(self.frames, self.regions, caps, L, self.tf)            # :183
+        cap_loss = losses.packed_cross_entropy(out, caps, self.lens, self.inv, unit_grad=True)            # :189-197
+        f_logit = D(out, obj.detach(), mot.detach(), att_mask=att_mask, alpha_all=alpha.detach())          # :218
+        loss_g = -f_logit.mean()
+        total = cap_loss + loss_g * self.lam
+        if self.world > 1:
+            DF.GRAD_SYNC = self.sync
+        try:
+            total.backward()
+        finally:
+            DF.GRAD_SYNC = None
+        if self.world > 1:
+            self.sync.wait()
+        self.opt_g.step()
+        return cap_loss.detach(), loss_g.detach(), loss_d, wass
+
+    def load(self, frames, regions, captions, cap_lens=None):
+        self.frames.copy_(frames, non_blocking=True)
+        self.regions.copy_(regions, non_blocking=True)
+        self.captions.copy_(captions, non_blocking=True)
+        if cap_lens is not None:
+            self.lens.copy_(torch.as_tensor(list(cap_lens), dtype=torch.int32))
+            self.inv.fill_(1.0 / max(1, int(sum(cap_lens))))
+
+    def set_lambda(self, lam):
+        self.lam.fill_(float(lam))
+
+    def __call__(self):
+        """Returns device scalars (cap_loss, loss_G, loss_D of the last D step, wasserstein of the last D step)."""
+        if self.graph is not None:
+            self.graph.replay()
+            return self.out
+        return self._body()

@@ -15,6 +15,18 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def param_scope(fn):
+    """Decorator for generic-path module forwards: opens a parameter-copy epoch (dlsg.linalg.param_epoch_scope) so bf16
+    weight copies are refreshed once per top-level forward (fused optimizers do not bump tensor versions)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*a, **k):
+        with la.param_epoch_scope():
+            return fn(*a, **k)
+    return wrapped
+
+
 # ----------------------------------------------------------------------------------------------- matmul
 class _MmNT(torch.autograd.Function):
     """y[..., M, N] = a[..., M, K] @ b[..., N, K]^T (batched when 3-D)."""
@@ -22,7 +34,7 @@ class _MmNT(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b):
         ctx.save_for_backward(a, b)
-        return la.mm(a.detach(), b.detach())
+        return la.mm(a, b, memo=True)
 
     @staticmethod
     def backward(ctx, dy):
@@ -227,21 +239,176 @@ def resblock(x_bcl, w3, b3):
     return resblock_blc(x_bcl.transpose(1, 2), w3, b3).transpose(1, 2)
 
 
+class _MmNTW(torch.autograd.Function):
+    """y = a @ w^T with a ready-made GEMM operand copy `w_op` of the weight (bf16 in bf16 mode; a transposed view of it
+    serves the data-gradient product in place), so a recurrent weight is converted once per sequence, not per step."""
+
+    @staticmethod
+    def forward(ctx, a, w, w_op):
+        ctx.save_for_backward(a, w)
+        ctx.w_op = w_op
+        out = torch.empty(a.shape[:-1] + (w_op.shape[-2],), dtype=torch.float32, device=a.device)
+        ops.backend().gemm(la.op_cached(a), w_op, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, w = ctx.saved_tensors
+        da = dw = None
+        if ctx.needs_input_grad[0]:
+            da = _MmNTW.apply(dy, w.transpose(-1, -2), ctx.w_op.transpose(-1, -2))
+        if ctx.needs_input_grad[1]:
+            dw = bmm_nt(dy.transpose(-1, -2), a.transpose(-1, -2))
+        return da, dw, None
+
+
+class _Cell(torch.autograd.Function):
+    """LSTM cell pointwise (gate order i,f,g,o): (pre (B,4H), c_prev (B,H)) -> (h, c, acts), one fused kernel.  The
+    backward is `_CellBwd` (one fused kernel) whose own backward is the closed-form dlsg_lstm_cell_bwd2 kernel, so the
+    WGAN-GP double backward through the discriminator LSTM costs one launch per step and level."""
+
+    @staticmethod
+    def forward(ctx, pre, c_prev):
+        acts = _c(pre).clone()
+        c = torch.empty_like(c_prev)
+        h = torch.empty_like(c_prev)
+        ops.backend().lstm_cell_fwd(acts, _c(c_prev), c, h_out=h)
+        ctx.save_for_backward(pre, c_prev)
+        ctx.acts, ctx.c = acts, c
+        ctx.mark_non_differentiable(acts)
+        return h, c, acts
+
+    @staticmethod
+    def backward(ctx, dh, dc, _dacts):
+        pre, c_prev = ctx.saved_tensors
+        return _CellBwd.apply(dh, dc, pre, c_prev, ctx.acts, ctx.c.detach())
+
+
+class _CellBwd(torch.autograd.Function):
+    """(dh, dc_next; pre, c_prev) -> (dpre, dc_prev).  `acts`/`c` are the forward's saved buffers (functions of pre and
+    c_prev: their dependence is folded into the closed-form second-order terms)."""
+
+    @staticmethod
+    def forward(ctx, dh, dc, pre, c_prev, acts, c):
+        dh = _c(dh) if dh is not None else torch.zeros_like(c)
+        dc = _c(dc) if dc is not None else None
+        dpre = torch.empty_like(acts)
+        dc_prev = torch.empty_like(c)
+        ops.backend().lstm_cell_bwd(acts, _c(c_prev), c, dh, dc, dc_prev, dgates=dpre)
+        ctx.save_for_backward(dh, dc)
+        ctx.acts, ctx.c, ctx.c_prev = acts, c, c_prev.detach()
+        return dpre, dc_prev
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, u, w):
+        dh, dc = ctx.saved_tensors
+        acts, c = ctx.acts, ctx.c
+        g_dh, g_dc = torch.empty_like(c), torch.empty_like(c)
+        g_pre, g_c0 = torch.empty_like(acts), torch.empty_like(c)
+        ops.backend().lstm_cell_bwd2(acts, _c(ctx.c_prev), c, dh, dc, _c(u) if u is not None else None,
+                                     _c(w) if w is not None else None, g_dh, g_dc, g_pre, g_c0)
+        return g_dh, (g_dc if dc is not None else None), g_pre, g_c0, None, None
+
+
+def _lstm_bptt_diff(gin, w_hh, dhs, need_dgin, need_dw):
+    """Differentiable BPTT (used only when the gradient itself must be differentiated: the WGAN-GP penalty).  The
+    forward is recomputed step by step with `_Cell` so that the result is a differentiable function of gin, w_hh, dhs."""
+    B, T, H4 = gin.shape
+    H = H4 // 4
+    w_op = la.op(w_hh.detach())
+    c = gin.new_zeros(B, H)
+    h = None
+    pres, cprevs, actss, cbufs, hs = [], [], [], [], []
+    gin_t = gin.unbind(1)                     # one unbind / stack pair instead of T select nodes (each of whose backward
+    dhs_t = dhs.unbind(1)                     # would materialise a full zero-padded (B,T,.) tensor)
+    for t in range(T):
+        pre = gin_t[t] if h is None else gin_t[t] + _MmNTW.apply(h, w_hh, w_op)
+        pres.append(pre)
+        cprevs.append(c)
+        h, c, acts = _Cell.apply(pre, c)
+        actss.append(acts)
+        cbufs.append(c.detach())
+        hs.append(h)
+    dh_rec = dc = None
+    dpres = [None] * T
+    w_t, w_op_t = w_hh.transpose(-1, -2), w_op.transpose(-1, -2)
+    for t in range(T - 1, -1, -1):
+        dh = dhs_t[t] if dh_rec is None else dhs_t[t] + dh_rec
+        dpres[t], dc = _CellBwd.apply(dh, dc, pres[t], cprevs[t], actss[t], cbufs[t])
+        if t > 0:
+            dh_rec = _MmNTW.apply(dpres[t], w_t, w_op_t)
+    dgin = torch.stack(dpres, 1) if need_dgin else None
+    dw = None
+    if need_dw and T > 1:
+        dp = torch.stack(dpres[1:], 1).reshape(-1, H4)              # rows (b, t>=1)
+        hp = torch.stack(hs[:-1], 1).reshape(-1, H)                 # h fed into step t
+        dw = bmm_nt(dp.transpose(0, 1), hp.transpose(0, 1))         # time-batched recurrent weight gradient (4H,H)
+    elif need_dw:
+        dw = torch.zeros_like(w_hh)
+    return dgin, dw
+
+
+class _LstmSeq(torch.autograd.Function):
+    """Zero-state uni-directional LSTM over all steps: gin (B,T,4H) = x W_ih^T + b_ih + b_hh -> h (B,T,H).
+    Forward and first-order backward are fused loops (recurrent GEMM with split-K partials summed by the cell kernel:
+    2 launches per step; one time-batched weight-gradient GEMM).  Under create_graph the backward is the
+    differentiable `_lstm_bptt_diff`."""
+
+    @staticmethod
+    def forward(ctx, gin, w_hh):
+        be = ops.backend()
+        gin = _c(gin)
+        B, T, H4 = gin.shape
+        H = H4 // 4
+        w_op = la.op(w_hh.detach())
+        S = la.splitk_for(B, H4, H)
+        gates = zeros((S, T, B, H4), gin)                 # split-K partials; [0] ends up holding the activated gates
+        cs = zeros((T + 1, B, H), gin)
+        hin = la.op_zeros((T, B), H, gin)                 # h fed INTO step t, as a GEMM operand
+        hs = empty((B, T, H), gin)
+        for t in range(T):
+            if t > 0:
+                be.gemm(hin[t], w_op, gates[:, t] if S > 1 else gates[0, t], splitk=S)
+            be.lstm_cell_fwd(gates[:, t], cs[t], cs[t + 1], row_bias=gin[:, t], h2=hs[:, t],
+                             h3=(hin[t + 1] if t + 1 < T else None))
+        ctx.save_for_backward(gin, w_hh)
+        ctx.bufs = (gates[0], cs, hin, w_op)
+        return hs
+
+    @staticmethod
+    def backward(ctx, dhs):
+        gin, w_hh = ctx.saved_tensors
+        need_dgin, need_dw = ctx.needs_input_grad
+        if torch.is_grad_enabled():
+            return _lstm_bptt_diff(gin, w_hh, dhs, need_dgin, need_dw)
+        be = ops.backend()
+        acts, cs, hin, w_op = ctx.bufs
+        T, B, H4 = acts.shape
+        H = H4 // 4
+        dhs = _c(dhs)
+        bf = la.precision() == 'bf16'
+        dg32 = empty((T, B, H4), gin)
+        dg_op = la.op_empty((T, B), H4, gin) if bf else dg32
+        Sd = la.splitk_for(B, H, H4)
+        dhrec = zeros((Sd, B, H), gin)
+        dc, dc2 = zeros((B, H), gin), empty((B, H), gin)
+        w_t = w_op.transpose(-1, -2)
+        for t in range(T - 1, -1, -1):
+            be.lstm_cell_bwd(acts[t], cs[t], cs[t + 1], dhs[:, t], dc, dc2, dgates=dg32[t], dgates2=(dg_op[t] if bf else None),
+                             dh2=dhrec)
+            dc, dc2 = dc2, dc
+            if t > 0:
+                be.gemm(dg_op[t], w_t, dhrec if Sd > 1 else dhrec[0], splitk=Sd)
+        dw = None
+        if need_dw:
+            dw = la.mm(la.flat2(dg_op).t(), la.flat2(hin).t())      # sum_t dgates_t^T h_{t-1}  (hin[0] = 0)
+        return (dg32.transpose(0, 1) if need_dgin else None), dw
+
+
 def lstm(x, w_ih, w_hh, b_ih, b_hh):
     """Uni-directional nn.LSTM(batch_first) with zero initial state (model.py:152), differentiable twice."""
-    B, T, _ = x.shape
-    H = w_hh.shape[1]
-    gin = linear(x, w_ih, b_ih + b_hh)
-    h = x.new_zeros(B, H)
-    c = x.new_zeros(B, H)
-    outs = []
-    for t in range(T):
-        g = gin[:, t] + (bmm_nt(h, w_hh) if t > 0 else 0)
-        i, f, gg, o = torch.sigmoid(g[:, :H]), torch.sigmoid(g[:, H:2 * H]), tanh_(g[:, 2 * H:3 * H]), torch.sigmoid(g[:, 3 * H:])
-        c = f * c + i * gg
-        h = o * tanh_(c)
-        outs.append(h)
-    return torch.stack(outs, 1)
+    return _LstmSeq.apply(linear(x, w_ih, b_ih + b_hh), w_hh)
 
 
 def sum_dim1(x):

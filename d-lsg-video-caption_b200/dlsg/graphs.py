@@ -52,7 +52,7 @@ class GraphedTrainStep:
     def _body(self):
         self.opt.zero_grad(set_to_none=True)
         out = self.model(self.frames, self.regions, self.captions, self.max_words, self.tf)[0]
-        loss = losses.packed_cross_entropy(out, self.captions, self.lens, self.inv)
+        loss = losses.packed_cross_entropy(out, self.captions, self.lens, self.inv, unit_grad=True)
         if self.world > 1:
             # per-block flat buckets, all-reduced on a side stream as soon as each block's backward is done
             DF.GRAD_SYNC = self.sync

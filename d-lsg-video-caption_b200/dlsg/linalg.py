@@ -146,6 +146,73 @@ def op(t):
     return out
 
 
+# ---- memoised operands for the generic (autograd-composed) path -----------------------------------------------------
+# The discriminator path is thousands of small GEMMs whose operands are immutable autograd values and parameters; the
+# same tensor typically feeds several products (dy -> data gradient AND weight gradient; a weight -> forward, backward
+# and double backward).  op_cached() converts each once.  Entries hold a reference to the source tensor (so ids are
+# never reused while an entry lives) and are validated by tensor._version; parameter entries additionally carry an
+# epoch, bumped at the start of every top-level generic-path module forward, because fused optimizers update
+# parameters without bumping _version.
+import collections as _collections
+
+_PMEMO = {}
+_AMEMO = _collections.OrderedDict()
+_AMEMO_MAX = 32
+_EPOCH = [0]
+_SCOPE_DEPTH = [0]
+_MANUAL_EPOCH = [False]
+
+
+def new_param_epoch():
+    _EPOCH[0] += 1
+    _AMEMO.clear()
+
+
+def set_manual_param_epochs(flag):
+    """True: the caller (dlsg.gan.GanIteration) bumps the epoch itself right after each optimizer step, so a weight is
+    converted once per optimizer step instead of once per module forward."""
+    _MANUAL_EPOCH[0] = bool(flag)
+
+
+class param_epoch_scope:
+    def __enter__(self):
+        if _SCOPE_DEPTH[0] == 0 and not _MANUAL_EPOCH[0]:
+            new_param_epoch()
+        _SCOPE_DEPTH[0] += 1
+
+    def __exit__(self, *exc):
+        _SCOPE_DEPTH[0] -= 1
+        return False
+
+
+def op_cached(t):
+    """op() with memoisation - ONLY for tensors nobody writes in place through a raw pointer (autograd values of the
+    generic path, parameters)."""
+    if _PRECISION != 'bf16' or t.dtype == torch.bfloat16 or t.dim() < 2:
+        return op(t)
+    if t.stride(-1) != 1 and t.shape[-1] != 1 and t.stride(-2) == 1:
+        return op_cached(t.transpose(-1, -2)).transpose(-1, -2)      # one copy serves both orientations
+    root = t._base if t._base is not None else t
+    key = (id(root), t.data_ptr(), tuple(t.shape), tuple(t.stride()))
+    if isinstance(root, torch.nn.Parameter):
+        ver = (root._version, _EPOCH[0])
+        hit = _PMEMO.get(key)
+        if hit is not None and hit[0] is root and hit[1] == ver:
+            return hit[2]
+        out = op(t)
+        _PMEMO[key] = (root, ver, out)
+        return out
+    hit = _AMEMO.get(key)
+    if hit is not None and hit[0] is root and hit[1] == root._version:
+        _AMEMO.move_to_end(key)
+        return hit[2]
+    out = op(t)
+    _AMEMO[key] = (root, root._version, out)
+    while len(_AMEMO) > _AMEMO_MAX:
+        _AMEMO.popitem(last=False)
+    return out
+
+
 def _convert_into(t, out):
     be = ops.backend()
     if t.stride(-1) == 1 or t.shape[-1] == 1:
@@ -155,9 +222,10 @@ def _convert_into(t, out):
         be.convert(t.transpose(-1, -2), dstT=out)
 
 
-def mm(a, b, out=None, out_dtype=torch.float32, **epi):
-    """out = epi(a @ b^T); a (..,M,K), b (..,N,K).  Operands are made precision-appropriate via op()."""
-    a2, b2 = op(a), op(b)
+def mm(a, b, out=None, out_dtype=torch.float32, memo=False, **epi):
+    """out = epi(a @ b^T); a (..,M,K), b (..,N,K).  Operands are made precision-appropriate via op() (memo=True: via
+    op_cached(), generic path only)."""
+    a2, b2 = (op_cached(a), op_cached(b)) if memo else (op(a), op(b))
     if out is None:
         out = torch.empty(a.shape[:-1] + (b.shape[-2],), dtype=out_dtype, device=a.device)
     ops.backend().gemm(a2, b2, out, **epi)

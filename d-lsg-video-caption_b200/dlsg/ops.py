@@ -74,8 +74,9 @@ class CudaBackend:
 
     # ------------------------------------------------------------------ GEMM
     def gemm(self, a, b, out, bias=None, bias_axis='n', tanh=False, alpha=1.0, accum=False, splitk=1,
-             impl=None):
+             impl=None, atomic=False):
         """out[(batch,)M,N] = epi(alpha * a[(batch,)M,K] @ b[(batch,)N,K]^T + bias).
+        atomic=True: out += result through fp32 atomic adds (DLSG_EPI_ATOMIC): skinny problems split K with no reduce launch.
 
         `out` may be a transposed view (unit stride on M) -> STORE_T.  For splitk>1 `out` has a
         leading split dim: (splitk, M, N) and receives partial sums."""
@@ -111,6 +112,9 @@ class CudaBackend:
             flags |= L.EPI_TANH
         if accum:
             flags |= L.EPI_ACCUM
+        if atomic:
+            assert not accum and not tanh and splitk <= 1 and o2.dtype == torch.float32
+            flags |= L.EPI_ATOMIC
         g.A, g.B, g.D, g.bias = a2.data_ptr(), b2.data_ptr(), o2.data_ptr(), _ptr(bias)
         g.M, g.N, g.K, g.batch = M, N, K, batch
         g.sam, g.sak, g.sbn, g.sbk = a2.stride(0), a2.stride(1), b2.stride(0), b2.stride(1)
@@ -179,7 +183,9 @@ class CudaBackend:
         L.check(self.lib.dlsg_norm_fwd(C.byref(p), _stream()), 'dlsg_norm_fwd')
 
     def norm_bwd(self, dy, x, gamma, beta, stats, dx=None, res=None, dgamma=None, dbeta=None, pre_tanh=False,
-                 post_tanh=False, in_is_tanh=False, drop=None, dx_accum=False):
+                 post_tanh=False, in_is_tanh=False, drop=None, dx_accum=False, dxsum=None):
+        """dxsum (D) += column sums of dx (the bias gradient of the Linear that produced x): fused into the streaming bf16
+        kernel when the call is eligible, otherwise one extra colsum launch."""
         self._ck(x)
         p = L.NormBwdT()
         rows, D, p.ldx = _rows2d(x)
@@ -202,7 +208,12 @@ class CudaBackend:
         if drop is not None and drop[0] > 0:
             p.drop_p, p.seed, p.offset = drop
         self.launches += 1
+        fused_sum = dxsum is not None and self.lib.dlsg_norm_bwd_streaming(C.byref(p)) == 1
+        if fused_sum:
+            p.dxsum = dxsum.data_ptr()
         L.check(self.lib.dlsg_norm_bwd(C.byref(p), _stream()), 'dlsg_norm_bwd')
+        if dxsum is not None and not fused_sum:
+            self.colsum(dx, dxsum)
 
     # ------------------------------------------------------------------ LSTM cell
     def lstm_cell_fwd(self, gates, c_prev, c_out, h_out=None, row_bias=None, bias=None, h2=None, h3=None, drop=None):
@@ -261,6 +272,20 @@ class CudaBackend:
         self._fill_cell_bwd(p, acts, c_prev, c_new, dh, dc_next, dc_prev, dgates, dgates2, dgatesT, drop, dh2)
         self.launches += 1
         L.check(self.lib.dlsg_lstm_cell_bwd(C.byref(p), _stream()), 'dlsg_lstm_cell_bwd')
+
+    def lstm_cell_bwd2(self, acts, c_prev, c_new, dh, dc_next, u, w, g_dh, g_dc, g_pre, g_cprev):
+        """Backward of lstm_cell_bwd: cotangents u (of dgates) / w (of dc_prev) -> cotangents of dh, dc_next, the gate
+        pre-activations and c_prev.  Contiguous fp32 (B,H) / (B,4H); c_prev, dc_next, u, w and outputs may be None."""
+        self._ck(acts)
+        p = L.CellBwd2T()
+        for t_ in (acts, c_prev, c_new, dh, dc_next, u, w, g_dh, g_dc, g_pre, g_cprev):
+            assert t_ is None or (t_.is_contiguous() and t_.dtype == torch.float32)
+        p.B, p.H = acts.shape[0], acts.shape[1] // 4
+        p.acts, p.c_prev, p.c_new, p.dh, p.dc_next = acts.data_ptr(), _ptr(c_prev), c_new.data_ptr(), dh.data_ptr(), _ptr(dc_next)
+        p.u, p.w = _ptr(u), _ptr(w)
+        p.g_dh, p.g_dc, p.g_pre, p.g_cprev = _ptr(g_dh), _ptr(g_dc), _ptr(g_pre), _ptr(g_cprev)
+        self.launches += 1
+        L.check(self.lib.dlsg_lstm_cell_bwd2(C.byref(p), _stream()), 'dlsg_lstm_cell_bwd2')
 
     def norm_lstm_cell_bwd(self, acts, c_prev, c_new, dc_next, dc_prev, dy, x, gamma, beta, stats, dgamma, dbeta, dh=None, dh2=None,
                            dgates=None, dgates2=None, dgatesT=None, dgates_sum=None, drop=None, post_tanh=False, ydrop=None):

@@ -334,6 +334,7 @@ class _PSLBase(nn.Module):
 class PSLScore(_PSLBase):
     """Dead alternate (reference layer.py:605-658); same parameters as PSLScore2."""
 
+    @G.param_scope
     def forward(self, psl, psl_alpha, att_out, seq_mask):
         p, a, adj = self._common(psl, psl_alpha, att_out)
         adj = G.softmax(adj, dim=1, scale=1.0 / math.sqrt(512), mask=seq_mask, mask_mode=1)
@@ -344,6 +345,7 @@ class PSLScore(_PSLBase):
 
 
 class PSLScore2(_PSLBase):
+    @G.param_scope
     def forward(self, psl, psl_alpha, att_out, seq_mask):
         """layer.py:688-715 -> 0-dim scalar (batch mean of alpha-weighted node scores)."""
         p, a, adj = self._common(psl, psl_alpha, att_out)

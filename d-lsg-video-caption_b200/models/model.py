@@ -137,6 +137,7 @@ class DiscV2(nn.Module):
             nn.LeakyReLU(0.2)
         )
 
+    @G.param_scope
     def forward(self, inputs, obj_proposals, motion_proposals, att_mask=None, alpha_all=None):
         """inputs (B,L,V) one-hot / logits / mix -> score (B,)   (model.py:145-168)."""
         p = 0.3 if self.training else 0.0

@@ -36,6 +36,7 @@ class AttentionShare(nn.Module):
             nn.Dropout(self.dropout)
         )
 
+    @G.param_scope
     def forward(self, meta_state, hidden_previous):
         """(B,P,Dv),(B,Dk) -> (attention (B,out), weight (B,P,1)); softmax over the node axis."""
         K = G.linear(meta_state, self.K.weight)
@@ -65,6 +66,7 @@ class SelfAttention(nn.Module):
             nn.Dropout(self.dropout)
         )
 
+    @G.param_scope
     def forward(self, x, att_mask=None):
         if self.get_pe:
             x = self.pe(x)
@@ -92,6 +94,7 @@ class PositionalEncoding_old(nn.Module):
         pe = pe.unsqueeze(0)
         self.register_buffer('pe', pe)
 
+    @G.param_scope
     def forward(self, x):
         return G.add_pe(x, self.pe, self.dropout.p if self.training else 0.0)
 
@@ -104,6 +107,7 @@ class ResBlock(nn.Module):
             nn.Conv1d(dim, dim, 3, padding=1),
         )
 
+    @G.param_scope
     def forward(self, input):
         """input (B,dim,L).  The reference's in-place ReLU makes this relu(x) + 0.3*conv3(relu(x))."""
         conv = self.res_block[1]
@@ -119,6 +123,7 @@ class GNN(nn.Module):
         self.adj_K = nn.Linear(2048, 2048)
         self.graph_update = nn.Linear(2048, 1024)
 
+    @G.param_scope
     def forward(self, region_feats):
         bs, win_len, num_obj, fs = region_feats.shape
         feats = region_feats.contiguous().view(bs, win_len * num_obj, fs)
@@ -157,6 +162,7 @@ class LatentPSL(nn.Module):
             nn.Dropout(0.3)
         )
 
+    @G.param_scope
     def forward(self, input_seq, mask=None):
         adj = G.softmax(G.linear(input_seq, self.theta), dim=1)                   # (B,T,P) over the sequence axis
         out = G.bmm_nt(adj.transpose(1, 2), input_seq.transpose(1, 2))            # (B,P,d)
@@ -194,6 +200,7 @@ class JointEmbedVideoModel2(nn.Module):
         self.visual_embed = nn.Sequential(nn.Linear(hidden_size, hidden_size), nn.Tanh())
         self.sent_embed = nn.Sequential(nn.Linear(hidden_size, hidden_size), nn.Tanh())
 
+    @G.param_scope
     def forward(self, visual, sent):
         v = G.linear(visual, self.visual_embed[0].weight, self.visual_embed[0].bias, tanh=True)
         s = G.linear(sent, self.sent_embed[0].weight, self.sent_embed[0].bias, tanh=True)

@@ -45,7 +45,11 @@ enum {
   DLSG_EPI_BIAS_M = 2,   /* bias[m] added                                                      */
   DLSG_EPI_TANH = 4,     /* tanh after bias                                                    */
   DLSG_EPI_ACCUM = 8,    /* D += result                                                        */
-  DLSG_EPI_STORE_T = 16  /* store D^T: element (m,n) goes to D[n*ldd + m]                      */
+  DLSG_EPI_STORE_T = 16, /* store D^T: element (m,n) goes to D[n*ldd + m]                      */
+  DLSG_EPI_ATOMIC = 32   /* D += result through fp32 atomic adds (fp32 D, no tanh): DLSG_GEMM_TC may then split K  */
+                         /* over the idle SMs with no workspace and no reduce launch (D holds the addend, e.g.     */
+                         /* zeros).  The order in which the splits land is not fixed: last-bit run-to-run noise.   */
+                         /* DLSG_GEMM_SIMT treats it as DLSG_EPI_ACCUM.                                             */
 };
 typedef struct {
   const void* A; const void* B; void* D; const float* bias;
@@ -95,8 +99,11 @@ typedef struct {
   int64_t lddy, ldx, ldres, lddx;
   int32_t dy_dtype, x_dtype, res_dtype, dx_dtype;
   float drop_p; int32_t dx_accum; uint64_t seed, offset;
+  float* dxsum;   /* optional (D): column sums of dx, ACCUMULATED (+=) - the bias gradient of the Linear that produced x; */
+                  /* only the streaming bf16 form computes it (dlsg_norm_bwd_streaming(p) == 1), else it must be NULL   */
 } dlsg_norm_bwd_t;
 int dlsg_norm_bwd(const dlsg_norm_bwd_t* p, void* stream);
+int dlsg_norm_bwd_streaming(const dlsg_norm_bwd_t* p);   /* 1 if this call runs the streaming bf16 kernel (large bf16 x/dy/dx) */
 
 /* ---- LSTM cell pointwise (nn.LSTMCell / nn.LSTM step, gate order i,f,g,o) ------------------
  * layer.py:52,571,593, model.py:152.  gates: nsplit partial (B,4H) fp32 buffers (split-K GEMM
@@ -125,6 +132,18 @@ typedef struct {
   int32_t dh2_nsplit; int32_t _pad3; int64_t dh2_stride_split;   /* dh2 = sum of dh2_nsplit (<=1: one) split-K partial buffers */
 } dlsg_lstm_cell_bwd_t;
 int dlsg_lstm_cell_bwd(const dlsg_lstm_cell_bwd_t* p, void* stream);
+/* Backward of the cell backward (second-order term of the WGAN-GP gradient penalty through DiscV2.lstm,
+ * run_gun.py:362-375 over model.py:152).  The cell backward maps (dh, dc_next; pre-activations, c_prev) ->
+ * (dgates (B,4H), dc_prev); given cotangents u (B,4H) of dgates and w (B,H) of dc_prev (either may be NULL = 0)
+ * this returns the cotangents of dh, dc_next, the gate pre-activations (B,4H) and c_prev (outputs may be NULL).
+ * All tensors contiguous fp32.                                                                    */
+typedef struct {
+  const float* acts; const float* c_prev; const float* c_new; const float* dh; const float* dc_next;
+  const float* u; const float* w;
+  float* g_dh; float* g_dc; float* g_pre; float* g_cprev;
+  int32_t B, H;
+} dlsg_lstm_cell_bwd2_t;
+int dlsg_lstm_cell_bwd2(const dlsg_lstm_cell_bwd2_t* p, void* stream);
 
 /* ---- per-step fusions (one CTA per batch row, H <= 2048): cell + LayerNorm forward, LayerNorm + cell backward.
  * fwd: split-K partials/bias -> gates -> c,h (dropout on h) -> y = [tanh](LN(h)) (dropout on y); replaces

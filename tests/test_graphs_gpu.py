@@ -76,3 +76,45 @@ def test_graphed_train_step_matches_eager_step():
     for (k, p), (_, q) in zip(nets[0].named_parameters(), nets[1].named_parameters()):
         worst = max(worst, float((p - q).abs().max()))
     assert worst < 5e-3, worst
+
+
+def test_gan_iteration_graph_matches_eager_and_trains_the_critic():
+    """dlsg.gan.GanIteration (run_gun.py:147-234 + 339-398).  With num_d=0 the iteration is deterministic in eval mode
+    (no WGAN-GP epsilon draw): the captured graph must reproduce the eager losses over two iterations.  With the
+    critic steps on, the WGAN-GP double backward runs inside the capture, updates every critic parameter and keeps
+    all four logged scalars finite."""
+    import models.model as M
+    from dlsg.gan import GanIteration
+    la.set_precision('bf16')
+    args, V, B = synth.msr_args(), 1201, 4
+    frames, regions, caps, lens = synth.make_inputs(B, args, V, seed=35)
+    fr, rg, cp = frames.to(DEV), regions.to(DEV), caps.to(DEV)
+
+    def make():
+        G = _net(args, V).eval()
+        D = M.DiscV2(args, V)
+        synth.fill_state_dict(D, prefix='D.')
+        D = D.to(DEV).eval()
+        og = torch.optim.Adam(G.parameters(), lr=1.6e-4, betas=(0.5, 0.9), fused=True, capturable=True)
+        od = torch.optim.Adam(D.parameters(), lr=1.6e-4, betas=(0.5, 0.9), fused=True, capturable=True)
+        return G, D, og, od
+    G0, D0, og0, od0 = make()
+    eager = GanIteration(G0, D0, og0, od0, fr, rg, cp, lens, 26, 1.0, num_d=0, graph=False)
+    ref = [[float(x) for x in eager()[:2]] for _ in range(3)]
+    G1, D1, og1, od1 = make()
+    warm = GanIteration(G1, D1, og1, od1, fr, rg, cp, lens, 26, 1.0, num_d=0, graph=False)
+    first = [float(x) for x in warm()[:2]]                      # initialises the Adam state outside the capture
+    assert abs(first[0] - ref[0][0]) < 1e-5
+    gi = GanIteration(G1, D1, og1, od1, fr, rg, cp, lens, 26, 1.0, num_d=0, graph=True, warmup=0)
+    for k in (1, 2):
+        got = [float(x) for x in gi()[:2]]
+        assert abs(got[0] - ref[k][0]) < 5e-3 and abs(got[1] - ref[k][1]) < 5e-3, (k, got, ref[k])
+    # critic steps inside the capture
+    G2, D2, og2, od2 = make()
+    before = {k: p.detach().clone() for k, p in D2.named_parameters()}
+    gi = GanIteration(G2, D2, og2, od2, fr, rg, cp, lens, 26, 1.0, num_d=2, graph=True, warmup=1)
+    for _ in range(2):
+        vals = [float(x) for x in gi()]
+    assert all(v == v and abs(v) < 1e4 for v in vals), vals
+    moved = [k for k, p in D2.named_parameters() if not torch.equal(p, before[k])]
+    assert len(moved) == len(before), sorted(set(before) - set(moved))

@@ -144,6 +144,8 @@ def test_gemm_tc_auto_splitk_fixup(be, M, N, K):
         both('gemm', be, [a, b, R(M, N)], dict(accum=True), [2], tol=2e-3)
         both('gemm', be, [a, b, torch.zeros(M, N, dtype=torch.bfloat16)], dict(bias=bias_n), [2], tol=1e-2)
         both('gemm', be, [a, b, torch.zeros(N, M).t()], dict(bias=bias_n), [2], tol=2e-3)
+        both('gemm', be, [a, b, R(M, N)], dict(atomic=True, bias=bias_n), [2], tol=2e-3)     # split-K landing in D by atomic adds
+        both('gemm', be, [a, b, R(N, M).t()], dict(atomic=True), [2], tol=2e-3)
     ad, bd = a.to(DEV), b.to(DEV)
     outs = []
     for _ in range(4):
@@ -219,6 +221,17 @@ def test_norm_bf16_streaming(be, rows, D, Dpad):
         both('norm_bwd', be, [dy, t, gamma, beta, stats],
              dict(dx=torch.zeros(rows, D, dtype=torch.bfloat16), dgamma=torch.zeros(D), dbeta=torch.zeros(D), in_is_tanh=tanh_in),
              ['dgamma', 'dbeta'], tol=2e-3)
+        # fused column sums of dx (the producing Linear's bias gradient), accumulated onto existing values; the emulator
+        # sums the un-rounded fp32 dx, the kernel too (before the bf16 store)
+        both('norm_bwd', be, [dy, t, gamma, beta, stats],
+             dict(dx=torch.zeros(rows, D, dtype=torch.bfloat16), dgamma=torch.zeros(D), dbeta=torch.zeros(D), in_is_tanh=tanh_in,
+                  dxsum=R(D)), ['dgamma', 'dbeta', 'dxsum'], tol=2e-3)
+    # not eligible for the streaming form (fp32 dx): the wrapper adds a colsum launch instead
+    x32 = R(64, D)
+    st32 = torch.zeros(64, 2)
+    EM.norm_fwd(x32, gamma, beta, stats=st32)
+    both('norm_bwd', be, [R(64, D), x32, gamma, beta, st32], dict(dx=torch.zeros(64, D), dgamma=torch.zeros(D), dbeta=torch.zeros(D),
+                                                                  dxsum=R(D)), ['dx', 'dxsum'], tol=1e-4)
 
 
 def test_norm_strided_slices(be):
@@ -247,6 +260,21 @@ def test_lstm_cell(be, H):
     kw = dict(dgates=torch.zeros(B_, 4 * H), dgates2=torch.zeros(B_, 4 * H + 16, dtype=torch.bfloat16)[:, :4 * H],
               dgatesT=torch.zeros(4 * H, 5 * B_)[:, 2 * B_:3 * B_], dh2=R(B_, 3 * H)[:, H:2 * H])
     both('lstm_cell_bwd', be, [acts, c_prev, c_new, R(B_, 2 * H)[:, :H], R(B_, H), torch.zeros(B_, H)], kw, [5, 'dgates', 'dgatesT'], tol=1e-5)
+
+
+@pytest.mark.parametrize('H', [64, 512])
+@pytest.mark.parametrize('nulls', [False, True])
+def test_lstm_cell_double_backward(be, H, nulls):
+    """Closed-form backward-of-backward kernel against automatic differentiation of the restated cell backward."""
+    B_ = 6
+    gates = R(1, B_, 4 * H)
+    c_prev = R(B_, H)
+    c_new = torch.zeros(B_, H)
+    EM.lstm_cell_fwd(gates, c_prev, c_new)
+    acts = gates[0].contiguous()
+    outs = [torch.zeros(B_, H), torch.zeros(B_, H), torch.zeros(B_, 4 * H), torch.zeros(B_, H)]
+    args = [acts, c_prev, c_new, R(B_, H), None if nulls else R(B_, H), R(B_, 4 * H), None if nulls else R(B_, H)] + outs
+    both('lstm_cell_bwd2', be, args, {}, [7, 8, 9, 10], tol=2e-5)
 
 
 @pytest.mark.parametrize('H,post', [(64, False), (1024, False), (1536, True)])

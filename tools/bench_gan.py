@@ -30,6 +30,9 @@ def main():
     ap.add_argument('--num-d', type=int, default=5)          # opt.py:36 num_D_visual
     ap.add_argument('--vocab', type=int, default=10547)
     ap.add_argument('--phases', action='store_true', help='also time G-fwd / D-loop / G-step separately (extra syncs)')
+    ap.add_argument('--graph', type=int, default=0, help='1: dlsg.gan.GanIteration captured as one CUDA graph')
+    ap.add_argument('--profile-dstep', action='store_true', help='warm up, then run ONE eager discriminator step inside '
+                    'cudaProfilerStart/Stop and exit (ncu --profile-from-start off)')
     a = ap.parse_args()
     from dlsg import synth, losses, ops, linalg as la
     import models.model as M
@@ -41,8 +44,9 @@ def main():
     with contextlib.redirect_stdout(io.StringIO()):
         G = M.CapGnnModel(args, synth.Vocab(V)).to(dev).train()
         D = M.DiscV2(args, V).to(dev).train()
-    opt_g = torch.optim.Adam(G.parameters(), lr=1.6e-4, betas=(0.5, 0.9), fused=True)     # run_gun.py:91
-    opt_d = torch.optim.Adam(D.parameters(), lr=1.6e-4, betas=(0.5, 0.9), fused=True)     # run_gun.py:100
+    cap = bool(a.graph)
+    opt_g = torch.optim.Adam(G.parameters(), lr=1.6e-4, betas=(0.5, 0.9), fused=True, capturable=cap)     # run_gun.py:91
+    opt_d = torch.optim.Adam(D.parameters(), lr=1.6e-4, betas=(0.5, 0.9), fused=True, capturable=cap)     # run_gun.py:100
     frames, regions, caps, lens = synth.make_inputs(B, args, V, seed=12)
     frames, regions, caps = frames.to(dev), regions.to(dev), caps.to(dev)
     att_mask = synth.att_mask_from_captions(caps).to(dev)
@@ -92,6 +96,23 @@ def main():
 
     import random
     random.seed(12)
+    if a.profile_dstep:
+        iteration()
+        with torch.no_grad():
+            f_cap, obj, mot, alpha = G(frames, regions, caps, L, eps_tf)
+        real = torch.zeros(B, L, V, device=dev).scatter_(2, caps.unsqueeze(2), 1)
+        a.num_d = 1
+        train_disc(real, f_cap, obj, mot, alpha)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        train_disc(real, f_cap, obj, mot, alpha)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+    if a.graph:
+        from dlsg.gan import GanIteration
+        it = GanIteration(G, D, opt_g, opt_d, frames, regions, caps, lens, L, eps_tf, a.num_d, lam, graph=True)
+        iteration = lambda: it()[0]
     for _ in range(a.warmup):
         iteration()
     torch.cuda.synchronize()
@@ -106,7 +127,7 @@ def main():
     ms = e0.elapsed_time(e1) / a.steps
     line = {'metric': 'GAN iteration (G fwd + %d x D step with WGAN-GP + G step), B=%d MSR-VTT-shaped' % (a.num_d, B),
             'ms_per_iteration': ms, 'clips_per_s': B / (ms * 1e-3), 'steps': a.steps, 'warmup': a.warmup,
-            'libdlsg_launches_per_iteration': (be.launches - l0) // a.steps, 'loss': float(loss), 'mode': 'eager'}
+            'libdlsg_launches_per_iteration': (it.launches if a.graph else (be.launches - l0) // a.steps), 'loss': float(loss), 'mode': 'cuda_graph' if a.graph else 'eager'}
     if a.phases:
         ph = {}
         for (n0, ev0), (n1, ev1) in zip(marks[:-1], marks[1:]):
