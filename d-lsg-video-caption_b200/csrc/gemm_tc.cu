@@ -18,7 +18,8 @@ constexpr int BM = 128;
 constexpr int BK = 64;           // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
 constexpr int TC_THREADS = 192;
-constexpr int EPI_PAD = 33;
+constexpr int EPI_PAD = 33;      // scalar staging pitch (conflict-free 4-byte accesses)
+constexpr int EPI_PADV = 36;     // vector staging pitch (16-byte aligned rows, conflict-free 16-byte accesses)
 constexpr int MN_BLOCK_BYTES = 64 * BK * 2;   // one 64(MN) x 64(K) bf16 box of an MN-major operand
 
 struct TcParams {
@@ -121,7 +122,7 @@ template <int BN> struct TcCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_BYTES = 4 * 32 * EPI_PAD * 4;
+  static constexpr int EPI_BYTES = 4 * 32 * EPI_PADV * 4;
   static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;  // +1024 alignment slack
   static constexpr int ACC_COLS = BN < 32 ? 32 : BN;                          // one accumulator stage
   static constexpr int TMEM_COLS = 2 * ACC_COLS;                              // double-buffered (<= 512)
@@ -256,7 +257,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ===== epilogue warps =====
     const int g = warp & 3;                                // TMEM lane quarter this warp may access
-    float* st = epi + (warp - 2) * 32 * EPI_PAD;
+    float* st = epi + (warp - 2) * 32 * EPI_PADV;
     uint8_t* Dbase = reinterpret_cast<uint8_t*>(prm.D);
     const bool bf16_out = prm.d_dtype != DLSG_F32;
     // packed bf16x2 stores need 4-byte aligned pairs
@@ -265,6 +266,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool plain_f32 = !bf16_out && !prm.accum && !prm.do_tanh && !prm.atomic;   // fp32 store, nothing else: the per-step GEMMs
     const bool atomic_f32 = prm.atomic != 0;                            // (host guarantees fp32 D, no tanh)
     const bool accum_f32 = !bf16_out && prm.accum && !prm.do_tanh;      // D += ...: all 32 loads in flight before the first store
+    // 16-byte row stores (lanes cover 64 B (bf16) / 128 B (fp32) contiguous per row, 8 / 4 rows per instruction)
+    const bool al16 = (reinterpret_cast<uintptr_t>(prm.D) & 15) == 0;
+    const bool bias16 = prm.bias == nullptr || (reinterpret_cast<uintptr_t>(prm.bias) & 15) == 0;
+    const bool vec_bf16 = !prm.store_t && bf16_out && !prm.accum && !prm.atomic && al16 && bias16 && (prm.ldd % 8 == 0) &&
+                          ((prm.stride_d | prm.stride_split) % 8 == 0);
+    const bool vec_f32 = !prm.store_t && !bf16_out && !prm.do_tanh && !prm.atomic && al16 && bias16 && (prm.ldd % 4 == 0) &&
+                         ((prm.stride_d | prm.stride_split) % 4 == 0);
     int acc = 0; uint32_t acc_ph = 0;
     for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
       const int tn = tile % ntn, tm = (tile / ntn) % ntm, z = tile / (ntn * ntm);
@@ -361,6 +369,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
+        } else if ((vec_bf16 || vec_f32) && qn == 32) {
+          // element (p,q) -> D[p*ldd + q], full 32-column chunk, 16-byte aligned rows: stage through smem with
+          // 16-byte accesses and store 16 bytes per lane
+          {
+            float4* s4 = reinterpret_cast<float4*>(st + lane * EPI_PADV);
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) s4[jj] = make_float4(f[4 * jj], f[4 * jj + 1], f[4 * jj + 2], f[4 * jj + 3]);
+          }
+          __syncwarp();
+          if (vec_bf16) {
+            const int cg = (lane & 3) * 8, rsel = lane >> 2;
+            float bq[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) bq[u] = 0.f;
+            if (add_bias && prm.bias_mode == 2) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(prm.bias + qb + cg));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(prm.bias + qb + cg + 4));
+              bq[0] = b0.x; bq[1] = b0.y; bq[2] = b0.z; bq[3] = b0.w; bq[4] = b1.x; bq[5] = b1.y; bq[6] = b1.z; bq[7] = b1.w;
+            }
+            __nv_bfloat16* dbase = reinterpret_cast<__nv_bfloat16*>(Dbase) + doff + (int64_t)pb * prm.ldd + qb + cg;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int r = it * 8 + rsel;
+              const float4 a0 = *reinterpret_cast<const float4*>(st + r * EPI_PADV + cg);
+              const float4 a1 = *reinterpret_cast<const float4*>(st + r * EPI_PADV + cg + 4);
+              float x[8] = {a0.x + bq[0], a0.y + bq[1], a0.z + bq[2], a0.w + bq[3], a1.x + bq[4], a1.y + bq[5], a1.z + bq[6], a1.w + bq[7]};
+              if (prm.do_tanh) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = tanh_fast(x[u]);
+              }
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(x[0], x[1]), h1 = __floats2bfloat162_rn(x[2], x[3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(x[4], x[5]), h3 = __floats2bfloat162_rn(x[6], x[7]);
+              uint4 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+              if (r < pn) *reinterpret_cast<uint4*>(dbase + (int64_t)r * prm.ldd) = pk;
+            }
+          } else {
+            const int cg = (lane & 7) * 4, rsel = lane >> 3;
+            float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (add_bias && prm.bias_mode == 2) bq = __ldg(reinterpret_cast<const float4*>(prm.bias + qb + cg));
+            float* dbase = reinterpret_cast<float*>(Dbase) + doff + (int64_t)pb * prm.ldd + qb + cg;
+            float4 o[8];
+            if (prm.accum) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int r = it * 4 + rsel;
+                o[it] = (r < pn) ? *reinterpret_cast<const float4*>(dbase + (int64_t)r * prm.ldd) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + rsel;
+              float4 a = *reinterpret_cast<const float4*>(st + r * EPI_PADV + cg);
+              a.x += bq.x; a.y += bq.y; a.z += bq.z; a.w += bq.w;
+              if (prm.accum) { a.x += o[it].x; a.y += o[it].y; a.z += o[it].z; a.w += o[it].w; }
+              if (r < pn) *reinterpret_cast<float4*>(dbase + (int64_t)r * prm.ldd) = a;
+            }
+          }
+          __syncwarp();
         } else {
           // element (p,q) -> D[p*ldd + q]: transpose through smem so lanes walk q
 #pragma unroll

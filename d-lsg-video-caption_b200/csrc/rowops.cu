@@ -540,6 +540,55 @@ lstm_cell_bwd_kernel(const dlsg_lstm_cell_bwd_t p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------- multi-segment convert
+// One launch refreshes every GEMM-operand copy of the parameters after an optimizer step: a device table of 2-D
+// segments dst[r,c] = cast(src[r,c] (+ src2[r,c])) (fp32 sources; bf16 or fp32 destinations with their own pitch: row
+// slices of stacked weights, column segments of the packed LSTM gate matrices, summed bias pairs) and a table of
+// (segment, first row, rows) chunks of ~16K elements, one CTA each.
+__global__ void __launch_bounds__(256)
+multi_convert_kernel(const dlsg_seg_t* __restrict__ segs, const int32_t* __restrict__ chunks) {
+  pdl_prologue();
+  const dlsg_seg_t sg = segs[chunks[3 * blockIdx.x]];
+  const int64_t row0 = chunks[3 * blockIdx.x + 1];
+  const int nrows = chunks[3 * blockIdx.x + 2];
+  const float* src = static_cast<const float*>(sg.src) + row0 * sg.ld_src;
+  const float* src2 = sg.src2 ? static_cast<const float*>(sg.src2) + row0 * sg.ld_src : nullptr;
+  const bool bf = sg.dst_dtype == DLSG_BF16;
+  const bool vec = (sg.cols % 4 == 0) && (sg.ld_src % 4 == 0) && (sg.ld_dst % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(sg.src) & 15) == 0) && (!sg.src2 || (reinterpret_cast<uintptr_t>(sg.src2) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(sg.dst) & (bf ? 7 : 15)) == 0);
+  if (vec) {
+    const int c4 = (int)(sg.cols >> 2);
+    const int64_t n = (int64_t)nrows * c4;
+    for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
+      const int64_t r = e / c4;
+      const int c = (int)(e % c4) * 4;
+      float4 v = *reinterpret_cast<const float4*>(src + r * sg.ld_src + c);
+      if (src2) {
+        const float4 w = *reinterpret_cast<const float4*>(src2 + r * sg.ld_src + c);
+        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+      }
+      if (bf) {
+        __nv_bfloat16* d = static_cast<__nv_bfloat16*>(sg.dst) + (row0 + r) * sg.ld_dst + c;
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(d) = pk;
+      } else {
+        *reinterpret_cast<float4*>(static_cast<float*>(sg.dst) + (row0 + r) * sg.ld_dst + c) = v;
+      }
+    }
+  } else {
+    const int64_t n = (int64_t)nrows * sg.cols;
+    for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
+      const int64_t r = e / sg.cols, c = e % sg.cols;
+      float v = src[r * sg.ld_src + c];
+      if (src2) v += src2[r * sg.ld_src + c];
+      st_from_float(sg.dst, sg.dst_dtype, (row0 + r) * sg.ld_dst + c, v);
+    }
+  }
+}
+
 // Backward OF the cell backward (WGAN-GP double backward through the discriminator LSTM, run_gun.py:362-375).
 // The cell backward maps (dh, dc; a=pre-activations, c0) -> (dpre[4], dc0) with D = dh*o*(1-tc^2) + dc:
 //   dpre_i = D*g*i(1-i)  dpre_f = D*c0*f(1-f)  dpre_g = D*i*(1-g^2)  dpre_o = dh*tc*o(1-o)  dc0 = D*f .
@@ -816,6 +865,13 @@ int dlsg_lstm_cell_bwd(const dlsg_lstm_cell_bwd_t* p, void* stream) {
   DLSG_REQUIRE(p->B > 0 && p->H > 0, "lstm_cell_bwd: bad shape");
   DLSG_LAUNCH(lstm_cell_bwd_kernel, ew_blocks((int64_t)p->B * p->H), 256, 0, (cudaStream_t)stream, *p);
   return check_launch("lstm_cell_bwd_kernel");
+}
+
+int dlsg_multi_convert(const dlsg_seg_t* segs_dev, const int32_t* chunks_dev, int32_t nchunks, void* stream) {
+  if (nchunks <= 0) return 0;
+  DLSG_REQUIRE(segs_dev && chunks_dev, "multi_convert: null tables");
+  DLSG_LAUNCH(multi_convert_kernel, (unsigned)nchunks, 256, 0, (cudaStream_t)stream, segs_dev, chunks_dev);
+  return check_launch("multi_convert_kernel");
 }
 
 int dlsg_lstm_cell_bwd2(const dlsg_lstm_cell_bwd2_t* p, void* stream) {

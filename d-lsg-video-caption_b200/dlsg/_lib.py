@@ -59,6 +59,11 @@ class CellBwdT(C.Structure):
                 ('dh2_nsplit', i32), ('_pad3', i32), ('dh2_stride_split', i64)]
 
 
+class SegT(C.Structure):
+    _fields_ = [('src', vp), ('src2', vp), ('dst', vp), ('rows', i64), ('cols', i64), ('ld_src', i64), ('ld_dst', i64),
+                ('src_dtype', i32), ('dst_dtype', i32)]
+
+
 class CellBwd2T(C.Structure):
     _fields_ = [('acts', vp), ('c_prev', vp), ('c_new', vp), ('dh', vp), ('dc_next', vp), ('u', vp), ('w', vp),
                 ('g_dh', vp), ('g_dc', vp), ('g_pre', vp), ('g_cprev', vp), ('B', i32), ('H', i32)]
@@ -127,6 +132,7 @@ SIGNATURES = {
     'dlsg_gemm': (i32, [C.POINTER(GemmT), vp]),
     'dlsg_convert2d': (i32, [vp, i32, i64, vp, i32, i64, vp, i64, i64, i64, vp]),
     'dlsg_convert2d_batched': (i32, [vp, i32, i64, vp, i32, i64, vp, i64, i64, i64, i64, i64, i64, i64, vp]),
+    'dlsg_multi_convert': (i32, [vp, vp, i32, vp]),
     'dlsg_colsum': (i32, [vp, i32, i64, i64, i64, vp, vp]),
     'dlsg_norm_fwd': (i32, [C.POINTER(NormFwdT), vp]),
     'dlsg_norm_bwd': (i32, [C.POINTER(NormBwdT), vp]),

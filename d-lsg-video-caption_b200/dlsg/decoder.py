@@ -66,27 +66,25 @@ class DecoderCore:
             ref = g('query_lstm.weight_ih')
             wih, whh = g('query_lstm.weight_ih'), g('query_lstm.weight_hh')
             Wq = op_zeros((4 * Hq,), self.Kq, ref)
-            be.convert(wih[:, :Hd], dst=Wq[:, :Hd])
-            be.convert(wih[:, Hd + GH:], dst=Wq[:, self.oW:self.oW + W])
-            be.convert(whh, dst=Wq[:, self.oQ:])
+            WC.cv(wih[:, :Hd], Wq[:, :Hd])
+            WC.cv(wih[:, Hd + GH:], Wq[:, self.oW:self.oW + W])
+            WC.cv(whh, Wq[:, self.oQ:])
             Wg = op_empty((4 * Hq,), GH, ref)
-            be.convert(wih[:, Hd:Hd + GH], dst=Wg)
+            WC.cv(wih[:, Hd:Hd + GH], Wg)
             bq = empty((4 * Hq,), ref)
-            be.axpby(g('query_lstm.bias_ih'), 1.0, bq, 0.0)
-            be.axpby(g('query_lstm.bias_hh'), 1.0, bq, 1.0)
+            WC.sum2(g('query_lstm.bias_ih'), g('query_lstm.bias_hh'), bq)
             lih, lhh = g('lang_lstm.weight_ih'), g('lang_lstm.weight_hh')
             Wl = op_zeros((4 * Hd,), self.Kl, ref)
-            be.convert(lih[:, :nh * H], dst=Wl[:, :nh * H])
-            be.convert(lih[:, nh * H:], dst=Wl[:, self.oq:self.oq + Hq])
-            be.convert(lhh, dst=Wl[:, self.ol:])
+            WC.cv(lih[:, :nh * H], Wl[:, :nh * H])
+            WC.cv(lih[:, nh * H:], Wl[:, self.oq:self.oq + Hq])
+            WC.cv(lhh, Wl[:, self.ol:])
             bl = empty((4 * Hd,), ref)
-            be.axpby(g('lang_lstm.bias_ih'), 1.0, bl, 0.0)
-            be.axpby(g('lang_lstm.bias_hh'), 1.0, bl, 1.0)
+            WC.sum2(g('lang_lstm.bias_ih'), g('lang_lstm.bias_hh'), bl)
             Wqp = op_empty((nh * H,), Hq, ref)
             Wo = op_empty((nh, H), H, ref)
             for i, h in enumerate(heads):
-                be.convert(g(h + '.Q.weight'), dst=Wqp[i * H:(i + 1) * H])
-                be.convert(g(h + '.output_layer.0.weight'), dst=Wo[i])
+                WC.cv(g(h + '.Q.weight'), Wqp[i * H:(i + 1) * H])
+                WC.cv(g(h + '.output_layer.0.weight'), Wo[i])
             d = dict(Wq=Wq, Wg=Wg, bq=bq, Wl=Wl, bl=bl, Wqp=Wqp, Wo=Wo)
             return d
         self.pk = WC.packed(('dec', id(t[pf + 'query_lstm.weight_ih'])), None, la.pver(*ps), build)

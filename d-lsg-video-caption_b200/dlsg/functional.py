@@ -165,8 +165,8 @@ class TunBlock:
                 Wc = op_empty((E * H,), Dr, R2)
                 bc = empty((E * H,), R2)
                 for i, (w, b) in enumerate(zip(ws, bs)):
-                    be.convert(w.detach(), dst=Wc[i * H:(i + 1) * H])
-                    be.convert(b.detach().view(1, H), dst=bc[i * H:(i + 1) * H].view(1, H))
+                    WC.cv(w.detach(), Wc[i * H:(i + 1) * H])
+                    WC.cv(b.detach().view(1, H), bc[i * H:(i + 1) * H].view(1, H))
                 return Wc, bc
             Wc, bc = WC.packed(('tunW',) + tuple(id(w) for w in ws), ws, la.pver(*ws, *bs), build)
             Ot = empty((M, E * H), R2, la.opdtype())
@@ -357,13 +357,11 @@ class EncoderVisualBlock:
 
         def build():
             Wih = op_empty((2 * H4,), H, wf)
-            be.convert(wf.detach(), dst=Wih[:H4])
-            be.convert(wr.detach(), dst=Wih[H4:])
+            WC.cv(wf.detach(), Wih[:H4])
+            WC.cv(wr.detach(), Wih[H4:])
             bsum = empty((2 * H4,), wf)
-            be.axpby(bs[0].detach(), 1.0, bsum[:H4], 0.0)
-            be.axpby(bs[1].detach(), 1.0, bsum[:H4], 1.0)
-            be.axpby(bs[2].detach(), 1.0, bsum[H4:], 0.0)
-            be.axpby(bs[3].detach(), 1.0, bsum[H4:], 1.0)
+            WC.sum2(bs[0].detach(), bs[1].detach(), bsum[:H4])
+            WC.sum2(bs[2].detach(), bs[3].detach(), bsum[H4:])
             return Wih, bsum
         return WC.packed(('evW', id(wf)), None, la.pver(wf, wr, *bs), build)
 
@@ -420,7 +418,7 @@ class EncoderVisualBlock:
         def build():
             W = op_empty((3 * D2,), D2, wk)
             for j, w in enumerate((wk, wq, wv)):
-                be.convert(w.detach(), dst=W[j * D2:(j + 1) * D2])
+                WC.cv(w.detach(), W[j * D2:(j + 1) * D2])
             return W
         Wkqv = WC.packed(('evKQV', id(wk)), None, la.pver(wk, wq, wv), build)
         Ypo = op(Ype)

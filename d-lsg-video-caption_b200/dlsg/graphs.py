@@ -15,7 +15,7 @@ from . import losses
 
 class GraphedTrainStep:
     def __init__(self, model, optimizer, frames, regions, captions, cap_lens, max_words=26, tf_ratio=1.0,
-                 process_group=None, warmup=3):
+                 process_group=None, warmup=3, pin_weights=True):
         dev = frames.device
         self.model, self.opt, self.pg = model, optimizer, process_group
         self.frames, self.regions, self.captions = frames.clone(), regions.clone(), captions.clone()
@@ -24,6 +24,7 @@ class GraphedTrainStep:
         self.max_words, self.tf = max_words, tf_ratio
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.world = 1
+        self.pinned = None
         if process_group is not None:
             import torch.distributed as dist
             self.dist = dist
@@ -36,6 +37,7 @@ class GraphedTrainStep:
                 self._body()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        self.pinned = self._record_weight_copies() if pin_weights else None
         self.graph = torch.cuda.CUDAGraph()
         self.opt.zero_grad(set_to_none=True)
         DF.WC.force = True
@@ -49,17 +51,39 @@ class GraphedTrainStep:
         self.launches = ops.backend().launches - l0          # libdlsg kernels recorded in one replay
         torch.cuda.synchronize()
 
+    def _record_weight_copies(self):
+        """One dry forward (nothing is updated; the host RNG / dropout seed counter are restored) that logs every weight
+        conversion of a training forward, so the captured step refreshes ALL bf16 operand copies with ONE multi-segment
+        launch (dlsg_multi_convert) instead of ~90 small conversion kernels."""
+        import copy
+        import random
+        rng = random.getstate()
+        counter = copy.copy(DF._seed_counter)
+        try:
+            with torch.enable_grad():
+                pinned = DF.WC.record(lambda: self.model(self.frames, self.regions, self.captions, self.max_words, self.tf))
+        finally:
+            random.setstate(rng)
+            DF._seed_counter = counter
+        return pinned
+
     def _body(self):
         self.opt.zero_grad(set_to_none=True)
-        out = self.model(self.frames, self.regions, self.captions, self.max_words, self.tf)[0]
-        loss = losses.packed_cross_entropy(out, self.captions, self.lens, self.inv, unit_grad=True)
-        if self.world > 1:
-            # per-block flat buckets, all-reduced on a side stream as soon as each block's backward is done
-            DF.GRAD_SYNC = self.sync
+        if self.pinned is not None:
+            self.pinned.refresh()                 # current fp32 masters -> every operand copy, one launch
+            DF.WC.pin(self.pinned)
         try:
-            loss.backward()
+            out = self.model(self.frames, self.regions, self.captions, self.max_words, self.tf)[0]
+            loss = losses.packed_cross_entropy(out, self.captions, self.lens, self.inv, unit_grad=True)
+            if self.world > 1:
+                # per-block flat buckets, all-reduced on a side stream as soon as each block's backward is done
+                DF.GRAD_SYNC = self.sync
+            try:
+                loss.backward()
+            finally:
+                DF.GRAD_SYNC = None
         finally:
-            DF.GRAD_SYNC = None
+            DF.WC.unpin()
         if self.world > 1:
             self.sync.wait()
         self.opt.step()

@@ -256,6 +256,42 @@ class WeightCache:
         self.force = False      # True while a CUDA graph is being captured: refresh kernels must be recorded every time
         self.gen = 0
         self.scope = ('eval', 0)
+        self._rec = None        # list of (src, src2, dst) while a forward is being recorded (record())
+        self._pinned = None     # PinnedWeights in effect: lookups are served from its snapshot, no conversion launches
+
+    # ---- conversions that can be recorded and later replayed as ONE multi-segment launch ---------------------------
+    def cv(self, src, dst):
+        """dst = cast(src) for a 2-D parameter view (the only way the cache builders convert weights)."""
+        ops.backend().convert(src, dst=dst)
+        if self._rec is not None:
+            self._rec.append((src, None, dst))
+
+    def sum2(self, a, b, dst):
+        """dst = a + b (fp32 vectors: the two LSTM bias vectors, summed once per weight update)."""
+        be = ops.backend()
+        be.axpby(a, 1.0, dst, 0.0)
+        be.axpby(b, 1.0, dst, 1.0)
+        if self._rec is not None:
+            self._rec.append((a.view(1, -1), b.view(1, -1), dst.view(1, -1)))
+
+    def record(self, fn):
+        """Run fn() (a training forward) with a cleared cache, logging every weight conversion and the cache entries it
+        creates; returns a PinnedWeights that can refresh all of them in one launch."""
+        assert self._pinned is None and self._rec is None
+        self._c.clear()
+        self._rec = []
+        try:
+            fn()
+            rec, snap = self._rec, dict(self._c)
+        finally:
+            self._rec = None
+        return PinnedWeights(rec, snap)
+
+    def pin(self, pinned):
+        self._pinned = pinned
+
+    def unpin(self):
+        self._pinned = None
 
     def begin_train_block(self):
         self.gen += 1
@@ -275,18 +311,26 @@ class WeightCache:
         if transpose:
             return self.get(w, key=key).t()         # MN-major view of the same bf16 copy (read in place by the GEMM)
         k = (id(w) if key is None else key, False)
+        if self._pinned is not None:
+            hit = self._pinned.snap.get(k)
+            if hit is not None and hit[0][1] == w.data_ptr():
+                return hit[1]
         ver = (w._version, w.data_ptr(), tuple(w.shape), self.scope)
         hit = self._c.get(k)
         if hit is not None and hit[0] == ver and not self.force:
             return hit[1]
         src = w.detach()
         out = op_empty((src.shape[0],), src.shape[1], src)
-        ops.backend().convert(src, dst=out)
+        self.cv(src, out)
         self._c[k] = (ver, out)
         return out
 
     def packed(self, key, parts, versions, builder):
         """Cache an arbitrary packed operand (e.g. concatenated LSTM weights) keyed on part versions."""
+        if self._pinned is not None:
+            hit = self._pinned.snap.get(key)
+            if hit is not None and hit[0][0] == _PRECISION and tuple(v[1] for v in hit[0][2:]) == tuple(v[1] for v in versions):
+                return hit[1]
         ver = (_PRECISION, self.scope) + tuple(versions)
         hit = self._c.get(key)
         if hit is not None and hit[0] == ver and not self.force:
@@ -297,6 +341,21 @@ class WeightCache:
 
     def clear(self):
         self._c.clear()
+
+
+class PinnedWeights:
+    """Snapshot of the operand copies one training forward uses, plus the conversion list that produced them: refresh()
+    re-runs ALL of them as one multi-segment launch (after an optimizer step / before the next forward).  While pinned
+    (WeightCache.pin) the blocks are served these buffers and launch no conversion of their own."""
+
+    def __init__(self, rec, snap):
+        self.snap = snap
+        self.pairs = [(s_.detach(), (s2.detach() if s2 is not None else None), d) for s_, s2, d in rec]
+        self.plan = ops.backend().make_convert_plan(self.pairs) if self.pairs else None
+
+    def refresh(self):
+        if self.plan is not None:
+            ops.backend().multi_convert(self.plan)
 
 
 def pver(*params):

@@ -151,6 +151,40 @@ class CudaBackend:
             _ptr(t2), t2.stride(0) if t2 is not None else 0, rows, cols, batch, bs[0], bs[1], bs[2], _stream()),
             'dlsg_convert2d')
 
+    def make_convert_plan(self, pairs, chunk_elems=16384):
+        """pairs: list of (src, src2 | None, dst) 2-D tensor views (fp32 sources with one common pitch per pair, unit
+        inner strides).  Returns a plan (device tables + references that keep the buffers alive) for multi_convert()."""
+        import numpy as np
+        segs = (L.SegT * max(1, len(pairs)))()
+        chunks = []
+        keep = []
+        for i, (src, src2, dst) in enumerate(pairs):
+            assert src.dim() == 2 and dst.shape == src.shape and src.dtype == torch.float32, (src.shape, dst.shape, src.dtype)
+            assert (src.stride(1) == 1 or src.shape[1] == 1) and (dst.stride(1) == 1 or dst.shape[1] == 1)
+            rows, cols = src.shape
+            sg = segs[i]
+            sg.src, sg.dst, sg.rows, sg.cols = src.data_ptr(), dst.data_ptr(), rows, cols
+            sg.ld_src, sg.ld_dst = (src.stride(0) if rows > 1 else cols), (dst.stride(0) if rows > 1 else cols)
+            sg.src_dtype, sg.dst_dtype = _dt(src), _dt(dst)
+            if src2 is not None:
+                assert src2.shape == src.shape and src2.dtype == torch.float32 and (rows == 1 or src2.stride(0) == src.stride(0))
+                sg.src2 = src2.data_ptr()
+            per = max(1, chunk_elems // max(1, cols))
+            for r0 in range(0, rows, per):
+                chunks.append((i, r0, min(per, rows - r0)))
+            keep.append((src, src2, dst))
+        dev = pairs[0][0].device
+        seg_t = torch.from_numpy(np.frombuffer(bytes(segs), dtype=np.uint8).copy()).to(dev)
+        chunk_t = torch.tensor(chunks, dtype=torch.int32).reshape(-1).to(dev)
+        return {'segs': seg_t, 'chunks': chunk_t, 'n': len(chunks), 'keep': keep}
+
+    def multi_convert(self, plan):
+        if plan['n'] == 0:
+            return
+        self.launches += 1
+        L.check(self.lib.dlsg_multi_convert(plan['segs'].data_ptr(), plan['chunks'].data_ptr(), plan['n'], _stream()),
+                'dlsg_multi_convert')
+
     def colsum(self, x, out):
         rows, cols, ld = _rows2d(x)
         self.launches += 1

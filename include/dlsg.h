@@ -72,6 +72,16 @@ int dlsg_convert2d(const void* src, int src_dtype, int64_t ld_src, void* dst, in
 int dlsg_convert2d_batched(const void* src, int src_dtype, int64_t ld_src, void* dst, int dst_dtype, int64_t ld_dst,
                            void* dstT, int64_t ld_dstT, int64_t rows, int64_t cols, int64_t batch,
                            int64_t bs_src, int64_t bs_dst, int64_t bs_dstT, void* stream);
+/* One launch for MANY conversions (all GEMM-operand copies of the parameters after an optimizer step):
+ * a DEVICE-resident table of segments dst[r,c] = cast(src[r,c] (+ src2[r,c])), fp32 sources (src2 optional, same
+ * pitch), bf16 / fp32 destination with its own pitch, and a DEVICE table of int32 triples (segment, first row, rows),
+ * one CTA per triple.                                                                              */
+typedef struct {
+  const void* src; const void* src2; void* dst;
+  int64_t rows, cols, ld_src, ld_dst;
+  int32_t src_dtype, dst_dtype;               /* src_dtype must be DLSG_F32 */
+} dlsg_seg_t;
+int dlsg_multi_convert(const dlsg_seg_t* segs_dev, const int32_t* chunks_dev, int32_t nchunks, void* stream);
 /* out[c] += sum_r x[r,c] : bias gradients (fp32 accumulate into out)                            */
 int dlsg_colsum(const void* x, int dtype, int64_t ld, int64_t rows, int64_t cols, float* out, void* stream);
 

@@ -51,6 +51,14 @@ class CpuEmulBackend:
         if dstT is not None:
             dstT.copy_(src.transpose(-1, -2))
 
+    def make_convert_plan(self, pairs, chunk_elems=16384):
+        return {'pairs': list(pairs), 'n': len(pairs)}
+
+    def multi_convert(self, plan):
+        self.launches += 1
+        for src, src2, dst in plan['pairs']:
+            dst.copy_(src if src2 is None else src + src2)
+
     def colsum(self, x, out):
         self.launches += 1
         out.add_(_f(x).reshape(-1, x.shape[-1]).sum(0))

@@ -224,3 +224,50 @@ def test_weight_copy_cache_sees_fused_optimizer_updates():
     assert losses_['fused'][0][2] < losses_['fused'][0][0] - 0.05          # it actually trains
     assert max(abs(a - b) for a, b in zip(losses_['fused'][0], losses_['foreach'][0])) < 1e-4
     assert torch.equal(losses_['fused'][1], losses_['foreach'][1])          # eval after training sees the final weights
+
+
+def test_pinned_weight_copies_refresh_in_one_launch():
+    """WeightCache.record() logs every weight conversion of a training forward; PinnedWeights.refresh() replays them as
+    ONE multi-segment launch (dlsg_multi_convert) and a pinned forward + backward launches no weight conversion of its
+    own.  After an in-place weight update that does not bump tensor versions (fused optimizers), the pinned path must
+    give exactly the losses / gradients of a cold-cache run."""
+    la.set_precision('bf16')
+    tag, args, V, B = CASES[0]
+    frames, regions, caps, lens = synth.make_inputs(B, args, V, seed=12)
+    net = _build('CapGnnModel', args, V)
+    net.eval()
+    pinned = DF.WC.record(lambda: net(frames, regions, caps, args.max_words, 1.0))
+    assert len(pinned.pairs) >= 20 and pinned.plan['n'] == len(pinned.pairs)
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.data.add_(0.02 * torch.randn(p.shape, generator=g))            # .data: no version bump
+
+    def run():
+        net.zero_grad()
+        out = net(frames, regions, caps, args.max_words, 1.0)[0]
+        loss = O.packed_ce_loss(out, caps, lens)
+        loss.backward()
+        return out.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+    be = ops.backend()
+    calls = {'cv': 0}
+    orig_cv = DF.WC.cv
+    DF.WC.cv = lambda s_, d: (calls.__setitem__('cv', calls['cv'] + 1), orig_cv(s_, d))[1]
+    try:
+        n0 = be.launches
+        pinned.refresh()
+        assert be.launches == n0 + 1
+        DF.WC.pin(pinned)
+        try:
+            out_a, grads_a = run()
+        finally:
+            DF.WC.unpin()
+        assert calls['cv'] == 0, 'a pinned step must not convert weights on its own'
+    finally:
+        DF.WC.cv = orig_cv
+    DF.WC.clear()
+    out_b, grads_b = run()
+    assert torch.equal(out_a, out_b)
+    assert set(grads_a) == set(grads_b)
+    for k in grads_a:
+        assert torch.equal(grads_a[k], grads_b[k]), k

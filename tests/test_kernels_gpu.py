@@ -76,7 +76,7 @@ def test_gemm_tc_plain(be, M, N, K):
     both('gemm', be, [a, b, out], {}, [2], tol=2e-3)
 
 
-@pytest.mark.parametrize('M,N,K', [(200, 300, 128), (64, 512, 200), (936, 26, 1024)])
+@pytest.mark.parametrize('M,N,K', [(200, 300, 128), (64, 512, 200), (936, 26, 1024), (200, 320, 128), (300, 2048, 64)])
 def test_gemm_tc_epilogues(be, M, N, K):
     a, b = bf(R(M, K, scale=0.2)), bf(R(N, K, scale=0.2))
     bias_n, bias_m = R(N), R(M)
@@ -88,6 +88,9 @@ def test_gemm_tc_epilogues(be, M, N, K):
     both('gemm', be, [a, b, torch.zeros(M, N, dtype=torch.bfloat16)], dict(bias=bias_n), [2], tol=1e-2)
     both('gemm', be, [a, b, torch.zeros(N, M).t()], dict(bias=bias_n), [2], tol=2e-3)      # STORE_T
     both('gemm', be, [a, b, torch.zeros(M, N + 5)[:, :N]], dict(), [2], tol=2e-3)            # ldd > N
+    both('gemm', be, [a, b, torch.zeros(M, N + 8, dtype=torch.bfloat16)[:, :N]], dict(bias=bias_n, tanh=True), [2], tol=1e-2)
+    both('gemm', be, [a, b, torch.zeros(M, N + 8, dtype=torch.bfloat16)[:, 8:]], dict(bias=bias_m, bias_axis='m', alpha=0.5), [2], tol=1e-2)
+    both('gemm', be, [a, b, R(M, N + 4)[:, 4:]], dict(accum=True, bias=bias_n), [2], tol=2e-3)
 
 
 def test_gemm_tc_batched_and_strided_views(be):
@@ -182,6 +185,33 @@ def test_convert_and_colsum(be):
     both('convert', be, [bf(R(40, 24))], dict(dst=torch.zeros(40, 24)), ['dst'])
     both('colsum', be, [R(1000, 70), torch.zeros(70)], {}, [1], tol=1e-5)
     both('colsum', be, [bf(R(300, 64)), R(64)], {}, [1], tol=1e-3)
+
+
+def test_multi_convert_segments(be):
+    """One launch over a device table of 2-D segments: bf16 / fp32 destinations with their own pitch, column slices of a
+    wider source (the packed LSTM gate matrices), summed bias pairs, odd widths (scalar path), multi-chunk segments."""
+    w1, w2, w3 = R(300, 3884), R(4096, 1024), R(37, 301)
+    b1, b2 = R(4096), R(4096)
+    d1 = torch.zeros(300, 1536 + 8, dtype=torch.bfloat16)
+    d2 = torch.zeros(300, 304, dtype=torch.bfloat16)
+    d3 = torch.zeros(2 * 4096, 1024, dtype=torch.bfloat16)
+    d4 = torch.zeros(37, 304, dtype=torch.bfloat16)
+    d5, d6 = torch.zeros(4096), torch.zeros(1, 301)
+    pairs = [(w1[:, :1536], None, d1[:, :1536]), (w1[:, 3584:], None, d2[:, :300]), (w2, None, d3[4096:]),
+             (w3, None, d4[:, :301]), (b1.view(1, -1), b2.view(1, -1), d5.view(1, -1)), (w3[5:6], None, d6)]
+    dev_pairs = []
+    for src, src2, dst in pairs:
+        def to_dev(x):
+            base = torch.empty(0, dtype=x.dtype).set_(x.untyped_storage()).to(DEV)
+            return torch.as_strided(base, x.shape, x.stride(), x.storage_offset())
+        dev_pairs.append((to_dev(src), to_dev(src2) if src2 is not None else None, to_dev(dst)))
+    plan = be.make_convert_plan(dev_pairs)
+    assert plan['n'] > len(pairs)                     # the big segments are split into several chunks
+    be.multi_convert(plan)
+    torch.cuda.synchronize()
+    for (src, src2, dst), (_, _, g) in zip(pairs, dev_pairs):
+        want = (src if src2 is None else src + src2).to(dst.dtype)
+        assert torch.equal(want, g.cpu()), (src.shape, dst.dtype)
 
 
 # ----------------------------------------------------------------------------------------------- norm family
