@@ -339,6 +339,23 @@ def main():
                         del gd
                     extra[name] = Bd / (dms * 1e-3)
             net.train()
+            # ---- full GAN iteration of the live trainer (BASELINE.json configs[4] at one GPU; run_gun.py:147-234 + :339-398):
+            # G forward, 5 critic steps with the WGAN-GP double backward, G step with the critic term, both Adams
+            try:
+                from dlsg.gan import GanIteration
+                with contextlib.redirect_stdout(io.StringIO()):
+                    Dnet = M.DiscV2(args, V_MSR).to(dev).train()
+                og = torch.optim.Adam(net.parameters(), lr=1.6e-4, betas=(0.5, 0.9), fused=True, capturable=True)
+                od = torch.optim.Adam(Dnet.parameters(), lr=1.6e-4, betas=(0.5, 0.9), fused=True, capturable=True)
+                gi = GanIteration(net, Dnet, og, od, d_fr, d_rg, d_cp, lens, 26, 0.6, 5, 0.01, graph=use_graph)
+                for _ in range(2):
+                    gi()
+                gms = timed(lambda: gi(), 3)
+                extra['gan_iteration_ms_B%d' % B] = gms
+                extra['gan_iteration_clips_per_s'] = B / (gms * 1e-3)
+                del gi, Dnet, og, od
+            except Exception as e:                  # secondary metric: never take the headline line down with it
+                extra['gan_iteration_error'] = repr(e)[:200]
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

@@ -540,6 +540,74 @@ lstm_cell_bwd_kernel(const dlsg_lstm_cell_bwd_t p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------- LayerNorm backward, differentiated
+// Backward of dx = rstd * P(dy*gamma), P(v) = v - mean(v) - xh * mean(v * xh), xh = (x - mean) * rstd, with respect to
+// (dy, x, gamma) for a cotangent u of dx (the WGAN-GP penalty differentiates the critic's input gradient, run_gun.py:362-375):
+//   g_dy = rstd * P(u) * gamma            g_gamma += sum_rows rstd * P(u) * dy
+//   g_x  = rstd * P(q) - (K rstd^2 / D) xh,   q = -rstd (u c_g + c_u g),  K = <u,g> - D mean(u) mean(g) - D c_u c_g,
+//   c_v = mean(v * xh), g = dy * gamma.   One warp per row, lanes stride over columns (D <= 32 * KC).
+template <int KC>
+__global__ void __launch_bounds__(256)
+norm_bwd2_kernel(const dlsg_norm_bwd2_t p) {
+  pdl_prologue();
+  extern __shared__ float sm2[];                 // [nw][D] partial g_gamma
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int D = p.D;
+  const float invD = 1.f / (float)D;
+  float gam[KC], acc[KC];
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const int c = lane + 32 * k;
+    gam[k] = c < D ? p.gamma[c] : 0.f;
+    acc[k] = 0.f;
+  }
+  for (int64_t row = (int64_t)blockIdx.x * nw + w; row < p.rows; row += (int64_t)gridDim.x * nw) {
+    const float mean = p.stats[row * 2], r = p.stats[row * 2 + 1];
+    float a[KC], uu[KC], dv[KC];
+    float s_u = 0.f, s_ua = 0.f, s_g = 0.f, s_ga = 0.f, s_ug = 0.f;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const int c = lane + 32 * k;
+      a[k] = 0.f; uu[k] = 0.f; dv[k] = 0.f;
+      if (c < D) {
+        a[k] = (p.x[row * D + c] - mean) * r;
+        uu[k] = p.u[row * D + c];
+        dv[k] = p.dy[row * D + c];
+      }
+      const float g = dv[k] * gam[k];
+      s_u += uu[k]; s_ua = fmaf(uu[k], a[k], s_ua); s_g += g; s_ga = fmaf(g, a[k], s_ga); s_ug = fmaf(uu[k], g, s_ug);
+    }
+    s_u = warp_sum(s_u); s_ua = warp_sum(s_ua); s_g = warp_sum(s_g); s_ga = warp_sum(s_ga); s_ug = warp_sum(s_ug);
+    const float mu_u = s_u * invD, c_u = s_ua * invD, mu_g = s_g * invD, c_g = s_ga * invD;
+    const float K = s_ug - (float)D * (mu_u * mu_g + c_u * c_g);
+    const float mq = -r * (mu_u * c_g + c_u * mu_g), mqa = -2.f * r * c_u * c_g, kx = K * r * r * invD;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const int c = lane + 32 * k;
+      if (c < D) {
+        const float pu = uu[k] - mu_u - a[k] * c_u;
+        const float g = dv[k] * gam[k];
+        if (p.g_dy) p.g_dy[row * D + c] = r * pu * gam[k];
+        acc[k] = fmaf(r * pu, dv[k], acc[k]);
+        const float q = -r * (uu[k] * c_g + c_u * g);
+        if (p.g_x) p.g_x[row * D + c] = r * (q - mq - a[k] * mqa) - kx * a[k];
+      }
+    }
+  }
+  if (p.g_gamma == nullptr) return;              // uniform
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const int c = lane + 32 * k;
+    if (c < D) sm2[w * D + c] = acc[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float t = 0.f;
+    for (int ww = 0; ww < nw; ++ww) t += sm2[ww * D + c];
+    atomicAdd(&p.g_gamma[c], t);
+  }
+}
+
 // ------------------------------------------------------------------------------------------- multi-segment convert
 // One launch refreshes every GEMM-operand copy of the parameters after an optimizer step: a device table of 2-D
 // segments dst[r,c] = cast(src[r,c] (+ src2[r,c])) (fp32 sources; bf16 or fp32 destinations with their own pitch: row
@@ -855,6 +923,18 @@ int dlsg_convert2d(const void* src, int sdt, int64_t lds, void* dst, int ddt, in
 int dlsg_norm_fwd(const dlsg_norm_fwd_t* p, void* stream) { return norm_fwd_launch(p, (cudaStream_t)stream); }
 int dlsg_norm_bwd(const dlsg_norm_bwd_t* p, void* stream) { return norm_bwd_launch(p, (cudaStream_t)stream); }
 int dlsg_norm_bwd_streaming(const dlsg_norm_bwd_t* p) { return norm_bwd_bf16_ok(p) ? 1 : 0; }
+int dlsg_norm_bwd2(const dlsg_norm_bwd2_t* p, void* stream) {
+  DLSG_REQUIRE(p->rows >= 0 && p->D > 0 && p->D <= 1024, "norm_bwd2: D=%d unsupported (<= 1024)", p->D);
+  DLSG_REQUIRE(p->x && p->dy && p->u && p->gamma && p->stats, "norm_bwd2: null input");
+  if (p->rows == 0) return 0;
+  const int nw = 8;
+  int64_t blocks = (p->rows + nw - 1) / nw;
+  if (blocks > kNumSM * 4) blocks = kNumSM * 4;
+  const size_t smem = (size_t)nw * p->D * sizeof(float);
+  if (p->D <= 512) DLSG_LAUNCH(norm_bwd2_kernel<16>, (unsigned)blocks, nw * 32, smem, (cudaStream_t)stream, *p);
+  else DLSG_LAUNCH(norm_bwd2_kernel<32>, (unsigned)blocks, nw * 32, smem, (cudaStream_t)stream, *p);
+  return check_launch("norm_bwd2_kernel");
+}
 
 int dlsg_lstm_cell_fwd(const dlsg_lstm_cell_fwd_t* p, void* stream) {
   DLSG_REQUIRE(p->B > 0 && p->H > 0 && p->nsplit >= 1, "lstm_cell_fwd: bad shape");

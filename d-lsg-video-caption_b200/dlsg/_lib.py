@@ -59,6 +59,11 @@ class CellBwdT(C.Structure):
                 ('dh2_nsplit', i32), ('_pad3', i32), ('dh2_stride_split', i64)]
 
 
+class NormBwd2T(C.Structure):
+    _fields_ = [('x', vp), ('dy', vp), ('u', vp), ('gamma', vp), ('stats', vp), ('g_dy', vp), ('g_x', vp), ('g_gamma', vp),
+                ('rows', i64), ('D', i32), ('_pad', i32)]
+
+
 class SegT(C.Structure):
     _fields_ = [('src', vp), ('src2', vp), ('dst', vp), ('rows', i64), ('cols', i64), ('ld_src', i64), ('ld_dst', i64),
                 ('src_dtype', i32), ('dst_dtype', i32)]
@@ -137,6 +142,7 @@ SIGNATURES = {
     'dlsg_norm_fwd': (i32, [C.POINTER(NormFwdT), vp]),
     'dlsg_norm_bwd': (i32, [C.POINTER(NormBwdT), vp]),
     'dlsg_norm_bwd_streaming': (i32, [C.POINTER(NormBwdT)]),
+    'dlsg_norm_bwd2': (i32, [C.POINTER(NormBwd2T), vp]),
     'dlsg_lstm_cell_fwd': (i32, [C.POINTER(CellFwdT), vp]),
     'dlsg_lstm_cell_bwd': (i32, [C.POINTER(CellBwdT), vp]),
     'dlsg_lstm_cell_bwd2': (i32, [C.POINTER(CellBwd2T), vp]),

@@ -19,14 +19,14 @@ from . import losses
 
 class GanIteration:
     def __init__(self, G, D, opt_g, opt_d, frames, regions, captions, cap_lens, max_words=26, tf_ratio=0.6, num_d=5,
-                 gan_lambda=0.01, process_group=None, graph=True, warmup=2):
+                 gan_lambda=0.01, process_group=None, graph=True, warmup=2, batched=True):
         dev = frames.device
         self.G, self.D, self.opt_g, self.opt_d = G, D, opt_g, opt_d
         self.frames, self.regions, self.captions = frames.clone(), regions.clone(), captions.clone()
         self.lens = torch.as_tensor(list(cap_lens), dtype=torch.int32, device=dev)
         self.inv = torch.tensor([1.0 / max(1, int(sum(cap_lens)))], dtype=torch.float32, device=dev)
         self.lam = torch.tensor(float(gan_lambda), dtype=torch.float32, device=dev)
-        self.max_words, self.tf, self.num_d = max_words, tf_ratio, num_d
+        self.max_words, self.tf, self.num_d, self.batched = max_words, tf_ratio, num_d, batched
         self.V = D.conv1d.weight.shape[1]
         self.pg, self.world, self.sync = process_group, 1, None
         if process_group is not None:
@@ -63,13 +63,21 @@ class GanIteration:
     def _disc_steps(self, real, fake, obj, mot, att_mask, alpha):
         D, B = self.D, real.shape[0]
         loss_d = wass = torch.zeros((), device=real.device)
+        if self.batched:
+            obj3, mot3, mask3, alpha3 = obj.repeat(3, 1, 1), mot.repeat(3, 1, 1), att_mask.repeat(3, 1, 1), alpha.repeat(3, 1, 1)
         for _ in range(self.num_d):
             self.opt_d.zero_grad(set_to_none=True)
-            r_logit = D(real, obj, mot, att_mask, alpha)
-            f_logit = D(fake, obj, mot, att_mask, alpha)
             eps = torch.rand(B, 1, 1, device=real.device, requires_grad=True)
             mixed = real * eps + fake * (1 - eps)
-            m_logit = D(mixed, obj, mot, att_mask, alpha)
+            if self.batched:
+                # the three critic calls of the step as ONE stacked forward (per-group batch means inside DiscV2): a third
+                # of the launches of D(real), D(fake), D(mixed); the penalty differentiates the mixed rows only
+                logits = D(torch.cat([real, fake, mixed], 0), obj3, mot3, mask3, alpha3, _groups=3)
+                r_logit, f_logit, m_logit = logits[:B], logits[B:2 * B], logits[2 * B:]
+            else:
+                r_logit = D(real, obj, mot, att_mask, alpha)
+                f_logit = D(fake, obj, mot, att_mask, alpha)
+                m_logit = D(mixed, obj, mot, att_mask, alpha)
             g = torch.autograd.grad(inputs=mixed, outputs=m_logit, grad_outputs=torch.ones_like(m_logit),
                                     create_graph=True, retain_graph=True)[0]
             gn = g.contiguous().view(B, -1).norm(2, dim=1)

@@ -56,12 +56,47 @@ def matmul_nn(a, b):
     return bmm_nt(a, b.transpose(-1, -2))
 
 
+class _ColSum(torch.autograd.Function):
+    """out[c] = sum_r x[r,c] (bias gradients) on the colsum kernel; its backward is a broadcast."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.rows = x.shape[0]
+        out = zeros((x.shape[1],), x)
+        ops.backend().colsum(_c(x), out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.unsqueeze(0).expand(ctx.rows, g.shape[0])
+
+
+class _LinearB(torch.autograd.Function):
+    """y = a @ w^T + bias with the bias added in the GEMM epilogue; bias gradient on the colsum kernel."""
+
+    @staticmethod
+    def forward(ctx, a, w, bias):
+        ctx.save_for_backward(a, w)
+        return la.mm(a, w, memo=True, bias=bias.detach())
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, w = ctx.saved_tensors
+        da = dw = db = None
+        if ctx.needs_input_grad[0]:
+            da = bmm_nt(dy, w.transpose(-1, -2))
+        if ctx.needs_input_grad[1]:
+            dw = bmm_nt(dy.transpose(-1, -2), a.transpose(-1, -2))
+        if ctx.needs_input_grad[2]:
+            db = _ColSum.apply(dy)
+        return da, dw, db
+
+
 def linear(x, w, b=None, tanh=False):
     """nn.Linear over the last dim of x (any leading dims)."""
     lead = x.shape[:-1]
-    y = bmm_nt(x.reshape(-1, x.shape[-1]), w)
-    if b is not None:
-        y = y + b
+    x2 = x.reshape(-1, x.shape[-1])
+    y = bmm_nt(x2, w) if b is None else _LinearB.apply(x2, w, b)
     if tanh:
         y = tanh_(y)
     return y.view(*lead, w.shape[0])
@@ -160,7 +195,11 @@ class _Norm(torch.autograd.Function):
     def backward(ctx, dy):
         x, gamma, beta, stats = ctx.saved_tensors
         if torch.is_grad_enabled() and (x.requires_grad or dy.requires_grad or gamma.requires_grad):
-            # double-backward path: differentiable restatement on the saved statistics
+            # double-backward path.  When only dx is wanted (the WGAN-GP penalty differentiates the critic's INPUT
+            # gradient: no parameter gradients in the first backward) it is one fused kernel whose own backward is the
+            # closed-form dlsg_norm_bwd2; otherwise a differentiable restatement in torch ops.
+            if x.shape[-1] <= 1024 and not SECOND_ORDER_THROUGH_NORM_PARAMS:
+                return _norm_bwd_fused_diff(x, gamma, dy, stats, ctx.pre_tanh, ctx.drop) + (None, None)
             return _norm_bwd_diff(x, gamma, dy, ctx.pre_tanh, ctx.drop) + (None, None)
         x2 = _c(x).view(-1, x.shape[-1])
         d2 = _c(dy).view(-1, x.shape[-1])
@@ -169,6 +208,54 @@ class _Norm(torch.autograd.Function):
         ops.backend().norm_bwd(d2, x2, gamma.detach(), beta.detach(), stats, dx=dx, dgamma=dg, dbeta=db,
                                pre_tanh=ctx.pre_tanh, drop=ctx.drop)
         return dx.view(x.shape), dg, db, None, None
+
+
+# The fused differentiable LayerNorm backward supports second derivatives through dx only (what the WGAN-GP penalty needs:
+# it differentiates the critic's INPUT gradient).  Set True to route through the all-torch restatement instead, which is
+# differentiable through the parameter gradients as well.
+SECOND_ORDER_THROUGH_NORM_PARAMS = False
+
+
+class _NormBwdCore(torch.autograd.Function):
+    """(dt, dgamma, dbeta) = LayerNorm backward of dy at the normalised input t: forward = the fused row kernel;
+    backward (for a cotangent of dt) = dlsg_norm_bwd2 (closed form)."""
+
+    @staticmethod
+    def forward(ctx, dy, t, gamma, stats):
+        D = t.shape[-1]
+        t2, d2 = _c(t).view(-1, D), _c(dy).view(-1, D)
+        dt = torch.empty_like(t2)
+        g0 = gamma.detach()
+        dg, db = zeros(gamma.shape, gamma), zeros(gamma.shape, gamma)
+        ops.backend().norm_bwd(d2, t2, g0, g0, stats, dx=dt, dgamma=dg, dbeta=db)
+        ctx.save_for_backward(d2, t2, gamma, stats)
+        ctx.set_materialize_grads(False)
+        return dt.view(t.shape), dg, db
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, u, u_gamma, u_beta):
+        if u_gamma is not None or u_beta is not None:
+            raise NotImplementedError('second derivative through LayerNorm parameter gradients: set '
+                                      'dlsg.generic.SECOND_ORDER_THROUGH_NORM_PARAMS = True')
+        if u is None:
+            return None, None, None, None
+        d2, t2, gamma, stats = ctx.saved_tensors
+        u2 = _c(u).view(t2.shape)
+        g_dy, g_t = torch.empty_like(t2), torch.empty_like(t2)
+        g_gamma = zeros(gamma.shape, gamma) if ctx.needs_input_grad[2] else None
+        ops.backend().norm_bwd2(t2, d2, u2, gamma.detach(), stats, g_dy=g_dy, g_x=g_t, g_gamma=g_gamma)
+        return g_dy.view(u.shape), g_t.view(u.shape), g_gamma, None
+
+
+def _norm_bwd_fused_diff(x, gamma, dy, stats, pre_tanh, drop):
+    if drop is not None:
+        dy = dropout_mask_apply(dy, drop)
+    t = tanh_(x) if pre_tanh else x
+    dt, dgamma, dbeta = _NormBwdCore.apply(dy, t, gamma, stats)
+    if pre_tanh:
+        dt = dt * (1 - t * t)
+    return dt, dgamma, dbeta
 
 
 def _norm_bwd_diff(x, gamma, dy, pre_tanh, drop):
@@ -423,11 +510,20 @@ def gather_rows(p, idx):
     return torch.gather(p, 1, idx.unsqueeze(-1).expand(idx.shape[0], idx.shape[1], p.shape[-1]))
 
 
-def weighted_mean_score(s, adj_alpha):
-    return ((s * adj_alpha).sum(-1) / adj_alpha.sum(-1)).mean(-1)
+def weighted_mean_score(s, adj_alpha, groups=1):
+    """layer.py:713-714: per-sample alpha-weighted node score, then the batch mean -> 0-dim scalar.  groups > 1: the
+    batch is `groups` independent calls stacked along dim 0 (dlsg.gan batches D(real), D(fake), D(mixed)): one mean
+    per group -> (groups,)."""
+    per = (s * adj_alpha).sum(-1) / adj_alpha.sum(-1)
+    if groups == 1:
+        return per.mean(-1)
+    return per.view(groups, -1).mean(-1)
 
 
-def fuse_scores(s_obj, s_mot, f):
+def fuse_scores(s_obj, s_mot, f, groups=1):
+    if groups > 1:
+        n = f.shape[0] // groups
+        s_obj, s_mot = s_obj.repeat_interleave(n), s_mot.repeat_interleave(n)
     return s_obj * f[:, 0] + s_mot * f[:, 1]
 
 

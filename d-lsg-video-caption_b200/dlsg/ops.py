@@ -249,6 +249,18 @@ class CudaBackend:
         if dxsum is not None and not fused_sum:
             self.colsum(dx, dxsum)
 
+    def norm_bwd2(self, x, dy, u, gamma, stats, g_dy=None, g_x=None, g_gamma=None):
+        """Backward of the plain LayerNorm backward w.r.t. (dy, x, gamma) for a cotangent u of dx; contiguous fp32 (rows, D)."""
+        self._ck(x)
+        p = L.NormBwd2T()
+        rows, D, _ = _rows2d(x)
+        for t_ in (x, dy, u, g_dy, g_x):
+            assert t_ is None or (t_.is_contiguous() and t_.dtype == torch.float32 and t_.numel() == rows * D)
+        p.x, p.dy, p.u, p.gamma, p.stats = x.data_ptr(), dy.data_ptr(), u.data_ptr(), gamma.data_ptr(), stats.data_ptr()
+        p.g_dy, p.g_x, p.g_gamma, p.rows, p.D = _ptr(g_dy), _ptr(g_x), _ptr(g_gamma), rows, D
+        self.launches += 1
+        L.check(self.lib.dlsg_norm_bwd2(C.byref(p), _stream()), 'dlsg_norm_bwd2')
+
     # ------------------------------------------------------------------ LSTM cell
     def lstm_cell_fwd(self, gates, c_prev, c_out, h_out=None, row_bias=None, bias=None, h2=None, h3=None, drop=None):
         """gates: (B,4H) or (nsplit,B,4H) fp32 (overwritten with activated i,f,g,o in gates[0])."""

@@ -346,12 +346,13 @@ class PSLScore(_PSLBase):
 
 class PSLScore2(_PSLBase):
     @G.param_scope
-    def forward(self, psl, psl_alpha, att_out, seq_mask):
-        """layer.py:688-715 -> 0-dim scalar (batch mean of alpha-weighted node scores)."""
+    def forward(self, psl, psl_alpha, att_out, seq_mask, _groups=1):
+        """layer.py:688-715 -> 0-dim scalar (batch mean of alpha-weighted node scores); (_groups,) when the batch stacks
+        several independent calls (dlsg.gan)."""
         p, a, adj = self._common(psl, psl_alpha, att_out)
         adj = G.softmax(adj, dim=1, scale=1.0 / math.sqrt(512), mask=seq_mask, mask_mode=2)   # over words, then zero pads
         adj_alpha = G.sum_dim1(adj)                                                          # (B,K)
         g = G.bmm_nt(adj.transpose(1, 2), a.transpose(1, 2))                                  # (B,K,512)
         g = G.norm(g, self.psl_norm[1].weight, self.psl_norm[1].bias, pre_tanh=True, p_drop=0.3 if self.training else 0.0)
         s = self.psl_scorer(p, g).squeeze()
-        return G.weighted_mean_score(s, adj_alpha)
+        return G.weighted_mean_score(s, adj_alpha, _groups)

@@ -138,8 +138,11 @@ class DiscV2(nn.Module):
         )
 
     @G.param_scope
-    def forward(self, inputs, obj_proposals, motion_proposals, att_mask=None, alpha_all=None):
-        """inputs (B,L,V) one-hot / logits / mix -> score (B,)   (model.py:145-168)."""
+    def forward(self, inputs, obj_proposals, motion_proposals, att_mask=None, alpha_all=None, _groups=1):
+        """inputs (B,L,V) one-hot / logits / mix -> score (B,)   (model.py:145-168).
+        _groups > 1 (our own extension, used by dlsg.gan): the batch is `_groups` independent reference calls stacked along
+        dim 0 - D(real), D(fake), D(mixed) of a critic step - so the per-call batch means of PSLScore2 (layer.py:713-714)
+        are taken per group and the result equals the concatenation of the separate calls."""
         p = 0.3 if self.training else 0.0
         x = G.linear(inputs, self.conv1d.weight[:, :, 0], self.conv1d.bias)          # conv1d k=1 == per-token Linear
         conv = self.block[0].res_block[1]
@@ -151,8 +154,8 @@ class DiscV2(nn.Module):
         seq = att_mask[:, 0, :].unsqueeze(dim=2)
         alpha_all = G.mul(alpha_all, seq.expand_as(alpha_all).contiguous())
         seq_mask_spl = seq.repeat(1, 1, self.num_top)
-        obj_score_out = self.obj_psl_score(obj_proposals, alpha_all[:, :, :self.num_psl], att_out, seq_mask_spl)
-        motion_score_out = self.motion_psl_score(motion_proposals, alpha_all[:, :, -self.num_psl:], att_out, seq_mask_spl)
+        obj_score_out = self.obj_psl_score(obj_proposals, alpha_all[:, :, :self.num_psl], att_out, seq_mask_spl, _groups)
+        motion_score_out = self.motion_psl_score(motion_proposals, alpha_all[:, :, -self.num_psl:], att_out, seq_mask_spl, _groups)
         sent_sum = self.text_sum(att_out).squeeze()                                   # (B,512)
         fusion_score = G.softmax(G.linear(sent_sum, self.fusion), dim=-1)             # (B,2)
-        return G.fuse_scores(obj_score_out, motion_score_out, fusion_score)
+        return G.fuse_scores(obj_score_out, motion_score_out, fusion_score, _groups)

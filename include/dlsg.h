@@ -113,6 +113,16 @@ typedef struct {
                   /* only the streaming bf16 form computes it (dlsg_norm_bwd_streaming(p) == 1), else it must be NULL   */
 } dlsg_norm_bwd_t;
 int dlsg_norm_bwd(const dlsg_norm_bwd_t* p, void* stream);
+/* Backward of the (plain) LayerNorm backward with respect to (dy, x, gamma), for a cotangent u of dx: the second-order
+ * term of the WGAN-GP gradient penalty through the critic's LayerNorms (run_gun.py:362-375 over model.py:128-131,153,
+ * layer.py:665-681).  All tensors contiguous fp32 (rows, D), D <= 1024; stats = (mean, rstd) of x saved by the forward;
+ * g_gamma (D) is ACCUMULATED (+=); g_dy / g_x / g_gamma may be NULL.                                */
+typedef struct {
+  const float* x; const float* dy; const float* u; const float* gamma; const float* stats;
+  float* g_dy; float* g_x; float* g_gamma;
+  int64_t rows; int32_t D; int32_t _pad;
+} dlsg_norm_bwd2_t;
+int dlsg_norm_bwd2(const dlsg_norm_bwd2_t* p, void* stream);
 int dlsg_norm_bwd_streaming(const dlsg_norm_bwd_t* p);   /* 1 if this call runs the streaming bf16 kernel (large bf16 x/dy/dx) */
 
 /* ---- LSTM cell pointwise (nn.LSTMCell / nn.LSTM step, gate order i,f,g,o) ------------------

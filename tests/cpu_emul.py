@@ -121,6 +121,27 @@ class CpuEmulBackend:
         if dxsum is not None:
             dxsum.add_(r.reshape(-1, D).sum(0))
 
+    def norm_bwd2(self, x, dy, u, gamma, stats, g_dy=None, g_x=None, g_gamma=None):
+        """Reference by automatic differentiation of the restated LayerNorm backward (the kernel uses closed forms)."""
+        self.launches += 1
+        D = x.shape[-1]
+        with torch.enable_grad():
+            x_ = x.detach().double().reshape(-1, D).requires_grad_(True)
+            dy_ = dy.detach().double().reshape(-1, D).requires_grad_(True)
+            gm = gamma.detach().double().requires_grad_(True)
+            mean = x_.mean(-1, keepdim=True)
+            r = torch.rsqrt(((x_ - mean) ** 2).mean(-1, keepdim=True) + 1e-5)
+            a = (x_ - mean) * r
+            g = dy_ * gm
+            dx = r * (g - g.mean(-1, keepdim=True) - a * (g * a).mean(-1, keepdim=True))
+            G_ = torch.autograd.grad((dx * u.detach().double().reshape(-1, D)).sum(), [dy_, x_, gm])
+        if g_dy is not None:
+            g_dy.copy_(G_[0].float().view(g_dy.shape))
+        if g_x is not None:
+            g_x.copy_(G_[1].float().view(g_x.shape))
+        if g_gamma is not None:
+            g_gamma.add_(G_[2].float())
+
     def lstm_cell_fwd(self, gates, c_prev, c_out, h_out=None, row_bias=None, bias=None, h2=None, h3=None, drop=None):
         self.launches += 1
         assert drop is None or drop[0] == 0

@@ -94,3 +94,30 @@ def test_disc_bf16_operand_memo_matches_fp32_reference(golden_dir):
              torch.ones(3, f_in.shape[1], f_in.shape[1]), torch.full((3, f_in.shape[1], 10), 0.1))
     key_hits = [e for e in la._PMEMO.values() if e[0] is w]
     assert key_hits and float(key_hits[-1][2].float().abs().max()) == 0.0
+
+
+def test_disc_grouped_forward_equals_separate_calls(golden_dir):
+    """DiscV2(..., _groups=3) over [real; fake; mixed] stacked along the batch must equal the three separate reference
+    calls (PSLScore2's batch mean is taken per group), for values and for the WGAN-GP input gradient."""
+    import models.model as M
+    args = synth.small_args(visual_hidden_size=1024, num_proposals=5, num_topk=5)
+    V, B, L = 37, 3, args.max_words
+    net = M.DiscV2(args, V)
+    synth.fill_state_dict(net, prefix='D.')
+    net.eval()
+    rs = np.random.RandomState(9)
+    _, _, caps, _ = synth.make_inputs(B, args, V, seed=14)
+    att_mask = synth.att_mask_from_captions(caps)
+    obj = torch.from_numpy(rs.standard_normal((B, 5, 1024)).astype(np.float32))
+    mot = torch.from_numpy(rs.standard_normal((B, 5, 1024)).astype(np.float32))
+    alpha = torch.softmax(torch.from_numpy(rs.standard_normal((B, L, 10)).astype(np.float32)), -1)
+    xs = [torch.from_numpy(rs.standard_normal((B, L, V)).astype(np.float32)) for _ in range(3)]
+    mixed_a = xs[2].clone().requires_grad_(True)
+    sep = [net(xs[0], obj, mot, att_mask, alpha), net(xs[1], obj, mot, att_mask, alpha), net(mixed_a, obj, mot, att_mask, alpha)]
+    ga = torch.autograd.grad(sep[2].sum(), mixed_a)[0]
+    mixed_b = xs[2].clone().requires_grad_(True)
+    out = net(torch.cat([xs[0], xs[1], mixed_b], 0), obj.repeat(3, 1, 1), mot.repeat(3, 1, 1), att_mask.repeat(3, 1, 1),
+              alpha.repeat(3, 1, 1), _groups=3)
+    gb = torch.autograd.grad(out[2 * B:].sum(), mixed_b)[0]
+    assert (out.detach() - torch.cat([s.detach() for s in sep])).abs().max() < 1e-5
+    assert (ga - gb).abs().max() < 1e-6

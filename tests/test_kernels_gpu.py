@@ -264,6 +264,17 @@ def test_norm_bf16_streaming(be, rows, D, Dpad):
                                                                   dxsum=R(D)), ['dx', 'dxsum'], tol=1e-4)
 
 
+@pytest.mark.parametrize('rows,D', [(37, 512), (1664, 512), (9, 96), (130, 1024)])
+def test_norm_double_backward(be, rows, D):
+    """Closed-form backward-of-backward of LayerNorm (dlsg_norm_bwd2) against automatic differentiation."""
+    x, dy, u = R(rows, D), R(rows, D), R(rows, D)
+    gamma = 1 + 0.1 * R(D)
+    stats = torch.zeros(rows, 2)
+    EM.norm_fwd(x, gamma, torch.zeros(D), stats=stats)
+    both('norm_bwd2', be, [x, dy, u, gamma, stats], dict(g_dy=torch.zeros(rows, D), g_x=torch.zeros(rows, D), g_gamma=R(D)),
+         ['g_dy', 'g_x', 'g_gamma'], tol=3e-5)
+
+
 def test_norm_strided_slices(be):
     D, rows = 96, 12
     big = R(rows, 4 * D)
