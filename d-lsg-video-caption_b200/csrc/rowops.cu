@@ -657,6 +657,80 @@ multi_convert_kernel(const dlsg_seg_t* __restrict__ segs, const int32_t* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------- multi-tensor Adam
+// torch.optim.Adam's update (run_gun.py:91: lr 1.6e-4, betas (0.5, 0.9), no weight decay / amsgrad) over a device table of
+// 2-D segments, one launch per parameter block, writing the bf16 GEMM-operand copy of each weight in the same pass:
+//   m = m + (g - m)(1 - b1);  v = b2 v + (1 - b2) g^2;  p -= (lr / (1 - b1^t)) m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(const dlsg_adam_seg_t* __restrict__ segs, const int32_t* __restrict__ chunks, const float* __restrict__ step,
+                  const float* __restrict__ lr_dev, float lr_host, float beta1, float beta2, float eps) {
+  pdl_prologue();
+  __shared__ float sh[2];
+  if (threadIdx.x == 0) {
+    const double t = (double)*step;
+    const float lr = lr_dev ? *lr_dev : lr_host;
+    const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
+    sh[0] = (float)((double)lr / bc1);
+    sh[1] = (float)sqrt(bc2);
+  }
+  __syncthreads();
+  const float step_size = sh[0], bc2_sqrt = sh[1];
+  const dlsg_adam_seg_t sg = segs[chunks[3 * blockIdx.x]];
+  const int64_t row0 = chunks[3 * blockIdx.x + 1];
+  const int nrows = chunks[3 * blockIdx.x + 2];
+  float* P = sg.p + row0 * sg.ld;
+  const float* G = sg.g + row0 * sg.ld;
+  float* M = sg.m + row0 * sg.ld;
+  float* V = sg.v + row0 * sg.ld;
+  __nv_bfloat16* S16 = sg.dst16 ? static_cast<__nv_bfloat16*>(sg.dst16) + row0 * sg.ld_dst : nullptr;
+  const float omb1 = 1.f - beta1, omb2 = 1.f - beta2;
+  const bool vec = (sg.cols % 4 == 0) && (sg.ld % 4 == 0) &&
+                   (((reinterpret_cast<uintptr_t>(sg.p) | reinterpret_cast<uintptr_t>(sg.g) | reinterpret_cast<uintptr_t>(sg.m) |
+                      reinterpret_cast<uintptr_t>(sg.v)) & 15) == 0) &&
+                   (!sg.dst16 || ((sg.ld_dst % 4 == 0) && (reinterpret_cast<uintptr_t>(sg.dst16) & 7) == 0));
+  if (vec) {
+    const int c4 = (int)(sg.cols >> 2);
+    const int64_t n = (int64_t)nrows * c4;
+    for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
+      const int64_t r = e / c4;
+      const int c = (int)(e % c4) * 4;
+      const int64_t o = r * sg.ld + c;
+      float4 p4 = *reinterpret_cast<const float4*>(P + o);
+      const float4 g4 = *reinterpret_cast<const float4*>(G + o);
+      float4 m4 = *reinterpret_cast<const float4*>(M + o), v4 = *reinterpret_cast<const float4*>(V + o);
+      float pp[4] = {p4.x, p4.y, p4.z, p4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+      float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        mm[u] = mm[u] + (gg[u] - mm[u]) * omb1;
+        vv[u] = beta2 * vv[u] + omb2 * gg[u] * gg[u];
+        pp[u] -= step_size * mm[u] / (sqrtf(vv[u]) / bc2_sqrt + eps);
+      }
+      *reinterpret_cast<float4*>(P + o) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+      *reinterpret_cast<float4*>(M + o) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+      *reinterpret_cast<float4*>(V + o) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      if (S16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(pp[0], pp[1]), hi = __floats2bfloat162_rn(pp[2], pp[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(S16 + r * sg.ld_dst + c) = pk;
+      }
+    }
+  } else {
+    const int64_t n = (int64_t)nrows * sg.cols;
+    for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
+      const int64_t r = e / sg.cols, c = e % sg.cols;
+      const int64_t o = r * sg.ld + c;
+      const float g = G[o];
+      const float m = M[o] + (g - M[o]) * omb1;
+      const float v = beta2 * V[o] + omb2 * g * g;
+      const float pnew = P[o] - step_size * m / (sqrtf(v) / bc2_sqrt + eps);
+      P[o] = pnew; M[o] = m; V[o] = v;
+      if (S16) S16[r * sg.ld_dst + c] = __float2bfloat16_rn(pnew);
+    }
+  }
+}
+
 // Backward OF the cell backward (WGAN-GP double backward through the discriminator LSTM, run_gun.py:362-375).
 // The cell backward maps (dh, dc; a=pre-activations, c0) -> (dpre[4], dc0) with D = dh*o*(1-tc^2) + dc:
 //   dpre_i = D*g*i(1-i)  dpre_f = D*c0*f(1-f)  dpre_g = D*i*(1-g^2)  dpre_o = dh*tc*o(1-o)  dc0 = D*f .
@@ -952,6 +1026,14 @@ int dlsg_multi_convert(const dlsg_seg_t* segs_dev, const int32_t* chunks_dev, in
   DLSG_REQUIRE(segs_dev && chunks_dev, "multi_convert: null tables");
   DLSG_LAUNCH(multi_convert_kernel, (unsigned)nchunks, 256, 0, (cudaStream_t)stream, segs_dev, chunks_dev);
   return check_launch("multi_convert_kernel");
+}
+
+int dlsg_adam_multi(const dlsg_adam_seg_t* segs_dev, const int32_t* chunks_dev, int32_t nchunks, const float* step_dev,
+                    const float* lr_dev, float lr, float beta1, float beta2, float eps, void* stream) {
+  if (nchunks <= 0) return 0;
+  DLSG_REQUIRE(segs_dev && chunks_dev && step_dev, "adam_multi: null tables");
+  DLSG_LAUNCH(adam_multi_kernel, (unsigned)nchunks, 256, 0, (cudaStream_t)stream, segs_dev, chunks_dev, step_dev, lr_dev, lr, beta1, beta2, eps);
+  return check_launch("adam_multi_kernel");
 }
 
 int dlsg_lstm_cell_bwd2(const dlsg_lstm_cell_bwd2_t* p, void* stream) {

@@ -59,6 +59,10 @@ class CellBwdT(C.Structure):
                 ('dh2_nsplit', i32), ('_pad3', i32), ('dh2_stride_split', i64)]
 
 
+class AdamSegT(C.Structure):
+    _fields_ = [('p', vp), ('g', vp), ('m', vp), ('v', vp), ('dst16', vp), ('rows', i64), ('cols', i64), ('ld', i64), ('ld_dst', i64)]
+
+
 class NormBwd2T(C.Structure):
     _fields_ = [('x', vp), ('dy', vp), ('u', vp), ('gamma', vp), ('stats', vp), ('g_dy', vp), ('g_x', vp), ('g_gamma', vp),
                 ('rows', i64), ('D', i32), ('_pad', i32)]
@@ -138,6 +142,7 @@ SIGNATURES = {
     'dlsg_convert2d': (i32, [vp, i32, i64, vp, i32, i64, vp, i64, i64, i64, vp]),
     'dlsg_convert2d_batched': (i32, [vp, i32, i64, vp, i32, i64, vp, i64, i64, i64, i64, i64, i64, i64, vp]),
     'dlsg_multi_convert': (i32, [vp, vp, i32, vp]),
+    'dlsg_adam_multi': (i32, [vp, vp, i32, vp, vp, f32, f32, f32, f32, vp]),
     'dlsg_colsum': (i32, [vp, i32, i64, i64, i64, vp, vp]),
     'dlsg_norm_fwd': (i32, [C.POINTER(NormFwdT), vp]),
     'dlsg_norm_bwd': (i32, [C.POINTER(NormBwdT), vp]),

@@ -48,6 +48,8 @@ class _BlockFn(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, *gouts):
+        if BLOCK_BWD_HOOK is not None:
+            BLOCK_BWD_HOOK(ctx.block)         # (every AccumulateGrad of the blocks that ran before this one has fired)
         WC.set_scope(ctx.wc_scope)
         la.begin_pool(gouts[0].device if gouts[0] is not None else next(g for g in gouts if g is not None).device)
         try:
@@ -62,6 +64,7 @@ class _BlockFn(torch.autograd.Function):
 
 BLOCK_INPUTS = ('regions', 'visual0', 'visual1', 'frames', 'pe', 'n1', 'n2', 'captions')
 GRAD_SYNC = None
+BLOCK_BWD_HOOK = None       # callable(block) invoked at the start of every block backward (dlsg.graphs: overlapped Adam)
 
 
 class GradSync:

@@ -11,11 +11,12 @@ import torch
 
 from . import functional as DF
 from . import losses
+from . import optim
 
 
 class GraphedTrainStep:
     def __init__(self, model, optimizer, frames, regions, captions, cap_lens, max_words=26, tf_ratio=1.0,
-                 process_group=None, warmup=3, pin_weights=True):
+                 process_group=None, warmup=3, pin_weights=True, own_adam=True):
         dev = frames.device
         self.model, self.opt, self.pg = model, optimizer, process_group
         self.frames, self.regions, self.captions = frames.clone(), regions.clone(), captions.clone()
@@ -25,6 +26,7 @@ class GraphedTrainStep:
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.world = 1
         self.pinned = None
+        self.adam = None
         if process_group is not None:
             import torch.distributed as dist
             self.dist = dist
@@ -38,6 +40,13 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.pinned = self._record_weight_copies() if pin_weights else None
+        self.adam = None
+        if own_adam and self.pinned is not None and optim.supported(optimizer):
+            # our multi-tensor Adam drives the optimizer's state in place and emits the bf16 operand copies itself
+            self.adam = optim.AdamDriver(optimizer, self.pinned)
+            self.pinned.refresh()                # copies are current before the first replay; Adam keeps them current
+            self.dec_params = [p for n, p in model.named_parameters() if n.startswith('decoder.') and p.requires_grad]
+            self.side = torch.cuda.Stream()
         self.graph = torch.cuda.CUDAGraph()
         self.opt.zero_grad(set_to_none=True)
         DF.WC.force = True
@@ -49,6 +58,7 @@ class GraphedTrainStep:
         finally:
             DF.WC.force = False
         self.launches = ops.backend().launches - l0          # libdlsg kernels recorded in one replay
+        self._adam_plans = list(self.adam._plans) if self.adam is not None else None     # pinned staging of the captured tables
         torch.cuda.synchronize()
 
     def _record_weight_copies(self):
@@ -70,8 +80,23 @@ class GraphedTrainStep:
     def _body(self):
         self.opt.zero_grad(set_to_none=True)
         if self.pinned is not None:
-            self.pinned.refresh()                 # current fp32 masters -> every operand copy, one launch
+            if self.adam is None:
+                self.pinned.refresh()             # current fp32 masters -> every operand copy, one launch
             DF.WC.pin(self.pinned)
+        done = []
+        if self.adam is not None and self.world == 1:
+            # the decoder's parameters (65 % of the model) are updated on a side stream the moment the first encoder block
+            # starts its backward: every decoder gradient is final by then, and the bandwidth-bound update hides behind
+            # the latency-bound encoder backward
+            def hook(block):
+                if not done and type(block).__name__ != 'DecoderTrainBlock':
+                    ps = [p for p in self.dec_params if p.grad is not None]
+                    cur = torch.cuda.current_stream()
+                    self.side.wait_stream(cur)
+                    with torch.cuda.stream(self.side):
+                        self.adam.step(ps)
+                    done.extend(ps)
+            DF.BLOCK_BWD_HOOK = hook
         try:
             out = self.model(self.frames, self.regions, self.captions, self.max_words, self.tf)[0]
             loss = losses.packed_cross_entropy(out, self.captions, self.lens, self.inv, unit_grad=True)
@@ -82,11 +107,19 @@ class GraphedTrainStep:
                 loss.backward()
             finally:
                 DF.GRAD_SYNC = None
+                DF.BLOCK_BWD_HOOK = None
         finally:
             DF.WC.unpin()
         if self.world > 1:
             self.sync.wait()
-        self.opt.step()
+        if self.adam is None:
+            self.opt.step()
+        else:
+            seen = set(id(p) for p in done)
+            self.adam.step([p for p in self.params if p.grad is not None and id(p) not in seen])
+            if done:
+                torch.cuda.current_stream().wait_stream(self.side)
+            self.adam.refresh_residual()          # the few copies Adam cannot emit itself (summed bias pairs)
         return loss.detach()
 
     def load(self, frames, regions, captions, cap_lens=None):
@@ -99,8 +132,16 @@ class GraphedTrainStep:
             self.inv.fill_(1.0 / max(1, int(sum(cap_lens))))
 
     def __call__(self):
+        if self.adam is not None:
+            self.adam.sync_lr()                   # a scheduler may have changed the learning rate since the last replay
         self.graph.replay()
         return self.loss
+
+    def refresh_weights(self):
+        """Call after changing the parameters from outside (load_state_dict, manual edits): re-derives every bf16 operand
+        copy from the fp32 masters (otherwise only the in-graph Adam keeps them current)."""
+        if self.pinned is not None:
+            self.pinned.refresh()
 
 
 class GraphedDecode:

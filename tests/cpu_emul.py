@@ -59,6 +59,22 @@ class CpuEmulBackend:
         for src, src2, dst in plan['pairs']:
             dst.copy_(src if src2 is None else src + src2)
 
+    def make_adam_plan(self, segs, chunk_elems=16384):
+        return {'segs': list(segs), 'n': len(segs)}
+
+    def adam_multi(self, plan, step, lr, beta1, beta2, eps, lr_dev=None):
+        self.launches += 1
+        t = float(step)
+        lr = float(lr_dev) if lr_dev is not None else lr
+        bc1, bc2 = 1.0 - beta1 ** t, 1.0 - beta2 ** t
+        for sg in plan['segs']:
+            p_, g_, m_, v_ = sg['p'], sg['g'], sg['m'], sg['v']
+            m_.copy_(m_ + (g_ - m_) * (1 - beta1))
+            v_.copy_(beta2 * v_ + (1 - beta2) * g_ * g_)
+            p_.sub_((lr / bc1) * m_ / (v_.sqrt() / (bc2 ** 0.5) + eps))
+            if sg.get('dst') is not None:
+                sg['dst'].copy_(p_)
+
     def colsum(self, x, out):
         self.launches += 1
         out.add_(_f(x).reshape(-1, x.shape[-1]).sum(0))

@@ -271,3 +271,44 @@ def test_pinned_weight_copies_refresh_in_one_launch():
     assert set(grads_a) == set(grads_b)
     for k in grads_a:
         assert torch.equal(grads_a[k], grads_b[k]), k
+
+
+def test_adam_driver_matches_torch_adam_and_emits_operand_copies():
+    """dlsg.optim.AdamDriver updates the caller's torch.optim.Adam state in place with torch's arithmetic (checked against
+    torch.optim.Adam over several steps, including a learning-rate change) and writes the bf16 operand copies of the weights
+    it owns; conversions it cannot emit (summed bias pairs) stay in the residual refresh."""
+    from dlsg import optim
+    la.set_precision('bf16')
+    tag, args, V, B = CASES[0]
+    frames, regions, caps, lens = synth.make_inputs(B, args, V, seed=12)
+    nets = [_build('CapGnnModel', args, V).eval() for _ in range(2)]
+    opts = [torch.optim.Adam(n.parameters(), lr=1.6e-4, betas=(0.5, 0.9)) for n in nets]
+    pinned = DF.WC.record(lambda: nets[1](frames, regions, caps, args.max_words, 1.0))
+    drv = optim.AdamDriver(opts[1], pinned)
+    assert len(drv.shadow) >= 15 and drv.residual is not None
+    for it in range(4):
+        if it == 2:
+            for o in opts:
+                o.param_groups[0]['lr'] = 4e-5
+            drv.sync_lr()
+        for i in (0, 1):
+            DF.WC.clear() if i == 0 else DF.WC.pin(pinned)
+            try:
+                nets[i].zero_grad()
+                out = nets[i](frames, regions, caps, args.max_words, 1.0)[0]
+                O.packed_ce_loss(out, caps, lens).backward()
+            finally:
+                DF.WC.unpin()
+        opts[0].step()
+        drv.step([p for p in nets[1].parameters() if p.grad is not None])
+        drv.refresh_residual()
+    for (k, p), (_, q) in zip(nets[0].named_parameters(), nets[1].named_parameters()):
+        assert (p - q).abs().max() < 2e-6, k
+        if p.grad is not None:
+            s0, s1 = opts[0].state[p], opts[1].state[q]
+            assert float(s0['step']) == float(s1['step']) == 4.0
+            assert (s0['exp_avg'] - s1['exp_avg']).abs().max() < 1e-6 and (s0['exp_avg_sq'] - s1['exp_avg_sq']).abs().max() < 1e-6
+    # the pinned copies equal a fresh conversion of the updated masters
+    for src, src2, dst in pinned.pairs:
+        want = (src if src2 is None else src + src2).to(dst.dtype)
+        assert torch.equal(want, dst)

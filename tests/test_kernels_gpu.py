@@ -187,6 +187,42 @@ def test_convert_and_colsum(be):
     both('colsum', be, [bf(R(300, 64)), R(64)], {}, [1], tol=1e-3)
 
 
+def test_adam_multi_segments(be):
+    """dlsg_adam_multi over a device table: whole parameters, column segments with bf16 operand copies (own pitch), a
+    1-row bias, an odd width (scalar path); three steps against the emulator's torch.optim.Adam arithmetic."""
+    shapes = [(300, 3884), (64, 301), (1, 4096), (513, 1024)]
+    cpu = [dict(p=R(*s_), m=torch.zeros(*s_), v=torch.zeros(*s_)) for s_ in shapes]
+    dst_cpu = [torch.zeros(300, 1536 + 8, dtype=torch.bfloat16), torch.zeros(300, 2352, dtype=torch.bfloat16),
+               torch.zeros(513, 1024, dtype=torch.bfloat16)]
+    gpu = [{k: v.to(DEV) for k, v in c.items()} for c in cpu]
+    dst_gpu = [d.to(DEV) for d in dst_cpu]
+    step_c, step_g = torch.zeros(()), torch.zeros((), device=DEV)
+    lr_g = torch.full((), 1.6e-4, device=DEV)
+
+    def segs(ts, ds, grads):
+        out = []
+        w, gw = ts[0], grads[0]
+        out.append(dict(p=w['p'][:, :1536], g=gw[:, :1536], m=w['m'][:, :1536], v=w['v'][:, :1536], dst=ds[0][:, :1536]))
+        out.append(dict(p=w['p'][:, 1536:], g=gw[:, 1536:], m=w['m'][:, 1536:], v=w['v'][:, 1536:], dst=ds[1][:, :2348]))
+        for i in (1, 2):
+            out.append(dict(p=ts[i]['p'], g=grads[i], m=ts[i]['m'], v=ts[i]['v'], dst=None))
+        out.append(dict(p=ts[3]['p'], g=grads[3], m=ts[3]['m'], v=ts[3]['v'], dst=ds[2]))
+        return out
+    for it in range(3):
+        grads_c = [R(*s_, scale=0.3) for s_ in shapes]
+        grads_g = [g.to(DEV) for g in grads_c]
+        step_c += 1
+        step_g += 1
+        EM.adam_multi(EM.make_adam_plan(segs(cpu, dst_cpu, grads_c)), step_c, 1.6e-4, 0.5, 0.9, 1e-8)
+        be.adam_multi(be.make_adam_plan(segs(gpu, dst_gpu, grads_g)), step_g, 123.0, 0.5, 0.9, 1e-8, lr_dev=lr_g)
+        torch.cuda.synchronize()
+    for c, g in zip(cpu, gpu):
+        for k in ('p', 'm', 'v'):
+            assert (c[k] - g[k].cpu()).abs().max() <= 2e-6 * max(1.0, float(c[k].abs().max())), k
+    for c, g in zip(dst_cpu, dst_gpu):
+        assert (c.float() - g.float().cpu()).abs().max() <= 1e-2
+
+
 def test_multi_convert_segments(be):
     """One launch over a device table of 2-D segments: bf16 / fp32 destinations with their own pitch, column slices of a
     wider source (the packed LSTM gate matrices), summed bias pairs, odd widths (scalar path), multi-chunk segments."""
