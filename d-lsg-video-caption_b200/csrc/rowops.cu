@@ -661,9 +661,17 @@ multi_convert_kernel(const dlsg_seg_t* __restrict__ segs, const int32_t* __restr
 // torch.optim.Adam's update (run_gun.py:91: lr 1.6e-4, betas (0.5, 0.9), no weight decay / amsgrad) over a device table of
 // 2-D segments, one launch per parameter block, writing the bf16 GEMM-operand copy of each weight in the same pass:
 //   m = m + (g - m)(1 - b1);  v = b2 v + (1 - b2) g^2;  p -= (lr / (1 - b1^t)) m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+constexpr int ADAM_MAX_SEGS = 320;
+struct AdamArgs {                       // passed BY VALUE as a kernel parameter (a CUDA-graph kernel node keeps it: no table upload)
+  dlsg_adam_seg_t seg[ADAM_MAX_SEGS];
+  int32_t chunk_start[ADAM_MAX_SEGS + 1];   // first chunk (CTA) of each segment
+  int32_t rows_per_chunk[ADAM_MAX_SEGS];
+  int32_t nsegs;
+};
+
 __global__ void __launch_bounds__(256)
-adam_multi_kernel(const dlsg_adam_seg_t* __restrict__ segs, const int32_t* __restrict__ chunks, const float* __restrict__ step,
-                  const float* __restrict__ lr_dev, float lr_host, float beta1, float beta2, float eps) {
+adam_multi_kernel(const __grid_constant__ AdamArgs a, const float* __restrict__ step, const float* __restrict__ lr_dev, float lr_host,
+                  float beta1, float beta2, float eps) {
   pdl_prologue();
   __shared__ float sh[2];
   if (threadIdx.x == 0) {
@@ -675,9 +683,14 @@ adam_multi_kernel(const dlsg_adam_seg_t* __restrict__ segs, const int32_t* __res
   }
   __syncthreads();
   const float step_size = sh[0], bc2_sqrt = sh[1];
-  const dlsg_adam_seg_t sg = segs[chunks[3 * blockIdx.x]];
-  const int64_t row0 = chunks[3 * blockIdx.x + 1];
-  const int nrows = chunks[3 * blockIdx.x + 2];
+  int lo = 0, hi = a.nsegs - 1;                     // segment of this CTA: last one whose first chunk <= blockIdx.x
+  while (lo < hi) {
+    const int md = (lo + hi + 1) >> 1;
+    if (a.chunk_start[md] <= (int)blockIdx.x) lo = md; else hi = md - 1;
+  }
+  const dlsg_adam_seg_t& sg = a.seg[lo];
+  const int64_t row0 = (int64_t)((int)blockIdx.x - a.chunk_start[lo]) * a.rows_per_chunk[lo];
+  const int nrows = (int)min((int64_t)a.rows_per_chunk[lo], sg.rows - row0);
   float* P = sg.p + row0 * sg.ld;
   const float* G = sg.g + row0 * sg.ld;
   float* M = sg.m + row0 * sg.ld;
@@ -1028,12 +1041,31 @@ int dlsg_multi_convert(const dlsg_seg_t* segs_dev, const int32_t* chunks_dev, in
   return check_launch("multi_convert_kernel");
 }
 
-int dlsg_adam_multi(const dlsg_adam_seg_t* segs_dev, const int32_t* chunks_dev, int32_t nchunks, const float* step_dev,
+int dlsg_adam_multi(const dlsg_adam_seg_t* segs_host, int32_t nsegs, int32_t chunk_elems, const float* step_dev,
                     const float* lr_dev, float lr, float beta1, float beta2, float eps, void* stream) {
-  if (nchunks <= 0) return 0;
-  DLSG_REQUIRE(segs_dev && chunks_dev && step_dev, "adam_multi: null tables");
-  DLSG_LAUNCH(adam_multi_kernel, (unsigned)nchunks, 256, 0, (cudaStream_t)stream, segs_dev, chunks_dev, step_dev, lr_dev, lr, beta1, beta2, eps);
-  return check_launch("adam_multi_kernel");
+  if (nsegs <= 0) return 0;
+  DLSG_REQUIRE(segs_host && step_dev && chunk_elems > 0, "adam_multi: bad arguments");
+  static thread_local AdamArgs args;                                   // 25 KB: filled per launch, copied into the launch by value
+  for (int s0 = 0; s0 < nsegs; s0 += ADAM_MAX_SEGS) {
+    const int n = nsegs - s0 < ADAM_MAX_SEGS ? nsegs - s0 : ADAM_MAX_SEGS;
+    int64_t chunks = 0;
+    for (int i = 0; i < n; ++i) {
+      const dlsg_adam_seg_t& sg = segs_host[s0 + i];
+      DLSG_REQUIRE(sg.rows > 0 && sg.cols > 0 && sg.p && sg.g && sg.m && sg.v, "adam_multi: empty segment %d", s0 + i);
+      int64_t per = chunk_elems / sg.cols;
+      if (per < 1) per = 1;
+      args.seg[i] = sg;
+      args.chunk_start[i] = (int32_t)chunks;
+      args.rows_per_chunk[i] = (int32_t)per;
+      chunks += (sg.rows + per - 1) / per;
+    }
+    args.chunk_start[n] = (int32_t)chunks;
+    args.nsegs = n;
+    DLSG_REQUIRE(chunks < (1ll << 31), "adam_multi: too many chunks");
+    DLSG_LAUNCH(adam_multi_kernel, (unsigned)chunks, 256, 0, (cudaStream_t)stream, args, step_dev, lr_dev, lr, beta1, beta2, eps);
+    if (int rc = check_launch("adam_multi_kernel")) return rc;
+  }
+  return 0;
 }
 
 int dlsg_lstm_cell_bwd2(const dlsg_lstm_cell_bwd2_t* p, void* stream) {

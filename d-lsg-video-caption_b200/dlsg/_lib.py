@@ -142,7 +142,7 @@ SIGNATURES = {
     'dlsg_convert2d': (i32, [vp, i32, i64, vp, i32, i64, vp, i64, i64, i64, vp]),
     'dlsg_convert2d_batched': (i32, [vp, i32, i64, vp, i32, i64, vp, i64, i64, i64, i64, i64, i64, i64, vp]),
     'dlsg_multi_convert': (i32, [vp, vp, i32, vp]),
-    'dlsg_adam_multi': (i32, [vp, vp, i32, vp, vp, f32, f32, f32, f32, vp]),
+    'dlsg_adam_multi': (i32, [vp, i32, i32, vp, vp, f32, f32, f32, f32, vp]),
     'dlsg_colsum': (i32, [vp, i32, i64, i64, i64, vp, vp]),
     'dlsg_norm_fwd': (i32, [C.POINTER(NormFwdT), vp]),
     'dlsg_norm_bwd': (i32, [C.POINTER(NormBwdT), vp]),

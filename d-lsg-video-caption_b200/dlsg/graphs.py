@@ -58,7 +58,7 @@ class GraphedTrainStep:
         finally:
             DF.WC.force = False
         self.launches = ops.backend().launches - l0          # libdlsg kernels recorded in one replay
-        self._adam_plans = list(self.adam._plans) if self.adam is not None else None     # pinned staging of the captured tables
+        self._adam_plans = list(self.adam._plans) if self.adam is not None else None     # (keeps the tensors the captured launches point at alive)
         torch.cuda.synchronize()
 
     def _record_weight_copies(self):

@@ -185,20 +185,10 @@ class CudaBackend:
         L.check(self.lib.dlsg_multi_convert(plan['segs'].data_ptr(), plan['chunks'].data_ptr(), plan['n'], _stream()),
                 'dlsg_multi_convert')
 
-    @staticmethod
-    def _upload(raw_bytes, dev):
-        """Host bytes -> device uint8 tensor through a pinned staging buffer (a graph-capturable memcpy node)."""
-        import numpy as np
-        host = torch.from_numpy(np.frombuffer(raw_bytes, dtype=np.uint8).copy()).pin_memory()
-        d = torch.empty(host.numel(), dtype=torch.uint8, device=dev)
-        d.copy_(host, non_blocking=True)
-        return d, host
-
     def make_adam_plan(self, segs, chunk_elems=16384):
-        """segs: list of dicts {p, g, m, v: 2-D fp32 views with one common pitch, dst: bf16 2-D view | None}."""
-        import numpy as np
+        """segs: list of dicts {p, g, m, v: 2-D fp32 views with one common pitch, dst: bf16 2-D view | None}.  The plan is a
+        host table: it rides to the device inside the kernel parameters (no upload; graph-capturable as is)."""
         table = (L.AdamSegT * max(1, len(segs)))()
-        chunks = []
         for i, sg in enumerate(segs):
             p_, g_, m_, v_, d_ = sg['p'], sg['g'], sg['m'], sg['v'], sg.get('dst')
             rows, cols = p_.shape
@@ -212,20 +202,14 @@ class CudaBackend:
             if d_ is not None:
                 assert d_.dtype == torch.bfloat16 and d_.shape == p_.shape and (cols == 1 or d_.stride(1) == 1)
                 e.dst16, e.ld_dst = d_.data_ptr(), (d_.stride(0) if rows > 1 else cols)
-            per = max(1, chunk_elems // max(1, cols))
-            for r0 in range(0, rows, per):
-                chunks.append((i, r0, min(per, rows - r0)))
-        dev = segs[0]['p'].device
-        seg_t, h1 = self._upload(bytes(table), dev)
-        chunk_t, h2 = self._upload(np.asarray(chunks, dtype=np.int32).tobytes(), dev)
-        return {'segs': seg_t, 'chunks': chunk_t, 'n': len(chunks), 'keep': (segs, h1, h2)}
+        return {'table': table, 'n': len(segs), 'chunk_elems': chunk_elems, 'keep': segs}
 
     def adam_multi(self, plan, step, lr, beta1, beta2, eps, lr_dev=None):
         if plan['n'] == 0:
             return
         assert step.dtype == torch.float32
-        self.launches += 1
-        L.check(self.lib.dlsg_adam_multi(plan['segs'].data_ptr(), plan['chunks'].data_ptr(), plan['n'], step.data_ptr(),
+        self.launches += (plan['n'] + 319) // 320
+        L.check(self.lib.dlsg_adam_multi(C.cast(plan['table'], C.c_void_p), plan['n'], plan['chunk_elems'], step.data_ptr(),
                                          _ptr(lr_dev), float(lr), float(beta1), float(beta2), float(eps), _stream()), 'dlsg_adam_multi')
 
     def colsum(self, x, out):

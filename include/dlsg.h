@@ -82,16 +82,17 @@ typedef struct {
   int32_t src_dtype, dst_dtype;               /* src_dtype must be DLSG_F32 */
 } dlsg_seg_t;
 int dlsg_multi_convert(const dlsg_seg_t* segs_dev, const int32_t* chunks_dev, int32_t nchunks, void* stream);
-/* Multi-tensor Adam (torch.optim.Adam semantics, no weight decay / amsgrad / maximize; run_gun.py:91,100) over a DEVICE
- * table of 2-D segments (p, g, m, v fp32 with one common pitch; dst16 = optional bf16 GEMM-operand copy of the updated
- * values with its own pitch) and a DEVICE table of int32 (segment, first row, rows) triples, one CTA each.  `step_dev`
- * holds the (already incremented) step count t as a float; the learning rate is *lr_dev when lr_dev != NULL (so a captured
- * CUDA graph follows a scheduler), else lr.  SURVEY 8f-3: the optimizer pass emits the bf16 weights.                     */
+/* Multi-tensor Adam (torch.optim.Adam semantics, no weight decay / amsgrad / maximize; run_gun.py:91,100) over a table of
+ * 2-D segments (p, g, m, v fp32 with one common pitch; dst16 = optional bf16 GEMM-operand copy of the updated values with
+ * its own pitch).  The table is a HOST array: it travels to the device inside the kernel's parameters (up to 320 segments
+ * per launch, one CTA per ~chunk_elems elements), so a CUDA graph keeps it in the kernel node and no table upload exists.
+ * `step_dev` holds the (already incremented) step count t as a float; the learning rate is *lr_dev when lr_dev != NULL (so
+ * a captured graph follows a scheduler), else lr.  SURVEY 8f-3: the optimizer pass emits the bf16 weights.               */
 typedef struct {
   float* p; const float* g; float* m; float* v; void* dst16;
   int64_t rows, cols, ld, ld_dst;
 } dlsg_adam_seg_t;
-int dlsg_adam_multi(const dlsg_adam_seg_t* segs_dev, const int32_t* chunks_dev, int32_t nchunks, const float* step_dev,
+int dlsg_adam_multi(const dlsg_adam_seg_t* segs_host, int32_t nsegs, int32_t chunk_elems, const float* step_dev,
                     const float* lr_dev, float lr, float beta1, float beta2, float eps, void* stream);
 /* out[c] += sum_r x[r,c] : bias gradients (fp32 accumulate into out)                            */
 int dlsg_colsum(const void* x, int dtype, int64_t ld, int64_t rows, int64_t cols, float* out, void* stream);
