@@ -311,6 +311,9 @@ class DecoderTrainBlock:
             dbo = small_zeros((V,), ref)
             be.colsum(dl2, dbo)
             grads[pf + 'word_restore.bias'] = dbo
+        from . import functional as _DF
+        # (data parallel) the vocabulary-projection gradients (16 M parameters, final here) travel during the BPTT
+        _DF.early_sync(grads, (pf + 'word_restore.weight', pf + 'word_restore.bias'))
         da_ext = None
         if dalpha is not None:
             da_ext = _c(dalpha.permute(1, 0, 2))                 # (T,B,nh*P)

@@ -77,21 +77,25 @@ class GradSync:
         import torch.distributed as dist
         self.dist, self.pg = dist, process_group
         self.side = torch.cuda.Stream()
+        self.skip = set()           # ids of gradient views that early_sync() already reduced in the running block backward
 
     def reduce(self, grads):
-        items = [(k, v) for k, v in grads.items() if v is not None and k not in BLOCK_INPUTS]
+        items = [(k, v) for k, v in grads.items() if v is not None and k not in BLOCK_INPUTS and id(v) not in self.skip]
         if not items:
             return grads
         uniq = {}
         for k, v in items:
             uniq.setdefault(id(v), v)
         tensors = list(uniq.values())
-        flat = torch.cat([x.reshape(-1) for x in tensors])
         cur = torch.cuda.current_stream()
         self.side.wait_stream(cur)
-        flat.record_stream(self.side)
         with torch.cuda.stream(self.side):
+            # the bucket copy runs on the side stream too: the main stream goes straight on with the next block
+            for x in tensors:
+                x.record_stream(self.side)
+            flat = torch.cat([x.reshape(-1) for x in tensors])
             self.dist.all_reduce(flat, op=self.dist.ReduceOp.AVG, group=self.pg)
+        flat.record_stream(cur)
         out, off, views = dict(grads), 0, {}
         for x in tensors:
             n = x.numel()
@@ -103,6 +107,21 @@ class GradSync:
 
     def wait(self):
         torch.cuda.current_stream().wait_stream(self.side)
+        self.skip.clear()
+
+
+def early_sync(grads, keys=None):
+    """Called by a block in the middle of its backward with the parameter gradients that are already final (everything
+    in `grads` so far): their all-reduce starts now and overlaps the rest of the block (the decoder's vocabulary-projection
+    gradients travel during its 26-step BPTT, the EncoderVisual attention gradients during the BiLSTM BPTT)."""
+    if GRAD_SYNC is None:
+        return
+    sub = grads if keys is None else {k: grads[k] for k in keys if k in grads}
+    red = GRAD_SYNC.reduce(sub)
+    for k, v in red.items():
+        if k not in BLOCK_INPUTS and v is not None:
+            GRAD_SYNC.skip.add(id(v))
+    grads.update(red)
 
 
 def run_block(block, tensors):
@@ -509,6 +528,7 @@ class EncoderVisualBlock:
         dL = empty((B, T, 2 * H), ref)
         be.norm_bwd(dYv, sv['lstm_out'].view(B * T, 2 * H), w, b, sv['stY'], dx=dL.view(B * T, 2 * H), dgamma=dw, dbeta=db,
                     drop=sv['dY'])
+        early_sync(grads)            # (data parallel) the attention / LayerNorm gradients travel during the BPTT below
         # BiLSTM BPTT
         dGin = empty((B, T, 2 * H4), ref, la.opdtype())
         gates, cs, hprev = sv['gates'], sv['cs'], sv['hprev']

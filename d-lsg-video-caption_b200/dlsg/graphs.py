@@ -84,16 +84,18 @@ class GraphedTrainStep:
                 self.pinned.refresh()             # current fp32 masters -> every operand copy, one launch
             DF.WC.pin(self.pinned)
         done = []
-        if self.adam is not None and self.world == 1:
+        if self.adam is not None:
             # the decoder's parameters (65 % of the model) are updated on a side stream the moment the first encoder block
             # starts its backward: every decoder gradient is final by then, and the bandwidth-bound update hides behind
-            # the latency-bound encoder backward
+            # the latency-bound encoder backward.  With several ranks the side stream is the gradient-sync stream: the
+            # update is queued right behind the decoder bucket's all-reduce (p.grad are views of the reduced bucket).
+            side = self.side if self.world == 1 else self.sync.side
+
             def hook(block):
                 if not done and type(block).__name__ != 'DecoderTrainBlock':
                     ps = [p for p in self.dec_params if p.grad is not None]
-                    cur = torch.cuda.current_stream()
-                    self.side.wait_stream(cur)
-                    with torch.cuda.stream(self.side):
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
                         self.adam.step(ps)
                     done.extend(ps)
             DF.BLOCK_BWD_HOOK = hook
@@ -118,7 +120,7 @@ class GraphedTrainStep:
             seen = set(id(p) for p in done)
             self.adam.step([p for p in self.params if p.grad is not None and id(p) not in seen])
             if done:
-                torch.cuda.current_stream().wait_stream(self.side)
+                torch.cuda.current_stream().wait_stream(self.side if self.world == 1 else self.sync.side)
             self.adam.refresh_residual()          # the few copies Adam cannot emit itself (summed bias pairs)
         return loss.detach()
 

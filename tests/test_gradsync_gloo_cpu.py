@@ -20,9 +20,14 @@ class _CpuSync:
     def __init__(self):
         from dlsg import functional as DF
         self.inputs = DF.BLOCK_INPUTS
+        self.skip = set()           # filled by DF.early_sync (mid-backward reductions of already-final gradients)
+        self.calls = 0
 
     def reduce(self, grads):
-        items = [(k, v) for k, v in grads.items() if v is not None and k not in self.inputs]
+        self.calls += 1
+        items = [(k, v) for k, v in grads.items() if v is not None and k not in self.inputs and id(v) not in self.skip]
+        if not items:
+            return grads
         uniq = {}
         for k, v in items:
             uniq.setdefault(id(v), v)
@@ -62,6 +67,7 @@ def _worker(rank, world, port, q):
     out = net(frames, regions, caps, args.max_words, 1.0)[0]
     DF.GRAD_SYNC = _CpuSync()
     O.packed_ce_loss(out, caps, lens).backward()
+    assert DF.GRAD_SYNC.calls >= 5, 'expected the early (mid-backward) reductions on top of one per block'
     DF.GRAD_SYNC = None
     sd = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
     for r in range(world):
