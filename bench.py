@@ -135,10 +135,40 @@ def run_reference(a):
     print(json.dumps(line))
 
 
+_STAGE = ['start']
+_T0 = time.time()
+
+
+def stage(name):
+    """Progress marker on stderr (one line per stage, rank-tagged): a stalled multi-rank run can be located from the log."""
+    _STAGE[0] = name
+    sys.stderr.write('[bench rank %s +%.1fs] %s\n' % (os.environ.get('RANK', '0'), time.time() - _T0, name))
+    sys.stderr.flush()
+
+
+def arm_watchdog(a):
+    """A run that has not printed its line after DLSG_BENCH_TIMEOUT seconds (default 420) reports where it stalled and exits,
+    instead of sitting in a collective until the caller's own limit kills it."""
+    limit = float(os.environ.get('DLSG_BENCH_TIMEOUT', '420'))
+
+    def fire():
+        if int(os.environ.get('RANK', '0')) == 0:
+            print(json.dumps({'metric': METRIC, 'value': None, 'unit': 'clips/s', 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
+                              'error': 'no result after %.0f s; last stage: %s' % (limit, _STAGE[0])}), flush=True)
+        sys.stderr.write('[bench rank %s] watchdog: stalled in stage %r\n' % (os.environ.get('RANK', '0'), _STAGE[0]))
+        sys.stderr.flush()
+        os._exit(3)
+    t = threading.Timer(limit, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def main():
     a = parse()
     if a.impl == 'reference':
         return run_reference(a)
+    watchdog = arm_watchdog(a)
     import contextlib
     import io
     from dlsg import synth, ops, losses, linalg as la
@@ -151,8 +181,14 @@ def main():
     dev = torch.device('cuda', local)
     dist = None
     if world > 1:
+        import datetime
         import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=dev)
+        # user-buffer registration for captured collectives only applies to VMM allocations (not the caching allocator's):
+        # switch the attempt off; a collective that cannot complete aborts after 3 minutes instead of hanging
+        os.environ.setdefault('NCCL_GRAPH_REGISTER', '0')
+        stage('init_process_group(nccl) world=%d' % world)
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
+        stage('process group ready')
     la.set_precision('bf16')
     args = synth.msr_args(train_batch_size=a.batch)
     B = a.batch
@@ -166,6 +202,7 @@ def main():
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], find_unused_parameters=True,
                                                           gradient_as_bucket_view=True)
     opt = torch.optim.Adam(net.parameters(), lr=1.6e-4, betas=(0.5, 0.9), fused=True, capturable=use_graph)
+    stage('model built; generating synthetic inputs')
     frames, regions, caps, lens = synth.make_inputs(B, args, V_MSR, seed=12 + rank)
     h_fr, h_rg, h_cp = frames.pin_memory(), regions.pin_memory(), caps.pin_memory()
     d_fr, d_rg, d_cp = h_fr.to(dev), h_rg.to(dev), h_cp.to(dev)
@@ -217,6 +254,7 @@ def main():
                 step(d_fr, d_rg, d_cp)
             eager_ms = timed(lambda: step(d_fr, d_rg, d_cp), 3)
         l0 = be.launches
+        stage('capturing the training step (eager warm-up steps first when world > 1)')
         gs = GraphedTrainStep(net, opt, d_fr, d_rg, d_cp, lens, 26, 1.0,
                               process_group=(dist.group.WORLD if dist is not None else None), warmup=(0 if world == 1 else 3))
         launches = gs.launches
@@ -234,8 +272,10 @@ def main():
             rg = h_rg.to(dev, non_blocking=True)
             cp = h_cp.to(dev, non_blocking=True)
             return step(fr, rg, cp).item()
+    stage('warm-up replays')
     for _ in range(a.warmup):
         run_dev()
+    stage('timed region: %d steps' % a.steps)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -245,6 +285,7 @@ def main():
         launches = (be.launches - l0) // a.steps
     clocks = sampler.stop() if rank == 0 else None
     # ---- end-to-end: host pinned inputs -> H2D -> step -> loss.item()
+    stage('end-to-end (host inputs) timing')
     for _ in range(2):
         e2e_step()
     ms_e2e_serial = timed(e2e_step, a.steps)
@@ -319,6 +360,7 @@ def main():
                 'ms_per_launch': k_ms, 'launches_per_step': 1}
         del A, Wt, O_
         # ---- decoding throughput (secondary metrics of BASELINE.json: greedy B=256, beam-5 B=128)
+        stage('secondary metrics (roofline kernel, decode, GAN iteration, CPU baseline)')
         if not a.no_decode and world == 1:
             net.eval()
             with torch.no_grad():
@@ -364,6 +406,8 @@ def main():
         t = cpu_port_step_time(sb, 2, 1, threads)
         cpu = {'value': sb / t, 'unit': 'clips/s', 'cores': threads, 'kind': 'port',
                'sample': '%d clips per step x 2 steps, fwd+CE+bwd+Adam, oracle/dlsg_oracle.py (torch CPU fp32)' % sb}
+    stage('done')
+    watchdog.cancel()
     if rank == 0:
         line = {'metric': METRIC, 'value': world * B / (ms * 1e-3), 'unit': 'clips/s', 'n_gpus': world, 'steps': a.steps,
                 'warmup': a.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
