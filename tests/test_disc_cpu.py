@@ -121,3 +121,46 @@ def test_disc_grouped_forward_equals_separate_calls(golden_dir):
     gb = torch.autograd.grad(out[2 * B:].sum(), mixed_b)[0]
     assert (out.detach() - torch.cat([s.detach() for s in sep])).abs().max() < 1e-5
     assert (ga - gb).abs().max() < 1e-6
+
+
+def test_gan_iteration_stacked_critic_calls_match_separate_calls():
+    """dlsg.gan.GanIteration on CPU (kernels emulated, eval mode, same WGAN-GP epsilon draws): running the three critic
+    calls of every critic step as ONE stacked forward (batched=True) must give the same four logged scalars and the same
+    updated critic / generator weights as the literal run_gun.py sequence of separate calls (batched=False)."""
+    import contextlib
+    import io
+    import models.model as M
+    from dlsg.gan import GanIteration
+    args = synth.small_args(visual_hidden_size=1024, region_projected_size=1024, query_hidden_size=1024, max_words=5, max_frames=4)
+    V, B = 37, 3
+    frames, regions, caps, lens = synth.make_inputs(B, args, V, seed=21)
+    results = []
+    for batched in (True, False):
+        DF.WC.clear()
+        with contextlib.redirect_stdout(io.StringIO()):
+            G_ = M.CapGnnModel(args, synth.Vocab(V))
+        D_ = M.DiscV2(args, V)
+        synth.fill_state_dict(G_)
+        synth.fill_state_dict(D_, prefix='D.')
+        G_.eval()
+        D_.eval()
+        og = torch.optim.Adam(G_.parameters(), lr=1.6e-4, betas=(0.5, 0.9))
+        od = torch.optim.Adam(D_.parameters(), lr=1.6e-4, betas=(0.5, 0.9))
+        it = GanIteration(G_, D_, og, od, frames, regions, caps, lens, args.max_words, 1.0, num_d=2, gan_lambda=0.05,
+                          graph=False, batched=batched)
+        torch.manual_seed(77)
+        outs = [[float(x) for x in it()] for _ in range(2)]
+        results.append((outs, {k: p.detach().clone() for k, p in D_.named_parameters()},
+                        {k: p.detach().clone() for k, p in G_.named_parameters()}))
+    (oa, da, ga), (ob, db, gb) = results
+    for ra, rb in zip(oa, ob):
+        for x, y in zip(ra, rb):
+            assert abs(x - y) <= 2e-4 * max(1.0, abs(y)), (oa, ob)
+    assert oa[1] != oa[0]                                           # the second iteration sees updated weights
+    # Adam normalises every gradient component by its own magnitude: where |g| is at the 1e-8 epsilon, summation-order noise
+    # between the stacked and the separate products moves an element by a fraction of lr per step.  Bound: 2 * lr over
+    # the 4 critic / 2 generator updates, and all but a few (< 2 %) elements of every tensor must agree to 1e-6.
+    for name, a_, b_ in [(k, da[k], db[k]) for k in da] + [(k, ga[k], gb[k]) for k in ga]:
+        d = (a_ - b_).abs()
+        assert d.max() < 3.2e-4, name
+        assert (d > 1e-6).float().mean() < 2e-2, name
