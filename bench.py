@@ -164,10 +164,63 @@ def arm_watchdog(a):
     return t
 
 
+# ---- multi-rank supervisor -------------------------------------------------------------------------------------------
+# The only 8-GPU attempt of round 1 stalled after NCCL's start-up line and could not be investigated.  For
+# world >= 4 every rank therefore runs the measurement in a child process and, if the children have not finished inside a
+# fixed wall-clock window, kills them and tries the next, more conservative configuration.  The windows are absolute
+# (measured from process start, which torchrun makes simultaneous on all ranks), so every rank switches at the same time.
+TIERS = [('cuda-graph step, gradient all-reduce inside the graph', {}, []),
+         ('cuda-graph step, gradient all-reduce inside the graph, NCCL_NVLS_ENABLE=0', {'NCCL_NVLS_ENABLE': '0'}, []),
+         ('eager DistributedDataParallel step, NCCL_NVLS_ENABLE=0', {'NCCL_NVLS_ENABLE': '0'}, ['--graph', '0'])]
+
+
+def supervise(a):
+    win = [float(x) for x in os.environ.get('DLSG_BENCH_TIER_SECONDS', '120,120,150').split(',')]
+    base_port = int(os.environ.get('MASTER_PORT', '29500'))
+    rank0 = int(os.environ.get('RANK', '0')) == 0
+    t_open = 0.0
+    for i, (name, env_add, extra) in enumerate(TIERS):
+        t_close = t_open + win[min(i, len(win) - 1)]
+        delay = _T0 + t_open - time.time()
+        if delay > 0:
+            time.sleep(delay)                         # every rank opens tier i at the same wall-clock time
+        env = dict(os.environ)
+        env.update(env_add)
+        env.update(DLSG_BENCH_WORKER='1', DLSG_BENCH_TIER=name, DLSG_BENCH_TIER_INDEX=str(i))
+        if i > 0:                                     # fresh rendezvous: rank 0's worker hosts a new store on another port
+            env['MASTER_PORT'] = str(base_port + 17 * i)
+            env['TORCHELASTIC_USE_AGENT_STORE'] = 'False'
+        stage('supervisor: tier %d (%s)' % (i, name))
+        child = subprocess.Popen([sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + extra, env=env)
+        rc = None
+        try:
+            rc = child.wait(timeout=max(1.0, _T0 + t_close - time.time()))
+        except subprocess.TimeoutExpired:
+            child.kill()
+            child.wait()
+        if rc == 0:
+            return 0
+        stage('supervisor: tier %d %s' % (i, 'timed out' if rc is None else 'exited with %s' % rc))
+        t_open = t_close + float(os.environ.get('DLSG_BENCH_TIER_GAP', '8'))   # let the killed workers' GPU contexts disappear
+    if rank0:
+        print(json.dumps({'metric': METRIC, 'value': None, 'unit': 'clips/s', 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
+                          'error': 'no multi-rank configuration finished (see the stage log on stderr)'}), flush=True)
+    return 3
+
+
 def main():
     a = parse()
     if a.impl == 'reference':
         return run_reference(a)
+    if int(os.environ.get('WORLD_SIZE', '1')) >= 4 and os.environ.get('DLSG_BENCH_WORKER') != '1':
+        sys.exit(supervise(a))
+    fake = os.environ.get('DLSG_BENCH_FAKE')          # supervisor self-test hook (tests/test_bench_supervisor_cpu.py)
+    if fake is not None:
+        if os.environ.get('DLSG_BENCH_TIER_INDEX', '0') in fake.split(','):
+            time.sleep(3600)
+        print(json.dumps({'fake': True, 'tier': os.environ.get('DLSG_BENCH_TIER'), 'port': os.environ.get('MASTER_PORT'),
+                          'nvls': os.environ.get('NCCL_NVLS_ENABLE'), 'argv': sys.argv[1:]}), flush=True)
+        return
     watchdog = arm_watchdog(a)
     import contextlib
     import io
@@ -415,6 +468,7 @@ def main():
                 'config': {'workload': 'D-LSG training step (CapGnnModel fwd + masked CE + bwd + Adam), batch %d/GPU, MSR-VTT-shaped '
                                        'synthetic features (26 frames, 1536+2048-d, 36x2048 regions, V=%d), bf16 GEMMs fp32 accum' % (B, V_MSR),
                            'global_batch': world * B, 'parallelism': 'dp%d' % world,
+                           'multi_rank_path': os.environ.get('DLSG_BENCH_TIER', TIERS[0][0] if use_graph else TIERS[2][0]) if world > 1 else None,
                            'l2': 'inputs (490 MB regions/step) exceed the 126 MB L2; no explicit flush'},
                 'e2e': {'value': world * B / (ms_e2e * 1e-3), 'unit': 'clips/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                         'ms_per_step': ms_e2e, 'mode': 'H2D of step k+1 prefetched on a copy stream during step k' if use_graph else 'serial',
