@@ -312,3 +312,41 @@ def test_adam_driver_matches_torch_adam_and_emits_operand_copies():
     for src, src2, dst in pinned.pairs:
         want = (src if src2 is None else src + src2).to(dst.dtype)
         assert torch.equal(want, dst)
+
+
+@pytest.mark.parametrize('tag,args,V,B', CASES)
+def test_decoder_contract_methods_the_callers_use(tag, args, V, B):
+    """What evaluate.py / run_gun.py / the reference BeamSearch call on the decoder besides forward:
+    `beam_step` as the AllenNLP step callable (layer.py:489-567) driven by the generic BeamSearch.search must give the
+    oracle's all-beam predictions and scores; `decode_tokens` (layer.py:464-477) stops at <end> for lists and tensors;
+    the two embedding helpers (layer.py:479-487)."""
+    la.set_precision('fp32')
+    net = _build('CapGnnModel', args, V)
+    net.eval()
+    sd = _sd(net)
+    frames, regions, caps, lens = synth.make_inputs(B, args, V, seed=12)
+    dec = net.decoder
+    with torch.no_grad():
+        robj, rmot = O.cap_gnn_encoder(sd, frames, regions, args.a_feature_size)
+        o, m = net.encoder(frames, regions)
+        for bm in (3, 5):
+            net.update_beam_size(bm)
+            dec.batch_size = B
+            z = lambda h: o.new_zeros(B, h)
+            st = {'query_lstm_h': z(args.query_hidden_size), 'query_lstm_c': z(args.query_hidden_size),
+                  'lang_lstm_h': z(args.decode_hidden_size), 'lang_lstm_c': z(args.decode_hidden_size),
+                  'cnn_feats': o, 'global_feat': torch.cat([o.mean(1), m.mean(1)], -1), 'cnn_feats_2': m}
+            preds, lp = dec.beam_search.search(torch.full((B,), 1, dtype=torch.long), st, dec.beam_step)
+            rbest, rall, rlp = O.decoder_beam(sd, 'decoder', robj, rmot, args.max_words, bm)
+            assert torch.equal(preds, rall)
+            assert (lp - rlp).abs().max() < 1e-4
+    # decode_tokens: words up to (not including) the first <end>; accepts a python list or a tensor
+    ids = [5, 9, 4, synth.END, 7, 7]
+    want = ' '.join(dec.vocab.idx2word[i] for i in ids[:3])
+    assert dec.decode_tokens(ids) == want == dec.decode_tokens(torch.tensor(ids))
+    assert dec.decode_tokens([synth.END, 5]) == '' and dec.decode_tokens([6, 8]) == 'w6 w8'
+    # embedding helpers
+    emb = dec.caption2wordembedding(caps)
+    assert torch.equal(emb, sd['decoder.word_embed.weight'][caps]) and not emb.requires_grad
+    probs = torch.softmax(torch.randn(B, 4, V, generator=torch.Generator().manual_seed(1)), -1)
+    assert (dec.output2wordembedding(probs) - probs @ sd['decoder.word_embed.weight']).abs().max() < 1e-5
