@@ -1,9 +1,10 @@
+"""models/__init__.py of the reference (:1-8): `setup(opt, vocab)` looks up `models.<opt.model>.CapModel`.  (The reference's
+default opt.model = 'RMN' names no module, so its factory always raises: same behaviour here.)"""
+import importlib
+
+
 def setup(opt, vocab):
-    """Same dynamic factory as the reference's models/__init__.py:1-8 (opt.model names a module holding CapModel)."""
-    import importlib
     try:
-        mod = importlib.import_module('models.{}'.format(opt.model))
-        model = getattr(mod, 'CapModel')(opt, vocab)
+        return getattr(importlib.import_module('models.%s' % opt.model), 'CapModel')(opt, vocab)
     except Exception:
         raise Exception("Model not supported: {}".format(opt.model))
-    return model

@@ -5,7 +5,7 @@ Live classes (reference line numbers): EncoderVisual :7-61, EncoderVisualGraphTU
 Decoder :276-602, PSLScore2 :661-715.  Dead alternates kept importable with identical parameters:
 EncoderVisualGraph :64-136, EncoderVisualGAT :204-272, PSLScore :605-658.
 """
-from models.sublayer import *
+from models.sublayer import *              # noqa: F401,F403  (the reference's layer.py re-exports sublayer the same way)
 from models.allennlp_beamsearch import BeamSearch
 import random
 import os
@@ -14,6 +14,7 @@ from collections import OrderedDict
 from dlsg import functional as DF
 from dlsg import decoder as DD
 from dlsg import generic as G
+from dlsg.modspec import declare, lin, tanh_norm, lin_tanh_norm
 
 
 def _named(module, prefix=''):
@@ -23,37 +24,29 @@ def _named(module, prefix=''):
 
 class EncoderVisual(nn.Module):
     def __init__(self, args, input_type='frame+motion', embed=True, baseline=False):
-        super(EncoderVisual, self).__init__()
-        self.embed = embed
-        hidden_size = args.visual_hidden_size
-        self.hidden_size = hidden_size
+        super().__init__()
+        H = self.hidden_size = args.visual_hidden_size
+        self.embed, self.baseline = embed, baseline
         if embed:
-            input_size = args.a_feature_size + args.m_feature_size
-            if input_type == 'object':
-                input_size = args.a_feature_size
-            if input_type == 'motion':
-                input_size = args.m_feature_size
-            self.input_size = input_size
+            self.input_size = {'object': args.a_feature_size, 'motion': args.m_feature_size}.get(
+                input_type, args.a_feature_size + args.m_feature_size)
             print('batch size', args.train_batch_size)
-            self.linear_embed = nn.Linear(input_size, hidden_size)
-            nn.init.xavier_normal_(self.linear_embed.weight)
-        self.lstm = nn.LSTM(hidden_size, hidden_size, batch_first=True, bidirectional=True)
-        self.layernorm_lstm = nn.LayerNorm(hidden_size * 2)
-        self.drop_lstm = nn.Dropout(args.dropout)
-        self.baseline = baseline
-        if not self.baseline:
-            self.self_attention = SelfAttention(hidden_size * 2, hidden_size * 2, hidden_size, args.dropout, True)
-            self.layernorm_sa = nn.LayerNorm(hidden_size)
-            self.drop_sa = nn.Dropout(args.dropout)
+        p = args.dropout
+        declare(self, [('linear_embed', (lambda: lin(self.input_size, H, xavier_normal=True)) if embed else None),
+                       ('lstm', lambda: nn.LSTM(H, H, batch_first=True, bidirectional=True)),
+                       ('layernorm_lstm', lambda: nn.LayerNorm(2 * H)),
+                       ('drop_lstm', lambda: nn.Dropout(p))])
+        if baseline:
+            self.out_try = lin(2 * H, H, xavier_normal=True)
         else:
-            self.out_try = nn.Linear(hidden_size * 2, hidden_size)
-            nn.init.xavier_normal_(self.out_try.weight)
+            declare(self, [('self_attention', lambda: SelfAttention(2 * H, 2 * H, H, p, True)),
+                           ('layernorm_sa', lambda: nn.LayerNorm(H)),
+                           ('drop_sa', lambda: nn.Dropout(p))])
 
     def _init_lstm_state(self, d):
-        batch_size = d.size(0)
-        lstm_state_h = d.data.new(2, batch_size, self.hidden_size).zero_()
-        lstm_state_c = d.data.new(2, batch_size, self.hidden_size).zero_()
-        return lstm_state_h, lstm_state_c
+        """Zero (h, c) for the two directions (layer.py:40-44); the fused BiLSTM starts from zeros implicitly."""
+        z = d.new_zeros(2, d.size(0), self.hidden_size)
+        return z, z.clone()
 
     def forward(self, inputs):
         if not self.embed:
@@ -66,25 +59,30 @@ class EncoderVisual(nn.Module):
         return DF.run_block(blk, t)[0]
 
 
+def _graph_encoder_parts(self, args, input_type, use_embed, baseline):
+    """Parameter containers shared by the three graph-encoder variants of the reference (layer.py:64-136, 139-201, 204-272),
+    in the reference's registration order up to and including `obj_visual_norm`."""
+    H = args.visual_hidden_size
+    self.baseline, self.use_embed = baseline, use_embed
+    with_regions = args.num_obj > 4
+    vis_in = args.m_feature_size if input_type == 'motion' else args.a_feature_size
+    declare(self, [('obj_embed', (lambda: lin(args.region_feature_size, args.region_projected_size)) if with_regions else None),
+                   ('obj_norm', (lambda: tanh_norm(args.region_projected_size)) if with_regions else None),
+                   ('visual_embed', (lambda: lin(vis_in, H)) if use_embed else None),
+                   ('visual_norm', lambda: tanh_norm(H)),
+                   ('obj_visual_norm', lambda: tanh_norm(H))])
+    return H
+
+
 class EncoderVisualGraph(nn.Module):
     """Dead alternate (reference layer.py:64-136, commented out in model.py:61). Parameters only."""
 
     def __init__(self, args, input_type='motion', use_embed=True, baseline=False):
-        super(EncoderVisualGraph, self).__init__()
-        self.baseline = baseline
-        H = args.visual_hidden_size
-        if args.num_obj > 4:
-            self.obj_embed = nn.Linear(args.region_feature_size, args.region_projected_size)
-            self.obj_norm = nn.Sequential(nn.Tanh(), nn.LayerNorm(args.region_projected_size))
-        visual_input_size = args.m_feature_size if input_type == 'motion' else args.a_feature_size
-        self.use_embed = use_embed
-        if self.use_embed:
-            self.visual_embed = nn.Linear(visual_input_size, H)
-        self.visual_norm = nn.Sequential(nn.Tanh(), nn.LayerNorm(H))
-        self.obj_visual_norm = nn.Sequential(nn.Tanh(), nn.LayerNorm(H))
-        self.v2l_layer = LatentPSL(H, args.num_proposals)
-        self.att_l2l = SelfAttention(H, H, H, args.dropout)
-        self.att_l2l_norm = nn.LayerNorm(H)
+        super().__init__()
+        H = _graph_encoder_parts(self, args, input_type, use_embed, baseline)
+        declare(self, [('v2l_layer', lambda: LatentPSL(H, args.num_proposals)),
+                       ('att_l2l', lambda: SelfAttention(H, H, H, args.dropout)),
+                       ('att_l2l_norm', lambda: nn.LayerNorm(H))])
 
     def forward(self, visual_feats, obj_feats):
         raise NotImplementedError('EncoderVisualGraph is a dead alternate in the reference (model.py:61 is commented '
@@ -93,34 +91,14 @@ class EncoderVisualGraph(nn.Module):
 
 class EncoderVisualGraphTUN(nn.Module):
     def __init__(self, args, input_type='motion', use_embed=True, baseline=False):
-        super(EncoderVisualGraphTUN, self).__init__()
-        self.baseline = baseline
-        if args.num_obj > 4:
-            self.obj_embed = nn.Linear(args.region_feature_size, args.region_projected_size)
-            self.obj_norm = nn.Sequential(
-                nn.Tanh(),
-                nn.LayerNorm(args.region_projected_size)
-            )
-        visual_input_size = args.m_feature_size
-        if input_type != 'motion':
-            visual_input_size = args.a_feature_size
-        self.use_embed = use_embed
-        if self.use_embed:
-            self.visual_embed = nn.Linear(visual_input_size, args.visual_hidden_size)
-        self.visual_norm = nn.Sequential(
-            nn.Tanh(),
-            nn.LayerNorm(args.visual_hidden_size)
-        )
-        self.obj_visual_norm = nn.Sequential(
-            nn.Tanh(),
-            nn.LayerNorm(args.visual_hidden_size),
-        )
-        self.v2l_layer = LatentPSL(args.visual_hidden_size, args.num_proposals)
-        self.att_l2l_norm = nn.LayerNorm(args.visual_hidden_size)
-        self.norm_func = F.normalize
-        self.drop_o2v = nn.Dropout(args.dropout)
-        self.drop_v2l = nn.Dropout(args.dropout)
+        super().__init__()
+        H = _graph_encoder_parts(self, args, input_type, use_embed, baseline)
         self.num_proposals = args.num_proposals
+        self.norm_func = F.normalize
+        declare(self, [('v2l_layer', lambda: LatentPSL(H, args.num_proposals)),
+                       ('att_l2l_norm', lambda: nn.LayerNorm(H)),          # constructed, never used (reference quirk)
+                       ('drop_o2v', lambda: nn.Dropout(args.dropout)),
+                       ('drop_v2l', lambda: nn.Dropout(args.dropout))])
 
     def _used(self, prefix=''):
         """Parameters that take part in forward (att_l2l_norm never does - reference quirk)."""
@@ -148,22 +126,12 @@ class EncoderVisualGAT(nn.Module):
     """Dead alternate (reference layer.py:204-272, commented out in model.py:62). Parameters only."""
 
     def __init__(self, args, input_type='motion', use_embed=True, baseline=False):
-        super(EncoderVisualGAT, self).__init__()
-        self.baseline = baseline
-        H = args.visual_hidden_size
-        if args.num_obj > 4:
-            self.obj_embed = nn.Linear(args.region_feature_size, args.region_projected_size)
-            self.obj_norm = nn.Sequential(nn.Tanh(), nn.LayerNorm(args.region_projected_size))
-        visual_input_size = args.m_feature_size if input_type == 'motion' else args.a_feature_size
-        self.use_embed = use_embed
-        if self.use_embed:
-            self.visual_embed = nn.Linear(visual_input_size, H)
-        self.visual_norm = nn.Sequential(nn.Tanh(), nn.LayerNorm(H))
-        self.obj_visual_norm = nn.Sequential(nn.Tanh(), nn.LayerNorm(H))
-        self.o2v_gat = GraphAttentionLayer(H, H, args.dropout)
-        self.v2l_layer = LatentPSL(H, args.num_proposals)
-        self.att_l2l = SelfAttention(H, H, H, args.dropout)
-        self.att_l2l_norm = nn.LayerNorm(H)
+        super().__init__()
+        H = _graph_encoder_parts(self, args, input_type, use_embed, baseline)
+        declare(self, [('o2v_gat', lambda: GraphAttentionLayer(H, H, args.dropout)),
+                       ('v2l_layer', lambda: LatentPSL(H, args.num_proposals)),
+                       ('att_l2l', lambda: SelfAttention(H, H, H, args.dropout)),
+                       ('att_l2l_norm', lambda: nn.LayerNorm(H))])
 
     def forward(self, visual_feats, obj_feats):
         raise NotImplementedError('EncoderVisualGAT is a dead alternate in the reference (model.py:62 is commented out)')
@@ -171,65 +139,48 @@ class EncoderVisualGAT(nn.Module):
 
 class Decoder(nn.Module):
     def __init__(self, args, vocab, multi_modal=False, baseline=False, use_fusion=False):
-        super(Decoder, self).__init__()
-        self.word_size = args.word_size
-        self.max_words = args.max_words
-        self.vocab = vocab
-        self.dataset = args.dataset
-        self.vocab_size = len(vocab)
-        self.beam_size = args.beam_size
-        self.batch_size = args.train_batch_size
-        self.query_hidden_size = args.query_hidden_size
-        self.decode_hidden_size = args.decode_hidden_size
-        self.multi_modal = multi_modal
-        self.use_fusion = use_fusion
-        if multi_modal and use_fusion:
-            self.beta_fusion = nn.Sequential(nn.Linear(2 * args.visual_hidden_size, 1), nn.Sigmoid())
-        self.word_embed = nn.Embedding(self.vocab_size, self.word_size)
+        super().__init__()
+        H, W, Hq, Hd, p = args.visual_hidden_size, args.word_size, args.query_hidden_size, args.decode_hidden_size, args.dropout
+        self.vocab, self.vocab_size, self.dataset = vocab, len(vocab), args.dataset
+        self.word_size, self.max_words, self.beam_size, self.batch_size = W, args.max_words, args.beam_size, args.train_batch_size
+        self.query_hidden_size, self.decode_hidden_size = Hq, Hd
+        self.multi_modal, self.use_fusion = multi_modal, use_fusion
+        two_heads = multi_modal and not use_fusion
+        query_in = H + W + Hd + (0 if baseline else H)            # [lang_h | global feature (H or 2H) | word]
+        lang_in = H + Hq + (H if two_heads else 0)                # [ctx (| ctx2) | q]
+        att = lambda: AttentionShare(input_value_size=H, input_key_size=Hq, output_size=H)
+        declare(self, [('beta_fusion', (lambda: nn.Sequential(lin(2 * H, 1), nn.Sigmoid())) if (multi_modal and use_fusion) else None),
+                       ('word_embed', lambda: nn.Embedding(self.vocab_size, W))])
         if args.use_glove:
             self.get_glove_embedding()
-        self.word_drop = nn.Dropout(p=args.dropout)
-        query_input_size = args.visual_hidden_size + args.word_size + args.decode_hidden_size
-        if baseline is False:
-            query_input_size += args.visual_hidden_size
-        self.query_lstm = nn.LSTMCell(query_input_size, args.query_hidden_size)
-        self.query_lstm_layernorm = nn.LayerNorm(args.query_hidden_size)
-        self.query_lstm_drop = nn.Dropout(p=args.dropout)
-        lang_decode_hidden_size = args.visual_hidden_size + args.query_hidden_size
-        if self.multi_modal and self.use_fusion is False:
-            lang_decode_hidden_size += args.visual_hidden_size
-        self.lang_lstm = nn.LSTMCell(lang_decode_hidden_size, args.decode_hidden_size)
-        self.lang_lstm_layernorm = nn.LayerNorm(args.decode_hidden_size)
-        self.lang_lstm_drop = nn.Dropout(p=args.dropout)
-        self.context_att = AttentionShare(input_value_size=args.visual_hidden_size,
-                                          input_key_size=args.query_hidden_size,
-                                          output_size=args.visual_hidden_size)
-        self.context_layernorm = nn.LayerNorm(args.decode_hidden_size)
-        if self.multi_modal:
-            self.context_att_2 = AttentionShare(input_value_size=args.visual_hidden_size,
-                                                input_key_size=args.query_hidden_size,
-                                                output_size=args.visual_hidden_size)
-        self.word_restore = nn.Linear(args.decode_hidden_size, self.vocab_size)
-        nn.init.xavier_normal_(self.word_restore.weight)
-        self.beam_search = BeamSearch(vocab('<end>'), self.max_words, self.beam_size, per_node_beam_size=self.beam_size)
+        declare(self, [('word_drop', lambda: nn.Dropout(p=p)),
+                       ('query_lstm', lambda: nn.LSTMCell(query_in, Hq)),
+                       ('query_lstm_layernorm', lambda: nn.LayerNorm(Hq)),
+                       ('query_lstm_drop', lambda: nn.Dropout(p=p)),
+                       ('lang_lstm', lambda: nn.LSTMCell(lang_in, Hd)),
+                       ('lang_lstm_layernorm', lambda: nn.LayerNorm(Hd)),
+                       ('lang_lstm_drop', lambda: nn.Dropout(p=p)),
+                       ('context_att', att),
+                       ('context_layernorm', lambda: nn.LayerNorm(Hd)),      # constructed, never used (reference quirk)
+                       ('context_att_2', att if multi_modal else None),
+                       ('word_restore', lambda: lin(Hd, self.vocab_size, xavier_normal=True))])
+        self.update_beam_size(self.beam_size)
 
     def update_beam_size(self, beam_size):
         self.beam_size = beam_size
         self.beam_search = BeamSearch(self.vocab('<end>'), self.max_words, beam_size, per_node_beam_size=beam_size)
 
     def get_glove_embedding(self):
-        glove_np_path = f'./data/{self.dataset}_glove.npy'
-        if not os.path.exists(glove_np_path):
-            raise FileNotFoundError('%s not found (GloVe table is prepared offline by the reference, layer.py:352-386)'
-                                    % glove_np_path)
-        weight_matrix = torch.from_numpy(np.load(glove_np_path))
-        self.word_embed.load_state_dict({'weight': weight_matrix})
+        """Load the (V, word_size) GloVe table the reference prepares offline (layer.py:352-386) into word_embed."""
+        path = './data/%s_glove.npy' % self.dataset
+        if not os.path.exists(path):
+            raise FileNotFoundError('%s not found (GloVe table is prepared offline by the reference, layer.py:352-386)' % path)
+        self.word_embed.load_state_dict({'weight': torch.from_numpy(np.load(path))})
 
     def _init_lstm_state(self, d, hidden_size):
-        batch_size = d.size(0)
-        lstm_state_h = d.data.new(batch_size, hidden_size).zero_()
-        lstm_state_c = d.data.new(batch_size, hidden_size).zero_()
-        return lstm_state_h, lstm_state_c
+        """Zero (h, c) of one LSTMCell (layer.py:388-392)."""
+        z = d.new_zeros(d.size(0), hidden_size)
+        return z, z.clone()
 
     def _used(self):
         """Parameters that take part in decoding (context_layernorm never does - reference quirk)."""
@@ -273,16 +224,11 @@ class Decoder(nn.Module):
         return outputs, None
 
     def decode_tokens(self, tokens):
-        '''convert word index to caption'''
-        if torch.is_tensor(tokens):
-            tokens = tokens.tolist()                     # one D2H copy instead of one sync per token
-        words = []
+        """Word ids -> caption string, up to (not including) the first <end> (layer.py:464-477)."""
+        ids = tokens.tolist() if torch.is_tensor(tokens) else list(tokens)       # one D2H copy, not one sync per token
         end = self.vocab('<end>')
-        for token in tokens:
-            if token == end:
-                break
-            words.append(self.vocab.idx2word[token])
-        return ' '.join(words)
+        n = ids.index(end) if end in ids else len(ids)
+        return ' '.join(self.vocab.idx2word[i] for i in ids[:n])
 
     def caption2wordembedding(self, caption):
         with torch.no_grad():
@@ -308,15 +254,13 @@ class Decoder(nn.Module):
 
 class _PSLBase(nn.Module):
     def __init__(self, num_psl, num_top):
-        super(_PSLBase, self).__init__()
-        self.psl_scorer = JointEmbedVideoModel2(512)
-        self.psl_embed = nn.Sequential(nn.Linear(1024, 512), nn.Tanh(), nn.LayerNorm(512))
-        self.psl_norm = nn.Sequential(nn.Tanh(), nn.LayerNorm(512), nn.Dropout(0.3))
-        self.att_norm = nn.Sequential(nn.Linear(512, 512), nn.Tanh(), nn.LayerNorm(512))
+        super().__init__()
+        declare(self, [('psl_scorer', lambda: JointEmbedVideoModel2(512)),
+                       ('psl_embed', lambda: lin_tanh_norm(1024, 512)),
+                       ('psl_norm', lambda: tanh_norm(512, 0.3)),
+                       ('att_norm', lambda: lin_tanh_norm(512, 512))])
         self.num_top = num_top
-        self.select = True
-        if num_psl <= self.num_top:
-            self.select = False
+        self.select = num_psl > num_top                       # keep the top-`num_top` nodes by attention mass (layer.py:684-686)
 
     def _common(self, psl, psl_alpha, att_out):
         bs = psl.size(0)

@@ -1,40 +1,31 @@
-"""Drop-in mirror of the reference's models/sublayer.py (same class names, ctor arguments,
-state_dict keys, init conventions).  torch.nn containers only HOLD parameters here; the arithmetic
-of the live classes runs in libdlsg kernels via dlsg.functional / dlsg.generic.
+"""Drop-in mirror of the reference's models/sublayer.py: same class names, constructor arguments, state_dict keys and
+initialisation.  The torch.nn containers only HOLD parameters (declared through dlsg.modspec tables); the arithmetic of the
+live classes runs in libdlsg kernels via dlsg.generic.
 
-Live:  AttentionShare :10-43, SelfAttention :46-82, PositionalEncoding_old :85-104, ResBlock :107-119,
-       LatentPSL :176-198, JointEmbedVideoModel2 :292-306   (reference line numbers)
-Dead in the reference (never constructed by a live model): GNN :121-144, LatentGNN :147-173,
-       GraphAttentionLayer :200-289 - kept importable with identical parameters.
+Live (reference line numbers): AttentionShare :10-43, SelfAttention :46-82, PositionalEncoding_old :85-104, ResBlock
+:107-119, LatentPSL :176-198, JointEmbedVideoModel2 :292-306.  Dead in the reference (never constructed by a live model) but
+kept importable with identical parameters: GNN :121-144, LatentGNN :147-173, GraphAttentionLayer :200-289.
 """
 import math
 
-import numpy as np
+import numpy as np                      # noqa: F401  (re-exported: models.layer star-imports this module, as the reference does)
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
-from torch.nn import Parameter
-from torch.autograd import Variable
 
 from dlsg import generic as G
+from dlsg.modspec import declare, lin, tanh_norm, xavier_uniform_param, sinusoid_table
 
 
 class AttentionShare(nn.Module):
     def __init__(self, input_value_size, input_key_size, output_size, dropout=0.1):
-        super(AttentionShare, self).__init__()
-        self.input_value_size = input_value_size
-        self.input_key_size = input_key_size
-        self.attention_size = output_size
-        self.dropout = dropout
-        self.K = nn.Linear(in_features=input_value_size, out_features=output_size, bias=False)
-        self.Q = nn.Linear(in_features=input_key_size, out_features=output_size, bias=False)
-        self.V = nn.Linear(in_features=input_value_size, out_features=output_size, bias=False)
-        self.output_layer = nn.Sequential(
-            nn.Linear(in_features=self.attention_size, out_features=output_size, bias=False),
-            nn.Tanh(),
-            nn.LayerNorm(output_size),
-            nn.Dropout(self.dropout)
-        )
+        super().__init__()
+        dv, dk, d = input_value_size, input_key_size, output_size
+        self.input_value_size, self.input_key_size, self.attention_size, self.dropout = dv, dk, d, dropout
+        declare(self, [('K', lambda: lin(dv, d, bias=False)),
+                       ('Q', lambda: lin(dk, d, bias=False)),
+                       ('V', lambda: lin(dv, d, bias=False)),
+                       ('output_layer', lambda: nn.Sequential(lin(d, d, bias=False), nn.Tanh(), nn.LayerNorm(d), nn.Dropout(dropout)))])
 
     @G.param_scope
     def forward(self, meta_state, hidden_previous):
@@ -53,18 +44,14 @@ class AttentionShare(nn.Module):
 
 class SelfAttention(nn.Module):
     def __init__(self, input_size, attention_size, output_size, dropout=0.2, get_pe=False):
-        super(SelfAttention, self).__init__()
-        self.attention_size = attention_size
-        self.dropout = dropout
-        self.get_pe = get_pe
-        self.pe = PositionalEncoding_old(attention_size)
-        self.K = nn.Linear(in_features=input_size, out_features=self.attention_size, bias=False)
-        self.Q = nn.Linear(in_features=input_size, out_features=self.attention_size, bias=False)
-        self.V = nn.Linear(in_features=input_size, out_features=self.attention_size, bias=False)
-        self.output_layer = nn.Sequential(
-            nn.Linear(in_features=self.attention_size, out_features=output_size, bias=False),
-            nn.Dropout(self.dropout)
-        )
+        super().__init__()
+        d = attention_size
+        self.attention_size, self.dropout, self.get_pe = d, dropout, get_pe
+        declare(self, [('pe', lambda: PositionalEncoding_old(d)),
+                       ('K', lambda: lin(input_size, d, bias=False)),
+                       ('Q', lambda: lin(input_size, d, bias=False)),
+                       ('V', lambda: lin(input_size, d, bias=False)),
+                       ('output_layer', lambda: nn.Sequential(lin(d, output_size, bias=False), nn.Dropout(dropout)))])
 
     @G.param_scope
     def forward(self, x, att_mask=None):
@@ -81,18 +68,12 @@ class SelfAttention(nn.Module):
 
 
 class PositionalEncoding_old(nn.Module):
-    "Implement the PE function."
+    """Sinusoidal position table added to the sequence, then dropout (buffer 'pe' of shape (1, max_len, d_model))."""
 
     def __init__(self, d_model, dropout=0.2, max_len=72):
-        super(PositionalEncoding_old, self).__init__()
+        super().__init__()
         self.dropout = nn.Dropout(p=dropout)
-        pe = torch.zeros(max_len, d_model)
-        position = torch.arange(0., max_len).unsqueeze(1)
-        div_term = torch.exp(torch.arange(0., d_model, 2) * -(math.log(10000.0) / d_model))
-        pe[:, 0::2] = torch.sin(position * div_term)
-        pe[:, 1::2] = torch.cos(position * div_term)
-        pe = pe.unsqueeze(0)
-        self.register_buffer('pe', pe)
+        self.register_buffer('pe', sinusoid_table(max_len, d_model))
 
     @G.param_scope
     def forward(self, x):
@@ -101,11 +82,8 @@ class PositionalEncoding_old(nn.Module):
 
 class ResBlock(nn.Module):
     def __init__(self, dim):
-        super(ResBlock, self).__init__()
-        self.res_block = nn.Sequential(
-            nn.ReLU(True),
-            nn.Conv1d(dim, dim, 3, padding=1),
-        )
+        super().__init__()
+        self.res_block = nn.Sequential(nn.ReLU(True), nn.Conv1d(dim, dim, 3, padding=1))     # key 'res_block.1.*'
 
     @G.param_scope
     def forward(self, input):
@@ -118,10 +96,9 @@ class GNN(nn.Module):
     """Dead in the reference (never constructed); parameters kept for import/state_dict compatibility."""
 
     def __init__(self):
-        super(GNN, self).__init__()
-        self.adj_Q = nn.Linear(2048, 2048)
-        self.adj_K = nn.Linear(2048, 2048)
-        self.graph_update = nn.Linear(2048, 1024)
+        super().__init__()
+        declare(self, [('adj_Q', lambda: lin(2048, 2048)), ('adj_K', lambda: lin(2048, 2048)),
+                       ('graph_update', lambda: lin(2048, 1024))])
 
     @G.param_scope
     def forward(self, region_feats):
@@ -138,13 +115,10 @@ class LatentGNN(nn.Module):
     """Dead in the reference (uses BatchNorm2d; never constructed by a live model)."""
 
     def __init__(self, input_size, num_latent, norm_func):
-        super(LatentGNN, self).__init__()
+        super().__init__()
         self.norm_func = F.normalize
-        self.v2l_adj_conv = nn.Sequential(
-            nn.Conv2d(in_channels=input_size, out_channels=num_latent, kernel_size=1, padding=0, bias=False),
-            nn.BatchNorm2d(num_latent),
-            nn.ReLU(inplace=True)
-        )
+        self.v2l_adj_conv = nn.Sequential(nn.Conv2d(input_size, num_latent, kernel_size=1, padding=0, bias=False),
+                                          nn.BatchNorm2d(num_latent), nn.ReLU(inplace=True))
 
     def forward(self, input_seq, mask=None):
         raise NotImplementedError('LatentGNN is dead code in the reference (sublayer.py:147-173) and outside the '
@@ -153,14 +127,9 @@ class LatentGNN(nn.Module):
 
 class LatentPSL(nn.Module):
     def __init__(self, input_size, num_psl):
-        super(LatentPSL, self).__init__()
-        self.theta = nn.Parameter(torch.empty(size=(num_psl, input_size)))
-        nn.init.xavier_uniform_(self.theta, gain=nn.init.calculate_gain('tanh'))
-        self.out_norm = nn.Sequential(
-            nn.Tanh(),
-            nn.LayerNorm(input_size),
-            nn.Dropout(0.3)
-        )
+        super().__init__()
+        declare(self, [('theta', lambda: xavier_uniform_param(num_psl, input_size, 'tanh')),
+                       ('out_norm', lambda: tanh_norm(input_size, 0.3))])
 
     @G.param_scope
     def forward(self, input_seq, mask=None):
@@ -174,19 +143,12 @@ class GraphAttentionLayer(nn.Module):
     """Dead in the reference (only used by the dead EncoderVisualGAT)."""
 
     def __init__(self, in_features, out_features, dropout, alpha=0.2, concat=True):
-        super(GraphAttentionLayer, self).__init__()
-        self.dropout = dropout
-        self.in_features = in_features
-        self.out_features = out_features
-        self.alpha = alpha
-        self.concat = concat
-        self.Ws = nn.Parameter(torch.empty(size=(in_features, out_features)))
-        nn.init.xavier_uniform_(self.Ws, gain=nn.init.calculate_gain('relu'))
-        self.We = nn.Parameter(torch.empty(size=(in_features, out_features)))
-        nn.init.xavier_uniform_(self.We, gain=nn.init.calculate_gain('relu'))
-        self.a = nn.Parameter(torch.empty(size=(2 * out_features, 1)))
-        nn.init.xavier_uniform_(self.a.data, gain=nn.init.calculate_gain('relu'))
-        self.leakyrelu = nn.LeakyReLU(self.alpha)
+        super().__init__()
+        self.dropout, self.in_features, self.out_features, self.alpha, self.concat = dropout, in_features, out_features, alpha, concat
+        declare(self, [('Ws', lambda: xavier_uniform_param(in_features, out_features, 'relu')),
+                       ('We', lambda: xavier_uniform_param(in_features, out_features, 'relu')),
+                       ('a', lambda: xavier_uniform_param(2 * out_features, 1, 'relu')),
+                       ('leakyrelu', lambda: nn.LeakyReLU(alpha))])
 
     def forward(self, start_feature, end_feature):
         raise NotImplementedError('GraphAttentionLayer is dead code in the reference (sublayer.py:200-289) and '
@@ -195,10 +157,11 @@ class GraphAttentionLayer(nn.Module):
 
 class JointEmbedVideoModel2(nn.Module):
     def __init__(self, hidden_size):
-        super(JointEmbedVideoModel2, self).__init__()
-        self.classify = nn.Linear(hidden_size, 1)
-        self.visual_embed = nn.Sequential(nn.Linear(hidden_size, hidden_size), nn.Tanh())
-        self.sent_embed = nn.Sequential(nn.Linear(hidden_size, hidden_size), nn.Tanh())
+        super().__init__()
+        h = hidden_size
+        declare(self, [('classify', lambda: lin(h, 1)),
+                       ('visual_embed', lambda: nn.Sequential(lin(h, h), nn.Tanh())),
+                       ('sent_embed', lambda: nn.Sequential(lin(h, h), nn.Tanh()))])
 
     @G.param_scope
     def forward(self, visual, sent):
