@@ -158,7 +158,29 @@ def gen_disc(tag, args, V, B):
     print(tag, 'r', r_logit.detach().numpy(), 'gp', gp.item())
 
 
+def gen_init_order():
+    """Registration order, shapes and seeded default initialisation of every parameter / buffer of the reference's live
+    models at the real (MSR-VTT / MSVD) widths: the mirror must reproduce all three (state_dict AND optimizer checkpoints
+    index parameters by position; a freshly initialised model must train like the reference's)."""
+    import json
+    out = {}
+    for name, args in (('msr', synth.msr_args()), ('msvd', synth.msvd_args())):
+        for cls_name, make in (('CapGnnModel', lambda: CapGnnModel(args, synth.Vocab(101))),
+                               ('CapBaseline1', lambda: CapBaseline1(args, synth.Vocab(101))),
+                               ('DiscV2', lambda: DiscV2(args, 101))):
+            torch.manual_seed(3)
+            with contextlib.redirect_stdout(io.StringIO()):
+                net = make()
+            out['%s.%s' % (name, cls_name)] = [[k, list(v.shape), float(v.double().abs().sum())] for k, v in net.state_dict().items()]
+    with open(os.path.join(HERE, 'init_order.json'), 'w') as f:
+        json.dump(out, f)
+    print('init_order.json:', {k: len(v) for k, v in out.items()})
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'init_order':
+        gen_init_order()
+        sys.exit(0)
     torch.manual_seed(12)
     torch.set_num_threads(8)
     gen_capgnn('capgnn_small_msr', synth.small_args(), V=37, B=3)
@@ -167,3 +189,4 @@ if __name__ == '__main__':
     gen_baseline1('baseline1_small', synth.small_args(decode_hidden_size=52), V=37, B=3)
     gen_disc('disc_small_msr', synth.small_args(visual_hidden_size=1024, num_proposals=5, num_topk=5), V=37, B=3)
     gen_disc('disc_small_msvd', synth.small_args(visual_hidden_size=1024, num_proposals=8, num_topk=3), V=37, B=3)
+    gen_init_order()

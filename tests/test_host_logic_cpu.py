@@ -350,3 +350,27 @@ def test_decoder_contract_methods_the_callers_use(tag, args, V, B):
     assert torch.equal(emb, sd['decoder.word_embed.weight'][caps]) and not emb.requires_grad
     probs = torch.softmax(torch.randn(B, 4, V, generator=torch.Generator().manual_seed(1)), -1)
     assert (dec.output2wordembedding(probs) - probs @ sd['decoder.word_embed.weight']).abs().max() < 1e-5
+
+
+def test_registration_order_and_seeded_init_equal_the_reference(golden_dir):
+    """tests/golden/init_order.json holds, for the reference's CapGnnModel / CapBaseline1 / DiscV2 at the real MSR-VTT and
+    MSVD widths under torch.manual_seed(3): every state_dict key IN ORDER, its shape and the abs-sum of its freshly
+    initialised values.  The mirror must reproduce all of it: optimizer checkpoints (run_gun.py:302-310) index parameters by
+    position, and a freshly initialised model has to start from the reference's initialisation."""
+    import contextlib
+    import io
+    import json
+    import models.model as M
+    want = json.load(open(os.path.join(golden_dir, 'init_order.json')))
+    for name, args in (('msr', synth.msr_args()), ('msvd', synth.msvd_args())):
+        for cls_name, make in (('CapGnnModel', lambda: M.CapGnnModel(args, synth.Vocab(101))),
+                               ('CapBaseline1', lambda: M.CapBaseline1(args, synth.Vocab(101))),
+                               ('DiscV2', lambda: M.DiscV2(args, 101))):
+            torch.manual_seed(3)
+            with contextlib.redirect_stdout(io.StringIO()):
+                net = make()
+            got = [[k, list(v.shape), float(v.double().abs().sum())] for k, v in net.state_dict().items()]
+            ref = want['%s.%s' % (name, cls_name)]
+            assert [g[:2] for g in got] == [r[:2] for r in ref], (name, cls_name)
+            for g, r in zip(got, ref):
+                assert abs(g[2] - r[2]) <= 1e-9 * max(1.0, abs(r[2])), (name, cls_name, g[0])
