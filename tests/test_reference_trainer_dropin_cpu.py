@@ -1,0 +1,157 @@
+"""Drop-in checks with the reference's OWN caller code (1) and (2).
+
+(1) `RunGAN.train_disc` (run_gun.py:339-398, the WGAN-GP critic loop with
+its double backward and Adam steps) is imported unchanged from /root/reference and run twice on identical seeded inputs -
+once on the reference's DiscV2 (in a subprocess, where `models` resolves to the reference package) and once on this
+repo's DiscV2 (`models` first on sys.path, exactly the integration of INTEGRATION.md 1; kernels emulated on CPU, fp32).
+The critic weights after the loop and the two returned running sums must agree.
+
+(2) `evaluate.gather_results` (evaluate.py:101-116: the inference loop of the evaluator - `net(frames, regions, None)` then
+`net.decoder.decode_tokens` per clip) is imported unchanged and run over a fake loader with the reference's CapGnnModel and
+with ours, greedy and beam-3: the caption strings per video id must be identical.
+
+Needs the reference checkout (only present in the build container): skipped elsewhere.  Stubs: `evaluate` (for run_gun: it would
+import h5py / tables), `utils.data` and `cocoeval` (for evaluate.py: h5py / java), `seaborn`, `matplotlib.pyplot`,
+`allennlp.common.checks`."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get('DLSG_REFERENCE', '/root/reference')
+
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, 'run_gun.py')), reason='reference checkout not present')
+
+WORKER = r'''
+import os, sys, types, contextlib, io
+ROOT, REF, which, out = sys.argv[1:5]
+pkg = os.path.join(ROOT, 'd-lsg-video-caption_b200')
+for name in ('allennlp', 'allennlp.common', 'allennlp.common.checks', 'seaborn', 'matplotlib', 'matplotlib.pyplot', 'evaluate'):
+    sys.modules[name] = types.ModuleType(name)
+sys.modules['allennlp.common.checks'].ConfigurationError = type('ConfigurationError', (Exception,), {})
+for n in ('evaluate', 'convert_data_to_coco_scorer_format', 'gather_results', 'evaluate_multi_gpu'):
+    setattr(sys.modules['evaluate'], n, None)
+sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+if which == 'reference':
+    sys.path[:0] = [REF, pkg, ROOT]                 # `models` = the reference's package
+else:
+    sys.path[:0] = [pkg, ROOT, os.path.join(ROOT, 'tests'), REF]      # `models` = ours; run_gun / utils come from the reference
+import numpy as np
+import torch
+torch.set_num_threads(4)
+with contextlib.redirect_stdout(io.StringIO()):
+    import run_gun                                   # the reference's trainer module, unmodified
+import models
+assert models.__file__.startswith(REF if which == 'reference' else pkg), models.__file__
+assert run_gun.__file__.startswith(REF)
+from dlsg import synth
+if which == 'ours':
+    from dlsg import ops, linalg as la
+    from cpu_emul import CpuEmulBackend
+    ops.set_backend(CpuEmulBackend())
+    la.set_precision('fp32')
+from models.model import DiscV2
+args = synth.small_args(visual_hidden_size=1024, num_proposals=5, num_topk=5)
+V, B, L = 37, 3, args.max_words
+D = DiscV2(args, V)
+synth.fill_state_dict(D, prefix='D.')
+D.eval()
+rs = np.random.RandomState(5)
+_, _, caps, lens = synth.make_inputs(B, args, V, seed=14)
+att_mask = synth.att_mask_from_captions(caps)
+obj = torch.from_numpy(rs.standard_normal((B, 5, 1024)).astype(np.float32))
+mot = torch.from_numpy(rs.standard_normal((B, 5, 1024)).astype(np.float32))
+alpha = torch.softmax(torch.from_numpy(rs.standard_normal((B, L, 10)).astype(np.float32)), -1)
+fake = torch.from_numpy(rs.standard_normal((B, L, V)).astype(np.float32))
+trainer = run_gun.RunGAN.__new__(run_gun.RunGAN)     # no __init__: it would build loaders, tensorboard files, ...
+trainer.device, trainer.multi_gpu, trainer.local_rank = torch.device('cpu'), False, 0
+trainer.writer = types.SimpleNamespace(add_scalar=lambda *a, **k: None)
+real = trainer.to_onehot(caps, V)                    # run_gun.py:449-453
+opt_d = torch.optim.Adam(D.parameters(), lr=1.6e-4, betas=(0.5, 0.9))
+torch.manual_seed(5)
+loss_sum, wass = trainer.train_disc(real, fake, opt_d, D, 3, 1, 0, 10, 0.0, 0.0, obj_psl=obj, motion_psl=mot, pos_tag=None,
+                                    att_mask=att_mask, alpha_all=alpha)
+np.savez(out, loss_sum=np.float64(loss_sum), wass=np.float64(wass),
+         **{'p.' + k: v.detach().numpy() for k, v in D.state_dict().items()})
+'''
+
+
+EVAL_WORKER = r'''
+import os, sys, types, contextlib, io, json
+ROOT, REF, which, out = sys.argv[1:5]
+pkg = os.path.join(ROOT, 'd-lsg-video-caption_b200')
+for name in ('allennlp', 'allennlp.common', 'allennlp.common.checks', 'cocoeval', 'utils.data'):
+    sys.modules[name] = types.ModuleType(name)
+sys.modules['allennlp.common.checks'].ConfigurationError = type('ConfigurationError', (Exception,), {})
+sys.modules['cocoeval'].COCOScorer = sys.modules['cocoeval'].suppress_stdout_stderr = None
+sys.modules['utils.data'].get_eval_loader = None
+if which == 'reference':
+    sys.path[:0] = [REF, pkg, ROOT]
+else:
+    sys.path[:0] = [pkg, ROOT, os.path.join(ROOT, 'tests'), REF]
+import torch
+torch.set_num_threads(4)
+import evaluate                                      # the reference's evaluator module, unmodified
+import models
+assert models.__file__.startswith(REF if which == 'reference' else pkg), models.__file__
+assert evaluate.__file__.startswith(REF)
+from dlsg import synth
+if which == 'ours':
+    from dlsg import ops, linalg as la
+    from cpu_emul import CpuEmulBackend
+    ops.set_backend(CpuEmulBackend())
+    la.set_precision('fp32')
+from models.model import CapGnnModel
+args = synth.small_args()
+V, B = 37, 3
+with contextlib.redirect_stdout(io.StringIO()):
+    net = CapGnnModel(args, synth.Vocab(V))
+synth.fill_state_dict(net)
+net.eval()
+loader = []
+for b in range(2):
+    fr, rg, _, _ = synth.make_inputs(B, args, V, seed=40 + b)
+    loader.append((fr, rg, None, ['vid%d_%d' % (b, i) for i in range(B)]))
+res = {}
+with torch.no_grad():
+    for beam in (1, 3):
+        net.update_beam_size(beam)
+        captions, _ = evaluate.gather_results(net, args, loader)
+        res['beam%d' % beam] = dict(captions)
+json.dump(res, open(out, 'w'))
+'''
+
+
+def _run(which, out, worker=WORKER):
+    r = subprocess.run([sys.executable, '-c', worker, ROOT, REF, which, out], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return np.load(out) if out.endswith('.npz') else __import__('json').load(open(out))
+
+
+def test_reference_gather_results_gives_the_same_captions_on_our_modules(tmp_path):
+    ref = _run('reference', str(tmp_path / 'ref.json'), EVAL_WORKER)
+    ours = _run('ours', str(tmp_path / 'ours.json'), EVAL_WORKER)
+    assert set(ref) == {'beam1', 'beam3'} and len(ref['beam1']) == 6
+    assert any(len(c.split()) > 0 for c in ref['beam1'].values())
+    assert ours == ref
+
+
+def test_reference_train_disc_gives_the_same_critic_on_our_modules(tmp_path):
+    ref = _run('reference', str(tmp_path / 'ref.npz'))
+    ours = _run('ours', str(tmp_path / 'ours.npz'))
+    assert abs(float(ref['loss_sum']) - float(ours['loss_sum'])) < 1e-4 * max(1.0, abs(float(ref['loss_sum'])))
+    assert abs(float(ref['wass']) - float(ours['wass'])) < 1e-4 * max(1.0, abs(float(ref['wass'])))
+    keys = [k for k in ref.files if k.startswith('p.')]
+    assert keys == [k for k in ours.files if k.startswith('p.')]
+    sys.path.insert(0, os.path.join(ROOT, 'd-lsg-video-caption_b200'))
+    from dlsg import synth
+    init = synth.fill_tensor('D.fusion', ref['p.fusion'].shape).numpy()
+    assert np.abs(ref['p.fusion'] - init).max() > 1e-4             # the loop really trained the critic
+    for k in keys:
+        d = np.abs(ref[k] - ours[k])
+        # three Adam steps of lr 1.6e-4: elements whose gradient sits at Adam's epsilon can differ by a fraction of a step
+        assert d.max() < 2e-4, k
+        assert (d > 2e-6).mean() < 2e-2, k
