@@ -10,6 +10,14 @@ The critic weights after the loop and the two returned running sums must agree.
 `net.decoder.decode_tokens` per clip) is imported unchanged and run over a fake loader with the reference's CapGnnModel and
 with ours, greedy and beam-3: the caption strings per video id must be identical.
 
+(3) The whole `RunGAN(...).train()` (run_gun.py:20-320: model construction with the msr-vtt overrides, both Adams and
+schedulers, GANLambdaHandler, per iteration G forward -> 2 critic steps -> G forward -> packed CE -> critic term -> backward
+-> Adam, evaluation hook at the saving schedule) runs unchanged for one epoch of two batches on the reference's models and
+on ours, from the same seeds (default initialisation: identical by construction, see tests/golden/init_order.json).  The
+generator and critic weights after training must agree.  Environment patches, identical for both runs: dropout is held off
+(`nn.Module.train` keeps eval mode; the RNG streams of custom dropout kernels cannot match torch's), `SummaryWriter` and
+`evaluate.evaluate` are stand-ins (tensorboard files / java scorers), the working directory is a scratch directory.
+
 Needs the reference checkout (only present in the build container): skipped elsewhere.  Stubs: `evaluate` (for run_gun: it would
 import h5py / tables), `utils.data` and `cocoeval` (for evaluate.py: h5py / java), `seaborn`, `matplotlib.pyplot`,
 `allennlp.common.checks`."""
@@ -125,6 +133,89 @@ json.dump(res, open(out, 'w'))
 '''
 
 
+TRAIN_WORKER = r'''
+import os, sys, types, contextlib, io, random
+ROOT, REF, which, out = sys.argv[1:5]
+os.chdir(os.path.dirname(out))
+pkg = os.path.join(ROOT, 'd-lsg-video-caption_b200')
+for name in ('allennlp', 'allennlp.common', 'allennlp.common.checks', 'seaborn', 'matplotlib', 'matplotlib.pyplot', 'evaluate'):
+    sys.modules[name] = types.ModuleType(name)
+sys.modules['allennlp.common.checks'].ConfigurationError = type('ConfigurationError', (Exception,), {})
+sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+
+
+def fake_evaluate(net, opt, loader, reference, multi_modal=False, multi_gpu=False):
+    res = {}
+    for frames, regions, _, vids in loader:                      # what evaluate.py:56-98 does, minus the java scorers
+        outputs = net(frames, regions[:, :, :opt.num_obj, :], None)[0]
+        for tokens, vid in zip(outputs, vids):
+            res[vid] = net.decoder.decode_tokens(tokens.data)
+    return {'Bleu_4': 0.1, 'METEOR': 0.1, 'CIDEr': 0.1, 'ROUGE_L': 0.1}, res, [], 0.0
+
+
+ev = sys.modules['evaluate']
+ev.evaluate = fake_evaluate
+ev.convert_data_to_coco_scorer_format = ev.gather_results = ev.evaluate_multi_gpu = None
+if which == 'reference':
+    sys.path[:0] = [REF, pkg, ROOT]
+else:
+    sys.path[:0] = [pkg, ROOT, os.path.join(ROOT, 'tests'), REF]
+import numpy as np
+import torch
+import torch.nn as nn
+torch.set_num_threads(4)
+_train, _init = nn.Module.train, nn.Module.__init__
+nn.Module.train = lambda self, mode=True: _train(self, False)     # dropout held off in both runs: .train() keeps eval mode
+
+
+def _init_eval(self, *a, **k):                                    # ... and modules are born in eval mode
+    _init(self, *a, **k)
+    self.training = False
+
+
+nn.Module.__init__ = _init_eval
+with contextlib.redirect_stdout(io.StringIO()):
+    import run_gun
+import models
+assert models.__file__.startswith(REF if which == 'reference' else pkg), models.__file__
+run_gun.SummaryWriter = lambda *a, **k: types.SimpleNamespace(add_scalar=lambda *a, **k: None)
+from dlsg import synth
+if which == 'ours':
+    from dlsg import ops, linalg as la
+    from cpu_emul import CpuEmulBackend
+    ops.set_backend(CpuEmulBackend())
+    la.set_precision('fp32')
+B, V = 2, 37
+args = synth.small_args(visual_hidden_size=1024, region_projected_size=1024, query_hidden_size=1024, max_words=26, max_frames=4,
+                        dataset='msr-vtt', num_obj=36, train_batch_size=B)
+for k, v in dict(local_rank=0, learning_rate=1.6e-4, epoch_num=1, test_batch_size=B, save_per_epoch=1, ss_factor=20,
+                 use_psl_loss=False, num_D_visual=2, lambda_D_visual=0.01).items():
+    setattr(args, k, v)
+train_loader, test_loader = [], []
+for b in range(2):
+    fr, rg, caps, lens = synth.make_inputs(B, args, V, seed=60 + b)
+    train_loader.append((fr, rg, 0, caps, 0, lens, [10 * b + i for i in range(B)]))
+    test_loader.append((fr, rg, 0, [100 + 10 * b + i for i in range(B)]))
+torch.manual_seed(12)
+random.seed(12)
+np.random.seed(12)
+log = io.StringIO()
+with contextlib.redirect_stdout(log):
+    trainer = run_gun.RunGAN(args, synth.Vocab(V), torch.device('cpu'), train_loader=train_loader, test_loader=test_loader,
+                             test_reference=None, is_debug=True)
+    w0 = trainer.model.decoder.word_restore.weight.detach().clone()
+    f0 = trainer.D_visual.fusion.detach().clone()
+    try:
+        trainer.train()
+    except AttributeError as e:                                   # the reference's own end_round() prints an attribute it never sets
+        assert 'bleu_best' in str(e), e
+sys.stdout = sys.__stdout__
+np.savez(out, init_g=w0.numpy(), init_d=f0.numpy(),
+         **{'g.' + k: v.detach().numpy() for k, v in trainer.model.state_dict().items()},
+         **{'d.' + k: v.detach().numpy() for k, v in trainer.D_visual.state_dict().items()})
+'''
+
+
 def _run(which, out, worker=WORKER):
     r = subprocess.run([sys.executable, '-c', worker, ROOT, REF, which, out], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
@@ -155,3 +246,19 @@ def test_reference_train_disc_gives_the_same_critic_on_our_modules(tmp_path):
         # three Adam steps of lr 1.6e-4: elements whose gradient sits at Adam's epsilon can differ by a fraction of a step
         assert d.max() < 2e-4, k
         assert (d > 2e-6).mean() < 2e-2, k
+
+
+def test_reference_rungan_train_runs_unchanged_and_trains_the_same_weights(tmp_path):
+    (tmp_path / 'ref').mkdir()
+    (tmp_path / 'ours').mkdir()
+    ref = _run('reference', str(tmp_path / 'ref' / 'w.npz'), TRAIN_WORKER)
+    ours = _run('ours', str(tmp_path / 'ours' / 'w.npz'), TRAIN_WORKER)
+    assert ref.files == ours.files and len(ref.files) > 120
+    assert np.array_equal(ref['init_g'], ours['init_g']) and np.array_equal(ref['init_d'], ours['init_d'])   # same seeded init
+    assert np.abs(ref['g.decoder.word_restore.weight'] - ref['init_g']).max() > 1e-4                          # both were trained
+    assert np.abs(ref['d.fusion'] - ref['init_d']).max() > 1e-4
+    for k in ref.files:
+        d = np.abs(ref[k] - ours[k])
+        # 2 generator / 4 critic Adam steps of lr 1.6e-4; elements whose gradient sits at Adam's epsilon may differ by a step
+        assert d.max() < 5e-4, (k, float(d.max()))
+        assert (d > 5e-6).mean() < 3e-2, (k, float((d > 5e-6).mean()))
