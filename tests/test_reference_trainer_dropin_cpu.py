@@ -18,6 +18,10 @@ generator and critic weights after training must agree.  Environment patches, id
 (`nn.Module.train` keeps eval mode; the RNG streams of custom dropout kernels cannot match torch's), `SummaryWriter` and
 `evaluate.evaluate` are stand-ins (tensorboard files / java scorers), the working directory is a scratch directory.
 
+(4) The baseline trainer `Run(...).train()` (run_graph.py:19-200; what train.py runs: CapBaseline1 with the msr-vtt override
+decode_hidden_size = 1300, an odd width for the GEMM / LSTM kernels) for two epochs of ten batches - including its every-10-
+steps sample print through `decoder.decode_tokens`, the MultiStepLR milestone and the evaluation hook - same comparison.
+
 Needs the reference checkout (only present in the build container): skipped elsewhere.  Stubs: `evaluate` (for run_gun: it would
 import h5py / tables), `utils.data` and `cocoeval` (for evaluate.py: h5py / java), `seaborn`, `matplotlib.pyplot`,
 `allennlp.common.checks`."""
@@ -216,6 +220,42 @@ np.savez(out, init_g=w0.numpy(), init_d=f0.numpy(),
 '''
 
 
+BASELINE_WORKER = TRAIN_WORKER.replace("'matplotlib.pyplot', 'evaluate')", "'matplotlib.pyplot', 'evaluate', 'utils.data')")
+BASELINE_WORKER = BASELINE_WORKER[:BASELINE_WORKER.index('B, V = 2, 37')].replace('import run_gun', 'import run_graph').replace(
+    "run_gun.SummaryWriter = lambda *a, **k: types.SimpleNamespace(add_scalar=lambda *a, **k: None)\n", '').replace(
+    "ev = sys.modules['evaluate']\n",
+    "sys.modules['utils.data'].get_train_loader = sys.modules['utils.data'].get_eval_loader = None\nev = sys.modules['evaluate']\n") + r'''
+B, V = 2, 37
+args = synth.small_args(max_words=26, dataset='msr-vtt', train_batch_size=B)
+for k, v in dict(local_rank=0, learning_rate=1.6e-4, epoch_num=2, test_batch_size=B, save_per_epoch=1, ss_factor=20).items():
+    setattr(args, k, v)
+train_loader, test_loader = [], []
+for b in range(10):
+    fr, rg, caps, lens = synth.make_inputs(B, args, V, seed=80 + b)
+    train_loader.append((fr, rg, 0, caps, 0, lens, [10 * b + i for i in range(B)]))
+fr, rg, _, _ = synth.make_inputs(B, args, V, seed=99)
+test_loader.append((fr, rg, 0, [500, 501]))
+torch.manual_seed(12)
+random.seed(12)
+np.random.seed(12)
+log = io.StringIO()
+with contextlib.redirect_stdout(log):
+    trainer = run_graph.Run(args, synth.Vocab(V), torch.device('cpu'), train_loader=train_loader, test_loader=test_loader,
+                            test_reference=None, is_debug=True)
+    assert trainer.model.decoder.decode_hidden_size == 1300
+    try:
+        trainer.train()
+    except AttributeError as e:
+        assert 'bleu_best' in str(e), e
+sys.stdout = sys.__stdout__
+text = log.getvalue()
+assert 'WE: ' in text and 'GT: ' in text, text[-2000:]              # the every-10-steps sample print ran (decode_tokens)
+samples = [l for l in text.splitlines() if l.startswith('WE: ') or l.startswith('GT: ')]
+open(out + '.txt', 'w').write('\n'.join(samples))
+np.savez(out, **{'g.' + k: v.detach().numpy() for k, v in trainer.model.state_dict().items()})
+'''
+
+
 def _run(which, out, worker=WORKER):
     r = subprocess.run([sys.executable, '-c', worker, ROOT, REF, which, out], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
@@ -262,3 +302,18 @@ def test_reference_rungan_train_runs_unchanged_and_trains_the_same_weights(tmp_p
         # 2 generator / 4 critic Adam steps of lr 1.6e-4; elements whose gradient sits at Adam's epsilon may differ by a step
         assert d.max() < 5e-4, (k, float(d.max()))
         assert (d > 5e-6).mean() < 3e-2, (k, float((d > 5e-6).mean()))
+
+
+def test_reference_baseline_trainer_runs_unchanged_and_trains_the_same_weights(tmp_path):
+    (tmp_path / 'ref').mkdir()
+    (tmp_path / 'ours').mkdir()
+    ref = _run('reference', str(tmp_path / 'ref' / 'w.npz'), BASELINE_WORKER)
+    ours = _run('ours', str(tmp_path / 'ours' / 'w.npz'), BASELINE_WORKER)
+    assert ref.files == ours.files and len(ref.files) > 30
+    for k in ref.files:
+        d = np.abs(ref[k] - ours[k])
+        # 20 Adam steps (lr 1.6e-4, halved after the first epoch)
+        assert d.max() < 2e-3, (k, float(d.max()))
+        assert (d > 2e-5).mean() < 3e-2, (k, float((d > 2e-5).mean()))
+    # the trainer's own sample prints (arg-max tokens of the first clip, decoded by decode_tokens) are the same text
+    assert open(str(tmp_path / 'ref' / 'w.npz') + '.txt').read() == open(str(tmp_path / 'ours' / 'w.npz') + '.txt').read()
