@@ -374,3 +374,57 @@ def test_registration_order_and_seeded_init_equal_the_reference(golden_dir):
             assert [g[:2] for g in got] == [r[:2] for r in ref], (name, cls_name)
             for g, r in zip(got, ref):
                 assert abs(g[2] - r[2]) <= 1e-9 * max(1.0, abs(r[2])), (name, cls_name, g[0])
+
+
+@pytest.mark.parametrize('case', ['batch_of_one', 'four_regions_no_graph_path', 'ragged_captions', 'long_video_short_caption'])
+def test_edge_shapes_match_oracle(case):
+    """Edge shapes of the live path against the oracle (fp32, kernels emulated): a batch of one clip; num_obj = 4, where the
+    reference skips the region -> frame aggregation and does not even construct obj_embed (layer.py:143,182-183); captions
+    of length 1 next to full-length ones (one counted token / none padded); more frames than words."""
+    la.set_precision('fp32')
+    V, B = 37, 3
+    args = synth.small_args()
+    if case == 'batch_of_one':
+        B = 1
+    elif case == 'four_regions_no_graph_path':
+        args = synth.small_args(num_obj=4)
+    elif case == 'long_video_short_caption':
+        args = synth.small_args(max_frames=11, max_words=3)
+    net = _build('CapGnnModel', args, V)
+    net.eval()
+    if case == 'four_regions_no_graph_path':
+        assert not any('obj_embed' in k for k in net.state_dict())
+    sd = _sd(net)
+    for v in sd.values():
+        v.requires_grad_(True)
+    frames, regions, caps, lens = synth.make_inputs(B, args, V, seed=31)
+    if case == 'ragged_captions':
+        L = args.max_words
+        caps = caps.clone()
+        caps[0] = 0
+        caps[0, 0] = synth.END                              # a caption that is just <end>
+        caps[1, :L - 1] = torch.arange(4, 4 + L - 1)
+        caps[1, L - 1] = synth.END                          # a caption that fills every slot
+        lens = [1, L] + list(lens[2:])
+    out, obj, mot, alpha = net(frames, regions, caps, args.max_words, 1.0)
+    ro, robj, rmot, ralpha = O.cap_gnn_forward(sd, frames, regions, caps, args.max_words, 1.0, args.a_feature_size)
+    assert out.shape == ro.shape and alpha.shape == ralpha.shape
+    assert (out - ro).abs().max() < 6e-5 and (obj - robj).abs().max() < 2e-5 and (mot - rmot).abs().max() < 2e-5
+    O.packed_ce_loss(out, caps, lens).backward()
+    O.packed_ce_loss(ro, caps, lens).backward()
+    for k, p in net.named_parameters():
+        ref = sd[k].grad
+        if p.grad is None:
+            assert ref is None or float(ref.abs().max()) == 0.0, k
+            continue
+        assert float((p.grad - ref).abs().max()) < 1e-6 or float((p.grad - ref).norm() / (ref.norm() + 1e-8)) < 2e-4, (case, k)
+    with torch.no_grad():
+        robj, rmot = O.cap_gnn_encoder(sd, frames, regions, args.a_feature_size)
+        for beam in (1, 3):
+            net.update_beam_size(beam)
+            got = net(frames, regions, None)[0]
+            if beam == 1:
+                want = O.cap_gnn_forward(sd, frames, regions, None, args.max_words, 1.0, args.a_feature_size, beam_size=1)[0]
+            else:
+                want = O.decoder_beam(sd, 'decoder', robj, rmot, args.max_words, beam)[0]
+            assert torch.equal(got, want), (case, beam)

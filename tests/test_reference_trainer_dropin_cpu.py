@@ -18,6 +18,10 @@ generator and critic weights after training must agree.  Environment patches, id
 (`nn.Module.train` keeps eval mode; the RNG streams of custom dropout kernels cannot match torch's), `SummaryWriter` and
 `evaluate.evaluate` are stand-ins (tensorboard files / java scorers), the working directory is a scratch directory.
 
+(5) Edge shapes straight against the reference modules (not via the oracle): a batch of one clip, and num_obj = 4 where the
+reference constructs no obj_embed and skips the region aggregation (layer.py:143,182-183): logits, nodes, attention weights
+and every parameter gradient.
+
 (4) The baseline trainer `Run(...).train()` (run_graph.py:19-200; what train.py runs: CapBaseline1 with the msr-vtt override
 decode_hidden_size = 1300, an odd width for the GEMM / LSTM kernels) for two epochs of ten batches - including its every-10-
 steps sample print through `decoder.decode_tokens`, the MultiStepLR milestone and the evaluation hook - same comparison.
@@ -256,6 +260,49 @@ np.savez(out, **{'g.' + k: v.detach().numpy() for k, v in trainer.model.state_di
 '''
 
 
+EDGE_WORKER = r'''
+import os, sys, types, contextlib, io
+ROOT, REF, which, out_path = sys.argv[1:5]
+pkg = os.path.join(ROOT, 'd-lsg-video-caption_b200')
+for name in ('allennlp', 'allennlp.common', 'allennlp.common.checks'):
+    sys.modules[name] = types.ModuleType(name)
+sys.modules['allennlp.common.checks'].ConfigurationError = type('ConfigurationError', (Exception,), {})
+sys.path[:0] = [REF, pkg, ROOT] if which == 'reference' else [pkg, ROOT, os.path.join(ROOT, 'tests'), REF]
+import numpy as np
+import torch
+torch.set_num_threads(4)
+import models
+assert models.__file__.startswith(REF if which == 'reference' else pkg), models.__file__
+from dlsg import synth
+if which == 'ours':
+    from dlsg import ops, linalg as la
+    from cpu_emul import CpuEmulBackend
+    ops.set_backend(CpuEmulBackend())
+    la.set_precision('fp32')
+from models.model import CapGnnModel
+res = {}
+for case, args, B in (('b1', synth.small_args(), 1), ('r4', synth.small_args(num_obj=4), 3)):
+    V = 37
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = CapGnnModel(args, synth.Vocab(V))
+    synth.fill_state_dict(net)
+    net.eval()
+    fr, rg, caps, lens = synth.make_inputs(B, args, V, seed=33)
+    out, obj, mot, alpha = net(fr, rg, caps, args.max_words, 1.0)
+    o = torch.cat([out[j][:lens[j]] for j in range(B)], 0)
+    t = torch.cat([caps[j][:lens[j]] for j in range(B)], 0)
+    torch.nn.CrossEntropyLoss()(o, t).backward()
+    res[case + '.logits'], res[case + '.obj'], res[case + '.mot'] = out.detach().numpy(), obj.detach().numpy(), mot.detach().numpy()
+    res[case + '.alpha'] = alpha.detach().numpy()
+    for k, p in net.named_parameters():
+        res[case + '.g.' + k] = np.zeros(0, np.float32) if p.grad is None else p.grad.numpy()
+    with torch.no_grad():
+        net.update_beam_size(3)
+        res[case + '.beam3'] = net(fr, rg, None)[0].numpy()
+np.savez(out_path, **res)
+'''
+
+
 def _run(which, out, worker=WORKER):
     r = subprocess.run([sys.executable, '-c', worker, ROOT, REF, which, out], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
@@ -317,3 +364,17 @@ def test_reference_baseline_trainer_runs_unchanged_and_trains_the_same_weights(t
         assert (d > 2e-5).mean() < 3e-2, (k, float((d > 2e-5).mean()))
     # the trainer's own sample prints (arg-max tokens of the first clip, decoded by decode_tokens) are the same text
     assert open(str(tmp_path / 'ref' / 'w.npz') + '.txt').read() == open(str(tmp_path / 'ours' / 'w.npz') + '.txt').read()
+
+
+def test_edge_shapes_equal_the_reference_modules(tmp_path):
+    ref = _run('reference', str(tmp_path / 'ref.npz'), EDGE_WORKER)
+    ours = _run('ours', str(tmp_path / 'ours.npz'), EDGE_WORKER)
+    assert ref.files == ours.files
+    assert not any('obj_embed' in k for k in ref.files if k.startswith('r4.'))
+    for k in ref.files:
+        a, b = ref[k], ours[k]
+        assert a.shape == b.shape, k
+        if k.endswith('.beam3'):
+            assert np.array_equal(a, b), k
+        elif a.size:
+            assert np.abs(a - b).max() < 1e-4 * max(1.0, float(np.abs(a).max())), (k, float(np.abs(a - b).max()))
