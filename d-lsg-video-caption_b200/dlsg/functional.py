@@ -40,6 +40,10 @@ class _BlockFn(torch.autograd.Function):
         ctx.wc_scope = WC.begin_train_block() if getattr(block, 'need_grad', False) else WC.eval_scope()
         outs, saved = block.forward(t)
         ctx.block, ctx.saved, ctx.names = block, saved, names
+        if isinstance(block, TunBlock):
+            # an encoder of the pair whose output nobody uses (CapBaselineModel drops the object nodes, model.py:86-88) must see
+            # None, not a zero tensor, so that its parameters end with grad None exactly as under the reference's autograd
+            ctx.set_materialize_grads(False)
         for o in outs:
             if o.dtype not in (torch.float32,):
                 ctx.mark_non_differentiable(o)
@@ -357,6 +361,8 @@ class TunBlock:
             dWc = empty((E * H, Dr), dOpre)
             be.gemm(op(dOpre.t()), sv['RbT'], dWc)
             for i, e in enumerate(self.encs):
+                if gouts[i] is None:
+                    continue        # an encoder whose output is unused gets grad None, as autograd gives the reference (CapBaselineModel)
                 grads[e['prefix'] + 'obj_embed.weight'] = dWc[i * H:(i + 1) * H]
                 grads[e['prefix'] + 'obj_embed.bias'] = dbc[i * H:(i + 1) * H]
         return grads

@@ -299,6 +299,25 @@ for case, args, B in (('b1', synth.small_args(), 1), ('r4', synth.small_args(num
     with torch.no_grad():
         net.update_beam_size(3)
         res[case + '.beam3'] = net(fr, rg, None)[0].numpy()
+# CapBaselineModel (model.py:76-91): the graph encoders in baseline mode (no latent pooling) + the single-head decoder over
+# the 26 motion frame vectors; constructed by no live trainer, same blocks in another wiring
+from models.model import CapBaselineModel
+args, B, V = synth.small_args(decode_hidden_size=52), 2, 37
+with contextlib.redirect_stdout(io.StringIO()):
+    net = CapBaselineModel(args, synth.Vocab(V))
+synth.fill_state_dict(net)
+net.eval()
+fr, rg, caps, lens = synth.make_inputs(B, args, V, seed=34)
+logits = net(fr, rg, caps, args.max_words, 1.0)[0]
+o = torch.cat([logits[j][:lens[j]] for j in range(B)], 0)
+t = torch.cat([caps[j][:lens[j]] for j in range(B)], 0)
+torch.nn.CrossEntropyLoss()(o, t).backward()
+res['cbm.logits'] = logits.detach().numpy()
+for k, p in net.named_parameters():
+    res['cbm.g.' + k] = np.zeros(0, np.float32) if p.grad is None else p.grad.numpy()
+with torch.no_grad():
+    net.update_beam_size(1)
+    res['cbm.greedy'] = net(fr, rg, None)[0].numpy()
 np.savez(out_path, **res)
 '''
 
@@ -374,7 +393,7 @@ def test_edge_shapes_equal_the_reference_modules(tmp_path):
     for k in ref.files:
         a, b = ref[k], ours[k]
         assert a.shape == b.shape, k
-        if k.endswith('.beam3'):
+        if k.endswith('.beam3') or k.endswith('.greedy'):
             assert np.array_equal(a, b), k
         elif a.size:
             assert np.abs(a - b).max() < 1e-4 * max(1.0, float(np.abs(a).max())), (k, float(np.abs(a - b).max()))
