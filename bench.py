@@ -349,22 +349,22 @@ def main():
         # copy of step k+1 runs on a copy stream while step k computes; every step still copies its own 515 MB from pinned
         # host memory inside the timed region and reads its loss back.
         copy_stream = torch.cuda.Stream()
-        stage = [torch.empty_like(d_fr), torch.empty_like(d_rg), torch.empty_like(d_cp)]
+        stage_bufs = [torch.empty_like(d_fr), torch.empty_like(d_rg), torch.empty_like(d_cp)]
         ready = torch.cuda.Event()
         consumed = torch.cuda.Event()
 
         def prefetch():
             copy_stream.wait_event(consumed)
             with torch.cuda.stream(copy_stream):
-                stage[0].copy_(h_fr, non_blocking=True)
-                stage[1].copy_(h_rg, non_blocking=True)
-                stage[2].copy_(h_cp, non_blocking=True)
+                stage_bufs[0].copy_(h_fr, non_blocking=True)
+                stage_bufs[1].copy_(h_rg, non_blocking=True)
+                stage_bufs[2].copy_(h_cp, non_blocking=True)
                 ready.record(copy_stream)
 
         def e2e_pipe():
             cur = torch.cuda.current_stream()
             cur.wait_event(ready)
-            gs.load(stage[0], stage[1], stage[2])          # device-to-device into the graph's static inputs
+            gs.load(stage_bufs[0], stage_bufs[1], stage_bufs[2])          # device-to-device into the graph's static inputs
             consumed.record(cur)
             prefetch()                                     # next step's H2D overlaps this step's compute
             return gs().item()

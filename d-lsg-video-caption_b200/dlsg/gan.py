@@ -24,7 +24,7 @@ class GanIteration:
         self.G, self.D, self.opt_g, self.opt_d = G, D, opt_g, opt_d
         self.frames, self.regions, self.captions = frames.clone(), regions.clone(), captions.clone()
         self.lens = torch.as_tensor(list(cap_lens), dtype=torch.int32, device=dev)
-        self.inv = torch.tensor([1.0 / max(1, int(sum(cap_lens)))], dtype=torch.float32, device=dev)
+        self.inv = torch.tensor([1.0 / max(1, sum(min(int(c), max_words) for c in cap_lens))], dtype=torch.float32, device=dev)
         self.lam = torch.tensor(float(gan_lambda), dtype=torch.float32, device=dev)
         self.max_words, self.tf, self.num_d, self.batched = max_words, tf_ratio, num_d, batched
         self.V = D.conv1d.weight.shape[1]
@@ -141,7 +141,7 @@ class GanIteration:
         self.captions.copy_(captions, non_blocking=True)
         if cap_lens is not None:
             self.lens.copy_(torch.as_tensor(list(cap_lens), dtype=torch.int32))
-            self.inv.fill_(1.0 / max(1, int(sum(cap_lens))))
+            self.inv.fill_(1.0 / max(1, sum(min(int(c), self.max_words) for c in cap_lens)))
 
     def set_lambda(self, lam):
         self.lam.fill_(float(lam))
@@ -150,5 +150,7 @@ class GanIteration:
         """Returns device scalars (cap_loss, loss_G, loss_D of the last D step, wasserstein of the last D step)."""
         if self.graph is not None:
             self.graph.replay()
+            DF.WC.gen += 1    # parameters changed through raw pointers: eval-scope bf16 copies are stale now
+            la.new_param_epoch()
             return self.out
         return self._body()

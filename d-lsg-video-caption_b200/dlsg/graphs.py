@@ -14,6 +14,12 @@ from . import losses
 from . import optim
 
 
+def _inv_count(cap_lens, max_words):
+    """1 / number of packed tokens: the reference slices outputs[j][:cap_lens[j]] of a (max_words)-long row
+    (run_gun.py:189-197), so a caption longer than max_words contributes max_words tokens."""
+    return 1.0 / max(1, sum(min(int(c), max_words) for c in cap_lens))
+
+
 class GraphedTrainStep:
     def __init__(self, model, optimizer, frames, regions, captions, cap_lens, max_words=26, tf_ratio=1.0,
                  process_group=None, warmup=3, pin_weights=True, own_adam=True):
@@ -21,8 +27,8 @@ class GraphedTrainStep:
         self.model, self.opt, self.pg = model, optimizer, process_group
         self.frames, self.regions, self.captions = frames.clone(), regions.clone(), captions.clone()
         self.lens = torch.as_tensor(list(cap_lens), dtype=torch.int32, device=dev)
-        self.inv = torch.tensor([1.0 / max(1, int(sum(cap_lens)))], dtype=torch.float32, device=dev)
         self.max_words, self.tf = max_words, tf_ratio
+        self.inv = torch.tensor([_inv_count(cap_lens, max_words)], dtype=torch.float32, device=dev)
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.world = 1
         self.pinned = None
@@ -131,12 +137,13 @@ class GraphedTrainStep:
         self.captions.copy_(captions, non_blocking=True)
         if cap_lens is not None:
             self.lens.copy_(torch.as_tensor(list(cap_lens), dtype=torch.int32), non_blocking=False)
-            self.inv.fill_(1.0 / max(1, int(sum(cap_lens))))
+            self.inv.fill_(_inv_count(cap_lens, self.max_words))
 
     def __call__(self):
         if self.adam is not None:
             self.adam.sync_lr()                   # a scheduler may have changed the learning rate since the last replay
         self.graph.replay()
+        DF.WC.gen += 1        # the replay changed the parameters through raw pointers: no eval-scope bf16 copy survives it
         return self.loss
 
     def refresh_weights(self):
