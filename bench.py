@@ -1,14 +1,17 @@
-"""Benchmark of the D-LSG hot path on B200 (contract: one JSON line on rank 0).
+"""Benchmark of the D-LSG hot path on B200 (contract: ONE JSON line on rank 0).
 
 Workload (BASELINE.json configs[1]): D-LSG training step, batch 64 per GPU, MSR-VTT-shaped synthetic features
 (26 frames, 1536-d 2D + 2048-d 3D features, 36 x 2048 regions, V=10547, captions <= 26 tokens), bf16 tensor-core
 GEMMs with fp32 accumulation / fp32 master weights.  One step = zero_grad -> CapGnnModel forward -> fused masked
-cross-entropy -> backward -> Adam (lr 1.6e-4, betas (0.5,0.9), run_gun.py:91).  Metric: train clips/s.
+cross-entropy -> backward -> [gradient all-reduce] -> Adam (lr 1.6e-4, betas (0.5,0.9), run_gun.py:91).  Metric: train clips/s.
 
   value : device-resident inputs (regions are 490 MB/step > 126 MB L2, so every step streams from HBM)
   e2e   : same step through the public module API with HOST (pinned) inputs, H2D inside the timed region and a
           D2H read of the loss every step
-  --impl reference : the reference algorithm's CPU port (oracle/) timed on the host cores on a bounded sample
+  --impl reference : the reference's own CPU implementation (oracle/_ref: the unmodified reference modules staged by
+          oracle/stage_ref.py; the oracle port when that copy is absent) timed on the host cores on a bounded sample
+Secondary keys: greedy B=256 / beam-5 B=128 captions/s, one full GAN iteration (5 critic steps + G step; BASELINE config 5,
+also at N > 1), a scheduled-sampling (teacher forcing < 1) step, CPU baselines.
 """
 import argparse
 import json
@@ -28,9 +31,10 @@ import torch  # noqa: E402
 
 METRIC = 'train clips/s (fwd+bwd+Adam, B=64/GPU, MSR-VTT-shaped)'
 V_MSR = 10547
+EMUL = os.environ.get('DLSG_BENCH_EMUL') == '1'      # tests/test_bench_flow_cpu.py: CPU emulation of kernels + CUDA runtime
 
 
-def parse():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
@@ -38,10 +42,13 @@ def parse():
     ap.add_argument('--impl', type=str, default='b200')
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--no-decode', action='store_true')
+    ap.add_argument('--no-gan', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ref-batch', type=int, default=16, help='clips per step of the CPU reference arm (bounded sample)')
+    ap.add_argument('--no-ref-extras', action='store_true', help='reference arm: train step only (no decode / config-1 timings)')
     ap.add_argument('--graph', type=int, default=int(os.environ.get('DLSG_GRAPH', '1')))
     ap.add_argument('--profile-step', action='store_true', help='run W warm-up steps, then ONE eager step inside cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)')
-    return ap.parse_args()
+    return ap.parse_args(argv)
 
 
 class ClockSampler:
@@ -55,7 +62,7 @@ class ClockSampler:
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits',
-                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -88,55 +95,159 @@ class ClockSampler:
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def cpu_port_step_time(batch, steps, warmup, threads):
-    """Reference algorithm (oracle port, torch CPU fp32 autograd) fwd+CE+bwd+Adam on `batch` MSR-shaped clips."""
-    from dlsg import synth
-    from oracle import dlsg_oracle as O
+# ---- reference arm ---------------------------------------------------------------------------------------------------
+REF_DIR = os.path.join(ROOT, 'oracle', '_ref')
+
+
+def _load_reference():
+    """The UNMODIFIED reference modules from oracle/_ref (staged by oracle/stage_ref.py in the build container; the copy is
+    git-ignored and travels with the snapshot), imported with the one stub they need (allennlp's ConfigurationError,
+    models/allennlp_beamsearch.py:12).  Returns the reference's models.model module, or None when the copy is absent."""
+    if not os.path.exists(os.path.join(REF_DIR, 'models', 'model.py')):
+        return None
+    import types
+    for name in ('allennlp', 'allennlp.common', 'allennlp.common.checks'):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    if not hasattr(sys.modules['allennlp.common.checks'], 'ConfigurationError'):
+        sys.modules['allennlp.common.checks'].ConfigurationError = type('ConfigurationError', (Exception,), {})
+    assert 'models' not in sys.modules, 'the reference arm must not share a process with the drop-in models package'
+    sys.path.insert(0, REF_DIR)
     import contextlib
     import io
-    import models.model as M
-    torch.set_num_threads(threads)
-    args = synth.msr_args()
     with contextlib.redirect_stdout(io.StringIO()):
-        net = M.CapGnnModel(args, synth.Vocab(V_MSR))          # parameter container only (CPU); math = oracle
-    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and not k.endswith('pe.pe'))
-          for k, v in net.state_dict().items()}
-    params = [v for v in sd.values() if v.requires_grad]
-    opt = torch.optim.Adam(params, lr=1.6e-4, betas=(0.5, 0.9))
-    frames, regions, caps, lens = synth.make_inputs(batch, args, V_MSR, seed=12)
-    times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        opt.zero_grad()
-        out = O.cap_gnn_forward(sd, frames, regions, caps, 26, 1.0, args.a_feature_size)[0]
-        loss = O.packed_ce_loss(out, caps, lens)
-        loss.backward()
-        opt.step()
-        if it >= warmup:
-            times.append(time.perf_counter() - t0)
-    return sum(times) / len(times)
+        import models.model as RM
+    assert RM.__file__.startswith(REF_DIR), RM.__file__
+    return RM
+
+
+def _median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2]
 
 
 def run_reference(a):
-    rank = int(os.environ.get('RANK', '0'))
-    if rank != 0:
+    """CPU reference arm: rank 0 only.  Same metric / workload as our arm (MSR-VTT-shaped training step with Adam), each step a
+    bounded sample of `--ref-batch` clips; all host threads."""
+    if int(os.environ.get('RANK', '0')) != 0:
         return
+    import contextlib
+    import io
     threads = os.cpu_count() or 1
-    sample_b = 2
-    t = cpu_port_step_time(sample_b, a.steps, a.warmup, threads)
-    v = sample_b / t
+    torch.set_num_threads(threads)
+    from dlsg import synth
+    RM = _load_reference()
+    kind = 'reference' if RM is not None else 'port'
+    B = a.ref_batch
+    args = synth.msr_args(train_batch_size=B)
+    frames, regions, caps, lens = synth.make_inputs(B, args, V_MSR, seed=12)
+    torch.manual_seed(12)
+    extras = {}
+    if RM is not None:
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = RM.CapGnnModel(args, synth.Vocab(V_MSR))
+        net.train()
+        opt = torch.optim.Adam(net.parameters(), lr=1.6e-4, betas=(0.5, 0.9))                 # run_gun.py:91
+        crit = torch.nn.CrossEntropyLoss()                                                     # run_gun.py:90
+
+        def step():
+            opt.zero_grad()
+            out = net(frames, regions, caps, 26, 1.0)[0]
+            o = torch.cat([out[j][:lens[j]] for j in range(B)], 0)                             # run_gun.py:189-197
+            t = torch.cat([caps[j][:lens[j]] for j in range(B)], 0)
+            loss = crit(o, t)
+            loss.backward()
+            opt.step()
+            return loss
+        sample = ('%d MSR-VTT-shaped clips per step: the unmodified reference CapGnnModel (oracle/_ref) fwd + packed CE + bwd + '
+                  'torch Adam, fp32, train mode' % B)
+    else:
+        from oracle import dlsg_oracle as O
+        import models.model as M
+        with contextlib.redirect_stdout(io.StringIO()):
+            holder = M.CapGnnModel(args, synth.Vocab(V_MSR))          # parameter container only (CPU); math = oracle port
+        sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and not k.endswith('pe.pe'))
+              for k, v in holder.state_dict().items()}
+        opt = torch.optim.Adam([v for v in sd.values() if v.requires_grad], lr=1.6e-4, betas=(0.5, 0.9))
+
+        def step():
+            opt.zero_grad()
+            out = O.cap_gnn_forward(sd, frames, regions, caps, 26, 1.0, args.a_feature_size)[0]
+            loss = O.packed_ce_loss(out, caps, lens)
+            loss.backward()
+            opt.step()
+            return loss
+        sample = '%d MSR-VTT-shaped clips per step: oracle/dlsg_oracle.py (port of the reference) fwd + CE + bwd + torch Adam, fp32' % B
+    times = []
+    for it in range(a.warmup + a.steps):
+        t0 = time.perf_counter()
+        step()
+        if it >= a.warmup:
+            times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    v = B / t
+    if RM is not None and not a.no_ref_extras:
+        # BASELINE.json configs[0]: fwd+bwd, batch 8, MSVD-shaped, fp32 on CPU (R=16 is the reference's msvd setting,
+        # run_gun.py:31-35; R=36 is BASELINE's wording), plus greedy / beam-5 decode of the MSR model at batch 8
+        for R in (16, 36):
+            m_args = synth.msvd_args(num_obj=R, train_batch_size=8)
+            V2 = 9468
+            with contextlib.redirect_stdout(io.StringIO()):
+                n2 = RM.CapGnnModel(m_args, synth.Vocab(V2)).train()
+            f2, r2, c2, l2 = synth.make_inputs(8, m_args, V2, seed=12)
+            ts = []
+            for it in range(3):
+                t0 = time.perf_counter()
+                n2.zero_grad()
+                out = n2(f2, r2, c2, 26, 1.0)[0]
+                crit(torch.cat([out[j][:l2[j]] for j in range(8)], 0), torch.cat([c2[j][:l2[j]] for j in range(8)], 0)).backward()
+                ts.append(time.perf_counter() - t0)
+            extras['config1_msvd_B8_R%d_fwd_bwd_clips_per_s' % R] = 8 / _median(ts[1:])
+            del n2
+        net.eval()
+        f8, r8 = frames[:8], regions[:8]
+        with torch.no_grad():
+            for name, beam in (('greedy_B8_captions_per_s', 1), ('beam5_B8_captions_per_s', 5)):
+                net.update_beam_size(beam)
+                ts = []
+                for it in range(3):
+                    t0 = time.perf_counter()
+                    net(f8, r8, None)
+                    ts.append(time.perf_counter() - t0)
+                extras[name] = 8 / _median(ts[1:])
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'clips/s', 'n_gpus': a.gpus, 'steps': a.steps,
             'warmup': a.warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'D-LSG training step, MSR-VTT-shaped synthetic features (bounded sample: %d clips/step)' % sample_b},
-            'cpu_baseline': {'value': v, 'unit': 'clips/s', 'cores': threads, 'kind': 'port',
-                             'sample': '%d clips per step, fwd+CE+bwd+Adam, oracle/dlsg_oracle.py on torch CPU fp32' % sample_b},
+            'config': {'workload': 'D-LSG training step (CapGnnModel fwd + CE + bwd + Adam), MSR-VTT-shaped synthetic features '
+                                   '(26 frames, 1536+2048-d, 36x2048 regions, V=%d); CPU arm: bounded sample of %d clips per step' % (V_MSR, B),
+                       'global_batch': B},
+            'cpu_baseline': {'value': v, 'unit': 'clips/s', 'cores': threads, 'kind': kind, 'sample': sample},
             'e2e': {'value': v, 'unit': 'clips/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line))
+    line.update(extras)
+    print(json.dumps(line), flush=True)
 
 
+def cpu_baseline_subprocess(a):
+    """cpu_baseline of our own line (rank 0, N=1): the reference arm in a fresh process (its `models` package is the reference's
+    own, ours is already imported here), 1 warm-up + 3 timed steps of the bounded sample, with the decode / config-1 extras."""
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '3', '--warmup', '1', '--ref-batch', str(a.ref_batch)]
+    env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK')}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        for ln in r.stdout.splitlines():
+            if ln.startswith('{'):
+                d = json.loads(ln)
+                cb = d['cpu_baseline']
+                cb.update({k: v for k, v in d.items() if k.endswith('_per_s')})
+                return cb
+        return {'error': (r.stderr or 'no line')[-300:]}
+    except Exception as e:          # a reported baseline, never a reason to lose the measured line
+        return {'error': repr(e)[:300]}
+
+
+# ---- progress log / watchdog -----------------------------------------------------------------------------------------
 _STAGE = ['start']
 _T0 = time.time()
+_RESULT = {}            # the line so far: a stall in a secondary measurement still reports the headline
 
 
 def stage(name):
@@ -147,17 +258,27 @@ def stage(name):
 
 
 def arm_watchdog(a):
-    """A run that has not printed its line after DLSG_BENCH_TIMEOUT seconds (default 420) reports where it stalled and exits,
-    instead of sitting in a collective until the caller's own limit kills it."""
+    """A run that has not printed its line after DLSG_BENCH_TIMEOUT seconds (default 420) dumps every thread's Python stack,
+    reports where it stalled and exits instead of sitting in a collective until the caller's own limit kills it.  If the
+    headline was already measured (the stall is in a secondary metric) the line is printed as is and the exit code is 0."""
     limit = float(os.environ.get('DLSG_BENCH_TIMEOUT', '420'))
 
     def fire():
-        if int(os.environ.get('RANK', '0')) == 0:
-            print(json.dumps({'metric': METRIC, 'value': None, 'unit': 'clips/s', 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
-                              'error': 'no result after %.0f s; last stage: %s' % (limit, _STAGE[0])}), flush=True)
+        import faulthandler
         sys.stderr.write('[bench rank %s] watchdog: stalled in stage %r\n' % (os.environ.get('RANK', '0'), _STAGE[0]))
+        faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
         sys.stderr.flush()
-        os._exit(3)
+        rc = 3
+        if _RESULT.get('value') is not None:
+            rc = 0
+        if int(os.environ.get('RANK', '0')) == 0:
+            if rc == 0:
+                _RESULT['note'] = 'stalled after the headline in stage %r (watchdog, %.0f s)' % (_STAGE[0], limit)
+                print(json.dumps(_RESULT), flush=True)
+            else:
+                print(json.dumps({'metric': METRIC, 'value': None, 'unit': 'clips/s', 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
+                                  'error': 'no result after %.0f s; last stage: %s' % (limit, _STAGE[0])}), flush=True)
+        os._exit(rc)
     t = threading.Timer(limit, fire)
     t.daemon = True
     t.start()
@@ -165,28 +286,25 @@ def arm_watchdog(a):
 
 
 # ---- multi-rank supervisor -------------------------------------------------------------------------------------------
-# The only 8-GPU attempt of round 1 stalled after NCCL's start-up line and could not be investigated.  For
-# world >= 4 every rank therefore runs the measurement in a child process and, if the children have not finished inside a
-# fixed wall-clock window, kills them and tries the next, more conservative configuration.  The windows are absolute
-# (measured from process start, which torchrun makes simultaneous on all ranks), so every rank switches at the same time.
-TIERS = [('cuda-graph step, gradient all-reduce inside the graph', {}, []),
-         ('cuda-graph step, gradient all-reduce inside the graph, NCCL_NVLS_ENABLE=0', {'NCCL_NVLS_ENABLE': '0'}, []),
-         ('eager DistributedDataParallel step, NCCL_NVLS_ENABLE=0', {'NCCL_NVLS_ENABLE': '0'}, ['--graph', '0'])]
+# For world >= 4 every rank runs the measurement in a child process; a child that has not finished inside its wall-clock
+# window is killed and the next, more conservative configuration is tried with a fresh rendezvous.  A child that EXITS
+# (crash) moves its rank on at once - nobody sleeps to the end of the window because of a Python error.
+TIERS = [('cuda-graph step, bf16 gradient buckets all-reduced inside the graph', {}, []),
+         ('cuda-graph step, bf16 gradient buckets all-reduced inside the graph, NCCL_NVLS_ENABLE=0', {'NCCL_NVLS_ENABLE': '0'}, []),
+         ('eager DistributedDataParallel step, NCCL_NVLS_ENABLE=0', {'NCCL_NVLS_ENABLE': '0'}, ['--graph', '0', '--no-gan'])]
 
 
 def supervise(a):
-    win = [float(x) for x in os.environ.get('DLSG_BENCH_TIER_SECONDS', '120,120,150').split(',')]
+    win = [float(x) for x in os.environ.get('DLSG_BENCH_TIER_SECONDS', '220,220,220').split(',')]
     base_port = int(os.environ.get('MASTER_PORT', '29500'))
     rank0 = int(os.environ.get('RANK', '0')) == 0
     t_open = 0.0
     for i, (name, env_add, extra) in enumerate(TIERS):
         t_close = t_open + win[min(i, len(win) - 1)]
-        delay = _T0 + t_open - time.time()
-        if delay > 0:
-            time.sleep(delay)                         # every rank opens tier i at the same wall-clock time
         env = dict(os.environ)
         env.update(env_add)
-        env.update(DLSG_BENCH_WORKER='1', DLSG_BENCH_TIER=name, DLSG_BENCH_TIER_INDEX=str(i))
+        env.update(DLSG_BENCH_WORKER='1', DLSG_BENCH_TIER=name, DLSG_BENCH_TIER_INDEX=str(i),
+                   DLSG_BENCH_TIMEOUT=str(max(5.0, _T0 + t_close - time.time() - 4.0)))
         if i > 0:                                     # fresh rendezvous: rank 0's worker hosts a new store on another port
             env['MASTER_PORT'] = str(base_port + 17 * i)
             env['TORCHELASTIC_USE_AGENT_STORE'] = 'False'
@@ -201,23 +319,33 @@ def supervise(a):
         if rc == 0:
             return 0
         stage('supervisor: tier %d %s' % (i, 'timed out' if rc is None else 'exited with %s' % rc))
-        t_open = t_close + float(os.environ.get('DLSG_BENCH_TIER_GAP', '8'))   # let the killed workers' GPU contexts disappear
+        if rc is None:
+            t_open = t_close + float(os.environ.get('DLSG_BENCH_TIER_GAP', '8'))   # let the killed workers' GPU contexts disappear
+            delay = _T0 + t_open - time.time()
+            if delay > 0:
+                time.sleep(delay)
+        else:
+            # crashed: go on at once (the peers follow when their own child fails or is killed; the new rendezvous waits for them)
+            t_open = max(0.0, time.time() - _T0)
     if rank0:
         print(json.dumps({'metric': METRIC, 'value': None, 'unit': 'clips/s', 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
                           'error': 'no multi-rank configuration finished (see the stage log on stderr)'}), flush=True)
     return 3
 
 
-def main():
-    a = parse()
+def main(argv=None):
+    a = parse(argv)
     if a.impl == 'reference':
         return run_reference(a)
     if int(os.environ.get('WORLD_SIZE', '1')) >= 4 and os.environ.get('DLSG_BENCH_WORKER') != '1':
         sys.exit(supervise(a))
     fake = os.environ.get('DLSG_BENCH_FAKE')          # supervisor self-test hook (tests/test_bench_supervisor_cpu.py)
     if fake is not None:
-        if os.environ.get('DLSG_BENCH_TIER_INDEX', '0') in fake.split(','):
+        idx = os.environ.get('DLSG_BENCH_TIER_INDEX', '0')
+        if idx in fake.split(','):
             time.sleep(3600)
+        if ('x' + idx) in fake.split(','):
+            sys.exit(7)                               # a crashing tier
         print(json.dumps({'fake': True, 'tier': os.environ.get('DLSG_BENCH_TIER'), 'port': os.environ.get('MASTER_PORT'),
                           'nvls': os.environ.get('NCCL_NVLS_ENABLE'), 'argv': sys.argv[1:]}), flush=True)
         return
@@ -225,13 +353,22 @@ def main():
     import contextlib
     import io
     from dlsg import synth, ops, losses, linalg as la
+    if EMUL:
+        sys.path.insert(0, os.path.join(ROOT, 'tests'))
+        import cpu_emul
+        import fake_cuda
+        fake_cuda.install()
+        ops.set_backend(cpu_emul.CpuEmulBackend())
     import models.model as M
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
-    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
+    if EMUL:
+        dev = torch.device('cpu')
+    else:
+        assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
+        torch.cuda.set_device(local)
+        dev = torch.device('cuda', local)
     dist = None
     if world > 1:
         import datetime
@@ -239,31 +376,44 @@ def main():
         # user-buffer registration for captured collectives only applies to VMM allocations (not the caching allocator's):
         # switch the attempt off; a collective that cannot complete aborts after 3 minutes instead of hanging
         os.environ.setdefault('NCCL_GRAPH_REGISTER', '0')
-        stage('init_process_group(nccl) world=%d' % world)
-        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
+        stage('init_process_group(%s) world=%d' % ('gloo' if EMUL else 'nccl', world))
+        if EMUL:
+            dist.init_process_group('gloo', timeout=datetime.timedelta(seconds=180))
+        else:
+            dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
         stage('process group ready')
-    la.set_precision('bf16')
-    args = synth.msr_args(train_batch_size=a.batch)
-    B = a.batch
+    la.set_precision('fp32' if EMUL else 'bf16')
+    if EMUL:
+        # (node width 1024: PSLScore2's 1024 -> 512 projection of the critic is hard-coded, layer.py:665)
+        args, V = synth.small_args(train_batch_size=a.batch, visual_hidden_size=1024, region_projected_size=1024, query_hidden_size=1024,
+                                   max_words=5, max_frames=4), 37
+    else:
+        args, V = synth.msr_args(train_batch_size=a.batch), V_MSR
+    B, L = a.batch, args.max_words
     torch.manual_seed(12)
     with contextlib.redirect_stdout(io.StringIO()):
-        net = M.CapGnnModel(args, synth.Vocab(V_MSR)).to(dev)
-    net.train()
+        net = M.CapGnnModel(args, synth.Vocab(V)).to(dev)
+    train_mode = (lambda m: m.eval()) if EMUL else (lambda m: m.train())      # (the CPU emulation has no dropout)
+    train_mode(net)
     model = net
     use_graph = bool(a.graph) and not a.profile_step
     if world > 1 and not use_graph:
-        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], find_unused_parameters=True,
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=None if EMUL else [local], find_unused_parameters=True,
                                                           gradient_as_bucket_view=True)
-    opt = torch.optim.Adam(net.parameters(), lr=1.6e-4, betas=(0.5, 0.9), fused=True, capturable=use_graph)
+    opt = torch.optim.Adam(net.parameters(), lr=1.6e-4, betas=(0.5, 0.9), fused=not EMUL, capturable=use_graph and not EMUL)
     stage('model built; generating synthetic inputs')
-    frames, regions, caps, lens = synth.make_inputs(B, args, V_MSR, seed=12 + rank)
+    frames, regions, caps, lens = synth.make_inputs(B, args, V, seed=12 + rank)
     h_fr, h_rg, h_cp = frames.pin_memory(), regions.pin_memory(), caps.pin_memory()
     d_fr, d_rg, d_cp = h_fr.to(dev), h_rg.to(dev), h_cp.to(dev)
+    # the input pipeline's host format: features kept in bf16 in pinned host memory - the same rounding the bf16
+    # GEMM path applies to its operands anyway (bit-identical results, tests/test_model_gpu.py::test_bf16_features_bit_identical),
+    # half the PCIe bytes of the fp32 loader format
+    h_fr16, h_rg16 = frames.to(torch.bfloat16).pin_memory(), regions.to(torch.bfloat16).pin_memory()
     be = ops.backend()
 
-    def step(fr, rg, cp):
+    def step(fr, rg, cp, tf=1.0):
         opt.zero_grad(set_to_none=True)
-        out = model(fr, rg, cp, 26, 1.0)[0]
+        out = model(fr, rg, cp, L, tf)[0]
         loss = losses.packed_cross_entropy(out, cp, lens)
         loss.backward()
         opt.step()
@@ -297,19 +447,27 @@ def main():
         step(d_fr, d_rg, d_cp)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
+        watchdog.cancel()
         return
     # ---- device-resident timing
-    eager_ms = None
+    eager_ms = eager_ss_ms = None
+    gs = None
+    pg = dist.group.WORLD if dist is not None else None
     if use_graph:
         from dlsg.graphs import GraphedTrainStep
         if world == 1:
+            import random
             for _ in range(2):
                 step(d_fr, d_rg, d_cp)
             eager_ms = timed(lambda: step(d_fr, d_rg, d_cp), 3)
-        l0 = be.launches
+            # scheduled sampling as the live trainer runs it (run_gun.py:149-151: ratio in [0.6, 1), one coin per time step for the
+            # whole batch, layer.py:432): the steps that feed the arg-max back pay a per-step vocabulary GEMM + arg-max.  Eager
+            # only: a captured graph freezes the coins.
+            random.seed(12)
+            step(d_fr, d_rg, d_cp, 0.8)
+            eager_ss_ms = timed(lambda: step(d_fr, d_rg, d_cp, 0.8), 3)
         stage('capturing the training step (eager warm-up steps first when world > 1)')
-        gs = GraphedTrainStep(net, opt, d_fr, d_rg, d_cp, lens, 26, 1.0,
-                              process_group=(dist.group.WORLD if dist is not None else None), warmup=(0 if world == 1 else 3))
+        gs = GraphedTrainStep(net, opt, d_fr, d_rg, d_cp, lens, L, 1.0, process_group=pg, warmup=(0 if world == 1 else 2))
         launches = gs.launches
         run_dev = lambda: gs()
 
@@ -330,54 +488,89 @@ def main():
         run_dev()
     stage('timed region: %d steps' % a.steps)
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not EMUL:
         sampler.start()
     l0 = be.launches
     ms = timed(run_dev, a.steps)
     if launches is None:
         launches = (be.launches - l0) // a.steps
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if rank == 0 and not EMUL else None
+    line = {'metric': METRIC, 'value': world * B / (ms * 1e-3), 'unit': 'clips/s', 'n_gpus': world, 'steps': a.steps,
+            'warmup': a.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': 'D-LSG training step (CapGnnModel fwd + masked CE + bwd + Adam), batch %d/GPU, MSR-VTT-shaped '
+                                   'synthetic features (26 frames, 1536+2048-d, 36x2048 regions, V=%d), bf16 GEMMs fp32 accum, '
+                                   'teacher forcing 1.0 (SURVEY 8d config 1)' % (B, V),
+                       'global_batch': world * B, 'parallelism': 'dp%d' % world,
+                       'multi_rank_path': os.environ.get('DLSG_BENCH_TIER', TIERS[0][0] if use_graph else TIERS[2][0]) if world > 1 else None,
+                       'grad_allreduce_bytes_per_step': (gs.sync.bytes if gs is not None and world > 1 else None),
+                       'l2': 'inputs (490 MB regions/step) exceed the 126 MB L2; no explicit flush'},
+            'gpu_launches': launches, 'clocks': clocks, 'cuda_graph': use_graph, 'eager_ms_per_step': eager_ms,
+            'eager_scheduled_sampling_tf0.8_ms_per_step': eager_ss_ms}
+    _RESULT.update(line)
     # ---- end-to-end: host pinned inputs -> H2D -> step -> loss.item()
     stage('end-to-end (host inputs) timing')
     for _ in range(2):
         e2e_step()
     ms_e2e_serial = timed(e2e_step, a.steps)
-    ms_e2e = ms_e2e_serial
-    h2d = h_fr.numel() * 4 + h_rg.numel() * 4 + h_cp.numel() * 8
+    ms_e2e = ms_e2e_fp32 = ms_e2e_serial
+    h2d = h2d_fp32 = h_fr.numel() * 4 + h_rg.numel() * 4 + h_cp.numel() * 8
+    mode = 'serial: fp32 pinned host features, H2D then step'
     if use_graph:
-        # Same work with the loader-style prefetch any trainer uses (DataLoader(pin_memory) + non_blocking copies): the H2D
-        # copy of step k+1 runs on a copy stream while step k computes; every step still copies its own 515 MB from pinned
-        # host memory inside the timed region and reads its loss back.
+        # The loader-style prefetch any trainer uses (DataLoader(pin_memory) + non_blocking copies): the H2D copy of step k+1
+        # runs on a copy stream while step k computes; every step still copies its own inputs from pinned host memory inside the
+        # timed region and reads its loss back.  Measured for both host formats: fp32 (the reference loader's, utils/data.py:60-62)
+        # and bf16 (half the PCIe bytes).
         copy_stream = torch.cuda.Stream()
-        stage_bufs = [torch.empty_like(d_fr), torch.empty_like(d_rg), torch.empty_like(d_cp)]
-        ready = torch.cuda.Event()
-        consumed = torch.cuda.Event()
 
-        def prefetch():
-            copy_stream.wait_event(consumed)
-            with torch.cuda.stream(copy_stream):
-                stage_bufs[0].copy_(h_fr, non_blocking=True)
-                stage_bufs[1].copy_(h_rg, non_blocking=True)
-                stage_bufs[2].copy_(h_cp, non_blocking=True)
-                ready.record(copy_stream)
+        def make_pipe(g, hf, hr):
+            bufs = [torch.empty_like(hf, device=dev), torch.empty_like(hr, device=dev), torch.empty_like(d_cp)]
+            ready, consumed = torch.cuda.Event(), torch.cuda.Event()
 
-        def e2e_pipe():
-            cur = torch.cuda.current_stream()
-            cur.wait_event(ready)
-            gs.load(stage_bufs[0], stage_bufs[1], stage_bufs[2])          # device-to-device into the graph's static inputs
-            consumed.record(cur)
-            prefetch()                                     # next step's H2D overlaps this step's compute
-            return gs().item()
-        consumed.record(torch.cuda.current_stream())
-        prefetch()
+            def prefetch():
+                copy_stream.wait_event(consumed)
+                with torch.cuda.stream(copy_stream):
+                    bufs[0].copy_(hf, non_blocking=True)
+                    bufs[1].copy_(hr, non_blocking=True)
+                    bufs[2].copy_(h_cp, non_blocking=True)
+                    ready.record(copy_stream)
+
+            def pipe():
+                cur = torch.cuda.current_stream()
+                cur.wait_event(ready)
+                g.load(bufs[0], bufs[1], bufs[2])              # device-to-device into the graph's static inputs
+                consumed.record(cur)
+                prefetch()                                     # next step's H2D overlaps this step's compute
+                return g().item()
+            consumed.record(torch.cuda.current_stream())
+            prefetch()
+            return pipe
+        pipe32 = make_pipe(gs, h_fr, h_rg)
         for _ in range(2):
-            e2e_pipe()
-        ms_e2e = timed(e2e_pipe, a.steps)
+            pipe32()
+        ms_e2e_fp32 = timed(pipe32, a.steps)
+        del pipe32
+        stage('end-to-end with bf16 host features (a step captured on bf16 static inputs)')
+        gs16 = GraphedTrainStep(net, opt, d_fr.to(torch.bfloat16), d_rg.to(torch.bfloat16), d_cp, lens, L, 1.0, process_group=pg,
+                                warmup=(0 if world == 1 else 1))
+        pipe16 = make_pipe(gs16, h_fr16, h_rg16)
+        for _ in range(2):
+            pipe16()
+        ms_e2e = timed(pipe16, a.steps)
+        line['device_resident_bf16_features_ms_per_step'] = timed(lambda: gs16(), a.steps)
+        h2d = h_fr16.numel() * 2 + h_rg16.numel() * 2 + h_cp.numel() * 8
+        mode = 'bf16 pinned host features; H2D of step k+1 prefetched on a copy stream during step k'
+        del pipe16, gs16
+    line['e2e'] = {'value': world * B / (ms_e2e * 1e-3), 'unit': 'clips/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+                   'ms_per_step': ms_e2e, 'mode': mode, 'serial_fp32_ms_per_step': ms_e2e_serial,
+                   'prefetched_fp32_host_features': {'ms_per_step': ms_e2e_fp32, 'h2d_bytes_per_step': h2d_fp32,
+                                                     'value': world * B / (ms_e2e_fp32 * 1e-3)}}
+    _RESULT.update(line)
 
     # ---- dominant kernel: region-projection GEMM (both encoders fused: M=B*936, N=2048, K=2048) timed alone
-    roof = None
     extra = {}
-    if rank == 0:
+    if rank == 0 and not EMUL:
+        stage('roofline kernel')
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -391,93 +584,89 @@ def main():
         for _ in range(3):
             be.gemm(A, Wt, O_, bias=bias, tanh=True)
         n = 10
-        k_ms = timed(lambda: be.gemm(A, Wt, O_, bias=bias, tanh=True), n) if dist is None else None
-        if k_ms is None:
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(n):
-                be.gemm(A, Wt, O_, bias=bias, tanh=True)
-            e1.record()
-            torch.cuda.synchronize()
-            k_ms = e0.elapsed_time(e1) / n
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            be.gemm(A, Wt, O_, bias=bias, tanh=True)
+        e1.record()
+        torch.cuda.synchronize()
+        k_ms = e0.elapsed_time(e1) / n
         flops = 2.0 * Mr * Nr * Kr
         ach = flops / (k_ms * 1e-3) / 1e12
         peak = peaks.get('bf16_tflops', 1590.0)
-        roof = {'bound': 'tensor', 'kernel': 'gemm_tc_kernel<256> region projection %dx%dx%d bf16 (+bias+tanh, bf16 out)' % (Mr, Nr, Kr),
-                'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the committed ncu --set full
-                # capture profiles/r01_ncu_full_top_kernels_v2.json (algorithmic: A 245 MB + W 8 MB read, 245 MB written)
-                'traffic': 253.84e6 + 208.14e6, 'traffic_unit': 'bytes/launch',
-                'peak_source': 'measured (MEASURED_PEAKS.json bf16_tflops, burst)' if 'bf16_tflops' in peaks else 'fallback',
-                'ms_per_launch': k_ms, 'launches_per_step': 1}
+        line['roofline'] = {'bound': 'tensor', 'kernel': 'gemm_tc_kernel<256> region projection %dx%dx%d bf16 (+bias+tanh, bf16 out)' % (Mr, Nr, Kr),
+                            'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
+                            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the committed ncu --set full
+                            # capture profiles/r01_ncu_full_top_kernels_v2.json (algorithmic: A 245 MB + W 8 MB read, 245 MB written)
+                            'traffic': 253.84e6 + 208.14e6, 'traffic_unit': 'bytes/launch',
+                            'peak_source': 'measured (MEASURED_PEAKS.json bf16_tflops, burst)' if 'bf16_tflops' in peaks else 'fallback',
+                            'ms_per_launch': k_ms, 'launches_per_step': 1}
         del A, Wt, O_
-        # ---- decoding throughput (secondary metrics of BASELINE.json: greedy B=256, beam-5 B=128)
-        stage('secondary metrics (roofline kernel, decode, GAN iteration, CPU baseline)')
-        if not a.no_decode and world == 1:
-            net.eval()
-            with torch.no_grad():
-                for name, Bd, beam in (('greedy_captions_per_s_B256', 256, 1), ('beam5_captions_per_s_B128', 128, 5)):
-                    f2, r2, _, _ = synth.make_inputs(Bd, args, V_MSR, seed=7)
-                    f2, r2 = f2.to(dev), r2.to(dev)
-                    net.update_beam_size(beam)
-                    for _ in range(3):
-                        net(f2, r2, None)
-                    dms = timed(lambda: net(f2, r2, None), 5)
-                    extra[name + '_eager'] = Bd / (dms * 1e-3)
-                    if use_graph:
-                        from dlsg.graphs import GraphedDecode
-                        gd = GraphedDecode(net, f2, r2, beam)
-                        for _ in range(2):
-                            gd()
-                        dms = timed(lambda: gd(), 5)
-                        del gd
-                    extra[name] = Bd / (dms * 1e-3)
-            net.train()
-            # ---- full GAN iteration of the live trainer (BASELINE.json configs[4] at one GPU; run_gun.py:147-234 + :339-398):
-            # G forward, 5 critic steps with the WGAN-GP double backward, G step with the critic term, both Adams
-            try:
-                from dlsg.gan import GanIteration
-                with contextlib.redirect_stdout(io.StringIO()):
-                    Dnet = M.DiscV2(args, V_MSR).to(dev).train()
-                og = torch.optim.Adam(net.parameters(), lr=1.6e-4, betas=(0.5, 0.9), fused=True, capturable=True)
-                od = torch.optim.Adam(Dnet.parameters(), lr=1.6e-4, betas=(0.5, 0.9), fused=True, capturable=True)
-                gi = GanIteration(net, Dnet, og, od, d_fr, d_rg, d_cp, lens, 26, 0.6, 5, 0.01, graph=use_graph)
-                for _ in range(2):
-                    gi()
-                gms = timed(lambda: gi(), 3)
-                extra['gan_iteration_ms_B%d' % B] = gms
-                extra['gan_iteration_clips_per_s'] = B / (gms * 1e-3)
-                del gi, Dnet, og, od
-            except Exception as e:                  # secondary metric: never take the headline line down with it
-                extra['gan_iteration_error'] = repr(e)[:200]
-    # ---- CPU baseline beside it (rank 0, N=1 only)
-    cpu = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        sb = 2
-        t = cpu_port_step_time(sb, 2, 1, threads)
-        cpu = {'value': sb / t, 'unit': 'clips/s', 'cores': threads, 'kind': 'port',
-               'sample': '%d clips per step x 2 steps, fwd+CE+bwd+Adam, oracle/dlsg_oracle.py (torch CPU fp32)' % sb}
+        _RESULT.update(line)
+    # ---- decoding throughput (secondary metrics of BASELINE.json: greedy B=256, beam-5 B=128), one GPU
+    if rank == 0 and world == 1 and not a.no_decode:
+        stage('decode throughput')
+        net.eval()
+        with torch.no_grad():
+            for name, Bd, beam in (('greedy_captions_per_s_B256', 256, 1), ('beam5_captions_per_s_B128', 128, 5)):
+                if EMUL:
+                    Bd = 2
+                f2, r2, _, _ = synth.make_inputs(Bd, args, V, seed=7)
+                f2, r2 = f2.to(dev), r2.to(dev)
+                net.update_beam_size(beam)
+                for _ in range(3):
+                    net(f2, r2, None)
+                dms = timed(lambda: net(f2, r2, None), 5)
+                extra[name + '_eager'] = Bd / (dms * 1e-3)
+                if use_graph:
+                    from dlsg.graphs import GraphedDecode
+                    gd = GraphedDecode(net, f2, r2, beam)
+                    for _ in range(2):
+                        gd()
+                    dms = timed(lambda: gd(), 5)
+                    del gd
+                extra[name] = Bd / (dms * 1e-3)
+        train_mode(net)
+        line.update(extra)
+        _RESULT.update(line)
+    # ---- full GAN iteration of the live trainer (BASELINE.json configs[4]; run_gun.py:147-234 + :339-398): G forward, 5 critic
+    # steps with the WGAN-GP double backward, G step with the critic term, both Adams; at N > 1 every rank runs it on its own 64
+    # clips with the critic and generator gradients all-reduced inside the captured iteration
+    if not a.no_gan and use_graph:
+        stage('GAN iteration (generator + critic losses)')
+        try:
+            from dlsg.gan import GanIteration
+            del gs
+            with contextlib.redirect_stdout(io.StringIO()):
+                Dnet = train_mode(M.DiscV2(args, V).to(dev))
+            if dist is not None:
+                for p_ in Dnet.parameters():
+                    dist.broadcast(p_.data, 0)
+            og = torch.optim.Adam(net.parameters(), lr=1.6e-4, betas=(0.5, 0.9), fused=not EMUL, capturable=not EMUL)
+            od = torch.optim.Adam(Dnet.parameters(), lr=1.6e-4, betas=(0.5, 0.9), fused=not EMUL, capturable=not EMUL)
+            gi = GanIteration(net, Dnet, og, od, d_fr, d_rg, d_cp, lens, L, 0.6, 5, 0.01, process_group=pg, graph=True,
+                              warmup=(2 if world == 1 else 1))
+            for _ in range(2):
+                gi()
+            gms = timed(lambda: gi(), 3)
+            extra['gan_iteration_ms_B%d' % B] = gms
+            extra['gan_iteration_clips_per_s'] = world * B / (gms * 1e-3)
+            del gi, Dnet, og, od
+        except Exception as e:                  # secondary metric: never take the headline line down with it
+            extra['gan_iteration_error'] = repr(e)[:300]
+        line.update(extra)
+        _RESULT.update(line)
+    # ---- CPU baseline beside it (rank 0, N=1 only): the reference arm in its own process
+    line['cpu_baseline'] = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and not EMUL:
+        stage('CPU baseline (reference arm, bounded sample)')
+        line['cpu_baseline'] = cpu_baseline_subprocess(a)
     stage('done')
     watchdog.cancel()
     if rank == 0:
-        line = {'metric': METRIC, 'value': world * B / (ms * 1e-3), 'unit': 'clips/s', 'n_gpus': world, 'steps': a.steps,
-                'warmup': a.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'bf16', 'data': 'synthetic',
-                'config': {'workload': 'D-LSG training step (CapGnnModel fwd + masked CE + bwd + Adam), batch %d/GPU, MSR-VTT-shaped '
-                                       'synthetic features (26 frames, 1536+2048-d, 36x2048 regions, V=%d), bf16 GEMMs fp32 accum' % (B, V_MSR),
-                           'global_batch': world * B, 'parallelism': 'dp%d' % world,
-                           'multi_rank_path': os.environ.get('DLSG_BENCH_TIER', TIERS[0][0] if use_graph else TIERS[2][0]) if world > 1 else None,
-                           'l2': 'inputs (490 MB regions/step) exceed the 126 MB L2; no explicit flush'},
-                'e2e': {'value': world * B / (ms_e2e * 1e-3), 'unit': 'clips/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
-                        'ms_per_step': ms_e2e, 'mode': 'H2D of step k+1 prefetched on a copy stream during step k' if use_graph else 'serial',
-                        'serial_ms_per_step': ms_e2e_serial},
-                'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
-                'cuda_graph': use_graph, 'eager_ms_per_step': eager_ms}
-        line.update(extra)
         print(json.dumps(line), flush=True)
-    if dist is not None:
+    if dist is not None and not EMUL:
         # A captured CUDA graph that contains NCCL kernels keeps the communicator busy at interpreter shutdown
         # (destroy_process_group was observed to hang): make sure all ranks are done, then leave without teardown.
         dist.barrier()

@@ -613,12 +613,31 @@ norm_bwd2_kernel(const dlsg_norm_bwd2_t p) {
 // segments dst[r,c] = cast(src[r,c] (+ src2[r,c])) (fp32 sources; bf16 or fp32 destinations with their own pitch: row
 // slices of stacked weights, column segments of the packed LSTM gate matrices, summed bias pairs) and a table of
 // (segment, first row, rows) chunks of ~16K elements, one CTA each.
-__global__ void __launch_bounds__(256)
-multi_convert_kernel(const dlsg_seg_t* __restrict__ segs, const int32_t* __restrict__ chunks) {
-  pdl_prologue();
-  const dlsg_seg_t sg = segs[chunks[3 * blockIdx.x]];
-  const int64_t row0 = chunks[3 * blockIdx.x + 1];
-  const int nrows = chunks[3 * blockIdx.x + 2];
+__device__ __forceinline__ void convert_rows(const dlsg_seg_t& sg, const int64_t row0, const int nrows) {
+  if (sg.src_dtype == DLSG_BF16) {               // bf16 source (a reduced gradient bucket read back as fp32): no src2
+    const __nv_bfloat16* s16 = static_cast<const __nv_bfloat16*>(sg.src) + row0 * sg.ld_src;
+    const bool v4 = (sg.cols % 4 == 0) && (sg.ld_src % 4 == 0) && (sg.ld_dst % 4 == 0) && sg.dst_dtype == DLSG_F32 &&
+                    ((reinterpret_cast<uintptr_t>(sg.src) & 7) == 0) && ((reinterpret_cast<uintptr_t>(sg.dst) & 15) == 0);
+    if (v4) {
+      const int c4 = (int)(sg.cols >> 2);
+      const int64_t n = (int64_t)nrows * c4;
+      for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
+        const int64_t r = e / c4;
+        const int c = (int)(e % c4) * 4;
+        const uint2 raw = *reinterpret_cast<const uint2*>(s16 + r * sg.ld_src + c);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+        *reinterpret_cast<float4*>(static_cast<float*>(sg.dst) + (row0 + r) * sg.ld_dst + c) = make_float4(a.x, a.y, b.x, b.y);
+      }
+    } else {
+      const int64_t n = (int64_t)nrows * sg.cols;
+      for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
+        const int64_t r = e / sg.cols, c = e % sg.cols;
+        st_from_float(sg.dst, sg.dst_dtype, (row0 + r) * sg.ld_dst + c, __bfloat162float(s16[r * sg.ld_src + c]));
+      }
+    }
+    return;
+  }
   const float* src = static_cast<const float*>(sg.src) + row0 * sg.ld_src;
   const float* src2 = sg.src2 ? static_cast<const float*>(sg.src2) + row0 * sg.ld_src : nullptr;
   const bool bf = sg.dst_dtype == DLSG_BF16;
@@ -657,11 +676,42 @@ multi_convert_kernel(const dlsg_seg_t* __restrict__ segs, const int32_t* __restr
   }
 }
 
+__global__ void __launch_bounds__(256)
+multi_convert_kernel(const dlsg_seg_t* __restrict__ segs, const int32_t* __restrict__ chunks) {
+  pdl_prologue();
+  const dlsg_seg_t sg = segs[chunks[3 * blockIdx.x]];
+  convert_rows(sg, chunks[3 * blockIdx.x + 1], chunks[3 * blockIdx.x + 2]);
+}
+
+// Same work with the segment table passed BY VALUE in the kernel parameters (like adam_multi_kernel): nothing is uploaded,
+// so it can be issued with fresh pointers in the middle of a CUDA-graph capture (the per-block gradient packs of a
+// data-parallel step, dlsg.functional.GradSync).
+constexpr int CONV_MAX_SEGS = 384;
+struct ConvArgs {
+  dlsg_seg_t seg[CONV_MAX_SEGS];
+  int32_t chunk_start[CONV_MAX_SEGS + 1];
+  int32_t rows_per_chunk[CONV_MAX_SEGS];
+  int32_t nsegs;
+};
+
+__global__ void __launch_bounds__(256)
+multi_convert_args_kernel(const __grid_constant__ ConvArgs a) {
+  pdl_prologue();
+  int lo = 0, hi = a.nsegs - 1;
+  while (lo < hi) {
+    const int md = (lo + hi + 1) >> 1;
+    if (a.chunk_start[md] <= (int)blockIdx.x) lo = md; else hi = md - 1;
+  }
+  const dlsg_seg_t& sg = a.seg[lo];
+  const int64_t row0 = (int64_t)((int)blockIdx.x - a.chunk_start[lo]) * a.rows_per_chunk[lo];
+  convert_rows(sg, row0, (int)min((int64_t)a.rows_per_chunk[lo], sg.rows - row0));
+}
+
 // ------------------------------------------------------------------------------------------- multi-tensor Adam
 // torch.optim.Adam's update (run_gun.py:91: lr 1.6e-4, betas (0.5, 0.9), no weight decay / amsgrad) over a device table of
 // 2-D segments, one launch per parameter block, writing the bf16 GEMM-operand copy of each weight in the same pass:
 //   m = m + (g - m)(1 - b1);  v = b2 v + (1 - b2) g^2;  p -= (lr / (1 - b1^t)) m / (sqrt(v) / sqrt(1 - b2^t) + eps)
-constexpr int ADAM_MAX_SEGS = 320;
+constexpr int ADAM_MAX_SEGS = 256;
 struct AdamArgs {                       // passed BY VALUE as a kernel parameter (a CUDA-graph kernel node keeps it: no table upload)
   dlsg_adam_seg_t seg[ADAM_MAX_SEGS];
   int32_t chunk_start[ADAM_MAX_SEGS + 1];   // first chunk (CTA) of each segment
@@ -692,14 +742,16 @@ adam_multi_kernel(const __grid_constant__ AdamArgs a, const float* __restrict__ 
   const int64_t row0 = (int64_t)((int)blockIdx.x - a.chunk_start[lo]) * a.rows_per_chunk[lo];
   const int nrows = (int)min((int64_t)a.rows_per_chunk[lo], sg.rows - row0);
   float* P = sg.p + row0 * sg.ld;
-  const float* G = sg.g + row0 * sg.ld;
+  const bool g16 = sg.g_dtype == DLSG_BF16;
+  const float* G = static_cast<const float*>(sg.g) + (g16 ? 0 : row0 * sg.ld_g);
+  const __nv_bfloat16* G16 = static_cast<const __nv_bfloat16*>(sg.g) + (g16 ? row0 * sg.ld_g : 0);
   float* M = sg.m + row0 * sg.ld;
   float* V = sg.v + row0 * sg.ld;
   __nv_bfloat16* S16 = sg.dst16 ? static_cast<__nv_bfloat16*>(sg.dst16) + row0 * sg.ld_dst : nullptr;
   const float omb1 = 1.f - beta1, omb2 = 1.f - beta2;
-  const bool vec = (sg.cols % 4 == 0) && (sg.ld % 4 == 0) &&
-                   (((reinterpret_cast<uintptr_t>(sg.p) | reinterpret_cast<uintptr_t>(sg.g) | reinterpret_cast<uintptr_t>(sg.m) |
-                      reinterpret_cast<uintptr_t>(sg.v)) & 15) == 0) &&
+  const bool vec = (sg.cols % 4 == 0) && (sg.ld % 4 == 0) && (sg.ld_g % 4 == 0) &&
+                   (((reinterpret_cast<uintptr_t>(sg.p) | reinterpret_cast<uintptr_t>(sg.m) | reinterpret_cast<uintptr_t>(sg.v)) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(sg.g) & (g16 ? 7 : 15)) == 0) &&
                    (!sg.dst16 || ((sg.ld_dst % 4 == 0) && (reinterpret_cast<uintptr_t>(sg.dst16) & 7) == 0));
   if (vec) {
     const int c4 = (int)(sg.cols >> 2);
@@ -709,7 +761,15 @@ adam_multi_kernel(const __grid_constant__ AdamArgs a, const float* __restrict__ 
       const int c = (int)(e % c4) * 4;
       const int64_t o = r * sg.ld + c;
       float4 p4 = *reinterpret_cast<const float4*>(P + o);
-      const float4 g4 = *reinterpret_cast<const float4*>(G + o);
+      float4 g4;
+      if (g16) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(G16 + r * sg.ld_g + c);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+        g4 = make_float4(a.x, a.y, b.x, b.y);
+      } else {
+        g4 = *reinterpret_cast<const float4*>(G + r * sg.ld_g + c);
+      }
       float4 m4 = *reinterpret_cast<const float4*>(M + o), v4 = *reinterpret_cast<const float4*>(V + o);
       float pp[4] = {p4.x, p4.y, p4.z, p4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
       float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
@@ -734,7 +794,7 @@ adam_multi_kernel(const __grid_constant__ AdamArgs a, const float* __restrict__ 
     for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
       const int64_t r = e / sg.cols, c = e % sg.cols;
       const int64_t o = r * sg.ld + c;
-      const float g = G[o];
+      const float g = g16 ? __bfloat162float(G16[r * sg.ld_g + c]) : G[r * sg.ld_g + c];
       const float m = M[o] + (g - M[o]) * omb1;
       const float v = beta2 * V[o] + omb2 * g * g;
       const float pnew = P[o] - step_size * m / (sqrtf(v) / bc2_sqrt + eps);
@@ -1041,17 +1101,45 @@ int dlsg_multi_convert(const dlsg_seg_t* segs_dev, const int32_t* chunks_dev, in
   return check_launch("multi_convert_kernel");
 }
 
+int dlsg_multi_convert_host(const dlsg_seg_t* segs_host, int32_t nsegs, int32_t chunk_elems, void* stream) {
+  if (nsegs <= 0) return 0;
+  DLSG_REQUIRE(segs_host && chunk_elems > 0, "multi_convert_host: bad arguments");
+  static thread_local ConvArgs args;
+  for (int s0 = 0; s0 < nsegs; s0 += CONV_MAX_SEGS) {
+    const int n = nsegs - s0 < CONV_MAX_SEGS ? nsegs - s0 : CONV_MAX_SEGS;
+    int64_t chunks = 0;
+    for (int i = 0; i < n; ++i) {
+      const dlsg_seg_t& sg = segs_host[s0 + i];
+      DLSG_REQUIRE(sg.rows > 0 && sg.cols > 0 && sg.src && sg.dst, "multi_convert_host: empty segment %d", s0 + i);
+      DLSG_REQUIRE(sg.src_dtype == DLSG_F32 || (sg.src_dtype == DLSG_BF16 && !sg.src2), "multi_convert_host: source dtype of segment %d", s0 + i);
+      int64_t per = chunk_elems / sg.cols;
+      if (per < 1) per = 1;
+      args.seg[i] = sg;
+      args.chunk_start[i] = (int32_t)chunks;
+      args.rows_per_chunk[i] = (int32_t)per;
+      chunks += (sg.rows + per - 1) / per;
+    }
+    args.chunk_start[n] = (int32_t)chunks;
+    args.nsegs = n;
+    DLSG_REQUIRE(chunks < (1ll << 31), "multi_convert_host: too many chunks");
+    DLSG_LAUNCH(multi_convert_args_kernel, (unsigned)chunks, 256, 0, (cudaStream_t)stream, args);
+    if (int rc = check_launch("multi_convert_args_kernel")) return rc;
+  }
+  return 0;
+}
+
 int dlsg_adam_multi(const dlsg_adam_seg_t* segs_host, int32_t nsegs, int32_t chunk_elems, const float* step_dev,
                     const float* lr_dev, float lr, float beta1, float beta2, float eps, void* stream) {
   if (nsegs <= 0) return 0;
   DLSG_REQUIRE(segs_host && step_dev && chunk_elems > 0, "adam_multi: bad arguments");
-  static thread_local AdamArgs args;                                   // 25 KB: filled per launch, copied into the launch by value
+  static thread_local AdamArgs args;                                   // 24.6 KB: filled per launch, copied into the launch by value
   for (int s0 = 0; s0 < nsegs; s0 += ADAM_MAX_SEGS) {
     const int n = nsegs - s0 < ADAM_MAX_SEGS ? nsegs - s0 : ADAM_MAX_SEGS;
     int64_t chunks = 0;
     for (int i = 0; i < n; ++i) {
       const dlsg_adam_seg_t& sg = segs_host[s0 + i];
       DLSG_REQUIRE(sg.rows > 0 && sg.cols > 0 && sg.p && sg.g && sg.m && sg.v, "adam_multi: empty segment %d", s0 + i);
+      DLSG_REQUIRE(sg.g_dtype == DLSG_F32 || sg.g_dtype == DLSG_BF16, "adam_multi: gradient dtype of segment %d", s0 + i);
       int64_t per = chunk_elems / sg.cols;
       if (per < 1) per = 1;
       args.seg[i] = sg;

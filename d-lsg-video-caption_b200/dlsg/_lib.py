@@ -60,7 +60,8 @@ class CellBwdT(C.Structure):
 
 
 class AdamSegT(C.Structure):
-    _fields_ = [('p', vp), ('g', vp), ('m', vp), ('v', vp), ('dst16', vp), ('rows', i64), ('cols', i64), ('ld', i64), ('ld_dst', i64)]
+    _fields_ = [('p', vp), ('g', vp), ('m', vp), ('v', vp), ('dst16', vp), ('rows', i64), ('cols', i64), ('ld', i64), ('ld_dst', i64),
+                ('ld_g', i64), ('g_dtype', i32), ('_pad', i32)]
 
 
 class NormBwd2T(C.Structure):
@@ -142,6 +143,7 @@ SIGNATURES = {
     'dlsg_convert2d': (i32, [vp, i32, i64, vp, i32, i64, vp, i64, i64, i64, vp]),
     'dlsg_convert2d_batched': (i32, [vp, i32, i64, vp, i32, i64, vp, i64, i64, i64, i64, i64, i64, i64, vp]),
     'dlsg_multi_convert': (i32, [vp, vp, i32, vp]),
+    'dlsg_multi_convert_host': (i32, [vp, i32, i32, vp]),
     'dlsg_adam_multi': (i32, [vp, i32, i32, vp, vp, f32, f32, f32, f32, vp]),
     'dlsg_colsum': (i32, [vp, i32, i64, i64, i64, vp, vp]),
     'dlsg_norm_fwd': (i32, [C.POINTER(NormFwdT), vp]),

@@ -40,6 +40,7 @@ class _BlockFn(torch.autograd.Function):
         ctx.wc_scope = WC.begin_train_block() if getattr(block, 'need_grad', False) else WC.eval_scope()
         outs, saved = block.forward(t)
         ctx.block, ctx.saved, ctx.names = block, saved, names
+        ctx.pids = {n: id(x) for n, x in zip(names, tensors) if isinstance(x, torch.nn.Parameter)}
         if isinstance(block, TunBlock):
             # an encoder of the pair whose output nobody uses (CapBaselineModel drops the object nodes, model.py:86-88) must see
             # None, not a zero tensor, so that its parameters end with grad None exactly as under the reference's autograd
@@ -55,6 +56,8 @@ class _BlockFn(torch.autograd.Function):
         if BLOCK_BWD_HOOK is not None:
             BLOCK_BWD_HOOK(ctx.block)         # (every AccumulateGrad of the blocks that ran before this one has fired)
         WC.set_scope(ctx.wc_scope)
+        if GRAD_SYNC is not None:
+            GRAD_SYNC.pids = ctx.pids
         la.begin_pool(gouts[0].device if gouts[0] is not None else next(g for g in gouts if g is not None).device)
         try:
             grads = ctx.block.backward(ctx.saved, gouts)
@@ -62,7 +65,8 @@ class _BlockFn(torch.autograd.Function):
             la.end_pool()
         ctx.saved = None
         if GRAD_SYNC is not None:
-            grads = GRAD_SYNC.reduce(grads)
+            GRAD_SYNC.reduce(grads)
+            GRAD_SYNC.skip.clear()
         return (None, None) + tuple(grads.get(n) for n in ctx.names)
 
 
@@ -72,46 +76,140 @@ BLOCK_BWD_HOOK = None       # callable(block) invoked at the start of every bloc
 
 
 class GradSync:
-    """Data-parallel gradient averaging, one flat fp32 bucket per block, launched on a side stream the moment the
-    block's backward has produced its parameter gradients: the decoder bucket (~76 M params) is reduced over
-    NCCL/NVLink while the encoder backward is still computing; only the last (smallest) bucket is exposed.
-    Same arithmetic as DistributedDataParallel's bucketed all-reduce (run_gun.py:63-72): SUM over ranks / world."""
+    """Data-parallel gradient averaging for a captured (or eager) step; the only collective of the path (run_gun.py:63-72).
 
-    def __init__(self, process_group=None):
+    Every reduce() call (one per block backward, plus the early ones in the middle of a block) owns a PERSISTENT flat
+    bucket: ONE multi-segment launch (dlsg_multi_convert) packs that call's parameter gradients into it - cast to bf16 by
+    default, so the bytes on NVLink and the bytes Adam reads are halved - and the all-reduce (AVG = SUM / world, the same
+    arithmetic as DistributedDataParallel) runs on ONE side stream, in the same order on every rank, the moment the
+    gradients exist: the decoder bucket travels while the encoder backward computes; only the last bucket is exposed.
+    No torch.cat, no per-step allocation, no unpacking: `reduced[id(param)]` is a view of the bucket in the parameter's
+    shape and dlsg_adam_multi reads it in place (AdamDriver.step(grad_of=...)).  p.grad keeps the LOCAL gradient.
+
+    dtype: torch.bfloat16 (default; DLSG_GRAD_REDUCE=fp32 selects torch.float32 buckets)."""
+
+    def __init__(self, process_group=None, dtype=None):
+        import os
         import torch.distributed as dist
         self.dist, self.pg = dist, process_group
-        self.side = torch.cuda.Stream()
-        self.skip = set()           # ids of gradient views that early_sync() already reduced in the running block backward
+        if dtype is None:
+            dtype = torch.float32 if os.environ.get('DLSG_GRAD_REDUCE', 'bf16') == 'fp32' else torch.bfloat16
+        self.dtype = dtype
+        self.side = torch.cuda.Stream() if torch.cuda.is_available() else None
+        self.skip = set()           # ids of gradient tensors that early_sync() already reduced in the running block backward
+        self.pids = {}              # name -> id(parameter) of the block whose backward is running (set by _BlockFn.backward)
+        self.reduced = {}           # id(parameter) -> bucket view (parameter shape, self.dtype) holding the averaged gradient
+        self._buckets = {}          # call signature -> flat bucket
+        self._plans = []            # pack plans of the current step (kept alive for graph replays)
+        self.bytes = 0              # bytes all-reduced in the last step
+
+    def begin_step(self):
+        self.reduced.clear()
+        self.skip.clear()
+        self._plans = []
+        self.bytes = 0
 
     def reduce(self, grads):
         items = [(k, v) for k, v in grads.items() if v is not None and k not in BLOCK_INPUTS and id(v) not in self.skip]
         if not items:
-            return grads
+            return
         uniq = {}
         for k, v in items:
             uniq.setdefault(id(v), v)
-        tensors = list(uniq.values())
-        cur = torch.cuda.current_stream()
-        self.side.wait_stream(cur)
-        with torch.cuda.stream(self.side):
-            # the bucket copy runs on the side stream too: the main stream goes straight on with the next block
-            for x in tensors:
-                x.record_stream(self.side)
-            flat = torch.cat([x.reshape(-1) for x in tensors])
-            self.dist.all_reduce(flat, op=self.dist.ReduceOp.AVG, group=self.pg)
-        flat.record_stream(cur)
-        out, off, views = dict(grads), 0, {}
+        tensors = [x if x.is_contiguous() else x.contiguous() for x in uniq.values()]
+        sig = tuple((k, tuple(v.shape)) for k, v in items)
+        offs, n = [], 0
         for x in tensors:
-            n = x.numel()
-            views[id(x)] = flat[off:off + n].view(x.shape)
-            off += n
+            offs.append(n)
+            n += (x.numel() + 7) // 8 * 8                      # 16-byte aligned slices (vector loads in pack and Adam)
+        flat = self._buckets.get(sig)
+        if flat is None or flat.device != tensors[0].device:
+            flat = self._buckets[sig] = torch.zeros(n, dtype=self.dtype, device=tensors[0].device)
+        views = {}
+        pairs = []
+        for key, x, off in zip(uniq.keys(), tensors, offs):
+            v = flat[off:off + x.numel()].view(x.shape)
+            views[key] = v
+            pairs.append((x.reshape(1, -1) if x.dim() != 2 else x, None, v.reshape(1, -1) if x.dim() != 2 else v))
+        be = ops.backend()
+        plan = be.make_convert_plan(pairs, host=True)
+        self._plans.append(plan)
+        if self.side is not None:
+            cur = torch.cuda.current_stream()
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                for x in tensors:
+                    x.record_stream(self.side)
+                be.multi_convert(plan)
+                self.dist.all_reduce(flat, op=self.dist.ReduceOp.AVG, group=self.pg)
+        else:                                                   # gloo on CPU (tests): no AVG, no streams
+            be.multi_convert(plan)
+            self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.pg)
+            flat.div_(self.dist.get_world_size(self.pg))
+        self.bytes += flat.numel() * flat.element_size()
         for k, v in items:
-            out[k] = views[id(v)]
-        return out
+            pid = self.pids.get(k)
+            if pid is not None:
+                self.reduced[pid] = views[id(v)]
+            self.skip.add(id(v))
 
     def wait(self):
-        torch.cuda.current_stream().wait_stream(self.side)
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
         self.skip.clear()
+
+    def grad_of(self, p):
+        """Averaged gradient of parameter p (bucket view) - what the optimizer consumes."""
+        return self.reduced.get(id(p))
+
+    def reduce_params(self, params):
+        """Average p.grad of `params` across the ranks in place, on the CURRENT stream (the critic's gradients,
+        run_gun.py:71-72: pack -> all-reduce -> unpack, three launches, one persistent bucket)."""
+        ps = [p for p in params if p.grad is not None]
+        if not ps:
+            return
+        sig = ('params',) + tuple((id(p), tuple(p.shape)) for p in ps)
+        offs, n = [], 0
+        for p in ps:
+            offs.append(n)
+            n += (p.numel() + 7) // 8 * 8
+        flat = self._buckets.get(sig)
+        if flat is None:
+            flat = self._buckets[sig] = torch.zeros(n, dtype=self.dtype, device=ps[0].device)
+        two = lambda x: x.reshape(1, -1) if x.dim() != 2 else x
+        fwd, back = [], []
+        for p, off in zip(ps, offs):
+            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+            if g is not p.grad:
+                p.grad = g
+            v = flat[off:off + p.numel()].view(p.shape)
+            fwd.append((two(g), None, two(v)))
+            back.append((two(v), None, two(g)))
+        be = ops.backend()
+        plan_f, plan_b = be.make_convert_plan(fwd, host=True), be.make_convert_plan(back, host=True)
+        self._plans += [plan_f, plan_b]
+        be.multi_convert(plan_f)
+        if flat.is_cuda:
+            self.dist.all_reduce(flat, op=self.dist.ReduceOp.AVG, group=self.pg)
+        else:
+            self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.pg)
+            flat.div_(self.dist.get_world_size(self.pg))
+        be.multi_convert(plan_b)
+        self.bytes += flat.numel() * flat.element_size()
+
+    def write_back(self, params):
+        """p.grad <- averaged gradient (fp32), for callers that hand the gradients to a foreign optimizer or inspect them
+        (tests): one multi-segment launch on the current stream.  Call after wait()."""
+        pairs = []
+        for p in params:
+            r = self.reduced.get(id(p))
+            if r is not None and p.grad is not None:
+                pairs.append((r.reshape(1, -1) if r.dim() != 2 else r, None, p.grad.reshape(1, -1) if p.grad.dim() != 2 else p.grad))
+        if pairs:
+            be = ops.backend()
+            plan = be.make_convert_plan(pairs, host=True)
+            self._plans.append(plan)
+            be.multi_convert(plan)
 
 
 def early_sync(grads, keys=None):
@@ -120,12 +218,7 @@ def early_sync(grads, keys=None):
     gradients travel during its 26-step BPTT, the EncoderVisual attention gradients during the BiLSTM BPTT)."""
     if GRAD_SYNC is None:
         return
-    sub = grads if keys is None else {k: grads[k] for k in keys if k in grads}
-    red = GRAD_SYNC.reduce(sub)
-    for k, v in red.items():
-        if k not in BLOCK_INPUTS and v is not None:
-            GRAD_SYNC.skip.add(id(v))
-    grads.update(red)
+    GRAD_SYNC.reduce(grads if keys is None else {k: grads[k] for k in keys if k in grads})
 
 
 def run_block(block, tensors):

@@ -34,6 +34,7 @@ class GanIteration:
             self.dist = dist
             self.world = dist.get_world_size(process_group)
             self.sync = DF.GradSync(process_group)
+            self.sync_d = DF.GradSync(process_group)
         self.d_params = [p for p in D.parameters() if p.requires_grad]
         self.graph = None
         self.out = None
@@ -86,14 +87,7 @@ class GanIteration:
             loss_d = f_loss - r_loss + 10 * gp
             loss_d.backward()
             if self.world > 1:
-                flat = torch.cat([p.grad.reshape(-1) for p in self.d_params if p.grad is not None])
-                self.dist.all_reduce(flat, op=self.dist.ReduceOp.AVG, group=self.pg)
-                off = 0
-                for p in self.d_params:
-                    if p.grad is not None:
-                        n = p.grad.numel()
-                        p.grad.copy_(flat[off:off + n].view_as(p.grad))
-                        off += n
+                self.sync_d.reduce_params(self.d_params)
             self.opt_d.step()
             la.new_param_epoch()                      # critic weights changed: refresh their bf16 copies on next use
             wass = (r_loss - f_loss).detach()
@@ -125,6 +119,7 @@ class GanIteration:
         loss_g = -f_logit.mean()
         total = cap_loss + loss_g * self.lam
         if self.world > 1:
+            self.sync.begin_step()
             DF.GRAD_SYNC = self.sync
         try:
             total.backward()
@@ -132,6 +127,7 @@ class GanIteration:
             DF.GRAD_SYNC = None
         if self.world > 1:
             self.sync.wait()
+            self.sync.write_back([p for p in G.parameters() if p.grad is not None])
         self.opt_g.step()
         return cap_loss.detach(), loss_g.detach(), loss_d, wass
 

@@ -67,6 +67,13 @@ class GraphedTrainStep:
         self._adam_plans = list(self.adam._plans) if self.adam is not None else None     # (keeps the tensors the captured launches point at alive)
         torch.cuda.synchronize()
 
+    def _side(self):
+        """Stream of the overlapped decoder update: our own side stream, or - with several ranks - the gradient-sync stream
+        (the update is queued right behind the decoder bucket's all-reduce)."""
+        if self.world > 1 and self.sync.side is not None:
+            return self.sync.side
+        return self.side
+
     def _record_weight_copies(self):
         """One dry forward (nothing is updated; the host RNG / dropout seed counter are restored) that logs every weight
         conversion of a training forward, so the captured step refreshes ALL bf16 operand copies with ONE multi-segment
@@ -85,6 +92,10 @@ class GraphedTrainStep:
 
     def _body(self):
         self.opt.zero_grad(set_to_none=True)
+        grad_of = None
+        if self.world > 1:
+            self.sync.begin_step()
+            grad_of = self.sync.grad_of           # Adam reads the averaged gradients in place from the reduced buckets
         if self.pinned is not None:
             if self.adam is None:
                 self.pinned.refresh()             # current fp32 masters -> every operand copy, one launch
@@ -95,14 +106,14 @@ class GraphedTrainStep:
             # starts its backward: every decoder gradient is final by then, and the bandwidth-bound update hides behind
             # the latency-bound encoder backward.  With several ranks the side stream is the gradient-sync stream: the
             # update is queued right behind the decoder bucket's all-reduce (p.grad are views of the reduced bucket).
-            side = self.side if self.world == 1 else self.sync.side
+            side = self._side()
 
             def hook(block):
                 if not done and type(block).__name__ != 'DecoderTrainBlock':
                     ps = [p for p in self.dec_params if p.grad is not None]
                     side.wait_stream(torch.cuda.current_stream())
                     with torch.cuda.stream(side):
-                        self.adam.step(ps)
+                        self.adam.step(ps, grad_of)
                     done.extend(ps)
             DF.BLOCK_BWD_HOOK = hook
         try:
@@ -121,12 +132,14 @@ class GraphedTrainStep:
         if self.world > 1:
             self.sync.wait()
         if self.adam is None:
+            if self.world > 1:
+                self.sync.write_back(self.params)     # a foreign optimizer reads p.grad
             self.opt.step()
         else:
             seen = set(id(p) for p in done)
-            self.adam.step([p for p in self.params if p.grad is not None and id(p) not in seen])
+            self.adam.step([p for p in self.params if p.grad is not None and id(p) not in seen], grad_of)
             if done:
-                torch.cuda.current_stream().wait_stream(self.side if self.world == 1 else self.sync.side)
+                torch.cuda.current_stream().wait_stream(self._side())
             self.adam.refresh_residual()          # the few copies Adam cannot emit itself (summed bias pairs)
         return loss.detach()
 

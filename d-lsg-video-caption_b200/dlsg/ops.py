@@ -151,15 +151,17 @@ class CudaBackend:
             _ptr(t2), t2.stride(0) if t2 is not None else 0, rows, cols, batch, bs[0], bs[1], bs[2], _stream()),
             'dlsg_convert2d')
 
-    def make_convert_plan(self, pairs, chunk_elems=16384):
-        """pairs: list of (src, src2 | None, dst) 2-D tensor views (fp32 sources with one common pitch per pair, unit
-        inner strides).  Returns a plan (device tables + references that keep the buffers alive) for multi_convert()."""
+    def make_convert_plan(self, pairs, chunk_elems=16384, host=False):
+        """pairs: list of (src, src2 | None, dst) 2-D tensor views (fp32 sources with one common pitch per pair, or a bf16
+        source without src2; unit inner strides).  Returns a plan (tables + references that keep the buffers alive) for
+        multi_convert().  host=False: device-resident tables (uploaded here: not inside a graph capture); host=True: the
+        table stays on the host and rides in the kernel parameters of every launch (capturable with fresh pointers)."""
         import numpy as np
         segs = (L.SegT * max(1, len(pairs)))()
         chunks = []
         keep = []
         for i, (src, src2, dst) in enumerate(pairs):
-            assert src.dim() == 2 and dst.shape == src.shape and src.dtype == torch.float32, (src.shape, dst.shape, src.dtype)
+            assert src.dim() == 2 and dst.shape == src.shape and (src.dtype == torch.float32 or src2 is None), (src.shape, dst.shape, src.dtype)
             assert (src.stride(1) == 1 or src.shape[1] == 1) and (dst.stride(1) == 1 or dst.shape[1] == 1)
             rows, cols = src.shape
             sg = segs[i]
@@ -169,10 +171,14 @@ class CudaBackend:
             if src2 is not None:
                 assert src2.shape == src.shape and src2.dtype == torch.float32 and (rows == 1 or src2.stride(0) == src.stride(0))
                 sg.src2 = src2.data_ptr()
+            keep.append((src, src2, dst))
+            if host:
+                continue
             per = max(1, chunk_elems // max(1, cols))
             for r0 in range(0, rows, per):
                 chunks.append((i, r0, min(per, rows - r0)))
-            keep.append((src, src2, dst))
+        if host:
+            return {'table': segs, 'n': len(pairs), 'chunk_elems': chunk_elems, 'keep': keep, 'host': True}
         dev = pairs[0][0].device
         seg_t = torch.from_numpy(np.frombuffer(bytes(segs), dtype=np.uint8).copy()).to(dev)
         chunk_t = torch.tensor(chunks, dtype=torch.int32).reshape(-1).to(dev)
@@ -181,24 +187,32 @@ class CudaBackend:
     def multi_convert(self, plan):
         if plan['n'] == 0:
             return
+        if plan.get('host'):
+            self.launches += (plan['n'] + 383) // 384
+            L.check(self.lib.dlsg_multi_convert_host(C.cast(plan['table'], C.c_void_p), plan['n'], plan['chunk_elems'], _stream()),
+                    'dlsg_multi_convert_host')
+            return
         self.launches += 1
         L.check(self.lib.dlsg_multi_convert(plan['segs'].data_ptr(), plan['chunks'].data_ptr(), plan['n'], _stream()),
                 'dlsg_multi_convert')
 
     def make_adam_plan(self, segs, chunk_elems=16384):
-        """segs: list of dicts {p, g, m, v: 2-D fp32 views with one common pitch, dst: bf16 2-D view | None}.  The plan is a
+        """segs: list of dicts {p, m, v: 2-D fp32 views with one common pitch, g: fp32 | bf16 view of the same shape (own
+        pitch), dst: bf16 2-D view | None}.  The plan is a
         host table: it rides to the device inside the kernel parameters (no upload; graph-capturable as is)."""
         table = (L.AdamSegT * max(1, len(segs)))()
         for i, sg in enumerate(segs):
             p_, g_, m_, v_, d_ = sg['p'], sg['g'], sg['m'], sg['v'], sg.get('dst')
             rows, cols = p_.shape
             ld = p_.stride(0) if rows > 1 else cols
-            for t_ in (p_, g_, m_, v_):
+            for t_ in (p_, m_, v_):
                 assert t_.dtype == torch.float32 and t_.shape == p_.shape and (cols == 1 or t_.stride(1) == 1)
-                assert rows == 1 or t_.stride(0) == ld, 'p, g, m, v of a segment must share one pitch'
+                assert rows == 1 or t_.stride(0) == ld, 'p, m, v of a segment must share one pitch'
+            assert g_.shape == p_.shape and (cols == 1 or g_.stride(1) == 1), 'gradient view must match the parameter segment'
             e = table[i]
             e.p, e.g, e.m, e.v = p_.data_ptr(), g_.data_ptr(), m_.data_ptr(), v_.data_ptr()
             e.rows, e.cols, e.ld = rows, cols, ld
+            e.ld_g, e.g_dtype = (g_.stride(0) if rows > 1 else cols), _dt(g_)
             if d_ is not None:
                 assert d_.dtype == torch.bfloat16 and d_.shape == p_.shape and (cols == 1 or d_.stride(1) == 1)
                 e.dst16, e.ld_dst = d_.data_ptr(), (d_.stride(0) if rows > 1 else cols)
@@ -208,7 +222,7 @@ class CudaBackend:
         if plan['n'] == 0:
             return
         assert step.dtype == torch.float32
-        self.launches += (plan['n'] + 319) // 320
+        self.launches += (plan['n'] + 255) // 256
         L.check(self.lib.dlsg_adam_multi(C.cast(plan['table'], C.c_void_p), plan['n'], plan['chunk_elems'], step.data_ptr(),
                                          _ptr(lr_dev), float(lr), float(beta1), float(beta2), float(eps), _stream()), 'dlsg_adam_multi')
 

@@ -87,9 +87,11 @@ class AdamDriver:
                 rest.extend(s_[5] for s_ in segs)
         self.residual = ops.backend().make_convert_plan(rest) if rest else None
 
-    def step(self, params):
+    def step(self, params, grad_of=None):
         """Update `params` (those with a gradient) with ONE kernel launch per (param group) + one step-counter increment.
-        Must run after their gradients are final; capturable (tables go through pinned staging)."""
+        Must run after their gradients are final; capturable (the segment table rides in the kernel parameters).
+        grad_of: callable(param) -> gradient tensor in the parameter's shape (fp32 or bf16, e.g. GradSync.grad_of: the
+        all-reduced bucket view is read in place); default p.grad."""
         be = ops.backend()
         by_group = {}
         for p in params:
@@ -101,7 +103,10 @@ class AdamDriver:
             for p in ps:
                 st = _ensure_state(self.opt, p)
                 steps.append(st['step'])
-                grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                grad = p.grad if grad_of is None else grad_of(p)
+                if grad is None:
+                    raise RuntimeError('AdamDriver: no reduced gradient for a parameter of shape %s' % (tuple(p.shape),))
+                grad = grad if grad.is_contiguous() else grad.contiguous()
                 m, v = st['exp_avg'], st['exp_avg_sq']
                 sh = self.shadow.get(id(p))
                 if sh is None:

@@ -74,23 +74,29 @@ int dlsg_convert2d_batched(const void* src, int src_dtype, int64_t ld_src, void*
                            int64_t bs_src, int64_t bs_dst, int64_t bs_dstT, void* stream);
 /* One launch for MANY conversions (all GEMM-operand copies of the parameters after an optimizer step):
  * a DEVICE-resident table of segments dst[r,c] = cast(src[r,c] (+ src2[r,c])), fp32 sources (src2 optional, same
- * pitch), bf16 / fp32 destination with its own pitch, and a DEVICE table of int32 triples (segment, first row, rows),
+ * pitch) or bf16 sources (no src2: a reduced gradient bucket read back), bf16 / fp32 destination with its own pitch, and a DEVICE table of int32 triples (segment, first row, rows),
  * one CTA per triple.                                                                              */
 typedef struct {
   const void* src; const void* src2; void* dst;
   int64_t rows, cols, ld_src, ld_dst;
-  int32_t src_dtype, dst_dtype;               /* src_dtype must be DLSG_F32 */
+  int32_t src_dtype, dst_dtype;               /* a DLSG_BF16 source takes no src2 */
 } dlsg_seg_t;
 int dlsg_multi_convert(const dlsg_seg_t* segs_dev, const int32_t* chunks_dev, int32_t nchunks, void* stream);
+/* Same conversions from a HOST table that travels inside the kernel parameters (up to 384 segments per launch, one CTA per
+ * ~chunk_elems elements): no table upload, so it may be issued with fresh pointers during a CUDA-graph capture (the
+ * per-block gradient packs of the data-parallel step).                                              */
+int dlsg_multi_convert_host(const dlsg_seg_t* segs_host, int32_t nsegs, int32_t chunk_elems, void* stream);
 /* Multi-tensor Adam (torch.optim.Adam semantics, no weight decay / amsgrad / maximize; run_gun.py:91,100) over a table of
- * 2-D segments (p, g, m, v fp32 with one common pitch; dst16 = optional bf16 GEMM-operand copy of the updated values with
- * its own pitch).  The table is a HOST array: it travels to the device inside the kernel's parameters (up to 320 segments
+ * 2-D segments (p, m, v fp32 with one common pitch; g fp32 or bf16 with its own pitch - the all-reduced gradient bucket of
+ * a data-parallel step is read in place; dst16 = optional bf16 GEMM-operand copy of the updated values with its own pitch).  The table is a HOST array: it travels to the device inside the kernel's parameters (up to 256 segments
  * per launch, one CTA per ~chunk_elems elements), so a CUDA graph keeps it in the kernel node and no table upload exists.
  * `step_dev` holds the (already incremented) step count t as a float; the learning rate is *lr_dev when lr_dev != NULL (so
  * a captured graph follows a scheduler), else lr.  SURVEY 8f-3: the optimizer pass emits the bf16 weights.               */
 typedef struct {
-  float* p; const float* g; float* m; float* v; void* dst16;
+  float* p; const void* g; float* m; float* v; void* dst16;
   int64_t rows, cols, ld, ld_dst;
+  int64_t ld_g;                               /* pitch of g (its own: a slice of a flat gradient bucket)            */
+  int32_t g_dtype, _pad;                      /* DLSG_F32 | DLSG_BF16: data-parallel buckets are reduced in bf16    */
 } dlsg_adam_seg_t;
 int dlsg_adam_multi(const dlsg_adam_seg_t* segs_host, int32_t nsegs, int32_t chunk_elems, const float* step_dev,
                     const float* lr_dev, float lr, float beta1, float beta2, float eps, void* stream);

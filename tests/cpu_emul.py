@@ -51,7 +51,7 @@ class CpuEmulBackend:
         if dstT is not None:
             dstT.copy_(src.transpose(-1, -2))
 
-    def make_convert_plan(self, pairs, chunk_elems=16384):
+    def make_convert_plan(self, pairs, chunk_elems=16384, host=False):
         return {'pairs': list(pairs), 'n': len(pairs)}
 
     def multi_convert(self, plan):
@@ -69,6 +69,7 @@ class CpuEmulBackend:
         bc1, bc2 = 1.0 - beta1 ** t, 1.0 - beta2 ** t
         for sg in plan['segs']:
             p_, g_, m_, v_ = sg['p'], sg['g'], sg['m'], sg['v']
+            g_ = g_.float()
             m_.copy_(m_ + (g_ - m_) * (1 - beta1))
             v_.copy_(beta2 * v_ + (1 - beta2) * g_ * g_)
             p_.sub_((lr / bc1) * m_ / (v_.sqrt() / (bc2 ** 0.5) + eps))

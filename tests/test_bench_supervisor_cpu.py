@@ -27,10 +27,20 @@ def test_first_tier_wins_when_it_finishes():
 def test_stalled_tiers_fall_through_to_the_conservative_one():
     rc, lines, err = _run('0,1')
     assert rc == 0 and len(lines) == 1, err
-    assert lines[0]['nvls'] == '0' and lines[0]['argv'][-2:] == ['--graph', '0'] and lines[0]['port'] == str(29611 + 34)
+    assert lines[0]['nvls'] == '0' and lines[0]['argv'][-3:] == ['--graph', '0', '--no-gan'] and lines[0]['port'] == str(29611 + 34)
     assert 'tier 0 timed out' in err and 'tier 1 timed out' in err
 
 
 def test_all_tiers_stalled_reports_an_error_line():
     rc, lines, _ = _run('0,1,2', secs='5,5,5')
     assert rc == 3 and len(lines) == 1 and lines[0]['value'] is None and 'error' in lines[0]
+
+
+def test_crashed_tier_falls_through_at_once():
+    """A child that exits non-zero (a Python error) must not cost its whole wall-clock window (round 1: 290 s x 8 GPUs)."""
+    import time
+    t0 = time.time()
+    rc, lines, err = _run('x0', secs='120,120,120')
+    assert rc == 0 and len(lines) == 1, err
+    assert lines[0]['nvls'] == '0' and 'tier 0 exited with 7' in err
+    assert time.time() - t0 < 60

@@ -14,36 +14,6 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-class _CpuSync:
-    """GradSync with the CUDA-stream plumbing removed (gloo runs synchronously on CPU)."""
-
-    def __init__(self):
-        from dlsg import functional as DF
-        self.inputs = DF.BLOCK_INPUTS
-        self.skip = set()           # filled by DF.early_sync (mid-backward reductions of already-final gradients)
-        self.calls = 0
-
-    def reduce(self, grads):
-        self.calls += 1
-        items = [(k, v) for k, v in grads.items() if v is not None and k not in self.inputs and id(v) not in self.skip]
-        if not items:
-            return grads
-        uniq = {}
-        for k, v in items:
-            uniq.setdefault(id(v), v)
-        tensors = list(uniq.values())
-        flat = torch.cat([x.reshape(-1) for x in tensors])
-        dist.all_reduce(flat)
-        flat /= dist.get_world_size()
-        out, off, views = dict(grads), 0, {}
-        for x in tensors:
-            views[id(x)] = flat[off:off + x.numel()].view(x.shape)
-            off += x.numel()
-        for k, v in items:
-            out[k] = views[id(v)]
-        return out
-
-
 def _worker(rank, world, port, q):
     for p in (os.path.join(ROOT, 'd-lsg-video-caption_b200'), ROOT, os.path.join(ROOT, 'tests')):
         if p not in sys.path:
@@ -64,11 +34,27 @@ def _worker(rank, world, port, q):
     synth.fill_state_dict(net)
     net.eval()
     frames, regions, caps, lens = synth.make_inputs(B, args, V, seed=200 + rank)
-    out = net(frames, regions, caps, args.max_words, 1.0)[0]
-    DF.GRAD_SYNC = _CpuSync()
-    O.packed_ce_loss(out, caps, lens).backward()
-    assert DF.GRAD_SYNC.calls >= 5, 'expected the early (mid-backward) reductions on top of one per block'
-    DF.GRAD_SYNC = None
+    params = [p for p in net.parameters()]
+    local = {}
+    worst16 = 0.0
+    for dtype in (torch.bfloat16, torch.float32):          # the product default (bf16 buckets) first, then exact fp32 buckets
+        net.zero_grad(set_to_none=True)
+        out = net(frames, regions, caps, args.max_words, 1.0)[0]
+        sync = DF.GradSync(None, dtype=dtype)               # the REAL GradSync: gloo + CPU tensors take its stream-less branch
+        sync.begin_step()
+        DF.GRAD_SYNC = sync
+        try:
+            O.packed_ce_loss(out, caps, lens).backward()
+        finally:
+            DF.GRAD_SYNC = None
+        sync.wait()
+        assert len(sync._plans) >= 5, 'expected the early (mid-backward) reductions on top of one per block'
+        for p_ in params:                                    # p.grad keeps the LOCAL gradient; every one has an averaged bucket view
+            assert (p_.grad is None) == (sync.grad_of(p_) is None)
+        if dtype == torch.bfloat16:
+            local = {id(p_): p_.grad.clone() for p_ in params if p_.grad is not None}
+            red16 = {id(p_): sync.grad_of(p_).float().clone() for p_ in params if p_.grad is not None}
+        sync.write_back(params)
     sd = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
     for r in range(world):
         f, g, c, l = synth.make_inputs(B, args, V, seed=200 + r)
@@ -81,7 +67,9 @@ def _worker(rank, world, port, q):
         ref = sd[k].grad
         if float((p.grad - ref).abs().max()) > 1e-7:
             worst = max(worst, float((p.grad - ref).norm() / (ref.norm() + 1e-12)))
-    q.put((rank, worst))
+        # bf16 buckets: one rounding of each rank's gradient + one of the sum (2^-9 relative each)
+        worst16 = max(worst16, float((red16[id(p)] - ref).norm() / (ref.norm() + 1e-12)))
+    q.put((rank, worst, worst16))
     dist.destroy_process_group()
 
 
@@ -97,5 +85,6 @@ def test_block_bucket_allreduce_world2():
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    for rank, worst in res:
+    for rank, worst, worst16 in res:
         assert worst < 1e-4, (rank, worst)
+        assert worst16 < 8e-3, (rank, worst16)
