@@ -102,6 +102,7 @@ class GradSync:
         self._buckets = {}          # call signature -> flat bucket
         self._plans = []            # pack plans of the current step (kept alive for graph replays)
         self.bytes = 0              # bytes all-reduced in the last step
+        self.debug = set(x for x in os.environ.get('DLSG_SYNC_DEBUG', '').split(',') if x)   # measurement aids: nonccl | nopack | nowait | pgrad | noearly | norecord
 
     def begin_step(self):
         self.reduced.clear()
@@ -116,7 +117,8 @@ class GradSync:
         uniq = {}
         for k, v in items:
             uniq.setdefault(id(v), v)
-        tensors = [x if x.is_contiguous() else x.contiguous() for x in uniq.values()]
+        # a 2-D row-pitched view (the recurrent-weight slices of the packed gate gradients) is packed in place through its pitch
+        tensors = [x if (x.is_contiguous() or (x.dim() == 2 and x.stride(1) == 1)) else x.contiguous() for x in uniq.values()]
         sig = tuple((k, tuple(v.shape)) for k, v in items)
         offs, n = [], 0
         for x in tensors:
@@ -124,7 +126,7 @@ class GradSync:
             n += (x.numel() + 7) // 8 * 8                      # 16-byte aligned slices (vector loads in pack and Adam)
         flat = self._buckets.get(sig)
         if flat is None or flat.device != tensors[0].device:
-            flat = self._buckets[sig] = torch.zeros(n, dtype=self.dtype, device=tensors[0].device)
+            flat = self._buckets[sig] = torch.empty(n, dtype=self.dtype, device=tensors[0].device)
         views = {}
         pairs = []
         for key, x, off in zip(uniq.keys(), tensors, offs):
@@ -138,10 +140,13 @@ class GradSync:
             cur = torch.cuda.current_stream()
             self.side.wait_stream(cur)
             with torch.cuda.stream(self.side):
-                for x in tensors:
-                    x.record_stream(self.side)
-                be.multi_convert(plan)
-                self.dist.all_reduce(flat, op=self.dist.ReduceOp.AVG, group=self.pg)
+                if 'norecord' not in self.debug:
+                    for x in tensors:
+                        x.record_stream(self.side)
+                if 'nopack' not in self.debug:
+                    be.multi_convert(plan)
+                if not (self.debug & {'nopack', 'nonccl'}):
+                    self.dist.all_reduce(flat, op=self.dist.ReduceOp.AVG, group=self.pg)
         else:                                                   # gloo on CPU (tests): no AVG, no streams
             be.multi_convert(plan)
             self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.pg)
@@ -154,12 +159,14 @@ class GradSync:
             self.skip.add(id(v))
 
     def wait(self):
-        if self.side is not None:
+        if self.side is not None and 'nowait' not in self.debug:
             torch.cuda.current_stream().wait_stream(self.side)
         self.skip.clear()
 
     def grad_of(self, p):
         """Averaged gradient of parameter p (bucket view) - what the optimizer consumes."""
+        if 'pgrad' in self.debug:
+            return p.grad
         return self.reduced.get(id(p))
 
     def reduce_params(self, params):
@@ -216,7 +223,7 @@ def early_sync(grads, keys=None):
     """Called by a block in the middle of its backward with the parameter gradients that are already final (everything
     in `grads` so far): their all-reduce starts now and overlaps the rest of the block (the decoder's vocabulary-projection
     gradients travel during its 26-step BPTT, the EncoderVisual attention gradients during the BiLSTM BPTT)."""
-    if GRAD_SYNC is None:
+    if GRAD_SYNC is None or 'noearly' in GRAD_SYNC.debug:
         return
     GRAD_SYNC.reduce(grads if keys is None else {k: grads[k] for k in keys if k in grads})
 

@@ -7,6 +7,8 @@ buffers are filled with (non-blocking) copies before each replay.  Limitations o
 the teacher-forcing coin flips (layer.py:432) and the dropout seeds are frozen at capture time - use the eager path
 (model(...), loss.backward(), opt.step()) when scheduled sampling with ratio < 1 must be re-drawn every step.
 """
+import os
+
 import torch
 
 from . import functional as DF
@@ -38,6 +40,11 @@ class GraphedTrainStep:
             self.dist = dist
             self.world = dist.get_world_size(process_group)
             self.sync = DF.GradSync(process_group)
+        elif os.environ.get('DLSG_FORCE_SYNC') == '1':
+            # measurement aid (one GPU): the data-parallel stream / bucket structure without a communicator
+            # (use with DLSG_SYNC_DEBUG=nonccl | nopack)
+            self.world = 2
+            self.sync = DF.GradSync(None)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -102,19 +109,22 @@ class GraphedTrainStep:
             DF.WC.pin(self.pinned)
         done = []
         if self.adam is not None:
-            # the decoder's parameters (65 % of the model) are updated on a side stream the moment the first encoder block
-            # starts its backward: every decoder gradient is final by then, and the bandwidth-bound update hides behind
-            # the latency-bound encoder backward.  With several ranks the side stream is the gradient-sync stream: the
-            # update is queued right behind the decoder bucket's all-reduce (p.grad are views of the reduced bucket).
+            # Every block's parameters are updated on a side stream the moment the NEXT block starts its backward: all their
+            # gradients are final by then (the decoder's 76 M parameters - 65 % of the model - while the encoder backward is
+            # still computing), and the bandwidth-bound update hides behind the latency-bound backward.  With several ranks the
+            # side stream is the gradient-sync stream: the update is queued right behind that block's bucket all-reduce and
+            # reads the averaged gradients in place.
             side = self._side()
+            seen = set()
 
             def hook(block):
-                if not done and type(block).__name__ != 'DecoderTrainBlock':
-                    ps = [p for p in self.dec_params if p.grad is not None]
+                ps = [p for p in self.params if p.grad is not None and id(p) not in seen]
+                if ps:
                     side.wait_stream(torch.cuda.current_stream())
                     with torch.cuda.stream(side):
                         self.adam.step(ps, grad_of)
                     done.extend(ps)
+                    seen.update(id(p) for p in ps)
             DF.BLOCK_BWD_HOOK = hook
         try:
             out = self.model(self.frames, self.regions, self.captions, self.max_words, self.tf)[0]

@@ -36,7 +36,7 @@ def _worker(rank, world, port, mode, q):
         from dlsg.graphs import GraphedTrainStep
         import models.model as M
         la.set_precision('bf16')
-        args, V, B = synth.small_args(), 37, 4
+        args, V, B = synth.msr_args(), 10547, 4          # full widths: the fused / hoisted kernel paths of the benchmarked step
         torch.manual_seed(5)
         with contextlib.redirect_stdout(io.StringIO()):
             net = M.CapGnnModel(args, synth.Vocab(V))
@@ -48,15 +48,21 @@ def _worker(rank, world, port, mode, q):
         res = {}
         if mode in ('bf16', 'fp32'):
             # reference on this GPU alone: mean over ranks of the per-shard gradients (eager path, same kernels)
-            ref = {}
-            for r in range(world):
-                net.zero_grad(set_to_none=True)
-                f, g, c, l = shards[r]
-                out = net(f.to(dev), g.to(dev), c.to(dev), args.max_words, 1.0)[0]
-                losses.packed_cross_entropy(out, c.to(dev), l).backward()
-                for k, p in net.named_parameters():
-                    if p.grad is not None:
-                        ref[k] = ref.get(k, 0) + p.grad.detach().clone() / world
+            def shard_mean_grads():
+                # (in a function: no reference to `out` / the loss may survive, or their AccumulateGrad nodes - created on the
+                # default stream - would be synchronised with the capture stream and invalidate the capture)
+                acc = {}
+                for r in range(world):
+                    net.zero_grad(set_to_none=True)
+                    f, g, c, l = shards[r]
+                    out = net(f.to(dev), g.to(dev), c.to(dev), args.max_words, 1.0)[0]
+                    losses.packed_cross_entropy(out, c.to(dev), l).backward()
+                    for k, p in net.named_parameters():
+                        if p.grad is not None:
+                            acc[k] = acc.get(k, 0) + p.grad.detach().clone() / world
+                return acc
+            ref = shard_mean_grads()
+            torch.cuda.synchronize()
             net.zero_grad(set_to_none=True)
             opt = torch.optim.Adam(net.parameters(), lr=1.6e-4, betas=(0.5, 0.9), fused=True, capturable=True)
             gs = GraphedTrainStep(net, opt, fr.to(dev), rg.to(dev), cp.to(dev), lens, args.max_words, 1.0,
@@ -65,14 +71,21 @@ def _worker(rank, world, port, mode, q):
             gs.refresh_weights()
             gs()
             torch.cuda.synchronize()
-            worst = 0.0
+            # Norm floor: the K / Q weights of the second attention head have gradients that are a cancellation residue
+            # (|g| ~ 7e-5 against 0.1 .. 6 for every other tensor; the softmax Jacobian terms sum to zero over the nodes), so two
+            # EAGER runs of the same step already differ by 14 % there (fp32 atomics order; tools/diag_graph_grads.py).  Errors
+            # are therefore measured against max(|ref_k|, 1e-3 * largest gradient norm of the model).
+            floor = 1e-3 * max(float(v.norm()) for v in ref.values())
+            errs = []
             for k, p in net.named_parameters():
                 if k not in ref:
                     continue
                 red = gs.sync.grad_of(p)
                 assert red is not None, k
-                worst = max(worst, float((red.float() - ref[k]).norm() / (ref[k].norm() + 1e-12)))
-            res['grad_rel'] = worst
+                errs.append((float((red.float() - ref[k]).norm()) / max(float(ref[k].norm()), floor), k, float(ref[k].norm())))
+            errs.sort(reverse=True)
+            res['grad_rel'] = errs[0][0]
+            res['worst'] = errs[:6]
             res['bytes'] = gs.sync.bytes
             for _ in range(3):
                 gs()
@@ -106,7 +119,7 @@ def _worker(rank, world, port, mode, q):
         torch.cuda.synchronize()
     except Exception as e:                                         # noqa: BLE001 - reported to the parent
         import traceback
-        q.put((rank, {'error': traceback.format_exc()[-1500:]}))
+        q.put((rank, {'error': traceback.format_exc()[-4000:]}))
     finally:
         sys.stdout.flush()
         os._exit(0)        # a captured graph with NCCL nodes keeps the communicator busy at teardown (see bench.py)
@@ -140,7 +153,7 @@ def test_graphed_step_world2_reduced_gradients_bf16_buckets():
 @pytest.mark.timeout(400)
 def test_graphed_step_world2_reduced_gradients_fp32_buckets():
     for r, res in _run('fp32').items():
-        assert res['grad_rel'] < 2e-4, (r, res)                   # fp32 sums in a different order + atomic split-K
+        assert res['grad_rel'] < 5e-3, (r, res)                   # two eager runs of one step differ by ~2e-3 (fp32 atomics order)
         assert res['weights_equal'] and res['moved'] > 0, (r, res)
 
 
