@@ -13,6 +13,7 @@ teacher-forcing coin flips (layer.py:432) and the dropout seeds are frozen at ca
 import torch
 
 from . import functional as DF
+from . import generic as GN
 from . import linalg as la
 from . import losses
 
@@ -39,6 +40,10 @@ class GanIteration:
         self.graph = None
         self.out = None
         if graph:
+            from . import graphs as GR
+            GR.check_capturable(opt_g)
+            GR.check_capturable(opt_d)
+            snap = GR.snapshot([G, D], [opt_g, opt_d]) if warmup > 0 else None
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
@@ -46,6 +51,11 @@ class GanIteration:
                     self._body()
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
+            if snap is not None:
+                GR.restore(snap)                  # warm-up iterations leave no trace in weights, Adam state or RNG streams
+                la.new_param_epoch()
+            GR.ensure_adam_state(opt_g, [p for p in G.parameters()])
+            GR.ensure_adam_state(opt_d, self.d_params)
             self.opt_g.zero_grad(set_to_none=True)
             self.opt_d.zero_grad(set_to_none=True)
             self.graph = torch.cuda.CUDAGraph()
@@ -62,26 +72,44 @@ class GanIteration:
 
     # ------------------------------------------------------------------ run_gun.py:339-383
     def _disc_steps(self, real, fake, obj, mot, att_mask, alpha):
-        D, B = self.D, real.shape[0]
-        loss_d = wass = torch.zeros((), device=real.device)
+        """real: (B,L,V) one-hot (literal form) or the (B,L) token ids (token form, batched=True)."""
+        D, B = self.D, fake.shape[0]
+        loss_d = wass = torch.zeros((), device=fake.device)
         if self.batched:
             obj3, mot3, mask3, alpha3 = obj.repeat(3, 1, 1), mot.repeat(3, 1, 1), att_mask.repeat(3, 1, 1), alpha.repeat(3, 1, 1)
         for _ in range(self.num_d):
             self.opt_d.zero_grad(set_to_none=True)
-            eps = torch.rand(B, 1, 1, device=real.device, requires_grad=True)
-            mixed = real * eps + fake * (1 - eps)
+            eps = torch.rand(B, 1, 1, device=fake.device, requires_grad=not self.batched)
             if self.batched:
-                # the three critic calls of the step as ONE stacked forward (per-group batch means inside DiscV2): a third
-                # of the launches of D(real), D(fake), D(mixed); the penalty differentiates the mixed rows only
-                logits = D(torch.cat([real, fake, mixed], 0), obj3, mot3, mask3, alpha3, _groups=3)
+                # Token form of the three critic calls (same function of the parameters, re-associated):
+                #  * D's first layer is linear, so the embedding of the ONE-HOT real caption is a column gather of its
+                #    weight (no (B,L,V) one-hot, no V-wide GEMM), and the embedding of the interpolate
+                #    eps * real + (1 - eps) * fake is the same mix of the two embeddings (the bias passes through: the
+                #    coefficients sum to 1) - only the fake logits pay the (B*L, V) x (V, 512) product;
+                #  * the penalty's gradient wrt the V-wide interpolate is g_tok @ W (W = that layer's (512,V) weight), so its
+                #    squared norm per sample is sum_t g_t (W W^T) g_t^T: a 512 x 512 Gram matrix once per critic step instead
+                #    of a (B*L, V) gradient and its double backward (SURVEY 7.3-5).
+                # One stacked D forward over [real | fake | mixed] tokens (per-group batch means inside DiscV2).
+                L = fake.shape[1]
+                W, bias = D.conv1d.weight[:, :, 0], D.conv1d.bias
+                tok_real = (GN.column_gather(W, real) + bias).view(B, L, -1)
+                tok_fake = GN.linear(fake, W, bias)
+                tok_mixed = tok_real * eps + tok_fake * (1 - eps)
+                logits = D(None, obj3, mot3, mask3, alpha3, _groups=3, _tokens=torch.cat([tok_real, tok_fake, tok_mixed], 0))
                 r_logit, f_logit, m_logit = logits[:B], logits[B:2 * B], logits[2 * B:]
+                g_tok = torch.autograd.grad(inputs=tok_mixed, outputs=m_logit, grad_outputs=torch.ones_like(m_logit),
+                                            create_graph=True, retain_graph=True)[0]
+                g2 = g_tok.reshape(B * L, -1)
+                gram = GN.bmm_nt(W, W)                                  # (512,512) = W W^T
+                gn = (GN.bmm_nt(g2, gram) * g2).view(B, -1).sum(1).sqrt()
             else:
+                mixed = real * eps + fake * (1 - eps)
                 r_logit = D(real, obj, mot, att_mask, alpha)
                 f_logit = D(fake, obj, mot, att_mask, alpha)
                 m_logit = D(mixed, obj, mot, att_mask, alpha)
-            g = torch.autograd.grad(inputs=mixed, outputs=m_logit, grad_outputs=torch.ones_like(m_logit),
-                                    create_graph=True, retain_graph=True)[0]
-            gn = g.contiguous().view(B, -1).norm(2, dim=1)
+                g = torch.autograd.grad(inputs=mixed, outputs=m_logit, grad_outputs=torch.ones_like(m_logit),
+                                        create_graph=True, retain_graph=True)[0]
+                gn = g.contiguous().view(B, -1).norm(2, dim=1)
             gp = ((gn - 1) * (gn - 1)).mean()
             r_loss, f_loss = r_logit.mean(), f_logit.mean()
             loss_d = f_loss - r_loss + 10 * gp
@@ -110,7 +138,10 @@ class GanIteration:
         att_mask = seq.unsqueeze(2) * seq.unsqueeze(1)                                   # run_gun.py:164-166
         with torch.no_grad():                                                            # :167 (detached right after, :170-174)
             f_cap, obj, mot, alpha = G(self.frames, self.regions, caps, L, self.tf)
-        real = torch.zeros(B, L, self.V, device=caps.device).scatter_(2, caps[:, :L].unsqueeze(2), 1)      # :449-453
+        if self.batched:
+            real = caps[:, :L].contiguous()                                              # token ids: the one-hot is never built
+        else:
+            real = torch.zeros(B, L, self.V, device=caps.device).scatter_(2, caps[:, :L].unsqueeze(2), 1)  # :449-453
         loss_d, wass = self._disc_steps(real, f_cap, obj, mot, att_mask, alpha)
         self.opt_g.zero_grad(set_to_none=True)
         out, obj, mot, alpha = G(self.frames, self.regions, caps, L, self.tf)            # :183

@@ -313,6 +313,37 @@ def add_pe(x, pe, p):
     return dropout(y, p)
 
 
+class _ColumnGather(torch.autograd.Function):
+    """out[n, :] = w[:, ids[n]]  for a (D, V) weight: the token embedding of a ONE-HOT input under a k=1 Conv1d / Linear
+    (model.py:147 on run_gun.py:449-453's to_onehot: a (N,V) x (V,D) product that is a pure column gather).
+    Forward: one transposing copy of the weight (V,D) + the embedding-gather kernel; backward: the scatter-add kernel."""
+
+    @staticmethod
+    def forward(ctx, w, ids):
+        D, V = w.shape
+        wt = empty((V, D), w)
+        ops.backend().convert(w.detach(), dstT=wt)
+        out = empty((ids.shape[0], D), w)
+        ops.backend().embedding_gather(wt, ids, out)
+        ctx.save_for_backward(ids)
+        ctx.shape = (D, V)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        (ids,) = ctx.saved_tensors
+        D, V = ctx.shape
+        dwt = zeros((V, D), dout)
+        ops.backend().embedding_scatter_add(dwt, ids, _c(dout))
+        return dwt.t(), None
+
+
+def column_gather(w, ids):
+    """w (D,V) (any row pitch), ids (N,) int64 -> (N,D) = rows of w^T."""
+    return _ColumnGather.apply(w, ids.reshape(-1))
+
+
 # ----------------------------------------------------------------------------------------------- misc (D path)
 def resblock_blc(x, w3, b3):
     """(B,L,C) layout: r = relu(x); r + 0.3 * conv1d_k3_pad1(r)   (sublayer.py:117-119 with the in-place ReLU)."""

@@ -22,6 +22,52 @@ def _inv_count(cap_lens, max_words):
     return 1.0 / max(1, sum(min(int(c), max_words) for c in cap_lens))
 
 
+def check_capturable(opt):
+    """A torch optimizer stepped inside a capture must keep its step counters on the device."""
+    if isinstance(opt, torch.optim.Adam) and any(p.is_cuda for g in opt.param_groups for p in g['params']):
+        for g in opt.param_groups:
+            if not (g.get('capturable', False) or optim.supported(opt)):
+                raise ValueError('optimizer must be torch.optim.Adam(..., capturable=True) to be captured in a CUDA graph')
+        for st in opt.state.values():
+            if 'step' in st and not (torch.is_tensor(st['step']) and st['step'].is_cuda):
+                raise ValueError('optimizer state holds host-side step counters (created with capturable=False): build the optimizer '
+                                 'with capturable=True (or fused=True) before its first step')
+
+
+def ensure_adam_state(opt, params):
+    if isinstance(opt, torch.optim.Adam):
+        for p in params:
+            if p.requires_grad:
+                optim._ensure_state(opt, p)
+
+
+def snapshot(model_or_models, opts):
+    """Parameters, optimizer state, host / device RNG state and the dropout seed counter, to undo capture warm-up steps."""
+    import copy
+    import random
+    models = model_or_models if isinstance(model_or_models, (list, tuple)) else [model_or_models]
+    return {'params': [(p, p.detach().clone()) for m in models for p in m.parameters()],
+            'opts': [(o, copy.deepcopy(o.state_dict())) for o in opts],
+            'py': random.getstate(), 'torch': torch.get_rng_state(),
+            'cuda': torch.cuda.get_rng_state() if torch.cuda.is_available() else None,
+            'seed_counter': copy.copy(DF._seed_counter)}
+
+
+def restore(snap):
+    import random
+    with torch.no_grad():
+        for p, v in snap['params']:
+            p.copy_(v)
+    for o, sd in snap['opts']:
+        o.load_state_dict(sd)
+    random.setstate(snap['py'])
+    torch.set_rng_state(snap['torch'])
+    if snap['cuda'] is not None:
+        torch.cuda.set_rng_state(snap['cuda'])
+    DF._seed_counter = snap['seed_counter']
+    DF.WC.gen += 1
+
+
 class GraphedTrainStep:
     def __init__(self, model, optimizer, frames, regions, captions, cap_lens, max_words=26, tf_ratio=1.0,
                  process_group=None, warmup=3, pin_weights=True, own_adam=True):
@@ -45,6 +91,8 @@ class GraphedTrainStep:
             # (use with DLSG_SYNC_DEBUG=nonccl | nopack)
             self.world = 2
             self.sync = DF.GradSync(None)
+        check_capturable(optimizer)
+        snap = snapshot(model, [optimizer]) if warmup > 0 else None
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -52,6 +100,9 @@ class GraphedTrainStep:
                 self._body()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        if snap is not None:
+            restore(snap)                         # the warm-up steps (allocator / NCCL warm-up) leave no trace in weights or Adam state
+        ensure_adam_state(optimizer, self.params) # state tensors must exist BEFORE the capture (a zero-fill captured with them would reset them on every replay)
         self.pinned = self._record_weight_copies() if pin_weights else None
         self.adam = None
         if own_adam and self.pinned is not None and optim.supported(optimizer):

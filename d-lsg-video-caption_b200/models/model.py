@@ -113,15 +113,20 @@ class DiscV2(nn.Module):
         return nn.Sequential(lin(input_dim, output_dim), nn.LeakyReLU(0.2))
 
     @G.param_scope
-    def forward(self, inputs, obj_proposals, motion_proposals, att_mask=None, alpha_all=None, _groups=1):
+    def forward(self, inputs, obj_proposals, motion_proposals, att_mask=None, alpha_all=None, _groups=1, _tokens=None):
         """inputs (B,L,V) one-hot / logits / mix -> score (B,)   (model.py:145-168).
         _groups > 1 (our own extension, used by dlsg.gan): the batch is `_groups` independent reference calls stacked along
         dim 0 - D(real), D(fake), D(mixed) of a critic step - so the per-call batch means of PSLScore2 (layer.py:713-714)
-        are taken per group and the result equals the concatenation of the separate calls."""
+        are taken per group and the result equals the concatenation of the separate calls.
+        _tokens (our own extension, dlsg.gan): the (B,L,512) output of the input projection computed by the caller (a column
+        gather for one-hot captions, a linear mix for the WGAN-GP interpolate); `inputs` is ignored."""
         drop = 0.3 if self.training else 0.0
         res_conv = self.block[0].res_block[1]
         rnn, ln = self.lstm, self.layer_norm
-        tokens = G.linear(inputs, self.conv1d.weight[:, :, 0], self.conv1d.bias)      # conv1d with k=1 == per-token Linear (B,L,512)
+        if _tokens is not None:
+            tokens = _tokens
+        else:
+            tokens = G.linear(inputs, self.conv1d.weight[:, :, 0], self.conv1d.bias)  # conv1d with k=1 == per-token Linear (B,L,512)
         tokens = G.resblock_blc(tokens, res_conv.weight, res_conv.bias)               # relu(x) + 0.3 * conv3(relu(x))
         states = G.lstm(tokens, rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0)
         states = G.norm(states, ln.weight, ln.bias, p_drop=drop)
