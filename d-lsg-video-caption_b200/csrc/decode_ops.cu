@@ -446,19 +446,82 @@ __device__ __forceinline__ ArgMax warp_argmax(ArgMax a) {
   return a;
 }
 
-__global__ void __launch_bounds__(256)
+// ---- vocabulary rows: one CTA per row.  A row (V ~ 1e4 fp32, arbitrary pitch, so its base is only 4-byte aligned) is walked
+// as [scalar head up to the first 16-byte boundary | float4 body | scalar tail]; every thread issues VR_UNROLL independent
+// 128-bit loads before it touches any of them (the old one-scalar-load-per-iteration loops were a chain of L2 round trips:
+// 31 us for a 27 MB top-k).  `F(v, col)` is applied to every element.
+constexpr int VR_UNROLL = 8;
+
+template <typename F>
+__device__ __forceinline__ void row_foreach(const float* __restrict__ x, int V, F&& f) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  int head = (int)(((16u - (uint32_t)(reinterpret_cast<uintptr_t>(x) & 15u)) & 15u) >> 2);
+  if (head > V) head = V;
+  if (tid < head) f(x[tid], tid);
+  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x + head);
+  const int n4 = (V - head) >> 2;
+  int j = tid;
+  for (; j + (VR_UNROLL - 1) * nt < n4; j += VR_UNROLL * nt) {
+    float4 v[VR_UNROLL];
+#pragma unroll
+    for (int u = 0; u < VR_UNROLL; ++u) v[u] = x4[j + u * nt];
+#pragma unroll
+    for (int u = 0; u < VR_UNROLL; ++u) {
+      const int c = head + 4 * (j + u * nt);
+      f(v[u].x, c); f(v[u].y, c + 1); f(v[u].z, c + 2); f(v[u].w, c + 3);
+    }
+  }
+  for (; j < n4; j += nt) {
+    const float4 v = x4[j];
+    const int c = head + 4 * j;
+    f(v.x, c); f(v.y, c + 1); f(v.z, c + 2); f(v.w, c + 3);
+  }
+  const int t0 = head + 4 * n4;
+  if (t0 + tid < V) f(x[t0 + tid], t0 + tid);
+}
+
+// running (max, sum of exp(x - max)) of the values a thread has seen: one rescale per NEW maximum only
+struct OnlineLse {
+  float m, s;
+  __device__ __forceinline__ void init() { m = -INFINITY; s = 0.f; }
+  __device__ __forceinline__ void add(float v) {
+    if (v > m) { s = s * __expf(m - v) + 1.f; m = v; }       // (m = -inf: s = 0 * exp(-inf) + 1 = 1)
+    else s += __expf(v - m);
+  }
+  __device__ __forceinline__ void merge(float m2, float s2) {
+    const float mm = fmaxf(m, m2);
+    if (mm == -INFINITY) return;
+    s = s * __expf(m - mm) + s2 * __expf(m2 - mm);
+    m = mm;
+  }
+};
+// block-wide log-sum-exp from per-thread OnlineLse (blockDim <= 1024); `sh` needs 64 floats.  All threads get the result.
+__device__ __forceinline__ float block_lse(OnlineLse o, float* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) o.merge(__shfl_xor_sync(0xffffffffu, o.m, d), __shfl_xor_sync(0xffffffffu, o.s, d));
+  __syncthreads();
+  if (lane == 0) { sh[w] = o.m; sh[32 + w] = o.s; }
+  __syncthreads();
+  OnlineLse r; r.m = lane < nw ? sh[lane] : -INFINITY; r.s = lane < nw ? sh[32 + lane] : 0.f;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) r.merge(__shfl_xor_sync(0xffffffffu, r.m, d), __shfl_xor_sync(0xffffffffu, r.s, d));
+  return r.m + logf(r.s);
+}
+
+__global__ void __launch_bounds__(128)
 row_argmax_kernel(const float* __restrict__ logits, int64_t ld, int V, int64_t* __restrict__ ids, int64_t ld_ids) {
   pdl_prologue();
-  __shared__ float sv[8]; __shared__ int si[8];
+  __shared__ float sv[4]; __shared__ int si[4];
   const float* x = logits + (int64_t)blockIdx.x * ld;
   ArgMax a; a.v = -INFINITY; a.i = 0x7fffffff;
-  for (int c = threadIdx.x; c < V; c += blockDim.x) { ArgMax b; b.v = x[c]; b.i = c; a = better(a, b); }
+  row_foreach(x, V, [&](float v, int c) { if (v > a.v || (v == a.v && c < a.i)) { a.v = v; a.i = c; } });
   a = warp_argmax(a);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   if (lane == 0) { sv[w] = a.v; si[w] = a.i; }
   __syncthreads();
   if (w == 0) {
-    ArgMax b; b.v = lane < 8 ? sv[lane] : -INFINITY; b.i = lane < 8 ? si[lane] : 0x7fffffff;
+    ArgMax b; b.v = lane < nw ? sv[lane] : -INFINITY; b.i = lane < nw ? si[lane] : 0x7fffffff;
     b = warp_argmax(b);
     if (lane == 0) ids[(int64_t)blockIdx.x * ld_ids] = b.i;
   }
@@ -486,7 +549,7 @@ ce_masked_kernel(const float* __restrict__ logits, const int64_t* __restrict__ t
                  int L, int V, float* __restrict__ loss_sum, float* __restrict__ dlogits, float inv_count_host,
                  const float* __restrict__ inv_count_dev, float* __restrict__ row_loss) {
   pdl_prologue();
-  __shared__ float red[32];
+  __shared__ float red[64];
   const float inv_count = inv_count_dev ? *inv_count_dev : inv_count_host;
   const int row = blockIdx.x, b = row / L, t = row % L;
   const float* x = logits + (int64_t)row * V;
@@ -495,13 +558,9 @@ ce_masked_kernel(const float* __restrict__ logits, const int64_t* __restrict__ t
     if (row_loss && threadIdx.x == 0) row_loss[row] = 0.f;
     return;
   }
-  float mx = -INFINITY;
-  for (int c = threadIdx.x; c < V; c += blockDim.x) mx = fmaxf(mx, x[c]);
-  mx = block_max(mx, red);
-  float s = 0.f;
-  for (int c = threadIdx.x; c < V; c += blockDim.x) s += expf(x[c] - mx);
-  s = block_sum(s, red);
-  const float lse = mx + logf(s);
+  OnlineLse o; o.init();
+  row_foreach(x, V, [&](float v, int) { o.add(v); });
+  const float lse = block_lse(o, red);
   const int tgt = (int)targets[row];
   if (threadIdx.x == 0) {
     const float l = (lse - x[tgt]) * inv_count;
@@ -509,10 +568,27 @@ ce_masked_kernel(const float* __restrict__ logits, const int64_t* __restrict__ t
     else atomicAdd(loss_sum, l);
   }
   if (dlogits) {
-    for (int c = threadIdx.x; c < V; c += blockDim.x) {
-      float g = expf(x[c] - lse);
-      if (c == tgt) g -= 1.f;
-      dlogits[(int64_t)row * V + c] = g * inv_count;
+    float* __restrict__ d = dlogits + (int64_t)row * V;          // same pitch as x: same alignment pattern
+    const bool same = ((reinterpret_cast<uintptr_t>(d) ^ reinterpret_cast<uintptr_t>(x)) & 15u) == 0;
+    if (same) {
+      const int tid = threadIdx.x, nt = blockDim.x;
+      int head = (int)(((16u - (uint32_t)(reinterpret_cast<uintptr_t>(x) & 15u)) & 15u) >> 2);
+      if (head > V) head = V;
+      if (tid < head) d[tid] = (expf(x[tid] - lse) - (tid == tgt ? 1.f : 0.f)) * inv_count;
+      const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x + head);
+      float4* __restrict__ d4 = reinterpret_cast<float4*>(d + head);
+      const int n4 = (V - head) >> 2;
+      for (int j = tid; j < n4; j += nt) {
+        const float4 v = x4[j];
+        const int c = head + 4 * j;
+        float4 g = make_float4(expf(v.x - lse), expf(v.y - lse), expf(v.z - lse), expf(v.w - lse));
+        if ((unsigned)(tgt - c) < 4u) { if (tgt == c) g.x -= 1.f; else if (tgt == c + 1) g.y -= 1.f; else if (tgt == c + 2) g.z -= 1.f; else g.w -= 1.f; }
+        d4[j] = make_float4(g.x * inv_count, g.y * inv_count, g.z * inv_count, g.w * inv_count);
+      }
+      const int t0 = head + 4 * n4;
+      if (t0 + tid < V) d[t0 + tid] = (expf(x[t0 + tid] - lse) - (t0 + tid == tgt ? 1.f : 0.f)) * inv_count;
+    } else {
+      for (int c = threadIdx.x; c < V; c += blockDim.x) d[c] = (expf(x[c] - lse) - (c == tgt ? 1.f : 0.f)) * inv_count;
     }
   }
 }
@@ -551,13 +627,13 @@ __device__ __forceinline__ void insert_topk(float (&tv)[KT], int (&ti)[KT], floa
 }
 
 template <int KT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 beam_topk_kernel(const float* __restrict__ logits, int64_t ld, int V, const int64_t* __restrict__ last, int end_index, int k,
                  float* __restrict__ top_lp, int64_t* __restrict__ top_id, int normalize) {
   pdl_prologue();
-  __shared__ float red[32];
-  __shared__ float cv[8 * MAXK];
-  __shared__ int ci[8 * MAXK];
+  __shared__ float red[64];
+  __shared__ float cv[4 * MAXK];
+  __shared__ int ci[4 * MAXK];
   const int row = blockIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (last && last[row] == end_index) {
@@ -575,20 +651,11 @@ beam_topk_kernel(const float* __restrict__ logits, int64_t ld, int V, const int6
   float tv[KT]; int ti[KT];
 #pragma unroll
   for (int j = 0; j < KT; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
-  float mx = -INFINITY;
-  for (int c = threadIdx.x; c < V; c += blockDim.x) {
-    const float v = x[c];
-    mx = fmaxf(mx, v);
-    insert_topk<KT>(tv, ti, v, c);
-  }
-  float lse = 0.f;
-  if (normalize) {
-    mx = block_max(mx, red);
-    float s = 0.f;
-    for (int c = threadIdx.x; c < V; c += blockDim.x) s += expf(x[c] - mx);
-    s = block_sum(s, red);
-    lse = mx + logf(s);
-  }
+  // ONE pass over the row: log-sum-exp statistics (online) and the per-thread top-k lists together
+  OnlineLse o; o.init();
+  if (normalize) row_foreach(x, V, [&](float v, int c) { o.add(v); insert_topk<KT>(tv, ti, v, c); });
+  else row_foreach(x, V, [&](float v, int c) { insert_topk<KT>(tv, ti, v, c); });
+  const float lse = normalize ? block_lse(o, red) : 0.f;
   // warp-level merge: k rounds of warp arg-max over the per-lane heads
   int head = 0;
   for (int j = 0; j < k; ++j) {
@@ -738,7 +805,7 @@ int dlsg_attn2_bwd(const dlsg_attn2_bwd_t* p, void* stream) {
 }
 int dlsg_row_argmax(const float* logits, int64_t ld, int32_t rows, int32_t V, int64_t* ids, int64_t ld_ids, void* stream) {
   if (rows <= 0) return 0;
-  DLSG_LAUNCH(row_argmax_kernel, rows, 256, 0, (cudaStream_t)stream, logits, ld, V, ids, ld_ids);
+  DLSG_LAUNCH(row_argmax_kernel, rows, 128, 0, (cudaStream_t)stream, logits, ld, V, ids, ld_ids);
   return check_launch("row_argmax_kernel");
 }
 int dlsg_log_softmax(const float* logits, int64_t ld, int32_t rows, int32_t V, float* out, int64_t ldo, void* stream) {
@@ -762,11 +829,11 @@ int dlsg_beam_topk(const float* logits, int64_t ld, int32_t rows, int32_t V, con
   DLSG_REQUIRE(k <= V, "beam_topk: Target vocab size (%d) too small relative to per_node_beam_size (%d)", V, k);
   if (rows <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (k <= 1) DLSG_LAUNCH(beam_topk_kernel<1>, rows, 256, 0, st, logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
-  else if (k <= 3) DLSG_LAUNCH(beam_topk_kernel<3>, rows, 256, 0, st, logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
-  else if (k <= 5) DLSG_LAUNCH(beam_topk_kernel<5>, rows, 256, 0, st, logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
-  else if (k <= 8) DLSG_LAUNCH(beam_topk_kernel<8>, rows, 256, 0, st, logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
-  else DLSG_LAUNCH(beam_topk_kernel<16>, rows, 256, 0, st, logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
+  if (k <= 1) DLSG_LAUNCH(beam_topk_kernel<1>, rows, 128, 0, st, logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
+  else if (k <= 3) DLSG_LAUNCH(beam_topk_kernel<3>, rows, 128, 0, st, logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
+  else if (k <= 5) DLSG_LAUNCH(beam_topk_kernel<5>, rows, 128, 0, st, logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
+  else if (k <= 8) DLSG_LAUNCH(beam_topk_kernel<8>, rows, 128, 0, st, logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
+  else DLSG_LAUNCH(beam_topk_kernel<16>, rows, 128, 0, st, logits, ld, V, last, end_index, k, top_lp, top_id, normalize);
   return check_launch("beam_topk_kernel");
 }
 int dlsg_beam_merge(const float* top_lp, const int64_t* top_id, const float* last_lp, int32_t B, int32_t beam, int32_t k,
