@@ -452,12 +452,12 @@ __device__ __forceinline__ ArgMax warp_argmax(ArgMax a) {
 // 31 us for a 27 MB top-k).  `F(v, col)` is applied to every element.
 constexpr int VR_UNROLL = 8;
 
-template <typename F>
-__device__ __forceinline__ void row_foreach(const float* __restrict__ x, int V, F&& f) {
+template <typename F1, typename F4>
+__device__ __forceinline__ void row_foreach(const float* __restrict__ x, int V, F1&& f1, F4&& f4) {
   const int tid = threadIdx.x, nt = blockDim.x;
   int head = (int)(((16u - (uint32_t)(reinterpret_cast<uintptr_t>(x) & 15u)) & 15u) >> 2);
   if (head > V) head = V;
-  if (tid < head) f(x[tid], tid);
+  if (tid < head) f1(x[tid], tid);
   const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x + head);
   const int n4 = (V - head) >> 2;
   int j = tid;
@@ -466,27 +466,30 @@ __device__ __forceinline__ void row_foreach(const float* __restrict__ x, int V, 
 #pragma unroll
     for (int u = 0; u < VR_UNROLL; ++u) v[u] = x4[j + u * nt];
 #pragma unroll
-    for (int u = 0; u < VR_UNROLL; ++u) {
-      const int c = head + 4 * (j + u * nt);
-      f(v[u].x, c); f(v[u].y, c + 1); f(v[u].z, c + 2); f(v[u].w, c + 3);
-    }
+    for (int u = 0; u < VR_UNROLL; ++u) f4(v[u], head + 4 * (j + u * nt));
   }
-  for (; j < n4; j += nt) {
-    const float4 v = x4[j];
-    const int c = head + 4 * j;
-    f(v.x, c); f(v.y, c + 1); f(v.z, c + 2); f(v.w, c + 3);
-  }
+  for (; j < n4; j += nt) f4(x4[j], head + 4 * j);
   const int t0 = head + 4 * n4;
-  if (t0 + tid < V) f(x[t0 + tid], t0 + tid);
+  if (t0 + tid < V) f1(x[t0 + tid], t0 + tid);
+}
+template <typename F>
+__device__ __forceinline__ void row_foreach(const float* __restrict__ x, int V, F&& f) {
+  row_foreach(x, V, f, [&](const float4 v, int c) { f(v.x, c); f(v.y, c + 1); f(v.z, c + 2); f(v.w, c + 3); });
 }
 
-// running (max, sum of exp(x - max)) of the values a thread has seen: one rescale per NEW maximum only
+// running (max, sum of exp(x - max)) of the values a thread has seen; add4 rescales at most once per 128-bit load, so the
+// common case is 4 x (subtract, ex2, add) with no per-element branch
 struct OnlineLse {
   float m, s;
   __device__ __forceinline__ void init() { m = -INFINITY; s = 0.f; }
   __device__ __forceinline__ void add(float v) {
     if (v > m) { s = s * __expf(m - v) + 1.f; m = v; }       // (m = -inf: s = 0 * exp(-inf) + 1 = 1)
-    else s += __expf(v - m);
+    else if (m > -INFINITY) s += __expf(v - m);              // (only -inf seen so far: nothing to add, exp(-inf + inf) is NaN)
+  }
+  __device__ __forceinline__ void add4(const float4 v) {
+    const float c = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+    if (c > m) { s *= __expf(m - c); m = c; }
+    if (m > -INFINITY) s += (__expf(v.x - m) + __expf(v.y - m)) + (__expf(v.z - m) + __expf(v.w - m));
   }
   __device__ __forceinline__ void merge(float m2, float s2) {
     const float mm = fmaxf(m, m2);
@@ -530,16 +533,18 @@ row_argmax_kernel(const float* __restrict__ logits, int64_t ld, int V, int64_t* 
 __global__ void __launch_bounds__(256)
 log_softmax_kernel(const float* __restrict__ logits, int64_t ld, int V, float* __restrict__ out, int64_t ldo) {
   pdl_prologue();
-  __shared__ float red[32];
+  __shared__ float red[64];
   const float* x = logits + (int64_t)blockIdx.x * ld;
-  float mx = -INFINITY;
-  for (int c = threadIdx.x; c < V; c += blockDim.x) mx = fmaxf(mx, x[c]);
-  mx = block_max(mx, red);
-  float s = 0.f;
-  for (int c = threadIdx.x; c < V; c += blockDim.x) s += expf(x[c] - mx);
-  s = block_sum(s, red);
-  const float lse = mx + logf(s);
-  for (int c = threadIdx.x; c < V; c += blockDim.x) out[(int64_t)blockIdx.x * ldo + c] = x[c] - lse;
+  float* y = out + (int64_t)blockIdx.x * ldo;
+  OnlineLse o; o.init();
+  row_foreach(x, V, [&](float v, int) { o.add(v); }, [&](const float4 v, int) { o.add4(v); });
+  const float lse = block_lse(o, red);
+  if (((reinterpret_cast<uintptr_t>(x) ^ reinterpret_cast<uintptr_t>(y)) & 15u) == 0) {
+    row_foreach(x, V, [&](float v, int c) { y[c] = v - lse; },
+                [&](const float4 v, int c) { *reinterpret_cast<float4*>(y + c) = make_float4(v.x - lse, v.y - lse, v.z - lse, v.w - lse); });
+  } else {
+    row_foreach(x, V, [&](float v, int c) { y[c] = v - lse; });
+  }
 }
 
 // masked CE: one CTA per (b,t) row.  loss_sum += -log p[target] for t < len[b];
@@ -559,7 +564,7 @@ ce_masked_kernel(const float* __restrict__ logits, const int64_t* __restrict__ t
     return;
   }
   OnlineLse o; o.init();
-  row_foreach(x, V, [&](float v, int) { o.add(v); });
+  row_foreach(x, V, [&](float v, int) { o.add(v); }, [&](const float4 v, int) { o.add4(v); });
   const float lse = block_lse(o, red);
   const int tgt = (int)targets[row];
   if (threadIdx.x == 0) {
@@ -626,14 +631,27 @@ __device__ __forceinline__ void insert_topk(float (&tv)[KT], int (&ti)[KT], floa
   }
 }
 
+// Two walks over the row (the second one hits L2): (1) per-thread maxima (+ the online log-sum-exp); the k-th largest of the
+// 128 thread maxima is a LOWER bound T of the row's k-th largest value (they are k distinct elements); (2) every element >= T
+// (a handful) is appended to a shared candidate list, from which one warp picks the top k by (value desc, index asc).
+// Per-thread sorted insertion - the old scheme - made every warp run the ~60-instruction insertion path on almost every
+// element (some lane always had a new top-5 entry among its first ~80 values): 33 us for 27 MB.  A degenerate row (more than
+// TOPK_CAP candidates, e.g. thousands of equal logits) falls back to that scheme.
+constexpr int TOPK_CAP = 512;
+
 template <int KT>
 __global__ void __launch_bounds__(128)
 beam_topk_kernel(const float* __restrict__ logits, int64_t ld, int V, const int64_t* __restrict__ last, int end_index, int k,
                  float* __restrict__ top_lp, int64_t* __restrict__ top_id, int normalize) {
   pdl_prologue();
   __shared__ float red[64];
+  __shared__ float tmax[128];
+  __shared__ float cand_v[TOPK_CAP];
+  __shared__ int cand_i[TOPK_CAP];
   __shared__ float cv[4 * MAXK];
   __shared__ int ci[4 * MAXK];
+  __shared__ int ncand;
+  __shared__ float thr;
   const int row = blockIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (last && last[row] == end_index) {
@@ -648,19 +666,77 @@ beam_topk_kernel(const float* __restrict__ logits, int64_t ld, int V, const int6
     return;
   }
   const float* x = logits + (int64_t)row * ld;
+  // ---- walk 1: thread maxima, log-sum-exp
+  OnlineLse o; o.init();
+  float mx = -INFINITY;
+  if (normalize) row_foreach(x, V, [&](float v, int) { o.add(v); }, [&](const float4 v, int) { o.add4(v); });
+  else row_foreach(x, V, [&](float v, int) { mx = fmaxf(mx, v); },
+                   [&](const float4 v, int) { mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w))); });
+  if (normalize) mx = o.m;
+  tmax[threadIdx.x] = mx;
+  if (threadIdx.x == 0) ncand = 0;
+  const float lse = normalize ? block_lse(o, red) : 0.f;     // (contains the __syncthreads that publish tmax / ncand)
+  if (!normalize) __syncthreads();
+  if (w == 0) {
+    // k-th largest of the 128 thread maxima (duplicates count separately): k rounds of warp arg-max with removal
+    float a[4] = {tmax[lane], tmax[lane + 32], tmax[lane + 64], tmax[lane + 96]};
+    float t = -INFINITY;
+    const int rounds = k < 128 ? k : 128;
+    for (int j = 0; j < rounds; ++j) {
+      int bu = 0;
+      float bv = a[0];
+#pragma unroll
+      for (int u = 1; u < 4; ++u) if (a[u] > bv) { bv = a[u]; bu = u; }
+      ArgMax c; c.v = bv; c.i = lane * 4 + bu;
+      const ArgMax best = warp_argmax(c);
+      t = best.v;
+      if ((best.i >> 2) == lane) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (u == (best.i & 3)) a[u] = -INFINITY;
+      }
+    }
+    if (lane == 0) thr = (V >= 128 * 1 && k <= 128) ? t : -INFINITY;
+  }
+  __syncthreads();
+  const float T = thr;
+  // ---- walk 2: candidates >= T
+  auto push = [&](float v, int c) {
+    if (v >= T) {
+      const int slot = atomicAdd(&ncand, 1);
+      if (slot < TOPK_CAP) { cand_v[slot] = v; cand_i[slot] = c; }
+    }
+  };
+  row_foreach(x, V, push);
+  __syncthreads();
+  const int n = ncand;
+  if (n <= TOPK_CAP) {
+    if (w == 0) {
+      for (int j = 0; j < k; ++j) {
+        ArgMax a; a.v = -INFINITY; a.i = 0x7fffffff;
+        int slot = -1;
+        for (int e = lane; e < n; e += 32) {
+          const float v = cand_v[e]; const int i = cand_i[e];
+          if (i != 0x7fffffff && kv_before(v, i, a.v, a.i)) { a.v = v; a.i = i; slot = e; }
+        }
+        const ArgMax best = warp_argmax(a);
+        if (slot >= 0 && a.i == best.i) cand_i[slot] = 0x7fffffff;     // (column indices are unique: exactly one lane removes)
+        __syncwarp();
+        if (lane == 0) {
+          top_lp[(int64_t)row * k + j] = best.v - lse;
+          top_id[(int64_t)row * k + j] = best.i;
+        }
+      }
+    }
+    return;
+  }
+  // ---- degenerate row: per-thread sorted lists + two-level merge
   float tv[KT]; int ti[KT];
 #pragma unroll
   for (int j = 0; j < KT; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
-  // ONE pass over the row: log-sum-exp statistics (online) and the per-thread top-k lists together
-  OnlineLse o; o.init();
-  if (normalize) row_foreach(x, V, [&](float v, int c) { o.add(v); insert_topk<KT>(tv, ti, v, c); });
-  else row_foreach(x, V, [&](float v, int c) { insert_topk<KT>(tv, ti, v, c); });
-  const float lse = normalize ? block_lse(o, red) : 0.f;
-  // warp-level merge: k rounds of warp arg-max over the per-lane heads
+  row_foreach(x, V, [&](float v, int c) { insert_topk<KT>(tv, ti, v, c); });
   int head = 0;
   for (int j = 0; j < k; ++j) {
     ArgMax a; a.v = -INFINITY; a.i = 0x7fffffff;
-    // select via static indexing to keep tv/ti in registers
 #pragma unroll
     for (int u = 0; u < KT; ++u) if (u == head && u < k) { a.v = tv[u]; a.i = ti[u]; }
     const ArgMax best = warp_argmax(a);

@@ -561,3 +561,28 @@ def test_beam_kernels(be, V_, k):
     backs = torch.randint(0, beam, (S - 1, B_, beam))
     both('beam_backtrack', be, [preds, backs, S, B_, beam, torch.zeros(B_, beam, S, dtype=torch.int64)], {}, [], int_outs=[5])
     both('beam_backtrack', be, [preds, backs, 4, B_, beam, torch.zeros(B_, beam, 4, dtype=torch.int64)], {}, [], int_outs=[5])
+
+
+@pytest.mark.parametrize('V_', [10547, 20011])
+def test_beam_topk_degenerate_and_strided_rows(be, V_):
+    """Rows that defeat the threshold shortcut of the top-k kernels (all logits equal / thousands of ties at the maximum /
+    -inf entries), rows taken as a column slice of a wider buffer (pitch != V, every 16-byte alignment), a vocabulary larger
+    than the register-resident variant holds (20011): ids and log-probs must equal torch's log_softmax + (value desc, index
+    asc) selection."""
+    k, rows = 5, 12
+    wide = R(rows, V_ + 13, scale=2.0)
+    lg = wide[:, 3:3 + V_]                       # pitch V_+13, misaligned base
+    lg[0] = 0.25                                 # all equal: top-k = the k lowest indices
+    lg[1, :] = -1.0
+    lg[1, 100:4100] = 7.0                        # 4000 ties at the maximum
+    lg[2, 50:] = float('-inf')                   # only 50 finite entries
+    lg[3, 7] = lg[3, 9000] = lg[3].max() + 2     # tie between a low and a high index
+    last = torch.full((rows,), 9, dtype=torch.int64)
+    ref_lp = torch.log_softmax(lg.double(), -1)
+    order = torch.argsort(torch.arange(V_).expand(rows, V_) - 1e9 * 0, 1)      # placeholder for clarity: indices ascending
+    # (value desc, index asc): sort by index first (stable), then by value descending (stable)
+    idx = torch.argsort(lg.double(), dim=1, descending=True, stable=True)[:, :k]
+    gtl, gti = torch.zeros(rows, k, device=DEV), torch.zeros(rows, k, dtype=torch.int64, device=DEV)
+    be.beam_topk(wide.to(DEV)[:, 3:3 + V_], last.to(DEV), 2, k, gtl, gti)
+    assert torch.equal(gti.cpu(), idx), (gti.cpu()[:4], idx[:4])
+    assert (gtl.cpu().double() - ref_lp.gather(1, idx)).abs().max() < 1e-4
