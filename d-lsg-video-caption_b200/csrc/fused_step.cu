@@ -37,6 +37,114 @@ __device__ __forceinline__ bool vecok(const void* p, int dt, int64_t ld) {
 }
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
+// Fast path (the shapes of the decoder loop): the number of split-K partials is a template parameter and EVERY global load
+// of a thread (4 gates x S partials, the bias, c_prev, the LayerNorm parameters: 20-30 independent 128-bit loads) is issued
+// before the first use, into registers of its own.  The generic kernel below sums the partials in a loop over a run-time
+// count; ptxas reuses two or three destination registers there, which serialises the loads into a chain of L2 round
+// trips: 10 us per launch inside the 26-step loop for 5 MB of data (ncu source view, profiles/r02_step_kernels_ncu.json).
+template <int S>
+__global__ void __launch_bounds__(384)
+lstm_cell_norm_fwd_fast(const dlsg_lstm_cell_norm_fwd_t q) {
+  pdl_prologue();
+  __shared__ float red[32];
+  const dlsg_lstm_cell_fwd_t& p = q.cell;
+  const int b = blockIdx.x, H = p.H, tid = threadIdx.x;
+  const int h = tid * 4;
+  const bool act = h < H;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 part[4][S], eb[4], cp = z4, ga = z4, bt = z4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    eb[k] = z4;
+#pragma unroll
+    for (int s_ = 0; s_ < S; ++s_) part[k][s_] = z4;
+  }
+  if (act) {
+    const float* g0p = p.gates + (int64_t)b * 4 * H + h;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int s_ = 0; s_ < S; ++s_) part[k][s_] = ld4f(g0p + (int64_t)k * H + (int64_t)s_ * p.stride_split);
+    if (p.row_bias) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) eb[k] = ld4f(p.row_bias + (int64_t)b * p.ld_row_bias + (int64_t)k * H + h);
+    } else if (p.bias) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) eb[k] = ld4f(p.bias + k * H + h);
+    }
+    if (p.c_prev) cp = ld4f(p.c_prev + (int64_t)b * H + h);
+    ga = ld4f(q.gamma + h);
+    bt = ld4f(q.beta + h);
+  }
+  float4 g[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float4 v = part[k][0];
+#pragma unroll
+    for (int s_ = 1; s_ < S; ++s_) v = f4add(v, part[k][s_]);
+    g[k] = f4add(v, eb[k]);
+  }
+  if (p.row_bias && p.bias && act) {            // both given (not the decoder's case): one more round trip
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g[k] = f4add(g[k], ld4f(p.bias + k * H + h));
+  }
+  const bool v2 = p.h2 && vecok(p.h2, p.h2_dtype, p.ldh2), v3 = p.h3 && vecok(p.h3, p.h3_dtype, p.ldh3);
+  const bool vy = q.y && vecok(q.y, q.y_dtype, q.ldy), vy2 = q.y2 && vecok(q.y2, q.y2_dtype, q.ldy2);
+  float4 h4 = z4;
+  float sum = 0.f;
+  if (act) {
+    const int64_t ei = (int64_t)b * H + h;
+    const float gi_[4] = {g[0].x, g[0].y, g[0].z, g[0].w}, gf_[4] = {g[1].x, g[1].y, g[1].z, g[1].w};
+    const float gg_[4] = {g[2].x, g[2].y, g[2].z, g[2].w}, go_[4] = {g[3].x, g[3].y, g[3].z, g[3].w};
+    const float cp_[4] = {cp.x, cp.y, cp.z, cp.w};
+    float ai[4], af[4], ag[4], ao[4], cc[4], hh[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ai[u] = sigmoidf_(gi_[u]); af[u] = sigmoidf_(gf_[u]); ag[u] = tanhf(gg_[u]); ao[u] = sigmoidf_(go_[u]);
+      cc[u] = af[u] * cp_[u] + ai[u] * ag[u];
+      hh[u] = ao[u] * tanhf(cc[u]);
+    }
+    if (p.drop_p > 0.f) {
+      const float4 m = drop_mask4(p.drop_p, 1.f / (1.f - p.drop_p), p.seed, p.offset + (uint64_t)ei);
+      hh[0] *= m.x; hh[1] *= m.y; hh[2] *= m.z; hh[3] *= m.w;
+    }
+    float* g0 = p.gates + (int64_t)b * 4 * H + h;
+    *reinterpret_cast<float4*>(g0) = make_float4(ai[0], ai[1], ai[2], ai[3]);
+    *reinterpret_cast<float4*>(g0 + H) = make_float4(af[0], af[1], af[2], af[3]);
+    *reinterpret_cast<float4*>(g0 + 2 * (int64_t)H) = make_float4(ag[0], ag[1], ag[2], ag[3]);
+    *reinterpret_cast<float4*>(g0 + 3 * (int64_t)H) = make_float4(ao[0], ao[1], ao[2], ao[3]);
+    *reinterpret_cast<float4*>(p.c_out + ei) = make_float4(cc[0], cc[1], cc[2], cc[3]);
+    h4 = make_float4(hh[0], hh[1], hh[2], hh[3]);
+    if (p.h_out) *reinterpret_cast<float4*>(p.h_out + ei) = h4;
+    if (p.h2) st4any(p.h2, p.h2_dtype, (int64_t)b * p.ldh2 + h, h4, v2);
+    if (p.h3) st4any(p.h3, p.h3_dtype, (int64_t)b * p.ldh3 + h, h4, v3);
+    sum = (h4.x + h4.y) + (h4.z + h4.w);
+  }
+  const float mean = block_sum(sum, red) / (float)H;
+  float sq = 0.f;
+  if (act) {
+    const float a = h4.x - mean, b2 = h4.y - mean, c = h4.z - mean, d = h4.w - mean;
+    sq = (a * a + b2 * b2) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(block_sum(sq, red) / (float)H + 1e-5f);
+  if (q.stats && tid == 0) { q.stats[b * 2] = mean; q.stats[b * 2 + 1] = rstd; }
+  if (act) {
+    float y[4] = {(h4.x - mean) * rstd * ga.x + bt.x, (h4.y - mean) * rstd * ga.y + bt.y,
+                  (h4.z - mean) * rstd * ga.z + bt.z, (h4.w - mean) * rstd * ga.w + bt.w};
+    if (q.post_tanh) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) y[u] = tanhf(y[u]);
+    }
+    if (q.ydrop_p > 0.f) {
+      const float4 m = drop_mask4(q.ydrop_p, 1.f / (1.f - q.ydrop_p), q.yseed, q.yoffset + (uint64_t)b * H + h);
+      y[0] *= m.x; y[1] *= m.y; y[2] *= m.z; y[3] *= m.w;
+    }
+    const float4 y4 = make_float4(y[0], y[1], y[2], y[3]);
+    if (q.y) st4any(q.y, q.y_dtype, (int64_t)b * q.ldy + h, y4, vy);
+    if (q.y2) st4any(q.y2, q.y2_dtype, (int64_t)b * q.ldy2 + h, y4, vy2);
+  }
+}
+
 __global__ void __launch_bounds__(512)
 lstm_cell_norm_fwd_kernel(const dlsg_lstm_cell_norm_fwd_t q) {
   pdl_prologue();
@@ -132,6 +240,108 @@ lstm_cell_norm_fwd_kernel(const dlsg_lstm_cell_norm_fwd_t q) {
       const float4 y4 = make_float4(y[0], y[1], y[2], y[3]);
       if (q.y) st4any(q.y, q.y_dtype, (int64_t)b * q.ldy + h, y4, vy);
       if (q.y2) st4any(q.y2, q.y2_dtype, (int64_t)b * q.ldy2 + h, y4, vy2);
+    }
+  }
+}
+
+// Backward counterpart of lstm_cell_norm_fwd_fast: every load of the thread (LayerNorm operands, the four saved gate
+// activations, cell states, the recurrent gradients with their S2 split-K partials, the running gate-gradient sum) is issued
+// before the first reduction, so the two block-wide sums overlap the memory round trip instead of following it.
+template <int S2>
+__global__ void __launch_bounds__(384)
+norm_lstm_cell_bwd_fast(const dlsg_norm_lstm_cell_bwd_t q) {
+  pdl_prologue();
+  __shared__ float red[32];
+  const dlsg_lstm_cell_bwd_t& p = q.cell;
+  const int b = blockIdx.x, H = p.H, tid = threadIdx.x;
+  const int h = tid * 4;
+  const bool act = h < H;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 x = z4, dy = z4, g = z4, be = z4, ai = z4, af = z4, ag = z4, ao = z4, cn = z4, cp = z4, dcn = z4, r1 = z4, r2[S2], gs[4];
+#pragma unroll
+  for (int s_ = 0; s_ < S2; ++s_) r2[s_] = z4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) gs[k] = z4;
+  float mean = 0.f, rstd = 0.f;
+  const int64_t ei = (int64_t)b * H + h, g0 = (int64_t)b * 4 * H + h;
+  if (act) {
+    x = ld4f(q.x + (int64_t)b * q.ldx + h);
+    dy = ld4f(q.dy + (int64_t)b * q.lddy + h);
+    g = ld4f(q.gamma + h);
+    if (q.post_tanh) be = ld4f(q.beta + h);
+    ai = ld4f(p.acts + g0); af = ld4f(p.acts + g0 + H); ag = ld4f(p.acts + g0 + 2 * (int64_t)H); ao = ld4f(p.acts + g0 + 3 * (int64_t)H);
+    cn = ld4f(p.c_new + ei);
+    if (p.c_prev) cp = ld4f(p.c_prev + ei);
+    if (p.dc_next) dcn = ld4f(p.dc_next + ei);
+    if (p.dh) r1 = ld4f(p.dh + (int64_t)b * p.lddh + h);
+    if (p.dh2) {
+#pragma unroll
+      for (int s_ = 0; s_ < S2; ++s_) r2[s_] = ld4f(p.dh2 + (int64_t)b * p.lddh2 + h + (int64_t)s_ * p.dh2_stride_split);
+    }
+    if (q.dgates_sum) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) gs[k] = ld4f(q.dgates_sum + g0 + (int64_t)k * H);
+    }
+  }
+  mean = q.stats[b * 2]; rstd = q.stats[b * 2 + 1];
+  const bool vd2 = p.dgates2 && vecok(p.dgates2, p.dgates2_dtype, p.ld_dgates2);
+  float4 xn = z4, d = z4;
+  float s1 = 0.f, s2 = 0.f;
+  if (act) {
+    if (q.ydrop_p > 0.f) {
+      const float4 m = drop_mask4(q.ydrop_p, 1.f / (1.f - q.ydrop_p), q.yseed, q.yoffset + (uint64_t)b * H + h);
+      dy.x *= m.x; dy.y *= m.y; dy.z *= m.z; dy.w *= m.w;
+    }
+    xn = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
+    if (q.post_tanh) {
+      float yt;
+      yt = tanhf(xn.x * g.x + be.x); dy.x *= (1.f - yt * yt);
+      yt = tanhf(xn.y * g.y + be.y); dy.y *= (1.f - yt * yt);
+      yt = tanhf(xn.z * g.z + be.z); dy.z *= (1.f - yt * yt);
+      yt = tanhf(xn.w * g.w + be.w); dy.w *= (1.f - yt * yt);
+    }
+    *reinterpret_cast<float4*>(q.dgamma + (int64_t)b * q.ld_dparam + h) = make_float4(dy.x * xn.x, dy.y * xn.y, dy.z * xn.z, dy.w * xn.w);
+    *reinterpret_cast<float4*>(q.dbeta + (int64_t)b * q.ld_dparam + h) = dy;
+    d = make_float4(dy.x * g.x, dy.y * g.y, dy.z * g.z, dy.w * g.w);
+    s1 = (d.x + d.y) + (d.z + d.w);
+    s2 = (d.x * xn.x + d.y * xn.y) + (d.z * xn.z + d.w * xn.w);
+  }
+  s1 = block_sum(s1, red) / (float)H;
+  s2 = block_sum(s2, red) / (float)H;
+  if (!act) return;
+  float4 r2s = r2[0];
+#pragma unroll
+  for (int s_ = 1; s_ < S2; ++s_) r2s = f4add(r2s, r2[s_]);
+  const float dxl[4] = {rstd * (d.x - s1 - xn.x * s2), rstd * (d.y - s1 - xn.y * s2), rstd * (d.z - s1 - xn.z * s2), rstd * (d.w - s1 - xn.w * s2)};
+  const float r1_[4] = {r1.x, r1.y, r1.z, r1.w}, r2_[4] = {r2s.x, r2s.y, r2s.z, r2s.w};
+  const float i_[4] = {ai.x, ai.y, ai.z, ai.w}, f_[4] = {af.x, af.y, af.z, af.w}, g_[4] = {ag.x, ag.y, ag.z, ag.w}, o_[4] = {ao.x, ao.y, ao.z, ao.w};
+  const float cn_[4] = {cn.x, cn.y, cn.z, cn.w}, cp_[4] = {cp.x, cp.y, cp.z, cp.w}, dcn_[4] = {dcn.x, dcn.y, dcn.z, dcn.w};
+  float dd[4][4], dcp[4];
+  float4 hm = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (p.drop_p > 0.f) hm = drop_mask4(p.drop_p, 1.f / (1.f - p.drop_p), p.seed, p.offset + (uint64_t)ei);
+  const float hm_[4] = {hm.x, hm.y, hm.z, hm.w};
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float dh = (dxl[u] + r1_[u] + r2_[u]) * hm_[u];   // gradient wrt the (dropped) h: LayerNorm path + recurrent paths
+    const float tc = tanhf(cn_[u]);
+    const float dc = dh * o_[u] * (1.f - tc * tc) + dcn_[u];
+    dd[0][u] = dc * g_[u] * i_[u] * (1.f - i_[u]);
+    dd[1][u] = dc * cp_[u] * f_[u] * (1.f - f_[u]);
+    dd[2][u] = dc * i_[u] * (1.f - g_[u] * g_[u]);
+    dd[3][u] = dh * tc * o_[u] * (1.f - o_[u]);
+    dcp[u] = dc * f_[u];
+  }
+  if (p.dc_prev) *reinterpret_cast<float4*>(p.dc_prev + ei) = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t col = (int64_t)k * H + h;
+    const float4 d4 = make_float4(dd[k][0], dd[k][1], dd[k][2], dd[k][3]);
+    if (p.dgates) *reinterpret_cast<float4*>(p.dgates + (int64_t)b * 4 * H + col) = d4;
+    if (q.dgates_sum) *reinterpret_cast<float4*>(q.dgates_sum + (int64_t)b * 4 * H + col) = f4add(gs[k], d4);
+    if (p.dgates2) st4any(p.dgates2, p.dgates2_dtype, (int64_t)b * p.ld_dgates2 + col, d4, vd2);
+    if (p.dgatesT) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) st_from_float(p.dgatesT, p.dgatesT_dtype, (col + u) * p.ld_dgatesT + b, dd[k][u]);
     }
   }
 }
@@ -257,7 +467,18 @@ int dlsg_lstm_cell_norm_fwd(const dlsg_lstm_cell_norm_fwd_t* q, void* stream) {
                (!p.c_prev || a16(p.c_prev)) && a16(p.c_out) && (!p.h_out || a16(p.h_out)) && a16(q->gamma) && a16(q->beta),
                "lstm_cell_norm_fwd: fp32 operands must be 16-byte aligned");
   DLSG_REQUIRE(p.offset % 4 == 0 && q->yoffset % 4 == 0, "lstm_cell_norm_fwd: dropout offsets must be multiples of 4");
-  DLSG_LAUNCH(lstm_cell_norm_fwd_kernel, p.B, fs_threads(p.H), 0, (cudaStream_t)stream, *q);
+  const int nt = fs_threads(p.H);
+  if (p.H <= 1536 && p.nsplit <= 4) {        // <= 384 threads: the register budget of the all-loads-first kernel
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (p.nsplit) {
+      case 1: DLSG_LAUNCH(lstm_cell_norm_fwd_fast<1>, p.B, nt, 0, st, *q); break;
+      case 2: DLSG_LAUNCH(lstm_cell_norm_fwd_fast<2>, p.B, nt, 0, st, *q); break;
+      case 3: DLSG_LAUNCH(lstm_cell_norm_fwd_fast<3>, p.B, nt, 0, st, *q); break;
+      default: DLSG_LAUNCH(lstm_cell_norm_fwd_fast<4>, p.B, nt, 0, st, *q); break;
+    }
+    return check_launch("lstm_cell_norm_fwd_fast");
+  }
+  DLSG_LAUNCH(lstm_cell_norm_fwd_kernel, p.B, nt, 0, (cudaStream_t)stream, *q);
   return check_launch("lstm_cell_norm_fwd_kernel");
 }
 
@@ -271,7 +492,19 @@ int dlsg_norm_lstm_cell_bwd(const dlsg_norm_lstm_cell_bwd_t* q, void* stream) {
                (!p.dgates || a16(p.dgates)) && (!q->dgates_sum || a16(q->dgates_sum)),
                "norm_lstm_cell_bwd: fp32 operands must be 16-byte aligned with row pitches multiple of 4");
   DLSG_REQUIRE(p.offset % 4 == 0 && q->yoffset % 4 == 0, "norm_lstm_cell_bwd: dropout offsets must be multiples of 4");
-  DLSG_LAUNCH(norm_lstm_cell_bwd_kernel, p.B, fs_threads(p.H), 0, (cudaStream_t)stream, *q);
+  const int nt = fs_threads(p.H);
+  const int ns = (p.dh2 && p.dh2_nsplit > 1) ? p.dh2_nsplit : 1;
+  if (p.H <= 1536 && ns <= 4) {
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (ns) {
+      case 1: DLSG_LAUNCH(norm_lstm_cell_bwd_fast<1>, p.B, nt, 0, st, *q); break;
+      case 2: DLSG_LAUNCH(norm_lstm_cell_bwd_fast<2>, p.B, nt, 0, st, *q); break;
+      case 3: DLSG_LAUNCH(norm_lstm_cell_bwd_fast<3>, p.B, nt, 0, st, *q); break;
+      default: DLSG_LAUNCH(norm_lstm_cell_bwd_fast<4>, p.B, nt, 0, st, *q); break;
+    }
+    return check_launch("norm_lstm_cell_bwd_fast");
+  }
+  DLSG_LAUNCH(norm_lstm_cell_bwd_kernel, p.B, nt, 0, (cudaStream_t)stream, *q);
   return check_launch("norm_lstm_cell_bwd_kernel");
 }
 

@@ -79,3 +79,25 @@ timeit('attn2_fwd', lambda: be.attn2_fwd(Kp, Vp, b.q32[i], b.alpha[i], b.co[i], 
 drops = ((0.3, 11, 0), (0.1, 11, 1 << 32), (0.3, 11, 2 << 32), None)
 timeit('whole step (dependent chain, dropout)', lambda: core.step(b, i, j, Kp, Vp, Gq, 1, drops, lang_y=Dall[:, i]))
 timeit('whole step (dependent chain, no dropout)', lambda: core.step(b, i, j, Kp, Vp, Gq, 1, lang_y=Dall[:, i]))
+
+# ---- marginal cost of each launch inside the dependent chain (what the 26-step loop actually pays): the chain with one member
+# removed; and the pure launch-to-launch period of a trivial dependent kernel
+scale = 1.0 / math.sqrt(H)
+g_q = lambda: be.gemm(b.Xq[i], pk['Wq'], b.gq[:, i] if b.Sq > 1 else b.gq[0, i], splitk=b.Sq)
+c_q = lambda: be.lstm_cell_norm_fwd(b.gq[:, i], b.cq[i], b.cq[j], lnq_w, lnq_b, b.q32[i], h_out=b.qh[i], row_bias=Gq,
+                                    h2=b.Xq[j][:, oQ:oQ + Hq], y2=b.Xl[i][:, oq:oq + Hq], stats=b.statq[i])
+a_2 = lambda: be.attn2_fwd(Kp, Vp, b.q32[i], b.alpha[i], b.co[i], scale, 1)
+g_l = lambda: be.gemm(b.Xl[i], pk['Wl'], b.gl[:, i] if b.Sl > 1 else b.gl[0, i], splitk=b.Sl)
+c_l = lambda: be.lstm_cell_norm_fwd(b.gl[:, i], b.cl[i], b.cl[j], lnl_w, lnl_b, Dall[:, i], h_out=b.lh[j], bias=pk['bl'],
+                                    h2=b.Xq[j][:, :Hd], h3=b.Xl[j][:, ol:ol + Hd], stats=b.statl[i], post_tanh=True)
+tiny = torch.zeros(256, device=dev)
+chains = {'chain: gemm_q, cell_q, attn2, gemm_l, cell_l (separate launches)': [g_q, c_q, a_2, g_l, c_l],
+          'chain without cell_q': [g_q, a_2, g_l, c_l],
+          'chain without cell_l': [g_q, c_q, a_2, g_l],
+          'chain without attn2': [g_q, c_q, g_l, c_l],
+          'chain: the two GEMMs only': [g_q, g_l],
+          'chain: gemm_q only': [g_q],
+          'chain: gemm_l only': [g_l],
+          'chain: 5 trivial dependent kernels (axpby on 256 floats)': [lambda: be.axpby(tiny, 1.0, tiny, 0.5)] * 5}
+for name, fns in chains.items():
+    timeit(name, lambda: [f() for f in fns], reps=24)
