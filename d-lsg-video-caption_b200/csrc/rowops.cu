@@ -501,6 +501,120 @@ lstm_cell_fwd_kernel(const dlsg_lstm_cell_fwd_t p) {
   }
 }
 
+// ---- vectorised variants for the recurrent loops (BiLSTM of EncoderVisual, the critic's LSTM): 4 hidden units per thread,
+// split counts as template parameters, every 128-bit load issued before its first use (the scalar kernels sum a run-time
+// number of partials through one or two registers, i.e. one L2 round trip after the other).
+__device__ __forceinline__ float4 ldf4(const float* q) { return *reinterpret_cast<const float4*>(q); }
+__device__ __forceinline__ float4 addf4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ void st4dt(void* base, int dt, int64_t off, float4 v) {      // off % 4 == 0, base aligned (host-checked)
+  if (dt == DLSG_F32) { *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off) = v; return; }
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + off) = u;
+}
+
+template <int S>
+__global__ void __launch_bounds__(256)
+lstm_cell_fwd_fast(const dlsg_lstm_cell_fwd_t p) {
+  pdl_prologue();
+  const int H = p.H, H4 = H >> 2;
+  const int64_t e4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e4 >= (int64_t)p.B * H4) return;
+  const int b = (int)(e4 / H4), h = (int)(e4 % H4) * 4;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 part[4][S], rb[4], bs[4], cp = z4;
+  const float* g0p = p.gates + (int64_t)b * 4 * H + h;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int s_ = 0; s_ < S; ++s_) part[k][s_] = ldf4(g0p + (int64_t)k * H + (int64_t)s_ * p.stride_split);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    rb[k] = p.row_bias ? ldf4(p.row_bias + (int64_t)b * p.ld_row_bias + (int64_t)k * H + h) : z4;
+    bs[k] = p.bias ? ldf4(p.bias + k * H + h) : z4;
+  }
+  const int64_t ei = (int64_t)b * H + h;
+  if (p.c_prev) cp = ldf4(p.c_prev + ei);
+  float g[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float4 v = addf4(rb[k], bs[k]);
+#pragma unroll
+    for (int s_ = 0; s_ < S; ++s_) v = addf4(v, part[k][s_]);
+    g[k][0] = v.x; g[k][1] = v.y; g[k][2] = v.z; g[k][3] = v.w;
+  }
+  const float cp_[4] = {cp.x, cp.y, cp.z, cp.w};
+  float ai[4], af[4], ag[4], ao[4], cc[4], hh[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    ai[u] = sigmoidf_(g[0][u]); af[u] = sigmoidf_(g[1][u]); ag[u] = tanhf(g[2][u]); ao[u] = sigmoidf_(g[3][u]);
+    cc[u] = af[u] * cp_[u] + ai[u] * ag[u];
+    hh[u] = ao[u] * tanhf(cc[u]);
+    if (p.drop_p > 0.f) hh[u] *= drop_scale(p.drop_p, p.seed, p.offset + (uint64_t)(ei + u));
+  }
+  float* g0 = p.gates + (int64_t)b * 4 * H + h;
+  *reinterpret_cast<float4*>(g0) = make_float4(ai[0], ai[1], ai[2], ai[3]);
+  *reinterpret_cast<float4*>(g0 + H) = make_float4(af[0], af[1], af[2], af[3]);
+  *reinterpret_cast<float4*>(g0 + 2 * (int64_t)H) = make_float4(ag[0], ag[1], ag[2], ag[3]);
+  *reinterpret_cast<float4*>(g0 + 3 * (int64_t)H) = make_float4(ao[0], ao[1], ao[2], ao[3]);
+  *reinterpret_cast<float4*>(p.c_out + ei) = make_float4(cc[0], cc[1], cc[2], cc[3]);
+  const float4 h4 = make_float4(hh[0], hh[1], hh[2], hh[3]);
+  if (p.h_out) *reinterpret_cast<float4*>(p.h_out + ei) = h4;
+  if (p.h2) st4dt(p.h2, p.h2_dtype, (int64_t)b * p.ldh2 + h, h4);
+  if (p.h3) st4dt(p.h3, p.h3_dtype, (int64_t)b * p.ldh3 + h, h4);
+}
+
+template <int S2>
+__global__ void __launch_bounds__(256)
+lstm_cell_bwd_fast(const dlsg_lstm_cell_bwd_t p) {
+  pdl_prologue();
+  const int H = p.H, H4 = H >> 2;
+  const int64_t e4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e4 >= (int64_t)p.B * H4) return;
+  const int b = (int)(e4 / H4), h = (int)(e4 % H4) * 4;
+  const int64_t ei = (int64_t)b * H + h, g0 = (int64_t)b * 4 * H + h;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 ai = ldf4(p.acts + g0), af = ldf4(p.acts + g0 + H), ag = ldf4(p.acts + g0 + 2 * (int64_t)H), ao = ldf4(p.acts + g0 + 3 * (int64_t)H);
+  const float4 cn = ldf4(p.c_new + ei);
+  const float4 r1 = ldf4(p.dh + (int64_t)b * p.lddh + h);
+  float4 r2[S2], cp = z4, dcn = z4;
+#pragma unroll
+  for (int s_ = 0; s_ < S2; ++s_) r2[s_] = p.dh2 ? ldf4(p.dh2 + (int64_t)b * p.lddh2 + h + (int64_t)s_ * p.dh2_stride_split) : z4;
+  if (p.c_prev) cp = ldf4(p.c_prev + ei);
+  if (p.dc_next) dcn = ldf4(p.dc_next + ei);
+  float4 r = r1;
+#pragma unroll
+  for (int s_ = 0; s_ < S2; ++s_) r = addf4(r, r2[s_]);
+  const float dh_[4] = {r.x, r.y, r.z, r.w};
+  const float i_[4] = {ai.x, ai.y, ai.z, ai.w}, f_[4] = {af.x, af.y, af.z, af.w}, g_[4] = {ag.x, ag.y, ag.z, ag.w}, o_[4] = {ao.x, ao.y, ao.z, ao.w};
+  const float cn_[4] = {cn.x, cn.y, cn.z, cn.w}, cp_[4] = {cp.x, cp.y, cp.z, cp.w}, dcn_[4] = {dcn.x, dcn.y, dcn.z, dcn.w};
+  float d[4][4], dcp[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    float dh = dh_[u];
+    if (p.drop_p > 0.f) dh *= drop_scale(p.drop_p, p.seed, p.offset + (uint64_t)(ei + u));
+    const float tc = tanhf(cn_[u]);
+    const float dc = dh * o_[u] * (1.f - tc * tc) + dcn_[u];
+    d[0][u] = dc * g_[u] * i_[u] * (1.f - i_[u]);
+    d[1][u] = dc * cp_[u] * f_[u] * (1.f - f_[u]);
+    d[2][u] = dc * i_[u] * (1.f - g_[u] * g_[u]);
+    d[3][u] = dh * tc * o_[u] * (1.f - o_[u]);
+    dcp[u] = dc * f_[u];
+  }
+  if (p.dc_prev) *reinterpret_cast<float4*>(p.dc_prev + ei) = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t col = (int64_t)k * H + h;
+    const float4 d4 = make_float4(d[k][0], d[k][1], d[k][2], d[k][3]);
+    if (p.dgates) *reinterpret_cast<float4*>(p.dgates + (int64_t)b * 4 * H + col) = d4;
+    if (p.dgates2) st4dt(p.dgates2, p.dgates2_dtype, (int64_t)b * p.ld_dgates2 + col, d4);
+    if (p.dgatesT) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) st_from_float(p.dgatesT, p.dgatesT_dtype, (col + u) * p.ld_dgatesT + b, d[k][u]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 lstm_cell_bwd_kernel(const dlsg_lstm_cell_bwd_t p) {
   pdl_prologue();
@@ -1085,11 +1199,42 @@ int dlsg_norm_bwd2(const dlsg_norm_bwd2_t* p, void* stream) {
 
 int dlsg_lstm_cell_fwd(const dlsg_lstm_cell_fwd_t* p, void* stream) {
   DLSG_REQUIRE(p->B > 0 && p->H > 0 && p->nsplit >= 1, "lstm_cell_fwd: bad shape");
+  auto a16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  auto okdt = [&](const void* q, int dt, int64_t ld) { return !q || ((ld % 4 == 0) && (reinterpret_cast<uintptr_t>(q) % (dt == DLSG_F32 ? 16 : 8)) == 0); };
+  if (p->H % 4 == 0 && p->nsplit <= 4 && a16(p->gates) && p->stride_split % 4 == 0 && (!p->row_bias || (a16(p->row_bias) && p->ld_row_bias % 4 == 0)) &&
+      (!p->bias || a16(p->bias)) && (!p->c_prev || a16(p->c_prev)) && a16(p->c_out) && (!p->h_out || a16(p->h_out)) &&
+      okdt(p->h2, p->h2_dtype, p->ldh2) && okdt(p->h3, p->h3_dtype, p->ldh3)) {
+    const unsigned nb = (unsigned)(((int64_t)p->B * (p->H / 4) + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (p->nsplit) {
+      case 1: DLSG_LAUNCH(lstm_cell_fwd_fast<1>, nb, 256, 0, st, *p); break;
+      case 2: DLSG_LAUNCH(lstm_cell_fwd_fast<2>, nb, 256, 0, st, *p); break;
+      case 3: DLSG_LAUNCH(lstm_cell_fwd_fast<3>, nb, 256, 0, st, *p); break;
+      default: DLSG_LAUNCH(lstm_cell_fwd_fast<4>, nb, 256, 0, st, *p); break;
+    }
+    return check_launch("lstm_cell_fwd_fast");
+  }
   DLSG_LAUNCH(lstm_cell_fwd_kernel, ew_blocks((int64_t)p->B * p->H), 256, 0, (cudaStream_t)stream, *p);
   return check_launch("lstm_cell_fwd_kernel");
 }
 int dlsg_lstm_cell_bwd(const dlsg_lstm_cell_bwd_t* p, void* stream) {
   DLSG_REQUIRE(p->B > 0 && p->H > 0, "lstm_cell_bwd: bad shape");
+  auto a16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const int ns = p->dh2 ? (p->dh2_nsplit > 1 ? p->dh2_nsplit : 1) : 1;
+  if (p->H % 4 == 0 && ns <= 4 && a16(p->acts) && a16(p->c_new) && p->dh && a16(p->dh) && p->lddh % 4 == 0 &&
+      (!p->dh2 || (a16(p->dh2) && p->lddh2 % 4 == 0 && p->dh2_stride_split % 4 == 0)) && (!p->c_prev || a16(p->c_prev)) &&
+      (!p->dc_next || a16(p->dc_next)) && (!p->dc_prev || a16(p->dc_prev)) && (!p->dgates || a16(p->dgates)) &&
+      (!p->dgates2 || (p->ld_dgates2 % 4 == 0 && (reinterpret_cast<uintptr_t>(p->dgates2) % (p->dgates2_dtype == DLSG_F32 ? 16 : 8)) == 0))) {
+    const unsigned nb = (unsigned)(((int64_t)p->B * (p->H / 4) + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (ns) {
+      case 1: DLSG_LAUNCH(lstm_cell_bwd_fast<1>, nb, 256, 0, st, *p); break;
+      case 2: DLSG_LAUNCH(lstm_cell_bwd_fast<2>, nb, 256, 0, st, *p); break;
+      case 3: DLSG_LAUNCH(lstm_cell_bwd_fast<3>, nb, 256, 0, st, *p); break;
+      default: DLSG_LAUNCH(lstm_cell_bwd_fast<4>, nb, 256, 0, st, *p); break;
+    }
+    return check_launch("lstm_cell_bwd_fast");
+  }
   DLSG_LAUNCH(lstm_cell_bwd_kernel, ew_blocks((int64_t)p->B * p->H), 256, 0, (cudaStream_t)stream, *p);
   return check_launch("lstm_cell_bwd_kernel");
 }
