@@ -131,7 +131,27 @@ class Attn2BwdT(C.Structure):
                 ('drop_p', f32), ('_pad1', i32), ('seed', u64), ('offset', u64), ('offset_head_stride', u64)]
 
 
+class RegionAggFwdT(C.Structure):
+    _fields_ = [('Y', vp * 2), ('ldy', i64), ('F', vp * 2), ('ldf', i64), ('gamma', vp * 2), ('beta', vp * 2),
+                ('agg', vp * 2), ('ldagg', i64), ('U', vp * 2), ('ldu', i64),
+                ('stats', vp * 2), ('St', vp * 2), ('tconst', vp * 2),
+                ('B', i32), ('E', i32), ('T', i32), ('TR', i32), ('H', i32), ('scores_only', i32), ('scale', f32), ('_pad', i32)]
+
+
+class RegionAggBwdT(C.Structure):
+    _fields_ = [('Y', vp * 2), ('ldy', i64), ('stats', vp * 2), ('St', vp * 2), ('dSm', vp * 2),
+                ('F', vp * 2), ('ldf', i64), ('dA', vp * 2), ('ldda', i64), ('U', vp * 2), ('ldu', i64),
+                ('tcF', vp * 2), ('tcA', vp * 2), ('gamma', vp * 2), ('beta', vp * 2),
+                ('dpre', vp * 2), ('ldd', i64), ('dF', vp * 2), ('lddf', i64),
+                ('dgamma', vp * 2), ('dbeta', vp * 2), ('dbias', vp * 2), ('work', vp * 2),
+                ('B', i32), ('E', i32), ('T', i32), ('TR', i32), ('H', i32), ('_pad', i32), ('scale', f32), ('_pad2', i32)]
+
+
 SIGNATURES = {
+    'dlsg_region_aggregate_supported': (i32, [i32, i32, i32]),
+    'dlsg_region_aggregate_fwd': (i32, [C.POINTER(RegionAggFwdT), vp]),
+    'dlsg_region_aggregate_bwd_workspace': (i64, [i32, i32, i32]),
+    'dlsg_region_aggregate_bwd': (i32, [C.POINTER(RegionAggBwdT), vp]),
     'dlsg_attn2_supported': (i32, [i32, i32, i32, i32]),
     'dlsg_attn2_fwd': (i32, [C.POINTER(Attn2FwdT), vp]),
     'dlsg_attn2_bwd': (i32, [C.POINTER(Attn2BwdT), vp]),

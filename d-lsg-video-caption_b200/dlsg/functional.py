@@ -10,12 +10,16 @@ Blocks (reference file:line they replace):
 """
 import itertools
 import math
+import os
 
 import torch
 
 from . import linalg as la
 from . import ops
 from .linalg import empty, zeros, small_zeros, op, op_empty, op_zeros, mm32, flat2
+
+# DLSG_FUSED_REGION_AGG=0 keeps the unfused LayerNorm / GEMM / softmax / GEMM composition (measurement switch)
+FUSED_REGION_AGG = os.environ.get('DLSG_FUSED_REGION_AGG', '1') != '0'
 
 _seed_counter = itertools.count(1)
 
@@ -299,7 +303,10 @@ class TunBlock:
             be.gemm(Rb, Wc, Ot, bias=bc, tanh=True)
             sv.update(RbT=RbT, Ot=Ot)
         seed = next_seed()
-        for i, e in enumerate(self.encs):
+        fused = use_regions and be.region_aggregate_supported(T, TR, H, Ot.dtype) and FUSED_REGION_AGG
+        sv['fused'] = fused
+        scale = 1.0 / math.sqrt(Dr)
+        for i, e in enumerate(self.encs):          # frame vectors F = LN(tanh(visual_embed(v)))  (layer.py:176-181)
             pf = e['prefix']
             v = _c(t['visual%d' % i])
             H = t[pf + 'visual_norm.1.weight'].shape[0]
@@ -312,29 +319,51 @@ class TunBlock:
             else:
                 Fv = v2
             F = empty((B * T, H), v2)
-            Fop = op_empty((B * T,), H, v2)
+            Fop = None if (fused or not use_regions) else op_empty((B * T,), H, v2)
             stF = empty((B * T, 2), v2)
             be.norm_fwd(Fv, t[pf + 'visual_norm.1.weight'], t[pf + 'visual_norm.1.bias'], y=F, y2=Fop, stats=stF,
                         pre_tanh=True)
-            s.update(Fv=Fv, F=F, stF=stF)
+            s.update(Fv=Fv, F=F, Fop=Fop, stF=stF, scale=scale)
+            sv['enc'].append(s)
+        if fused:
+            # ONE launch for both encoders: obj_norm + scores + softmax over the T*R regions + weighted sum, Y read once
+            # (csrc/region_agg.cu); the backward recomputes the normalised rows from Y and the saved row statistics
+            S_ = sv['enc']
+            for s in S_:
+                s['agg'] = empty((B * T, H), S_[0]['F'])
+                if need_grad:
+                    s.update(U=empty((B * T, H), s['F']), stO=empty((M, 2), s['F']), St=empty((B, T, TR), s['F']),
+                             tcF=empty((B * T, 4), s['F']))
+            opt = (lambda k: [s[k] for s in S_]) if need_grad else (lambda k: None)
+            be.region_aggregate_fwd([Ot[:, i * H:(i + 1) * H] for i in range(E)], [s['F'] for s in S_],
+                                    [t[e['prefix'] + 'obj_norm.1.weight'].detach() for e in self.encs],
+                                    [t[e['prefix'] + 'obj_norm.1.bias'].detach() for e in self.encs], scale, T,
+                                    agg=[s['agg'] for s in S_], U=opt('U'), stats=opt('stO'), St=opt('St'), tconst=opt('tcF'))
+        for i, e in enumerate(self.encs):
+            pf, s = e['prefix'], sv['enc'][i]
+            F = s['F']
+            v2 = F
+            H = F.shape[1]
             if use_regions:
-                O = empty((M, H), v2, la.opdtype())
-                stO = empty((M, 2), v2)
-                be.norm_fwd(Ot[:, i * H:(i + 1) * H], t[pf + 'obj_norm.1.weight'], t[pf + 'obj_norm.1.bias'], y=O, stats=stO)
-                O3 = O.view(B, TR, H)
-                St = empty((B, T, TR), v2)                      # raw scores, transposed: (frame, object)
-                be.gemm(Fop.view(B, T, H), O3, St)
-                Sm = empty((B, T, TR), v2)
-                scale = 1.0 / math.sqrt(Dr)
-                be.softmax_fwd(St, Sm, dim=2, scale=scale)       # softmax over the T*R objects (layer.py:188 dim=1)
-                OT = op(O3.transpose(1, 2))                      # (B,H,TR) K-major over objects
-                agg = empty((B, T, H), v2)
-                be.gemm(op(Sm), OT, agg)
+                if not fused:
+                    O = empty((M, H), v2, la.opdtype())
+                    stO = empty((M, 2), v2)
+                    be.norm_fwd(Ot[:, i * H:(i + 1) * H], t[pf + 'obj_norm.1.weight'], t[pf + 'obj_norm.1.bias'], y=O, stats=stO)
+                    O3 = O.view(B, TR, H)
+                    St = empty((B, T, TR), v2)                      # raw scores, transposed: (frame, object)
+                    be.gemm(s['Fop'].view(B, T, H), O3, St)
+                    Sm = empty((B, T, TR), v2)
+                    be.softmax_fwd(St, Sm, dim=2, scale=scale)       # softmax over the T*R objects (layer.py:188 dim=1)
+                    OT = op(O3.transpose(1, 2))                      # (B,H,TR) K-major over objects
+                    agg = empty((B, T, H), v2)
+                    be.gemm(op(Sm), OT, agg)
+                    s.update(O=O, stO=stO, St=St, Sm=Sm, OT=OT, agg=agg)
+                agg = s['agg']
                 X = empty((B * T, H), v2)
                 stX = empty((B * T, 2), v2)
                 be.norm_fwd(agg.view(B * T, H), t[pf + 'obj_visual_norm.1.weight'], t[pf + 'obj_visual_norm.1.bias'],
                             y=X, res=F, stats=stX, pre_tanh=True)
-                s.update(O=O, stO=stO, St=St, Sm=Sm, OT=OT, agg=agg, X=X, stX=stX, scale=scale)
+                s.update(X=X, stX=stX)
             else:
                 X = F
                 s['X'] = X
@@ -359,7 +388,6 @@ class TunBlock:
                             y=nodes.view(B * P, H), stats=stN, pre_tanh=True, drop=dn)
                 s.update(G=G, Gs=Gs, N=N, stN=stN, dn=dn)
                 outs.append(nodes)
-            sv['enc'].append(s)
         sv['t'] = t
         return outs, sv
 
@@ -370,27 +398,27 @@ class TunBlock:
         TR, M = T * R, B * T * R
         E = len(self.encs)
         use_regions = R >= 5
+        fused = sv.get('fused', False)
         grads = {}
         dOpre = dbc = None
-        for i, e in enumerate(self.encs):
-            pf, s = e['prefix'], sv['enc'][i]
-            g = gouts[i]
+        active = [i for i in range(E) if gouts[i] is not None]
+
+        def lnp(pf, name):
+            w, b = t[pf + name + '.weight'], t[pf + name + '.bias']
+            dw, db = small_zeros(w.shape, w), small_zeros(b.shape, b)
+            grads[pf + name + '.weight'], grads[pf + name + '.bias'] = dw, db
+            return w, b, dw, db
+        dXs, dAs, dFs = {}, {}, {}
+        for i in active:                             # node pooling and obj_visual_norm backward: dA = d(agg + F)
+            pf, s = self.encs[i]['prefix'], sv['enc'][i]
+            g = _c(gouts[i])
             X = s['X']
             H = X.shape[-1]
-
-            def lnp(name):
-                w, b = t[pf + name + '.weight'], t[pf + name + '.bias']
-                dw, db = small_zeros(w.shape, w), small_zeros(b.shape, b)
-                grads[pf + name + '.weight'], grads[pf + name + '.bias'] = dw, db
-                return w, b, dw, db
-            if g is None:
-                continue
-            g = _c(g)
             if self.baseline:
                 dX = g.view(B, T, H)
             else:
                 P = self.P
-                w, b, dw, db = lnp('v2l_layer.out_norm.1')
+                w, b, dw, db = lnp(pf, 'v2l_layer.out_norm.1')
                 dN = empty((B * P, H), X)
                 be.norm_bwd(g.view(B * P, H), s['N'].view(B * P, H), w, b, s['stN'], dx=dN, dgamma=dw, dbeta=db,
                             pre_tanh=True, drop=s['dn'])
@@ -410,11 +438,47 @@ class TunBlock:
                     dth = empty(theta.shape, X)
                     be.gemm(dG.view(B * T, P).t(), X.t(), dth)
                 grads[pf + 'v2l_layer.theta'] = dth
+            dXs[i] = dX
             if use_regions:
-                w, b, dw, db = lnp('obj_visual_norm.1')
+                w, b, dw, db = lnp(pf, 'obj_visual_norm.1')
                 dA = empty((B * T, H), X)
                 be.norm_bwd(dX.view(B * T, H), s['agg'].view(B * T, H), w, b, s['stX'], dx=dA, res=s['F'], dgamma=dw,
                             dbeta=db, pre_tanh=True)
+                dAs[i] = dA
+        if use_regions and active:
+            X = sv['enc'][active[0]]['X']
+            H = X.shape[-1]
+            dOpre = empty((M, E * H), X, la.opdtype())
+            if len(active) < E:
+                dOpre.zero_()
+            dbc = small_zeros((E * H,), dOpre)
+        if use_regions and active and fused:
+            # pass 1: dSm = dA . LN(Y) (the forward kernel, scores only); pass 2: everything else, Y read once more and
+            # d(pre-activation of the region projection) written once (csrc/region_agg.cu)
+            S_ = [sv['enc'][i] for i in active]
+            Ys = [sv['Ot'][:, i * H:(i + 1) * H] for i in active]
+            lns = [lnp(self.encs[i]['prefix'], 'obj_norm.1') for i in active]
+            gam, bet = [l[0].detach() for l in lns], [l[1].detach() for l in lns]
+            dA_l = [dAs[i] for i in active]
+            dSm = [empty((B, T, TR), X) for _ in active]
+            tcA = [empty((B * T, 4), X) for _ in active]
+            be.region_aggregate_fwd(Ys, dA_l, gam, bet, S_[0]['scale'], T, St=dSm, tconst=tcA, scores_only=True)
+            nwork = be.region_aggregate_bwd_workspace(B, T, TR)
+            for i in active:
+                dFs[i] = empty((B * T, H), X)
+            be.region_aggregate_bwd(Ys, [s['stO'] for s in S_], [s['St'] for s in S_], dSm,
+                                    [s['F'] for s in S_], dA_l, [s['U'] for s in S_], [s['tcF'] for s in S_], tcA, gam, bet,
+                                    S_[0]['scale'], T, dpre=[dOpre[:, i * H:(i + 1) * H] for i in active],
+                                    dF=[dFs[i] for i in active], dgamma=[l[2] for l in lns], dbeta=[l[3] for l in lns],
+                                    dbias=[dbc[i * H:(i + 1) * H] for i in active],
+                                    work=[empty((nwork,), X, torch.uint8) for _ in active])
+        for i in active:
+            e = self.encs[i]
+            pf, s = e['prefix'], sv['enc'][i]
+            X = s['X']
+            H = X.shape[-1]
+            if use_regions and not fused:
+                dA = dAs[i]
                 dF = empty((B * T, H), X)
                 be.axpby(dA, 1.0, dF, 0.0)
                 O3 = s['O'].view(B, TR, H)
@@ -433,23 +497,18 @@ class TunBlock:
                 dO = empty((M, H), X, la.opdtype())
                 be.gemm(Ac, Bc, dO.view(B, TR, H))
                 be.gemm(op(dSt), s['OT'], dF.view(B, T, H), accum=True)
-                if dOpre is None:
-                    dOpre = empty((M, E * H), X, la.opdtype())
-                    if any(g_ is None for g_ in gouts):
-                        dOpre.zero_()
-                w, b, dw, db = lnp('obj_norm.1')
-                if dbc is None:
-                    dbc = small_zeros((E * H,), dOpre)
+                w, b, dw, db = lnp(pf, 'obj_norm.1')
                 # the region-projection bias gradient (column sums of dOpre) is accumulated by the same kernel
                 be.norm_bwd(dO, sv['Ot'][:, i * H:(i + 1) * H], w, b, s['stO'], dx=dOpre[:, i * H:(i + 1) * H], dgamma=dw,
                             dbeta=db, in_is_tanh=True, dxsum=dbc[i * H:(i + 1) * H])
+            elif use_regions:
+                dF = dFs[i]
             else:
-                dF = dX.view(B * T, H)
-            w, b, dw, db = lnp('visual_norm.1')
+                dF = dXs[i].view(B * T, H)
+            w, b, dw, db = lnp(pf, 'visual_norm.1')
             dFv = empty((B * T, H), X)
             be.norm_bwd(dF, s['Fv'], w, b, s['stF'], dx=dFv, dgamma=dw, dbeta=db, pre_tanh=True)
             if e['use_embed']:
-                wv = t[pf + 'visual_embed.weight']
                 grads[pf + 'visual_embed.weight'] = la.mm(dFv.t(), s['v2'].t())
                 dbv = small_zeros((H,), X)
                 be.colsum(dFv, dbv)

@@ -552,6 +552,102 @@ class CudaBackend:
         L.check(self.lib.dlsg_latent_psl_bwd(X.data_ptr(), theta.data_ptr(), Gs.data_ptr(), dN.data_ptr(), dX.data_ptr(),
                                              dtheta.data_ptr(), B, T, P, H, _stream()), 'latent_psl_bwd')
 
+    # ------------------------------------------------------------------ fused region -> frame aggregation (layer.py:184-192)
+    def region_aggregate_supported(self, T, TR, H, dtype):
+        return dtype == torch.bfloat16 and bool(self.lib.dlsg_region_aggregate_supported(T, TR, H))
+
+    @staticmethod
+    def _ra_set(field, tensors, check=None):
+        for i, t in enumerate(tensors):
+            if t is not None:
+                if check is not None:
+                    check(t)
+                field[i] = t.data_ptr()
+
+    def region_aggregate_fwd(self, Y, F, gamma, beta, scale, T, agg=None, U=None, stats=None, St=None, tconst=None, scores_only=False):
+        """Lists (one entry per encoder, E <= 2).  Y[e]: bf16 (B*TR, H) view (unit inner stride); F[e]: fp32 (B*T, H);
+        outputs (optional lists) agg / U (B*T, H) fp32, stats (B*TR, 2), St (B, T, TR) raw scores, tconst (B*T, 4) =
+        [sum_h bf16(F*gamma), F.beta, m, 1/l] (softmax weights = exp(scale*St - m) / l).
+        scores_only: only St = F . LN(Y) and the first two columns of tconst."""
+        E = len(Y)
+        p = L.RegionAggFwdT()
+        rowsY, H, ldy = _rows2d(Y[0])
+        rowsF, _, ldf = _rows2d(F[0])
+        B = rowsF // T
+        TR = rowsY // B
+        self._ck(Y[0])
+        assert Y[0].dtype == torch.bfloat16 and F[0].dtype == torch.float32
+
+        def same(ref_ld):
+            def f(t):
+                assert t.stride(-1) == 1 and _rows2d(t)[2] == ref_ld, 'encoders must share the row pitch'
+            return f
+
+        def contig(t):
+            assert t.is_contiguous() and t.dtype == torch.float32
+        self._ra_set(p.Y, Y, same(ldy))
+        self._ra_set(p.F, F, same(ldf))
+        self._ra_set(p.gamma, gamma, contig)
+        self._ra_set(p.beta, beta, contig)
+        p.ldy, p.ldf = ldy, ldf
+        if agg is not None:
+            p.ldagg = _rows2d(agg[0])[2]
+            self._ra_set(p.agg, agg, same(p.ldagg))
+        if U is not None:
+            p.ldu = _rows2d(U[0])[2]
+            self._ra_set(p.U, U, same(p.ldu))
+        for name, lst in (('stats', stats), ('St', St), ('tconst', tconst)):
+            if lst is not None:
+                self._ra_set(getattr(p, name), lst, contig)
+        p.B, p.E, p.T, p.TR, p.H, p.scores_only, p.scale = B, E, T, TR, H, int(scores_only), float(scale)
+        self.launches += 1
+        L.check(self.lib.dlsg_region_aggregate_fwd(C.byref(p), _stream()), 'dlsg_region_aggregate_fwd')
+
+    def region_aggregate_bwd_workspace(self, B, T, TR):
+        return int(self.lib.dlsg_region_aggregate_bwd_workspace(B, T, TR))
+
+    def region_aggregate_bwd(self, Y, stats, St, dSm, F, dA, U, tcF, tcA, gamma, beta, scale, T, dpre, dF, dgamma, dbeta, dbias=None,
+                             work=None):
+        """Second backward pass (after region_aggregate_fwd(scores_only=True, F=dA) produced dSm, tcA); work[e]: uint8 scratch
+        of region_aggregate_bwd_workspace(B, T, TR) bytes.
+        dpre[e]: bf16 (B*TR, H) view written; dF[e] (B*T, H) fp32 written (= dA + score-path gradient); dgamma / dbeta /
+        dbias[e] (H) fp32 accumulated (zero them first)."""
+        E = len(Y)
+        p = L.RegionAggBwdT()
+        rowsY, H, ldy = _rows2d(Y[0])
+        rowsF, _, ldf = _rows2d(F[0])
+        B = rowsF // T
+        TR = rowsY // B
+        self._ck(Y[0])
+        assert Y[0].dtype == torch.bfloat16 and dpre[0].dtype == torch.bfloat16
+
+        def same(ref_ld):
+            def f(t):
+                assert t.stride(-1) == 1 and _rows2d(t)[2] == ref_ld, 'encoders must share the row pitch'
+            return f
+
+        def contig(t):
+            assert t.is_contiguous() and t.dtype == torch.float32
+        p.ldy, p.ldf, p.ldda, p.ldu = ldy, ldf, _rows2d(dA[0])[2], _rows2d(U[0])[2]
+        p.ldd, p.lddf = _rows2d(dpre[0])[2], _rows2d(dF[0])[2]
+        self._ra_set(p.Y, Y, same(ldy))
+        self._ra_set(p.F, F, same(ldf))
+        self._ra_set(p.dA, dA, same(p.ldda))
+        self._ra_set(p.U, U, same(p.ldu))
+        self._ra_set(p.dpre, dpre, same(p.ldd))
+        self._ra_set(p.dF, dF, same(p.lddf))
+        for name, lst in (('stats', stats), ('St', St), ('dSm', dSm), ('tcF', tcF), ('tcA', tcA), ('gamma', gamma),
+                          ('beta', beta), ('dgamma', dgamma), ('dbeta', dbeta), ('dbias', dbias)):
+            if lst is not None:
+                self._ra_set(getattr(p, name), lst, contig)
+        need = self.region_aggregate_bwd_workspace(B, T, TR)
+        for i, w in enumerate(work):
+            assert w.dtype == torch.uint8 and w.is_contiguous() and w.numel() >= need
+            p.work[i] = w.data_ptr()
+        p.B, p.E, p.T, p.TR, p.H, p.scale = B, E, T, TR, H, float(scale)
+        self.launches += 2
+        L.check(self.lib.dlsg_region_aggregate_bwd(C.byref(p), _stream()), 'dlsg_region_aggregate_bwd')
+
     # ------------------------------------------------------------------ embedding / small
     def embedding_gather(self, table, ids, out=None, out2=None, drop=None):
         """ids: 1-D int64 view (any stride). out/out2: (rows, W) views."""

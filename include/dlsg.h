@@ -276,6 +276,50 @@ int dlsg_latent_psl_fwd(const float* X, const float* theta, float* Gs, float* N,
 int dlsg_latent_psl_bwd(const float* X, const float* theta, const float* Gs, const float* dN, float* dX, float* dtheta,
                         int32_t B, int32_t T, int32_t P, int32_t H, void* stream);
 
+/* ---- region -> frame aggregation of EncoderVisualGraphTUN (models/layer.py:184-192), fused -------------------------------
+ * Replaces, per encoder e (E <= 2, both in one launch): obj_norm LayerNorm over the tanh'ed region projection Y, the
+ * frame x region score product, the softmax over ALL T*R regions of a clip (layer.py:188, dim=1) and the weighted sum.
+ *   O_r = LN(Y_r) ; S_tr = F_t . O_r ; A = softmax_r(scale * S) ; U_t = sum_r A_tr xhat_r ; agg_t = gamma o U_t + beta
+ * fwd : one CTA per (clip, encoder) streams the (T*R, H) bf16 tile of Y ONCE (bulk copies into a 2-stage shared-memory
+ *       ring), LayerNorm folded into the two mma.sync products, online softmax over the 32-row tiles.
+ *       scores_only != 0: only St (= F . O, any fp32 F, e.g. the aggregate's gradient) and tconst are produced.
+ * bwd : (after a scores_only pass with F := dA that yields dSm = dA . O and tcA) a small kernel turns the (T, T*R) matrices
+ *       into per-tile mma operands and row scalars (softmax backward, closed-form LayerNorm-backward statistics), then one
+ *       CTA per (256-column slice, clip, encoder) re-reads its slice of Y once and writes d(pre-activation of the region projection) as bf16, with the
+ *       softmax backward, the LayerNorm backward (its row reductions in closed form from the T x T*R matrices) and the
+ *       tanh derivative fused; dF = dA + gamma o V (the residual path of layer.py:192 included), obj_norm parameter
+ *       gradients and the projection's bias gradient are ACCUMULATED with fp32 atomics.
+ * Supported: H == 1024, T <= 26, bf16 Y with 16-byte aligned rows (dlsg_region_aggregate_supported).              */
+typedef struct {
+  const void* Y[2]; int64_t ldy;            /* bf16 (B*TR, H) per encoder, row pitch in elements                              */
+  const float* F[2]; int64_t ldf;           /* fp32 (B*T, H)                                                                  */
+  const float* gamma[2]; const float* beta[2];
+  float* agg[2]; int64_t ldagg;             /* out fp32 (B*T, H) (unused when scores_only)                                    */
+  float* U[2]; int64_t ldu;                 /* out, optional: aggregate before the affine part (the backward's dgamma needs it) */
+  float* stats[2];                          /* out, optional (B*TR, 2): mean, rstd of every region row                        */
+  float* St[2];                             /* out, optional (B, T, TR): raw scores F_t . O_r                                 */
+  float* tconst[2];                         /* out, optional (B*T, 4): sum_h bf16(F*gamma), F.beta, and (full pass only) the
+                                               softmax normalisers m_t, 1/l_t: A_tr = exp(scale S_tr - m_t) / l_t            */
+  int32_t B, E, T, TR, H, scores_only; float scale; int32_t _pad;
+} dlsg_region_agg_fwd_t;
+typedef struct {
+  const void* Y[2]; int64_t ldy;
+  const float* stats[2];
+  const float* St[2]; const float* dSm[2];                         /* (B, T, TR) fp32: raw scores, dA . O                    */
+  const float* F[2]; int64_t ldf; const float* dA[2]; int64_t ldda; const float* U[2]; int64_t ldu;
+  const float* tcF[2]; const float* tcA[2];                        /* tconst of the forward (F) and of the dA scores pass    */
+  const float* gamma[2]; const float* beta[2];
+  void* dpre[2]; int64_t ldd;                                      /* out bf16 (B*TR, H)                                     */
+  float* dF[2]; int64_t lddf;                                      /* out fp32 (B*T, H) = dA + gamma o V                     */
+  float* dgamma[2]; float* dbeta[2]; float* dbias[2];              /* (H) fp32, ACCUMULATED                                  */
+  void* work[2];                                                   /* scratch, dlsg_region_aggregate_bwd_workspace() bytes each */
+  int32_t B, E, T, TR, H, _pad; float scale; int32_t _pad2;
+} dlsg_region_agg_bwd_t;
+int dlsg_region_aggregate_supported(int32_t T, int32_t TR, int32_t H);
+int dlsg_region_aggregate_fwd(const dlsg_region_agg_fwd_t* p, void* stream);
+int64_t dlsg_region_aggregate_bwd_workspace(int32_t B, int32_t T, int32_t TR);   /* bytes per encoder, 16-byte aligned base */
+int dlsg_region_aggregate_bwd(const dlsg_region_agg_bwd_t* p, void* stream);       /* two launches: prep + streaming pass */
+
 /* ---- embedding (layer.py:421,438,535) and small reductions ---------------------------------- */
 int dlsg_embedding_gather(const float* table, const int64_t* ids, int64_t ld_ids, int32_t rows, int32_t W,
                           void* out, int out_dtype, int64_t ldo, void* out2, int out2_dtype, int64_t ldo2,

@@ -384,6 +384,81 @@ class CpuEmulBackend:
             dKW[h].add_(torch.einsum('rp,rk->rpk', dl, q))
             dVW[h].add_(torch.einsum('rp,rv->rpv', a, dc))
 
+    # ---- fused region -> frame aggregation (csrc/region_agg.cu): plain composition of the same algebra
+    @staticmethod
+    def region_aggregate_supported(T, TR, H, dtype):
+        return dtype == torch.bfloat16 and H == 1024 and 1 <= T <= 26
+
+    @staticmethod
+    def _bfr(x):
+        return x.to(torch.bfloat16).float()
+
+    def region_aggregate_fwd(self, Y, F, gamma, beta, scale, T, agg=None, U=None, stats=None, St=None, tconst=None, scores_only=False):
+        self.launches += 1
+        for e in range(len(Y)):
+            y = _f(Y[e])
+            H = y.shape[1]
+            B = F[e].shape[0] // T
+            TR = y.shape[0] // B
+            mu = y.mean(1, keepdim=True)
+            var = ((y * y).mean(1, keepdim=True) - mu * mu).clamp_min(0)
+            rstd = torch.rsqrt(var + 1e-5)
+            xh = ((y - mu) * rstd).view(B, TR, H)
+            f = _f(F[e])
+            fg = self._bfr(f * gamma[e])                                   # the kernel's bf16 A operand
+            S = fg.view(B, T, H) @ xh.transpose(1, 2) + (f @ beta[e]).view(B, T, 1)
+            if stats is not None:
+                stats[e].copy_(torch.cat([mu, rstd], 1))
+            if St is not None:
+                St[e].copy_(S)
+            tc = torch.zeros(B * T, 4)
+            tc[:, 0] = fg.sum(1)
+            tc[:, 1] = f @ beta[e]
+            if not scores_only:
+                m = (S * scale).max(-1).values
+                tc[:, 2] = m.reshape(-1)
+                tc[:, 3] = (1.0 / torch.exp(S * scale - m.unsqueeze(-1)).sum(-1)).reshape(-1)
+            if tconst is not None:
+                tconst[e].copy_(tc)
+            if scores_only:
+                continue
+            A = torch.softmax(S * scale, dim=2)
+            u = (A @ xh).view(B * T, H)
+            if U is not None:
+                U[e].copy_(u)
+            agg[e].copy_(u * gamma[e] + beta[e])
+
+    @staticmethod
+    def region_aggregate_bwd_workspace(B, T, TR):
+        return 16
+
+    def region_aggregate_bwd(self, Y, stats, St, dSm, F, dA, U, tcF, tcA, gamma, beta, scale, T, dpre, dF, dgamma, dbeta, dbias=None,
+                             work=None):
+        self.launches += 2
+        for e in range(len(Y)):
+            y = _f(Y[e])
+            H = y.shape[1]
+            B = F[e].shape[0] // T
+            TR = y.shape[0] // B
+            mu, rstd = stats[e][:, 0:1], stats[e][:, 1:2]
+            xh = ((y - mu) * rstd).view(B, TR, H)
+            A = torch.exp(St[e] * scale - tcF[e][:, 2].view(B, T, 1)) * tcF[e][:, 3].view(B, T, 1)
+            c = (A * dSm[e]).sum(-1, keepdim=True)
+            dS = scale * A * (dSm[e] - c)                                  # softmax backward
+            dAg = self._bfr(_f(dA[e]) * gamma[e]).view(B, T, H)
+            Fg = self._bfr(_f(F[e]) * gamma[e]).view(B, T, H)
+            dxh = self._bfr(A).transpose(1, 2) @ dAg + self._bfr(dS).transpose(1, 2) @ Fg        # (B,TR,H)
+            a = dxh.mean(-1, keepdim=True)
+            b = (dxh * xh).mean(-1, keepdim=True)
+            dp = rstd.view(B, TR, 1) * (dxh - a - xh * b) * (1 - y.view(B, TR, H) ** 2)
+            dpre[e].copy_(dp.view(B * TR, H))
+            V = dS @ xh                                                    # (B,T,H)
+            dF[e].copy_(_f(dA[e]) + (V * gamma[e]).view(B * T, H))
+            dgamma[e].add_((_f(dA[e]) * U[e] + _f(F[e]) * V.view(B * T, H)).sum(0))
+            dbeta[e].add_(_f(dA[e]).sum(0))
+            if dbias is not None:
+                dbias[e].add_(dp.view(B * TR, H).sum(0))
+
     @staticmethod
     def latent_psl_supported(T, P, H):
         return P <= 8 and T <= 32 and H % 4 == 0

@@ -37,9 +37,9 @@ def test_struct_sizes_match_c_layout():
     import subprocess
     import tempfile
     from dlsg import _lib
-    src = '#include <stdio.h>\n#include "dlsg.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
+    src = '#include <stdio.h>\n#include "dlsg.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
           'sizeof(dlsg_gemm_t),sizeof(dlsg_norm_fwd_t),sizeof(dlsg_norm_bwd_t),sizeof(dlsg_lstm_cell_fwd_t),' \
-          'sizeof(dlsg_lstm_cell_bwd_t),sizeof(dlsg_softmax_t),sizeof(dlsg_node_attn_fwd_t),sizeof(dlsg_node_attn_bwd_t),sizeof(dlsg_lstm_cell_bwd2_t),sizeof(dlsg_seg_t),sizeof(dlsg_norm_bwd2_t),sizeof(dlsg_adam_seg_t));return 0;}\n'
+          'sizeof(dlsg_lstm_cell_bwd_t),sizeof(dlsg_softmax_t),sizeof(dlsg_node_attn_fwd_t),sizeof(dlsg_node_attn_bwd_t),sizeof(dlsg_lstm_cell_bwd2_t),sizeof(dlsg_seg_t),sizeof(dlsg_norm_bwd2_t),sizeof(dlsg_adam_seg_t),sizeof(dlsg_region_agg_fwd_t),sizeof(dlsg_region_agg_bwd_t));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, 'p.c')
         open(c, 'w').write(src)
@@ -47,7 +47,8 @@ def test_struct_sizes_match_c_layout():
         subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), c, '-o', exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     ours = [ctypes.sizeof(s) for s in (_lib.GemmT, _lib.NormFwdT, _lib.NormBwdT, _lib.CellFwdT, _lib.CellBwdT, _lib.SoftmaxT,
-                                       _lib.AttnFwdT, _lib.AttnBwdT, _lib.CellBwd2T, _lib.SegT, _lib.NormBwd2T, _lib.AdamSegT)]
+                                       _lib.AttnFwdT, _lib.AttnBwdT, _lib.CellBwd2T, _lib.SegT, _lib.NormBwd2T, _lib.AdamSegT,
+                                       _lib.RegionAggFwdT, _lib.RegionAggBwdT)]
     assert ours == sizes, (ours, sizes)
 
 

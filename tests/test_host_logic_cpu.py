@@ -428,3 +428,57 @@ def test_edge_shapes_match_oracle(case):
             else:
                 want = O.decoder_beam(sd, 'decoder', robj, rmot, args.max_words, beam)[0]
             assert torch.equal(got, want), (case, beam)
+
+
+@pytest.mark.parametrize('active', [(0, 1), (1,)])
+def test_tunblock_fused_region_aggregate_equals_unfused_composition(active):
+    """TunBlock at the real node width (H=1024, the only width the fused aggregation kernels take): the fused path
+    (region_aggregate_fwd / scores pass / region_aggregate_bwd, emulated from the kernels' own algebra: LayerNorm folded
+    into the products, closed-form LayerNorm-backward row statistics, dgamma / dbeta from U and V) against the unfused
+    LayerNorm -> scores GEMM -> softmax -> aggregation GEMM composition, outputs and every gradient; also with one
+    encoder's output unused (CapBaselineModel: that encoder's gradients stay None)."""
+    la.set_precision('bf16')
+    B, T, R, Dr, H, P, Dv = 2, 26, 6, 64, 1024, 3, 48
+    g = torch.Generator().manual_seed(5)
+    rnd = lambda *s, sc=1.0: torch.randn(*s, generator=g) * sc
+    encs = [{'prefix': 'a.', 'use_embed': True}, {'prefix': 'b.', 'use_embed': True}]
+    base = {'regions': rnd(B, T, R, Dr), 'visual0': rnd(B, T, Dv), 'visual1': rnd(B, T, Dv)}
+    for e in encs:
+        pf = e['prefix']
+        base[pf + 'obj_embed.weight'] = rnd(H, Dr, sc=0.2)
+        base[pf + 'obj_embed.bias'] = rnd(H, sc=0.1)
+        base[pf + 'visual_embed.weight'] = rnd(H, Dv, sc=0.2)
+        base[pf + 'visual_embed.bias'] = rnd(H, sc=0.1)
+        for n in ('visual_norm.1', 'obj_norm.1', 'obj_visual_norm.1', 'v2l_layer.out_norm.1'):
+            base[pf + n + '.weight'] = 1 + 0.1 * rnd(H)
+            base[pf + n + '.bias'] = 0.1 * rnd(H)
+        base[pf + 'v2l_layer.theta'] = rnd(P, H, sc=0.05)
+    gouts = [rnd(B, P, H), rnd(B, P, H)]
+    res = {}
+    for fused in (False, True):
+        DF.FUSED_REGION_AGG = fused
+        DF.WC.clear()
+        try:
+            t = {k: v.clone().requires_grad_(k != 'regions') for k, v in base.items()}
+            blk = DF.TunBlock(encs, P, training=False)
+            outs = DF.run_block(blk, t)
+            loss = sum((outs[i] * gouts[i]).sum() for i in active)
+            loss.backward()
+            res[fused] = ([o.detach() for o in outs], {k: v.grad for k, v in t.items()})
+        finally:
+            DF.FUSED_REGION_AGG = True
+    (o0, g0), (o1, g1) = res[False], res[True]
+    for a, b in zip(o0, o1):
+        assert (a - b).abs().max() < 2e-2 * max(1.0, float(a.abs().max()))
+    for k in g0:
+        if k == 'regions':
+            continue
+        pf = k.split('.')[0]
+        if (0 if pf == 'a' else 1) not in active and k.startswith(('a.', 'b.')):
+            assert g0[k] is None and g1[k] is None, k
+            continue
+        if g0[k] is None:
+            assert g1[k] is None, k
+            continue
+        err = float((g0[k] - g1[k]).norm() / (g0[k].norm() + 1e-12))
+        assert err < 3e-2, (k, err)

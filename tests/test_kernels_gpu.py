@@ -586,3 +586,72 @@ def test_beam_topk_degenerate_and_strided_rows(be, V_):
     be.beam_topk(wide.to(DEV)[:, 3:3 + V_], last.to(DEV), 2, k, gtl, gti)
     assert torch.equal(gti.cpu(), idx), (gti.cpu()[:4], idx[:4])
     assert (gtl.cpu().double() - ref_lp.gather(1, idx)).abs().max() < 1e-4
+
+
+# ----------------------------------------------------------------------------------------------- fused region aggregation
+@pytest.mark.parametrize('B_,T,TR,E', [(3, 26, 936, 2), (2, 26, 37, 2), (2, 5, 20, 1), (1, 1, 1, 1), (2, 13, 64, 2)])
+def test_region_aggregate_fused(be, B_, T, TR, E):
+    """csrc/region_agg.cu (layer.py:184-192 in one pass over the region activations) against the plain composition
+    LayerNorm -> scores -> softmax over all T*R regions -> weighted sum and its hand-derived backward (cpu_emul).
+    Y is a column slice of the two-encoder projection buffer (row pitch 2H), ragged last tile, T < 26, one encoder only.
+    Tolerances: the kernels round the softmax weights (x rstd) and the gamma-folded frame vectors to bf16 for the mma;
+    the emulator rounds the same frame vectors, so scores are tight (2e-3) and aggregates / gradients are 1e-2 of scale."""
+    H = 1024
+    scale = 1.0 / math.sqrt(2048)
+    Ybuf = bf(torch.tanh(R(B_ * TR, 2 * H)))
+    Y = [Ybuf[:, e * H:(e + 1) * H] for e in range(E)]
+    F = [R(B_ * T, H) for _ in range(E)]
+    gamma = [1 + 0.1 * R(H) for _ in range(E)]
+    beta = [0.1 * R(H) for _ in range(E)]
+    z = lambda *s, dt=torch.float32: [torch.zeros(*s, dtype=dt) for _ in range(E)]
+    cpu = dict(agg=z(B_ * T, H), U=z(B_ * T, H), stats=z(B_ * TR, 2), St=z(B_, T, TR), tconst=z(B_ * T, 4))
+    dev = lambda lst: None if lst is None else [x.to(DEV) for x in lst]
+    Ybuf_d = Ybuf.to(DEV)
+    Yd = [Ybuf_d[:, e * H:(e + 1) * H] for e in range(E)]
+    gpu = {k: dev(v) for k, v in cpu.items()}
+    # amplify the scores so that the softmax is far from uniform (scale * S of order 1-5)
+    sc = scale * 40
+    EM.region_aggregate_fwd(Y, F, gamma, beta, sc, T, **cpu)
+    be.region_aggregate_fwd(Yd, dev(F), dev(gamma), dev(beta), sc, T, **gpu)
+    torch.cuda.synchronize()
+    tols = dict(agg=1e-2, U=1e-2, stats=1e-4, St=2e-3, tconst=2e-3)
+    for k in cpu:
+        for e in range(E):
+            c, g_ = cpu[k][e], gpu[k][e].cpu()
+            s_ = max(1.0, float(c.abs().max()))
+            assert float((c - g_).abs().max()) <= tols[k] * s_, (k, e, float((c - g_).abs().max()), s_)
+    # inference form: no optional outputs
+    agg2 = dev(z(B_ * T, H))
+    be.region_aggregate_fwd(Yd, dev(F), dev(gamma), dev(beta), sc, T, agg=agg2)
+    for e in range(E):
+        assert torch.equal(agg2[e], gpu['agg'][e])
+    # ---- backward: scores pass with F := dA, then the prep + streaming pass
+    dA = [R(B_ * T, H) for _ in range(E)]
+    c1 = dict(St=z(B_, T, TR), tconst=z(B_ * T, 4))
+    g1 = {k: dev(v) for k, v in c1.items()}
+    EM.region_aggregate_fwd(Y, dA, gamma, beta, sc, T, scores_only=True, **c1)
+    be.region_aggregate_fwd(Yd, dev(dA), dev(gamma), dev(beta), sc, T, scores_only=True, **g1)
+    torch.cuda.synchronize()
+    for k, tol in (('St', 2e-3), ('tconst', 2e-3)):
+        for e in range(E):
+            c, g_ = c1[k][e], g1[k][e].cpu()
+            assert float((c - g_).abs().max()) <= tol * max(1.0, float(c.abs().max())), (k, e)
+    dbuf = torch.zeros(B_ * TR, 2 * H, dtype=torch.bfloat16)
+    dbuf_d = dbuf.to(DEV)
+    c2 = dict(dpre=[dbuf[:, e * H:(e + 1) * H] for e in range(E)], dF=z(B_ * T, H), dgamma=[R(H) for _ in range(E)],
+              dbeta=[R(H) for _ in range(E)], dbias=[R(H) for _ in range(E)])
+    g2 = dict(dpre=[dbuf_d[:, e * H:(e + 1) * H] for e in range(E)], dF=dev(c2['dF']), dgamma=dev(c2['dgamma']),
+              dbeta=dev(c2['dbeta']), dbias=dev(c2['dbias']))
+    # both sides start from the emulator's forward tensors, so only the backward kernels are compared
+    args = [cpu['stats'], cpu['St'], c1['St'], F, dA, cpu['U'], cpu['tconst'], c1['tconst'], gamma, beta]
+    EM.region_aggregate_bwd(Y, *args, sc, T, **c2)
+    work = [torch.empty(be.region_aggregate_bwd_workspace(B_, T, TR), dtype=torch.uint8, device=DEV) for _ in range(E)]
+    be.region_aggregate_bwd(Yd, *[dev(a) for a in args], sc, T, work=work, **g2)
+    torch.cuda.synchronize()
+    for k, tol in (('dpre', 2e-2), ('dF', 1e-2), ('dgamma', 1e-2), ('dbeta', 1e-4), ('dbias', 1e-2)):
+        for e in range(E):
+            c, g_ = c2[k][e].float(), g2[k][e].float().cpu()
+            s_ = max(1e-6, float(c.abs().max()))
+            assert float((c - g_).abs().max()) <= tol * s_, (k, e, float((c - g_).abs().max()), s_)
+    if E < 2:       # the other encoder's half of the gradient buffer is untouched
+        assert float(dbuf_d[:, H:].abs().max()) == 0.0
