@@ -521,29 +521,16 @@ def main(argv=None):
         # runs on a copy stream while step k computes; every step still copies its own inputs from pinned host memory inside the
         # timed region and reads its loss back.  Measured for both host formats: fp32 (the reference loader's, utils/data.py:60-62)
         # and bf16 (half the PCIe bytes).
-        copy_stream = torch.cuda.Stream()
+        from dlsg.pipeline import FeaturePipe          # the product's input pipeline (dlsg/pipeline.py), not a bench-only loop
 
         def make_pipe(g, hf, hr):
-            bufs = [torch.empty_like(hf, device=dev), torch.empty_like(hr, device=dev), torch.empty_like(d_cp)]
-            ready, consumed = torch.cuda.Event(), torch.cuda.Event()
-
-            def prefetch():
-                copy_stream.wait_event(consumed)
-                with torch.cuda.stream(copy_stream):
-                    bufs[0].copy_(hf, non_blocking=True)
-                    bufs[1].copy_(hr, non_blocking=True)
-                    bufs[2].copy_(h_cp, non_blocking=True)
-                    ready.record(copy_stream)
+            fp = FeaturePipe(g, hf, hr, h_cp, dev)
+            fp.put(hf, hr, h_cp)
 
             def pipe():
-                cur = torch.cuda.current_stream()
-                cur.wait_event(ready)
-                g.load(bufs[0], bufs[1], bufs[2])              # device-to-device into the graph's static inputs
-                consumed.record(cur)
-                prefetch()                                     # next step's H2D overlaps this step's compute
-                return g().item()
-            consumed.record(torch.cuda.current_stream())
-            prefetch()
+                loss = fp.run()                                # waits for the staged batch, hands it to the captured step
+                fp.put(hf, hr, h_cp)                           # next step's H2D overlaps this step's compute
+                return loss.item()
             return pipe
         pipe32 = make_pipe(gs, h_fr, h_rg)
         for _ in range(2):

@@ -15,7 +15,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start o
     --log-file $OUT/${TAG}_launches_eager_step.csv python bench.py --profile-step --warmup 3 > $OUT/ncu_step.log 2>&1
 python tools/agg_launches.py $OUT/${TAG}_launches_eager_step.csv 60 > $OUT/${TAG}_launches_eager_step_summary.txt
 # full metric set: one launch of every kernel class of the real step (first occurrence of each name inside one eager step)
-ncu --set full --clock-control none --import-source on --profile-from-start off \
+ncu --set full --clock-control none --profile-from-start off \
     -k regex:"gemm_tc_kernel|region_aggregate|norm_fwd_vec|norm_bwd_vec|cast_f32_bf16|lstm_cell|attn2|adam_multi|ce_masked|latent_psl" \
     --kernel-id :::1 -o $OUT/${TAG}_step_kernels python bench.py --profile-step --warmup 3 > $OUT/ncu_full.log 2>&1
 ncu -i $OUT/${TAG}_step_kernels.ncu-rep --page raw --csv > $OUT/raw.csv 2>/dev/null && \
@@ -33,5 +33,8 @@ python tools/profile_blocks.py > $OUT/${TAG}_blocks.jsonl 2> $OUT/blocks.err
 python tools/bench_gan.py > $OUT/${TAG}_gan_iteration.json 2> $OUT/gan.err
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file $OUT/dstep.csv python tools/bench_gan.py --profile-dstep > $OUT/ncu_dstep.log 2>&1
-python tools/agg_launches.py $OUT/dstep.csv 60 > $OUT/${TAG}_launches_dstep_summary.txt
+python tools/agg_launches.py $OUT/dstep.csv 60 > $OUT/${TAG}_launches_dstep_summary.txt 2>/dev/null
+tail -5 $OUT/gan.err $OUT/ncu_dstep.log
+# the reports themselves are too large to travel back (gpurun_out is capped at 64 MiB): keep the summaries
+rm -f $OUT/*.ncu-rep $OUT/raw.csv $OUT/raw2.csv
 ls -la $OUT
