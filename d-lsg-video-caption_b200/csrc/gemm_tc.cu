@@ -34,6 +34,8 @@ struct TcParams {
   int splitk, kb_total, kb_per_split;
   int ntm, ntn, tiles_total;
   int a_mn, b_mn;      // operand is MN-major in global memory (unit stride along P resp. Q, not along K)
+  int pre_a, pre_b;    // operand is STATIC (DLSG_GEMM_*_STATIC: not written by the preceding kernels of the stream, e.g. a weight
+                       // inside a recurrent loop): its first ring-full of tiles is fetched BEFORE griddepcontrol.wait
   unsigned long long* trace;   // debug: per-CTA phase timestamps (dlsg_debug_gemm_trace), nullptr in production
 };
 
@@ -118,7 +120,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 }
 
 template <int BN> struct TcCfg {
-  static constexpr int STAGES = (BN >= 256) ? 4 : 6;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN <= 64 ? 8 : 6);   // skinny tiles: a deeper ring = a larger early weight fetch
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -181,7 +183,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) tc_trace(prm, 1);               // barriers + TMEM ready
-  pdl_prologue();      // barrier init / TMEM allocation above overlap the previous kernel's tail; operands are read below
+  // barrier init / TMEM allocation above overlap the previous kernel's tail (programmatic dependent launch).  The producer
+  // thread goes further for a STATIC operand: the first ring-full of its tiles (a weight slab of a per-step recurrent GEMM:
+  // up to STAGES x 16 KB per CTA) is requested before the dependency wait, so the weight stream overlaps the preceding
+  // latency-bound kernels of the chain; only the dependent operand (64 activation rows) waits.
+  const bool is_producer = (warp == 0 && lane == 0);
+  int pre = 0;
+  if (is_producer && (prm.pre_a | prm.pre_b) && (int)blockIdx.x < tiles_total) {
+    const int tile = blockIdx.x;
+    const int tn = tile % ntn, tm = (tile / ntn) % ntm, z = tile / (ntn * ntm);
+    const int zb = z / prm.splitk, zs = z % prm.splitk;
+    const int kb_begin = zs * prm.kb_per_split;
+    const int nkb = min(prm.kb_total, kb_begin + prm.kb_per_split) - kb_begin;
+    pre = min(nkb, Cfg::STAGES);
+    for (int kb = 0; kb < pre; ++kb) {
+      const uint32_t full = smem_u32(&full_bar[kb]);
+      mbar_expect_tx(full, Cfg::STAGE_BYTES);
+      const uint32_t a_dst = smem_u32(tiles + kb * Cfg::STAGE_BYTES);
+      const int kc = (kb_begin + kb) * BK;
+      if (prm.pre_a) {
+        if (!prm.a_mn) {
+          tma_load_3d(a_dst, &tmA, full, kc, tm * BM, zb);
+        } else {
+          tma_load_3d(a_dst, &tmA, full, tm * BM, kc, zb);
+          tma_load_3d(a_dst + MN_BLOCK_BYTES, &tmA, full, tm * BM + 64, kc, zb);
+        }
+      }
+      if (prm.pre_b) {
+        if (!prm.b_mn) {
+          tma_load_3d(a_dst + Cfg::A_BYTES, &tmB, full, kc, tn * BN, zb);
+        } else {
+#pragma unroll
+          for (int jb = 0; jb < BN / 64; ++jb)
+            tma_load_3d(a_dst + Cfg::A_BYTES + jb * MN_BLOCK_BYTES, &tmB, full, tn * BN + 64 * jb, kc, zb);
+        }
+      }
+    }
+  }
+  pdl_prologue();      // operands that depend on the preceding kernel are read below
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -195,21 +234,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
           const uint32_t full = smem_u32(&full_bar[s]);
-          mbar_expect_tx(full, Cfg::STAGE_BYTES);
+          // the first `pre` k-blocks of this CTA's first tile: transaction count armed and static operand(s) already in flight
+          const bool early = (tile == (int)blockIdx.x) && (kb < pre);
+          if (!early) mbar_expect_tx(full, Cfg::STAGE_BYTES);
           const uint32_t a_dst = smem_u32(tiles + s * Cfg::STAGE_BYTES);
           const int kc = (kb_begin + kb) * BK;
-          if (!prm.a_mn) {
-            tma_load_3d(a_dst, &tmA, full, kc, tm * BM, zb);
-          } else {                                     // two 64(P) x 64(K) boxes
-            tma_load_3d(a_dst, &tmA, full, tm * BM, kc, zb);
-            tma_load_3d(a_dst + MN_BLOCK_BYTES, &tmA, full, tm * BM + 64, kc, zb);
+          if (!(early && prm.pre_a)) {
+            if (!prm.a_mn) {
+              tma_load_3d(a_dst, &tmA, full, kc, tm * BM, zb);
+            } else {                                     // two 64(P) x 64(K) boxes
+              tma_load_3d(a_dst, &tmA, full, tm * BM, kc, zb);
+              tma_load_3d(a_dst + MN_BLOCK_BYTES, &tmA, full, tm * BM + 64, kc, zb);
+            }
           }
-          if (!prm.b_mn) {
-            tma_load_3d(a_dst + Cfg::A_BYTES, &tmB, full, kc, tn * BN, zb);
-          } else {
+          if (!(early && prm.pre_b)) {
+            if (!prm.b_mn) {
+              tma_load_3d(a_dst + Cfg::A_BYTES, &tmB, full, kc, tn * BN, zb);
+            } else {
 #pragma unroll
-            for (int jb = 0; jb < BN / 64; ++jb)
-              tma_load_3d(a_dst + Cfg::A_BYTES + jb * MN_BLOCK_BYTES, &tmB, full, tn * BN + 64 * jb, kc, zb);
+              for (int jb = 0; jb < BN / 64; ++jb)
+                tma_load_3d(a_dst + Cfg::A_BYTES + jb * MN_BLOCK_BYTES, &tmB, full, tn * BN + 64 * jb, kc, zb);
+            }
           }
           if (tile == (int)blockIdx.x && kb == 0) tc_trace(prm, 2);     // first TMA issued
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
@@ -640,7 +685,7 @@ int gemm_tc_dispatch(const dlsg_gemm_t* g, cudaStream_t st) {
       const int64_t need = (int64_t)S * batch * g->M * g->N * 4;
       if (S >= 2 && need <= g->workspace_bytes) {
         dlsg_gemm_t part = *g;
-        part.D = g->workspace; part.d_dtype = DLSG_F32; part.bias = nullptr; part.flags = 0; part.alpha = 1.f;
+        part.D = g->workspace; part.d_dtype = DLSG_F32; part.bias = nullptr; part.flags = g->flags & (DLSG_GEMM_A_STATIC | DLSG_GEMM_B_STATIC); part.alpha = 1.f;
         part.ldd = g->N; part.stride_d = (int64_t)g->M * g->N; part.splitk = S;
         part.stride_split = (int64_t)batch * g->M * g->N; part.workspace = nullptr;
         if (int rc = gemm_tc_direct(&part, st)) return rc;
@@ -716,6 +761,11 @@ static int gemm_tc_direct(const dlsg_gemm_t* g, cudaStream_t st) {
   if (make_map(&ta, Ap, P, g->K, ldp, batch, strp, BM, p_mn)) return -1;
   if (make_map(&tb, Bq, Q, g->K, ldq, batch, strq, bn, q_mn)) return -1;
   prm.a_mn = p_mn ? 1 : 0; prm.b_mn = q_mn ? 1 : 0;
+  {
+    const bool a_static = (g->flags & DLSG_GEMM_A_STATIC) != 0, b_static = (g->flags & DLSG_GEMM_B_STATIC) != 0;
+    prm.pre_a = (swap ? b_static : a_static) ? 1 : 0;
+    prm.pre_b = (swap ? a_static : b_static) ? 1 : 0;
+  }
   prm.ntm = ptiles;
   prm.ntn = (Q + bn - 1) / bn;
   const int64_t tiles_total = (int64_t)prm.ntm * prm.ntn * batch * splitk;

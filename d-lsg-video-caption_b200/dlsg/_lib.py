@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(HERE, 'libdlsg.so')
 F32, BF16 = 0, 1
 GEMM_SIMT, GEMM_TC = 0, 1
 EPI_BIAS_N, EPI_BIAS_M, EPI_TANH, EPI_ACCUM, EPI_STORE_T, EPI_ATOMIC = 1, 2, 4, 8, 16, 32
+GEMM_A_STATIC, GEMM_B_STATIC = 64, 128
 NORM_PRE_TANH, NORM_POST_TANH, NORM_IN_IS_TANH = 1, 2, 4
 
 i32, i64, u32, u64, f32, vp = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_float, C.c_void_p

@@ -142,7 +142,9 @@ class DecoderCore:
         dq, dc, dl, _ = drops
         R = b.Xq.shape[1]
         # split-K partial sums go straight into the cell kernel (no reduce launch)
-        be.gemm(b.Xq[i], pk['Wq'], b.gq[:, i] if b.Sq > 1 else b.gq[0, i], splitk=b.Sq)
+        # weights are static inside the loop (b_static): their tiles are requested while the previous step's cell kernel runs;
+        # not at step 0, where the preceding launch may be the conversion of these very weights
+        be.gemm(b.Xq[i], pk['Wq'], b.gq[:, i] if b.Sq > 1 else b.gq[0, i], splitk=b.Sq, b_static=i > 0)
         # fused: split-K partials + hoisted global-feature bias -> cell -> q = dropout(LN(query_h))
         qy, qy2 = (b.q32[i], b.Xl[i][:, oq:oq + Hq]) if self.hoist else (b.Xl[i][:, oq:oq + Hq], None)
         lnq_w, lnq_b = t[pf + 'query_lstm_layernorm.weight'], t[pf + 'query_lstm_layernorm.bias']
@@ -168,7 +170,7 @@ class DecoderCore:
                 be.norm_fwd(b.co[i][:, k * H:(k + 1) * H], t[pf + h + '.output_layer.2.weight'], t[pf + h + '.output_layer.2.bias'],
                             y=b.Xl[i][:, k * H:(k + 1) * H], stats=b.statc[i, k], pre_tanh=True,
                             drop=(None if dc is None else (dc[0], dc[1], dc[2] + (k << 28))))
-        be.gemm(b.Xl[i], pk['Wl'], b.gl[:, i] if b.Sl > 1 else b.gl[0, i], splitk=b.Sl)
+        be.gemm(b.Xl[i], pk['Wl'], b.gl[:, i] if b.Sl > 1 else b.gl[0, i], splitk=b.Sl, b_static=True)   # preceded by the attention kernel
         # fused: cell -> lang_h = dropout(h) (recurrent state, layer.py:594) -> tanh(LN(lang_h))
         lnl_w, lnl_b = t[pf + 'lang_lstm_layernorm.weight'], t[pf + 'lang_lstm_layernorm.bias']
         stl = lang_stats if lang_stats is not None else b.statl[i]
@@ -356,7 +358,7 @@ class DecoderTrainBlock:
                 be.lstm_cell_bwd(b.gl[0, i], b.cl[i], b.cl[j], dXq[j][:, :Hd], dcl, dcl2, dgates2=dgl_all[rows],
                                  drop=dl, dh2=dXl[j][:, ol:ol + Hd])
             dcl, dcl2 = dcl2, dcl
-            be.gemm(dgl_all[rows], pk['WlT'], dXl[i], atomic=True)      # dXl / dXq start as zeros: split-K lands by atomic adds
+            be.gemm(dgl_all[rows], pk['WlT'], dXl[i], atomic=True, b_static=True)      # dXl / dXq start as zeros: split-K lands by atomic adds
             if hoist:
                 # one kernel: output-layer backward (dropout, LayerNorm, tanh) of both heads -> d(alpha), softmax backward,
                 # dq += sum_h sum_p dl KW, dKW / dVW accumulated over time; LN parameter gradients as per-row contributions
@@ -386,7 +388,7 @@ class DecoderTrainBlock:
                                  dgates2=dgq_all[rows])
                 be.axpby(dgq32, 1.0, dgq_sum, 1.0)
             dcq, dcq2 = dcq2, dcq
-            be.gemm(dgq_all[rows], pk['WqT'], dXq[i], atomic=True)
+            be.gemm(dgq_all[rows], pk['WqT'], dXq[i], atomic=True, b_static=True)
         # ---- parameter gradients batched over time
         if fused:
             be.colsum(lq_g.view(TB, Hq), lnq[2])
@@ -480,7 +482,7 @@ def _step_logits(core, b, i, j, Kp, Vp, Gq, rpn, dbuf, logits):
     be = ops.backend()
     t, pf = core.t, core.pf
     core.step(b, i, j, Kp, Vp, Gq, rpn, lang_y=dbuf)
-    be.gemm(dbuf, WC.get(t[pf + 'word_restore.weight']), logits, bias=t[pf + 'word_restore.bias'].detach())
+    be.gemm(dbuf, WC.get(t[pf + 'word_restore.weight']), logits, bias=t[pf + 'word_restore.bias'].detach(), b_static=True)
 
 
 def decode_greedy(t, pf, multi_modal, n1, n2, T):

@@ -580,7 +580,7 @@ class EncoderVisualBlock:
             order = list(range(T)) if d == 0 else list(range(T - 1, -1, -1))
             for k, tt in enumerate(order):
                 if k > 0:
-                    be.gemm(hprev[d, :, tt], whh[d], gates[:, d, tt] if Sg > 1 else gates[0, d, tt], splitk=Sg)
+                    be.gemm(hprev[d, :, tt], whh[d], gates[:, d, tt] if Sg > 1 else gates[0, d, tt], splitk=Sg, b_static=True)
                 nxt = order[k + 1] if k + 1 < T else None
                 be.lstm_cell_fwd(gates[:, d, tt], cs[d, k], cs[d, k + 1], row_bias=Gin[:, tt, d * H4:(d + 1) * H4],
                                  h2=lstm_out[:, tt, d * H:(d + 1) * H], h3=(hprev[d, :, nxt] if nxt is not None else None))
@@ -713,7 +713,7 @@ class EncoderVisualBlock:
                                  dgates2=dg2, dh2=dhrec)
                 dc, dc2 = dc2, dc
                 if k > 0:
-                    be.gemm(op(dg2), whhT[d], dhrec if Sd > 1 else dhrec[0], splitk=Sd)
+                    be.gemm(op(dg2), whhT[d], dhrec if Sd > 1 else dhrec[0], splitk=Sd, b_static=True)
         two_streams(ref, lambda: run_dir_bwd(0), lambda: run_dir_bwd(1))
         dGin2 = dGin.view(B * T, 2 * H4)
         for d in range(2):

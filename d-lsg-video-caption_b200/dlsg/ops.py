@@ -6,12 +6,15 @@ caller-provided tensors (nothing is allocated here, so every call is CUDA-graph 
 (tests/cpu_emul.py) to exercise the host orchestration without a GPU - the product never does.
 """
 import ctypes as C
+import os
 
 import torch
 
 from . import _lib as L
 
 F32, BF16 = L.F32, L.BF16
+# DLSG_STATIC_PREFETCH=0: never request the early weight fetch of the recurrent GEMMs (measurement switch)
+STATIC_PREFETCH = os.environ.get('DLSG_STATIC_PREFETCH', '1') != '0'
 
 
 def _dt(t):
@@ -74,9 +77,11 @@ class CudaBackend:
 
     # ------------------------------------------------------------------ GEMM
     def gemm(self, a, b, out, bias=None, bias_axis='n', tanh=False, alpha=1.0, accum=False, splitk=1,
-             impl=None, atomic=False):
+             impl=None, atomic=False, b_static=False):
         """out[(batch,)M,N] = epi(alpha * a[(batch,)M,K] @ b[(batch,)N,K]^T + bias).
         atomic=True: out += result through fp32 atomic adds (DLSG_EPI_ATOMIC): skinny problems split K with no reduce launch.
+        b_static=True: promise that `b` (a weight) is not written by the kernel launched just before this one on the stream
+        (DLSG_GEMM_B_STATIC): its first tiles are fetched while that kernel still runs.  Same results.
 
         `out` may be a transposed view (unit stride on M) -> STORE_T.  For splitk>1 `out` has a
         leading split dim: (splitk, M, N) and receives partial sums."""
@@ -115,6 +120,8 @@ class CudaBackend:
         if atomic:
             assert not accum and not tanh and splitk <= 1 and o2.dtype == torch.float32
             flags |= L.EPI_ATOMIC
+        if b_static and STATIC_PREFETCH:
+            flags |= L.GEMM_B_STATIC
         g.A, g.B, g.D, g.bias = a2.data_ptr(), b2.data_ptr(), o2.data_ptr(), _ptr(bias)
         g.M, g.N, g.K, g.batch = M, N, K, batch
         g.sam, g.sak, g.sbn, g.sbk = a2.stride(0), a2.stride(1), b2.stride(0), b2.stride(1)

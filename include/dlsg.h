@@ -46,10 +46,14 @@ enum {
   DLSG_EPI_TANH = 4,     /* tanh after bias                                                    */
   DLSG_EPI_ACCUM = 8,    /* D += result                                                        */
   DLSG_EPI_STORE_T = 16, /* store D^T: element (m,n) goes to D[n*ldd + m]                      */
-  DLSG_EPI_ATOMIC = 32   /* D += result through fp32 atomic adds (fp32 D, no tanh): DLSG_GEMM_TC may then split K  */
+  DLSG_EPI_ATOMIC = 32,  /* D += result through fp32 atomic adds (fp32 D, no tanh): DLSG_GEMM_TC may then split K  */
                          /* over the idle SMs with no workspace and no reduce launch (D holds the addend, e.g.     */
                          /* zeros).  The order in which the splits land is not fixed: last-bit run-to-run noise.   */
                          /* DLSG_GEMM_SIMT treats it as DLSG_EPI_ACCUM.                                             */
+  DLSG_GEMM_A_STATIC = 64,  /* promise: operand A (resp. B) is not written by the kernels that precede this launch in the  */
+  DLSG_GEMM_B_STATIC = 128  /* stream (a weight inside a recurrent loop).  DLSG_GEMM_TC then requests its first ring-full  */
+                            /* of tiles BEFORE the programmatic-dependent-launch wait, overlapping the weight stream with  */
+                            /* the tail of the preceding kernels.  Results are identical; ignored by DLSG_GEMM_SIMT.       */
 };
 typedef struct {
   const void* A; const void* B; void* D; const float* bias;

@@ -21,7 +21,8 @@ class CpuEmulBackend:
     def __init__(self):
         self.launches = 0
 
-    def gemm(self, a, b, out, bias=None, bias_axis='n', tanh=False, alpha=1.0, accum=False, splitk=1, impl=None, atomic=False):
+    def gemm(self, a, b, out, bias=None, bias_axis='n', tanh=False, alpha=1.0, accum=False, splitk=1, impl=None, atomic=False,
+             b_static=False):
         self.launches += 1
         accum = accum or atomic
         r = torch.matmul(_f(a), _f(b).transpose(-1, -2)) * alpha

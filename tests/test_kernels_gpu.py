@@ -655,3 +655,37 @@ def test_region_aggregate_fused(be, B_, T, TR, E):
             assert float((c - g_).abs().max()) <= tol * s_, (k, e, float((c - g_).abs().max()), s_)
     if E < 2:       # the other encoder's half of the gradient buffer is untouched
         assert float(dbuf_d[:, H:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('M,N,K,splitk,atomic', [(64, 4096, 2864, 4, False), (64, 6144, 4608, 1, True), (64, 1024, 1024, 1, False),
+                                                 (200, 384, 520, 1, False), (640, 10547, 1536, 1, False)])
+def test_gemm_static_operand_early_fetch_is_bit_identical(be, M, N, K, splitk, atomic):
+    """DLSG_GEMM_B_STATIC (weight tiles requested before the programmatic-dependent-launch wait) changes WHEN the tiles
+    travel, not what is computed: bit-identical output with and without it, directly behind a kernel that rewrites the
+    activations (the dependent operand), in the swap-AB (M <= 64: the weight rides the 128-row side), plain, split-K
+    and atomic-accumulate forms."""
+    Kp = (K + 7) // 8 * 8
+    w = bf(R(N, Kp))[:, :K]
+    x_src = R(M, Kp)
+    outs = []
+    for static in (False, True):
+        x = torch.empty(M, Kp, dtype=torch.bfloat16, device=DEV)
+        wd = w.to(DEV)
+        if splitk > 1:
+            o = torch.zeros(splitk, M, N, device=DEV)
+        else:
+            o = torch.zeros(M, N, device=DEV)
+        xs = x_src.to(DEV)
+        for rep in range(3):                              # the conversion kernel right before the GEMM writes its A operand
+            be.convert(xs * (rep + 1), dst=x)
+            if atomic:
+                o.zero_()
+            be.gemm(x[:, :K], wd, o, splitk=splitk, atomic=atomic, b_static=static)
+        torch.cuda.synchronize()
+        outs.append(o.sum(0) if splitk > 1 else o)
+    if atomic:                                            # split order is not fixed: last-bit noise in either run
+        assert float((outs[0] - outs[1]).abs().max()) <= 1e-3 * float(outs[0].abs().max())
+    else:
+        assert torch.equal(outs[0], outs[1])
+    ref = (x_src * 3).to(torch.bfloat16).float()[:, :K] @ w.float().t()
+    assert float((outs[1].cpu() - ref).abs().max()) <= 2e-3 * float(ref.abs().max())

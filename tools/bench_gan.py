@@ -60,7 +60,8 @@ def main():
         it()
         with torch.no_grad():
             f_cap, obj, mot, alpha = G(frames, regions, caps, L, eps_tf)
-        real = torch.zeros(B, L, V, device=dev).scatter_(2, caps.unsqueeze(2), 1)
+        # token form (batched critic calls) takes the caption ids; the literal form the (B,L,V) one-hot (run_gun.py:449-453)
+        real = caps if a.batched else torch.zeros(B, L, V, device=dev).scatter_(2, caps.unsqueeze(2), 1)
         att_mask = synth.att_mask_from_captions(caps).to(dev)
         it._disc_steps(real, f_cap, obj, mot, att_mask, alpha)
         torch.cuda.synchronize()

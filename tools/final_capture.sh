@@ -19,7 +19,7 @@ ncu --set full --clock-control none --profile-from-start off \
     -k regex:"gemm_tc_kernel|region_aggregate|norm_fwd_vec|norm_bwd_vec|cast_f32_bf16|lstm_cell|attn2|adam_multi|ce_masked|latent_psl" \
     --kernel-id :::1 -o $OUT/${TAG}_step_kernels python bench.py --profile-step --warmup 3 > $OUT/ncu_full.log 2>&1
 ncu -i $OUT/${TAG}_step_kernels.ncu-rep --page raw --csv > $OUT/raw.csv 2>/dev/null && \
-    python tools/ncu_summary.py $OUT/raw.csv > $OUT/${TAG}_ncu_full_step_kernels.json
+    python tools/ncu_summary.py $OUT/raw.csv > $OUT/${TAG}_ncu_full_step_kernels.json 2> $OUT/ncu_summary.err
 # the dominant GEMMs / streaming kernels in isolation at the benched shapes
 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_kernel|norm_bwd_bf16|norm_fwd_bf16|cast_f32_bf16" \
     -o $OUT/${TAG}_top_kernels python tools/profile_kernels.py > $OUT/ncu_full2.log 2>&1
@@ -36,5 +36,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start o
 python tools/agg_launches.py $OUT/dstep.csv 60 > $OUT/${TAG}_launches_dstep_summary.txt 2>/dev/null
 tail -5 $OUT/gan.err $OUT/ncu_dstep.log
 # the reports themselves are too large to travel back (gpurun_out is capped at 64 MiB): keep the summaries
-rm -f $OUT/*.ncu-rep $OUT/raw.csv $OUT/raw2.csv
+gzip -f $OUT/raw.csv; rm -f $OUT/*.ncu-rep $OUT/raw2.csv
 ls -la $OUT

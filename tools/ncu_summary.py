@@ -29,14 +29,12 @@ for r in rows[hdr + 2:]:
     for w in WANT:
         if w in col and r[col[w]] != '':
             o[w] = ('%s %s' % (r[col[w]], units[col[w]])).strip()
-    # tensor-pipe activity: ONLY the recipe's metric (B200_PROFILING.md: sm__pipe_tensor_cycles_active, % of peak) - the
-    # round-1 summary also swept every column with "tensor" in its name (per-subpipe instruction shares) and the table
-    # built from it mixed them up (46.8 vs 12.5 for one kernel)
+    # tensor-pipe activity: ONLY the recipe's metric (B200_PROFILING.md: sm__pipe_tensor_cycles_active, % of peak, plain
+    # counter).  The round-1 summary also swept every column with "tensor" in its name, among them the sampled
+    # TriageCompute `..._realtime` variant, which reads 12.5 and 49.7 for two identical launches of one kernel (the
+    # 46.8 / 12.5 pair the review found): not a usable measurement, no longer reported.
     for n in names:
-        if n.split('.')[-4:-3] == ['sm__pipe_tensor_cycles_active_realtime'] or n.startswith('sm__pipe_tensor_cycles_active'):
-            if 'pct_of_peak' in n and r[col[n]] != '':
-                o[n] = ('%s %s' % (r[col[n]], units[col[n]])).strip()
-        if 'sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed' in n and r[col[n]] != '':
-            o['tensor_pipe_cycles_active_pct'] = float(r[col[n]].replace(',', ''))
+        if n.startswith('sm__pipe_tensor_cycles_active') and 'pct_of_peak' in n and n.split('.')[1] == 'avg' and r[col[n]] != '':
+            o[n] = ('%s %s' % (r[col[n]], units[col[n]])).strip()
     out.append(o)
 json.dump(out, sys.stdout, indent=1)
