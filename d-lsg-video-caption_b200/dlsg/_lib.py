@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libdlsg.so')
+LIB_PATH = os.environ.get('DLSG_LIB') or os.path.join(HERE, 'libdlsg.so')     # DLSG_LIB: an experimental build (tools only)
 
 F32, BF16 = 0, 1
 GEMM_SIMT, GEMM_TC = 0, 1

@@ -142,9 +142,9 @@ class DecoderCore:
         dq, dc, dl, _ = drops
         R = b.Xq.shape[1]
         # split-K partial sums go straight into the cell kernel (no reduce launch)
-        # weights are static inside the loop (b_static): their tiles are requested while the previous step's cell kernel runs;
-        # not at step 0, where the preceding launch may be the conversion of these very weights
-        be.gemm(b.Xq[i], pk['Wq'], b.gq[:, i] if b.Sq > 1 else b.gq[0, i], splitk=b.Sq, b_static=i > 0)
+        # weights are static inside the loop (b_static): their tiles are requested while the previous step's cell kernel runs
+        # (the backend drops the request when the launch directly before is a weight conversion, e.g. at step 0)
+        be.gemm(b.Xq[i], pk['Wq'], b.gq[:, i] if b.Sq > 1 else b.gq[0, i], splitk=b.Sq, b_static=True)
         # fused: split-K partials + hoisted global-feature bias -> cell -> q = dropout(LN(query_h))
         qy, qy2 = (b.q32[i], b.Xl[i][:, oq:oq + Hq]) if self.hoist else (b.Xl[i][:, oq:oq + Hq], None)
         lnq_w, lnq_b = t[pf + 'query_lstm_layernorm.weight'], t[pf + 'query_lstm_layernorm.bias']
@@ -170,7 +170,7 @@ class DecoderCore:
                 be.norm_fwd(b.co[i][:, k * H:(k + 1) * H], t[pf + h + '.output_layer.2.weight'], t[pf + h + '.output_layer.2.bias'],
                             y=b.Xl[i][:, k * H:(k + 1) * H], stats=b.statc[i, k], pre_tanh=True,
                             drop=(None if dc is None else (dc[0], dc[1], dc[2] + (k << 28))))
-        be.gemm(b.Xl[i], pk['Wl'], b.gl[:, i] if b.Sl > 1 else b.gl[0, i], splitk=b.Sl, b_static=True)   # preceded by the attention kernel
+        be.gemm(b.Xl[i], pk['Wl'], b.gl[:, i] if b.Sl > 1 else b.gl[0, i], splitk=b.Sl, b_static=True)
         # fused: cell -> lang_h = dropout(h) (recurrent state, layer.py:594) -> tanh(LN(lang_h))
         lnl_w, lnl_b = t[pf + 'lang_lstm_layernorm.weight'], t[pf + 'lang_lstm_layernorm.bias']
         stl = lang_stats if lang_stats is not None else b.statl[i]

@@ -13,8 +13,10 @@ import torch
 from . import _lib as L
 
 F32, BF16 = L.F32, L.BF16
-# DLSG_STATIC_PREFETCH=0: never request the early weight fetch of the recurrent GEMMs (measurement switch)
-STATIC_PREFETCH = os.environ.get('DLSG_STATIC_PREFETCH', '1') != '0'
+# DLSG_STATIC_PREFETCH=1 requests the early weight fetch (DLSG_GEMM_B_STATIC) of the recurrent GEMMs.  OFF by default: measured
+# on B200 it does not change the captured step (6.55 vs 6.55 ms with a 6-stage ring, 6.64 vs 6.63 with 8 stages,
+# gpurun r02w): behind the ~1.3 us CTA prologue the fetch wins nothing the L2-resident weights had not already given.
+STATIC_PREFETCH = os.environ.get('DLSG_STATIC_PREFETCH', '0') == '1'
 
 
 def _dt(t):
@@ -59,8 +61,28 @@ class CudaBackend:
 
     def __init__(self):
         self.lib = L.load()
-        self.launches = 0
+        self._launches = 0
+        self._writer_last = {}          # stream handle -> the last libdlsg launch on it wrote GEMM-operand copies of weights
         self._ws = {}
+
+    # Every wrapper counts its launch with `self.launches += 1`; the setter also notes, per stream, that the newest launch is
+    # an ordinary kernel.  The wrappers that WRITE operand copies of weights (convert / multi_convert / adam_multi) then mark
+    # themselves with _mark_writer().  gemm(b_static=True) asks for the early weight fetch only when the launch directly
+    # before it on its stream is not such a writer: with programmatic dependent launch a kernel may start while its direct
+    # predecessor still runs (never earlier: every kernel triggers its dependents after its own dependency wait), so that is
+    # the one case in which the early fetch could read a weight copy that is still being written.
+    @property
+    def launches(self):
+        return self._launches
+
+    @launches.setter
+    def launches(self, v):
+        self._launches = v
+        if torch.cuda.is_available():
+            self._writer_last[_stream()] = False
+
+    def _mark_writer(self):
+        self._writer_last[_stream()] = True
 
     def _workspace(self, dev):
         """Per-device scratch for automatic split-K (allocated once, before any graph capture uses it)."""
@@ -120,7 +142,7 @@ class CudaBackend:
         if atomic:
             assert not accum and not tanh and splitk <= 1 and o2.dtype == torch.float32
             flags |= L.EPI_ATOMIC
-        if b_static and STATIC_PREFETCH:
+        if b_static and STATIC_PREFETCH and self._writer_last.get(_stream(), True) is False:
             flags |= L.GEMM_B_STATIC
         g.A, g.B, g.D, g.bias = a2.data_ptr(), b2.data_ptr(), o2.data_ptr(), _ptr(bias)
         g.M, g.N, g.K, g.batch = M, N, K, batch
@@ -153,6 +175,7 @@ class CudaBackend:
             s2, d2, t2 = src, dst, dstT
         assert s2.stride(1) == 1 or cols == 1
         self.launches += 1
+        self._mark_writer()
         L.check(self.lib.dlsg_convert2d_batched(
             s2.data_ptr(), _dt(s2), s2.stride(0), _ptr(d2), _dt(ref), d2.stride(0) if d2 is not None else 0,
             _ptr(t2), t2.stride(0) if t2 is not None else 0, rows, cols, batch, bs[0], bs[1], bs[2], _stream()),
@@ -196,10 +219,12 @@ class CudaBackend:
             return
         if plan.get('host'):
             self.launches += (plan['n'] + 383) // 384
+            self._mark_writer()
             L.check(self.lib.dlsg_multi_convert_host(C.cast(plan['table'], C.c_void_p), plan['n'], plan['chunk_elems'], _stream()),
                     'dlsg_multi_convert_host')
             return
         self.launches += 1
+        self._mark_writer()
         L.check(self.lib.dlsg_multi_convert(plan['segs'].data_ptr(), plan['chunks'].data_ptr(), plan['n'], _stream()),
                 'dlsg_multi_convert')
 
@@ -230,6 +255,7 @@ class CudaBackend:
             return
         assert step.dtype == torch.float32
         self.launches += (plan['n'] + 255) // 256
+        self._mark_writer()
         L.check(self.lib.dlsg_adam_multi(C.cast(plan['table'], C.c_void_p), plan['n'], plan['chunk_elems'], step.data_ptr(),
                                          _ptr(lr_dev), float(lr), float(beta1), float(beta2), float(eps), _stream()), 'dlsg_adam_multi')
 
