@@ -206,6 +206,11 @@ region_aggregate_fwd_kernel(const dlsg_region_agg_fwd_t p) {
       }
       __syncthreads();
     }
+    if (p.scores_only == 2) {                    // measurement only: stream the tiles, no arithmetic (tools/bench_region_agg.py)
+      __syncthreads();
+      if (tile + 2 < ntiles) { ra_fence_async(); issue(tile + 2, stage); }
+      continue;
+    }
     // ---- scores: S'[t][r] = sum_h F'[t][h] Y[r][h]; this warp covers h in [warp*128, warp*128+128).  Row T of F' is ones, so
     // S'[T][r] = sum_h Y[r][h]; the diagonal blocks of Y Y^T (4 more mma per k-step) give sum_h Y[r][h]^2: LayerNorm statistics
     // on the tensor cores, no separate pass over the tile.

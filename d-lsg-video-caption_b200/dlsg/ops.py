@@ -632,7 +632,7 @@ class CudaBackend:
         for name, lst in (('stats', stats), ('St', St), ('tconst', tconst)):
             if lst is not None:
                 self._ra_set(getattr(p, name), lst, contig)
-        p.B, p.E, p.T, p.TR, p.H, p.scores_only, p.scale = B, E, T, TR, H, int(scores_only), float(scale)
+        p.B, p.E, p.T, p.TR, p.H, p.scores_only, p.scale = B, E, T, TR, H, int(scores_only), float(scale)     # (2: loads only, tools)
         self.launches += 1
         L.check(self.lib.dlsg_region_aggregate_fwd(C.byref(p), _stream()), 'dlsg_region_aggregate_fwd')
 

@@ -59,6 +59,8 @@ def main():
          lambda: be.region_aggregate_fwd(Y, F, gamma, beta, scale, T, agg=o['agg'])),
         ('region_aggregate_fwd_kernel (scores pass of the backward)', ybytes,
          lambda: be.region_aggregate_fwd(Y, dA, gamma, beta, scale, T, St=dSm, tconst=tcA, scores_only=True)),
+        ('region_aggregate_fwd_kernel (loads only: the bulk-copy ring without arithmetic)', ybytes,
+         lambda: be.region_aggregate_fwd(Y, dA, gamma, beta, scale, T, St=dSm, tconst=tcA, scores_only=2)),
         ('region_aggregate_prep_kernel + region_aggregate_bwd_kernel', 2 * ybytes,
          lambda: be.region_aggregate_bwd(Y, o['stats'], o['St'], dSm, F, dA, o['U'], o['tconst'], tcA, gamma, beta, scale, T,
                                          dpre=dpre, dF=dF, dgamma=dg, dbeta=db, dbias=dbias, work=work)),
