@@ -392,9 +392,17 @@ attn2_bwd_kernel(const dlsg_attn2_bwd_t p) {
       if (p.dalpha_ext) s += p.dalpha_ext[(int64_t)r * p.ldalpha + hd * p.P + j];
       da[j] = s; dot = fmaf(al[j], s, dot);
     }
-    for (int j = 0; j < p.P; ++j) dl[hd][j] = al[j] * (da[j] - dot) * p.scale;
+    for (int j = 0; j < p.P; ++j) {
+      const float v = al[j] * (da[j] - dot) * p.scale;
+      dl[hd][j] = v;
+      if (p.dl_save) p.dl_save[(int64_t)r * p.ld_dl_save + hd * p.P + j] = v;
+    }
   }
   __syncthreads();
+  // deferred node gradients (dlsg_attn2_bwd_nodes after the time loop): this step only records dl and d(co); the per-step
+  // read-modify-write of dKW / dVW (2 x 80 KB per row and step at nh = 2, P = 5, H = 1024) disappears
+  const bool defer = p.dl_save != nullptr;
+  if (defer && av) *reinterpret_cast<float4*>(p.dco_save + (int64_t)r * p.ld_dco_save + hd * p.Hv + c) = d4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int j = 0; j < APM; ++j) {
@@ -402,6 +410,9 @@ attn2_bwd_kernel(const dlsg_attn2_bwd_t p) {
       const float g = dl[hd][j], a = al[j];
       if (ak) {
         acc.x = fmaf(g, k4[j].x, acc.x); acc.y = fmaf(g, k4[j].y, acc.y); acc.z = fmaf(g, k4[j].z, acc.z); acc.w = fmaf(g, k4[j].w, acc.w);
+      }
+      if (defer) continue;
+      if (ak) {
         float4* dk = reinterpret_cast<float4*>(p.dKW + nk + (int64_t)j * p.Hk + c);
         float4 ok = *dk;
         ok.x = fmaf(g, q4.x, ok.x); ok.y = fmaf(g, q4.y, ok.y); ok.z = fmaf(g, q4.z, ok.z); ok.w = fmaf(g, q4.w, ok.w);
@@ -818,6 +829,55 @@ __global__ void beam_backtrack_kernel(const int64_t* __restrict__ preds, const i
   }
 }
 
+
+// dKW[hd][r][j][:] (+)= sum_t dl[t][r][hd*P+j] q[t][r][:] ;  dVW[hd][r][j][:] (+)= sum_t alpha[t][r][hd*P+j] dco[t][r][hd*Hv + :]
+// (the node gradients of the hoisted attention, accumulated over the T decode steps in ONE launch after the time loop;
+// grid (rows, nh), 256 threads x 4 columns, all loads of a step independent)
+__global__ void __launch_bounds__(256)
+attn2_bwd_nodes_kernel(const float* __restrict__ q_all, int64_t ldq, int64_t q_ts, const float* __restrict__ dl_all, int64_t lddl, int64_t dl_ts,
+                       const float* __restrict__ al_all, int64_t ldal, int64_t al_ts, const float* __restrict__ dco_all, int64_t lddco,
+                       int64_t dco_ts, float* __restrict__ dKW, float* __restrict__ dVW, int T, int rows, int P, int Hk, int Hv, int accum) {
+  pdl_prologue();
+  const int r = blockIdx.x, hd = blockIdx.y, c = threadIdx.x * 4;
+  const bool ak = c < Hk, av = c < Hv;
+  float4 ka[APM], va[APM];
+#pragma unroll
+  for (int j = 0; j < APM; ++j) { ka[j] = make_float4(0.f, 0.f, 0.f, 0.f); va[j] = ka[j]; }
+  for (int t = 0; t < T; ++t) {
+    float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = q4;
+    if (ak) q4 = *reinterpret_cast<const float4*>(q_all + (int64_t)t * q_ts + (int64_t)r * ldq + c);
+    if (av) d4 = *reinterpret_cast<const float4*>(dco_all + (int64_t)t * dco_ts + (int64_t)r * lddco + hd * Hv + c);
+    const float* dlp = dl_all + (int64_t)t * dl_ts + (int64_t)r * lddl + hd * P;
+    const float* alp = al_all + (int64_t)t * al_ts + (int64_t)r * ldal + hd * P;
+#pragma unroll
+    for (int j = 0; j < APM; ++j) {
+      if (j < P) {
+        const float g = dlp[j], a = alp[j];
+        ka[j].x = fmaf(g, q4.x, ka[j].x); ka[j].y = fmaf(g, q4.y, ka[j].y); ka[j].z = fmaf(g, q4.z, ka[j].z); ka[j].w = fmaf(g, q4.w, ka[j].w);
+        va[j].x = fmaf(a, d4.x, va[j].x); va[j].y = fmaf(a, d4.y, va[j].y); va[j].z = fmaf(a, d4.z, va[j].z); va[j].w = fmaf(a, d4.w, va[j].w);
+      }
+    }
+  }
+  const int64_t nk = (((int64_t)hd * rows + r) * P) * Hk, nv = (((int64_t)hd * rows + r) * P) * Hv;
+#pragma unroll
+  for (int j = 0; j < APM; ++j) {
+    if (j < P) {
+      if (ak) {
+        float4* o = reinterpret_cast<float4*>(dKW + nk + (int64_t)j * Hk + c);
+        float4 v = ka[j];
+        if (accum) { const float4 u = *o; v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+        *o = v;
+      }
+      if (av) {
+        float4* o = reinterpret_cast<float4*>(dVW + nv + (int64_t)j * Hv + c);
+        float4 v = va[j];
+        if (accum) { const float4 u = *o; v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+        *o = v;
+      }
+    }
+  }
+}
+
 }  // namespace dlsg
 
 using namespace dlsg;
@@ -929,6 +989,22 @@ int dlsg_beam_backtrack(const int64_t* preds, const int64_t* backs, int32_t S, i
   if (B * beam <= 0 || S <= 0) return 0;
   DLSG_LAUNCH(beam_backtrack_kernel, (B * beam + 127) / 128, 128, 0, (cudaStream_t)stream, preds, backs, S, B, beam, out);
   return check_launch("beam_backtrack_kernel");
+}
+
+
+int dlsg_attn2_bwd_nodes(const float* q_all, int64_t ldq, int64_t q_step_stride, const float* dl_all, int64_t lddl, int64_t dl_step_stride,
+                         const float* alpha_all, int64_t ldalpha, int64_t alpha_step_stride, const float* dco_all, int64_t lddco,
+                         int64_t dco_step_stride, float* dKW, float* dVW, int32_t T, int32_t rows, int32_t nh, int32_t P, int32_t Hk,
+                         int32_t Hv, int32_t accumulate, void* stream) {
+  DLSG_REQUIRE(dlsg_attn2_supported(nh, P, Hk, Hv), "attn2_bwd_nodes: unsupported shape nh=%d P=%d Hk=%d Hv=%d", nh, P, Hk, Hv);
+  DLSG_REQUIRE(q_all && dl_all && alpha_all && dco_all && dKW && dVW, "attn2_bwd_nodes: null operand");
+  DLSG_REQUIRE(ldq % 4 == 0 && q_step_stride % 4 == 0 && lddco % 4 == 0 && dco_step_stride % 4 == 0 &&
+               ((reinterpret_cast<uintptr_t>(q_all) | reinterpret_cast<uintptr_t>(dco_all) | reinterpret_cast<uintptr_t>(dKW) |
+                 reinterpret_cast<uintptr_t>(dVW)) & 15) == 0, "attn2_bwd_nodes: rows must be 16-byte aligned");
+  if (rows <= 0 || T <= 0) return 0;
+  DLSG_LAUNCH(attn2_bwd_nodes_kernel, dim3(rows, nh), 256, 0, (cudaStream_t)stream, q_all, ldq, q_step_stride, dl_all, lddl, dl_step_stride,
+              alpha_all, ldalpha, alpha_step_stride, dco_all, lddco, dco_step_stride, dKW, dVW, T, rows, P, Hk, Hv, accumulate);
+  return check_launch("attn2_bwd_nodes_kernel");
 }
 
 }  // extern "C"

@@ -129,7 +129,8 @@ class Attn2BwdT(C.Structure):
                 ('dy', vp), ('lddy', i64), ('co', vp), ('ldco', i64),
                 ('gamma', vp * 2), ('stats', vp), ('stats_head_stride', i64),
                 ('dgamma_rows', vp), ('dbeta_rows', vp), ('ld_dparam', i64),
-                ('drop_p', f32), ('_pad1', i32), ('seed', u64), ('offset', u64), ('offset_head_stride', u64)]
+                ('drop_p', f32), ('_pad1', i32), ('seed', u64), ('offset', u64), ('offset_head_stride', u64),
+                ('dl_save', vp), ('ld_dl_save', i64), ('dco_save', vp), ('ld_dco_save', i64)]
 
 
 class RegionAggFwdT(C.Structure):
@@ -156,6 +157,7 @@ SIGNATURES = {
     'dlsg_attn2_supported': (i32, [i32, i32, i32, i32]),
     'dlsg_attn2_fwd': (i32, [C.POINTER(Attn2FwdT), vp]),
     'dlsg_attn2_bwd': (i32, [C.POINTER(Attn2BwdT), vp]),
+    'dlsg_attn2_bwd_nodes': (i32, [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     'dlsg_version': (i32, []),
     'dlsg_sm_arch': (i32, []),
     'dlsg_last_error': (C.c_char_p, []),

@@ -329,11 +329,16 @@ class DecoderTrainBlock:
         hoist = core.hoist
         if hoist:
             lc_g, lc_b = empty((T, B, nh * H), ref), empty((T, B, nh * H), ref)     # per-row ctx-LayerNorm gradient terms
+            # d(logits) and d(co) of every step: the node gradients dKW / dVW are summed over time by ONE launch after the loop
+            dl_all, dco_sv = empty((T, B, nh * P), ref), empty((T, B, nh * H), ref)
         else:
             dqp_all = op_empty((TB,), nh * H, ref)
             dco_all = op_empty((T, B), nh * H, ref)
             dctxr = empty((B, nh * H), ref)
-        dKp, dVp = zeros(Kp.shape, ref), zeros(Vp.shape, ref)        # (dKW, dVW when hoisted)
+        if hoist:
+            dKp, dVp = empty(Kp.shape, ref), empty(Vp.shape, ref)    # dKW, dVW: written once by attn2_bwd_nodes
+        else:
+            dKp, dVp = zeros(Kp.shape, ref), zeros(Vp.shape, ref)
         att_scale = 1.0 / math.sqrt(H)
         dcq, dcq2 = small_zeros((B, Hq), ref), empty((B, Hq), ref)
         dcl, dcl2 = zeros((B, Hd), ref), empty((B, Hd), ref)
@@ -365,7 +370,8 @@ class DecoderTrainBlock:
                 be.attn2_bwd(Kp, Vp, b.q32[i], b.alpha[i], None, dXl[i][:, oq:oq + Hq], dKp, dVp, att_scale,
                              dalpha_ext=(da_ext[i] if da_ext is not None else None),
                              ln=dict(dy=dXl[i][:, :nh * H], co=b.co[i], gamma=[lnc[k][0] for k in range(nh)], stats=b.statc[i],
-                                     dgamma_rows=lc_g[i], dbeta_rows=lc_b[i], drop=dc, drop_head_stride=1 << 28))
+                                     dgamma_rows=lc_g[i], dbeta_rows=lc_b[i], drop=dc, drop_head_stride=1 << 28),
+                             save=(dl_all[i], dco_sv[i]))       # node gradients deferred to ONE launch after the loop
             else:
                 for k, h in enumerate(heads):
                     be.norm_bwd(dXl[i][:, k * H:(k + 1) * H], b.co[i][:, k * H:(k + 1) * H], lnc[k][0], lnc[k][1], b.statc[i, k],
@@ -396,6 +402,7 @@ class DecoderTrainBlock:
             be.colsum(ll_g.view(TB, Hd), lnl[2])
             be.colsum(ll_b.view(TB, Hd), lnl[3])
         if hoist:
+            be.attn2_bwd_nodes(b.q32[:T], dl_all, b.alpha[:T], dco_sv, dKp, dVp)
             for k in range(nh):
                 be.colsum(lc_g.view(TB, nh * H)[:, k * H:(k + 1) * H], lnc[k][2])
                 be.colsum(lc_b.view(TB, nh * H)[:, k * H:(k + 1) * H], lnc[k][3])

@@ -534,9 +534,11 @@ class CudaBackend:
         self.launches += 1
         L.check(self.lib.dlsg_attn2_fwd(C.byref(p), _stream()), 'dlsg_attn2_fwd')
 
-    def attn2_bwd(self, KW, VW, q, alpha, dco, dq, dKW, dVW, scale, dalpha_ext=None, ln=None):
+    def attn2_bwd(self, KW, VW, q, alpha, dco, dq, dKW, dVW, scale, dalpha_ext=None, ln=None, save=None):
         """ln = dict(dy=(rows,nh*Hv) fp32 view, co=(rows,nh*Hv), gamma=[..nh], stats=(nh,rows,2), dgamma_rows, dbeta_rows
-        (rows,nh*Hv) views, drop, drop_head_stride): the backward of the fused output layer produces dco in-kernel."""
+        (rows,nh*Hv) views, drop, drop_head_stride): the backward of the fused output layer produces dco in-kernel.
+        save = (dl (rows, nh*P), dco (rows, nh*Hv)) fp32 views: record this step's d(logits) / d(co) instead of accumulating
+        dKW / dVW (attn2_bwd_nodes does that once after the time loop)."""
         self._ck(KW)
         p = L.Attn2BwdT()
         nh, nodes, P, Hk = KW.shape
@@ -561,8 +563,28 @@ class CudaBackend:
                 p.offset_head_stride = ln['drop_head_stride']
         else:
             assert dco is not None
+        if save is not None:
+            dl_s, dco_s = save
+            assert dl_s.stride(1) == 1 and dco_s.stride(1) == 1 and dl_s.dtype == torch.float32 and dco_s.dtype == torch.float32
+            p.dl_save, p.ld_dl_save, p.dco_save, p.ld_dco_save = dl_s.data_ptr(), dl_s.stride(0), dco_s.data_ptr(), dco_s.stride(0)
         self.launches += 1
         L.check(self.lib.dlsg_attn2_bwd(C.byref(p), _stream()), 'dlsg_attn2_bwd')
+
+    def attn2_bwd_nodes(self, q_all, dl_all, alpha_all, dco_all, dKW, dVW, accumulate=False):
+        """q_all (T, rows, Hk), dl_all / alpha_all (T, rows, nh*P), dco_all (T, rows, nh*Hv) fp32 (unit inner strides);
+        dKW / dVW (nh, rows, P, H) contiguous: the node gradients of the hoisted attention summed over the T steps."""
+        self._ck(q_all)
+        T, rows, Hk = q_all.shape
+        nh, rows2, P, Hk2 = dKW.shape
+        Hv = dVW.shape[3]
+        assert rows2 == rows and Hk2 == Hk and dKW.is_contiguous() and dVW.is_contiguous()
+        for x in (q_all, dl_all, alpha_all, dco_all):
+            assert x.dtype == torch.float32 and x.stride(2) == 1 and x.shape[0] == T and x.shape[1] == rows
+        self.launches += 1
+        L.check(self.lib.dlsg_attn2_bwd_nodes(q_all.data_ptr(), q_all.stride(1), q_all.stride(0), dl_all.data_ptr(), dl_all.stride(1),
+                                              dl_all.stride(0), alpha_all.data_ptr(), alpha_all.stride(1), alpha_all.stride(0),
+                                              dco_all.data_ptr(), dco_all.stride(1), dco_all.stride(0), dKW.data_ptr(), dVW.data_ptr(),
+                                              T, rows, nh, P, Hk, Hv, int(accumulate), _stream()), 'dlsg_attn2_bwd_nodes')
 
     # ------------------------------------------------------------------ LatentPSL
     @staticmethod

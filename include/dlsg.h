@@ -269,10 +269,20 @@ typedef struct {
   const float* gamma[2]; const float* stats; int64_t stats_head_stride;
   float* dgamma_rows; float* dbeta_rows; int64_t ld_dparam;
   float drop_p; int32_t _pad1; uint64_t seed, offset, offset_head_stride;
+  /* optional: DEFER the node gradients.  When dl_save != NULL this step records d(logits) (rows, nh*P) [ld_dl_save] and
+   * d(co) (rows, nh*Hv) [ld_dco_save] and does NOT touch dKW / dVW; dlsg_attn2_bwd_nodes accumulates them over all steps
+   * in one launch after the time loop (no per-step read-modify-write of the (nh, rows, P, H) node-gradient tensors). */
+  float* dl_save; int64_t ld_dl_save; float* dco_save; int64_t ld_dco_save;
 } dlsg_attn2_bwd_t;
 int dlsg_attn2_supported(int32_t nh, int32_t P, int32_t Hk, int32_t Hv);
 int dlsg_attn2_fwd(const dlsg_attn2_fwd_t* p, void* stream);
 int dlsg_attn2_bwd(const dlsg_attn2_bwd_t* p, void* stream);
+/* dKW[hd][r][j][:] (+)= sum_t dl[t][r][hd*P+j] q[t][r][:] ; dVW[hd][r][j][:] (+)= sum_t alpha[t][r][hd*P+j] dco[t][r][hd*Hv+:]
+ * over T recorded steps (step t of tensor X at X + t * X_step_stride elements).  accumulate != 0: += onto dKW / dVW.       */
+int dlsg_attn2_bwd_nodes(const float* q_all, int64_t ldq, int64_t q_step_stride, const float* dl_all, int64_t lddl, int64_t dl_step_stride,
+                         const float* alpha_all, int64_t ldalpha, int64_t alpha_step_stride, const float* dco_all, int64_t lddco,
+                         int64_t dco_step_stride, float* dKW, float* dVW, int32_t T, int32_t rows, int32_t nh, int32_t P, int32_t Hk,
+                         int32_t Hv, int32_t accumulate, void* stream);
 
 /* ---- LatentPSL pooling (sublayer.py:191-196), one fused kernel per direction, one CTA per clip (P<=8, T<=32, H%4==0)
  * fwd: Gs (B,T,P) = softmax over T of X theta^T ; N (B,P,H) = Gs^T X.   bwd: dX (B,T,H) written, dtheta (P,H) ACCUMULATED. */

@@ -353,7 +353,7 @@ class CpuEmulBackend:
                               stats=ln['stats'][h], pre_tanh=True, drop=d)
                 self.launches -= 1
 
-    def attn2_bwd(self, KW, VW, q, alpha, dco, dq, dKW, dVW, scale, dalpha_ext=None, ln=None):
+    def attn2_bwd(self, KW, VW, q, alpha, dco, dq, dKW, dVW, scale, dalpha_ext=None, ln=None, save=None):
         self.launches += 1
         nh, nodes, P, Hk = KW.shape
         Hv = VW.shape[3]
@@ -382,8 +382,26 @@ class CpuEmulBackend:
                 da = da + dalpha_ext[:, h * P:(h + 1) * P]
             dl = a * (da - (a * da).sum(1, keepdim=True)) * scale
             dq.add_(torch.einsum('rp,rpk->rk', dl, KW[h]))
+            if save is not None:                      # deferred node gradients: record, attn2_bwd_nodes accumulates
+                save[0][:, h * P:(h + 1) * P].copy_(dl)
+                save[1][:, h * Hv:(h + 1) * Hv].copy_(dc)
+                continue
             dKW[h].add_(torch.einsum('rp,rk->rpk', dl, q))
             dVW[h].add_(torch.einsum('rp,rv->rpv', a, dc))
+
+    def attn2_bwd_nodes(self, q_all, dl_all, alpha_all, dco_all, dKW, dVW, accumulate=False):
+        self.launches += 1
+        nh, rows, P, Hk = dKW.shape
+        Hv = dVW.shape[3]
+        for h in range(nh):
+            k = torch.einsum('trp,trk->rpk', dl_all[:, :, h * P:(h + 1) * P], q_all)
+            v = torch.einsum('trp,trv->rpv', alpha_all[:, :, h * P:(h + 1) * P], dco_all[:, :, h * Hv:(h + 1) * Hv])
+            if accumulate:
+                dKW[h].add_(k)
+                dVW[h].add_(v)
+            else:
+                dKW[h].copy_(k)
+                dVW[h].copy_(v)
 
     # ---- fused region -> frame aggregation (csrc/region_agg.cu): plain composition of the same algebra
     @staticmethod

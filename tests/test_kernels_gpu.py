@@ -413,6 +413,48 @@ def test_attn2_hoisted(be, nh, P, Hk, Hv, rpn):
              dict(dalpha_ext=R(rows, nh * P)), [5, 6, 7], tol=3e-5)
 
 
+@pytest.mark.parametrize('nh,P,Hk,Hv,T', [(2, 5, 1024, 1024, 4), (1, 8, 64, 96, 3), (2, 3, 128, 64, 26)])
+def test_attn2_deferred_node_gradients(be, nh, P, Hk, Hv, T):
+    """Decoder attention backward with the node gradients deferred: every step records d(logits) / d(co)
+    (`save=`) instead of read-modify-writing dKW / dVW, and ONE dlsg_attn2_bwd_nodes launch sums them over time.
+    Equal to the per-step accumulation (kernel vs kernel, and vs the emulator), step slices taken from padded buffers."""
+    rows = 7
+    KW, VW = R(nh, rows, P, Hk, scale=0.3), R(nh, rows, P, Hv)
+    q_all = R(T, rows, Hk + 4)[:, :, :Hk]
+    dco_in = R(T, rows, nh * Hv)
+    al_all = torch.zeros(T, rows, nh * P + 3)[:, :, :nh * P]
+    for t in range(T):
+        EM.attn2_fwd(KW, VW, q_all[t], al_all[t], torch.zeros(rows, nh * Hv), 0.2, 1)
+    dev = lambda x: x.to(DEV)
+    KWd, VWd, qd, ald, dcd = dev(KW), dev(VW), dev(q_all.contiguous()), dev(al_all.contiguous()), dev(dco_in)
+    # (a) per-step accumulation on the device
+    dq_a = torch.zeros(T, rows, Hk, device=DEV)
+    dK_a, dV_a = torch.zeros(nh, rows, P, Hk, device=DEV), torch.zeros(nh, rows, P, Hv, device=DEV)
+    for t in range(T):
+        be.attn2_bwd(KWd, VWd, qd[t], ald[t], dcd[t], dq_a[t], dK_a, dV_a, 0.2)
+    # (b) deferred
+    dq_b = torch.zeros(T, rows, Hk, device=DEV)
+    dl_s, dco_s = torch.zeros(T, rows, nh * P, device=DEV), torch.zeros(T, rows, nh * Hv, device=DEV)
+    dK_b, dV_b = torch.full((nh, rows, P, Hk), 7.0, device=DEV), torch.full((nh, rows, P, Hv), 7.0, device=DEV)
+    untouched = dK_b.clone()
+    for t in range(T):
+        be.attn2_bwd(KWd, VWd, qd[t], ald[t], dcd[t], dq_b[t], dK_b, dV_b, 0.2, save=(dl_s[t], dco_s[t]))
+    assert torch.equal(dK_b, untouched)                       # the step kernel no longer touches the node gradients
+    be.attn2_bwd_nodes(qd, dl_s, ald, dco_s, dK_b, dV_b)
+    torch.cuda.synchronize()
+    assert torch.equal(dq_a, dq_b)
+    for a, b_ in ((dK_a, dK_b), (dV_a, dV_b)):
+        assert float((a - b_).abs().max()) <= 2e-5 * max(1.0, float(a.abs().max()))
+    # accumulate form and the emulator
+    be.attn2_bwd_nodes(qd, dl_s, ald, dco_s, dK_b, dV_b, accumulate=True)
+    torch.cuda.synchronize()
+    assert float((dK_b - 2 * dK_a).abs().max()) <= 4e-5 * max(1.0, float(dK_a.abs().max()))
+    eK, eV = torch.zeros(nh, rows, P, Hk), torch.zeros(nh, rows, P, Hv)
+    EM.attn2_bwd_nodes(q_all, dl_s.cpu(), al_all, dco_s.cpu(), eK, eV)
+    assert float((eK - dK_a.cpu()).abs().max()) <= 3e-5 * max(1.0, float(eK.abs().max()))
+    assert float((eV - dV_a.cpu()).abs().max()) <= 3e-5 * max(1.0, float(eV.abs().max()))
+
+
 @pytest.mark.parametrize('nh,P,Hk,Hv,ydt', [(2, 5, 1024, 1024, torch.bfloat16), (2, 8, 64, 64, torch.float32), (1, 6, 64, 96, torch.float32)])
 def test_attn2_fused_output_layer(be, nh, P, Hk, Hv, ydt):
     """attn2 with the context output layer (tanh -> LayerNorm -> dropout) fused in: forward and backward against the
