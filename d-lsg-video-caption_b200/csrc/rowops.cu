@@ -838,8 +838,16 @@ adam_multi_kernel(const __grid_constant__ AdamArgs a, const float* __restrict__ 
                   float beta1, float beta2, float eps) {
   pdl_prologue();
   __shared__ float sh[2];
+  int lo = 0, hi = a.nsegs - 1;                     // segment of this CTA: last one whose first chunk <= blockIdx.x
+  while (lo < hi) {
+    const int md = (lo + hi + 1) >> 1;
+    if (a.chunk_start[md] <= (int)blockIdx.x) lo = md; else hi = md - 1;
+  }
+  const dlsg_adam_seg_t& sg = a.seg[lo];
   if (threadIdx.x == 0) {
-    const double t = (double)*step;
+    // bias correction from THIS segment's step counter when it has one (torch keeps one `step` per parameter: they
+    // diverge for a parameter that was frozen for a while or restored from another checkpoint), else the launch-wide one
+    const double t = (double)(sg.step ? *sg.step : *step);
     const float lr = lr_dev ? *lr_dev : lr_host;
     const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
     sh[0] = (float)((double)lr / bc1);
@@ -847,12 +855,6 @@ adam_multi_kernel(const __grid_constant__ AdamArgs a, const float* __restrict__ 
   }
   __syncthreads();
   const float step_size = sh[0], bc2_sqrt = sh[1];
-  int lo = 0, hi = a.nsegs - 1;                     // segment of this CTA: last one whose first chunk <= blockIdx.x
-  while (lo < hi) {
-    const int md = (lo + hi + 1) >> 1;
-    if (a.chunk_start[md] <= (int)blockIdx.x) lo = md; else hi = md - 1;
-  }
-  const dlsg_adam_seg_t& sg = a.seg[lo];
   const int64_t row0 = (int64_t)((int)blockIdx.x - a.chunk_start[lo]) * a.rows_per_chunk[lo];
   const int nrows = (int)min((int64_t)a.rows_per_chunk[lo], sg.rows - row0);
   float* P = sg.p + row0 * sg.ld;

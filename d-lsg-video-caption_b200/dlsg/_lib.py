@@ -62,7 +62,7 @@ class CellBwdT(C.Structure):
 
 class AdamSegT(C.Structure):
     _fields_ = [('p', vp), ('g', vp), ('m', vp), ('v', vp), ('dst16', vp), ('rows', i64), ('cols', i64), ('ld', i64), ('ld_dst', i64),
-                ('ld_g', i64), ('g_dtype', i32), ('_pad', i32)]
+                ('ld_g', i64), ('g_dtype', i32), ('_pad', i32), ('step', vp)]
 
 
 class NormBwd2T(C.Structure):

@@ -230,7 +230,7 @@ class CudaBackend:
 
     def make_adam_plan(self, segs, chunk_elems=16384):
         """segs: list of dicts {p, m, v: 2-D fp32 views with one common pitch, g: fp32 | bf16 view of the same shape (own
-        pitch), dst: bf16 2-D view | None}.  The plan is a
+        pitch), dst: bf16 2-D view | None, step: optional device scalar with this parameter's own step count}.  The plan is a
         host table: it rides to the device inside the kernel parameters (no upload; graph-capturable as is)."""
         table = (L.AdamSegT * max(1, len(segs)))()
         for i, sg in enumerate(segs):
@@ -245,6 +245,9 @@ class CudaBackend:
             e.p, e.g, e.m, e.v = p_.data_ptr(), g_.data_ptr(), m_.data_ptr(), v_.data_ptr()
             e.rows, e.cols, e.ld = rows, cols, ld
             e.ld_g, e.g_dtype = (g_.stride(0) if rows > 1 else cols), _dt(g_)
+            if sg.get('step') is not None:
+                assert sg['step'].dtype == torch.float32 and sg['step'].numel() == 1
+                e.step = sg['step'].data_ptr()
             if d_ is not None:
                 assert d_.dtype == torch.bfloat16 and d_.shape == p_.shape and (cols == 1 or d_.stride(1) == 1)
                 e.dst16, e.ld_dst = d_.data_ptr(), (d_.stride(0) if rows > 1 else cols)

@@ -110,11 +110,11 @@ class AdamDriver:
                 m, v = st['exp_avg'], st['exp_avg_sq']
                 sh = self.shadow.get(id(p))
                 if sh is None:
-                    segs.append(dict(p=_as2d(p.data), g=_as2d(grad), m=_as2d(m), v=_as2d(v), dst=None))
+                    segs.append(dict(p=_as2d(p.data), g=_as2d(grad), m=_as2d(m), v=_as2d(v), dst=None, step=st['step']))
                 else:
                     for r0, c0, nr, nc, dst in sh:
                         sl = (slice(r0, r0 + nr), slice(c0, c0 + nc))
-                        segs.append(dict(p=p.data[sl], g=grad[sl], m=m[sl], v=v[sl], dst=dst))
+                        segs.append(dict(p=p.data[sl], g=grad[sl], m=m[sl], v=v[sl], dst=dst, step=st['step']))
             torch._foreach_add_(steps, 1)
             plan = be.make_adam_plan(segs)
             b1, b2 = g['betas']

@@ -101,6 +101,8 @@ typedef struct {
   int64_t rows, cols, ld, ld_dst;
   int64_t ld_g;                               /* pitch of g (its own: a slice of a flat gradient bucket)            */
   int32_t g_dtype, _pad;                      /* DLSG_F32 | DLSG_BF16: data-parallel buckets are reduced in bf16    */
+  const float* step;                          /* optional DEVICE scalar: this parameter's own (already incremented)  */
+                                              /* step count; NULL = the launch-wide step_dev                         */
 } dlsg_adam_seg_t;
 int dlsg_adam_multi(const dlsg_adam_seg_t* segs_host, int32_t nsegs, int32_t chunk_elems, const float* step_dev,
                     const float* lr_dev, float lr, float beta1, float beta2, float eps, void* stream);

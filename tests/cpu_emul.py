@@ -65,10 +65,10 @@ class CpuEmulBackend:
 
     def adam_multi(self, plan, step, lr, beta1, beta2, eps, lr_dev=None):
         self.launches += 1
-        t = float(step)
         lr = float(lr_dev) if lr_dev is not None else lr
-        bc1, bc2 = 1.0 - beta1 ** t, 1.0 - beta2 ** t
         for sg in plan['segs']:
+            t = float(sg['step']) if sg.get('step') is not None else float(step)      # per-parameter step counters
+            bc1, bc2 = 1.0 - beta1 ** t, 1.0 - beta2 ** t
             p_, g_, m_, v_ = sg['p'], sg['g'], sg['m'], sg['v']
             g_ = g_.float()
             m_.copy_(m_ + (g_ - m_) * (1 - beta1))

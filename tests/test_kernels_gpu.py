@@ -221,6 +221,20 @@ def test_adam_multi_segments(be):
             assert (c[k] - g[k].cpu()).abs().max() <= 2e-6 * max(1.0, float(c[k].abs().max())), k
     for c, g in zip(dst_cpu, dst_gpu):
         assert (c.float() - g.float().cpu()).abs().max() <= 1e-2
+    # per-parameter step counters (torch keeps one `step` per parameter; they diverge for a parameter that sat out some
+    # steps): each segment's bias correction follows its own counter, not the launch-wide one
+    own = [3.0, 3.0, 11.0, 1.0, 40.0]
+    grads_c = [R(*s_, scale=0.3) for s_ in shapes]
+    grads_g = [g.to(DEV) for g in grads_c]
+    sc, sg_ = segs(cpu, dst_cpu, grads_c), segs(gpu, dst_gpu, grads_g)
+    for k_, (a_, b_) in enumerate(zip(sc, sg_)):
+        a_['step'] = torch.tensor(own[k_])
+        b_['step'] = torch.tensor(own[k_], device=DEV)
+    EM.adam_multi(EM.make_adam_plan(sc), torch.tensor(999.0), 1.6e-4, 0.5, 0.9, 1e-8)
+    be.adam_multi(be.make_adam_plan(sg_), torch.tensor(999.0, device=DEV), 123.0, 0.5, 0.9, 1e-8, lr_dev=lr_g)
+    torch.cuda.synchronize()
+    for c, g in zip(cpu, gpu):
+        assert (c['p'] - g['p'].cpu()).abs().max() <= 2e-6 * max(1.0, float(c['p'].abs().max()))
 
 
 def test_multi_convert_segments(be):
