@@ -582,13 +582,19 @@ def main(argv=None):
         flops = 2.0 * Mr * Nr * Kr
         ach = flops / (k_ms * 1e-3) / 1e12
         peak = peaks.get('bf16_tflops', 1590.0)
-        line['roofline'] = {'bound': 'tensor', 'kernel': 'gemm_tc_kernel<256> region projection %dx%dx%d bf16 (+bias+tanh, bf16 out)' % (Mr, Nr, Kr),
+        line['roofline'] = {'bound': 'tensor', 'kernel': 'gemm_tc_kernel<256, pair> region projection %dx%dx%d bf16 (+bias+tanh, bf16 out), '
+                                                         '256x256 tiles on CTA pairs (tcgen05.mma.cta_group::2)' % (Mr, Nr, Kr),
                             'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
                             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the committed ncu --set full
-                            # capture profiles/r01_ncu_full_top_kernels_v2.json (algorithmic: A 245 MB + W 8 MB read, 245 MB written)
-                            'traffic': 253.84e6 + 208.14e6, 'traffic_unit': 'bytes/launch',
+                            # capture profiles/r02u_ncu_full_top_kernels.json (algorithmic: A 245 MB + W 8 MB read, 245 MB written)
+                            'traffic': 253.84e6 + 210.18e6, 'traffic_unit': 'bytes/launch',
                             'peak_source': 'measured (MEASURED_PEAKS.json bf16_tflops, burst)' if 'bf16_tflops' in peaks else 'fallback',
                             'ms_per_launch': k_ms, 'launches_per_step': 1}
+        if 'bf16_tflops_sustained' in peaks:
+            # the launches above run back to back (the regime of MEASURED_PEAKS' sustained figure: clocks drop under a continuous
+            # tensor load); `frac` stays against the burst peak, this is the same measurement against the sustained one
+            line['roofline']['peak_sustained'] = peaks['bf16_tflops_sustained']
+            line['roofline']['frac_of_sustained'] = ach / peaks['bf16_tflops_sustained']
         del A, Wt, O_
         _RESULT.update(line)
     # ---- decoding throughput (secondary metrics of BASELINE.json: greedy B=256, beam-5 B=128), one GPU

@@ -10,6 +10,7 @@
 // tile index -> (batch*splitk, P tile, Q tile) with the Q tile fastest.  Every spin-wait is bounded and traps
 // instead of hanging.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace dlsg {
@@ -76,6 +77,39 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// ---- CTA-pair (cta_group::2) helpers: PTX forms as in CUTLASS cute/arch/{copy_sm100_tma,mma_sm100_umma}.hpp, cutlass/arch/barrier.h
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // shared::cluster address of the same offset in the EVEN CTA of the pair
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+// both CTAs of a pair load their own tile; the bytes are counted on the LEADER's barrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// MMA completion -> the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+// arrive on the barrier at this offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+               "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(rank) : "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 version=1)
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -119,13 +153,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr) : "memory");
 }
 
-template <int BN> struct TcCfg {
+// NCTA = 2: a CTA pair (thread-block cluster of two, one TPC) computes a 256 x BN tile with tcgen05.mma.cta_group::2 - each CTA
+// stages its own 128 rows of A and HALF of the B tile, the leader issues the MMAs for both, each CTA's TMEM receives its
+// 128 accumulator rows.  Per k-block a CTA fills 16 KB + BN/2 rows instead of 16 KB + BN rows: the L2 -> SM operand traffic
+// per flop drops by 1/3 at BN = 256 (the 1-CTA 128 x 256 tile is exactly L2-bandwidth bound at 85 flop/B).
+template <int BN, int NCTA = 1> struct TcCfg {
 #ifndef DLSG_SKINNY_STAGES
 #define DLSG_SKINNY_STAGES 6      /* 8 measured 0.08 ms/step slower (216 KB CTAs co-reside less with the preceding kernel) */
 #endif
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN <= 64 ? DLSG_SKINNY_STAGES : 6);
+  static constexpr int STAGES = (NCTA == 2) ? 6 : ((BN >= 256) ? 4 : (BN <= 64 ? DLSG_SKINNY_STAGES : 6));
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = BN / NCTA;                                    // rows of B this CTA stages
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_BYTES = 4 * 32 * EPI_PADV * 4;
   static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;  // +1024 alignment slack
@@ -142,10 +181,14 @@ __device__ __forceinline__ float tanh_fast(float x) {
 // Persistent: grid = min(#tiles, #SMs); CTA walks tiles t = blockIdx.x + i*gridDim.x (n-tile fastest so that the CTAs
 // running concurrently share A row-panels and the whole weight matrix in L2).  Two TMEM accumulator stages let the
 // epilogue of tile i overlap the TMA/MMA main loop of tile i+1.
-template <int BN>
+template <int BN, int NCTA>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams prm) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, NCTA>;
+  // CTA pair: rank 0 (leader) issues the MMAs; unit = the pair.  prm.ntm then counts 256-row tile PAIRS.
+  const uint32_t crank = (NCTA == 2) ? cluster_ctarank() : 0u;
+  const int unit = (NCTA == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nunits = (NCTA == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* tiles = smem;
@@ -172,17 +215,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tfull_bar[s]), 1);
-      mbar_init(smem_u32(&tempty_bar[s]), 4);          // one arrival per epilogue warp
+      mbar_init(smem_u32(&tempty_bar[s]), 4 * NCTA);   // one arrival per epilogue warp (of both CTAs of a pair, on the leader)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (NCTA == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all(); else __syncthreads();   // the pair's barriers exist before any remote arrive
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) tc_trace(prm, 1);               // barriers + TMEM ready
@@ -192,7 +241,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // latency-bound kernels of the chain; only the dependent operand (64 activation rows) waits.
   const bool is_producer = (warp == 0 && lane == 0);
   int pre = 0;
-  if (is_producer && (prm.pre_a | prm.pre_b) && (int)blockIdx.x < tiles_total) {
+  if (NCTA == 1 && is_producer && (prm.pre_a | prm.pre_b) && (int)blockIdx.x < tiles_total) {
     const int tile = blockIdx.x;
     const int tn = tile % ntn, tm = (tile / ntn) % ntm, z = tile / (ntn * ntm);
     const int zb = z / prm.splitk, zs = z % prm.splitk;
@@ -229,14 +278,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===== TMA producer =====
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
-        const int tn = tile % ntn, tm = (tile / ntn) % ntm, z = tile / (ntn * ntm);
+      for (int tile = unit; tile < tiles_total; tile += nunits) {
+        const int tn = tile % ntn, tmu = (tile / ntn) % ntm, z = tile / (ntn * ntm);
+        const int tm = (NCTA == 2) ? tmu * 2 + (int)crank : tmu;       // this CTA's 128-row tile
         const int zb = z / prm.splitk, zs = z % prm.splitk;
         const int kb_begin = zs * prm.kb_per_split;
         const int nkb = min(prm.kb_total, kb_begin + prm.kb_per_split) - kb_begin;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
           const uint32_t full = smem_u32(&full_bar[s]);
+          if constexpr (NCTA == 2) {
+            // both CTAs stage their own A rows and their half of the B tile; all bytes are counted on the leader's barrier
+            if (crank == 0) mbar_expect_tx(full, 2 * Cfg::STAGE_BYTES);
+            const uint32_t a_dst = smem_u32(tiles + s * Cfg::STAGE_BYTES);
+            const int kc = (kb_begin + kb) * BK;
+            const int bq0 = tn * BN + (int)crank * Cfg::B_ROWS;
+            if (!prm.a_mn) {
+              tma_load_3d_2sm(a_dst, &tmA, full, kc, tm * BM, zb);
+            } else {
+              tma_load_3d_2sm(a_dst, &tmA, full, tm * BM, kc, zb);
+              tma_load_3d_2sm(a_dst + MN_BLOCK_BYTES, &tmA, full, tm * BM + 64, kc, zb);
+            }
+            if (!prm.b_mn) {
+              tma_load_3d_2sm(a_dst + Cfg::A_BYTES, &tmB, full, kc, bq0, zb);
+            } else {
+#pragma unroll
+              for (int jb = 0; jb < Cfg::B_ROWS / 64; ++jb)
+                tma_load_3d_2sm(a_dst + Cfg::A_BYTES + jb * MN_BLOCK_BYTES, &tmB, full, bq0 + 64 * jb, kc, zb);
+            }
+            if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+            continue;
+          }
           // the first `pre` k-blocks of this CTA's first tile: transaction count armed and static operand(s) already in flight
           const bool early = (tile == (int)blockIdx.x) && (kb < pre);
           if (!early) mbar_expect_tx(full, Cfg::STAGE_BYTES);
@@ -266,17 +338,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_trace(prm, 3);                                 // all loads issued
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one elected thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer (one elected thread; in a CTA pair only the leader's) =====
+    if (lane == 0 && crank == 0) {
       // instruction descriptor: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24
       //                         a_major @15, b_major @16 (1 = MN-major)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24) |
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * NCTA) >> 4) << 24) |
                              (prm.a_mn ? (1u << 15) : 0u) | (prm.b_mn ? (1u << 16) : 0u);
       // descriptor advance per UMMA_K=16 step: K-major +32 B inside the swizzle row, MN-major +16 K-rows (2048 B)
       const uint32_t a_step = prm.a_mn ? (16 * 128) >> 4 : 2, b_step = prm.b_mn ? (16 * 128) >> 4 : 2;
       int s = 0; uint32_t ph = 0;
       int acc = 0; uint32_t acc_ph = 0;
-      for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+      for (int tile = unit; tile < tiles_total; tile += nunits) {
         const int z = tile / (ntn * ntm);
         const int zs = z % prm.splitk;
         const int kb_begin = zs * prm.kb_per_split;
@@ -292,12 +364,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t adesc = prm.a_mn ? make_sw128_mn_desc(a_addr, MN_BLOCK_BYTES) : make_sw128_desc(a_addr);
           const uint64_t bdesc = prm.b_mn ? make_sw128_mn_desc(a_addr + Cfg::A_BYTES, MN_BLOCK_BYTES) : make_sw128_desc(a_addr + Cfg::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16(tmem_d, adesc + (uint64_t)(a_step * k), bdesc + (uint64_t)(b_step * k), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(smem_u32(&empty_bar[s]));                      // frees the smem slot when the MMAs retire
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            if constexpr (NCTA == 2)
+              umma_bf16_2sm(tmem_d, adesc + (uint64_t)(a_step * k), bdesc + (uint64_t)(b_step * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16(tmem_d, adesc + (uint64_t)(a_step * k), bdesc + (uint64_t)(b_step * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if constexpr (NCTA == 2) umma_commit_2sm(smem_u32(&empty_bar[s]));   // frees the slot in BOTH CTAs
+          else umma_commit(smem_u32(&empty_bar[s]));                 // frees the smem slot when the MMAs retire
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(smem_u32(&tfull_bar[acc]));                      // accumulator complete -> epilogue
+        if constexpr (NCTA == 2) umma_commit_2sm(smem_u32(&tfull_bar[acc]));   // both CTAs' epilogues
+        else umma_commit(smem_u32(&tfull_bar[acc]));                 // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
       }
       tc_trace(prm, 5);                                 // all MMAs issued
@@ -322,12 +400,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool vec_f32 = !prm.store_t && !bf16_out && !prm.do_tanh && !prm.atomic && al16 && bias16 && (prm.ldd % 4 == 0) &&
                          ((prm.stride_d | prm.stride_split) % 4 == 0);
     int acc = 0; uint32_t acc_ph = 0;
-    for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
-      const int tn = tile % ntn, tm = (tile / ntn) % ntm, z = tile / (ntn * ntm);
+    for (int tile = unit; tile < tiles_total; tile += nunits) {
+      const int tn = tile % ntn, tmu = (tile / ntn) % ntm, z = tile / (ntn * ntm);
+      const int tm = (NCTA == 2) ? tmu * 2 + (int)crank : tmu;
       const int zb = z / prm.splitk, zs = z % prm.splitk;
       const int p0 = tm * BM, q0 = tn * BN;
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_ph);
-      if (threadIdx.x == 64 && tile + (int)gridDim.x >= tiles_total) tc_trace(prm, 6);   // last accumulator complete
+      if (threadIdx.x == 64 && tile + nunits >= tiles_total) tc_trace(prm, 6);   // last accumulator complete
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS) + ((uint32_t)(g * 32) << 16);
       const int p_row = p0 + g * 32 + lane;                  // this thread's accumulator row
@@ -347,7 +426,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty_bar[acc])) : "memory");
+          if (lane == 0) {
+            if constexpr (NCTA == 2) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]), 0);     // the leader's MMA thread waits for both CTAs
+            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty_bar[acc])) : "memory");
+          }
         }
         float f[32];
 #pragma unroll
@@ -554,11 +636,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all(); else __syncthreads();   // neither CTA of a pair leaves while the other may still touch it
   if (threadIdx.x == 0) tc_trace(prm, 7);               // epilogue stores issued, CTA about to exit
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+    if constexpr (NCTA == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
   }
 }
 
@@ -632,12 +717,34 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcParam
   using Cfg = TcCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     DLSG_REQUIRE(e == cudaSuccess, "gemm_tc: cudaFuncSetAttribute(%d) failed: %s", Cfg::SMEM, cudaGetErrorString(e));
     attr_set = true;
   }
-  DLSG_LAUNCH(gemm_tc_kernel<BN>, grid, TC_THREADS, Cfg::SMEM, st, ta, tb, prm);
+  DLSG_LAUNCH((gemm_tc_kernel<BN, 1>), grid, TC_THREADS, Cfg::SMEM, st, ta, tb, prm);
   return check_launch("gemm_tc_kernel");
+}
+
+// CTA-pair variant: thread-block cluster (2,1,1) + programmatic dependent launch
+template <int BN>
+static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& prm, dim3 grid, cudaStream_t st) {
+  using Cfg = TcCfg<BN, 2>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    DLSG_REQUIRE(e == cudaSuccess, "gemm_tc: cudaFuncSetAttribute(%d) failed: %s", Cfg::SMEM, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, 2>, ta, tb, prm);
+  return check_launch("gemm_tc_kernel<pair>");
 }
 
 static int gemm_tc_direct(const dlsg_gemm_t* g, cudaStream_t st);
@@ -760,10 +867,26 @@ static int gemm_tc_direct(const dlsg_gemm_t* g, cudaStream_t st) {
     if (Q > 128 && cost(256) <= cost(bn)) bn = 256;
     if (cost(64) < cost(bn)) bn = 64;        // small problems: more, narrower tiles cover more SMs
   }
+  // CTA pairs (256 x bn tiles, tcgen05.mma.cta_group::2) for the big tensor-bound products: many tiles, no split-K.  The
+  // 1-CTA 128 x 256 tile moves (128 + 256) rows per k-block for 128 x 256 outputs = 85 flop/B and is L2 -> SM bandwidth bound
+  // (measured 15.3 TB/s aggregate = 1300 TFLOP/s); a pair moves (256 + 256) rows for 256 x 256 outputs = 128 flop/B.
+  static const bool pair_on = [] { const char* e = getenv("DLSG_GEMM_2CTA"); return !(e && e[0] == '0'); }();
+  const bool pair = pair_on && splitk == 1 && bn >= 128 && ptiles >= 2 && tiles_for(bn) >= 96;   // a pair occupies two SMs: never fewer SMs busy
   CUtensorMap ta, tb;
   if (make_map(&ta, Ap, P, g->K, ldp, batch, strp, BM, p_mn)) return -1;
-  if (make_map(&tb, Bq, Q, g->K, ldq, batch, strq, bn, q_mn)) return -1;
+  if (make_map(&tb, Bq, Q, g->K, ldq, batch, strq, pair ? bn / 2 : bn, q_mn)) return -1;
   prm.a_mn = p_mn ? 1 : 0; prm.b_mn = q_mn ? 1 : 0;
+  if (pair) {
+    prm.pre_a = prm.pre_b = 0;
+    prm.ntm = (ptiles + 1) / 2;                  // 256-row tile pairs (an odd last 128-row tile is zero-filled / masked)
+    prm.ntn = (Q + bn - 1) / bn;
+    const int64_t units = (int64_t)prm.ntm * prm.ntn * batch;
+    DLSG_REQUIRE(units < (1ll << 31), "gemm_tc: too many tiles");
+    prm.tiles_total = (int)units;
+    const int64_t npairs = units < kNumSM / 2 ? units : kNumSM / 2;
+    dim3 grid2((unsigned)(2 * npairs));
+    return bn == 128 ? launch_tc_pair<128>(ta, tb, prm, grid2, st) : launch_tc_pair<256>(ta, tb, prm, grid2, st);
+  }
   {
     const bool a_static = (g->flags & DLSG_GEMM_A_STATIC) != 0, b_static = (g->flags & DLSG_GEMM_B_STATIC) != 0;
     prm.pre_a = (swap ? b_static : a_static) ? 1 : 0;

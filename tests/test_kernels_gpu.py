@@ -93,6 +93,24 @@ def test_gemm_tc_epilogues(be, M, N, K):
     both('gemm', be, [a, b, R(M, N + 4)[:, 4:]], dict(accum=True, bias=bias_n), [2], tol=2e-3)
 
 
+@pytest.mark.parametrize('M,N,K', [(8192, 2048, 192), (128 * 75 + 17, 1024, 136), (5000, 1000, 72), (4736, 2048, 2048)])
+def test_gemm_tc_cta_pair_tiles(be, M, N, K):
+    """Shapes large enough for the CTA-pair path (256 x bn tiles, tcgen05.mma.cta_group::2, thread-block cluster of two):
+    an odd number of 128-row tiles (the last pair is half empty), N not a multiple of the tile, K tails, the bias + tanh bf16
+    epilogue of the region projection, fp32 accumulate, a transposed store, and both operands MN-major (the weight-gradient
+    form); each against the fp32 product of the same bf16 operands."""
+    a, b = bf(R(M, K, scale=0.2)), bf(R(N, K, scale=0.2))
+    bias_n = R(N)
+    both('gemm', be, [a, b, torch.zeros(M, N)], {}, [2], tol=2e-3)
+    both('gemm', be, [a, b, torch.zeros(M, N, dtype=torch.bfloat16)], dict(bias=bias_n, tanh=True), [2], tol=1e-2)
+    both('gemm', be, [a, b, R(M, N)], dict(accum=True, bias=bias_n), [2], tol=2e-3)
+    both('gemm', be, [a, b, torch.zeros(N, M).t()], dict(bias=bias_n), [2], tol=2e-3)                       # STORE_T
+    if K % 8 == 0 and M % 8 == 0 and N % 8 == 0:
+        at, bt = bf(R(K, M, scale=0.2)), bf(R(K, N, scale=0.2))                                            # MN-major views
+        both('gemm', be, [at.t(), bt.t(), torch.zeros(M, N)], {}, [2], tol=2e-3)
+        both('gemm', be, [a, bt.t(), torch.zeros(M, N)], {}, [2], tol=2e-3)
+
+
 def test_gemm_tc_batched_and_strided_views(be):
     B_, M, N, K = 6, 150, 40, 136
     a, b = bf(R(B_, M, K)), bf(R(B_, N, K))
