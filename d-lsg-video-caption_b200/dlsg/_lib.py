@@ -133,6 +133,12 @@ class Attn2BwdT(C.Structure):
                 ('dl_save', vp), ('ld_dl_save', i64), ('dco_save', vp), ('ld_dco_save', i64)]
 
 
+class LstmStepT(C.Structure):
+    _fields_ = [('W', vp * 2), ('h_in', vp * 2), ('ldh_in', i64), ('gin', vp * 2), ('ldgin', i64), ('c_in', vp * 2), ('c_out', vp * 2),
+                ('acts', vp * 2), ('h_out', vp * 2), ('ldh_out', i64), ('h_op', vp * 2), ('ldh_op', i64),
+                ('B', i32), ('H', i32), ('ndir', i32), ('_pad', i32)]
+
+
 class RegionAggFwdT(C.Structure):
     _fields_ = [('Y', vp * 2), ('ldy', i64), ('F', vp * 2), ('ldf', i64), ('gamma', vp * 2), ('beta', vp * 2),
                 ('agg', vp * 2), ('ldagg', i64), ('U', vp * 2), ('ldu', i64),
@@ -150,6 +156,8 @@ class RegionAggBwdT(C.Structure):
 
 
 SIGNATURES = {
+    'dlsg_lstm_step_supported': (i32, [i32, i32]),
+    'dlsg_lstm_step_fwd': (i32, [C.POINTER(LstmStepT), vp]),
     'dlsg_region_aggregate_supported': (i32, [i32, i32, i32]),
     'dlsg_region_aggregate_fwd': (i32, [C.POINTER(RegionAggFwdT), vp]),
     'dlsg_region_aggregate_bwd_workspace': (i64, [i32, i32, i32]),

@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), 'csrc')
 LIB = os.path.join(HERE, 'libdlsg.so')
-SOURCES = ['api.cu', 'gemm_tc.cu', 'gemm_simt.cu', 'rowops.cu', 'decode_ops.cu', 'graph_ops.cu', 'fused_step.cu', 'norm_bf16.cu', 'region_agg.cu']
+SOURCES = ['api.cu', 'gemm_tc.cu', 'gemm_simt.cu', 'rowops.cu', 'decode_ops.cu', 'graph_ops.cu', 'fused_step.cu', 'norm_bf16.cu', 'region_agg.cu', 'lstm_step.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Xptxas', '-v']

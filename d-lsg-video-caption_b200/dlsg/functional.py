@@ -20,6 +20,8 @@ from .linalg import empty, zeros, small_zeros, op, op_empty, op_zeros, mm32, fla
 
 # DLSG_FUSED_REGION_AGG=0 keeps the unfused LayerNorm / GEMM / softmax / GEMM composition (measurement switch)
 FUSED_REGION_AGG = os.environ.get('DLSG_FUSED_REGION_AGG', '1') != '0'
+# DLSG_FUSED_LSTM_STEP=0 keeps the recurrent GEMM + cell kernel pair per BiLSTM step (measurement switch)
+FUSED_LSTM_STEP = os.environ.get('DLSG_FUSED_LSTM_STEP', '1') != '0'
 
 _seed_counter = itertools.count(1)
 
@@ -570,11 +572,12 @@ class EncoderVisualBlock:
         lstm_out = empty((B, T, 2 * H), frames)
         # the two directions run concurrently: each recurrent GEMM is split over K to fill HALF of the SMs and the cell
         # kernel sums the partials itself (no reduce launch)
-        Sg = la.splitk_for(B, H4, H, sms=74)
+        whh = [WC.get(t[pf + 'lstm.weight_hh_l0']), WC.get(t[pf + 'lstm.weight_hh_l0_reverse'])]
+        fused_step = FUSED_LSTM_STEP and whh[0].dtype == torch.bfloat16 and be.lstm_step_supported(B, H)
+        Sg = 1 if fused_step else la.splitk_for(B, H4, H, sms=74)
         gates = zeros((Sg, 2, T, B, H4), frames)     # [0] ends up holding the activated gates (saved for BPTT)
         cs = zeros((2, T + 1, B, H), frames)
         hprev = op_zeros((2, B, T), H, frames)       # h fed INTO step t (operand dtype), clip-major like Gin / dGin
-        whh = [WC.get(t[pf + 'lstm.weight_hh_l0']), WC.get(t[pf + 'lstm.weight_hh_l0_reverse'])]
 
         def run_dir(d):
             order = list(range(T)) if d == 0 else list(range(T - 1, -1, -1))
@@ -584,7 +587,19 @@ class EncoderVisualBlock:
                 nxt = order[k + 1] if k + 1 < T else None
                 be.lstm_cell_fwd(gates[:, d, tt], cs[d, k], cs[d, k + 1], row_bias=Gin[:, tt, d * H4:(d + 1) * H4],
                                  h2=lstm_out[:, tt, d * H:(d + 1) * H], h3=(hprev[d, :, nxt] if nxt is not None else None))
-        two_streams(frames, lambda: run_dir(0), lambda: run_dir(1))     # the two directions are independent chains
+        if fused_step:
+            # ONE launch per time step for BOTH directions: recurrent product + cell per CTA owning 16 hidden units
+            # (csrc/lstm_step.cu) instead of split-K tcgen05 GEMM + cell kernel per direction on two streams
+            for k in range(T):
+                tt = (k, T - 1 - k)
+                nx = (k + 1, T - 2 - k) if k + 1 < T else None
+                be.lstm_step_fwd(whh, [hprev[d, :, tt[d]] for d in (0, 1)] if k > 0 else None,
+                                 [Gin[:, tt[d], d * H4:(d + 1) * H4] for d in (0, 1)], [cs[d, k] for d in (0, 1)],
+                                 [cs[d, k + 1] for d in (0, 1)], [gates[0, d, tt[d]] for d in (0, 1)],
+                                 [lstm_out[:, tt[d], d * H:(d + 1) * H] for d in (0, 1)],
+                                 [hprev[d, :, nx[d]] for d in (0, 1)] if nx is not None else None)
+        else:
+            two_streams(frames, lambda: run_dir(0), lambda: run_dir(1))     # the two directions are independent chains
         Y = empty((B * T, 2 * H), frames)
         stY = empty((B * T, 2), frames)
         dY = site(self.p if training else 0.0, seed, 1)

@@ -610,6 +610,44 @@ class CudaBackend:
         L.check(self.lib.dlsg_latent_psl_bwd(X.data_ptr(), theta.data_ptr(), Gs.data_ptr(), dN.data_ptr(), dX.data_ptr(),
                                              dtheta.data_ptr(), B, T, P, H, _stream()), 'latent_psl_bwd')
 
+    # ------------------------------------------------------------------ one LSTM step (recurrent product + cell) in one launch
+    def lstm_step_supported(self, B, H):
+        return bool(self.lib.dlsg_lstm_step_supported(B, H))
+
+    def lstm_step_fwd(self, W, h_in, gin, c_in, c_out, acts, h_out=None, h_op=None):
+        """Lists with one entry per direction (<= 2).  W[d] bf16 (4H, H) contiguous; h_in[d] bf16 (B, H) view or h_in=None for
+        the first step; gin[d] fp32 (B, 4H) view; c_in / c_out fp32 (B, H) contiguous; acts[d] fp32 (B, 4H) contiguous
+        (activated gates out); h_out[d] fp32 (B, H) view; h_op[d] bf16 (B, H) view (the next step's h_in) or None."""
+        nd = len(W)
+        p = L.LstmStepT()
+        B, H4 = gin[0].shape
+        H = H4 // 4
+        self._ck(gin[0])
+        for d in range(nd):
+            assert W[d].dtype == torch.bfloat16 and W[d].is_contiguous() and tuple(W[d].shape) == (H4, H)
+            assert gin[d].dtype == torch.float32 and gin[d].stride(1) == 1 and gin[d].stride(0) == gin[0].stride(0)
+            assert c_out[d].is_contiguous() and acts[d].is_contiguous() and acts[d].dtype == torch.float32
+            p.W[d], p.gin[d], p.c_out[d], p.acts[d] = W[d].data_ptr(), gin[d].data_ptr(), c_out[d].data_ptr(), acts[d].data_ptr()
+            if c_in is not None and c_in[d] is not None:
+                assert c_in[d].is_contiguous()
+                p.c_in[d] = c_in[d].data_ptr()
+            if h_in is not None:
+                assert h_in[d].dtype == torch.bfloat16 and h_in[d].stride(1) == 1 and h_in[d].stride(0) == h_in[0].stride(0)
+                p.h_in[d] = h_in[d].data_ptr()
+            if h_out is not None:
+                assert h_out[d].dtype == torch.float32 and h_out[d].stride(1) == 1 and h_out[d].stride(0) == h_out[0].stride(0)
+                p.h_out[d] = h_out[d].data_ptr()
+            if h_op is not None:
+                assert h_op[d].dtype == torch.bfloat16 and h_op[d].stride(1) == 1 and h_op[d].stride(0) == h_op[0].stride(0)
+                p.h_op[d] = h_op[d].data_ptr()
+        p.ldgin = gin[0].stride(0)
+        p.ldh_in = h_in[0].stride(0) if h_in is not None else 0
+        p.ldh_out = h_out[0].stride(0) if h_out is not None else 0
+        p.ldh_op = h_op[0].stride(0) if h_op is not None else 0
+        p.B, p.H, p.ndir = B, H, nd
+        self.launches += 1
+        L.check(self.lib.dlsg_lstm_step_fwd(C.byref(p), _stream()), 'dlsg_lstm_step_fwd')
+
     # ------------------------------------------------------------------ fused region -> frame aggregation (layer.py:184-192)
     def region_aggregate_supported(self, T, TR, H, dtype):
         return dtype == torch.bfloat16 and bool(self.lib.dlsg_region_aggregate_supported(T, TR, H))

@@ -292,6 +292,24 @@ int dlsg_latent_psl_fwd(const float* X, const float* theta, float* Gs, float* N,
 int dlsg_latent_psl_bwd(const float* X, const float* theta, const float* Gs, const float* dN, float* dX, float* dtheta,
                         int32_t B, int32_t T, int32_t P, int32_t H, void* stream);
 
+/* ---- one LSTM time step in one launch (nn.LSTM of EncoderVisual, layer.py:52; up to two independent directions) -----
+ * gates = h_in W^T + gin ; i,f,o = sigmoid, g = tanh ; c_out = f c_in + i g ; h = o tanh(c_out)   (torch gate order i,f,g,o)
+ * Each CTA owns 16 hidden units (64 rows of W), streams its weight slab and h_in through shared memory (cp.async, bf16),
+ * mma.sync with fp32 accumulation, cell in the epilogue: replaces a split-K GEMM launch + a cell launch per direction.
+ * Supported: B <= 64, H a multiple of 128, bf16 W / h_in with 16-byte aligned rows.                                   */
+typedef struct {
+  const void* W[2];                       /* bf16 (4H, H) row-major recurrent weights                                   */
+  const void* h_in[2]; int64_t ldh_in;    /* bf16 (B, H) previous hidden state; NULL (all directions) = first step       */
+  const float* gin[2]; int64_t ldgin;     /* fp32 (B, 4H) input projection + biases of this step                         */
+  const float* c_in[2]; float* c_out[2];  /* fp32 (B, H) contiguous; c_in NULL = zeros                                   */
+  float* acts[2];                         /* out fp32 (B, 4H) contiguous: activated gates [i|f|g|o] (saved for BPTT)     */
+  float* h_out[2]; int64_t ldh_out;       /* out fp32 (B, H) view, optional                                              */
+  void* h_op[2]; int64_t ldh_op;          /* out bf16 (B, H) view, optional: the next step's h_in                        */
+  int32_t B, H, ndir, _pad;
+} dlsg_lstm_step_t;
+int dlsg_lstm_step_supported(int32_t B, int32_t H);
+int dlsg_lstm_step_fwd(const dlsg_lstm_step_t* p, void* stream);
+
 /* ---- region -> frame aggregation of EncoderVisualGraphTUN (models/layer.py:184-192), fused -------------------------------
  * Replaces, per encoder e (E <= 2, both in one launch): obj_norm LayerNorm over the tanh'ed region projection Y, the
  * frame x region score product, the softmax over ALL T*R regions of a clip (layer.py:188, dim=1) and the weighted sum.

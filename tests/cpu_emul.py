@@ -403,6 +403,29 @@ class CpuEmulBackend:
                 dKW[h].copy_(k)
                 dVW[h].copy_(v)
 
+    # ---- one LSTM step in one launch (csrc/lstm_step.cu)
+    @staticmethod
+    def lstm_step_supported(B, H):
+        return 1 <= B <= 64 and H >= 128 and H % 128 == 0
+
+    def lstm_step_fwd(self, W, h_in, gin, c_in, c_out, acts, h_out=None, h_op=None):
+        self.launches += 1
+        for d in range(len(W)):
+            H = W[d].shape[1]
+            pre = _f(gin[d])
+            if h_in is not None:
+                pre = pre + _f(h_in[d]) @ _f(W[d]).t()
+            i, f, g, o = pre[:, :H], pre[:, H:2 * H], pre[:, 2 * H:3 * H], pre[:, 3 * H:]
+            i, f, g, o = torch.sigmoid(i), torch.sigmoid(f), torch.tanh(g), torch.sigmoid(o)
+            c = f * (c_in[d] if (c_in is not None and c_in[d] is not None) else 0) + i * g
+            h = o * torch.tanh(c)
+            acts[d].copy_(torch.cat([i, f, g, o], 1))
+            c_out[d].copy_(c)
+            if h_out is not None:
+                h_out[d].copy_(h)
+            if h_op is not None:
+                h_op[d].copy_(h)
+
     # ---- fused region -> frame aggregation (csrc/region_agg.cu): plain composition of the same algebra
     @staticmethod
     def region_aggregate_supported(T, TR, H, dtype):

@@ -482,3 +482,48 @@ def test_tunblock_fused_region_aggregate_equals_unfused_composition(active):
             continue
         err = float((g0[k] - g1[k]).norm() / (g0[k].norm() + 1e-12))
         assert err < 3e-2, (k, err)
+
+
+def test_encoder_visual_fused_lstm_step_equals_gemm_plus_cell():
+    """EncoderVisualBlock at a width the one-launch LSTM step takes (H a multiple of 128): the fused per-step launch for
+    both directions against the recurrent-GEMM + cell-kernel loop on two streams - outputs and every gradient."""
+    la.set_precision('bf16')
+    B, T, Din, H = 3, 5, 72, 128
+    g = torch.Generator().manual_seed(7)
+    rnd = lambda *s, sc=1.0: torch.randn(*s, generator=g) * sc
+    pf = 'e.'
+    base = {'frames': rnd(B, T, Din), 'pe': rnd(1, 72, 2 * H, sc=0.1),
+            pf + 'linear_embed.weight': rnd(H, Din, sc=0.2), pf + 'linear_embed.bias': rnd(H, sc=0.1)}
+    for sfx in ('', '_reverse'):
+        base[pf + 'lstm.weight_ih_l0' + sfx] = rnd(4 * H, H, sc=0.1)
+        base[pf + 'lstm.weight_hh_l0' + sfx] = rnd(4 * H, H, sc=0.1)
+        base[pf + 'lstm.bias_ih_l0' + sfx] = rnd(4 * H, sc=0.1)
+        base[pf + 'lstm.bias_hh_l0' + sfx] = rnd(4 * H, sc=0.1)
+    base[pf + 'layernorm_lstm.weight'] = 1 + 0.1 * rnd(2 * H)
+    base[pf + 'layernorm_lstm.bias'] = 0.1 * rnd(2 * H)
+    for n in ('K', 'Q', 'V'):
+        base[pf + 'self_attention.%s.weight' % n] = rnd(2 * H, 2 * H, sc=0.1)
+    base[pf + 'self_attention.output_layer.0.weight'] = rnd(H, 2 * H, sc=0.1)
+    base[pf + 'layernorm_sa.weight'] = 1 + 0.1 * rnd(H)
+    base[pf + 'layernorm_sa.bias'] = 0.1 * rnd(H)
+    gout = rnd(B, T, H)
+    res = {}
+    for fused in (False, True):
+        DF.FUSED_LSTM_STEP = fused
+        DF.WC.clear()
+        try:
+            t = {k: v.clone().requires_grad_(k not in ('frames', 'pe')) for k, v in base.items()}
+            blk = DF.EncoderVisualBlock(pf, baseline=False, p_drop=0.0, training=False)
+            out = DF.run_block(blk, t)[0]
+            (out * gout).sum().backward()
+            res[fused] = (out.detach(), {k: v.grad for k, v in t.items()})
+        finally:
+            DF.FUSED_LSTM_STEP = True
+    (o0, g0), (o1, g1) = res[False], res[True]
+    assert (o0 - o1).abs().max() < 2e-2 * max(1.0, float(o0.abs().max()))
+    for k in g0:
+        if g0[k] is None:
+            assert g1[k] is None, k
+            continue
+        err = float((g0[k] - g1[k]).norm() / (g0[k].norm() + 1e-12))
+        assert err < 3e-2, (k, err)

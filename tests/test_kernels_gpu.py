@@ -766,3 +766,34 @@ def test_gemm_static_operand_early_fetch_is_bit_identical(be, M, N, K, splitk, a
         assert torch.equal(outs[0], outs[1])
     ref = (x_src * 3).to(torch.bfloat16).float()[:, :K] @ w.float().t()
     assert float((outs[1].cpu() - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize('B_,H,nd,first', [(64, 1024, 2, False), (64, 1024, 2, True), (5, 128, 1, False), (33, 256, 2, False)])
+def test_lstm_step_fused(be, B_, H, nd, first):
+    """csrc/lstm_step.cu: recurrent product + LSTM cell of one time step in one launch (two directions), against the
+    emulator's fp32 product of the same bf16 operands; strided views as the BiLSTM passes them (h of a (B, T, H) operand
+    buffer, the direction's half of the (B, T, 8H) input projection, the layer-output slice), batch < 64, first step."""
+    T = 3
+    W = [bf(R(4 * H, H, scale=0.05)) for _ in range(nd)]
+    hbuf = bf(R(nd, B_, T, H))
+    Gin = R(B_, T, nd * 4 * H)
+    c_in = [R(B_, H) for _ in range(nd)]
+    outbuf, opbuf = torch.zeros(B_, T, nd * H), torch.zeros(nd, B_, T, H, dtype=torch.bfloat16)
+
+    def args(dev_):
+        mv = (lambda x: x.to(DEV)) if dev_ else (lambda x: x)
+        hb, gi, ob, pb = mv(hbuf), mv(Gin), mv(outbuf.clone()), mv(opbuf.clone())
+        out = dict(c_out=[mv(torch.zeros(B_, H)) for _ in range(nd)], acts=[mv(torch.zeros(B_, 4 * H)) for _ in range(nd)],
+                   h_out=[ob[:, 1, d * H:(d + 1) * H] for d in range(nd)], h_op=[pb[d, :, 2] for d in range(nd)])
+        a = ([mv(w) for w in W], None if first else [hb[d, :, 1] for d in range(nd)],
+             [gi[:, 1, d * 4 * H:(d + 1) * 4 * H] for d in range(nd)], [mv(c) for c in c_in])
+        return a, out, (ob, pb)
+    (ac, oc, bc), (ag, og, bg) = args(False), args(True)
+    EM.lstm_step_fwd(*ac, oc['c_out'], oc['acts'], oc['h_out'], oc['h_op'])
+    be.lstm_step_fwd(*ag, og['c_out'], og['acts'], og['h_out'], og['h_op'])
+    torch.cuda.synchronize()
+    for k in ('c_out', 'acts'):
+        for d in range(nd):
+            assert float((oc[k][d] - og[k][d].cpu()).abs().max()) <= 2e-4, (k, d)
+    assert float((bc[0] - bg[0].cpu()).abs().max()) <= 2e-4                     # h into the layer-output slice, rest untouched
+    assert float((bc[1].float() - bg[1].float().cpu()).abs().max()) <= 1e-2      # bf16 operand copy
