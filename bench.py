@@ -586,8 +586,8 @@ def main(argv=None):
                                                          '256x256 tiles on CTA pairs (tcgen05.mma.cta_group::2)' % (Mr, Nr, Kr),
                             'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
                             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the committed ncu --set full
-                            # capture profiles/r02u_ncu_full_top_kernels.json (algorithmic: A 245 MB + W 8 MB read, 245 MB written)
-                            'traffic': 253.84e6 + 210.18e6, 'traffic_unit': 'bytes/launch',
+                            # capture profiles/r02v_ncu_full_top_kernels.json (algorithmic: A 245 MB + W 8 MB read, 245 MB written)
+                            'traffic': 253.84e6 + 212.24e6, 'traffic_unit': 'bytes/launch',
                             'peak_source': 'measured (MEASURED_PEAKS.json bf16_tflops, burst)' if 'bf16_tflops' in peaks else 'fallback',
                             'ms_per_launch': k_ms, 'launches_per_step': 1}
         if 'bf16_tflops_sustained' in peaks:
