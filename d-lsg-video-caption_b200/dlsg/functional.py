@@ -77,6 +77,13 @@ class _BlockFn(torch.autograd.Function):
 
 
 BLOCK_INPUTS = ('regions', 'visual0', 'visual1', 'frames', 'pe', 'n1', 'n2', 'captions')
+def _rows2(x):
+    """2-D view of a gradient / bucket slice for the multi-segment kernels (segments are spread over CTAs by rows)."""
+    if x.dim() == 2:
+        return x
+    return x.reshape(x.shape[0], -1) if x.dim() > 2 else x.reshape(1, -1)
+
+
 GRAD_SYNC = None
 BLOCK_BWD_HOOK = None       # callable(block) invoked at the start of every block backward (dlsg.graphs: overlapped Adam)
 
@@ -138,7 +145,7 @@ class GradSync:
         for key, x, off in zip(uniq.keys(), tensors, offs):
             v = flat[off:off + x.numel()].view(x.shape)
             views[key] = v
-            pairs.append((x.reshape(1, -1) if x.dim() != 2 else x, None, v.reshape(1, -1) if x.dim() != 2 else v))
+            pairs.append((_rows2(x), None, _rows2(v)))
         be = ops.backend()
         plan = be.make_convert_plan(pairs, host=True)
         self._plans.append(plan)
@@ -189,7 +196,10 @@ class GradSync:
         flat = self._buckets.get(sig)
         if flat is None:
             flat = self._buckets[sig] = torch.zeros(n, dtype=self.dtype, device=ps[0].device)
-        two = lambda x: x.reshape(1, -1) if x.dim() != 2 else x
+        # 2-D views for the multi-segment kernel, which spreads a segment over CTAs by ROWS: a tensor of more than two dims keeps
+        # its leading dim as rows (the critic's conv1d weight (512, V, 1) as ONE row of 5.4 M elements was converted by a single
+        # CTA: 4.1 ms per critic step, tools/diag_critic_sync.py)
+        two = _rows2
         fwd, back = [], []
         for p, off in zip(ps, offs):
             g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
@@ -217,7 +227,7 @@ class GradSync:
         for p in params:
             r = self.reduced.get(id(p))
             if r is not None and p.grad is not None:
-                pairs.append((r.reshape(1, -1) if r.dim() != 2 else r, None, p.grad.reshape(1, -1) if p.grad.dim() != 2 else p.grad))
+                pairs.append((_rows2(r), None, _rows2(p.grad)))
         if pairs:
             be = ops.backend()
             plan = be.make_convert_plan(pairs, host=True)

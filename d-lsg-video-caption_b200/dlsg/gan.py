@@ -114,7 +114,7 @@ class GanIteration:
             r_loss, f_loss = r_logit.mean(), f_logit.mean()
             loss_d = f_loss - r_loss + 10 * gp
             loss_d.backward()
-            if self.world > 1:
+            if self.world > 1 and 'nodsync' not in self.sync_d.debug:      # (measurement switch: DLSG_SYNC_DEBUG=nodsync)
                 self.sync_d.reduce_params(self.d_params)
             self.opt_d.step()
             la.new_param_epoch()                      # critic weights changed: refresh their bf16 copies on next use
@@ -149,14 +149,15 @@ class GanIteration:
         f_logit = D(out, obj.detach(), mot.detach(), att_mask=att_mask, alpha_all=alpha.detach())          # :218
         loss_g = -f_logit.mean()
         total = cap_loss + loss_g * self.lam
-        if self.world > 1:
+        gsync = self.world > 1 and 'nogsync' not in self.sync.debug               # (measurement switch: DLSG_SYNC_DEBUG=nogsync)
+        if gsync:
             self.sync.begin_step()
             DF.GRAD_SYNC = self.sync
         try:
             total.backward()
         finally:
             DF.GRAD_SYNC = None
-        if self.world > 1:
+        if gsync:
             self.sync.wait()
             self.sync.write_back([p for p in G.parameters() if p.grad is not None])
         self.opt_g.step()
