@@ -508,6 +508,22 @@ def main(argv=None):
             'gpu_launches': launches, 'clocks': clocks, 'cuda_graph': use_graph, 'eager_ms_per_step': eager_ms,
             'eager_scheduled_sampling_tf0.8_ms_per_step': eager_ss_ms}
     _RESULT.update(line)
+    if use_graph and world == 1:
+        # the same step with scheduled sampling captured (teacher forcing 0.8; the coins are drawn once, at capture, with the
+        # trainer's seed: 5 of the 25 decisions feed the arg-max back, each paying a per-step vocabulary GEMM + arg-max + gather).
+        # The headline above is the teacher-forced step; this is what a live epoch costs per step.
+        stage('captured step with scheduled sampling (tf 0.8)')
+        try:
+            import random
+            random.seed(12)
+            gss = GraphedTrainStep(net, opt, d_fr, d_rg, d_cp, lens, L, 0.8, process_group=None, warmup=0)
+            for _ in range(2):
+                gss()
+            line['graphed_scheduled_sampling_tf0.8_ms_per_step'] = timed(lambda: gss(), a.steps)
+            del gss
+        except Exception as e:                  # secondary number: never take the headline line down with it
+            line['graphed_scheduled_sampling_tf0.8_error'] = repr(e)[:200]
+        _RESULT.update(line)
     # ---- end-to-end: host pinned inputs -> H2D -> step -> loss.item()
     stage('end-to-end (host inputs) timing')
     for _ in range(2):
