@@ -816,6 +816,24 @@ __global__ void beam_gather_kernel(const uint32_t* __restrict__ src, uint32_t* _
   for (int c = threadIdx.x; c < W; c += blockDim.x) dst[(int64_t)row * W + c] = src[srow * W + c];
 }
 
+// the same re-indexing for up to four state buffers in ONE launch (h / c rows of both LSTMs after a beam step): grid (rows, n),
+// 16-byte copies when every row is 16-byte sized and aligned
+struct BeamGatherMulti { const void* src[4]; void* dst[4]; int32_t row_bytes[4]; int32_t n; };
+__global__ void beam_gather_multi_kernel(const BeamGatherMulti a, const int64_t* __restrict__ backptr, int beam) {
+  pdl_prologue();
+  const int row = blockIdx.x, k = blockIdx.y;
+  const int b = row / beam;
+  const int64_t srow = (int64_t)b * beam + backptr[row];
+  const int rb = a.row_bytes[k];
+  const uint8_t* s = static_cast<const uint8_t*>(a.src[k]) + srow * rb;
+  uint8_t* d = static_cast<uint8_t*>(a.dst[k]) + (int64_t)row * rb;
+  if ((rb & 15) == 0 && ((reinterpret_cast<uintptr_t>(a.src[k]) | reinterpret_cast<uintptr_t>(a.dst[k])) & 15) == 0) {
+    for (int c = threadIdx.x; c < (rb >> 4); c += blockDim.x) reinterpret_cast<uint4*>(d)[c] = reinterpret_cast<const uint4*>(s)[c];
+  } else {
+    for (int c = threadIdx.x; c < (rb >> 2); c += blockDim.x) reinterpret_cast<uint32_t*>(d)[c] = reinterpret_cast<const uint32_t*>(s)[c];
+  }
+}
+
 __global__ void beam_backtrack_kernel(const int64_t* __restrict__ preds, const int64_t* __restrict__ backs, int S, int B, int beam,
                                       int64_t* __restrict__ out) {
   pdl_prologue();
@@ -984,6 +1002,19 @@ int dlsg_beam_gather(const void* src, void* dst, const int64_t* backptr, int32_t
   DLSG_REQUIRE(row_bytes % 4 == 0, "beam_gather: row_bytes must be a multiple of 4");
   DLSG_LAUNCH(beam_gather_kernel, B * beam, 256, 0, (cudaStream_t)stream, (const uint32_t*)src, (uint32_t*)dst, backptr, beam, row_bytes / 4);
   return check_launch("beam_gather_kernel");
+}
+int dlsg_beam_gather_multi(const void* const* src, void* const* dst, const int32_t* row_bytes, int32_t n, const int64_t* backptr,
+                           int32_t B, int32_t beam, void* stream) {
+  DLSG_REQUIRE(n >= 1 && n <= 4, "beam_gather_multi: 1..4 buffers per launch");
+  if (B * beam <= 0) return 0;
+  BeamGatherMulti a = {};
+  for (int k = 0; k < n; ++k) {
+    DLSG_REQUIRE(src[k] && dst[k] && row_bytes[k] > 0 && row_bytes[k] % 4 == 0, "beam_gather_multi: buffer %d: null or row_bytes not a multiple of 4", k);
+    a.src[k] = src[k]; a.dst[k] = dst[k]; a.row_bytes[k] = row_bytes[k];
+  }
+  a.n = n;
+  DLSG_LAUNCH(beam_gather_multi_kernel, dim3(B * beam, n), 256, 0, (cudaStream_t)stream, a, backptr, beam);
+  return check_launch("beam_gather_multi_kernel");
 }
 int dlsg_beam_backtrack(const int64_t* preds, const int64_t* backs, int32_t S, int32_t B, int32_t beam, int64_t* out, void* stream) {
   if (B * beam <= 0 || S <= 0) return 0;

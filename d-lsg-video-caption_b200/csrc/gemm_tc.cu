@@ -871,7 +871,7 @@ static int gemm_tc_direct(const dlsg_gemm_t* g, cudaStream_t st) {
   // 1-CTA 128 x 256 tile moves (128 + 256) rows per k-block for 128 x 256 outputs = 85 flop/B and is L2 -> SM bandwidth bound
   // (measured 15.3 TB/s aggregate = 1300 TFLOP/s); a pair moves (256 + 256) rows for 256 x 256 outputs = 128 flop/B.
   static const bool pair_on = [] { const char* e = getenv("DLSG_GEMM_2CTA"); return !(e && e[0] == '0'); }();
-  const bool pair = pair_on && splitk == 1 && bn >= 128 && ptiles >= 2 && tiles_for(bn) >= 96;   // a pair occupies two SMs: never fewer SMs busy
+  const bool pair = pair_on && splitk == 1 && bn >= 128 && ptiles >= 2 && tiles_for(bn) >= 40;   // a pair occupies two SMs: never fewer SMs busy
   CUtensorMap ta, tb;
   if (make_map(&ta, Ap, P, g->K, ldp, batch, strp, BM, p_mn)) return -1;
   if (make_map(&tb, Bq, Q, g->K, ldq, batch, strq, pair ? bn / 2 : bn, q_mn)) return -1;

@@ -209,6 +209,7 @@ SIGNATURES = {
     'dlsg_beam_topk': (i32, [vp, i64, i32, i32, vp, i32, i32, vp, vp, i32, vp]),
     'dlsg_beam_merge': (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp]),
     'dlsg_beam_gather': (i32, [vp, vp, vp, i32, i32, i32, vp]),
+    'dlsg_beam_gather_multi': (i32, [vp, vp, vp, i32, vp, i32, i32, vp]),
     'dlsg_beam_backtrack': (i32, [vp, vp, i32, i32, i32, vp, vp]),
 }
 

@@ -485,6 +485,12 @@ def _decode_setup(t, pf, multi_modal, n1, n2, R_per_clip):
     return core, nodes, Kp, Vp, Gq, b
 
 
+def _logits_buf(rows, V, like):
+    """(rows, V) fp32 logits of one decode step with a row pitch padded to 8 elements: V = 10547 is odd, and only 16-byte
+    aligned rows get the GEMM epilogue's vector stores (the arg-max / top-k kernels take the pitch)."""
+    return empty((rows, (V + 7) // 8 * 8), like)[:, :V]
+
+
 def _step_logits(core, b, i, j, Kp, Vp, Gq, rpn, dbuf, logits):
     be = ops.backend()
     t, pf = core.t, core.pf
@@ -501,7 +507,7 @@ def decode_greedy(t, pf, multi_modal, n1, n2, T):
     ids = torch.empty((B, T + 1), dtype=torch.int64, device=nodes.device)
     ids[:, 0].fill_(START)
     dbuf = op_zeros((B,), core.Hd, nodes)
-    logits = empty((B, core.V), nodes)
+    logits = _logits_buf(B, core.V, nodes)
     oW, W = core.oW, core.W
     for s in range(T):
         i, j = s % 2, (s + 1) % 2
@@ -542,7 +548,7 @@ def decode_beam_core(t, pf, multi_modal, n1, n2, T, beam, end_index, per_node=No
     top_id = torch.empty((R, k), dtype=torch.int64, device=dev)
     start = torch.full((R,), START, dtype=torch.int64, device=dev)
     dbuf = op_zeros((R,), core.Hd, nodes)
-    logits = empty((R, core.V), nodes)
+    logits = _logits_buf(R, core.V, nodes)
     # step 0: every beam row of a clip is identical; candidates come from the first row of each clip
     be.embedding_gather(table, start, out=b.Xq[0][:, oW:oW + W])
     _step_logits(core, b, 0, 1, Kp, Vp, Gq, beam, dbuf, logits)
@@ -556,8 +562,7 @@ def decode_beam_core(t, pf, multi_modal, n1, n2, T, beam, end_index, per_node=No
         be.beam_merge(top_lp, top_id, lps[cur], B, beam, k, lps[1 - cur], preds[s], backs[s - 1], None, end_index)
         cur = 1 - cur
         # keep only the state rows of the surviving ancestors (h/c of both LSTMs; node tensors are indexed, not copied)
-        for buf in (b.Xq, b.Xl, b.cq, b.cl):
-            be.beam_gather(_fullrows(buf[j]), _fullrows(buf[g]), backs[s - 1], B, beam)
+        be.beam_gather_multi([(_fullrows(buf[j]), _fullrows(buf[g])) for buf in (b.Xq, b.Xl, b.cq, b.cl)], backs[s - 1], B, beam)
         i, j, g = g, i, j
     return preds, backs, lps[cur], lps[0]
 

@@ -846,6 +846,16 @@ class CudaBackend:
         self.launches += 1
         L.check(self.lib.dlsg_beam_gather(src.data_ptr(), dst.data_ptr(), backptr.data_ptr(), B, beam, row_bytes, _stream()), 'beam_gather')
 
+    def beam_gather_multi(self, pairs, backptr, B, beam):
+        """pairs: up to 4 (src, dst) row buffers as for beam_gather; one launch re-indexes all of them."""
+        n = len(pairs)
+        src, dst, rb = (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_int32 * n)()
+        for k, (s_, d_) in enumerate(pairs):
+            assert s_.stride(-1) == 1 and s_.stride() == d_.stride() and s_.dtype == d_.dtype
+            src[k], dst[k], rb[k] = s_.data_ptr(), d_.data_ptr(), s_.stride(0) * s_.element_size()
+        self.launches += 1
+        L.check(self.lib.dlsg_beam_gather_multi(src, dst, rb, n, backptr.data_ptr(), B, beam, _stream()), 'beam_gather_multi')
+
     def beam_backtrack(self, preds, backs, S, B, beam, out):
         self.launches += 1
         L.check(self.lib.dlsg_beam_backtrack(preds.data_ptr(), _ptr(backs), S, B, beam, out.data_ptr(), _stream()), 'beam_backtrack')

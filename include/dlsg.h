@@ -396,6 +396,9 @@ int dlsg_beam_merge(const float* top_lp, const int64_t* top_id, const float* las
                     float* new_lp, int64_t* new_cls, int64_t* backptr, int32_t* all_end, int32_t end_index, void* stream);
 /* dst[b,j,:] = src[b, backptr[b,j], :] for contiguous state rows of row_bytes bytes (any dtype)    */
 int dlsg_beam_gather(const void* src, void* dst, const int64_t* backptr, int32_t B, int32_t beam, int32_t row_bytes, void* stream);
+/* the same for n <= 4 buffers in one launch (host arrays of n pointers / row sizes): the h / c rows of both LSTMs          */
+int dlsg_beam_gather_multi(const void* const* src, void* const* dst, const int32_t* row_bytes, int32_t n, const int64_t* backptr,
+                           int32_t B, int32_t beam, void* stream);
 /* back-track: preds (S,B,beam), backs (S-1,B,beam) -> out (B,beam,S)                             */
 int dlsg_beam_backtrack(const int64_t* preds, const int64_t* backs, int32_t S, int32_t B, int32_t beam, int64_t* out, void* stream);
 

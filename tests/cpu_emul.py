@@ -617,6 +617,12 @@ class CpuEmulBackend:
         idx = (torch.arange(B).unsqueeze(1) * beam + backptr.view(B, beam)).reshape(-1)
         dst.copy_(src[idx])
 
+    def beam_gather_multi(self, pairs, backptr, B, beam):
+        self.launches += 1
+        idx = (torch.arange(B).unsqueeze(1) * beam + backptr.view(B, beam)).reshape(-1)
+        for src, dst in pairs:
+            dst.copy_(src[idx])
+
     def beam_backtrack(self, preds, backs, S, B, beam, out):
         self.launches += 1
         cur = torch.arange(beam).unsqueeze(0).expand(B, beam).clone()

@@ -797,3 +797,20 @@ def test_lstm_step_fused(be, B_, H, nd, first):
             assert float((oc[k][d] - og[k][d].cpu()).abs().max()) <= 2e-4, (k, d)
     assert float((bc[0] - bg[0].cpu()).abs().max()) <= 2e-4                     # h into the layer-output slice, rest untouched
     assert float((bc[1].float() - bg[1].float().cpu()).abs().max()) <= 1e-2      # bf16 operand copy
+
+
+def test_beam_gather_multi(be):
+    """One launch re-indexes up to four state buffers by the beam back-pointers (rows of different widths / dtypes, one of
+    them not 16-byte sized): equal to four single-buffer gathers."""
+    B_, beam = 7, 5
+    g = torch.Generator().manual_seed(3)
+    back = torch.randint(0, beam, (B_, beam), generator=g)
+    bufs = [bf(R(B_ * beam, 2864 + 8)), bf(R(B_ * beam, 4608)), R(B_ * beam, 1024), R(B_ * beam, 1537)]
+    want = [torch.zeros_like(x) for x in bufs]
+    for s_, d_ in zip(bufs, want):
+        EM.beam_gather(s_, d_, back, B_, beam)
+    got = [torch.zeros_like(x).to(DEV) for x in bufs]
+    be.beam_gather_multi([(s_.to(DEV), d_) for s_, d_ in zip(bufs, got)], back.to(DEV), B_, beam)
+    torch.cuda.synchronize()
+    for w, g_ in zip(want, got):
+        assert torch.equal(w, g_.cpu())
