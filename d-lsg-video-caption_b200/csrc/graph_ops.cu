@@ -34,13 +34,20 @@ __device__ __forceinline__ void lp_row_dots(const float* __restrict__ X, const f
   }
 }
 
+// up to two independent poolings (the object and the motion encoder) per launch: blockIdx.y selects the set of pointers
+struct LpFwdArgs { const float* X[2]; const float* theta[2]; float* Gs[2]; float* N[2]; };
+struct LpBwdArgs { const float* X[2]; const float* theta[2]; const float* Gs[2]; const float* dN[2]; float* dX[2]; float* dtheta[2]; };
+
 __global__ void __launch_bounds__(256)
-latent_psl_fwd_kernel(const float* __restrict__ X, const float* __restrict__ theta, float* __restrict__ Gs, float* __restrict__ N,
-                      int T, int P, int H) {
+latent_psl_fwd_kernel(const LpFwdArgs a, int T, int P, int H) {
   pdl_prologue();
   extern __shared__ float sm[];                // theta (P x H)
   __shared__ float g[LP_MAXT][LP_MAXP];
-  const int b = blockIdx.x;
+  const int b = blockIdx.x, e = blockIdx.y;
+  const float* __restrict__ X = a.X[e];
+  const float* __restrict__ theta = a.theta[e];
+  float* __restrict__ Gs = a.Gs[e];
+  float* __restrict__ N = a.N[e];
   X += (int64_t)b * T * H;
   for (int i = threadIdx.x * 4; i < P * H; i += blockDim.x * 4)
     *reinterpret_cast<float4*>(sm + i) = *reinterpret_cast<const float4*>(theta + i);
@@ -75,13 +82,18 @@ latent_psl_fwd_kernel(const float* __restrict__ X, const float* __restrict__ the
 }
 
 __global__ void __launch_bounds__(256)
-latent_psl_bwd_kernel(const float* __restrict__ X, const float* __restrict__ theta, const float* __restrict__ Gs,
-                      const float* __restrict__ dN, float* __restrict__ dX, float* __restrict__ dtheta, int T, int P, int H) {
+latent_psl_bwd_kernel(const LpBwdArgs a, int T, int P, int H) {
   pdl_prologue();
   extern __shared__ float sm[];                // dN (P x H) then theta (P x H)
   __shared__ float gs[LP_MAXT][LP_MAXP];
   __shared__ float dg[LP_MAXT][LP_MAXP];
-  const int b = blockIdx.x;
+  const int b = blockIdx.x, e = blockIdx.y;
+  const float* __restrict__ X = a.X[e];
+  const float* __restrict__ theta = a.theta[e];
+  const float* __restrict__ Gs = a.Gs[e];
+  const float* __restrict__ dN = a.dN[e];
+  float* __restrict__ dX = a.dX[e];
+  float* __restrict__ dtheta = a.dtheta[e];
   X += (int64_t)b * T * H;
   float* sdn = sm;
   float* sth = sm + P * H;
@@ -134,27 +146,52 @@ using namespace dlsg;
 
 extern "C" {
 
-int dlsg_latent_psl_fwd(const float* X, const float* theta, float* Gs, float* N, int32_t B, int32_t T, int32_t P, int32_t H, void* stream) {
-  DLSG_REQUIRE(P >= 1 && P <= LP_MAXP && T >= 1 && T <= LP_MAXT && H % 4 == 0, "latent_psl_fwd: unsupported shape T=%d P=%d H=%d", T, P, H);
-  if (B <= 0) return 0;
+static int lp_check(const char* what, int32_t E, int32_t T, int32_t P, int32_t H, size_t smem) {
+  DLSG_REQUIRE(E >= 1 && E <= 2, "%s: 1 or 2 poolings per launch", what);
+  DLSG_REQUIRE(P >= 1 && P <= LP_MAXP && T >= 1 && T <= LP_MAXT && H % 4 == 0, "%s: unsupported shape T=%d P=%d H=%d", what, T, P, H);
+  DLSG_REQUIRE(smem <= 200 * 1024, "%s: P*H too large", what);
+  return 0;
+}
+
+int dlsg_latent_psl_fwd_multi(const float* const* X, const float* const* theta, float* const* Gs, float* const* N, int32_t E,
+                              int32_t B, int32_t T, int32_t P, int32_t H, void* stream) {
   const size_t smem = (size_t)P * H * sizeof(float);
-  DLSG_REQUIRE(smem <= 200 * 1024, "latent_psl_fwd: P*H too large");
+  if (int rc = lp_check("latent_psl_fwd", E, T, P, H, smem)) return rc;
+  if (B <= 0) return 0;
+  LpFwdArgs a = {};
+  for (int e = 0; e < E; ++e) {
+    DLSG_REQUIRE(X[e] && theta[e] && Gs[e] && N[e], "latent_psl_fwd: null operand (set %d)", e);
+    a.X[e] = X[e]; a.theta[e] = theta[e]; a.Gs[e] = Gs[e]; a.N[e] = N[e];
+  }
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(latent_psl_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-  DLSG_LAUNCH(latent_psl_fwd_kernel, B, 256, smem, (cudaStream_t)stream, X, theta, Gs, N, T, P, H);
+  DLSG_LAUNCH(latent_psl_fwd_kernel, dim3(B, E), 256, smem, (cudaStream_t)stream, a, T, P, H);
   return check_launch("latent_psl_fwd_kernel");
+}
+
+int dlsg_latent_psl_bwd_multi(const float* const* X, const float* const* theta, const float* const* Gs, const float* const* dN,
+                              float* const* dX, float* const* dtheta, int32_t E, int32_t B, int32_t T, int32_t P, int32_t H, void* stream) {
+  const size_t smem = (size_t)2 * P * H * sizeof(float);
+  if (int rc = lp_check("latent_psl_bwd", E, T, P, H, smem)) return rc;
+  if (B <= 0) return 0;
+  LpBwdArgs a = {};
+  for (int e = 0; e < E; ++e) {
+    DLSG_REQUIRE(X[e] && theta[e] && Gs[e] && dN[e] && dX[e] && dtheta[e], "latent_psl_bwd: null operand (set %d)", e);
+    a.X[e] = X[e]; a.theta[e] = theta[e]; a.Gs[e] = Gs[e]; a.dN[e] = dN[e]; a.dX[e] = dX[e]; a.dtheta[e] = dtheta[e];
+  }
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(latent_psl_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  DLSG_LAUNCH(latent_psl_bwd_kernel, dim3(B, E), 256, smem, (cudaStream_t)stream, a, T, P, H);
+  return check_launch("latent_psl_bwd_kernel");
+}
+
+int dlsg_latent_psl_fwd(const float* X, const float* theta, float* Gs, float* N, int32_t B, int32_t T, int32_t P, int32_t H, void* stream) {
+  return dlsg_latent_psl_fwd_multi(&X, &theta, &Gs, &N, 1, B, T, P, H, stream);
 }
 
 int dlsg_latent_psl_bwd(const float* X, const float* theta, const float* Gs, const float* dN, float* dX, float* dtheta,
                         int32_t B, int32_t T, int32_t P, int32_t H, void* stream) {
-  DLSG_REQUIRE(P >= 1 && P <= LP_MAXP && T >= 1 && T <= LP_MAXT && H % 4 == 0, "latent_psl_bwd: unsupported shape T=%d P=%d H=%d", T, P, H);
-  if (B <= 0) return 0;
-  const size_t smem = (size_t)2 * P * H * sizeof(float);
-  DLSG_REQUIRE(smem <= 200 * 1024, "latent_psl_bwd: P*H too large");
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(latent_psl_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-  DLSG_LAUNCH(latent_psl_bwd_kernel, B, 256, smem, (cudaStream_t)stream, X, theta, Gs, dN, dX, dtheta, T, P, H);
-  return check_launch("latent_psl_bwd_kernel");
+  return dlsg_latent_psl_bwd_multi(&X, &theta, &Gs, &dN, &dX, &dtheta, 1, B, T, P, H, stream);
 }
 
 }  // extern "C"

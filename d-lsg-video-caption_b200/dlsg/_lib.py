@@ -193,6 +193,8 @@ SIGNATURES = {
     'dlsg_node_attn_bwd': (i32, [C.POINTER(AttnBwdT), vp]),
     'dlsg_latent_psl_fwd': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     'dlsg_latent_psl_bwd': (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    'dlsg_latent_psl_fwd_multi': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    'dlsg_latent_psl_bwd_multi': (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     'dlsg_embedding_gather': (i32, [vp, vp, i64, i32, i32, vp, i32, i64, vp, i32, i64, f32, u64, u64, vp]),
     'dlsg_embedding_scatter_add': (i32, [vp, vp, i64, i32, i32, vp, i64, f32, u64, u64, vp]),
     'dlsg_mean_nodes_fwd': (i32, [vp, i32, i32, i32, vp, i64, vp]),

@@ -381,24 +381,32 @@ class TunBlock:
                 s['X'] = X
             if self.baseline:
                 outs.append(X.view(B, T, H))
+        if not self.baseline:
+            # LatentPSL pooling (sublayer.py:189-198) of BOTH encoders in one launch, then the output LayerNorms
+            P = self.P
+            S_ = sv['enc']
+            H = S_[0]['X'].shape[-1]
+            like = S_[0]['X']
+            thetas = [t[e['prefix'] + 'v2l_layer.theta'] for e in self.encs]
+            for s in S_:
+                s.update(Gs=empty((B, T, P), like), N=empty((B, P, H), like), G=None)
+            if be.latent_psl_supported(T, P, H):
+                be.latent_psl_fwd_multi([s['X'].view(B, T, H) for s in S_], [th.detach() for th in thetas], [s['Gs'] for s in S_],
+                                        [s['N'] for s in S_])
             else:
-                P = self.P
-                theta = t[pf + 'v2l_layer.theta']
-                Gs = empty((B, T, P), v2)
-                N = empty((B, P, H), v2)
-                if be.latent_psl_supported(T, P, H):
-                    G = None
-                    be.latent_psl_fwd(X.view(B, T, H), theta.detach(), Gs, N)   # fused: scores, softmax over T, pooling
-                else:
-                    G = mm32(X, theta.detach())                     # (B*T,P)
-                    be.softmax_fwd(G.view(B, T, P), Gs, dim=1)       # over the T frames (sublayer.py:192)
-                    be.gemm(Gs.transpose(1, 2), X.view(B, T, H).transpose(1, 2), N)
-                nodes = empty((B, P, H), v2)
-                stN = empty((B * P, 2), v2)
+                for s, theta in zip(S_, thetas):
+                    X = s['X']
+                    s['G'] = mm32(X, theta.detach())                                   # (B*T,P)
+                    be.softmax_fwd(s['G'].view(B, T, P), s['Gs'], dim=1)              # over the T frames (sublayer.py:192)
+                    be.gemm(s['Gs'].transpose(1, 2), X.view(B, T, H).transpose(1, 2), s['N'])
+            for i, e in enumerate(self.encs):
+                pf, s = e['prefix'], S_[i]
+                nodes = empty((B, P, H), like)
+                stN = empty((B * P, 2), like)
                 dn = site(0.3 if self.training else 0.0, seed, i)
-                be.norm_fwd(N.view(B * P, H), t[pf + 'v2l_layer.out_norm.1.weight'], t[pf + 'v2l_layer.out_norm.1.bias'],
+                be.norm_fwd(s['N'].view(B * P, H), t[pf + 'v2l_layer.out_norm.1.weight'], t[pf + 'v2l_layer.out_norm.1.bias'],
                             y=nodes.view(B * P, H), stats=stN, pre_tanh=True, drop=dn)
-                s.update(G=G, Gs=Gs, N=N, stN=stN, dn=dn)
+                s.update(stN=stN, dn=dn)
                 outs.append(nodes)
         sv['t'] = t
         return outs, sv
@@ -421,36 +429,53 @@ class TunBlock:
             grads[pf + name + '.weight'], grads[pf + name + '.bias'] = dw, db
             return w, b, dw, db
         dXs, dAs, dFs = {}, {}, {}
-        for i in active:                             # node pooling and obj_visual_norm backward: dA = d(agg + F)
-            pf, s = self.encs[i]['prefix'], sv['enc'][i]
-            g = _c(gouts[i])
-            X = s['X']
-            H = X.shape[-1]
-            if self.baseline:
-                dX = g.view(B, T, H)
-            else:
-                P = self.P
+        if self.baseline:
+            for i in active:
+                X = sv['enc'][i]['X']
+                dXs[i] = _c(gouts[i]).view(B, T, X.shape[-1])
+        elif active:
+            # output LayerNorm backward per encoder, then the pooling backward of all active encoders in ONE launch
+            P = self.P
+            dN3s, ths, dths = {}, {}, {}
+            for i in active:
+                pf, s = self.encs[i]['prefix'], sv['enc'][i]
+                X = s['X']
+                H = X.shape[-1]
                 w, b, dw, db = lnp(pf, 'v2l_layer.out_norm.1')
                 dN = empty((B * P, H), X)
-                be.norm_bwd(g.view(B * P, H), s['N'].view(B * P, H), w, b, s['stN'], dx=dN, dgamma=dw, dbeta=db,
+                be.norm_bwd(_c(gouts[i]).view(B * P, H), s['N'].view(B * P, H), w, b, s['stN'], dx=dN, dgamma=dw, dbeta=db,
                             pre_tanh=True, drop=s['dn'])
-                dN3 = dN.view(B, P, H)
-                dX = empty((B, T, H), X)
-                theta = t[pf + 'v2l_layer.theta'].detach()
-                if s['G'] is None:
-                    dth = small_zeros(theta.shape, X)
-                    be.latent_psl_bwd(X.view(B, T, H), theta, s['Gs'], dN3, dX, dth)
-                else:
-                    dGs = empty((B, T, P), X)
-                    be.gemm(X.view(B, T, H), dN3, dGs)
-                    be.gemm(s['Gs'], dN3.transpose(1, 2), dX)
-                    dG = empty((B, T, P), X)
-                    be.softmax_bwd(s['G'].view(B, T, P), dGs, dG, dim=1)
-                    be.gemm(dG.view(B * T, P), theta.t(), dX.view(B * T, H), accum=True)
-                    dth = empty(theta.shape, X)
-                    be.gemm(dG.view(B * T, P).t(), X.t(), dth)
-                grads[pf + 'v2l_layer.theta'] = dth
-            dXs[i] = dX
+                dN3s[i] = dN.view(B, P, H)
+                dXs[i] = empty((B, T, H), X)
+                ths[i] = t[pf + 'v2l_layer.theta'].detach()
+            fusedp = [i for i in active if sv['enc'][i]['G'] is None]
+            if fusedp:
+                for i in fusedp:
+                    dths[i] = small_zeros(ths[i].shape, sv['enc'][i]['X'])
+                be.latent_psl_bwd_multi([sv['enc'][i]['X'].view(B, T, -1) for i in fusedp], [ths[i] for i in fusedp],
+                                        [sv['enc'][i]['Gs'] for i in fusedp], [dN3s[i] for i in fusedp], [dXs[i] for i in fusedp],
+                                        [dths[i] for i in fusedp])
+            for i in active:
+                if i in fusedp:
+                    continue
+                s = sv['enc'][i]
+                X, dN3, dX, theta = s['X'], dN3s[i], dXs[i], ths[i]
+                H = X.shape[-1]
+                dGs = empty((B, T, P), X)
+                be.gemm(X.view(B, T, H), dN3, dGs)
+                be.gemm(s['Gs'], dN3.transpose(1, 2), dX)
+                dG = empty((B, T, P), X)
+                be.softmax_bwd(s['G'].view(B, T, P), dGs, dG, dim=1)
+                be.gemm(dG.view(B * T, P), theta.t(), dX.view(B * T, H), accum=True)
+                dths[i] = empty(theta.shape, X)
+                be.gemm(dG.view(B * T, P).t(), X.t(), dths[i])
+            for i in active:
+                grads[self.encs[i]['prefix'] + 'v2l_layer.theta'] = dths[i]
+        for i in active:                             # obj_visual_norm backward: dA = d(agg + F)
+            pf, s = self.encs[i]['prefix'], sv['enc'][i]
+            X = s['X']
+            H = X.shape[-1]
+            dX = dXs[i]
             if use_regions:
                 w, b, dw, db = lnp(pf, 'obj_visual_norm.1')
                 dA = empty((B * T, H), X)

@@ -610,6 +610,28 @@ class CudaBackend:
         L.check(self.lib.dlsg_latent_psl_bwd(X.data_ptr(), theta.data_ptr(), Gs.data_ptr(), dN.data_ptr(), dX.data_ptr(),
                                              dtheta.data_ptr(), B, T, P, H, _stream()), 'latent_psl_bwd')
 
+    def latent_psl_fwd_multi(self, X, theta, Gs, N):
+        """Lists (<= 2 entries: the two encoders) of the latent_psl_fwd arguments: one launch."""
+        E = len(X)
+        B, T, H = X[0].shape
+        P = theta[0].shape[0]
+        arr = lambda ts: (C.c_void_p * E)(*[t.data_ptr() for t in ts])
+        for t in list(X) + list(theta) + list(Gs) + list(N):
+            assert t.is_contiguous() and t.dtype == torch.float32
+        self.launches += 1
+        L.check(self.lib.dlsg_latent_psl_fwd_multi(arr(X), arr(theta), arr(Gs), arr(N), E, B, T, P, H, _stream()), 'latent_psl_fwd_multi')
+
+    def latent_psl_bwd_multi(self, X, theta, Gs, dN, dX, dtheta):
+        E = len(X)
+        B, T, H = X[0].shape
+        P = theta[0].shape[0]
+        arr = lambda ts: (C.c_void_p * E)(*[t.data_ptr() for t in ts])
+        for t in list(X) + list(theta) + list(Gs) + list(dN) + list(dX) + list(dtheta):
+            assert t.is_contiguous() and t.dtype == torch.float32
+        self.launches += 1
+        L.check(self.lib.dlsg_latent_psl_bwd_multi(arr(X), arr(theta), arr(Gs), arr(dN), arr(dX), arr(dtheta), E, B, T, P, H, _stream()),
+                'latent_psl_bwd_multi')
+
     # ------------------------------------------------------------------ one LSTM step (recurrent product + cell) in one launch
     def lstm_step_supported(self, B, H):
         return bool(self.lib.dlsg_lstm_step_supported(B, H))

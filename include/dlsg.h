@@ -291,6 +291,11 @@ int dlsg_attn2_bwd_nodes(const float* q_all, int64_t ldq, int64_t q_step_stride,
 int dlsg_latent_psl_fwd(const float* X, const float* theta, float* Gs, float* N, int32_t B, int32_t T, int32_t P, int32_t H, void* stream);
 int dlsg_latent_psl_bwd(const float* X, const float* theta, const float* Gs, const float* dN, float* dX, float* dtheta,
                         int32_t B, int32_t T, int32_t P, int32_t H, void* stream);
+/* the same for E <= 2 independent poolings in ONE launch (host arrays of E pointers: the object and the motion encoder)   */
+int dlsg_latent_psl_fwd_multi(const float* const* X, const float* const* theta, float* const* Gs, float* const* N, int32_t E,
+                              int32_t B, int32_t T, int32_t P, int32_t H, void* stream);
+int dlsg_latent_psl_bwd_multi(const float* const* X, const float* const* theta, const float* const* Gs, const float* const* dN,
+                              float* const* dX, float* const* dtheta, int32_t E, int32_t B, int32_t T, int32_t P, int32_t H, void* stream);
 
 /* ---- one LSTM time step in one launch (nn.LSTM of EncoderVisual, layer.py:52; up to two independent directions) -----
  * gates = h_in W^T + gin ; i,f,o = sigmoid, g = tanh ; c_out = f c_in + i g ; h = o tanh(c_out)   (torch gate order i,f,g,o)

@@ -511,6 +511,16 @@ class CpuEmulBackend:
         Gs.copy_(g)
         N.copy_(g.transpose(1, 2) @ X)
 
+    def latent_psl_fwd_multi(self, X, theta, Gs, N):
+        for e in range(len(X)):
+            self.latent_psl_fwd(X[e], theta[e], Gs[e], N[e])
+        self.launches -= len(X) - 1
+
+    def latent_psl_bwd_multi(self, X, theta, Gs, dN, dX, dtheta):
+        for e in range(len(X)):
+            self.latent_psl_bwd(X[e], theta[e], Gs[e], dN[e], dX[e], dtheta[e])
+        self.launches -= len(X) - 1
+
     def latent_psl_bwd(self, X, theta, Gs, dN, dX, dtheta):
         self.launches += 1
         dGs = X @ dN.transpose(1, 2)
