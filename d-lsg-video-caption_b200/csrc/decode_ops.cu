@@ -315,15 +315,15 @@ attn2_fwd_kernel(const dlsg_attn2_fwd_t p) {
   }
 }
 
-// grid (rows), block 256*nh: thread group hd = tid/256 handles head hd; the heads' dq contributions are summed
-// through smem in a fixed order (deterministic) and ADDED to dq by group 0.
-__global__ void __launch_bounds__(512)
+// grid (rows, nh), block 256: one CTA per (row, head); the heads' dq contributions are ADDED to dq with fp32 atomics when
+// nh > 1 (half the work per CTA and twice the CTAs of the former (rows) x 512-thread form: 10.5 -> ~6 us per decode step)
+__global__ void __launch_bounds__(256)
 attn2_bwd_kernel(const dlsg_attn2_bwd_t p) {
   pdl_prologue();
   __shared__ float red[2][8][APM];
   __shared__ float dl[2][APM];
-  __shared__ float dqs[1][1024];
-  const int r = blockIdx.x, hd = threadIdx.x >> 8, tid = threadIdx.x & 255, lane = tid & 31, w = tid >> 5;
+  // one CTA per (row, head): the heads only meet in dq, which they accumulate with fp32 atomics (nh > 1)
+  const int r = blockIdx.x, hd = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int c = tid * 4;
   const bool ak = c < p.Hk, av = c < p.Hv;
   const int64_t nk = (((int64_t)hd * p.rows + r) * p.P) * p.Hk, nv = (((int64_t)hd * p.rows + r) * p.P) * p.Hv;
@@ -426,17 +426,15 @@ attn2_bwd_kernel(const dlsg_attn2_bwd_t p) {
       }
     }
   }
-  if (hd > 0 && ak) *reinterpret_cast<float4*>(&dqs[hd - 1][c]) = acc;
-  __syncthreads();
-  if (hd == 0 && ak) {
-    for (int h2 = 1; h2 < p.nh; ++h2) {
-      const float4 o = *reinterpret_cast<const float4*>(&dqs[h2 - 1][c]);
-      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+  if (ak) {
+    float* dq = p.dq + (int64_t)r * p.lddq + c;
+    if (p.nh > 1) {
+      atomicAdd(dq, acc.x); atomicAdd(dq + 1, acc.y); atomicAdd(dq + 2, acc.z); atomicAdd(dq + 3, acc.w);
+    } else {
+      float4 old = *reinterpret_cast<float4*>(dq);
+      old.x += acc.x; old.y += acc.y; old.z += acc.z; old.w += acc.w;
+      *reinterpret_cast<float4*>(dq) = old;
     }
-    float4* dq = reinterpret_cast<float4*>(p.dq + (int64_t)r * p.lddq + c);
-    float4 old = *dq;
-    old.x += acc.x; old.y += acc.y; old.z += acc.z; old.w += acc.w;
-    *dq = old;
   }
 }
 
@@ -954,7 +952,7 @@ int dlsg_attn2_bwd(const dlsg_attn2_bwd_t* p, void* stream) {
     DLSG_REQUIRE(al16(p->dco) && p->lddco % 4 == 0, "attn2_bwd: unaligned dco");
   }
   if (p->rows <= 0) return 0;
-  DLSG_LAUNCH(attn2_bwd_kernel, p->rows, 256 * p->nh, 0, (cudaStream_t)stream, *p);
+  DLSG_LAUNCH(attn2_bwd_kernel, dim3(p->rows, p->nh), 256, 0, (cudaStream_t)stream, *p);
   return check_launch("attn2_bwd_kernel");
 }
 int dlsg_row_argmax(const float* logits, int64_t ld, int32_t rows, int32_t V, int64_t* ids, int64_t ld_ids, void* stream) {
