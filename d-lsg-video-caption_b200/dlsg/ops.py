@@ -78,11 +78,12 @@ class CudaBackend:
     @launches.setter
     def launches(self, v):
         self._launches = v
-        if torch.cuda.is_available():
+        if STATIC_PREFETCH and torch.cuda.is_available():    # (the tracking only matters when the early fetch is requested)
             self._writer_last[_stream()] = False
 
     def _mark_writer(self):
-        self._writer_last[_stream()] = True
+        if STATIC_PREFETCH:
+            self._writer_last[_stream()] = True
 
     def _workspace(self, dev):
         """Per-device scratch for automatic split-K (allocated once, before any graph capture uses it)."""
