@@ -752,10 +752,15 @@ def test_gemm_static_operand_early_fetch_is_bit_identical(be, M, N, K, splitk, a
         else:
             o = torch.zeros(M, N, device=DEV)
         xs = x_src.to(DEV)
-        for rep in range(3):                              # the conversion kernel right before the GEMM writes its A operand
+        d1, d2 = torch.zeros(64, device=DEV), torch.zeros(64, device=DEV)
+        for rep in range(3):                              # the activations (operand A) are rewritten right before every GEMM
             be.convert(xs * (rep + 1), dst=x)
             if atomic:
                 o.zero_()
+            # the backend drops the request directly behind a conversion launch (it could be writing the weight copy):
+            # put an ordinary kernel in between, as the recurrent loops have (cell / attention kernel before each GEMM)
+            be.axpby(d1, 1.0, d2, 0.0)
+            assert be._writer_last.get(torch.cuda.current_stream().cuda_stream) is False
             be.gemm(x[:, :K], wd, o, splitk=splitk, atomic=atomic, b_static=static)
         torch.cuda.synchronize()
         outs.append(o.sum(0) if splitk > 1 else o)
