@@ -582,9 +582,16 @@ lstm_cell_bwd_fast(const dlsg_lstm_cell_bwd_t p) {
   for (int s_ = 0; s_ < S2; ++s_) r2[s_] = p.dh2 ? ldf4(p.dh2 + (int64_t)b * p.lddh2 + h + (int64_t)s_ * p.dh2_stride_split) : z4;
   if (p.c_prev) cp = ldf4(p.c_prev + ei);
   if (p.dc_next) dcn = ldf4(p.dc_next + ei);
+  float4 ga[4] = {z4, z4, z4, z4};
+  if (p.dc_next2) dcn = addf4(dcn, ldf4(p.dc_next2 + ei));
+  if (p.dgates_add) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ga[k] = ldf4(p.dgates_add + g0 + (int64_t)k * H);
+  }
   float4 r = r1;
 #pragma unroll
   for (int s_ = 0; s_ < S2; ++s_) r = addf4(r, r2[s_]);
+  if (p.dh_total) *reinterpret_cast<float4*>(p.dh_total + ei) = r;
   const float dh_[4] = {r.x, r.y, r.z, r.w};
   const float i_[4] = {ai.x, ai.y, ai.z, ai.w}, f_[4] = {af.x, af.y, af.z, af.w}, g_[4] = {ag.x, ag.y, ag.z, ag.w}, o_[4] = {ao.x, ao.y, ao.z, ao.w};
   const float cn_[4] = {cn.x, cn.y, cn.z, cn.w}, cp_[4] = {cp.x, cp.y, cp.z, cp.w}, dcn_[4] = {dcn.x, dcn.y, dcn.z, dcn.w};
@@ -601,6 +608,8 @@ lstm_cell_bwd_fast(const dlsg_lstm_cell_bwd_t p) {
     d[3][u] = dh * tc * o_[u] * (1.f - o_[u]);
     dcp[u] = dc * f_[u];
   }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { d[k][0] += ga[k].x; d[k][1] += ga[k].y; d[k][2] += ga[k].z; d[k][3] += ga[k].w; }
   if (p.dc_prev) *reinterpret_cast<float4*>(p.dc_prev + ei) = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -633,10 +642,12 @@ lstm_cell_bwd_kernel(const dlsg_lstm_cell_bwd_t p) {
         if (s < p.dh2_nsplit) v += d2[(int64_t)s * p.dh2_stride_split];
       dh += v;
     }
+    if (p.dh_total) p.dh_total[e] = dh;
     if (p.drop_p > 0.f) dh *= drop_scale(p.drop_p, p.seed, p.offset + (uint64_t)e);
     const float tc = tanhf(p.c_new[e]);
     float dc = dh * og * (1.f - tc * tc);
     if (p.dc_next) dc += p.dc_next[e];
+    if (p.dc_next2) dc += p.dc_next2[e];
     const float cp = p.c_prev ? p.c_prev[e] : 0.f;
     float d[4];
     d[0] = dc * gg * ig * (1.f - ig);
@@ -647,6 +658,7 @@ lstm_cell_bwd_kernel(const dlsg_lstm_cell_bwd_t p) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int64_t col = (int64_t)k * H + h;
+      if (p.dgates_add) d[k] += p.dgates_add[(int64_t)b * 4 * H + col];
       if (p.dgates) p.dgates[(int64_t)b * 4 * H + col] = d[k];
       if (p.dgates2) st_from_float(p.dgates2, p.dgates2_dtype, (int64_t)b * p.ld_dgates2 + col, d[k]);
       if (p.dgatesT) st_from_float(p.dgatesT, p.dgatesT_dtype, col * p.ld_dgatesT + b, d[k]);
@@ -941,12 +953,21 @@ lstm_cell_bwd2_kernel(const dlsg_lstm_cell_bwd2_t p) {
     const float omt = 1.f - tc * tc;
     float ui = 0.f, uf = 0.f, ug = 0.f, uo = 0.f;
     if (p.u) { ui = p.u[g0]; uf = p.u[g0 + H]; ug = p.u[g0 + 2 * (int64_t)H]; uo = p.u[g0 + 3 * (int64_t)H]; }
+    if (p.u2) {
+      const int ns = p.u2_nsplit > 1 ? p.u2_nsplit : 1;
+      for (int s_ = 0; s_ < ns; ++s_) {
+        const float* q = p.u2 + (int64_t)s_ * p.u2_stride_split + g0;
+        ui += q[0]; uf += q[H]; ug += q[2 * (int64_t)H]; uo += q[3 * (int64_t)H];
+      }
+    }
     const float w = p.w ? p.w[e] : 0.f;
     const float si = ig * (1.f - ig), sf = fg * (1.f - fg), sg = 1.f - gg * gg, so = og * (1.f - og);
     const float D = dh * og * omt + dcn;
     const float S = ui * gg * si + uf * c0 * sf + ug * ig * sg + w * fg;       // d(L2)/dD
     const float Q = S * dh * og * (-2.f * tc * omt) + uo * dh * so * omt;       // d(L2)/dc through tc
-    if (p.g_dh) p.g_dh[e] = S * og * omt + uo * tc * so;
+    const float gdh = S * og * omt + uo * tc * so;
+    if (p.g_dh) p.g_dh[e] = gdh;
+    if (p.g_dh2) st_from_float(p.g_dh2, p.g_dh2_dtype, (int64_t)b * p.ld_g_dh2 + h, gdh);
     if (p.g_dc) p.g_dc[e] = S;
     if (p.g_cprev) p.g_cprev[e] = D * uf * sf + Q * fg;
     if (p.g_pre) {
@@ -1030,6 +1051,120 @@ softmax_bwd_kernel(const dlsg_softmax_t p, const float* __restrict__ dy, float* 
       dx[i] = masked_pre ? 0.f : p.scale * s * (g - dot);
     }
   }
+}
+
+// Backward of softmax_bwd_kernel with respect to (dy, x): see dlsg_softmax_bwd2 in dlsg.h.  One warp per (outer, inner) pair.
+__global__ void __launch_bounds__(256)
+softmax_bwd2_kernel(const dlsg_softmax_t p, const float* __restrict__ dy, const float* __restrict__ u, float* __restrict__ g_dy,
+                    float* __restrict__ g_x) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31;
+  const int64_t pairs = p.outer * p.inner;
+  for (int64_t pr = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; pr < pairs; pr += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const int64_t base = (pr / p.inner) * p.so + (pr % p.inner) * p.si;
+    float mx = -INFINITY;
+    for (int64_t j = lane; j < p.n; j += 32) {
+      float v = p.x[base + j * p.sn] * p.scale;
+      if (p.mask_mode == 1 && !(p.mask[base + j * p.sn] > 0.f)) v = -9e15f;
+      mx = fmaxf(mx, v);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f, A = 0.f, Bq = 0.f;
+    for (int64_t j = lane; j < p.n; j += 32) {
+      const int64_t i = base + j * p.sn;
+      const bool keep = p.mask_mode == 0 || p.mask[i] > 0.f;
+      float v = p.x[i] * p.scale;
+      if (p.mask_mode == 1 && !keep) v = -9e15f;
+      const float e = expf(v - mx);
+      const float g = (p.mask_mode == 2 && !keep) ? 0.f : dy[i];
+      const float uu = (p.mask_mode == 1 && !keep) ? 0.f : u[i];
+      sum += e; A = fmaf(e, g, A); Bq = fmaf(e, uu, Bq);
+    }
+    sum = warp_sum(sum); A = warp_sum(A); Bq = warp_sum(Bq);
+    const float inv = 1.f / sum;
+    A *= inv; Bq *= inv;
+    float Cq = 0.f;
+    for (int64_t j = lane; j < p.n; j += 32) {
+      const int64_t i = base + j * p.sn;
+      const bool keep = p.mask_mode == 0 || p.mask[i] > 0.f;
+      float v = p.x[i] * p.scale;
+      if (p.mask_mode == 1 && !keep) v = -9e15f;
+      const float s = expf(v - mx) * inv;
+      const float g = (p.mask_mode == 2 && !keep) ? 0.f : dy[i];
+      const float uu = (p.mask_mode == 1 && !keep) ? 0.f : u[i];
+      Cq = fmaf(s, p.scale * (uu * (g - A) - g * Bq), Cq);
+    }
+    Cq = warp_sum(Cq);
+    for (int64_t j = lane; j < p.n; j += 32) {
+      const int64_t i = base + j * p.sn;
+      const bool keep = p.mask_mode == 0 || p.mask[i] > 0.f;
+      float v = p.x[i] * p.scale;
+      if (p.mask_mode == 1 && !keep) v = -9e15f;
+      const float s = expf(v - mx) * inv;
+      const float g = (p.mask_mode == 2 && !keep) ? 0.f : dy[i];
+      const float uu = (p.mask_mode == 1 && !keep) ? 0.f : u[i];
+      const float q = p.scale * (uu * (g - A) - g * Bq);
+      if (g_dy) g_dy[i] = (p.mask_mode == 2 && !keep) ? 0.f : p.scale * s * (uu - Bq);
+      if (g_x) g_x[i] = (p.mask_mode == 1 && !keep) ? 0.f : p.scale * s * (q - Cq);
+    }
+  }
+}
+
+// Small fused element-wise forms (dlsg_ew in dlsg.h): one float4 (or one element) per thread and trip.
+template <int W>
+__device__ __forceinline__ void ew_apply(const dlsg_ew_t& p, int64_t i) {
+  float a[5][W], o[3][W];
+  const int nin = p.op == DLSG_EW_MUL_BWD2 ? 5 : (p.op == DLSG_EW_TANH_BWD || p.op == DLSG_EW_LERP_ROWS_BWD ? 2 : 3);
+  const bool rows_e = p.op == DLSG_EW_LERP_ROWS || p.op == DLSG_EW_LERP_ROWS_BWD;
+  const int e_slot = p.op == DLSG_EW_LERP_ROWS ? 2 : 1;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    if (k >= nin) continue;
+    if (rows_e && k == e_slot) {
+      const float e = p.in[k][i / p.cols];                 // W consecutive elements share a row (cols % W == 0)
+#pragma unroll
+      for (int w = 0; w < W; ++w) a[k][w] = e;
+    } else if constexpr (W == 4) {
+      const float4 v = *reinterpret_cast<const float4*>(p.in[k] + i);
+      a[k][0] = v.x; a[k][1] = v.y; a[k][2] = v.z; a[k][3] = v.w;
+    } else {
+      a[k][0] = p.in[k][i];
+    }
+  }
+  int nout = 2;
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    switch (p.op) {
+      case DLSG_EW_TANH_BWD: o[0][w] = a[0][w] * (1.f - a[1][w] * a[1][w]); nout = 1; break;
+      case DLSG_EW_TANH_BWD2:
+        o[0][w] = a[2][w] * (1.f - a[1][w] * a[1][w]);
+        o[1][w] = -2.f * a[1][w] * a[0][w] * a[2][w];
+        break;
+      case DLSG_EW_MUL_BWD: o[0][w] = a[0][w] * a[2][w]; o[1][w] = a[0][w] * a[1][w]; break;
+      case DLSG_EW_MUL_BWD2:
+        o[0][w] = a[3][w] * a[2][w] + a[4][w] * a[1][w];
+        o[1][w] = a[4][w] * a[0][w];
+        o[2][w] = a[3][w] * a[0][w];
+        nout = 3;
+        break;
+      case DLSG_EW_LERP_ROWS: o[0][w] = a[0][w] * a[2][w] + a[1][w] * (1.f - a[2][w]); nout = 1; break;
+      default: o[0][w] = a[0][w] * a[1][w]; o[1][w] = a[0][w] * (1.f - a[1][w]); break;      // DLSG_EW_LERP_ROWS_BWD
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (k >= nout || !p.out[k]) continue;
+    if constexpr (W == 4) *reinterpret_cast<float4*>(p.out[k] + i) = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
+    else p.out[k][i] = o[k][0];
+  }
+}
+
+template <int W>
+__global__ void __launch_bounds__(256)
+ew_kernel(const dlsg_ew_t p) {
+  pdl_prologue();
+  const int64_t nv = p.n / W;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nv; e += (int64_t)gridDim.x * blockDim.x) ew_apply<W>(p, e * W);
 }
 
 // ------------------------------------------------------------------------------------------- embedding etc.
@@ -1226,6 +1361,7 @@ int dlsg_lstm_cell_bwd(const dlsg_lstm_cell_bwd_t* p, void* stream) {
   if (p->H % 4 == 0 && ns <= 4 && a16(p->acts) && a16(p->c_new) && p->dh && a16(p->dh) && p->lddh % 4 == 0 &&
       (!p->dh2 || (a16(p->dh2) && p->lddh2 % 4 == 0 && p->dh2_stride_split % 4 == 0)) && (!p->c_prev || a16(p->c_prev)) &&
       (!p->dc_next || a16(p->dc_next)) && (!p->dc_prev || a16(p->dc_prev)) && (!p->dgates || a16(p->dgates)) &&
+      (!p->dc_next2 || a16(p->dc_next2)) && (!p->dgates_add || a16(p->dgates_add)) && (!p->dh_total || a16(p->dh_total)) &&
       (!p->dgates2 || (p->ld_dgates2 % 4 == 0 && (reinterpret_cast<uintptr_t>(p->dgates2) % (p->dgates2_dtype == DLSG_F32 ? 16 : 8)) == 0))) {
     const unsigned nb = (unsigned)(((int64_t)p->B * (p->H / 4) + 255) / 256);
     cudaStream_t st = (cudaStream_t)stream;
@@ -1322,6 +1458,35 @@ int dlsg_softmax_bwd(const dlsg_softmax_t* p, const float* dy, float* dx, void* 
   DLSG_REQUIRE(p->mask_mode == 0 || p->mask != nullptr, "softmax: mask_mode set without mask");
   DLSG_LAUNCH(softmax_bwd_kernel, ew_blocks(pairs * 32), 256, 0, (cudaStream_t)stream, *p, dy, dx);
   return check_launch("softmax_bwd_kernel");
+}
+
+int dlsg_softmax_bwd2(const dlsg_softmax_t* p, const float* dy, const float* u, float* g_dy, float* g_x, void* stream) {
+  const int64_t pairs = p->outer * p->inner;
+  if (pairs <= 0 || p->n <= 0) return 0;
+  DLSG_REQUIRE(p->mask_mode == 0 || p->mask != nullptr, "softmax_bwd2: mask_mode set without mask");
+  DLSG_REQUIRE(dy && u, "softmax_bwd2: dy and u are required");
+  DLSG_LAUNCH(softmax_bwd2_kernel, ew_blocks(pairs * 32), 256, 0, (cudaStream_t)stream, *p, dy, u, g_dy, g_x);
+  return check_launch("softmax_bwd2_kernel");
+}
+int dlsg_ew(const dlsg_ew_t* p, void* stream) {
+  if (p->n <= 0) return 0;
+  DLSG_REQUIRE(p->op >= DLSG_EW_TANH_BWD && p->op <= DLSG_EW_LERP_ROWS_BWD, "ew: unknown op");
+  const int nin = p->op == DLSG_EW_MUL_BWD2 ? 5 : (p->op == DLSG_EW_TANH_BWD || p->op == DLSG_EW_LERP_ROWS_BWD ? 2 : 3);
+  const bool rows_e = p->op == DLSG_EW_LERP_ROWS || p->op == DLSG_EW_LERP_ROWS_BWD;
+  const int e_slot = p->op == DLSG_EW_LERP_ROWS ? 2 : 1;
+  DLSG_REQUIRE(!rows_e || p->cols > 0, "ew: cols required for a per-row operand");
+  bool vec = p->n % 4 == 0 && (!rows_e || p->cols % 4 == 0);
+  for (int k = 0; k < nin; ++k) {
+    DLSG_REQUIRE(p->in[k] != nullptr, "ew: missing input");
+    if (!(rows_e && k == e_slot)) vec = vec && (reinterpret_cast<uintptr_t>(p->in[k]) & 15) == 0;
+  }
+  for (int k = 0; k < 3; ++k) vec = vec && (reinterpret_cast<uintptr_t>(p->out[k]) & 15) == 0;
+  if (vec) {
+    DLSG_LAUNCH(ew_kernel<4>, ew_blocks(p->n / 4), 256, 0, (cudaStream_t)stream, *p);
+  } else {
+    DLSG_LAUNCH(ew_kernel<1>, ew_blocks(p->n), 256, 0, (cudaStream_t)stream, *p);
+  }
+  return check_launch("ew_kernel");
 }
 
 int dlsg_embedding_gather(const float* table, const int64_t* ids, int64_t ld_ids, int32_t rows, int32_t W, void* out,

@@ -57,7 +57,8 @@ class CellBwdT(C.Structure):
                 ('dgatesT', vp), ('ld_dgatesT', i64), ('dgatesT_dtype', i32), ('_pad1', i32),
                 ('dc_prev', vp), ('B', i32), ('H', i32),
                 ('drop_p', f32), ('_pad2', i32), ('seed', u64), ('offset', u64),
-                ('dh2_nsplit', i32), ('_pad3', i32), ('dh2_stride_split', i64)]
+                ('dh2_nsplit', i32), ('_pad3', i32), ('dh2_stride_split', i64),
+                ('dc_next2', vp), ('dgates_add', vp), ('dh_total', vp)]
 
 
 class AdamSegT(C.Structure):
@@ -77,7 +78,8 @@ class SegT(C.Structure):
 
 class CellBwd2T(C.Structure):
     _fields_ = [('acts', vp), ('c_prev', vp), ('c_new', vp), ('dh', vp), ('dc_next', vp), ('u', vp), ('w', vp),
-                ('g_dh', vp), ('g_dc', vp), ('g_pre', vp), ('g_cprev', vp), ('B', i32), ('H', i32)]
+                ('g_dh', vp), ('g_dc', vp), ('g_pre', vp), ('g_cprev', vp), ('B', i32), ('H', i32),
+                ('u2', vp), ('u2_stride_split', i64), ('u2_nsplit', i32), ('g_dh2_dtype', i32), ('g_dh2', vp), ('ld_g_dh2', i64)]
 
 
 class CellNormFwdT(C.Structure):
@@ -91,6 +93,13 @@ class NormCellBwdT(C.Structure):
     _fields_ = [('cell', CellBwdT), ('dy', vp), ('lddy', i64), ('x', vp), ('ldx', i64),
                 ('gamma', vp), ('beta', vp), ('stats', vp), ('dgamma', vp), ('dbeta', vp), ('ld_dparam', i64), ('dgates_sum', vp),
                 ('post_tanh', i32), ('_pad', i32), ('ydrop_p', f32), ('_pad2', i32), ('yseed', u64), ('yoffset', u64)]
+
+
+class EwT(C.Structure):
+    _fields_ = [('inp', vp * 5), ('out', vp * 3), ('n', i64), ('cols', i64), ('op', i32), ('_pad', i32)]
+
+
+EW_TANH_BWD, EW_TANH_BWD2, EW_MUL_BWD, EW_MUL_BWD2, EW_LERP_ROWS, EW_LERP_ROWS_BWD = range(6)
 
 
 class SoftmaxT(C.Structure):
@@ -189,6 +198,8 @@ SIGNATURES = {
     'dlsg_fused_step_supported': (i32, [i32]),
     'dlsg_softmax_fwd': (i32, [C.POINTER(SoftmaxT), vp]),
     'dlsg_softmax_bwd': (i32, [C.POINTER(SoftmaxT), vp, vp, vp]),
+    'dlsg_softmax_bwd2': (i32, [C.POINTER(SoftmaxT), vp, vp, vp, vp, vp]),
+    'dlsg_ew': (i32, [C.POINTER(EwT), vp]),
     'dlsg_node_attn_fwd': (i32, [C.POINTER(AttnFwdT), vp]),
     'dlsg_node_attn_bwd': (i32, [C.POINTER(AttnBwdT), vp]),
     'dlsg_latent_psl_fwd': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),

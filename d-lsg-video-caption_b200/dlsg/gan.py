@@ -79,6 +79,7 @@ class GanIteration:
             obj3, mot3, mask3, alpha3 = obj.repeat(3, 1, 1), mot.repeat(3, 1, 1), att_mask.repeat(3, 1, 1), alpha.repeat(3, 1, 1)
         for _ in range(self.num_d):
             self.opt_d.zero_grad(set_to_none=True)
+            la.begin_pool(fake.device)                # one zero-filled slab for this critic step's ~70 small gradient accumulators
             eps = torch.rand(B, 1, 1, device=fake.device, requires_grad=not self.batched)
             if self.batched:
                 # Token form of the three critic calls (same function of the parameters, re-associated):
@@ -94,11 +95,12 @@ class GanIteration:
                 W, bias = D.conv1d.weight[:, :, 0], D.conv1d.bias
                 tok_real = (GN.column_gather(W, real) + bias).view(B, L, -1)
                 tok_fake = GN.linear(fake, W, bias)
-                tok_mixed = tok_real * eps + tok_fake * (1 - eps)
+                tok_mixed = GN.lerp_rows(tok_real, tok_fake, eps)
                 logits = D(None, obj3, mot3, mask3, alpha3, _groups=3, _tokens=torch.cat([tok_real, tok_fake, tok_mixed], 0))
                 r_logit, f_logit, m_logit = logits[:B], logits[B:2 * B], logits[2 * B:]
-                g_tok = torch.autograd.grad(inputs=tok_mixed, outputs=m_logit, grad_outputs=torch.ones_like(m_logit),
-                                            create_graph=True, retain_graph=True)[0]
+                with GN.input_grads_only():           # tok_mixed is a non-leaf: weight / bias gradients of this pass are not computed
+                    g_tok = torch.autograd.grad(inputs=tok_mixed, outputs=m_logit, grad_outputs=torch.ones_like(m_logit),
+                                                create_graph=True, retain_graph=True)[0]
                 g2 = g_tok.reshape(B * L, -1)
                 gram = GN.bmm_nt(W, W)                                  # (512,512) = W W^T
                 gn = (GN.bmm_nt(g2, gram) * g2).view(B, -1).sum(1).sqrt()
@@ -114,6 +116,7 @@ class GanIteration:
             r_loss, f_loss = r_logit.mean(), f_logit.mean()
             loss_d = f_loss - r_loss + 10 * gp
             loss_d.backward()
+            la.end_pool()
             if self.world > 1 and 'nodsync' not in self.sync_d.debug:      # (measurement switch: DLSG_SYNC_DEBUG=nodsync)
                 self.sync_d.reduce_params(self.d_params)
             self.opt_d.step()

@@ -6,6 +6,7 @@ import math
 
 import torch
 
+from . import _lib as L
 from . import linalg as la
 from . import ops
 from .linalg import empty, zeros
@@ -27,6 +28,35 @@ def param_scope(fn):
     return wrapped
 
 
+# ----------------------------------------------------------------------------------------------- gradient scope
+_INPUT_GRADS_ONLY = False
+
+
+class input_grads_only:
+    """Scope for a backward pass that wants gradients of NON-LEAF tensors only (the WGAN-GP penalty's
+    torch.autograd.grad(m_logit, tok_mixed, create_graph=True), run_gun.py:362-371): inside it the backward functions skip
+    the gradients of leaves and of views of leaves (weights, biases: a weight-gradient GEMM + operand casts + a column sum
+    per Linear, all of which autograd would compute - needs_input_grad is fixed at forward time - and then discard)."""
+
+    def __enter__(self):
+        global _INPUT_GRADS_ONLY
+        self.old, _INPUT_GRADS_ONLY = _INPUT_GRADS_ONLY, True
+
+    def __exit__(self, *exc):
+        global _INPUT_GRADS_ONLY
+        _INPUT_GRADS_ONLY = self.old
+
+
+def _want(ctx, i, t):
+    if not ctx.needs_input_grad[i]:
+        return False
+    if _INPUT_GRADS_ONLY:
+        base = t._base if (t._is_view() and t._base is not None) else t
+        if base.grad_fn is None and base.requires_grad:                # a parameter or a view of one
+            return False
+    return True
+
+
 # ----------------------------------------------------------------------------------------------- matmul
 class _MmNT(torch.autograd.Function):
     """y[..., M, N] = a[..., M, K] @ b[..., N, K]^T (batched when 3-D)."""
@@ -40,9 +70,9 @@ class _MmNT(torch.autograd.Function):
     def backward(ctx, dy):
         a, b = ctx.saved_tensors
         da = db = None
-        if ctx.needs_input_grad[0]:
+        if _want(ctx, 0, a):
             da = bmm_nt(dy, b.transpose(-1, -2))          # dy @ b
-        if ctx.needs_input_grad[1]:
+        if _want(ctx, 1, b):
             db = bmm_nt(dy.transpose(-1, -2), a.transpose(-1, -2))   # dy^T @ a
         return da, db
 
@@ -62,7 +92,7 @@ class _ColSum(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
         ctx.rows = x.shape[0]
-        out = zeros((x.shape[1],), x)
+        out = la.small_zeros((x.shape[1],), x)
         ops.backend().colsum(_c(x), out)
         return out
 
@@ -83,11 +113,11 @@ class _LinearB(torch.autograd.Function):
     def backward(ctx, dy):
         a, w = ctx.saved_tensors
         da = dw = db = None
-        if ctx.needs_input_grad[0]:
+        if _want(ctx, 0, a):
             da = bmm_nt(dy, w.transpose(-1, -2))
-        if ctx.needs_input_grad[1]:
+        if _want(ctx, 1, w):
             dw = bmm_nt(dy.transpose(-1, -2), a.transpose(-1, -2))
-        if ctx.needs_input_grad[2]:
+        if ctx.needs_input_grad[2] and not _INPUT_GRADS_ONLY:
             db = _ColSum.apply(dy)
         return da, dw, db
 
@@ -102,6 +132,14 @@ def linear(x, w, b=None, tanh=False):
     return y.view(*lead, w.shape[0])
 
 
+def _ew(op, ins, n_out, cols=0, want=None):
+    """One dlsg_ew launch: contiguous fp32 inputs -> n_out fresh outputs (want[k] False: that output is not computed)."""
+    ins = [_c(t) for t in ins]
+    outs = [torch.empty_like(ins[0]) if (want is None or want[k]) else None for k in range(n_out)]
+    ops.backend().ew(op, ins, outs, cols)
+    return outs
+
+
 class _Tanh(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
@@ -112,15 +150,99 @@ class _Tanh(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         (y,) = ctx.saved_tensors
-        return dy * (1 - y * y)
+        return _TanhBwd.apply(dy, y)
+
+
+class _TanhBwd(torch.autograd.Function):
+    """dx = dy (1 - y^2) (one launch); its own backward is the closed form (u (1 - y^2), -2 y dy u) (one launch)."""
+
+    @staticmethod
+    def forward(ctx, dy, y):
+        dy, y = _c(dy), _c(y)
+        ctx.save_for_backward(dy, y)
+        return _ew(L.EW_TANH_BWD, [dy, y], 1)[0].view(dy.shape)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, u):
+        dy, y = ctx.saved_tensors
+        g_dy, g_y = _ew(L.EW_TANH_BWD2, [dy, y, u], 2, want=ctx.needs_input_grad[:2])
+        return g_dy, g_y
 
 
 def tanh_(x):
     return _Tanh.apply(x)
 
 
+class _Mul(torch.autograd.Function):
+    """Same-shape product whose backward pair (dy b, dy a) and second-order triple are one launch each."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return a * b
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, b = ctx.saved_tensors
+        return _MulBwd.apply(dy, a, b)
+
+
+class _MulBwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dy, a, b):
+        dy, a, b = _c(dy), _c(a), _c(b)
+        ctx.save_for_backward(dy, a, b)
+        da, db = _ew(L.EW_MUL_BWD, [dy, a, b], 2)
+        return da, db
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, u0, u1):
+        dy, a, b = ctx.saved_tensors
+        return tuple(_ew(L.EW_MUL_BWD2, [dy, a, b, u0, u1], 3))
+
+
 def mul(a, b):
+    if a.shape == b.shape and a.dtype == torch.float32 and b.dtype == torch.float32 and (a.requires_grad or b.requires_grad):
+        return _Mul.apply(a, b)
     return a * b
+
+
+class _LerpRows(torch.autograd.Function):
+    """out[r] = a[r] e[r] + b[r] (1 - e[r]) with one coefficient per leading row (the WGAN-GP interpolate, run_gun.py:355-358);
+    e carries no gradient.  The backward pair (dy e, dy (1 - e)) is linear in dy, so its own backward is this function."""
+
+    @staticmethod
+    def forward(ctx, a, b, e):
+        a, b = _c(a), _c(b)
+        ctx.save_for_backward(e)
+        return _ew(L.EW_LERP_ROWS, [a, b, e.reshape(-1)], 1, cols=a.numel() // e.numel())[0]
+
+    @staticmethod
+    def backward(ctx, dy):
+        (e,) = ctx.saved_tensors
+        da, db = _LerpRowsBwd.apply(dy, e)
+        return da, db, None
+
+
+class _LerpRowsBwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dy, e):
+        dy = _c(dy)
+        ctx.save_for_backward(e)
+        da, db = _ew(L.EW_LERP_ROWS_BWD, [dy, e.reshape(-1)], 2, cols=dy.numel() // e.numel())
+        return da, db
+
+    @staticmethod
+    def backward(ctx, u0, u1):
+        (e,) = ctx.saved_tensors
+        return _LerpRows.apply(u0, u1, e), None
+
+
+def lerp_rows(a, b, e):
+    """a * e + b * (1 - e), e of shape (rows, 1, ..., 1) broadcast over everything but the leading dim."""
+    return _LerpRows.apply(a, b, e)
 
 
 # ----------------------------------------------------------------------------------------------- softmax
@@ -158,15 +280,35 @@ def _from3(y, shp, dim):
     return y.view(shp)
 
 
+class _SoftmaxBwd(torch.autograd.Function):
+    """dx of the softmax (one launch); its own backward with respect to (x, dy) is the closed-form dlsg_softmax_bwd2."""
+
+    @staticmethod
+    def forward(ctx, x, dy, dim, scale, mask, mask_mode):
+        x3, shp = _as3(x, dim)
+        d3 = _as3(dy, dim)[0]
+        m3 = _as3(mask, dim)[0] if mask is not None else None
+        dx = torch.empty_like(x3)
+        ops.backend().softmax_bwd(x3, d3, dx, 1, scale, m3, mask_mode)
+        ctx.save_for_backward(x3, d3, m3)
+        ctx.shp, ctx.scale, ctx.mask_mode = shp, scale, mask_mode
+        return dx.view(shp)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, u):
+        x3, d3, m3 = ctx.saved_tensors
+        u3 = _c(u).view(x3.shape)
+        g_x = torch.empty_like(x3) if ctx.needs_input_grad[0] else None
+        g_dy = torch.empty_like(x3) if ctx.needs_input_grad[1] else None
+        ops.backend().softmax_bwd2(x3, d3, u3, 1, g_dy=g_dy, g_x=g_x, scale=ctx.scale, mask=m3, mask_mode=ctx.mask_mode)
+        return (g_x.view(ctx.shp) if g_x is not None else None), (g_dy.view(ctx.shp) if g_dy is not None else None), None, None, None, None
+
+
 def _softmax_bwd(x, dy, dim, scale, mask, mask_mode):
-    """dx of softmax; differentiable again (expressed with torch elementwise ops on the recomputed softmax)."""
+    """dx of softmax; differentiable again through the closed-form `_SoftmaxBwd`."""
     if torch.is_grad_enabled() and (x.requires_grad or dy.requires_grad):
-        s = _Softmax.apply(x, dim, scale, mask, 1 if mask_mode == 1 else 0)
-        g = dy if mask_mode != 2 else torch.where(mask > 0, dy, torch.zeros_like(dy))
-        r = scale * s * (g - (g * s).sum(dim, keepdim=True))
-        if mask_mode == 1:
-            r = torch.where(mask > 0, r, torch.zeros_like(r))
-        return r
+        return _SoftmaxBwd.apply(x, dy, dim, scale, mask, mask_mode)
     x3, shp = _as3(x, dim)
     d3 = _as3(dy, dim)[0]
     m3 = _as3(mask, dim)[0] if mask is not None else None
@@ -204,7 +346,7 @@ class _Norm(torch.autograd.Function):
         x2 = _c(x).view(-1, x.shape[-1])
         d2 = _c(dy).view(-1, x.shape[-1])
         dx = torch.empty_like(x2)
-        dg, db = zeros(gamma.shape, gamma), zeros(beta.shape, beta)
+        dg, db = la.small_zeros(gamma.shape, gamma), la.small_zeros(beta.shape, beta)
         ops.backend().norm_bwd(d2, x2, gamma.detach(), beta.detach(), stats, dx=dx, dgamma=dg, dbeta=db,
                                pre_tanh=ctx.pre_tanh, drop=ctx.drop)
         return dx.view(x.shape), dg, db, None, None
@@ -226,7 +368,7 @@ class _NormBwdCore(torch.autograd.Function):
         t2, d2 = _c(t).view(-1, D), _c(dy).view(-1, D)
         dt = torch.empty_like(t2)
         g0 = gamma.detach()
-        dg, db = zeros(gamma.shape, gamma), zeros(gamma.shape, gamma)
+        dg, db = la.small_zeros(gamma.shape, gamma), la.small_zeros(gamma.shape, gamma)
         ops.backend().norm_bwd(d2, t2, g0, g0, stats, dx=dt, dgamma=dg, dbeta=db)
         ctx.save_for_backward(d2, t2, gamma, stats)
         ctx.set_materialize_grads(False)
@@ -243,7 +385,7 @@ class _NormBwdCore(torch.autograd.Function):
         d2, t2, gamma, stats = ctx.saved_tensors
         u2 = _c(u).view(t2.shape)
         g_dy, g_t = torch.empty_like(t2), torch.empty_like(t2)
-        g_gamma = zeros(gamma.shape, gamma) if ctx.needs_input_grad[2] else None
+        g_gamma = la.small_zeros(gamma.shape, gamma) if ctx.needs_input_grad[2] else None
         ops.backend().norm_bwd2(t2, d2, u2, gamma.detach(), stats, g_dy=g_dy, g_x=g_t, g_gamma=g_gamma)
         return g_dy.view(u.shape), g_t.view(u.shape), g_gamma, None
 
@@ -254,7 +396,7 @@ def _norm_bwd_fused_diff(x, gamma, dy, stats, pre_tanh, drop):
     t = tanh_(x) if pre_tanh else x
     dt, dgamma, dbeta = _NormBwdCore.apply(dy, t, gamma, stats)
     if pre_tanh:
-        dt = dt * (1 - t * t)
+        dt = _TanhBwd.apply(dt, t)
     return dt, dgamma, dbeta
 
 
@@ -467,6 +609,101 @@ def _lstm_bptt_diff(gin, w_hh, dhs, need_dgin, need_dw):
     return dgin, dw
 
 
+# Under create_graph the LSTM's backward is the fused twice-differentiable node `_LstmBptt2` (second derivatives through dgin
+# only: what the WGAN-GP penalty needs); False routes through the step-by-step restatement `_lstm_bptt_diff`, which is
+# differentiable through the recurrent weight gradient as well.
+FUSED_LSTM_BPTT2 = True
+
+
+class _LstmBptt2(torch.autograd.Function):
+    """The BPTT of the zero-state LSTM as ONE twice-differentiable node: (gin, w_hh, dhs) -> (dgin, dw_hh), reusing the
+    buffers `_LstmSeq.forward` saved (activated gates, cell states, h operands: nothing is recomputed).
+    forward = the fused first-order loop (cell backward + recurrent data-gradient GEMM per step) that also keeps every
+    step's total dh and incoming dc;
+    backward (for a cotangent U of dgin: the WGAN-GP penalty, run_gun.py:362-375) = two more fused loops,
+      A (t ascending, the reverse of the BPTT recurrence): u_t = U_t + g_dh(t-1) W^T, then the closed-form
+        dlsg_lstm_cell_bwd2 -> cotangents of dh_t (= of dhs_t), of dc, and the injections g_pre_t / g_c0_t into the
+        forward's pre-activations / cell states;
+      B (t descending, an ordinary BPTT over the same forward with those injections): -> cotangent of gin;
+    and two time-batched weight-gradient GEMMs.  2 launches per step and loop, no torch arithmetic.  A cotangent of
+    dw_hh (second derivative through the recurrent weight gradient) is not supported: `_lstm_bptt_diff` covers it."""
+
+    @staticmethod
+    def forward(ctx, gin, w_hh, dhs, bufs, need_dw):
+        be = ops.backend()
+        acts, cs, hin, w_op = bufs
+        T, B, H4 = acts.shape
+        H = H4 // 4
+        dhs = _c(dhs)
+        bf = la.precision() == 'bf16'
+        dg32 = empty((T, B, H4), gin)
+        dg_op = la.op_empty((T, B), H4, gin) if bf else dg32
+        Sd = la.splitk_for(B, H, H4)
+        dhrec = zeros((Sd, B, H), gin)
+        dcs = zeros((T + 1, B, H), gin)                   # dcs[t+1] enters step t, dcs[t] leaves it
+        dht = empty((T, B, H), gin)                       # dh_t = dhs_t + recurrent part
+        w_t = w_op.transpose(-1, -2)
+        for t in range(T - 1, -1, -1):
+            be.lstm_cell_bwd(acts[t], cs[t], cs[t + 1], dhs[:, t], dcs[t + 1], dcs[t], dgates=dg32[t],
+                             dgates2=(dg_op[t] if bf else None), dh2=dhrec, dh_total=dht[t])
+            if t > 0:
+                be.gemm(dg_op[t], w_t, dhrec if Sd > 1 else dhrec[0], splitk=Sd)
+        dw = la.mm(la.flat2(dg_op).t(), la.flat2(hin).t()) if need_dw else None
+        ctx.save_for_backward(gin, w_hh)
+        ctx.bufs, ctx.mine = bufs, (dg_op, dcs, dht)
+        ctx.set_materialize_grads(False)
+        return dg32.transpose(0, 1), dw
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, U, u_w):
+        if u_w is not None:
+            raise NotImplementedError('second derivative through the recurrent weight gradient: use _lstm_bptt_diff')
+        if U is None:
+            return None, None, None, None, None
+        be = ops.backend()
+        gin, w_hh = ctx.saved_tensors
+        acts, cs, hin, w_op = ctx.bufs
+        dg_op, dcs, dht = ctx.mine
+        T, B, H4 = acts.shape
+        H = H4 // 4
+        bf = la.precision() == 'bf16'
+        Ut = U.transpose(0, 1).contiguous()
+        S = la.splitk_for(B, H4, H)
+        up = zeros((S, B, H4), gin)                       # split-K partials of g_dh(t-1) W^T
+        gdh = empty((T, B, H), gin)
+        gdh_in = la.op_zeros((T, B), H, gin)              # slot t: g_dh(t-1) as a GEMM operand (slot 0 = 0)
+        gdc = empty((T, B, H), gin)
+        gpre = empty((T, B, H4), gin)
+        gc0 = empty((T, B, H), gin)
+        for t in range(T):
+            if t > 0:
+                be.gemm(gdh_in[t], w_op, up if S > 1 else up[0], splitk=S)
+            be.lstm_cell_bwd2(acts[t], cs[t], cs[t + 1], dht[t], dcs[t + 1], Ut[t], gdc[t - 1] if t > 0 else None,
+                              gdh[t], gdc[t], gpre[t], gc0[t], u2=(up if t > 0 else None),
+                              g_dh2=(gdh_in[t + 1] if t + 1 < T else None))
+        a32 = empty((T, B, H4), gin)
+        a_op = la.op_empty((T, B), H4, gin) if bf else a32
+        Sd = la.splitk_for(B, H, H4)
+        hrec = zeros((Sd, B, H), gin)
+        zero_dh = zeros((B, H), gin)
+        dc, dc2 = empty((B, H), gin), empty((B, H), gin)
+        w_t = w_op.transpose(-1, -2)
+        for t in range(T - 1, -1, -1):
+            last = t == T - 1
+            be.lstm_cell_bwd(acts[t], cs[t], cs[t + 1], zero_dh, None if last else dc, dc2, dgates=a32[t],
+                             dgates2=(a_op[t] if bf else None), dh2=hrec, dc_next2=(None if last else gc0[t + 1]),
+                             dgates_add=gpre[t])
+            dc, dc2 = dc2, dc
+            if t > 0:
+                be.gemm(a_op[t], w_t, hrec if Sd > 1 else hrec[0], splitk=Sd)
+        g_w = None
+        if ctx.needs_input_grad[1]:
+            g_w = la.mm(la.flat2(a_op).t(), la.flat2(hin).t())                 # sum_t a_pre_t^T h(t-1)
+            la.mm(la.flat2(dg_op).t(), la.flat2(gdh_in).t(), out=g_w, accum=True)   # + sum_t dpre_t^T g_dh(t-1)
+        return a32.transpose(0, 1), g_w, gdh.transpose(0, 1), None, None
+
+
 class _LstmSeq(torch.autograd.Function):
     """Zero-state uni-directional LSTM over all steps: gin (B,T,4H) = x W_ih^T + b_ih + b_hh -> h (B,T,H).
     Forward and first-order backward are fused loops (recurrent GEMM with split-K partials summed by the cell kernel:
@@ -499,6 +736,9 @@ class _LstmSeq(torch.autograd.Function):
         gin, w_hh = ctx.saved_tensors
         need_dgin, need_dw = ctx.needs_input_grad
         if torch.is_grad_enabled():
+            if FUSED_LSTM_BPTT2:
+                dgin, dw = _LstmBptt2.apply(gin, w_hh, dhs, ctx.bufs, need_dw and not _INPUT_GRADS_ONLY)
+                return (dgin if need_dgin else None), (dw if need_dw else None)
             return _lstm_bptt_diff(gin, w_hh, dhs, need_dgin, need_dw)
         be = ops.backend()
         acts, cs, hin, w_op = ctx.bufs

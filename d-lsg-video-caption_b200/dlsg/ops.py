@@ -389,17 +389,23 @@ class CudaBackend:
             p.drop_p, p.seed, p.offset = drop
 
     def lstm_cell_bwd(self, acts, c_prev, c_new, dh, dc_next, dc_prev, dgates=None, dgates2=None, dgatesT=None,
-                      drop=None, dh2=None):
-        """dh / dh2: (B,H) fp32 views (unit inner stride); their sum is the gradient wrt the (dropped) h."""
+                      drop=None, dh2=None, dc_next2=None, dgates_add=None, dh_total=None):
+        """dh / dh2: (B,H) fp32 views (unit inner stride); their sum is the gradient wrt the (dropped) h.
+        dc_next2 (B,H) is added to dc_next, dgates_add (B,4H) to the gate gradients (injections of the second-order
+        reverse pass), dh_total (B,H) receives dh + dh2; all three contiguous fp32."""
         self._ck(acts)
         p = L.CellBwdT()
         self._fill_cell_bwd(p, acts, c_prev, c_new, dh, dc_next, dc_prev, dgates, dgates2, dgatesT, drop, dh2)
+        for t_ in (dc_next2, dgates_add, dh_total):
+            assert t_ is None or (t_.is_contiguous() and t_.dtype == torch.float32)
+        p.dc_next2, p.dgates_add, p.dh_total = _ptr(dc_next2), _ptr(dgates_add), _ptr(dh_total)
         self.launches += 1
         L.check(self.lib.dlsg_lstm_cell_bwd(C.byref(p), _stream()), 'dlsg_lstm_cell_bwd')
 
-    def lstm_cell_bwd2(self, acts, c_prev, c_new, dh, dc_next, u, w, g_dh, g_dc, g_pre, g_cprev):
+    def lstm_cell_bwd2(self, acts, c_prev, c_new, dh, dc_next, u, w, g_dh, g_dc, g_pre, g_cprev, u2=None, g_dh2=None):
         """Backward of lstm_cell_bwd: cotangents u (of dgates) / w (of dc_prev) -> cotangents of dh, dc_next, the gate
-        pre-activations and c_prev.  Contiguous fp32 (B,H) / (B,4H); c_prev, dc_next, u, w and outputs may be None."""
+        pre-activations and c_prev.  Contiguous fp32 (B,H) / (B,4H); c_prev, dc_next, u, w and outputs may be None.
+        u2: (B,4H) or split-K partials (S,B,4H) added to u; g_dh2: second copy of g_dh (any dtype, own row pitch)."""
         self._ck(acts)
         p = L.CellBwd2T()
         for t_ in (acts, c_prev, c_new, dh, dc_next, u, w, g_dh, g_dc, g_pre, g_cprev):
@@ -408,6 +414,14 @@ class CudaBackend:
         p.acts, p.c_prev, p.c_new, p.dh, p.dc_next = acts.data_ptr(), _ptr(c_prev), c_new.data_ptr(), dh.data_ptr(), _ptr(dc_next)
         p.u, p.w = _ptr(u), _ptr(w)
         p.g_dh, p.g_dc, p.g_pre, p.g_cprev = _ptr(g_dh), _ptr(g_dc), _ptr(g_pre), _ptr(g_cprev)
+        if u2 is not None:
+            assert u2.dtype == torch.float32 and (u2[0] if u2.dim() == 3 else u2).is_contiguous()
+            if u2.dim() == 3:
+                p.u2_nsplit, p.u2_stride_split = u2.shape[0], u2.stride(0)
+            p.u2 = u2.data_ptr()
+        if g_dh2 is not None:
+            assert g_dh2.stride(1) == 1
+            p.g_dh2, p.ld_g_dh2, p.g_dh2_dtype = g_dh2.data_ptr(), g_dh2.stride(0), _dt(g_dh2)
         self.launches += 1
         L.check(self.lib.dlsg_lstm_cell_bwd2(C.byref(p), _stream()), 'dlsg_lstm_cell_bwd2')
 
@@ -481,6 +495,36 @@ class CudaBackend:
         p.x, p.mask, p.scale, p.mask_mode = x.data_ptr(), _ptr(mask), scale, mask_mode
         self.launches += 1
         L.check(self.lib.dlsg_softmax_bwd(C.byref(p), dy.data_ptr(), dx.data_ptr(), _stream()), 'dlsg_softmax_bwd')
+
+    def softmax_bwd2(self, x, dy, u, dim, g_dy=None, g_x=None, scale=1.0, mask=None, mask_mode=0):
+        """Backward of softmax_bwd wrt (dy, x) for a cotangent u of its dx (closed form, one launch)."""
+        self._ck(x)
+        p = L.SoftmaxT()
+        for t_ in (dy, u, g_dy, g_x, mask):
+            assert t_ is None or self._same_layout(x, t_)
+        p.outer, p.n, p.inner, p.so, p.sn, p.si = self._softmax_desc(x, dim)
+        p.x, p.mask, p.scale, p.mask_mode = x.data_ptr(), _ptr(mask), scale, mask_mode
+        self.launches += 1
+        L.check(self.lib.dlsg_softmax_bwd2(C.byref(p), dy.data_ptr(), u.data_ptr(), _ptr(g_dy), _ptr(g_x), _stream()), 'dlsg_softmax_bwd2')
+
+    def ew(self, op, ins, outs, cols=0):
+        """Small fused element-wise forms (dlsg_ew, op = dlsg._lib.EW_*): contiguous fp32 tensors of one size (the per-row
+        operand of the LERP ops has n / cols elements); outputs may be None."""
+        p = L.EwT()
+        n = ins[0].numel()
+        self._ck(ins[0])
+        rows_e = {L.EW_LERP_ROWS: 2, L.EW_LERP_ROWS_BWD: 1}.get(op)
+        for k, t_ in enumerate(ins):
+            assert t_.is_contiguous() and t_.dtype == torch.float32
+            assert t_.numel() == (n // cols if k == rows_e else n), (op, k, t_.shape)
+            p.inp[k] = t_.data_ptr()
+        for k, t_ in enumerate(outs):
+            if t_ is not None:
+                assert t_.is_contiguous() and t_.dtype == torch.float32 and t_.numel() == n
+                p.out[k] = t_.data_ptr()
+        p.n, p.cols, p.op = n, cols, op
+        self.launches += 1
+        L.check(self.lib.dlsg_ew(C.byref(p), _stream()), 'dlsg_ew')
 
     # ------------------------------------------------------------------ node attention
     def node_attn_fwd(self, Kp, Vp, qp, alpha, ctx, rows_per_node=1):

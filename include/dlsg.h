@@ -174,6 +174,10 @@ typedef struct {
   int32_t B, H;
   float drop_p; int32_t _pad2; uint64_t seed, offset;
   int32_t dh2_nsplit; int32_t _pad3; int64_t dh2_stride_split;   /* dh2 = sum of dh2_nsplit (<=1: one) split-K partial buffers */
+  /* injections of the critic's second-order reverse pass (dlsg.generic._LstmBptt2): contiguous fp32, may be NULL */
+  const float* dc_next2;      /* (B,H)  added to dc_next                                              */
+  const float* dgates_add;    /* (B,4H) added to the gate gradients before they are written anywhere  */
+  float* dh_total;            /* (B,H)  out: dh + dh2 (before dropout), saved for dlsg_lstm_cell_bwd2 */
 } dlsg_lstm_cell_bwd_t;
 int dlsg_lstm_cell_bwd(const dlsg_lstm_cell_bwd_t* p, void* stream);
 /* Backward of the cell backward (second-order term of the WGAN-GP gradient penalty through DiscV2.lstm,
@@ -186,6 +190,9 @@ typedef struct {
   const float* u; const float* w;
   float* g_dh; float* g_dc; float* g_pre; float* g_cprev;
   int32_t B, H;
+  /* u_total = u + sum of u2_nsplit (<=1: one) split-K partial buffers (B,4H) of the recurrent product g_dh(t-1) W^T  */
+  const float* u2; int64_t u2_stride_split; int32_t u2_nsplit; int32_t g_dh2_dtype;
+  void* g_dh2; int64_t ld_g_dh2;     /* optional second copy of g_dh (any dtype, own pitch): the next step's GEMM operand */
 } dlsg_lstm_cell_bwd2_t;
 int dlsg_lstm_cell_bwd2(const dlsg_lstm_cell_bwd2_t* p, void* stream);
 
@@ -225,6 +232,30 @@ typedef struct {
 int dlsg_softmax_fwd(const dlsg_softmax_t* p, void* stream);
 /* dx = scale * y_unmasked*(dy' - sum(dy'*y_unmasked)), dy' = dy*postmask; y = forward output   */
 int dlsg_softmax_bwd(const dlsg_softmax_t* p, const float* dy, float* dx, void* stream);
+/* Backward OF dlsg_softmax_bwd with respect to (dy, x) for a cotangent u of dx (same layout as x): the second-order term of
+ * the WGAN-GP penalty through the critic's three softmaxes (run_gun.py:362-375 over sublayer.py:34,74,192, layer.py:706):
+ *   s = softmax(scale x [pre-masked]), g = dy [o postmask], u' = u [o premask], A = <g,s>, B = <u',s>
+ *   g_dy = scale s (u' - B) [o postmask];  q = scale (u' (g - A) - g B);  g_x = scale s (q - <q,s>).
+ * g_dy / g_x may be NULL. */
+int dlsg_softmax_bwd2(const dlsg_softmax_t* p, const float* dy, const float* u, float* g_dy, float* g_x, void* stream);
+
+/* ---- small fused element-wise forms (contiguous fp32, n elements): the pieces of the critic's first and second backward
+ * that are neither a GEMM, a LayerNorm, a softmax nor an LSTM cell (model.py:145-168, sublayer.py:167-170, run_gun.py:355-358).
+ * in[] / out[] are used as listed per op; `cols` is the row length for ops with a per-row operand e (index i / cols).   */
+enum {
+  DLSG_EW_TANH_BWD = 0,       /* in: dy, y            out0 = dy (1 - y^2)                                             */
+  DLSG_EW_TANH_BWD2 = 1,      /* in: dy, y, u         out0 = u (1 - y^2) [cot. of dy];  out1 = -2 y dy u [cot. of y]  */
+  DLSG_EW_MUL_BWD = 2,        /* in: dy, a, b         out0 = dy b [da];  out1 = dy a [db]                             */
+  DLSG_EW_MUL_BWD2 = 3,       /* in: dy, a, b, u0, u1 out0 = u0 b + u1 a [cot. of dy]; out1 = u1 dy [of a]; out2 = u0 dy [of b] */
+  DLSG_EW_LERP_ROWS = 4,      /* in: a, b, e(rows)    out0 = a e + b (1 - e)                                          */
+  DLSG_EW_LERP_ROWS_BWD = 5   /* in: dy, e(rows)      out0 = dy e;  out1 = dy (1 - e)       (any output may be NULL)  */
+};
+typedef struct {
+  const float* in[5]; float* out[3];
+  int64_t n; int64_t cols;
+  int32_t op; int32_t _pad;
+} dlsg_ew_t;
+int dlsg_ew(const dlsg_ew_t* p, void* stream);
 
 /* ---- AttentionShare core, one decode step (sublayer.py:32-39) ------------------------------
  * logits[r,p] = Kp[node(r),p,:].qp[r,:]/sqrt(H); alpha = softmax_p; ctx[r,:] = sum_p alpha*Vp.

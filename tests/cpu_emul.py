@@ -180,11 +180,15 @@ class CpuEmulBackend:
                 dst.copy_(h)
 
     def lstm_cell_bwd(self, acts, c_prev, c_new, dh, dc_next, dc_prev, dgates=None, dgates2=None, dgatesT=None, drop=None,
-                      dh2=None):
+                      dh2=None, dc_next2=None, dgates_add=None, dh_total=None):
         self.launches += 1
         assert drop is None or drop[0] == 0
         if dh2 is not None:
             dh = dh + (dh2.sum(0) if dh2.dim() == 3 else dh2)
+        if dh_total is not None:
+            dh_total.copy_(dh)
+        if dc_next2 is not None:
+            dc_next = dc_next2 if dc_next is None else dc_next + dc_next2
         H = acts.shape[1] // 4
         i, f, g, o = acts[:, :H], acts[:, H:2 * H], acts[:, 2 * H:3 * H], acts[:, 3 * H:]
         tc = torch.tanh(c_new)
@@ -193,6 +197,8 @@ class CpuEmulBackend:
             dc = dc + dc_next
         cp = c_prev if c_prev is not None else torch.zeros_like(c_new)
         d = torch.cat([dc * g * i * (1 - i), dc * cp * f * (1 - f), dc * i * (1 - g * g), dh * tc * o * (1 - o)], 1)
+        if dgates_add is not None:
+            d = d + dgates_add
         if dc_prev is not None:
             dc_prev.copy_(dc * f)
         if dgates is not None:
@@ -202,9 +208,12 @@ class CpuEmulBackend:
         if dgatesT is not None:
             dgatesT[:, :d.shape[0]].copy_(d.t())
 
-    def lstm_cell_bwd2(self, acts, c_prev, c_new, dh, dc_next, u, w, g_dh, g_dc, g_pre, g_cprev):
+    def lstm_cell_bwd2(self, acts, c_prev, c_new, dh, dc_next, u, w, g_dh, g_dc, g_pre, g_cprev, u2=None, g_dh2=None):
         """Reference by automatic differentiation of the restated cell backward (the kernel uses closed forms)."""
         self.launches += 1
+        if u2 is not None:
+            u2s = u2.sum(0) if u2.dim() == 3 else u2
+            u = u2s if u is None else u + u2s
         with torch.enable_grad():
             H = acts.shape[1] // 4
             a = acts.double()
@@ -235,6 +244,8 @@ class CpuEmulBackend:
         for dst, g_ in zip((g_dh, g_dc, g_pre, g_cprev), grads):
             if dst is not None:
                 dst.copy_(g_.float())
+        if g_dh2 is not None:
+            g_dh2.copy_(grads[0].float())
 
     @staticmethod
     def fused_step_supported(H):
@@ -298,6 +309,48 @@ class CpuEmulBackend:
         if mask_mode == 1:
             r = torch.where(mask > 0, r, torch.zeros_like(r))
         dx.copy_(r)
+
+    def softmax_bwd2(self, x, dy, u, dim, g_dy=None, g_x=None, scale=1.0, mask=None, mask_mode=0):
+        """Reference by automatic differentiation of the restated softmax backward (the kernel uses closed forms)."""
+        self.launches += 1
+        with torch.enable_grad():
+            x_ = x.detach().double().requires_grad_(True)
+            dy_ = dy.detach().double().requires_grad_(True)
+            s = self._sm(x_, dim, scale, mask, mask_mode)
+            g = dy_ if mask_mode != 2 else torch.where(mask > 0, dy_, torch.zeros_like(dy_))
+            r = scale * s * (g - (g * s).sum(dim, keepdim=True))
+            if mask_mode == 1:
+                r = torch.where(mask > 0, r, torch.zeros_like(r))
+            a, b = torch.autograd.grad((r * u.double()).sum(), [dy_, x_])
+        if g_dy is not None:
+            g_dy.copy_(a.float())
+        if g_x is not None:
+            g_x.copy_(b.float())
+
+    def ew(self, op, ins, outs, cols=0):
+        from dlsg import _lib as L
+        self.launches += 1
+        n = ins[0].numel()
+        v = [t.reshape(-1) for t in ins]
+        if op == L.EW_TANH_BWD:
+            res = [v[0] * (1 - v[1] * v[1])]
+        elif op == L.EW_TANH_BWD2:
+            res = [v[2] * (1 - v[1] * v[1]), -2 * v[1] * v[0] * v[2]]
+        elif op == L.EW_MUL_BWD:
+            res = [v[0] * v[2], v[0] * v[1]]
+        elif op == L.EW_MUL_BWD2:
+            res = [v[3] * v[2] + v[4] * v[1], v[4] * v[0], v[3] * v[0]]
+        elif op == L.EW_LERP_ROWS:
+            e = v[2].repeat_interleave(cols)
+            res = [v[0] * e + v[1] * (1 - e)]
+        elif op == L.EW_LERP_ROWS_BWD:
+            e = v[1].repeat_interleave(cols)
+            res = [v[0] * e, v[0] * (1 - e)]
+        else:
+            raise ValueError(op)
+        for dst, r in zip(outs, res):
+            if dst is not None:
+                dst.copy_(r.view(dst.shape))
 
     def node_attn_fwd(self, Kp, Vp, qp, alpha, ctx, rows_per_node=1):
         self.launches += 1

@@ -386,6 +386,31 @@ def test_lstm_cell_double_backward(be, H, nulls):
     both('lstm_cell_bwd2', be, args, {}, [7, 8, 9, 10], tol=2e-5)
 
 
+@pytest.mark.parametrize('H,S', [(64, 1), (512, 1), (512, 3), (50, 2)])
+def test_lstm_cell_second_order_loop_fields(be, H, S):
+    """The fields the critic's fused second-order loops use (dlsg.generic._LstmBptt2): cell backward with the injections
+    dc_next2 / dgates_add and the dh_total output; cell backward-of-backward with split-K partials added to u and a
+    second (bf16, pitched) copy of g_dh."""
+    B_ = 7
+    gates = R(1, B_, 4 * H)
+    c_prev, c_new = R(B_, H), torch.zeros(B_, H)
+    EM.lstm_cell_fwd(gates, c_prev, c_new)
+    acts = gates[0].contiguous()
+    kw = dict(dgates=torch.zeros(B_, 4 * H), dgates2=torch.zeros(B_, 4 * H + 16, dtype=torch.bfloat16)[:, :4 * H], dh2=R(S, B_, H),
+              dc_next2=R(B_, H), dgates_add=R(B_, 4 * H), dh_total=torch.zeros(B_, H))
+    both('lstm_cell_bwd', be, [acts, c_prev, c_new, R(B_, H), R(B_, H), torch.zeros(B_, H)], kw, [5, 'dgates', 'dh_total'], tol=1e-5)
+    both('lstm_cell_bwd', be, [acts, c_prev, c_new, R(B_, H), R(B_, H), torch.zeros(B_, H)], kw, ['dgates2'], tol=1e-2)
+    kw = dict(dgates=torch.zeros(B_, 4 * H), dh2=R(S, B_, H), dc_next2=None, dgates_add=R(B_, 4 * H))
+    both('lstm_cell_bwd', be, [acts, c_prev, c_new, torch.zeros(B_, H), None, torch.zeros(B_, H)], kw, [5, 'dgates'], tol=1e-5)
+    outs = [torch.zeros(B_, H), torch.zeros(B_, H), torch.zeros(B_, 4 * H), torch.zeros(B_, H)]
+    args = [acts, c_prev, c_new, R(B_, H), R(B_, H), R(B_, 4 * H), R(B_, H)] + outs
+    kw = dict(u2=R(S, B_, 4 * H) if S > 1 else R(B_, 4 * H), g_dh2=torch.zeros(B_, H + 24, dtype=torch.bfloat16)[:, 8:8 + H])
+    both('lstm_cell_bwd2', be, args, kw, [7, 8, 9, 10], tol=2e-5)
+    both('lstm_cell_bwd2', be, args, kw, ['g_dh2'], tol=1e-2)
+    args[5] = None                                            # u only from the partials
+    both('lstm_cell_bwd2', be, args, dict(u2=R(S, B_, 4 * H)), [7, 8, 9, 10], tol=2e-5)
+
+
 @pytest.mark.parametrize('H,post', [(64, False), (1024, False), (1536, True)])
 def test_fused_cell_norm(be, H, post):
     B_ = 7
@@ -418,6 +443,44 @@ def test_softmax(be, shape, dim, mask_mode):
     kw = dict(scale=0.37, mask=mask if mask_mode else None, mask_mode=mask_mode)
     both('softmax_fwd', be, [x, torch.zeros(*shape), dim], kw, [1], tol=1e-6)
     both('softmax_bwd', be, [x, R(*shape), torch.zeros(*shape), dim], kw, [2], tol=1e-5)
+
+
+@pytest.mark.parametrize('shape,dim', [((4, 70, 26), 1), ((3, 26, 5), 1), ((6, 26, 26), 2), ((7, 5, 1), 1), ((9, 2), 1)])
+@pytest.mark.parametrize('mask_mode', [0, 1, 2])
+def test_softmax_double_backward(be, shape, dim, mask_mode):
+    """Closed-form backward of the softmax backward (dlsg_softmax_bwd2) against automatic differentiation of its restatement."""
+    if len(shape) == 2:
+        shape = (shape[0], shape[1], 1)
+    x = R(*shape, scale=3.0)
+    mask = (R(*shape) > -0.5).float()
+    mask[0] = 0
+    kw = dict(g_dy=torch.zeros(*shape), g_x=torch.zeros(*shape), scale=0.37, mask=mask if mask_mode else None, mask_mode=mask_mode)
+    both('softmax_bwd2', be, [x, R(*shape), R(*shape), dim], kw, ['g_dy', 'g_x'], tol=2e-5)
+    kw['g_dy'] = None
+    both('softmax_bwd2', be, [x, R(*shape), R(*shape), dim], kw, ['g_x'], tol=2e-5)
+
+
+@pytest.mark.parametrize('n,cols', [(6 * 26 * 512, 26 * 512), (3 * 35, 35)])
+def test_elementwise_forms(be, n, cols):
+    """dlsg_ew: every op, the float4 path (aligned, n % 4 == 0) and the scalar path."""
+    from dlsg import _lib as L
+    t = lambda: R(n)
+    z = lambda: torch.zeros(n)
+    e = torch.rand(n // cols)
+    cases = [(L.EW_TANH_BWD, [t(), torch.tanh(t())], 1, 0), (L.EW_TANH_BWD2, [t(), torch.tanh(t()), t()], 2, 0),
+             (L.EW_MUL_BWD, [t(), t(), t()], 2, 0), (L.EW_MUL_BWD2, [t(), t(), t(), t(), t()], 3, 0),
+             (L.EW_LERP_ROWS, [t(), t(), e], 1, cols), (L.EW_LERP_ROWS_BWD, [t(), e], 2, cols)]
+    for op, ins, n_out, c in cases:
+        ref = [z() for _ in range(n_out)]
+        EM.ew(op, ins, ref, c)
+        outs = [torch.zeros(n, device=DEV) for _ in range(n_out)]
+        be.ew(op, [i_.to(DEV) for i_ in ins], outs, c)
+        for a_, b_ in zip(ref, outs):
+            assert float((a_ - b_.cpu()).abs().max()) <= 1e-6 * max(1.0, float(a_.abs().max())), op
+        if n_out > 1:                                         # an output left out
+            outs2 = [None] + [torch.zeros(n, device=DEV) for _ in range(n_out - 1)]
+            be.ew(op, [i_.to(DEV) for i_ in ins], outs2, c)
+            assert torch.equal(outs2[1], outs[1]), op
 
 
 # ----------------------------------------------------------------------------------------------- node attention
