@@ -615,7 +615,7 @@ lstm_cell_bwd_fast(const dlsg_lstm_cell_bwd_t p) {
   for (int k = 0; k < 4; ++k) {
     const int64_t col = (int64_t)k * H + h;
     const float4 d4 = make_float4(d[k][0], d[k][1], d[k][2], d[k][3]);
-    if (p.dgates) *reinterpret_cast<float4*>(p.dgates + (int64_t)b * 4 * H + col) = d4;
+    if (p.dgates) *reinterpret_cast<float4*>(p.dgates + (int64_t)b * (p.ld_dgates ? p.ld_dgates : 4 * (int64_t)H) + col) = d4;
     if (p.dgates2) st4dt(p.dgates2, p.dgates2_dtype, (int64_t)b * p.ld_dgates2 + col, d4);
     if (p.dgatesT) {
 #pragma unroll
@@ -659,7 +659,7 @@ lstm_cell_bwd_kernel(const dlsg_lstm_cell_bwd_t p) {
     for (int k = 0; k < 4; ++k) {
       const int64_t col = (int64_t)k * H + h;
       if (p.dgates_add) d[k] += p.dgates_add[(int64_t)b * 4 * H + col];
-      if (p.dgates) p.dgates[(int64_t)b * 4 * H + col] = d[k];
+      if (p.dgates) p.dgates[(int64_t)b * (p.ld_dgates ? p.ld_dgates : 4 * (int64_t)H) + col] = d[k];
       if (p.dgates2) st_from_float(p.dgates2, p.dgates2_dtype, (int64_t)b * p.ld_dgates2 + col, d[k]);
       if (p.dgatesT) st_from_float(p.dgatesT, p.dgatesT_dtype, col * p.ld_dgatesT + b, d[k]);
     }
@@ -952,7 +952,10 @@ lstm_cell_bwd2_kernel(const dlsg_lstm_cell_bwd2_t p) {
     const float tc = tanhf(p.c_new[e]);
     const float omt = 1.f - tc * tc;
     float ui = 0.f, uf = 0.f, ug = 0.f, uo = 0.f;
-    if (p.u) { ui = p.u[g0]; uf = p.u[g0 + H]; ug = p.u[g0 + 2 * (int64_t)H]; uo = p.u[g0 + 3 * (int64_t)H]; }
+    if (p.u) {
+      const float* q = p.u + (p.ld_u ? (int64_t)b * p.ld_u + h : g0);
+      ui = q[0]; uf = q[H]; ug = q[2 * (int64_t)H]; uo = q[3 * (int64_t)H];
+    }
     if (p.u2) {
       const int ns = p.u2_nsplit > 1 ? p.u2_nsplit : 1;
       for (int s_ = 0; s_ < ns; ++s_) {
@@ -966,7 +969,7 @@ lstm_cell_bwd2_kernel(const dlsg_lstm_cell_bwd2_t p) {
     const float S = ui * gg * si + uf * c0 * sf + ug * ig * sg + w * fg;       // d(L2)/dD
     const float Q = S * dh * og * (-2.f * tc * omt) + uo * dh * so * omt;       // d(L2)/dc through tc
     const float gdh = S * og * omt + uo * tc * so;
-    if (p.g_dh) p.g_dh[e] = gdh;
+    if (p.g_dh) p.g_dh[p.ld_g_dh ? (int64_t)b * p.ld_g_dh + h : e] = gdh;
     if (p.g_dh2) st_from_float(p.g_dh2, p.g_dh2_dtype, (int64_t)b * p.ld_g_dh2 + h, gdh);
     if (p.g_dc) p.g_dc[e] = S;
     if (p.g_cprev) p.g_cprev[e] = D * uf * sf + Q * fg;
@@ -1362,6 +1365,7 @@ int dlsg_lstm_cell_bwd(const dlsg_lstm_cell_bwd_t* p, void* stream) {
       (!p->dh2 || (a16(p->dh2) && p->lddh2 % 4 == 0 && p->dh2_stride_split % 4 == 0)) && (!p->c_prev || a16(p->c_prev)) &&
       (!p->dc_next || a16(p->dc_next)) && (!p->dc_prev || a16(p->dc_prev)) && (!p->dgates || a16(p->dgates)) &&
       (!p->dc_next2 || a16(p->dc_next2)) && (!p->dgates_add || a16(p->dgates_add)) && (!p->dh_total || a16(p->dh_total)) &&
+      p->ld_dgates % 4 == 0 &&
       (!p->dgates2 || (p->ld_dgates2 % 4 == 0 && (reinterpret_cast<uintptr_t>(p->dgates2) % (p->dgates2_dtype == DLSG_F32 ? 16 : 8)) == 0))) {
     const unsigned nb = (unsigned)(((int64_t)p->B * (p->H / 4) + 255) / 256);
     cudaStream_t st = (cudaStream_t)stream;

@@ -58,7 +58,7 @@ class CellBwdT(C.Structure):
                 ('dc_prev', vp), ('B', i32), ('H', i32),
                 ('drop_p', f32), ('_pad2', i32), ('seed', u64), ('offset', u64),
                 ('dh2_nsplit', i32), ('_pad3', i32), ('dh2_stride_split', i64),
-                ('dc_next2', vp), ('dgates_add', vp), ('dh_total', vp)]
+                ('dc_next2', vp), ('dgates_add', vp), ('dh_total', vp), ('ld_dgates', i64)]
 
 
 class AdamSegT(C.Structure):
@@ -79,7 +79,8 @@ class SegT(C.Structure):
 class CellBwd2T(C.Structure):
     _fields_ = [('acts', vp), ('c_prev', vp), ('c_new', vp), ('dh', vp), ('dc_next', vp), ('u', vp), ('w', vp),
                 ('g_dh', vp), ('g_dc', vp), ('g_pre', vp), ('g_cprev', vp), ('B', i32), ('H', i32),
-                ('u2', vp), ('u2_stride_split', i64), ('u2_nsplit', i32), ('g_dh2_dtype', i32), ('g_dh2', vp), ('ld_g_dh2', i64)]
+                ('u2', vp), ('u2_stride_split', i64), ('u2_nsplit', i32), ('g_dh2_dtype', i32), ('g_dh2', vp), ('ld_g_dh2', i64),
+                ('ld_u', i64), ('ld_g_dh', i64)]
 
 
 class CellNormFwdT(C.Structure):

@@ -636,23 +636,23 @@ class _LstmBptt2(torch.autograd.Function):
         H = H4 // 4
         dhs = _c(dhs)
         bf = la.precision() == 'bf16'
-        dg32 = empty((T, B, H4), gin)
-        dg_op = la.op_empty((T, B), H4, gin) if bf else dg32
-        Sd = la.splitk_for(B, H, H4)
+        dg32 = empty((B, T, H4), gin)                     # batch-major like gin: returned as it is
+        dg_op = la.op_empty((T, B), H4, gin) if bf else empty((T, B, H4), gin)   # time-major GEMM operand copy
+        Sd = la.splitk_rows(B, H, H4)
         dhrec = zeros((Sd, B, H), gin)
-        dcs = zeros((T + 1, B, H), gin)                   # dcs[t+1] enters step t, dcs[t] leaves it
+        dcs = empty((T + 1, B, H), gin)                   # dcs[t+1] enters step t (none at T-1), dcs[t] leaves it
         dht = empty((T, B, H), gin)                       # dh_t = dhs_t + recurrent part
         w_t = w_op.transpose(-1, -2)
         for t in range(T - 1, -1, -1):
-            be.lstm_cell_bwd(acts[t], cs[t], cs[t + 1], dhs[:, t], dcs[t + 1], dcs[t], dgates=dg32[t],
-                             dgates2=(dg_op[t] if bf else None), dh2=dhrec, dh_total=dht[t])
+            be.lstm_cell_bwd(acts[t], cs[t], cs[t + 1], dhs[:, t], dcs[t + 1] if t + 1 < T else None, dcs[t], dgates=dg32[:, t],
+                             dgates2=dg_op[t], dh2=dhrec, dh_total=dht[t])
             if t > 0:
                 be.gemm(dg_op[t], w_t, dhrec if Sd > 1 else dhrec[0], splitk=Sd)
         dw = la.mm(la.flat2(dg_op).t(), la.flat2(hin).t()) if need_dw else None
         ctx.save_for_backward(gin, w_hh)
         ctx.bufs, ctx.mine = bufs, (dg_op, dcs, dht)
         ctx.set_materialize_grads(False)
-        return dg32.transpose(0, 1), dw
+        return dg32, dw
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -668,10 +668,11 @@ class _LstmBptt2(torch.autograd.Function):
         T, B, H4 = acts.shape
         H = H4 // 4
         bf = la.precision() == 'bf16'
-        Ut = U.transpose(0, 1).contiguous()
-        S = la.splitk_for(B, H4, H)
-        up = zeros((S, B, H4), gin)                       # split-K partials of g_dh(t-1) W^T
-        gdh = empty((T, B, H), gin)
+        if U.stride(2) != 1:
+            U = U.contiguous()
+        S = la.splitk_rows(B, H4, H)
+        up = empty((S, B, H4), gin)                       # split-K partials of g_dh(t-1) W^T
+        gdh = empty((B, T, H), gin)                       # batch-major like dhs: returned as it is
         gdh_in = la.op_zeros((T, B), H, gin)              # slot t: g_dh(t-1) as a GEMM operand (slot 0 = 0)
         gdc = empty((T, B, H), gin)
         gpre = empty((T, B, H4), gin)
@@ -679,21 +680,20 @@ class _LstmBptt2(torch.autograd.Function):
         for t in range(T):
             if t > 0:
                 be.gemm(gdh_in[t], w_op, up if S > 1 else up[0], splitk=S)
-            be.lstm_cell_bwd2(acts[t], cs[t], cs[t + 1], dht[t], dcs[t + 1], Ut[t], gdc[t - 1] if t > 0 else None,
-                              gdh[t], gdc[t], gpre[t], gc0[t], u2=(up if t > 0 else None),
+            be.lstm_cell_bwd2(acts[t], cs[t], cs[t + 1], dht[t], dcs[t + 1] if t + 1 < T else None, U[:, t],
+                              gdc[t - 1] if t > 0 else None, gdh[:, t], gdc[t], gpre[t], gc0[t], u2=(up if t > 0 else None),
                               g_dh2=(gdh_in[t + 1] if t + 1 < T else None))
-        a32 = empty((T, B, H4), gin)
-        a_op = la.op_empty((T, B), H4, gin) if bf else a32
-        Sd = la.splitk_for(B, H, H4)
+        a32 = empty((B, T, H4), gin)
+        a_op = la.op_empty((T, B), H4, gin) if bf else empty((T, B, H4), gin)
+        Sd = la.splitk_rows(B, H, H4)
         hrec = zeros((Sd, B, H), gin)
         zero_dh = zeros((B, H), gin)
         dc, dc2 = empty((B, H), gin), empty((B, H), gin)
         w_t = w_op.transpose(-1, -2)
         for t in range(T - 1, -1, -1):
             last = t == T - 1
-            be.lstm_cell_bwd(acts[t], cs[t], cs[t + 1], zero_dh, None if last else dc, dc2, dgates=a32[t],
-                             dgates2=(a_op[t] if bf else None), dh2=hrec, dc_next2=(None if last else gc0[t + 1]),
-                             dgates_add=gpre[t])
+            be.lstm_cell_bwd(acts[t], cs[t], cs[t + 1], zero_dh, None if last else dc, dc2, dgates=a32[:, t],
+                             dgates2=a_op[t], dh2=hrec, dc_next2=(None if last else gc0[t + 1]), dgates_add=gpre[t])
             dc, dc2 = dc2, dc
             if t > 0:
                 be.gemm(a_op[t], w_t, hrec if Sd > 1 else hrec[0], splitk=Sd)
@@ -701,7 +701,7 @@ class _LstmBptt2(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             g_w = la.mm(la.flat2(a_op).t(), la.flat2(hin).t())                 # sum_t a_pre_t^T h(t-1)
             la.mm(la.flat2(dg_op).t(), la.flat2(gdh_in).t(), out=g_w, accum=True)   # + sum_t dpre_t^T g_dh(t-1)
-        return a32.transpose(0, 1), g_w, gdh.transpose(0, 1), None, None
+        return a32, g_w, gdh, None, None
 
 
 class _LstmSeq(torch.autograd.Function):
@@ -718,8 +718,10 @@ class _LstmSeq(torch.autograd.Function):
         H = H4 // 4
         w_op = la.op(w_hh.detach())
         S = la.splitk_for(B, H4, H)
-        gates = zeros((S, T, B, H4), gin)                 # split-K partials; [0] ends up holding the activated gates
-        cs = zeros((T + 1, B, H), gin)
+        gates = empty((S, T, B, H4), gin)                 # split-K partials; [0] ends up holding the activated gates
+        gates[:, 0].zero_()                               # (step 0 has no recurrent product; later steps are overwritten by theirs)
+        cs = empty((T + 1, B, H), gin)
+        cs[0].zero_()
         hin = la.op_zeros((T, B), H, gin)                 # h fed INTO step t, as a GEMM operand
         hs = empty((B, T, H), gin)
         for t in range(T):
@@ -746,22 +748,22 @@ class _LstmSeq(torch.autograd.Function):
         H = H4 // 4
         dhs = _c(dhs)
         bf = la.precision() == 'bf16'
-        dg32 = empty((T, B, H4), gin)
-        dg_op = la.op_empty((T, B), H4, gin) if bf else dg32
-        Sd = la.splitk_for(B, H, H4)
+        dg32 = empty((B, T, H4), gin)                     # batch-major like gin: returned as it is
+        dg_op = la.op_empty((T, B), H4, gin) if bf else empty((T, B, H4), gin)   # time-major GEMM operand copy
+        Sd = la.splitk_rows(B, H, H4)
         dhrec = zeros((Sd, B, H), gin)
-        dc, dc2 = zeros((B, H), gin), empty((B, H), gin)
+        dc, dc2 = empty((B, H), gin), empty((B, H), gin)
         w_t = w_op.transpose(-1, -2)
         for t in range(T - 1, -1, -1):
-            be.lstm_cell_bwd(acts[t], cs[t], cs[t + 1], dhs[:, t], dc, dc2, dgates=dg32[t], dgates2=(dg_op[t] if bf else None),
-                             dh2=dhrec)
+            be.lstm_cell_bwd(acts[t], cs[t], cs[t + 1], dhs[:, t], dc if t + 1 < T else None, dc2, dgates=(dg32[:, t] if need_dgin else None),
+                             dgates2=dg_op[t], dh2=dhrec)
             dc, dc2 = dc2, dc
             if t > 0:
                 be.gemm(dg_op[t], w_t, dhrec if Sd > 1 else dhrec[0], splitk=Sd)
         dw = None
         if need_dw:
             dw = la.mm(la.flat2(dg_op).t(), la.flat2(hin).t())      # sum_t dgates_t^T h_{t-1}  (hin[0] = 0)
-        return (dg32.transpose(0, 1) if need_dgin else None), dw
+        return (dg32 if need_dgin else None), dw
 
 
 def lstm(x, w_ih, w_hh, b_ih, b_hh):

@@ -157,7 +157,7 @@ import collections as _collections
 
 _PMEMO = {}
 _AMEMO = _collections.OrderedDict()
-_AMEMO_MAX = 32
+_AMEMO_MAX = 256
 _EPOCH = [0]
 _SCOPE_DEPTH = [0]
 _MANUAL_EPOCH = [False]
@@ -238,6 +238,23 @@ def mm32(a, b, out=None, **epi):
         out = torch.empty(a.shape[:-1] + (b.shape[-2],), dtype=torch.float32, device=a.device)
     ops.backend().gemm(a, b, out, **epi)
     return out
+
+
+def splitk_rows(rows, n_out, K, sms=148, cap=4):
+    """Split-K factor for a recurrent GEMM with MORE than 64 rows (the critic's stacked LSTM: 192 rows, dlsg.generic): few
+    128 x 128 tiles and a long K loop.  Same rule as the kernel's automatic split (gemm_tc.cu), but explicit, so that the
+    consuming cell kernel sums the partials instead of a reduce launch per step; capped at what its vector path sums."""
+    if rows <= 64:
+        return splitk_for(rows, n_out, K, sms)
+    if precision() != 'bf16':
+        return 1
+    tiles = ((rows + 127) // 128) * ((n_out + 127) // 128)
+    kb = (K + 63) // 64
+    if tiles * 2 > sms or kb < 16:
+        return 1
+    s = min(sms // tiles, kb // 8, cap)
+    per = (kb + s - 1) // s
+    return max(1, (kb + per - 1) // per)
 
 
 class WeightCache:

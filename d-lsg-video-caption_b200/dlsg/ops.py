@@ -408,8 +408,14 @@ class CudaBackend:
         u2: (B,4H) or split-K partials (S,B,4H) added to u; g_dh2: second copy of g_dh (any dtype, own row pitch)."""
         self._ck(acts)
         p = L.CellBwd2T()
-        for t_ in (acts, c_prev, c_new, dh, dc_next, u, w, g_dh, g_dc, g_pre, g_cprev):
+        for t_ in (acts, c_prev, c_new, dh, dc_next, w, g_dc, g_pre, g_cprev):
             assert t_ is None or (t_.is_contiguous() and t_.dtype == torch.float32)
+        for t_ in (u, g_dh):                              # row-pitched (B,.) slices of batch-major (B,T,.) tensors are fine
+            assert t_ is None or (t_.stride(1) == 1 and t_.dtype == torch.float32)
+        if u is not None:
+            p.ld_u = u.stride(0)
+        if g_dh is not None:
+            p.ld_g_dh = g_dh.stride(0)
         p.B, p.H = acts.shape[0], acts.shape[1] // 4
         p.acts, p.c_prev, p.c_new, p.dh, p.dc_next = acts.data_ptr(), _ptr(c_prev), c_new.data_ptr(), dh.data_ptr(), _ptr(dc_next)
         p.u, p.w = _ptr(u), _ptr(w)
@@ -430,6 +436,7 @@ class CudaBackend:
         """Fused LayerNorm backward (dy wrt y=[tanh](LN(x)), x = the cell's dropped h) + LSTM cell backward."""
         self._ck(acts)
         q = L.NormCellBwdT()
+        assert dgates is None or dgates.is_contiguous(), 'the fused LayerNorm + cell backward writes contiguous dgates'
         self._fill_cell_bwd(q.cell, acts, c_prev, c_new, dh, dc_next, dc_prev, dgates, dgates2, dgatesT, drop, dh2)
         assert dy.stride(1) == 1 and x.stride(1) == 1
         q.dy, q.lddy, q.x, q.ldx = dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0)
@@ -458,6 +465,9 @@ class CudaBackend:
             p.dh2, p.lddh2 = dh2.data_ptr(), dh2.stride(0)
         assert c_new.is_contiguous() and acts.is_contiguous()
         p.dgates, p.dc_prev, p.B, p.H = _ptr(dgates), _ptr(dc_prev), B, H4 // 4
+        if dgates is not None:
+            assert dgates.stride(1) == 1 and dgates.dtype == torch.float32
+            p.ld_dgates = dgates.stride(0)
         if dgates2 is not None:
             p.dgates2, p.ld_dgates2, p.dgates2_dtype = dgates2.data_ptr(), dgates2.stride(0), _dt(dgates2)
         if dgatesT is not None:

@@ -178,6 +178,7 @@ typedef struct {
   const float* dc_next2;      /* (B,H)  added to dc_next                                              */
   const float* dgates_add;    /* (B,4H) added to the gate gradients before they are written anywhere  */
   float* dh_total;            /* (B,H)  out: dh + dh2 (before dropout), saved for dlsg_lstm_cell_bwd2 */
+  int64_t ld_dgates;          /* row pitch of dgates (0: contiguous, 4H) - a (B,4H) slice of a batch-major (B,T,4H) tensor */
 } dlsg_lstm_cell_bwd_t;
 int dlsg_lstm_cell_bwd(const dlsg_lstm_cell_bwd_t* p, void* stream);
 /* Backward of the cell backward (second-order term of the WGAN-GP gradient penalty through DiscV2.lstm,
@@ -193,6 +194,7 @@ typedef struct {
   /* u_total = u + sum of u2_nsplit (<=1: one) split-K partial buffers (B,4H) of the recurrent product g_dh(t-1) W^T  */
   const float* u2; int64_t u2_stride_split; int32_t u2_nsplit; int32_t g_dh2_dtype;
   void* g_dh2; int64_t ld_g_dh2;     /* optional second copy of g_dh (any dtype, own pitch): the next step's GEMM operand */
+  int64_t ld_u, ld_g_dh;             /* row pitches of u / g_dh (0: contiguous): slices of batch-major (B,T,.) tensors    */
 } dlsg_lstm_cell_bwd2_t;
 int dlsg_lstm_cell_bwd2(const dlsg_lstm_cell_bwd2_t* p, void* stream);
 

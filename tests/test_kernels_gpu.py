@@ -153,6 +153,16 @@ def test_gemm_tc_splitk(be, splitk):
     both('gemm', be, [a, b, torch.zeros(splitk, M, N)], dict(splitk=splitk, bias=R(N)), [2], tol=2e-3)
 
 
+@pytest.mark.parametrize('M,N,K,splitk', [(192, 512, 2048, 4), (192, 2048, 512, 2), (130, 512, 2048, 3)])
+def test_gemm_tc_explicit_splitk_more_than_64_rows(be, M, N, K, splitk):
+    """Explicit split-K partials for a recurrent GEMM with more than 64 rows (the critic's stacked LSTM, 192 rows:
+    dlsg.linalg.splitk_rows), weight read K-major and as a transposed (MN-major) view."""
+    a, w = bf(R(M, K, scale=0.3)), bf(R(N, K, scale=0.3))
+    both('gemm', be, [a, w, torch.zeros(splitk, M, N)], dict(splitk=splitk), [2], tol=2e-3)
+    wt = bf(R(K, N, scale=0.3))
+    both('gemm', be, [a, wt.t(), torch.zeros(splitk, M, N)], dict(splitk=splitk), [2], tol=2e-3)
+
+
 @pytest.mark.parametrize('M,N,K', [(64, 4096, 2880), (64, 2880, 4096), (17, 1000, 1544), (256, 384, 1664), (3, 130, 520)])
 def test_gemm_tc_auto_splitk_fixup(be, M, N, K):
     """Skinny problems split K automatically (partials in the workspace + a reduce/epilogue kernel, fixed summation
@@ -400,7 +410,7 @@ def test_lstm_cell_second_order_loop_fields(be, H, S):
               dc_next2=R(B_, H), dgates_add=R(B_, 4 * H), dh_total=torch.zeros(B_, H))
     both('lstm_cell_bwd', be, [acts, c_prev, c_new, R(B_, H), R(B_, H), torch.zeros(B_, H)], kw, [5, 'dgates', 'dh_total'], tol=1e-5)
     both('lstm_cell_bwd', be, [acts, c_prev, c_new, R(B_, H), R(B_, H), torch.zeros(B_, H)], kw, ['dgates2'], tol=1e-2)
-    kw = dict(dgates=torch.zeros(B_, 4 * H), dh2=R(S, B_, H), dc_next2=None, dgates_add=R(B_, 4 * H))
+    kw = dict(dgates=torch.zeros(B_, 3, 4 * H)[:, 1], dh2=R(S, B_, H), dc_next2=None, dgates_add=R(B_, 4 * H))     # pitched dgates
     both('lstm_cell_bwd', be, [acts, c_prev, c_new, torch.zeros(B_, H), None, torch.zeros(B_, H)], kw, [5, 'dgates'], tol=1e-5)
     outs = [torch.zeros(B_, H), torch.zeros(B_, H), torch.zeros(B_, 4 * H), torch.zeros(B_, H)]
     args = [acts, c_prev, c_new, R(B_, H), R(B_, H), R(B_, 4 * H), R(B_, H)] + outs
@@ -409,6 +419,8 @@ def test_lstm_cell_second_order_loop_fields(be, H, S):
     both('lstm_cell_bwd2', be, args, kw, ['g_dh2'], tol=1e-2)
     args[5] = None                                            # u only from the partials
     both('lstm_cell_bwd2', be, args, dict(u2=R(S, B_, 4 * H)), [7, 8, 9, 10], tol=2e-5)
+    args[5], args[7] = R(B_, 2, 4 * H)[:, 1], torch.zeros(B_, 3, H)[:, 2]        # row-pitched u and g_dh (batch-major slices)
+    both('lstm_cell_bwd2', be, args, {}, [7, 8, 9, 10], tol=2e-5)
 
 
 @pytest.mark.parametrize('H,post', [(64, False), (1024, False), (1536, True)])

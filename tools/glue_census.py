@@ -21,6 +21,7 @@ from torch.utils._python_dispatch import TorchDispatchMode
 from cpu_emul import CpuEmulBackend
 from dlsg import synth, ops, linalg as la, functional as DF
 
+DEPTH = int(os.environ.get('CENSUS_DEPTH', '1'))
 SKIP = {'aten.view.default', 'aten.detach.default', 'aten.t.default', 'aten.transpose.int', 'aten.unsqueeze.default',
         'aten.expand.default', 'aten.slice.Tensor', 'aten.select.int', 'aten._unsafe_view.default', 'aten.as_strided.default',
         'aten.alias.default', 'aten.squeeze.dim', 'aten.squeeze.default', 'aten.permute.default', 'aten.unbind.int',
@@ -65,12 +66,14 @@ def wrap_backend(be, census):
                 if not census.inside and k not in ('make_convert_plan', 'make_adam_plan', 'fused_step_supported', 'attn2_supported',
                                                    'lstm_step_supported', 'region_aggregate_supported', 'latent_psl_supported'):
                     census.by_kernel[k] += 1
-                    site = '?'
+                    site = []
                     for fr in reversed(traceback.extract_stack(limit=40)):
                         fn = fr.filename
                         if ('/dlsg/' in fn or '/models/' in fn) and not fn.endswith(('ops.py', 'linalg.py')):
-                            site = '%s:%d' % (os.path.basename(fn), fr.lineno)
-                            break
+                            site.append('%s:%d' % (os.path.basename(fn), fr.lineno))
+                            if len(site) == DEPTH:
+                                break
+                    site = ' < '.join(site)
                     census.kernel_site[(k, site)] += 1
                 census.inside += 1
                 try:
