@@ -1,5 +1,5 @@
-OUT=gpurun_out/r04a; mkdir -p $OUT
-timeout 600 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu -k "lstm_cell or softmax or elementwise" > $OUT/t_kernels.log 2>&1; echo "kernels rc=$?" 
+OUT=gpurun_out/r04b; mkdir -p $OUT
+timeout 600 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu -k "lstm_cell or softmax or elementwise or splitk" > $OUT/t_kernels.log 2>&1; echo "kernels rc=$?" 
 timeout 600 python -m pytest tests/test_model_gpu.py tests/test_graphs_gpu.py -x -q -m gpu -k "disc or gan" > $OUT/t_disc.log 2>&1; echo "disc rc=$?"
 tail -3 $OUT/t_kernels.log $OUT/t_disc.log
 timeout 300 python tools/bench_gan.py > $OUT/gan_iteration.json 2> $OUT/gan.err; cat $OUT/gan_iteration.json

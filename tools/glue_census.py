@@ -48,6 +48,9 @@ class Census(TorchDispatchMode):
                 if ('/dlsg/' in fn or '/models/' in fn) and 'glue_census' not in fn:
                     site = '%s:%d' % (os.path.relpath(fn, ROOT).replace('d-lsg-video-caption_b200/', ''), fr.lineno)
                     break
+            ts = [x for x in list(args) + list((kwargs or {}).values()) if torch.is_tensor(x)]
+            if any(not x.is_contiguous() for x in ts) or len({tuple(x.shape) for x in ts if x.dim() > 0}) > 1:
+                name += '  [strided/broadcast %s]' % ','.join('x'.join(map(str, x.shape)) for x in ts[:2])
             self.by_site[(site, name)] += 1
             self.by_op[name] += 1
         return func(*args, **(kwargs or {}))
