@@ -178,7 +178,7 @@ int dlsg_lstm_step_fwd(const dlsg_lstm_step_t* p, void* stream) {
   DLSG_REQUIRE(p, "lstm_step_fwd: null params");
   DLSG_REQUIRE(dlsg_lstm_step_supported(p->B, p->H), "lstm_step_fwd: unsupported shape B=%d H=%d (B <= %d, H a multiple of %d)", p->B, p->H,
                LS_BMAX, LS_KC);
-  DLSG_REQUIRE(p->ndir >= 1 && p->ndir <= 2, "lstm_step_fwd: ndir must be 1 or 2");
+  DLSG_REQUIRE(p->ndir >= 1 && p->ndir <= DLSG_LSTM_STEP_MAXG, "lstm_step_fwd: ndir must be 1..%d", DLSG_LSTM_STEP_MAXG);
   auto a16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   DLSG_REQUIRE(p->ldgin % 4 == 0 && p->ldh_in % 8 == 0 && p->ldh_out % 4 == 0 && p->ldh_op % 4 == 0, "lstm_step_fwd: unaligned row pitches");
   for (int d = 0; d < p->ndir; ++d) {

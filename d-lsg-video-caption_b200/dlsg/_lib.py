@@ -144,8 +144,8 @@ class Attn2BwdT(C.Structure):
 
 
 class LstmStepT(C.Structure):
-    _fields_ = [('W', vp * 2), ('h_in', vp * 2), ('ldh_in', i64), ('gin', vp * 2), ('ldgin', i64), ('c_in', vp * 2), ('c_out', vp * 2),
-                ('acts', vp * 2), ('h_out', vp * 2), ('ldh_out', i64), ('h_op', vp * 2), ('ldh_op', i64),
+    _fields_ = [('W', vp * 4), ('h_in', vp * 4), ('ldh_in', i64), ('gin', vp * 4), ('ldgin', i64), ('c_in', vp * 4), ('c_out', vp * 4),
+                ('acts', vp * 4), ('h_out', vp * 4), ('ldh_out', i64), ('h_op', vp * 4), ('ldh_op', i64),
                 ('B', i32), ('H', i32), ('ndir', i32), ('_pad', i32)]
 
 

@@ -613,6 +613,8 @@ def _lstm_bptt_diff(gin, w_hh, dhs, need_dgin, need_dw):
 # only: what the WGAN-GP penalty needs); False routes through the step-by-step restatement `_lstm_bptt_diff`, which is
 # differentiable through the recurrent weight gradient as well.
 FUSED_LSTM_BPTT2 = True
+# Forward loop of the generic LSTM on the one-launch step kernel (recurrent product + cell) when the shape allows it.
+FUSED_LSTM_STEP = True
 
 
 class _LstmBptt2(torch.autograd.Function):
@@ -717,13 +719,30 @@ class _LstmSeq(torch.autograd.Function):
         B, T, H4 = gin.shape
         H = H4 // 4
         w_op = la.op(w_hh.detach())
+        hs = empty((B, T, H), gin)
+        ng = (B + 63) // 64                                # 64-row groups for the one-launch step kernel
+        if (FUSED_LSTM_STEP and la.precision() == 'bf16' and ng <= 4 and B % ng == 0 and w_op.is_contiguous()
+                and be.lstm_step_supported(B // ng, H)):
+            # recurrent product + cell in ONE launch per step (csrc/lstm_step.cu; the row groups share the weight)
+            sl = [slice(g * (B // ng), (g + 1) * (B // ng)) for g in range(ng)]
+            acts = empty((T, B, H4), gin)
+            cs = empty((T + 1, B, H), gin)
+            cs[0].zero_()
+            hin = la.op_empty((T, B), H, gin)
+            hin[0].zero_()
+            for t in range(T):
+                be.lstm_step_fwd([w_op] * ng, [hin[t][s_] for s_ in sl] if t > 0 else None, [gin[s_, t] for s_ in sl],
+                                 [cs[t][s_] for s_ in sl] if t > 0 else None, [cs[t + 1][s_] for s_ in sl], [acts[t][s_] for s_ in sl],
+                                 h_out=[hs[s_, t] for s_ in sl], h_op=([hin[t + 1][s_] for s_ in sl] if t + 1 < T else None))
+            ctx.save_for_backward(gin, w_hh)
+            ctx.bufs = (acts, cs, hin, w_op)
+            return hs
         S = la.splitk_for(B, H4, H)
         gates = empty((S, T, B, H4), gin)                 # split-K partials; [0] ends up holding the activated gates
         gates[:, 0].zero_()                               # (step 0 has no recurrent product; later steps are overwritten by theirs)
         cs = empty((T + 1, B, H), gin)
         cs[0].zero_()
         hin = la.op_zeros((T, B), H, gin)                 # h fed INTO step t, as a GEMM operand
-        hs = empty((B, T, H), gin)
         for t in range(T):
             if t > 0:
                 be.gemm(hin[t], w_op, gates[:, t] if S > 1 else gates[0, t], splitk=S)

@@ -330,19 +330,21 @@ int dlsg_latent_psl_fwd_multi(const float* const* X, const float* const* theta, 
 int dlsg_latent_psl_bwd_multi(const float* const* X, const float* const* theta, const float* const* Gs, const float* const* dN,
                               float* const* dX, float* const* dtheta, int32_t E, int32_t B, int32_t T, int32_t P, int32_t H, void* stream);
 
-/* ---- one LSTM time step in one launch (nn.LSTM of EncoderVisual, layer.py:52; up to two independent directions) -----
+/* ---- one LSTM time step in one launch (nn.LSTM of EncoderVisual, layer.py:52; up to DLSG_LSTM_STEP_MAXG independent groups) -----
  * gates = h_in W^T + gin ; i,f,o = sigmoid, g = tanh ; c_out = f c_in + i g ; h = o tanh(c_out)   (torch gate order i,f,g,o)
  * Each CTA owns 16 hidden units (64 rows of W), streams its weight slab and h_in through shared memory (cp.async, bf16),
  * mma.sync with fp32 accumulation, cell in the epilogue: replaces a split-K GEMM launch + a cell launch per direction.
- * Supported: B <= 64, H a multiple of 128, bf16 W / h_in with 16-byte aligned rows.                                   */
+ * Supported: B <= 64 rows per group, H a multiple of 128, bf16 W / h_in with 16-byte aligned rows.  A group is a direction of
+ * the BiLSTM (own weights) or a 64-row slice of a larger batch sharing one weight (the critic's stacked LSTM, model.py:152). */
+#define DLSG_LSTM_STEP_MAXG 4
 typedef struct {
-  const void* W[2];                       /* bf16 (4H, H) row-major recurrent weights                                   */
-  const void* h_in[2]; int64_t ldh_in;    /* bf16 (B, H) previous hidden state; NULL (all directions) = first step       */
-  const float* gin[2]; int64_t ldgin;     /* fp32 (B, 4H) input projection + biases of this step                         */
-  const float* c_in[2]; float* c_out[2];  /* fp32 (B, H) contiguous; c_in NULL = zeros                                   */
-  float* acts[2];                         /* out fp32 (B, 4H) contiguous: activated gates [i|f|g|o] (saved for BPTT)     */
-  float* h_out[2]; int64_t ldh_out;       /* out fp32 (B, H) view, optional                                              */
-  void* h_op[2]; int64_t ldh_op;          /* out bf16 (B, H) view, optional: the next step's h_in                        */
+  const void* W[DLSG_LSTM_STEP_MAXG];                       /* bf16 (4H, H) row-major recurrent weights                                   */
+  const void* h_in[DLSG_LSTM_STEP_MAXG]; int64_t ldh_in;    /* bf16 (B, H) previous hidden state; NULL (all directions) = first step       */
+  const float* gin[DLSG_LSTM_STEP_MAXG]; int64_t ldgin;     /* fp32 (B, 4H) input projection + biases of this step                         */
+  const float* c_in[DLSG_LSTM_STEP_MAXG]; float* c_out[DLSG_LSTM_STEP_MAXG];  /* fp32 (B, H) contiguous; c_in NULL = zeros                                   */
+  float* acts[DLSG_LSTM_STEP_MAXG];                         /* out fp32 (B, 4H) contiguous: activated gates [i|f|g|o] (saved for BPTT)     */
+  float* h_out[DLSG_LSTM_STEP_MAXG]; int64_t ldh_out;       /* out fp32 (B, H) view, optional                                              */
+  void* h_op[DLSG_LSTM_STEP_MAXG]; int64_t ldh_op;          /* out bf16 (B, H) view, optional: the next step's h_in                        */
   int32_t B, H, ndir, _pad;
 } dlsg_lstm_step_t;
 int dlsg_lstm_step_supported(int32_t B, int32_t H);

@@ -848,7 +848,8 @@ def test_gemm_static_operand_early_fetch_is_bit_identical(be, M, N, K, splitk, a
     assert float((outs[1].cpu() - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
 
 
-@pytest.mark.parametrize('B_,H,nd,first', [(64, 1024, 2, False), (64, 1024, 2, True), (5, 128, 1, False), (33, 256, 2, False)])
+@pytest.mark.parametrize('B_,H,nd,first', [(64, 1024, 2, False), (64, 1024, 2, True), (5, 128, 1, False), (33, 256, 2, False),
+                                           (64, 512, 3, False), (48, 512, 4, True)])
 def test_lstm_step_fused(be, B_, H, nd, first):
     """csrc/lstm_step.cu: recurrent product + LSTM cell of one time step in one launch (two directions), against the
     emulator's fp32 product of the same bf16 operands; strided views as the BiLSTM passes them (h of a (B, T, H) operand
