@@ -20,7 +20,7 @@ from . import losses
 
 class GanIteration:
     def __init__(self, G, D, opt_g, opt_d, frames, regions, captions, cap_lens, max_words=26, tf_ratio=0.6, num_d=5,
-                 gan_lambda=0.01, process_group=None, graph=True, warmup=2, batched=True):
+                 gan_lambda=0.01, process_group=None, graph=True, warmup=2, batched=True, overlap_g=True):
         dev = frames.device
         self.G, self.D, self.opt_g, self.opt_d = G, D, opt_g, opt_d
         self.frames, self.regions, self.captions = frames.clone(), regions.clone(), captions.clone()
@@ -37,6 +37,10 @@ class GanIteration:
             self.sync = DF.GradSync(process_group)
             self.sync_d = DF.GradSync(process_group)
         self.d_params = [p for p in D.parameters() if p.requires_grad]
+        # The generator's second forward (run_gun.py:183) does not depend on the critic steps (they update D only): it runs on
+        # a side stream next to them - the critic steps are ~10^3 small dependent launches that leave most SMs idle - and
+        # joins before D scores its output.  (Same program order on the host; only the stream differs.)
+        self.side = torch.cuda.Stream() if (overlap_g and dev.type == 'cuda') else None
         self.graph = None
         self.out = None
         if graph:
@@ -145,9 +149,17 @@ class GanIteration:
             real = caps[:, :L].contiguous()                                              # token ids: the one-hot is never built
         else:
             real = torch.zeros(B, L, self.V, device=caps.device).scatter_(2, caps[:, :L].unsqueeze(2), 1)  # :449-453
-        loss_d, wass = self._disc_steps(real, f_cap, obj, mot, att_mask, alpha)
         self.opt_g.zero_grad(set_to_none=True)
-        out, obj, mot, alpha = G(self.frames, self.regions, caps, L, self.tf)            # :183
+        if self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.side):
+                g_out = G(self.frames, self.regions, caps, L, self.tf)                   # :183, under the critic steps
+        loss_d, wass = self._disc_steps(real, f_cap, obj, mot, att_mask, alpha)
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+        else:
+            g_out = G(self.frames, self.regions, caps, L, self.tf)                       # :183
+        out, obj, mot, alpha = g_out
         cap_loss = losses.packed_cross_entropy(out, caps, self.lens, self.inv, unit_grad=True)            # :189-197
         f_logit = D(out, obj.detach(), mot.detach(), att_mask=att_mask, alpha_all=alpha.detach())          # :218
         loss_g = -f_logit.mean()

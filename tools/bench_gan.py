@@ -31,6 +31,7 @@ def main():
     ap.add_argument('--num-d', type=int, default=5)          # opt.py:36 num_D_visual
     ap.add_argument('--vocab', type=int, default=10547)
     ap.add_argument('--graph', type=int, default=1, help='1: the iteration captured as one CUDA graph; 0: eager')
+    ap.add_argument('--overlap-g', type=int, default=1, help='1: G forward #2 on a side stream under the critic steps')
     ap.add_argument('--batched', type=int, default=1, help='1: the three critic calls of a step as one stacked forward')
     ap.add_argument('--profile-dstep', action='store_true', help='warm up, then run ONE eager critic step inside '
                     'cudaProfilerStart/Stop and exit (ncu --profile-from-start off)')
@@ -70,7 +71,7 @@ def main():
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
-    it = GanIteration(G, D, opt_g, opt_d, frames, regions, caps, lens, L, eps_tf, a.num_d, lam, graph=bool(a.graph),
+    it = GanIteration(G, D, opt_g, opt_d, frames, regions, caps, lens, L, eps_tf, a.num_d, lam, graph=bool(a.graph), overlap_g=bool(a.overlap_g),
                       batched=bool(a.batched))
     for _ in range(a.warmup):
         it()
