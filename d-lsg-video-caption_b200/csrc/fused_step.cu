@@ -43,10 +43,7 @@ __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4
 // count; ptxas reuses two or three destination registers there, which serialises the loads into a chain of L2 round
 // trips: 10 us per launch inside the 26-step loop for 5 MB of data (ncu source view, profiles/r02_step_kernels_ncu.json).
 template <int S>
-__global__ void __launch_bounds__(384)
-lstm_cell_norm_fwd_fast(const dlsg_lstm_cell_norm_fwd_t q) {
-  pdl_prologue();
-  __shared__ float red[32];
+__device__ __forceinline__ float4 cell_norm_fwd_body(const dlsg_lstm_cell_norm_fwd_t& q, float* red) {
   const dlsg_lstm_cell_fwd_t& p = q.cell;
   const int b = blockIdx.x, H = p.H, tid = threadIdx.x;
   const int h = tid * 4;
@@ -142,6 +139,128 @@ lstm_cell_norm_fwd_fast(const dlsg_lstm_cell_norm_fwd_t q) {
     const float4 y4 = make_float4(y[0], y[1], y[2], y[3]);
     if (q.y) st4any(q.y, q.y_dtype, (int64_t)b * q.ldy + h, y4, vy);
     if (q.y2) st4any(q.y2, q.y2_dtype, (int64_t)b * q.ldy2 + h, y4, vy2);
+    return y4;
+  }
+  return z4;
+}
+
+template <int S>
+__global__ void __launch_bounds__(384)
+lstm_cell_norm_fwd_fast(const dlsg_lstm_cell_norm_fwd_t q) {
+  pdl_prologue();
+  __shared__ float red[32];
+  cell_norm_fwd_body<S>(q, red);
+}
+
+// ---- query-LSTM cell + LayerNorm AND the hoisted attention step + context output layer in ONE launch (layer.py:571-591):
+// one CTA per batch row, 256 threads per attention head.  Threads [0, H/4) run the cell + LayerNorm exactly as
+// lstm_cell_norm_fwd_fast does and leave q = dropout(LN(query_h)) in shared memory; then every head's 256 threads run
+// attn2_fwd_kernel's step (scores over the P latent nodes, softmax, weighted sum, tanh -> LayerNorm -> dropout) on it.
+// Same arithmetic, same Philox sites, same outputs as the two kernels launched back to back - one launch gap and one
+// kernel latency less per decode step.
+constexpr int FA_PM = 8;          // max latent nodes (= APM of decode_ops.cu)
+__device__ __forceinline__ float fa_dot4(const float4 a, const float4 b) { return (a.x * b.x + a.y * b.y) + (a.z * b.z + a.w * b.w); }
+// sum over the 256 threads of one head; every thread of the block calls it
+__device__ __forceinline__ float fa_head_sum(float v, float (*sh)[8], int hd, int w, int lane) {
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[hd][w] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r += sh[hd][i];
+  return r;
+}
+
+template <int S>
+__global__ void __launch_bounds__(512)
+cell_norm_attn2_fwd_kernel(const dlsg_cell_norm_attn2_fwd_t f) {
+  pdl_prologue();
+  __shared__ float red[32];
+  __shared__ __align__(16) float qs[1024];
+  __shared__ float ared[2][8][FA_PM];
+  __shared__ float al[2][FA_PM];
+  __shared__ float hred[2][8];
+  const dlsg_attn2_fwd_t& p = f.at;
+  const int tid = threadIdx.x;
+  {
+    const float4 y4 = cell_norm_fwd_body<S>(f.cn, red);
+    if (tid * 4 < f.cn.cell.H) *reinterpret_cast<float4*>(qs + tid * 4) = y4;
+  }
+  __syncthreads();
+  const int r = blockIdx.x, hd = tid >> 8, t = tid & 255, lane = tid & 31, w = t >> 5;
+  const int node = r / p.rows_per_node;
+  const int c = t * 4;
+  const bool ak = c < p.Hk, av = c < p.Hv;
+  const float* KW = p.KW + (((int64_t)hd * p.nodes + node) * p.P) * p.Hk;
+  const float* VW = p.VW + (((int64_t)hd * p.nodes + node) * p.P) * p.Hv;
+  float4 k4[FA_PM], v4[FA_PM], q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ak) q4 = *reinterpret_cast<const float4*>(qs + c);
+#pragma unroll
+  for (int j = 0; j < FA_PM; ++j) {
+    k4[j] = make_float4(0.f, 0.f, 0.f, 0.f); v4[j] = k4[j];
+    if (j < p.P) {
+      if (ak) k4[j] = *reinterpret_cast<const float4*>(KW + (int64_t)j * p.Hk + c);
+      if (av) v4[j] = *reinterpret_cast<const float4*>(VW + (int64_t)j * p.Hv + c);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < FA_PM; ++j) {
+    const float s_ = warp_sum(fa_dot4(k4[j], q4));
+    if (lane == 0) ared[hd][w][j] = s_;
+  }
+  __syncthreads();
+  if (t == 0) {
+    float lg[FA_PM], mx = -INFINITY;
+    for (int j = 0; j < p.P; ++j) {
+      float s_ = 0.f;
+      for (int ww = 0; ww < 8; ++ww) s_ += ared[hd][ww][j];
+      lg[j] = s_ * p.scale; mx = fmaxf(mx, lg[j]);
+    }
+    float sum = 0.f;
+    for (int j = 0; j < p.P; ++j) { lg[j] = expf(lg[j] - mx); sum += lg[j]; }
+    const float inv = 1.f / sum;
+    for (int j = 0; j < p.P; ++j) {
+      const float a = lg[j] * inv;
+      al[hd][j] = a;
+      if (p.alpha) p.alpha[(int64_t)r * p.ldalpha + hd * p.P + j] = a;
+    }
+  }
+  __syncthreads();
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (av) {
+#pragma unroll
+    for (int j = 0; j < FA_PM; ++j) {
+      if (j < p.P) { const float a = al[hd][j]; acc.x = fmaf(a, v4[j].x, acc.x); acc.y = fmaf(a, v4[j].y, acc.y); acc.z = fmaf(a, v4[j].z, acc.z); acc.w = fmaf(a, v4[j].w, acc.w); }
+    }
+    *reinterpret_cast<float4*>(p.co + (int64_t)r * p.ldco + hd * p.Hv + c) = acc;
+  }
+  if (p.y == nullptr) return;                       // uniform
+  float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (av) t4 = make_float4(tanhf(acc.x), tanhf(acc.y), tanhf(acc.z), tanhf(acc.w));
+  const float* gam = hd ? p.gamma[1] : p.gamma[0];
+  const float* bet = hd ? p.beta[1] : p.beta[0];
+  float4 g4 = t4, b4 = t4;
+  if (av) { g4 = *reinterpret_cast<const float4*>(gam + c); b4 = *reinterpret_cast<const float4*>(bet + c); }
+  const float invH = 1.f / (float)p.Hv;
+  const float mean = fa_head_sum(av ? (t4.x + t4.y) + (t4.z + t4.w) : 0.f, hred, hd, w, lane) * invH;
+  float sq = 0.f;
+  if (av) { const float a = t4.x - mean, b = t4.y - mean, cc = t4.z - mean, d = t4.w - mean; sq = (a * a + b * b) + (cc * cc + d * d); }
+  const float rstd = rsqrtf(fa_head_sum(sq, hred, hd, w, lane) * invH + 1e-5f);
+  if (p.stats && t == 0) {
+    float* st = p.stats + (int64_t)hd * p.stats_head_stride + 2 * (int64_t)r;
+    st[0] = mean; st[1] = rstd;
+  }
+  if (av) {
+    float4 y;
+    y.x = (t4.x - mean) * rstd * g4.x + b4.x; y.y = (t4.y - mean) * rstd * g4.y + b4.y;
+    y.z = (t4.z - mean) * rstd * g4.z + b4.z; y.w = (t4.w - mean) * rstd * g4.w + b4.w;
+    if (p.drop_p > 0.f) {
+      const float4 m = drop_mask4(p.drop_p, 1.f / (1.f - p.drop_p), p.seed,
+                                  p.offset + (uint64_t)hd * p.offset_head_stride + (uint64_t)r * p.Hv + c);
+      y.x *= m.x; y.y *= m.y; y.z *= m.z; y.w *= m.w;
+    }
+    st4any(p.y, p.y_dtype, (int64_t)r * p.ldy + hd * p.Hv + c, y, true);
   }
 }
 
@@ -480,6 +599,35 @@ int dlsg_lstm_cell_norm_fwd(const dlsg_lstm_cell_norm_fwd_t* q, void* stream) {
   }
   DLSG_LAUNCH(lstm_cell_norm_fwd_kernel, p.B, nt, 0, (cudaStream_t)stream, *q);
   return check_launch("lstm_cell_norm_fwd_kernel");
+}
+
+int dlsg_cell_norm_attn2_supported(const dlsg_cell_norm_attn2_fwd_t* f) {
+  const dlsg_lstm_cell_fwd_t& p = f->cn.cell;
+  const dlsg_attn2_fwd_t& a = f->at;
+  return (p.H % 4 == 0 && p.H <= 1024 && p.H == a.Hk && a.Hv % 4 == 0 && a.Hv <= 1024 && a.nh >= 1 && a.nh <= 2 && a.P >= 1 && a.P <= FA_PM &&
+          p.nsplit >= 1 && p.nsplit <= 4 && p.B == a.rows && a.rows_per_node >= 1) ? 1 : 0;
+}
+int dlsg_cell_norm_attn2_fwd(const dlsg_cell_norm_attn2_fwd_t* f, void* stream) {
+  const dlsg_lstm_cell_fwd_t& p = f->cn.cell;
+  const dlsg_attn2_fwd_t& a = f->at;
+  DLSG_REQUIRE(dlsg_cell_norm_attn2_supported(f), "cell_norm_attn2_fwd: unsupported shape (H=%d Hk=%d Hv=%d nh=%d P=%d nsplit=%d)", p.H, a.Hk, a.Hv, a.nh, a.P, p.nsplit);
+  DLSG_REQUIRE(a16(p.gates) && p.stride_split % 4 == 0 && (!p.row_bias || (a16(p.row_bias) && p.ld_row_bias % 4 == 0)) && (!p.bias || a16(p.bias)) &&
+               (!p.c_prev || a16(p.c_prev)) && a16(p.c_out) && (!p.h_out || a16(p.h_out)) && a16(f->cn.gamma) && a16(f->cn.beta),
+               "cell_norm_attn2_fwd: fp32 cell operands must be 16-byte aligned");
+  DLSG_REQUIRE(p.offset % 4 == 0 && f->cn.yoffset % 4 == 0 && a.offset % 4 == 0, "cell_norm_attn2_fwd: dropout offsets must be multiples of 4");
+  DLSG_REQUIRE(a.KW && a.VW && a.co && a16(a.KW) && a16(a.VW) && a16(a.co) && a.ldco % 4 == 0, "cell_norm_attn2_fwd: attention operands must be 16-byte aligned");
+  DLSG_REQUIRE(!a.y || (a.gamma[0] && a.beta[0] && (a.nh < 2 || (a.gamma[1] && a.beta[1])) && a.ldy % 4 == 0 &&
+                        (reinterpret_cast<uintptr_t>(a.y) % (a.y_dtype == DLSG_F32 ? 16 : 8)) == 0),
+               "cell_norm_attn2_fwd: output-layer operands missing or unaligned");
+  const int nt = 256 * a.nh;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (p.nsplit) {
+    case 1: DLSG_LAUNCH(cell_norm_attn2_fwd_kernel<1>, p.B, nt, 0, st, *f); break;
+    case 2: DLSG_LAUNCH(cell_norm_attn2_fwd_kernel<2>, p.B, nt, 0, st, *f); break;
+    case 3: DLSG_LAUNCH(cell_norm_attn2_fwd_kernel<3>, p.B, nt, 0, st, *f); break;
+    default: DLSG_LAUNCH(cell_norm_attn2_fwd_kernel<4>, p.B, nt, 0, st, *f); break;
+  }
+  return check_launch("cell_norm_attn2_fwd_kernel");
 }
 
 int dlsg_norm_lstm_cell_bwd(const dlsg_norm_lstm_cell_bwd_t* q, void* stream) {

@@ -11,6 +11,7 @@
 // instead of hanging.
 #include <cuda.h>
 #include <stdlib.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace dlsg {
@@ -785,10 +786,13 @@ int gemm_tc_dispatch(const dlsg_gemm_t* g, cudaStream_t st) {
     const int bn = Q <= 32 ? 32 : (Q <= 64 ? 64 : 128);
     const int64_t tiles = (int64_t)((P + BM - 1) / BM) * ((Q + bn - 1) / bn) * batch;
     const int kb = (g->K + BK - 1) / BK;
-    // the reduce launch costs ~2-3 us in a dependent chain: only worth it when every split still streams >= 8 k-blocks
-    if (tiles * 2 <= kNumSM && kb >= 16) {
+    // the reduce launch costs ~2-3 us in a dependent chain: only worth it when every split still streams >= 16 k-blocks
+    // (8 -> 16 measured: step 6.28 -> 6.24 ms, greedy B=256 35.4 -> 37.8 k captions/s, beam-5 18.6 -> 19.6 k; profiles/r04e_*)
+    // (DLSG_AUTOSPLIT_MIN_KB: measurement switch for that threshold, k-blocks per split)
+    static const int min_kb = [] { const char* e = getenv("DLSG_AUTOSPLIT_MIN_KB"); const int v = e ? atoi(e) : 16; return v < 2 ? 2 : v; }();
+    if (tiles * 2 <= kNumSM && kb >= 2 * min_kb) {
       int S = (int)(kNumSM / tiles);      // floor: all tiles*S CTAs run in ONE wave of the persistent grid
-      if (S > kb / 8) S = kb / 8;
+      if (S > kb / min_kb) S = kb / min_kb;
       if (S > 16) S = 16;
       const int per = (kb + S - 1) / S;
       S = (kb + per - 1) / per;

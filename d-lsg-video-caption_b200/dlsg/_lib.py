@@ -131,6 +131,10 @@ class Attn2FwdT(C.Structure):
                 ('drop_p', f32), ('_pad1', i32), ('seed', u64), ('offset', u64), ('offset_head_stride', u64)]
 
 
+class CellNormAttn2FwdT(C.Structure):
+    _fields_ = [('cn', CellNormFwdT), ('at', Attn2FwdT)]
+
+
 class Attn2BwdT(C.Structure):
     _fields_ = [('KW', vp), ('VW', vp), ('q', vp), ('alpha', vp), ('dco', vp), ('dalpha_ext', vp),
                 ('dq', vp), ('dKW', vp), ('dVW', vp),
@@ -174,6 +178,8 @@ SIGNATURES = {
     'dlsg_region_aggregate_bwd': (i32, [C.POINTER(RegionAggBwdT), vp]),
     'dlsg_attn2_supported': (i32, [i32, i32, i32, i32]),
     'dlsg_attn2_fwd': (i32, [C.POINTER(Attn2FwdT), vp]),
+    'dlsg_cell_norm_attn2_supported': (i32, [C.POINTER(CellNormAttn2FwdT)]),
+    'dlsg_cell_norm_attn2_fwd': (i32, [C.POINTER(CellNormAttn2FwdT), vp]),
     'dlsg_attn2_bwd': (i32, [C.POINTER(Attn2BwdT), vp]),
     'dlsg_attn2_bwd_nodes': (i32, [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     'dlsg_version': (i32, []),

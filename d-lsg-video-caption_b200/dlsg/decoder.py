@@ -10,6 +10,7 @@ Per step the two LSTM gate GEMMs read one concatenated operand row each:
 and every kernel writes its result straight into the slot of the operand row that consumes it.
 """
 import math
+import os
 
 import torch
 
@@ -21,7 +22,9 @@ from .linalg import empty, zeros, small_zeros, op, op_empty, op_zeros, ceil8
 START = 1
 
 
-splitk_for = la.splitk_for
+# the decode step's cell + LayerNorm + attention as one launch when the shape allows (measurement switch)
+FUSED_CELL_ATTN = os.environ.get('DLSG_FUSED_CELL_ATTN', '1') != '0'
+splitk_for = la.splitk_rows          # (= la.splitk_for up to 64 rows; explicit partials for the 65..~300-row decode batches too)
 
 
 flat2 = la.flat2
@@ -149,19 +152,32 @@ class DecoderCore:
         qy, qy2 = (b.q32[i], b.Xl[i][:, oq:oq + Hq]) if self.hoist else (b.Xl[i][:, oq:oq + Hq], None)
         lnq_w, lnq_b = t[pf + 'query_lstm_layernorm.weight'], t[pf + 'query_lstm_layernorm.bias']
         rb = Gq if gq_rows is None else gq_rows
-        if self.fused:
+        attn = None
+        if self.hoist:
+            # attention over the hoisted KW / VW (Kp, Vp hold them) + the context output layer tanh -> LayerNorm -> dropout of
+            # both heads, written straight into the lang-LSTM operand row
+            attn = dict(KW=Kp, VW=Vp, q=b.q32[i], alpha=b.alpha[i], co=b.co[i], scale=1.0 / math.sqrt(H), rows_per_node=rows_per_node,
+                        ln=dict(gamma=[t[pf + h + '.output_layer.2.weight'] for h in self.heads],
+                                beta=[t[pf + h + '.output_layer.2.bias'] for h in self.heads],
+                                y=b.Xl[i][:, :nh * H], stats=b.statc[i], drop=dc, drop_head_stride=1 << 28))
+        one_launch = False
+        if self.fused and self.hoist and FUSED_CELL_ATTN:
+            # cell + LayerNorm + attention + output layer of the step in ONE launch (csrc/fused_step.cu)
+            one_launch = be.cell_norm_attn2_fwd(dict(gates=b.gq[:, i], c_prev=b.cq[i], c_out=b.cq[j], gamma=lnq_w, beta=lnq_b, y=qy,
+                                                     h_out=b.qh[i], row_bias=rb, h2=b.Xq[j][:, oQ:oQ + Hq], y2=qy2, stats=b.statq[i],
+                                                     ydrop=dq), attn)
+        if one_launch:
+            pass
+        elif self.fused:
             be.lstm_cell_norm_fwd(b.gq[:, i], b.cq[i], b.cq[j], lnq_w, lnq_b, qy, h_out=b.qh[i], row_bias=rb,
                                   h2=b.Xq[j][:, oQ:oQ + Hq], y2=qy2, stats=b.statq[i], ydrop=dq)
         else:
             be.lstm_cell_fwd(b.gq[:, i], b.cq[i], b.cq[j], h_out=b.qh[i], row_bias=rb, h2=b.Xq[j][:, oQ:oQ + Hq])
             be.norm_fwd(b.qh[i], lnq_w, lnq_b, y=qy, y2=qy2, stats=b.statq[i], drop=dq)
-        if self.hoist:
-            # one kernel: attention over the hoisted KW / VW (Kp, Vp hold them) + the context output layer
-            # tanh -> LayerNorm -> dropout of both heads, written straight into the lang-LSTM operand row
-            be.attn2_fwd(Kp, Vp, b.q32[i], b.alpha[i], b.co[i], 1.0 / math.sqrt(H), rows_per_node,
-                         ln=dict(gamma=[t[pf + h + '.output_layer.2.weight'] for h in self.heads],
-                                 beta=[t[pf + h + '.output_layer.2.bias'] for h in self.heads],
-                                 y=b.Xl[i][:, :nh * H], stats=b.statc[i], drop=dc, drop_head_stride=1 << 28))
+        if one_launch:
+            pass
+        elif self.hoist:
+            be.attn2_fwd(**attn)
         else:
             be.gemm(b.Xl[i][:, oq:oq + Hq], pk['Wqp'], b.qp[i])
             be.node_attn_fwd(Kp, Vp, b.qp[i], b.alpha[i], b.ctxr[i], rows_per_node)

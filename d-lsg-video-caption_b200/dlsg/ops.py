@@ -357,6 +357,11 @@ class CudaBackend:
         """Fused cell + LayerNorm: y = [tanh](LN(h)) (+dropout); h itself goes to h_out/h2/h3 as in lstm_cell_fwd."""
         self._ck(gates)
         q = L.CellNormFwdT()
+        self._fill_cell_norm_fwd(q, gates, c_prev, c_out, gamma, beta, y, h_out, row_bias, bias, h2, h3, drop, y2, stats, post_tanh, ydrop)
+        self.launches += 1
+        L.check(self.lib.dlsg_lstm_cell_norm_fwd(C.byref(q), _stream()), 'dlsg_lstm_cell_norm_fwd')
+
+    def _fill_cell_norm_fwd(self, q, gates, c_prev, c_out, gamma, beta, y, h_out, row_bias, bias, h2, h3, drop, y2, stats, post_tanh, ydrop):
         self._fill_cell_fwd(q.cell, gates, c_prev, c_out, h_out, row_bias, bias, h2, h3, drop)
         q.gamma, q.beta, q.stats = gamma.data_ptr(), beta.data_ptr(), _ptr(stats)
         q.y, q.ldy, q.y_dtype = y.data_ptr(), y.stride(0), _dt(y)
@@ -365,8 +370,25 @@ class CudaBackend:
         q.post_tanh = 1 if post_tanh else 0
         if ydrop is not None and ydrop[0] > 0:
             q.ydrop_p, q.yseed, q.yoffset = ydrop
+
+    def cell_norm_attn2_fwd(self, cell, attn):
+        """The query LSTM's cell + LayerNorm and the hoisted attention step of one decode step in ONE launch
+        (dlsg_cell_norm_attn2_fwd).  cell: dict of lstm_cell_norm_fwd's arguments; attn: dict of attn2_fwd's arguments (its
+        `q` must be the cell part's `y`: the kernel takes it from there).  Returns False (nothing launched) when the shape
+        is outside the fused kernel's range - the caller then issues the two launches."""
+        self._ck(cell['gates'])
+        f = L.CellNormAttn2FwdT()
+        c = dict(h_out=None, row_bias=None, bias=None, h2=None, h3=None, drop=None, y2=None, stats=None, post_tanh=False, ydrop=None)
+        c.update(cell)
+        assert attn['q'].data_ptr() == c['y'].data_ptr() and c['y'].dtype == torch.float32 and not c['post_tanh']
+        self._fill_cell_norm_fwd(f.cn, c['gates'], c['c_prev'], c['c_out'], c['gamma'], c['beta'], c['y'], c['h_out'], c['row_bias'], c['bias'],
+                                 c['h2'], c['h3'], c['drop'], c['y2'], c['stats'], c['post_tanh'], c['ydrop'])
+        self._fill_attn2_fwd(f.at, **attn)
+        if not self.lib.dlsg_cell_norm_attn2_supported(C.byref(f)):
+            return False
         self.launches += 1
-        L.check(self.lib.dlsg_lstm_cell_norm_fwd(C.byref(q), _stream()), 'dlsg_lstm_cell_norm_fwd')
+        L.check(self.lib.dlsg_cell_norm_attn2_fwd(C.byref(f), _stream()), 'dlsg_cell_norm_attn2_fwd')
+        return True
 
     @staticmethod
     def _fill_cell_fwd(p, gates, c_prev, c_out, h_out, row_bias, bias, h2, h3, drop):
@@ -574,6 +596,12 @@ class CudaBackend:
         drop_head_stride=int) fuses the context output layer tanh -> LayerNorm -> dropout into the same kernel."""
         self._ck(KW)
         p = L.Attn2FwdT()
+        self._fill_attn2_fwd(p, KW, VW, q, alpha, co, scale, rows_per_node, ln)
+        self.launches += 1
+        L.check(self.lib.dlsg_attn2_fwd(C.byref(p), _stream()), 'dlsg_attn2_fwd')
+
+    @staticmethod
+    def _fill_attn2_fwd(p, KW, VW, q, alpha, co, scale, rows_per_node=1, ln=None):
         nh, nodes, P, Hk = KW.shape
         assert KW.is_contiguous() and VW.is_contiguous() and q.stride(1) == 1 and co.stride(1) == 1
         p.KW, p.VW, p.q, p.alpha, p.co = KW.data_ptr(), VW.data_ptr(), q.data_ptr(), _ptr(alpha), co.data_ptr()
@@ -589,8 +617,6 @@ class CudaBackend:
             if ln.get('drop') is not None:
                 p.drop_p, p.seed, p.offset = ln['drop']
                 p.offset_head_stride = ln['drop_head_stride']
-        self.launches += 1
-        L.check(self.lib.dlsg_attn2_fwd(C.byref(p), _stream()), 'dlsg_attn2_fwd')
 
     def attn2_bwd(self, KW, VW, q, alpha, dco, dq, dKW, dVW, scale, dalpha_ext=None, ln=None, save=None):
         """ln = dict(dy=(rows,nh*Hv) fp32 view, co=(rows,nh*Hv), gamma=[..nh], stats=(nh,rows,2), dgamma_rows, dbeta_rows

@@ -310,6 +310,13 @@ typedef struct {
   float* dl_save; int64_t ld_dl_save; float* dco_save; int64_t ld_dco_save;
 } dlsg_attn2_bwd_t;
 int dlsg_attn2_supported(int32_t nh, int32_t P, int32_t Hk, int32_t Hv);
+/* The query LSTM's cell + LayerNorm (dlsg_lstm_cell_norm_fwd) and the hoisted attention step + context output layer
+ * (dlsg_attn2_fwd) of one decode step in ONE launch (layer.py:571-591): `at.q` is ignored - the attention reads
+ * q = dropout(LN(query_h)) from the cell part (which still writes y / y2 as before).  One CTA per batch row, 256 threads
+ * per head.  Supported: cell.H == at.Hk <= 1024, at.Hv <= 1024, nh <= 2, P <= 8, nsplit <= 4, cell.B == at.rows.       */
+typedef struct { dlsg_lstm_cell_norm_fwd_t cn; dlsg_attn2_fwd_t at; } dlsg_cell_norm_attn2_fwd_t;
+int dlsg_cell_norm_attn2_supported(const dlsg_cell_norm_attn2_fwd_t* f);
+int dlsg_cell_norm_attn2_fwd(const dlsg_cell_norm_attn2_fwd_t* f, void* stream);
 int dlsg_attn2_fwd(const dlsg_attn2_fwd_t* p, void* stream);
 int dlsg_attn2_bwd(const dlsg_attn2_bwd_t* p, void* stream);
 /* dKW[hd][r][j][:] (+)= sum_t dl[t][r][hd*P+j] q[t][r][:] ; dVW[hd][r][j][:] (+)= sum_t alpha[t][r][hd*P+j] dco[t][r][hd*Hv+:]

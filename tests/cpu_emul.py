@@ -261,6 +261,20 @@ class CpuEmulBackend:
         self.norm_fwd(h, gamma, beta, y=y, y2=y2, stats=stats, post_tanh=post_tanh, drop=ydrop)
         self.launches -= 1
 
+    def cell_norm_attn2_fwd(self, cell, attn):
+        """The two stages back to back (the kernel fuses them into one launch); same shape limits as the kernel."""
+        g = cell['gates']
+        H = g.shape[-1] // 4
+        KW, VW = attn['KW'], attn['VW']
+        if not (H % 4 == 0 and H <= 1024 and H == KW.shape[3] and VW.shape[3] <= 1024 and KW.shape[0] <= 2 and KW.shape[2] <= 8
+                and (g.shape[0] if g.dim() == 3 else 1) <= 4):
+            return False
+        c = dict(cell)
+        self.lstm_cell_norm_fwd(c.pop('gates'), c.pop('c_prev'), c.pop('c_out'), c.pop('gamma'), c.pop('beta'), c.pop('y'), **c)
+        self.attn2_fwd(**attn)
+        self.launches -= 1
+        return True
+
     def norm_lstm_cell_bwd(self, acts, c_prev, c_new, dc_next, dc_prev, dy, x, gamma, beta, stats, dgamma, dbeta, dh=None, dh2=None,
                            dgates=None, dgates2=None, dgatesT=None, dgates_sum=None, drop=None, post_tanh=False, ydrop=None):
         B, H = c_new.shape

@@ -609,6 +609,57 @@ def test_attn2_fused_output_layer(be, nh, P, Hk, Hv, ydt):
             cmp('dgamma', r['dg'][k], f['dgr'][:, sl].sum(0), 1e-4); cmp('dbeta', r['db'][k], f['dbr'][:, sl].sum(0), 1e-4)
 
 
+@pytest.mark.parametrize('nh,P,H,Hv,S,rpn', [(2, 5, 1024, 1024, 3, 1), (2, 5, 1024, 1024, 1, 5), (1, 8, 256, 128, 2, 1), (2, 3, 64, 1024, 4, 1)])
+def test_cell_norm_attn2_one_launch_equals_two_launches(be, nh, P, H, Hv, S, rpn):
+    """dlsg_cell_norm_attn2_fwd (query-LSTM cell + LayerNorm + hoisted attention + context output layer of a decode step in
+    one launch) against dlsg_lstm_cell_norm_fwd followed by dlsg_attn2_fwd on the same inputs: same arithmetic and same
+    Philox sites, with and without the three dropouts; rows sharing node tensors (beam search: rows_per_node)."""
+    rows = 10
+    nodes = rows // rpn
+    D = lambda x: x.to(DEV)
+    gates0, c_prev, rb = R(S, rows, 4 * H), R(rows, H), R(rows, 2, 4 * H)[:, 1]
+    gam, bet = 1 + 0.1 * R(H), 0.1 * R(H)
+    KW, VW = R(nh, nodes, P, H, scale=0.3), R(nh, nodes, P, Hv)
+    og, ob = [1 + 0.1 * R(Hv) for _ in range(nh)], [0.1 * R(Hv) for _ in range(nh)]
+    for drops in ((None, None, None), ((0.5, 11, 1 << 20), (0.3, 12, 2 << 20), (0.3, 13, 4 << 32))):
+        outs = []
+        for one in (False, True):
+            g = D(gates0.clone())
+            o = dict(c_out=D(torch.zeros(rows, H)), q32=D(torch.zeros(rows, H)), h_out=D(torch.zeros(rows, H)),
+                     h2=D(torch.zeros(rows, H + 40, dtype=torch.bfloat16))[:, 8:8 + H], y2=D(torch.zeros(rows, 2 * H, dtype=torch.bfloat16))[:, H:],
+                     stq=D(torch.zeros(rows, 2)), alpha=D(torch.zeros(rows, nh * P)), co=D(torch.zeros(rows, nh * Hv)),
+                     y=D(torch.zeros(rows, nh * Hv + 8, dtype=torch.bfloat16))[:, :nh * Hv], stc=D(torch.zeros(nh, rows, 2)))
+            cell = dict(gates=g, c_prev=D(c_prev), c_out=o['c_out'], gamma=D(gam), beta=D(bet), y=o['q32'], h_out=o['h_out'], row_bias=D(rb),
+                        h2=o['h2'], y2=o['y2'], stats=o['stq'], drop=drops[0], ydrop=drops[1])
+            attn = dict(KW=D(KW), VW=D(VW), q=o['q32'], alpha=o['alpha'], co=o['co'], scale=0.09, rows_per_node=rpn,
+                        ln=dict(gamma=[D(x) for x in og], beta=[D(x) for x in ob], y=o['y'], stats=o['stc'], drop=drops[2],
+                                drop_head_stride=1 << 28))
+            if one:
+                assert be.cell_norm_attn2_fwd(cell, attn)
+            else:
+                c2 = dict(cell)
+                be.lstm_cell_norm_fwd(c2.pop('gates'), c2.pop('c_prev'), c2.pop('c_out'), c2.pop('gamma'), c2.pop('beta'), c2.pop('y'), **c2)
+                be.attn2_fwd(**attn)
+            torch.cuda.synchronize()
+            o['acts'] = g[0]
+            outs.append(o)
+        for k in outs[0]:
+            a_, b_ = outs[0][k].float().cpu(), outs[1][k].float().cpu()
+            tol = 1e-2 if outs[0][k].dtype == torch.bfloat16 else 2e-6
+            assert float((a_ - b_).abs().max()) <= tol * max(1.0, float(a_.abs().max())), (k, drops[0] is not None)
+        if drops[0] is None:
+            plain = outs[1]
+    if S == 1:                                                   # the emulator path of the same entry
+        g = gates0[0].clone()
+        o = dict(c_out=torch.zeros(rows, H), q32=torch.zeros(rows, H), alpha=torch.zeros(rows, nh * P), co=torch.zeros(rows, nh * Hv),
+                 y=torch.zeros(rows, nh * Hv), stc=torch.zeros(nh, rows, 2))
+        assert EM.cell_norm_attn2_fwd(dict(gates=g, c_prev=c_prev, c_out=o['c_out'], gamma=gam, beta=bet, y=o['q32'], row_bias=rb),
+                                      dict(KW=KW, VW=VW, q=o['q32'], alpha=o['alpha'], co=o['co'], scale=0.09, rows_per_node=rpn,
+                                           ln=dict(gamma=og, beta=ob, y=o['y'], stats=o['stc'], drop=None, drop_head_stride=1 << 28)))
+        _close('alpha vs emulator', o['alpha'], plain['alpha'], 2e-5)
+        _close('y vs emulator', o['y'], plain['y'].float(), 2e-2)
+
+
 def _close(name, a, b, tol):
     a, b = a.float().cpu(), b.float().cpu()
     err, scale = float((a - b).abs().max()), max(1.0, float(a.abs().max()))
