@@ -24,6 +24,9 @@ START = 1
 
 # the decode step's cell + LayerNorm + attention as one launch when the shape allows (measurement switch)
 FUSED_CELL_ATTN = os.environ.get('DLSG_FUSED_CELL_ATTN', '1') != '0'
+# ... up to this many rows: one CTA per row runs the two stages one after the other, which wins at the training batch (64 rows:
+# 6.230 -> 6.195 ms per step) and loses once the rows alone fill the GPU (beam-5 at 640 rows: 19.9 k -> 19.0 k captions/s)
+FUSED_CELL_ATTN_MAX_ROWS = int(os.environ.get('DLSG_FUSED_CELL_ATTN_MAX_ROWS', '128'))
 splitk_for = la.splitk_rows          # (= la.splitk_for up to 64 rows; explicit partials for the 65..~300-row decode batches too)
 
 
@@ -161,7 +164,7 @@ class DecoderCore:
                                 beta=[t[pf + h + '.output_layer.2.bias'] for h in self.heads],
                                 y=b.Xl[i][:, :nh * H], stats=b.statc[i], drop=dc, drop_head_stride=1 << 28))
         one_launch = False
-        if self.fused and self.hoist and FUSED_CELL_ATTN:
+        if self.fused and self.hoist and FUSED_CELL_ATTN and R <= FUSED_CELL_ATTN_MAX_ROWS:
             # cell + LayerNorm + attention + output layer of the step in ONE launch (csrc/fused_step.cu)
             one_launch = be.cell_norm_attn2_fwd(dict(gates=b.gq[:, i], c_prev=b.cq[i], c_out=b.cq[j], gamma=lnq_w, beta=lnq_b, y=qy,
                                                      h_out=b.qh[i], row_bias=rb, h2=b.Xq[j][:, oQ:oQ + Hq], y2=qy2, stats=b.statq[i],
