@@ -164,3 +164,101 @@ def test_gan_iteration_stacked_critic_calls_match_separate_calls():
         d = (a_ - b_).abs()
         assert d.max() < 3.2e-4, name
         assert (d > 1e-6).float().mean() < 2e-2, name
+
+
+# ----------------------------------------------------------------------------------------------- second-order building blocks
+def _grads(fn, inputs, seed, wrt=None):
+    """Gradients of a random scalar functional of the create_graph gradient of fn(*inputs) wrt every input (wrt: indices of the
+    first gradients that enter the functional; default all)."""
+    xs = [x.detach().clone().requires_grad_(True) for x in inputs]
+    y = fn(*xs)
+    g = torch.Generator().manual_seed(seed)
+    w1 = torch.randn(y.shape, generator=g)
+    first = torch.autograd.grad((y * w1).sum(), xs, create_graph=True, allow_unused=True)
+    tot = 0
+    for k, f in enumerate(first):
+        if f is not None and (wrt is None or k in wrt):
+            tot = tot + (f * torch.randn(f.shape, generator=g)).sum()
+    second = torch.autograd.grad(tot, xs, allow_unused=True)
+    return [f.detach() if f is not None else None for f in first], second
+
+
+def _same(a, b, tol=2e-5):
+    for x, y in zip(a, b):
+        if x is None or y is None:
+            assert (x is None or float(x.abs().max()) == 0) and (y is None or float(y.abs().max()) == 0)
+            continue
+        assert float((x - y).abs().max()) <= tol * max(1.0, float(y.abs().max())), float((x - y).abs().max())
+
+
+def test_elementwise_and_softmax_second_order_match_torch_autograd():
+    """The closed-form first / second backward of the fused element-wise forms and of the axis softmax (dlsg.generic: _Tanh /
+    _TanhBwd, _Mul / _MulBwd, _LerpRows, _Softmax / _SoftmaxBwd) against torch's own double backward of the same functions."""
+    from dlsg import generic as GN
+    rs = torch.Generator().manual_seed(3)
+    a, b = torch.randn(4, 6, 8, generator=rs), torch.randn(4, 6, 8, generator=rs)
+    e = torch.rand(4, 1, 1, generator=rs)
+    f1, s1 = _grads(lambda x: GN.tanh_(x), [a], 1)
+    f2, s2 = _grads(lambda x: torch.tanh(x), [a], 1)
+    _same(f1, f2); _same(s1, s2)
+    f1, s1 = _grads(lambda x, y: GN.mul(GN.tanh_(x), y), [a, b], 2)
+    f2, s2 = _grads(lambda x, y: torch.tanh(x) * y, [a, b], 2)
+    _same(f1, f2); _same(s1, s2)
+    f1, s1 = _grads(lambda x, y: GN.tanh_(GN.lerp_rows(x, y, e)), [a, b], 3)
+    f2, s2 = _grads(lambda x, y: torch.tanh(x * e + y * (1 - e)), [a, b], 3)
+    _same(f1, f2); _same(s1, s2)
+    mask = (torch.randn(4, 6, 8, generator=rs) > -0.7).float()
+    mask[1] = 0
+    for dim in (1, 2):
+        for mode in (0, 1, 2):
+            def ours(x):
+                return GN.tanh_(GN.softmax(x, dim, scale=0.41, mask=mask if mode else None, mask_mode=mode))
+
+            def ref(x):
+                v = x * 0.41
+                if mode == 1:
+                    v = torch.where(mask > 0, v, torch.full_like(v, -9e15))
+                s = torch.softmax(v, dim)
+                if mode == 2:
+                    s = torch.where(mask > 0, s, torch.zeros_like(s))
+                return torch.tanh(s)
+            f1, s1 = _grads(ours, [a], 10 + dim * 3 + mode)
+            f2, s2 = _grads(ref, [a], 10 + dim * 3 + mode)
+            _same(f1, f2); _same(s1, s2)
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+def test_lstm_fused_second_order_equals_stepwise_restatement(prec):
+    """generic._LstmBptt2 (the LSTM's differentiable BPTT as one node on fused loops, closed-form cell backward-of-backward)
+    against the step-by-step autograd restatement `_lstm_bptt_diff` and, in fp32, against torch.nn.LSTM's own double backward:
+    first-order gradients and the gradients of a functional of them, for the input projection, both weights and the biases."""
+    from dlsg import generic as GN
+    la.set_precision(prec)
+    B, T, H = 5, 7, 128
+    rs = torch.Generator().manual_seed(11)
+    x = torch.randn(B, T, H, generator=rs)
+    w_ih, w_hh = 0.1 * torch.randn(4 * H, H, generator=rs), 0.1 * torch.randn(4 * H, H, generator=rs)
+    b_ih, b_hh = 0.1 * torch.randn(4 * H, generator=rs), 0.1 * torch.randn(4 * H, generator=rs)
+    res = {}
+    for fused in (True, False):
+        GN.FUSED_LSTM_BPTT2 = fused
+        la.new_param_epoch()
+        # (the functional reads the INPUT gradient only - the WGAN-GP case; second derivatives through the recurrent weight
+        # gradient are outside the fused node's contract)
+        res[fused] = _grads(lambda x_, a_, b_, c_, d_: GN.lstm(x_, a_, b_, c_, d_), [x, w_ih, w_hh, b_ih, b_hh], 5, wrt=(0,))
+    GN.FUSED_LSTM_BPTT2 = True
+    tol = 2e-5 if prec == 'fp32' else 2e-2
+    _same(res[True][0], res[False][0], tol); _same(res[True][1], res[False][1], tol)
+    if prec == 'fp32':
+        def ref(x_, a_, b_, c_, d_):
+            h, c = torch.zeros(B, H), torch.zeros(B, H)
+            out = []
+            for t in range(T):
+                g = x_[:, t] @ a_.t() + c_ + d_ + h @ b_.t()
+                i, f, gg, o = torch.sigmoid(g[:, :H]), torch.sigmoid(g[:, H:2 * H]), torch.tanh(g[:, 2 * H:3 * H]), torch.sigmoid(g[:, 3 * H:])
+                c = f * c + i * gg
+                h = o * torch.tanh(c)
+                out.append(h)
+            return torch.stack(out, 1)
+        f2, s2 = _grads(ref, [x, w_ih, w_hh, b_ih, b_hh], 5, wrt=(0,))
+        _same(res[True][0], f2, 1e-4); _same(res[True][1], s2, 1e-4)
