@@ -615,6 +615,8 @@ def _lstm_bptt_diff(gin, w_hh, dhs, need_dgin, need_dw):
 FUSED_LSTM_BPTT2 = True
 # Forward loop of the generic LSTM on the one-launch step kernel (recurrent product + cell) when the shape allows it.
 FUSED_LSTM_STEP = True
+# The second-order reverse loop over the forward (loop B of `_LstmBptt2`) rides on the first-order backward loop of `_LstmSeq`.
+MERGE_LSTM_REVERSE_LOOPS = True
 
 
 class _LstmBptt2(torch.autograd.Function):
@@ -631,9 +633,10 @@ class _LstmBptt2(torch.autograd.Function):
     dw_hh (second derivative through the recurrent weight gradient) is not supported: `_lstm_bptt_diff` covers it."""
 
     @staticmethod
-    def forward(ctx, gin, w_hh, dhs, bufs, need_dw):
+    def forward(ctx, gin, w_hh, dhs, hs, bufs, need_dw, link):
         be = ops.backend()
         acts, cs, hin, w_op = bufs
+        ctx.link = link
         T, B, H4 = acts.shape
         H = H4 // 4
         dhs = _c(dhs)
@@ -662,7 +665,7 @@ class _LstmBptt2(torch.autograd.Function):
         if u_w is not None:
             raise NotImplementedError('second derivative through the recurrent weight gradient: use _lstm_bptt_diff')
         if U is None:
-            return None, None, None, None, None
+            return None, None, None, None, None, None, None
         be = ops.backend()
         gin, w_hh = ctx.saved_tensors
         acts, cs, hin, w_op = ctx.bufs
@@ -685,6 +688,20 @@ class _LstmBptt2(torch.autograd.Function):
             be.lstm_cell_bwd2(acts[t], cs[t], cs[t + 1], dht[t], dcs[t + 1] if t + 1 < T else None, U[:, t],
                               gdc[t - 1] if t > 0 else None, gdh[:, t], gdc[t], gpre[t], gc0[t], u2=(up if t > 0 else None),
                               g_dh2=(gdh_in[t + 1] if t + 1 < T else None))
+        if ctx.link is not None and MERGE_LSTM_REVERSE_LOOPS:
+            # Loop B is an ordinary BPTT over the same forward as the first-order backward of `_LstmSeq`, which is linear in its
+            # inputs and which autograd runs AFTER this node (`hs`, that node's output, is a formal input here: the edge puts
+            # it into every backward pass that reaches this node, behind it): hand it loop A's injections and let ONE loop
+            # produce the sum of both gradients.
+            link = ctx.link
+            link['inject'] = (gpre, gc0, dg_op, gdh_in)
+
+            def check():
+                if link.pop('inject', None) is not None:
+                    raise RuntimeError('dlsg.generic._LstmBptt2: the LSTM forward node did not run its backward in this pass, so the '
+                                       'second-order gradient of its inputs was lost; set dlsg.generic.MERGE_LSTM_REVERSE_LOOPS = False')
+            torch.autograd.Variable._execution_engine.queue_callback(check)
+            return None, None, gdh, None, None, None, None
         a32 = empty((B, T, H4), gin)
         a_op = la.op_empty((T, B), H4, gin) if bf else empty((T, B, H4), gin)
         Sd = la.splitk_rows(B, H, H4)
@@ -703,7 +720,7 @@ class _LstmBptt2(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             g_w = la.mm(la.flat2(a_op).t(), la.flat2(hin).t())                 # sum_t a_pre_t^T h(t-1)
             la.mm(la.flat2(dg_op).t(), la.flat2(gdh_in).t(), out=g_w, accum=True)   # + sum_t dpre_t^T g_dh(t-1)
-        return a32, g_w, gdh, None, None
+        return a32, g_w, gdh, None, None, None, None
 
 
 class _LstmSeq(torch.autograd.Function):
@@ -734,7 +751,7 @@ class _LstmSeq(torch.autograd.Function):
                 be.lstm_step_fwd([w_op] * ng, [hin[t][s_] for s_ in sl] if t > 0 else None, [gin[s_, t] for s_ in sl],
                                  [cs[t][s_] for s_ in sl] if t > 0 else None, [cs[t + 1][s_] for s_ in sl], [acts[t][s_] for s_ in sl],
                                  h_out=[hs[s_, t] for s_ in sl], h_op=([hin[t + 1][s_] for s_ in sl] if t + 1 < T else None))
-            ctx.save_for_backward(gin, w_hh)
+            ctx.save_for_backward(gin, w_hh, hs)
             ctx.bufs = (acts, cs, hin, w_op)
             return hs
         S = la.splitk_for(B, H4, H)
@@ -748,17 +765,19 @@ class _LstmSeq(torch.autograd.Function):
                 be.gemm(hin[t], w_op, gates[:, t] if S > 1 else gates[0, t], splitk=S)
             be.lstm_cell_fwd(gates[:, t], cs[t], cs[t + 1], row_bias=gin[:, t], h2=hs[:, t],
                              h3=(hin[t + 1] if t + 1 < T else None))
-        ctx.save_for_backward(gin, w_hh)
+        ctx.save_for_backward(gin, w_hh, hs)
         ctx.bufs = (gates[0], cs, hin, w_op)
         return hs
 
     @staticmethod
     def backward(ctx, dhs):
-        gin, w_hh = ctx.saved_tensors
+        gin, w_hh, hs = ctx.saved_tensors
         need_dgin, need_dw = ctx.needs_input_grad
         if torch.is_grad_enabled():
             if FUSED_LSTM_BPTT2:
-                dgin, dw = _LstmBptt2.apply(gin, w_hh, dhs, ctx.bufs, need_dw and not _INPUT_GRADS_ONLY)
+                if not hasattr(ctx, 'link'):
+                    ctx.link = {}
+                dgin, dw = _LstmBptt2.apply(gin, w_hh, dhs, hs, ctx.bufs, need_dw and not _INPUT_GRADS_ONLY, ctx.link)
                 return (dgin if need_dgin else None), (dw if need_dw else None)
             return _lstm_bptt_diff(gin, w_hh, dhs, need_dgin, need_dw)
         be = ops.backend()
@@ -773,15 +792,20 @@ class _LstmSeq(torch.autograd.Function):
         dhrec = zeros((Sd, B, H), gin)
         dc, dc2 = empty((B, H), gin), empty((B, H), gin)
         w_t = w_op.transpose(-1, -2)
+        inj = ctx.link.pop('inject', None) if hasattr(ctx, 'link') else None     # second-order injections (see _LstmBptt2.backward)
+        gpre, gc0 = (inj[0], inj[1]) if inj is not None else (None, None)
         for t in range(T - 1, -1, -1):
             be.lstm_cell_bwd(acts[t], cs[t], cs[t + 1], dhs[:, t], dc if t + 1 < T else None, dc2, dgates=(dg32[:, t] if need_dgin else None),
-                             dgates2=dg_op[t], dh2=dhrec)
+                             dgates2=dg_op[t], dh2=dhrec, dc_next2=(gc0[t + 1] if (inj is not None and t + 1 < T) else None),
+                             dgates_add=(gpre[t] if inj is not None else None))
             dc, dc2 = dc2, dc
             if t > 0:
                 be.gemm(dg_op[t], w_t, dhrec if Sd > 1 else dhrec[0], splitk=Sd)
         dw = None
         if need_dw:
             dw = la.mm(la.flat2(dg_op).t(), la.flat2(hin).t())      # sum_t dgates_t^T h_{t-1}  (hin[0] = 0)
+            if inj is not None:
+                la.mm(la.flat2(inj[2]).t(), la.flat2(inj[3]).t(), out=dw, accum=True)      # + sum_t dpre_t^T g_dh(t-1)
         return (dg32 if need_dgin else None), dw
 
 
