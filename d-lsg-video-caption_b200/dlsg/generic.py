@@ -64,6 +64,12 @@ class _MmNT(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b):
         ctx.save_for_backward(a, b)
+        if (SMALL_BMM_SIMT and a.dim() == 3 and a.dtype == torch.float32 and b.dtype == torch.float32
+                and (min(a.shape[-2], b.shape[-2]) <= 32 or a.shape[-1] <= 32)):
+            # per-sample products of the critic's attention / node scoring (26 x 26 x 512, 26 x 5 x 512, 5 x 512 x 26 ...): the
+            # fp32 FFMA kernel on the tensors as they are - a 128-row tensor-core tile would be mostly empty, and both operands
+            # would first be cast to bf16 (two more launches)
+            return la.mm32(a, b)
         return la.mm(a, b, memo=True)
 
     @staticmethod
@@ -615,6 +621,9 @@ def _lstm_bptt_diff(gin, w_hh, dhs, need_dgin, need_dw):
 FUSED_LSTM_BPTT2 = True
 # Forward loop of the generic LSTM on the one-launch step kernel (recurrent product + cell) when the shape allows it.
 FUSED_LSTM_STEP = True
+# Small per-sample (batched) products on the fp32 FFMA kernel (measurement switch: DLSG_SMALL_BMM_SIMT=0)
+import os as _os
+SMALL_BMM_SIMT = _os.environ.get('DLSG_SMALL_BMM_SIMT', '1') != '0'
 # The second-order reverse loop over the forward (loop B of `_LstmBptt2`) rides on the first-order backward loop of `_LstmSeq`.
 MERGE_LSTM_REVERSE_LOOPS = True
 
