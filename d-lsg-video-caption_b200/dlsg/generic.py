@@ -65,10 +65,12 @@ class _MmNT(torch.autograd.Function):
     def forward(ctx, a, b):
         ctx.save_for_backward(a, b)
         if (SMALL_BMM_SIMT and a.dim() == 3 and a.dtype == torch.float32 and b.dtype == torch.float32
-                and (min(a.shape[-2], b.shape[-2]) <= 32 or a.shape[-1] <= 32)):
-            # per-sample products of the critic's attention / node scoring (26 x 26 x 512, 26 x 5 x 512, 5 x 512 x 26 ...): the
-            # fp32 FFMA kernel on the tensors as they are - a 128-row tensor-core tile would be mostly empty, and both operands
-            # would first be cast to bf16 (two more launches)
+                and (a.shape[-1] <= 32 or (SMALL_BMM_SIMT > 1 and min(a.shape[-2], b.shape[-2]) <= 32))):
+            # per-sample products of the critic's attention / node scoring with a SHORT reduction (weights x values: K = 26
+            # words or 5 nodes): the fp32 FFMA kernel on the tensors as they are - the tensor-core path would pad K to 64
+            # and cast both operands to bf16 first (two more launches).  The long-K ones (26 x 26 x 512 scores) stay on the
+            # tensor-core kernel: measured 45.6 vs 39.2 ms per GAN iteration with all of them on the FFMA kernel
+            # (profiles/r04i_gan_iteration_small_bmm_simt_all.json).
             return la.mm32(a, b)
         return la.mm(a, b, memo=True)
 
@@ -76,11 +78,24 @@ class _MmNT(torch.autograd.Function):
     def backward(ctx, dy):
         a, b = ctx.saved_tensors
         da = db = None
+        # An operand that is a transposed VIEW (a weight read as W^T by a data-gradient product) gets its gradient computed in
+        # the layout of the tensor underneath and handed back as a transposed view of that: once autograd has undone the
+        # transpose the gradient is contiguous - no strided accumulate / copy kernels behind every such product.
         if _want(ctx, 0, a):
-            da = bmm_nt(dy, b.transpose(-1, -2))          # dy @ b
+            if _tview(a):
+                da = bmm_nt(b.transpose(-1, -2), dy).transpose(-1, -2)            # (dy @ b)^T = b^T @ dy^T
+            else:
+                da = bmm_nt(dy, b.transpose(-1, -2))                              # dy @ b
         if _want(ctx, 1, b):
-            db = bmm_nt(dy.transpose(-1, -2), a.transpose(-1, -2))   # dy^T @ a
+            if _tview(b):
+                db = bmm_nt(a.transpose(-1, -2), dy.transpose(-1, -2)).transpose(-1, -2)   # (dy^T @ a)^T = a^T @ dy
+            else:
+                db = bmm_nt(dy.transpose(-1, -2), a.transpose(-1, -2))            # dy^T @ a
         return da, db
+
+
+def _tview(x):
+    return x.dim() >= 2 and x.shape[-1] > 1 and x.shape[-2] > 1 and x.stride(-1) != 1 and x.stride(-2) == 1
 
 
 def bmm_nt(a, b):
@@ -623,7 +638,7 @@ FUSED_LSTM_BPTT2 = True
 FUSED_LSTM_STEP = True
 # Small per-sample (batched) products on the fp32 FFMA kernel (measurement switch: DLSG_SMALL_BMM_SIMT=0)
 import os as _os
-SMALL_BMM_SIMT = _os.environ.get('DLSG_SMALL_BMM_SIMT', '1') != '0'
+SMALL_BMM_SIMT = int(_os.environ.get('DLSG_SMALL_BMM_SIMT', '1'))      # 0 off, 1 short reductions only, 2 every small product
 # The second-order reverse loop over the forward (loop B of `_LstmBptt2`) rides on the first-order backward loop of `_LstmSeq`.
 MERGE_LSTM_REVERSE_LOOPS = True
 

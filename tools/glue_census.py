@@ -42,12 +42,14 @@ class Census(TorchDispatchMode):
     def __torch_dispatch__(self, func, types, args=(), kwargs=None):
         name = str(func)
         if not self.inside and name not in SKIP:
-            site = '?'
+            site = []
             for fr in reversed(traceback.extract_stack(limit=40)):
                 fn = fr.filename
                 if ('/dlsg/' in fn or '/models/' in fn) and 'glue_census' not in fn:
-                    site = '%s:%d' % (os.path.relpath(fn, ROOT).replace('d-lsg-video-caption_b200/', ''), fr.lineno)
-                    break
+                    site.append('%s:%d' % (os.path.basename(fn), fr.lineno))
+                    if len(site) == DEPTH:
+                        break
+            site = ' < '.join(site) or '?'
             ts = [x for x in list(args) + list((kwargs or {}).values()) if torch.is_tensor(x)]
             if any(not x.is_contiguous() for x in ts) or len({tuple(x.shape) for x in ts if x.dim() > 0}) > 1:
                 name += '  [strided/broadcast %s]' % ','.join('x'.join(map(str, x.shape)) for x in ts[:2])
