@@ -66,11 +66,10 @@ class _MmNT(torch.autograd.Function):
         ctx.save_for_backward(a, b)
         if (SMALL_BMM_SIMT and a.dim() == 3 and a.dtype == torch.float32 and b.dtype == torch.float32
                 and (a.shape[-1] <= 32 or (SMALL_BMM_SIMT > 1 and min(a.shape[-2], b.shape[-2]) <= 32))):
-            # per-sample products of the critic's attention / node scoring with a SHORT reduction (weights x values: K = 26
-            # words or 5 nodes): the fp32 FFMA kernel on the tensors as they are - the tensor-core path would pad K to 64
-            # and cast both operands to bf16 first (two more launches).  The long-K ones (26 x 26 x 512 scores) stay on the
-            # tensor-core kernel: measured 45.6 vs 39.2 ms per GAN iteration with all of them on the FFMA kernel
-            # (profiles/r04i_gan_iteration_small_bmm_simt_all.json).
+            # measurement switch, OFF by default: the per-sample products of the critic's attention / node scoring on the fp32
+            # FFMA kernel (no operand casts) are SLOWER than the mostly empty tensor-core tiles + two casts - 45.6 ms per GAN
+            # iteration with all of them there, 40.5 ms with only the short reductions (K = 26 / 5), 37.7 ms on the tensor-core
+            # kernel (profiles/r04i_*, r04j_*): the FFMA kernel's 64 x 64 tiles are ~28 us per batched launch at these shapes.
             return la.mm32(a, b)
         return la.mm(a, b, memo=True)
 
@@ -636,9 +635,9 @@ def _lstm_bptt_diff(gin, w_hh, dhs, need_dgin, need_dw):
 FUSED_LSTM_BPTT2 = True
 # Forward loop of the generic LSTM on the one-launch step kernel (recurrent product + cell) when the shape allows it.
 FUSED_LSTM_STEP = True
-# Small per-sample (batched) products on the fp32 FFMA kernel (measurement switch: DLSG_SMALL_BMM_SIMT=0)
+# Small per-sample (batched) products on the fp32 FFMA kernel (measurement switch DLSG_SMALL_BMM_SIMT; measured slower)
 import os as _os
-SMALL_BMM_SIMT = int(_os.environ.get('DLSG_SMALL_BMM_SIMT', '1'))      # 0 off, 1 short reductions only, 2 every small product
+SMALL_BMM_SIMT = int(_os.environ.get('DLSG_SMALL_BMM_SIMT', '0'))      # 0 off (kept), 1 short reductions only, 2 every small product
 # The second-order reverse loop over the forward (loop B of `_LstmBptt2`) rides on the first-order backward loop of `_LstmSeq`.
 MERGE_LSTM_REVERSE_LOOPS = True
 
