@@ -8,6 +8,7 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 if [ "$2" != "nobench" ]; then
 python -m pytest tests -m gpu -q > $OUT/${TAG}_pytest_gpu.log 2>&1; tail -3 $OUT/${TAG}_pytest_gpu.log
+python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err; cut -c1-200 $OUT/${TAG}_bench_ref.json
 python bench.py --gpus 1 --steps 20 --warmup 5 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; cut -c1-300 $OUT/${TAG}_bench.json
 fi
 # ncu launch list of ONE eager training step (cold-cache, serialised: shares of the step, not absolute times)
@@ -16,7 +17,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start o
 python tools/agg_launches.py $OUT/${TAG}_launches_eager_step.csv 60 > $OUT/${TAG}_launches_eager_step_summary.txt
 # full metric set: one launch of every kernel class of the real step (first occurrence of each name inside one eager step)
 ncu --set full --clock-control none --profile-from-start off \
-    -k regex:"gemm_tc_kernel|region_aggregate|norm_fwd_vec|norm_bwd_vec|cast_f32_bf16|lstm_cell|attn2|adam_multi|ce_masked|latent_psl" \
+    -k regex:"gemm_tc_kernel|region_aggregate|norm_fwd_vec|norm_bwd_vec|cast_f32_bf16|lstm_cell|lstm_step|attn2|adam_multi|ce_masked|latent_psl" \
     --kernel-id :::1 -o $OUT/${TAG}_step_kernels python bench.py --profile-step --warmup 3 > $OUT/ncu_full.log 2>&1
 ncu -i $OUT/${TAG}_step_kernels.ncu-rep --page raw --csv > $OUT/raw.csv 2>/dev/null && \
     python tools/ncu_summary.py $OUT/raw.csv > $OUT/${TAG}_ncu_full_step_kernels.json 2> $OUT/ncu_summary.err
