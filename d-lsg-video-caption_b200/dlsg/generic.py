@@ -3,6 +3,7 @@ stand-alone sub-layer forwards).  Each primitive is a torch.autograd.Function wh
 written with these primitives, so gradients of gradients (WGAN-GP, run_gun.py:362-371) work.
 """
 import math
+import os
 
 import torch
 
@@ -636,8 +637,7 @@ FUSED_LSTM_BPTT2 = True
 # Forward loop of the generic LSTM on the one-launch step kernel (recurrent product + cell) when the shape allows it.
 FUSED_LSTM_STEP = True
 # Small per-sample (batched) products on the fp32 FFMA kernel (measurement switch DLSG_SMALL_BMM_SIMT; measured slower)
-import os as _os
-SMALL_BMM_SIMT = int(_os.environ.get('DLSG_SMALL_BMM_SIMT', '0'))      # 0 off (kept), 1 short reductions only, 2 every small product
+SMALL_BMM_SIMT = int(os.environ.get('DLSG_SMALL_BMM_SIMT', '0'))      # 0 off (kept), 1 short reductions only, 2 every small product
 # The second-order reverse loop over the forward (loop B of `_LstmBptt2`) rides on the first-order backward loop of `_LstmSeq`.
 MERGE_LSTM_REVERSE_LOOPS = True
 
@@ -651,7 +651,8 @@ class _LstmBptt2(torch.autograd.Function):
       A (t ascending, the reverse of the BPTT recurrence): u_t = U_t + g_dh(t-1) W^T, then the closed-form
         dlsg_lstm_cell_bwd2 -> cotangents of dh_t (= of dhs_t), of dc, and the injections g_pre_t / g_c0_t into the
         forward's pre-activations / cell states;
-      B (t descending, an ordinary BPTT over the same forward with those injections): -> cotangent of gin;
+      B (t descending, an ordinary BPTT over the same forward with those injections): -> cotangent of gin - by default NOT
+        run here: it rides on the first-order backward loop of the forward node (MERGE_LSTM_REVERSE_LOOPS);
     and two time-batched weight-gradient GEMMs.  2 launches per step and loop, no torch arithmetic.  A cotangent of
     dw_hh (second derivative through the recurrent weight gradient) is not supported: `_lstm_bptt_diff` covers it."""
 
@@ -748,9 +749,11 @@ class _LstmBptt2(torch.autograd.Function):
 
 class _LstmSeq(torch.autograd.Function):
     """Zero-state uni-directional LSTM over all steps: gin (B,T,4H) = x W_ih^T + b_ih + b_hh -> h (B,T,H).
-    Forward and first-order backward are fused loops (recurrent GEMM with split-K partials summed by the cell kernel:
-    2 launches per step; one time-batched weight-gradient GEMM).  Under create_graph the backward is the
-    differentiable `_lstm_bptt_diff`."""
+    Forward: the one-launch step kernel (recurrent product + cell; up to four 64-row groups sharing the weight) or, outside
+    its range, recurrent GEMM + cell kernel per step.  First-order backward: cell backward + data-gradient GEMM per step
+    (split-K partials summed by the cell kernel), one time-batched weight-gradient GEMM; it also carries the injections of
+    a pending second-order pass (`_LstmBptt2.backward`).  Under create_graph the backward is the twice-differentiable node
+    `_LstmBptt2` (or the step-by-step restatement `_lstm_bptt_diff` when FUSED_LSTM_BPTT2 is off)."""
 
     @staticmethod
     def forward(ctx, gin, w_hh):
