@@ -579,7 +579,8 @@ lstm_cell_bwd_fast(const dlsg_lstm_cell_bwd_t p) {
   const float4 r1 = ldf4(p.dh + (int64_t)b * p.lddh + h);
   float4 r2[S2], cp = z4, dcn = z4;
 #pragma unroll
-  for (int s_ = 0; s_ < S2; ++s_) r2[s_] = p.dh2 ? ldf4(p.dh2 + (int64_t)b * p.lddh2 + h + (int64_t)s_ * p.dh2_stride_split) : z4;
+  for (int s_ = 0; s_ < S2; ++s_)      // (S2 > 4: the wide instantiation, partial count at run time - predicated, all loads still issued together)
+    r2[s_] = (p.dh2 && (S2 <= 4 || s_ < p.dh2_nsplit)) ? ldf4(p.dh2 + (int64_t)b * p.lddh2 + h + (int64_t)s_ * p.dh2_stride_split) : z4;
   if (p.c_prev) cp = ldf4(p.c_prev + ei);
   if (p.dc_next) dcn = ldf4(p.dc_next + ei);
   float4 ga[4] = {z4, z4, z4, z4};
@@ -1361,7 +1362,7 @@ int dlsg_lstm_cell_bwd(const dlsg_lstm_cell_bwd_t* p, void* stream) {
   DLSG_REQUIRE(p->B > 0 && p->H > 0, "lstm_cell_bwd: bad shape");
   auto a16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const int ns = p->dh2 ? (p->dh2_nsplit > 1 ? p->dh2_nsplit : 1) : 1;
-  if (p->H % 4 == 0 && ns <= 4 && a16(p->acts) && a16(p->c_new) && p->dh && a16(p->dh) && p->lddh % 4 == 0 &&
+  if (p->H % 4 == 0 && ns <= 16 && a16(p->acts) && a16(p->c_new) && p->dh && a16(p->dh) && p->lddh % 4 == 0 &&
       (!p->dh2 || (a16(p->dh2) && p->lddh2 % 4 == 0 && p->dh2_stride_split % 4 == 0)) && (!p->c_prev || a16(p->c_prev)) &&
       (!p->dc_next || a16(p->dc_next)) && (!p->dc_prev || a16(p->dc_prev)) && (!p->dgates || a16(p->dgates)) &&
       (!p->dc_next2 || a16(p->dc_next2)) && (!p->dgates_add || a16(p->dgates_add)) && (!p->dh_total || a16(p->dh_total)) &&
@@ -1373,7 +1374,8 @@ int dlsg_lstm_cell_bwd(const dlsg_lstm_cell_bwd_t* p, void* stream) {
       case 1: DLSG_LAUNCH(lstm_cell_bwd_fast<1>, nb, 256, 0, st, *p); break;
       case 2: DLSG_LAUNCH(lstm_cell_bwd_fast<2>, nb, 256, 0, st, *p); break;
       case 3: DLSG_LAUNCH(lstm_cell_bwd_fast<3>, nb, 256, 0, st, *p); break;
-      default: DLSG_LAUNCH(lstm_cell_bwd_fast<4>, nb, 256, 0, st, *p); break;
+      case 4: DLSG_LAUNCH(lstm_cell_bwd_fast<4>, nb, 256, 0, st, *p); break;
+      default: DLSG_LAUNCH(lstm_cell_bwd_fast<16>, nb, 256, 0, st, *p); break;      // 5..16 partials (the BiLSTM's two half-GPU chains: 9)
     }
     return check_launch("lstm_cell_bwd_fast");
   }

@@ -396,7 +396,7 @@ def test_lstm_cell_double_backward(be, H, nulls):
     both('lstm_cell_bwd2', be, args, {}, [7, 8, 9, 10], tol=2e-5)
 
 
-@pytest.mark.parametrize('H,S', [(64, 1), (512, 1), (512, 3), (50, 2)])
+@pytest.mark.parametrize('H,S', [(64, 1), (512, 1), (512, 3), (50, 2), (1024, 9), (64, 16)])
 def test_lstm_cell_second_order_loop_fields(be, H, S):
     """The fields the critic's fused second-order loops use (dlsg.generic._LstmBptt2): cell backward with the injections
     dc_next2 / dgates_add and the dh_total output; cell backward-of-backward with split-K partials added to u and a
