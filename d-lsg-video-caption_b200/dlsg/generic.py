@@ -48,14 +48,16 @@ class input_grads_only:
         _INPUT_GRADS_ONLY = self.old
 
 
+def _param_like(t):
+    """A leaf that requires grad (a parameter) or a view of one."""
+    base = t._base if (t._is_view() and t._base is not None) else t
+    return base.grad_fn is None and base.requires_grad
+
+
 def _want(ctx, i, t):
     if not ctx.needs_input_grad[i]:
         return False
-    if _INPUT_GRADS_ONLY:
-        base = t._base if (t._is_view() and t._base is not None) else t
-        if base.grad_fn is None and base.requires_grad:                # a parameter or a view of one
-            return False
-    return True
+    return not (_INPUT_GRADS_ONLY and _param_like(t))
 
 
 # ----------------------------------------------------------------------------------------------- matmul
@@ -128,6 +130,7 @@ class _LinearB(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, w, bias):
         ctx.save_for_backward(a, w)
+        ctx.bias_is_param = _param_like(bias)
         return la.mm(a, w, memo=True, bias=bias.detach())
 
     @staticmethod
@@ -138,7 +141,7 @@ class _LinearB(torch.autograd.Function):
             da = bmm_nt(dy, w.transpose(-1, -2))
         if _want(ctx, 1, w):
             dw = bmm_nt(dy.transpose(-1, -2), a.transpose(-1, -2))
-        if ctx.needs_input_grad[2] and not _INPUT_GRADS_ONLY:
+        if ctx.needs_input_grad[2] and not (_INPUT_GRADS_ONLY and ctx.bias_is_param):
             db = _ColSum.apply(dy)
         return da, dw, db
 
