@@ -262,3 +262,48 @@ def test_lstm_fused_second_order_equals_stepwise_restatement(prec):
             return torch.stack(out, 1)
         f2, s2 = _grads(ref, [x, w_ih, w_hh, b_ih, b_hh], 5, wrt=(0,))
         _same(res[True][0], f2, 1e-4); _same(res[True][1], s2, 1e-4)
+
+
+def test_input_grads_only_scope_skips_parameter_gradients_only():
+    """generic.input_grads_only(): inside the scope a backward pass computes the gradients of non-leaf tensors (what the WGAN-GP
+    penalty asks for) and skips those of parameters and of views of parameters; the gradient it does return is unchanged."""
+    from dlsg import generic as GN
+    rs = torch.Generator().manual_seed(2)
+    x = torch.randn(6, 16, generator=rs).requires_grad_(True)
+    w = torch.nn.Parameter(torch.randn(8, 16, generator=rs))
+    b1, b2 = torch.nn.Parameter(torch.randn(8, generator=rs)), torch.nn.Parameter(torch.randn(8, generator=rs))
+    be = ops.backend()
+
+    def run(scoped):
+        h = x * 2.0                                                  # a non-leaf input, like the interpolated tokens
+        y = GN.linear(GN.linear(h, w, b1), w[:, :8], b1 + b2)        # parameter, view of a parameter, non-leaf bias
+        l0 = be.launches
+        if scoped:
+            with GN.input_grads_only():
+                g = torch.autograd.grad(y.sum(), h, create_graph=True)[0]
+        else:
+            g = torch.autograd.grad(y.sum(), h, create_graph=True)[0]
+        return g.detach(), be.launches - l0
+    g_all, n_all = run(False)
+    g_in, n_in = run(True)
+    assert torch.equal(g_all, g_in)
+    assert n_in < n_all                                               # the weight-gradient products / bias column sums are gone
+    assert not GN._INPUT_GRADS_ONLY
+
+
+def test_splitk_rows_rule():
+    """linalg.splitk_rows: explicit split-K factors for recurrent products with more than 64 rows (the critic's 192 stacked
+    rows): 1 when K is short or the tiles already fill the GPU, never more than the cell kernels' vector path sums, no empty
+    split; up to 64 rows it is splitk_for."""
+    la.set_precision('bf16')
+    assert la.splitk_rows(192, 512, 2048) == 4                       # data-gradient product of the critic LSTM: 8 tiles, 32 k-blocks
+    assert la.splitk_rows(192, 2048, 512) == 1                       # forward product: 8 k-blocks only
+    assert la.splitk_rows(256, 4096, 2864) == 2                      # greedy decode, query-LSTM gates: 64 tiles
+    assert la.splitk_rows(640, 6144, 4608) == 1                      # beam-5 rows: the tiles alone fill the GPU
+    assert la.splitk_rows(64, 4096, 2864) == la.splitk_for(64, 4096, 2864)
+    for rows, n, k in [(130, 512, 2048), (192, 512, 1100), (100, 1024, 4096)]:
+        s = la.splitk_rows(rows, n, k)
+        kb = (k + 63) // 64
+        assert 1 <= s <= 4 and (s - 1) * ((kb + s - 1) // s) < kb
+    la.set_precision('fp32')
+    assert la.splitk_rows(192, 512, 2048) == 1
