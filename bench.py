@@ -376,6 +376,13 @@ def main(argv=None):
         # user-buffer registration for captured collectives only applies to VMM allocations (not the caching allocator's):
         # switch the attempt off; a collective that cannot complete aborts after 3 minutes instead of hanging
         os.environ.setdefault('NCCL_GRAPH_REGISTER', '0')
+        if not EMUL:
+            # native libraries write to file descriptor 1 (NCCL prints its version banner there): point fd 1 at stderr and keep
+            # Python's own sys.stdout on the original descriptor, so the process's stdout carries the JSON line and nothing else
+            sys.stdout.flush()
+            keep = os.dup(1)
+            os.dup2(2, 1)
+            sys.stdout = os.fdopen(keep, 'w', buffering=1)
         stage('init_process_group(%s) world=%d' % ('gloo' if EMUL else 'nccl', world))
         if EMUL:
             dist.init_process_group('gloo', timeout=datetime.timedelta(seconds=180))
